@@ -1,0 +1,340 @@
+"""Pins the CPU oracle against everything the reference tree offers as a known answer:
+the .rle <-> .npy sample pair, the RNG recipe (finding 9), and independent brute-force restatements."""
+import hashlib
+import json
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, pick_seeds, random_blob_grid
+
+
+def test_rle_fixture_decodes_to_shipped_npy(orc, golden_rle_bytes):
+    meta = json.load(open(os.path.join(GOLDEN, "golden.json")))
+    assert hashlib.sha256(golden_rle_bytes).hexdigest() == meta["rle_sha256"]
+    g = orc.decode_rle(golden_rle_bytes)
+    assert list(g.shape) == meta["dims"] == [128, 110, 128]
+    assert int((g != 0).sum()) == meta["occupied"] == 111152
+    assert set(np.unique(g)) == {0, 1}
+    # docs/decompress/decompress_grid.py:33-37: flip axis 1, pad to max dim, store as uint8
+    ref = np.load(os.path.join(GOLDEN, "AL_12B_grid_128r.npz"))["grid"]
+    mine = np.flip(g.astype(np.uint8), 1)
+    mine = np.pad(mine, [(0, 128 - s) for s in mine.shape])
+    assert hashlib.sha256(mine.tobytes()).hexdigest() == meta["npy_sha256"]
+    assert np.array_equal(mine, ref)
+
+
+def test_rle_encoder_reproduces_reference_bytes(orc, golden_rle_bytes):
+    """exportRLE (RegularGrid.cpp:672-714) restated: re-encoding the decoded fixture gives the fixture byte for byte."""
+    g = orc.decode_rle(golden_rle_bytes)
+    assert orc.encode_rle(g) == golden_rle_bytes
+    assert (len(golden_rle_bytes) - 12) // 6 == 42977
+
+
+def test_rle_matches_python_decoder_restated(orc):
+    g = random_blob_grid((12, 9, 16), 3) * 7
+    data = orc.encode_rle(g)
+    w, h, d = struct.unpack("<III", data[:12])
+    flat = np.zeros(w * h * d, dtype=np.uint16)
+    off = 0
+    for p in range(12, len(data), 6):  # decompress_grid.py:25-32
+        v, n = struct.unpack("<HI", data[p : p + 6])
+        flat[off : off + n] = v
+        off += n
+    assert off == flat.size and np.array_equal(flat.reshape(w, h, d), g)
+
+
+def test_bing_squared_layout(orc):
+    g = (random_blob_grid((8, 4, 12), 5) * 3).astype(np.uint16)
+    b = orc.encode_bing_squared(g)
+    M = 12
+    assert struct.unpack("<III", b[:12]) == (M, M, M)
+    cube = np.frombuffer(b[12:], dtype=np.uint16).reshape(M, M, M)
+    exp = np.zeros((M, M, M), np.uint16)
+    exp[2:10, 4:8, 0:12] = g  # start = (M - dims) / 2, RegularGrid.cpp:643
+    assert np.array_equal(cube, exp)
+
+
+def test_rng_recipe_matches_libstdcxx_and_survey_draws(orc):
+    assert orc.selfcheck_rng(80, 200000) == 0
+    assert orc.selfcheck_rng(12345, 200000) == 0
+    r = orc.Rng(80)
+    got = [r.uniform() for _ in range(8)]
+    want = [0.521915734, 0.676156342, 0.699406385, 0.52944237, 0.26986897, 0.155109122, 0.674481869, 0.797937274]
+    assert np.allclose(np.float32(got), np.float32(want), rtol=0, atol=6e-8)
+    # mt19937 known answer: 10000th draw of a default-seeded (5489) engine is 4123659995 (ISO C++ [rand.predef])
+    r = orc.Rng(5489)
+    for _ in range(9999):
+        r.raw()
+    assert r.raw() == 4123659995
+
+
+def test_float_decode_mismatches_only_above_2_24(orc):
+    for dims in [(128, 128, 128), (128, 110, 128), (200, 200, 200), (256, 256, 256)]:
+        n = dims[0] * dims[1] * dims[2]
+        rs = np.random.RandomState(1).randint(0, n, size=2000)
+        for i in list(rs) + [n - 1, n - 2]:
+            assert orc.decode_position(int(i), dims, 0) == orc.decode_position(int(i), dims, 1)
+    # SURVEY finding 6: first float-decode error at 512^3
+    assert orc.decode_position(17039359, (512, 512, 512), 0) == (64, 511, 511)
+    assert orc.decode_position(17039359, (512, 512, 512), 1) == (65, 511, 511)
+
+
+def test_dims_rule(orc):
+    assert orc.dims_rule([-0.5, -0.5, -0.5], [0.5, 0.5, 0.5], 128) == (128, 128, 128)
+    assert orc.dims_rule([0, 0, 0], [1.0, 0.86, 1.0], 128) == (128, 112, 128)  # floor(110.08)=110 -> 112
+    assert orc.dims_rule([0, 0, 0], [0.3, 1.0, 0.3], 256) == (76, 256, 76)    # floor(76.8)=76 (already x4)
+
+
+def _brute_naive(grid, seeds, dfunc):
+    out = grid.copy()
+    X, Y, Z = grid.shape
+    xs, ys, zs = np.meshgrid(np.arange(X), np.arange(Y), np.arange(Z), indexing="ij")
+    best = np.full(grid.shape, np.inf, dtype=np.float32)
+    lab = grid.copy()
+    for s in seeds:
+        dx, dy, dz = (xs - int(s[0])).astype(np.float32), (ys - int(s[1])).astype(np.float32), (zs - int(s[2])).astype(np.float32)
+        if dfunc == 0:
+            d = np.sqrt(dx * dx + dy * dy + dz * dz, dtype=np.float32)
+        elif dfunc == 1:
+            d = np.abs(dx) + np.abs(dy) + np.abs(dz)
+        else:
+            d = np.maximum(np.abs(dx), np.maximum(np.abs(dy), np.abs(dz)))
+        upd = d < best
+        best[upd] = d[upd]
+        lab[upd] = s[3]
+    out[grid != 0] = lab[grid != 0]
+    return out
+
+
+@pytest.mark.parametrize("dfunc", [0, 1, 2])
+def test_naive_vs_bruteforce(orc, dfunc):
+    g = random_blob_grid((24, 20, 28), 7)
+    seeds = pick_seeds(g, 9, 11)
+    want = _brute_naive(g, seeds, dfunc)
+    got = orc.naive(g.copy(), seeds, dfunc)
+    assert np.array_equal(got, want)
+
+
+def _py_bfs(grid, seeds, nb):
+    """level-synchronous min-claim BFS in plain python (tiny grids only)."""
+    X, Y, Z = grid.shape
+    g = (grid != 0).astype(np.int64)
+    lab = np.where(g != 0, 1, 0).astype(np.int64)
+    order = {}
+    for i, s in enumerate(seeds):
+        order[(int(s[0]), int(s[1]), int(s[2]))] = i
+    front = {}
+    for c, i in order.items():
+        lab[c] = int(seeds[i][3])
+        front[c] = i
+    while front:
+        cand = {}
+        for (x, y, z), o in front.items():
+            for dx, dy, dz in nb:
+                n = (x + dx, y + dy, z + dz)
+                if not (0 <= n[0] < X and 0 <= n[1] < Y and 0 <= n[2] < Z):
+                    continue
+                if lab[n] != 1:
+                    continue
+                cand[n] = min(cand.get(n, 1 << 30), o)
+        for n, o in cand.items():
+            lab[n] = int(seeds[o][3])
+        front = cand
+    return lab.astype(np.uint16)
+
+
+NB6 = [(1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)]
+NB26 = [(a, b, c) for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1) if (a, b, c) != (0, 0, 0)]
+
+
+@pytest.mark.parametrize("dfunc,nb", [(1, NB6), (2, NB26), (0, NB26)])
+def test_flood_levels_dijkstra_python_agree(orc, dfunc, nb):
+    for trial in range(4):
+        g = random_blob_grid((14, 12, 13), 100 + trial, fill=0.5, smooth=1)
+        seeds = pick_seeds(g, 5, trial)
+        a, sa = orc.flood(g.copy(), seeds, dfunc, id_bits=8, algo=0)
+        b, sb = orc.flood(g.copy(), seeds, dfunc, id_bits=8, algo=1)
+        c = _py_bfs(g, seeds, nb)
+        assert np.array_equal(a, b)
+        assert np.array_equal(a, c)
+        assert sa.rounds == 1 and sa.freed_voxels == 0
+        # unreachable occupied cells stay FREE, empties stay EMPTY
+        assert np.array_equal(a == 0, g == 0)
+        a15, _ = orc.flood(g.copy(), seeds, dfunc, id_bits=15, algo=0)
+        assert np.array_equal(a15, a)
+
+
+def _literal_prefix_merge(words, nb):
+    """floodFracturer-comp.glsl:49-63 taken literally: adjacent cells with the same fragment id and different
+    prefixes converge to the lower prefix; iterate to the fixed point (tiny grids only)."""
+    w = words.astype(np.int64).copy()
+    X, Y, Z = w.shape
+    changed = True
+    while changed:
+        changed = False
+        for x in range(X):
+            for y in range(Y):
+                for z in range(Z):
+                    v = w[x, y, z]
+                    if v <= 1:
+                        continue
+                    for dx, dy, dz in nb:
+                        n = (x + dx, y + dy, z + dz)
+                        if not (0 <= n[0] < X and 0 <= n[1] < Y and 0 <= n[2] < Z):
+                            continue
+                        u = w[n]
+                        if u > 1 and (u & 0xFF) == (v & 0xFF) and (u >> 8) < (w[x, y, z] >> 8):
+                            w[x, y, z] = u
+                            changed = True
+    return w
+
+
+@pytest.mark.parametrize("dfunc,nb", [(1, NB6), (2, NB26)])
+def test_flood_with_extra_seeds_against_literal_rounds(orc, dfunc, nb):
+    """F3: rounds of {flood, prefix merge, per-fragment min prefix, free the rest, re-flood} restated literally in python."""
+    for trial in range(3):
+        g = random_blob_grid((13, 11, 12), 40 + trial, fill=0.5, smooth=1)
+        rng = orc.Rng(80 + trial)
+        seeds = orc.make_seeds(rng, g, 3, 6, merge_dfunc=0)
+        assert len(seeds) == 3 + 3 + 6
+        got, st = orc.flood(g.copy(), seeds, dfunc, id_bits=8, algo=0)
+        # literal restatement
+        lab = _py_bfs(g, seeds, nb).astype(np.int64)
+        rounds = 1
+        while True:
+            lab = _literal_prefix_merge(lab, nb)
+            minp = {}
+            for v in lab[lab > 1]:
+                minp[v & 0xFF] = min(minp.get(v & 0xFF, 1 << 30), v >> 8)
+            kill = np.zeros(lab.shape, bool)
+            for idx in np.argwhere(lab > 1):
+                v = lab[tuple(idx)]
+                if (v >> 8) != minp[v & 0xFF]:
+                    kill[tuple(idx)] = True
+            if not kill.any():
+                break
+            lab[kill] = 1
+            # re-flood from all labelled cells, order = lowest seed index carrying the word
+            order_of_word = {}
+            for i, s in enumerate(seeds):
+                order_of_word.setdefault(int(s[3]), i)
+            front = {tuple(i): order_of_word[int(lab[tuple(i)])] for i in np.argwhere(lab > 1)}
+            while front:
+                cand = {}
+                for (x, y, z), o in front.items():
+                    for dx, dy, dz in nb:
+                        n = (x + dx, y + dy, z + dz)
+                        if not (0 <= n[0] < lab.shape[0] and 0 <= n[1] < lab.shape[1] and 0 <= n[2] < lab.shape[2]):
+                            continue
+                        if lab[n] != 1:
+                            continue
+                        cand[n] = min(cand.get(n, 1 << 30), o)
+                for n, o in cand.items():
+                    lab[n] = int(seeds[o][3])
+                front = cand
+            rounds += 1
+        want = (lab & 0xFF).astype(np.uint16)
+        assert np.array_equal(got, want)
+        assert st.rounds == rounds
+        assert set(np.unique(got)) <= {0, 1, 2, 3, 4}
+
+
+def test_seed_uniform_properties(orc, vessel_grid):
+    r = orc.Rng(80)
+    seeds, attempts = orc.seed_uniform(r, vessel_grid, 8, location=orc.OUTER)
+    assert attempts >= 8
+    assert list(seeds[:, 3]) == list(range(2, 10))
+    xyz = [tuple(s[:3]) for s in seeds]
+    assert xyz == sorted(xyz) and len(set(xyz)) == 8
+    for x, y, z in xyz:
+        assert vessel_grid[x, y, z] != 0
+        box = vessel_grid[max(x - 1, 0) : x + 2, max(y - 1, 0) : y + 2, max(z - 1, 0) : z + 2]
+        assert (box == 0).any()  # OUTER
+    # the draws consumed are exactly 3 per attempt
+    r2 = orc.Rng(80)
+    for _ in range(3 * attempts):
+        r2.raw()
+    assert r.raw() == r2.raw()
+    with pytest.raises(orc.OracleError):
+        orc.seed_uniform(orc.Rng(1), np.zeros((8, 8, 8), np.uint16), 1)
+
+
+def test_merge_seeds_prefixes(orc):
+    frags = np.array([[1, 1, 1, 2], [10, 10, 10, 3]], np.uint32)
+    seeds = np.array([[1, 1, 1, 2], [10, 10, 10, 3], [2, 2, 2, 9], [9, 9, 9, 9], [3, 3, 3, 9]], np.uint32)
+    out = orc.merge_seeds(frags, seeds, 0)
+    assert list(out[:, 3]) == [2 | 1 << 8, 3 | 1 << 8, 2 | 2 << 8, 3 | 2 << 8, 2 | 3 << 8]
+
+
+def test_remove_isolated_regions_cpu(orc):
+    g = np.zeros((6, 6, 6), np.uint16)
+    g[0:3] = 2
+    g[3:6] = 3
+    g[5, 5, 5] = 2  # an island of label 2 inside 3's half
+    seeds = np.array([[0, 0, 0, 2], [4, 0, 0, 3]], np.uint32)
+    out = orc.remove_isolated_regions_cpu(g.copy(), seeds)
+    assert out[5, 5, 5] == 0 and (out[0:3] == 2).all() and (out[3:6] == 3).sum() == 3 * 36 - 1
+
+
+def test_detect_boundaries_and_undo(orc):
+    g = np.zeros((6, 6, 6), np.uint16)
+    g[0:3] = 2
+    g[3:6] = 3
+    g[0, 0, 0] = 1
+    b = orc.detect_boundaries(g.copy(), 1)
+    assert (b[2] == (2 | 0x8000)).all() and (b[3] == (3 | 0x8000)).all()
+    assert (b[1] == 2).all() and (b[4] == 3).all() and b[0, 0, 0] == 1
+    # second application without undoMask: tagged cells stay tagged, and tag their untagged like-labelled neighbours? no:
+    b2 = orc.detect_boundaries(b.copy(), 1)
+    assert np.array_equal(b2 & 0x8000, b & 0x8000) or ((b2 & 0x8000) >= (b & 0x8000)).all()
+    assert np.array_equal(orc.undo_mask(b.copy(), 15, False), g)
+    assert np.array_equal(orc.undo_mask(np.array([0x0302, 0x0103, 1, 0], np.uint16), 8, True), np.array([2, 3, 1, 0], np.uint16))
+
+
+def test_erode_mask_and_activation(orc):
+    m, act = orc.erode_mask(orc.ELLIPSE, 3)
+    assert m.sum() == 7 and abs(act - 7 / 27) < 1e-7
+    m, act = orc.erode_mask(orc.CROSS, 3)
+    assert m.sum() == 7 and abs(act - 1 / 3) < 1e-7
+    m, act = orc.erode_mask(orc.SQUARE, 4)  # even sizes are bumped to odd
+    assert m.shape == (5, 5, 5) and act == 1.0
+
+
+def test_erode_is_deterministic_and_only_removes(orc, vessel_grid):
+    seeds, _ = orc.seed_uniform(orc.Rng(80), vessel_grid, 8)
+    g = orc.naive(vessel_grid.copy(), seeds, 0)
+    noise = orc.Rng(80).fill_noise(100000)
+    a = orc.erode(g.copy(), noise)
+    b = orc.erode(g.copy(), noise)
+    assert np.array_equal(a, b)
+    kept = a != 0
+    assert (g[kept] == (a[kept] & 0x7FFF)).all() and kept.sum() < (g != 0).sum()
+
+
+def test_count_values(orc):
+    g = np.array([0, 1, 2, 2, 3 | 0x8000, 3, 1, 0], np.uint16)
+    counts, occ = orc.count_values(g)
+    assert occ == 4 and counts[2] == 2 and counts[3] == 2 and counts.sum() == 4
+
+
+def test_sat_predicate_basics(orc):
+    tri = ([0.1, 0.1, 0.5], [0.9, 0.1, 0.5], [0.1, 0.9, 0.5])
+    assert orc.tri_box_intersect(*tri, [0, 0, 0], [1, 1, 1])
+    assert not orc.tri_box_intersect(*tri, [0, 0, 0.6], [1, 1, 1])
+    assert orc.tri_box_intersect(*tri, [0, 0, 0.5], [1, 1, 1])  # touching counts (planeBoxOverlap >= 0)
+    assert not orc.tri_box_intersect(*tri, [0.6, 0.6, 0], [1, 1, 1])  # beyond the hypotenuse
+    # a big triangle that cuts a box corner off
+    assert orc.tri_box_intersect([2, -1, 0], [-1, 2, 0], [-1, -1, 3], [0, 0, 0], [1, 1, 1])
+
+
+def test_sat_voxelize_plane(orc):
+    verts = np.array([[-0.4, -0.4, 0.013], [0.4, -0.4, 0.013], [0.4, 0.4, 0.013], [-0.4, 0.4, 0.013]], np.float32)
+    faces = np.array([[0, 1, 2], [0, 2, 3]], np.uint32)
+    g, margin = orc.voxelize_sat(verts, faces, [-0.5] * 3, [0.5] * 3, (16, 16, 16), want_margin=True)
+    assert g[:, :, 8].sum() > 100 and g[:, :, :8].sum() == 0 and g[:, :, 9:].sum() == 0
+    g2 = orc.voxelize_sat(verts, faces, [-0.5] * 3, [0.5] * 3, (16, 16, 16))
+    assert np.array_equal(g, g2)
+    assert (margin[g == 1] < 1e30).all()
