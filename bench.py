@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py — measures the hot path on B200 (contract: see DESIGN.md §measurement).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the CPU oracle on the host cores (bounded sample)
+
+Workload (N=1 default) = BASELINE.json configs[2], the configuration the metric "Gvoxels/s fragmented at 512^3" is quoted on:
+512^3 grid, NAIVE EUCLIDEAN nearest-seed fragmentation with 64 seeds, boundary noise (erode ELLIPSE 3, 3 iterations, p .5,
+thr .5), connected-to-seed small-fragment removal and the per-fragment histogram.  The grid is the DENSE variant (every cell
+occupied: worst case, algorithmic bytes 4N for the naive kernel); the sparse synthetic-vessel variant is reported alongside.
+A step = one pass of that pipeline over one grid; with N GPUs every rank runs its own grid (weak scaling, no collective on
+the data path).  Inputs (256 MiB) are larger than L2 (126 MB), so no explicit L2 flush is needed between iterations.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def load_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ workload definition
+CFG3 = dict(nseeds=64, dfunc=0, erosion=(1, 3, 3, 0.5, 0.5), rng_seed=80, nnoise=1000000)
+
+
+def synth_seeds_dense(n: int, nseeds: int, rng_raw):
+    """Seeder::uniform restated for a fully occupied grid with location BOTH (a dense grid has no OUTER cell): rejection only
+    on duplicates, three draws per attempt, std::set order, labels 2.. — identical on the CUDA and the oracle side because
+    both receive this array."""
+    seen = set()
+    while len(seen) < nseeds:
+        x, y, z = (int(np.float32(0.0) + np.float32(n - 1) * rng_raw()) for _ in range(3))
+        seen.add((x, y, z))
+    pts = sorted(seen)
+    return np.array([[x, y, z, 2 + i] for i, (x, y, z) in enumerate(pts)], dtype=np.uint32)
+
+
+def rng_uniform_stream(seed):
+    """The reference float recipe on numpy's MT19937 (init_genrand seeding == std::mt19937(seed))."""
+    rs = np.random.RandomState(seed)
+
+    def draw():
+        raw = int(rs.randint(0, 2**32, dtype=np.uint64))
+        u = np.float32(raw) * np.float32(2.3283064365386963e-10)
+        return np.float32(0.99999994) if u >= np.float32(1.0) else u
+
+    return draw
+
+
+def noise_table(seed, n):
+    rs = np.random.RandomState(seed)
+    raw = rs.randint(0, 2**32, size=n, dtype=np.uint64).astype(np.float32)
+    u = raw * np.float32(2.3283064365386963e-10)
+    u[u >= 1.0] = np.float32(0.99999994)
+    return u.astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------ CUDA arm
+def run_cuda(args):
+    import torch
+
+    import voxelfragmentml_b200 as vf
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    ctx = vf.Context(local_rank)
+    n = args.size
+    N = n**3
+    dims = (n, n, n)
+    peak, peak_src = load_peak()
+
+    seeds = synth_seeds_dense(n, CFG3["nseeds"], rng_uniform_stream(CFG3["rng_seed"] + rank))
+    noise = noise_table(CFG3["rng_seed"] + 1000 + rank, CFG3["nnoise"])
+    pristine = torch.ones(N, dtype=torch.int16, device="cuda")  # dense variant: every cell FREE (1)
+    work = torch.empty_like(pristine)
+    grid = vf.RegularGrid(ctx, dims, device_ptr=work.data_ptr())
+    ctx.reserve(dims)
+    naive = vf.NaiveFracturer()
+    naive.setDistanceFunction(CFG3["dfunc"])
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    stages_run = []
+
+    def restore():
+        with torch.cuda.stream(stream):
+            work.copy_(pristine)
+
+    def pipeline(record=None):
+        """one step of cfg3 on the device-resident grid; returns the histogram when the stage exists"""
+        t = {}
+
+        def stage(name, fn):
+            try:
+                if record is not None:
+                    ctx.timer_start()
+                fn()
+                if record is not None:
+                    t[name] = ctx.timer_stop()
+                if name not in stages_run:
+                    stages_run.append(name)
+            except vf.VoxFragError as e:
+                if e.status != 7:  # VF_ERR_UNSUPPORTED: stage not built yet
+                    raise
+
+        stage("naive", lambda: naive.build(grid, seeds))
+        et, es, ei, ep, eth = CFG3["erosion"]
+        stage("erode", lambda: grid.erode(et, es, ei, ep, eth, noise=noise))
+        stage("remove_isolated", lambda: vf.NaiveFracturer.removeIsolatedRegions(grid, seeds))
+        stage("histogram", lambda: grid.countValues())
+        if record is not None:
+            record.append(t)
+
+    # ---- warm-up, then K timed steps (CUDA events on the context's stream; the input restore is outside the events)
+    for _ in range(args.warmup):
+        restore()
+        pipeline()
+    ctx.synchronize()
+    launches0 = ctx.kernel_launches
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    step_ms = []
+    for _ in range(args.steps):
+        restore()
+        ctx.synchronize()
+        ctx.timer_start()
+        pipeline()
+        step_ms.append(ctx.timer_stop())
+    torch.cuda.synchronize()
+    launches = ctx.kernel_launches - launches0
+    total_ms = float(sum(step_ms))
+    if world > 1:
+        tt = torch.tensor([total_ms], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+        dist.barrier()
+
+    # ---- per-stage breakdown (separate pass: event pairs per stage add sync points, so they are not part of the timed steps)
+    breakdown = []
+    for _ in range(3):
+        restore()
+        ctx.synchronize()
+        pipeline(record=breakdown)
+    stage_ms = {k: float(np.median([b[k] for b in breakdown if k in b])) for k in stages_run}
+
+    # ---- roofline of the dominant kernel, timed alone with CUDA events on its launch stream
+    naive_ms = []
+    for _ in range(max(10, args.steps)):
+        restore()
+        ctx.synchronize()
+        ctx.timer_start()
+        naive.build(grid, seeds)
+        naive_ms.append(ctx.timer_stop())
+    clocks = sampler.stop()
+    naive_t = float(np.median(naive_ms)) * 1e-3
+    algo_bytes = 4.0 * N  # dense: read 2N + write 2N
+    achieved = algo_bytes / naive_t / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "naive_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(str(n))
+        except Exception:
+            traffic = None
+
+    # ---- end to end through the public API with HOST buffers: pinned upload -> pipeline -> download, every step
+    h_in = torch.ones(N, dtype=torch.int16).pin_memory()
+    h_out = torch.empty(N, dtype=torch.int16).pin_memory()
+    e2e_steps = max(2, min(args.steps, 5))
+    for it in range(1 + e2e_steps):
+        if it == 1:
+            ctx.synchronize()
+            t0 = time.perf_counter()
+        grid.upload_async(h_in)
+        pipeline()
+        grid.download_async(h_out)
+        ctx.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        tt = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+
+    out = {
+        "metric": "Gvoxels/s fragmented at 512^3", "value": world * N * args.steps / (total_ms * 1e-3) / 1e9, "unit": "Gvoxels/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u16 labels / int32 distance keys", "data": "synthetic",
+        "config": {"workload": f"cfg3-dense: {n}^3 all-occupied grid, NAIVE EUCLIDEAN {CFG3['nseeds']} seeds + erode(ELLIPSE,3,3it,p.5,thr.5)"
+                               " + connected-to-seed cleanup + histogram", "stages": stages_run, "grid": list(dims),
+                   "l2": "inputs (256 MiB at 512^3) larger than L2 (126 MB); no explicit flush", "parallelism": f"replicas x{world} (one grid per GPU)"},
+        "stage_ms": stage_ms,
+        "roofline": {"kernel": "naive_brick_kernel<EUCLIDEAN,8>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": algo_bytes,
+                     "kernel_ms": naive_t * 1e3},
+        "e2e": {"value": world * N / e2e_s / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": 2 * N + seeds.nbytes + noise.nbytes,
+                "d2h_bytes_per_step": 2 * N + 4 * 32768, "ms_per_step": e2e_s * 1e3},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if rank == 0 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args.cpu_size, stages_run)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms (oracle)
+def oracle_pipeline(orc, grid, seeds, noise, stages):
+    if "naive" in stages:
+        orc.naive(grid, seeds, CFG3["dfunc"])
+    if "erode" in stages:
+        et, es, ei, ep, eth = CFG3["erosion"]
+        orc.erode(grid, noise, et, es, ei, ep, eth)
+    if "remove_isolated" in stages:
+        orc.remove_isolated_regions_cpu(grid, seeds)
+    if "histogram" in stages:
+        orc.count_values(grid)
+
+
+def cpu_baseline(n, stages, steps=1):
+    import oracle as orc
+
+    seeds = synth_seeds_dense(n, CFG3["nseeds"], rng_uniform_stream(CFG3["rng_seed"]))
+    noise = noise_table(CFG3["rng_seed"] + 1000, CFG3["nnoise"])
+    best = None
+    for _ in range(steps):
+        g = np.ones((n, n, n), np.uint16)
+        t0 = time.perf_counter()
+        oracle_pipeline(orc, g, seeds, noise, stages)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": n**3 / best / 1e9, "unit": "Gvoxels/s", "cores": orc.num_threads(), "kind": "port",
+            "sample": f"{n}^3 dense grid, same pipeline and seed count (stages {stages}), {best:.2f} s", "seconds": best}
+
+
+ALL_STAGES = ["naive", "erode", "remove_isolated", "histogram"]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle as orc
+
+    n = args.cpu_size
+    seeds = synth_seeds_dense(n, CFG3["nseeds"], rng_uniform_stream(CFG3["rng_seed"]))
+    noise = noise_table(CFG3["rng_seed"] + 1000, CFG3["nnoise"])
+    for _ in range(min(args.warmup, 1)):
+        oracle_pipeline(orc, np.ones((n, n, n), np.uint16), seeds, noise, ALL_STAGES)
+    times = []
+    for _ in range(args.steps):
+        g = np.ones((n, n, n), np.uint16)
+        t0 = time.perf_counter()
+        oracle_pipeline(orc, g, seeds, noise, ALL_STAGES)
+        times.append(time.perf_counter() - t0)
+    total = float(sum(times))
+    v = n**3 * args.steps / total / 1e9
+    print(json.dumps({
+        "impl": "reference", "metric": "Gvoxels/s fragmented at 512^3", "value": v, "unit": "Gvoxels/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u16 labels / f32 distances", "data": "synthetic",
+        "config": {"workload": f"cfg3-dense pipeline on a bounded {n}^3 sample (the reference has no native CPU path; this is the CPU oracle, "
+                               "a restatement of NaiveFracturer::buildCPU + erode + removeIsolatedRegionsCPU + countValues)", "stages": ALL_STAGES,
+                   "grid": [n, n, n]},
+        "cpu_baseline": {"value": v, "unit": "Gvoxels/s", "cores": orc.num_threads(), "kind": "port", "sample": f"{n}^3 dense grid x {args.steps} steps"},
+        "e2e": {"value": v, "unit": "Gvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--cpu-size", type=int, default=192)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

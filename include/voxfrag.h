@@ -1,0 +1,198 @@
+/*
+ * voxfrag.h — C ABI of libvoxfrag.so: the B200-native (sm_100a) implementation of VoxelFragmentML's
+ * hot path  mesh -> uint16 voxel grid -> seeded fragmentation -> small-fragment cleanup.
+ *
+ * This is the drop-in boundary.  Every entry point names the reference interface it
+ * replaces.  Shorthand: SRC/ = MeshFragments/Source/ of AlfonsoLRz/VoxelFragmentML.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross this boundary; no exception crosses it.
+ *   - every call returns a vf_status (0 = ok); vf_last_error() gives a thread-local message.
+ *   - a vf_ctx owns one CUDA device + one stream + scratch memory.  Calls on one context are issued on its
+ *     stream and must be serialised by the caller (mirrors the reference's single-GL-thread rule,
+ *     SRC/Graphics/Core/ComputeShader.cpp); distinct contexts may be driven from distinct host threads.
+ *   - grids are device resident; host copies happen only in vf_grid_upload / vf_grid_download / vf_export
+ *     (the reference's updateSSBO / updateGrid, SRC/DataStructures/RegularGrid.cpp:505-514).
+ *   - label word layout is the reference's (SRC/DataStructures/RegularGrid.h:12-27): uint16 per voxel,
+ *     0 = EMPTY, 1 = FREE, >= 2 fragment id, bit 15 = boundary mask, bits 8..14 = sub-seed prefix while flooding.
+ *     Linear index = x*Y*Z + y*Z + z (z fastest; RegularGrid.cpp:839-842).
+ *   - seeds are uint32[n][4] = {x, y, z, label} exactly like std::vector<glm::uvec4> (SRC/Fracturer/Fracturer.h:35).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns VF_ERR_CUDA.
+ */
+#ifndef VOXFRAG_H
+#define VOXFRAG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VF_VOXEL_EMPTY 0u      /* RegularGrid.h:12 */
+#define VF_VOXEL_FREE 1u       /* RegularGrid.h:13 */
+#define VF_MASK_POSITION 15u   /* RegularGrid.h:18 */
+#define VF_ID_POSITION 8u      /* SRC/Fracturer/Seeder.h:12 */
+#define VF_HISTOGRAM_BINS 32768u
+
+typedef enum vf_status {
+    VF_OK = 0,
+    VF_ERR_INVALID_ARGUMENT = 1,
+    VF_ERR_SEEDER_EXHAUSTED = 2,   /* Seeder::SeederSearchError, SRC/Fracturer/Seeder.cpp:173-174 */
+    VF_ERR_INVALID_DISTANCE = 3,   /* "Invalid distance function", SRC/Graphics/Application/CADScene.cpp:665 */
+    VF_ERR_CAPACITY = 4,           /* label / distance / seed-count capacity exceeded (FloodFracturer::StackOverflowError's role) */
+    VF_ERR_CUDA = 5,
+    VF_ERR_IO = 6,
+    VF_ERR_UNSUPPORTED = 7
+} vf_status;
+
+/* SRC/Fracturer/Fracturer.h:10-14 == FractureParameters::DistanceFunction (FractureParameters.h:20) */
+typedef enum { VF_EUCLIDEAN = 0, VF_MANHATTAN = 1, VF_CHEBYSHEV = 2 } vf_distance;
+/* FractureParameters.h:17 */
+typedef enum { VF_NAIVE = 0, VF_FLOOD = 1, VF_VORONOI = 2 } vf_algorithm;
+/* FractureParameters.h:23 */
+typedef enum { VF_STD_UNIFORM = 0, VF_HALTON = 1, VF_BOOST_NORMAL_DISTRIBUTION = 2 } vf_random_type;
+/* FractureParameters.h:26 */
+typedef enum { VF_SQUARE = 0, VF_ELLIPSE = 1, VF_CROSS = 2 } vf_erosion_type;
+/* FractureParameters.h:29 */
+typedef enum { VF_VON_NEUMANN = 0, VF_MOORE = 1 } vf_neighbourhood;
+/* FractureParameters.h:35 */
+typedef enum { VF_RLE = 0, VF_QUADSTACK = 1, VF_VOX = 2, VF_UNCOMPRESSED_BINARY = 3 } vf_export_grid;
+/* SRC/Fracturer/Seeder.h:24 */
+typedef enum { VF_INNER = 0, VF_OUTER = 1, VF_BOTH = 2 } vf_seed_location;
+
+/* The unchanged fragmentation-parameter surface: same field names (minus the leading underscore), same
+ * enumerator values and same defaults (vf_params_default) as struct FractureParameters
+ * (SRC/Graphics/Core/FractureParameters.h:43-145).  Rendering / mesh-export fields are not on this path. */
+typedef struct vf_params {
+    int32_t biasFocus;                   /* :43  (nearSeeds only)            default 5   */
+    int32_t biasSeeds;                   /* :44                              default 32  */
+    int32_t clampVoxelMetricUnit;        /* :46                              default 200 */
+    int32_t erode;                       /* :47  bool                        default 0   */
+    int32_t erosionConvolution;          /* :48  vf_erosion_type             default ELLIPSE */
+    int32_t erosionIterations;           /* :49                              default 3   */
+    float   erosionProbability;          /* :50                              default .5  */
+    int32_t erosionSize;                 /* :51                              default 3   */
+    float   erosionThreshold;            /* :52                              default .5  */
+    int32_t fractureAlgorithm;           /* :53  vf_algorithm                default FLOOD */
+    int32_t distanceFunction;            /* :54  vf_distance                 default CHEBYSHEV */
+    int32_t launchGPU;                   /* :55  kept for layout parity; the CUDA path always runs */
+    int32_t mergeSeedsDistanceFunction;  /* :57                              default EUCLIDEAN */
+    int32_t neighbourhoodType;           /* :59                              default VON_NEUMANN (unused by FloodFracturer::build, which keys on the distance function, FloodFracturer.cpp:114) */
+    int32_t numExtraSeeds;               /* :61                              default 16  */
+    int32_t numImpacts;                  /* :62                              default 0   */
+    int32_t numSeeds;                    /* :63                              default 8   */
+    int32_t removeIsolatedRegions;       /* :65  bool                        default 1   */
+    int32_t seed;                        /* :66                              default 80  */
+    int32_t seedingRandom;               /* :67  vf_random_type              default STD_UNIFORM */
+    int32_t voxelPerMetricUnit;          /* :70                              default 20  */
+    int32_t voxelizationSize[3];         /* :71                              default 128^3 */
+    int32_t exportGridExtension;         /* :79  vf_export_grid              default VOX */
+    /* -- extensions (not in the reference; 0 = reference behaviour) -- */
+    int32_t floodIdBits;                 /* 0/8: fragId|prefix<<8 words + disjoint rounds; 15: ids up to 32767, no prefixes (SURVEY finding 7) */
+    int32_t erodeBoundaryMode;           /* 0: erodeGrid-comp.glsl:31 as written; 1: test bit 15 (SURVEY finding 8) */
+} vf_params;
+
+typedef struct vf_flood_stats {
+    uint32_t tile_rounds;    /* global relaxation rounds (tile worklist generations), summed over flood phases */
+    uint32_t tile_visits;    /* tiles processed, summed */
+    uint32_t disjoint_rounds;/* outer `while (numDisjointVoxels != 0)` iterations, FloodFracturer.cpp:135 */
+    uint32_t freed_voxels;   /* voxels returned to FREE by the disjoint step, summed */
+    uint32_t max_dist;       /* largest geodesic distance reached in phase 1 */
+} vf_flood_stats;
+
+typedef struct vf_ctx vf_ctx;
+typedef struct vf_grid vf_grid;
+
+/* ------------------------------------------------------------------ library / context */
+const char* vf_last_error(void);
+const char* vf_version(void);
+int vf_device_count(void);
+void vf_params_default(vf_params* p);                                   /* FractureParameters::FractureParameters(), FractureParameters.h:91-145 */
+
+vf_status vf_ctx_create(int device, vf_ctx** out);                       /* replaces the GL context + ShaderList singletons */
+vf_status vf_ctx_create_on_stream(int device, void* cuda_stream, vf_ctx** out); /* borrow an existing cudaStream_t (e.g. torch's current stream) */
+void      vf_ctx_destroy(vf_ctx* ctx);
+vf_status vf_ctx_reserve(vf_ctx* ctx, uint32_t X, uint32_t Y, uint32_t Z); /* Fracturer::prepareSSBOs / init, Fracturer.h:43-48; FloodFracturer.cpp:47-59 */
+vf_status vf_ctx_synchronize(vf_ctx* ctx);
+void*     vf_ctx_stream(vf_ctx* ctx);                                    /* the cudaStream_t every call of this context is issued on */
+uint64_t  vf_ctx_kernel_launches(vf_ctx* ctx);                           /* kernels launched by this context so far (bench "gpu_launches") */
+/* CUDA-event timing on the context's stream (ResourceTracker's role, SRC/Utilities/ResourceTracker.cpp:58-72) */
+vf_status vf_ctx_timer_start(vf_ctx* ctx);
+vf_status vf_ctx_timer_stop(vf_ctx* ctx, float* elapsed_ms);             /* synchronises on the stop event */
+
+/* ------------------------------------------------------------------ RNG (process-global in the reference, per context here) */
+vf_status vf_rng_seed(vf_ctx* ctx, uint32_t seed);                       /* RandomUtilities::initSeed, SRC/Utilities/RandomUtilities.h:86-89; CADScene.cpp:36-37 */
+float     vf_rng_uniform(vf_ctx* ctx);                                   /* RandomUtilities::getUniformRandom, :103-106 (libstdc++ float recipe, SURVEY finding 9) */
+uint32_t  vf_rng_raw(vf_ctx* ctx);
+vf_status vf_fill_noise(vf_ctx* ctx, float* noise, uint32_t n);          /* RegularGrid::fillNoiseBuffer, RegularGrid.cpp:238-244 (serial draw order) */
+
+/* ------------------------------------------------------------------ grid (class RegularGrid) */
+vf_status vf_grid_create(vf_ctx* ctx, uint32_t X, uint32_t Y, uint32_t Z, vf_grid** out);  /* RegularGrid(ivec3), RegularGrid.cpp:28-32 */
+vf_status vf_grid_wrap(vf_ctx* ctx, void* device_u16, uint32_t X, uint32_t Y, uint32_t Z, vf_grid** out); /* borrow caller-owned device memory (16-byte aligned) */
+void      vf_grid_destroy(vf_grid* g);
+vf_status vf_grid_set_aabb(vf_grid* g, const float aabb_min[3], const float aabb_max[3], uint32_t X, uint32_t Y, uint32_t Z); /* RegularGrid::setAABB + cleanGrid, :426-441,591-599 */
+vf_status vf_grid_dims(const vf_grid* g, uint32_t dims[3]);              /* getNumSubdivisions, :528-531 */
+void*     vf_grid_device_ptr(vf_grid* g);                                /* RegularGrid::ssbo() */
+vf_status vf_grid_upload(vf_grid* g, const uint16_t* host);              /* updateSSBO, :511-514 */
+vf_status vf_grid_download(vf_grid* g, uint16_t* host);                  /* updateGrid, :505-509 (synchronises) */
+vf_status vf_grid_upload_async(vf_grid* g, const uint16_t* pinned_host);
+vf_status vf_grid_download_async(vf_grid* g, uint16_t* pinned_host);
+vf_status vf_grid_fill(vf_grid* g, uint16_t value);
+/* interactive dims rule of CADScene::allocateMeshGrid, CADScene.cpp:545-556 (host arithmetic only) */
+void      vf_dims_rule(const float aabb_min[3], const float aabb_max[3], uint32_t max_voxels, uint32_t dims_out[3]);
+
+/* ------------------------------------------------------------------ V2: voxelization */
+/* RegularGrid::fill(Model3D*) (RegularGrid.cpp:173-212) with the north-star occupancy predicate: voxel = FREE iff some
+ * triangle passes Intersections3D::intersect(Triangle3D&, AABB&) (SRC/Geometry/3D/Intersections3D.h:204-420) against the
+ * voxel box of RegularGrid.cpp:258-259.  verts/faces are HOST pointers: float[nv][3], uint32[nf][3]. */
+vf_status vf_voxelize(vf_grid* g, const float* verts, uint32_t nv, const uint32_t* faces, uint32_t nf);
+
+/* ------------------------------------------------------------------ S1/S2: seeding (class fracturer::Seeder) */
+/* Seeder::uniform (Seeder.cpp:154-208).  The grid stays on the device: candidate draws are made on the host in the
+ * reference's order and tested on the device in batches; the RNG ends exactly where the reference's would. */
+vf_status vf_seed_uniform(vf_grid* g, uint32_t n, int random_mode, int location, uint32_t* seeds_out, uint32_t* attempts_out);
+/* Seeder::mergeSeeds (Seeder.cpp:115-152) — host only */
+vf_status vf_merge_seeds(const uint32_t* frags, uint32_t nfrags, uint32_t* seeds, uint32_t nseeds, int dfunc);
+/* seed block of CADScene::fractureModel (CADScene.cpp:626-655, numImpacts == 0): returns n or n + n + n_extra seeds */
+vf_status vf_make_seeds(vf_grid* g, uint32_t n, uint32_t n_extra, int random_mode, int merge_dfunc, uint32_t* seeds_out,
+                        uint32_t capacity, uint32_t* count_out);
+
+/* ------------------------------------------------------------------ F1..F3: fragmentation (class fracturer::Fracturer) */
+/* NaiveFracturer::build (NaiveFracturer.cpp:215-225; spec = buildCPU :26-68 / naiveFracturer-comp.glsl:19-43) */
+vf_status vf_fracture_naive(vf_grid* g, const uint32_t* seeds, uint32_t nseeds, int dfunc);
+/* FloodFracturer::build (FloodFracturer.cpp:98-191) under the deterministic lowest-seed-index rule.
+ * dfunc MANHATTAN -> 6-neighbourhood, otherwise 26 (FloodFracturer.cpp:114).  id_bits 0/8 or 15 (see vf_params). */
+vf_status vf_fracture_flood(vf_grid* g, const uint32_t* seeds, uint32_t nseeds, int dfunc, int id_bits, vf_flood_stats* stats);
+
+/* ------------------------------------------------------------------ C1..C4: cleanup */
+vf_status vf_remove_isolated_regions(vf_grid* g, const uint32_t* seeds, uint32_t nseeds); /* NaiveFracturer::removeIsolatedRegionsCPU semantics, NaiveFracturer.cpp:111-150 */
+vf_status vf_detect_boundaries(vf_grid* g, int boundary_size);           /* RegularGrid::detectBoundaries, RegularGrid.cpp:64-80 */
+/* RegularGrid::erode (RegularGrid.cpp:82-159); noise = HOST table (vf_fill_noise), boundary_mode see vf_params */
+vf_status vf_erode(vf_grid* g, int erosion_type, uint32_t size, uint32_t iterations, float probability, float threshold,
+                   const float* noise, uint32_t nnoise, int boundary_mode);
+vf_status vf_remove_isolated_regions_grid(vf_grid* g);                   /* RegularGrid::removeIsolatedRegions, RegularGrid.cpp:1006-1015 (snapshot semantics) */
+vf_status vf_undo_mask(vf_grid* g);                                      /* RegularGrid::undoMask, RegularGrid.cpp:488-503 */
+vf_status vf_reset_filling(vf_grid* g);                                  /* RegularGrid::resetFilling, :412-418 */
+vf_status vf_homogenize(vf_grid* g);                                     /* RegularGrid::homogenize, :533-541 */
+
+/* ------------------------------------------------------------------ H1: histogram */
+/* RegularGrid::countValues + numOccupiedVoxels (RegularGrid.cpp:601-625, 280-287): counts[VF_HISTOGRAM_BINS] indexed by
+ * (value & 0x7FFF) over cells with value > FREE; *occupied = number of such cells. */
+vf_status vf_histogram(vf_grid* g, uint32_t* counts, uint64_t* occupied);
+
+/* ------------------------------------------------------------------ X1: export */
+vf_status vf_export(vf_grid* g, const char* path_without_extension, int export_type, int squared); /* RegularGrid::exportGrid, :161-171 */
+/* in-memory encoders (host): return bytes needed; write when out != NULL && cap is large enough */
+uint64_t  vf_encode_rle(const uint16_t* grid, const uint32_t dims[3], uint8_t* out, uint64_t cap);          /* exportRLE :672-714 */
+uint64_t  vf_encode_bing_squared(const uint16_t* grid, const uint32_t dims[3], uint8_t* out, uint64_t cap); /* exportRawCompressed squared :638-666 */
+
+/* ------------------------------------------------------------------ the caller's block: CADScene::fractureModel */
+/* CADScene.cpp:624-691: seeds -> Fracturer::build -> erode | detectBoundaries(1).  seeds_out (optional, capacity
+ * numSeeds*2+numExtraSeeds entries of uint32[4]) receives the seed list used. */
+vf_status vf_fracture_model(vf_grid* g, const vf_params* p, uint32_t* seeds_out, uint32_t* nseeds_out, vf_flood_stats* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOXFRAG_H */

@@ -1,0 +1,413 @@
+// context.cu — contexts, grids, RNG, errors, host<->device copies and the trivially HBM-bound pointwise passes.
+// Replaces the reference's GL runtime plumbing (SRC/Graphics/Core/ComputeShader.cpp) and RegularGrid's
+// host/SSBO mirroring (SRC/DataStructures/RegularGrid.cpp:505-514, 583-599).
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "vf_internal.h"
+
+// ---------------------------------------------------------------------------------------------- errors
+static thread_local char g_err[512] = "";
+
+vf_status vf_set_error(vf_status code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" const char* vf_last_error(void) { return g_err; }
+extern "C" const char* vf_version(void) { return "voxfrag-b200 0.1 (sm_100a)"; }
+
+extern "C" int vf_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" void vf_params_default(vf_params* p)
+{
+    // FractureParameters::FractureParameters(), FractureParameters.h:91-145
+    std::memset(p, 0, sizeof(*p));
+    p->biasFocus = 5;
+    p->biasSeeds = 32;
+    p->clampVoxelMetricUnit = 200;
+    p->erode = 0;
+    p->erosionConvolution = VF_ELLIPSE;
+    p->erosionIterations = 3;
+    p->erosionProbability = .5f;
+    p->erosionSize = 3;
+    p->erosionThreshold = .5f;
+    p->fractureAlgorithm = VF_FLOOD;
+    p->distanceFunction = VF_CHEBYSHEV;
+    p->launchGPU = 1;
+    p->mergeSeedsDistanceFunction = VF_EUCLIDEAN;
+    p->neighbourhoodType = VF_VON_NEUMANN;
+    p->numExtraSeeds = 16;
+    p->numImpacts = 0;
+    p->numSeeds = 8;
+    p->removeIsolatedRegions = 1;
+    p->seed = 80;
+    p->seedingRandom = VF_STD_UNIFORM;
+    p->voxelPerMetricUnit = 20;
+    p->voxelizationSize[0] = p->voxelizationSize[1] = p->voxelizationSize[2] = 128;
+    p->exportGridExtension = VF_VOX;
+    p->floodIdBits = 0;
+    p->erodeBoundaryMode = 0;
+}
+
+// ---------------------------------------------------------------------------------------------- context
+vf_status vf_enter(vf_ctx* ctx)
+{
+    VF_REQUIRE(ctx != nullptr, VF_ERR_INVALID_ARGUMENT, "null context");
+    VF_CUDA(cudaSetDevice(ctx->device));
+    return VF_OK;
+}
+
+static vf_status ctx_create(int device, void* stream, bool borrow, vf_ctx** out)
+{
+    VF_REQUIRE(out != nullptr, VF_ERR_INVALID_ARGUMENT, "out == NULL");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return vf_set_error(VF_ERR_CUDA, "no CUDA device: libvoxfrag has no CPU fallback");
+    }
+    VF_REQUIRE(device >= 0 && device < n, VF_ERR_INVALID_ARGUMENT, "device %d out of range (have %d)", device, n);
+    VF_CUDA(cudaSetDevice(device));
+    vf_ctx* c = new (std::nothrow) vf_ctx();
+    VF_REQUIRE(c != nullptr, VF_ERR_CAPACITY, "out of host memory");
+    c->device = device;
+    cudaDeviceProp prop;
+    VF_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    c->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (borrow) {
+        c->stream = (cudaStream_t)stream;
+        c->own_stream = false;
+    } else {
+        VF_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    VF_CUDA(cudaEventCreate(&c->ev_start));
+    VF_CUDA(cudaEventCreate(&c->ev_stop));
+    c->pinned_bytes = 1 << 16;
+    VF_CUDA(cudaMallocHost(&c->pinned, c->pinned_bytes));
+    c->rng.seed(80);  // FractureParameters::_seed default (FractureParameters.h:116), applied at CADScene.cpp:36-37
+    *out = c;
+    return VF_OK;
+}
+
+extern "C" vf_status vf_ctx_create(int device, vf_ctx** out) { return ctx_create(device, nullptr, false, out); }
+extern "C" vf_status vf_ctx_create_on_stream(int device, void* s, vf_ctx** out) { return ctx_create(device, s, true, out); }
+
+extern "C" void vf_ctx_destroy(vf_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    VfScratch* all[] = { &c->keys, &c->grid2, &c->tiles, &c->small, &c->noise, &c->mesh };
+    for (VfScratch* s : all)
+        if (s->ptr) cudaFree(s->ptr);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->ev_start) cudaEventDestroy(c->ev_start);
+    if (c->ev_stop) cudaEventDestroy(c->ev_stop);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+vf_status vf_scratch_reserve(vf_ctx* ctx, VfScratch& s, size_t bytes)
+{
+    if (s.bytes >= bytes) return VF_OK;
+    if (s.ptr) {
+        VF_CUDA(cudaStreamSynchronize(ctx->stream));
+        VF_CUDA(cudaFree(s.ptr));
+        s.ptr = nullptr;
+        s.bytes = 0;
+    }
+    bytes = (bytes + 255) & ~(size_t)255;
+    VF_CUDA(cudaMalloc(&s.ptr, bytes));
+    s.bytes = bytes;
+    return VF_OK;
+}
+
+extern "C" vf_status vf_ctx_reserve(vf_ctx* ctx, uint32_t X, uint32_t Y, uint32_t Z)
+{
+    VF_TRY(vf_enter(ctx));
+    const size_t n = (size_t)X * Y * Z;
+    VF_TRY(vf_scratch_reserve(ctx, ctx->keys, n * 4));
+    VF_TRY(vf_scratch_reserve(ctx, ctx->grid2, n * 2));
+    return VF_OK;
+}
+
+extern "C" vf_status vf_ctx_synchronize(vf_ctx* ctx)
+{
+    VF_TRY(vf_enter(ctx));
+    VF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VF_OK;
+}
+
+extern "C" void* vf_ctx_stream(vf_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" uint64_t vf_ctx_kernel_launches(vf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" vf_status vf_ctx_timer_start(vf_ctx* ctx)
+{
+    VF_TRY(vf_enter(ctx));
+    VF_CUDA(cudaEventRecord(ctx->ev_start, ctx->stream));
+    return VF_OK;
+}
+extern "C" vf_status vf_ctx_timer_stop(vf_ctx* ctx, float* ms)
+{
+    VF_TRY(vf_enter(ctx));
+    VF_CUDA(cudaEventRecord(ctx->ev_stop, ctx->stream));
+    VF_CUDA(cudaEventSynchronize(ctx->ev_stop));
+    VF_CUDA(cudaEventElapsedTime(ms, ctx->ev_start, ctx->ev_stop));
+    return VF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- RNG
+extern "C" vf_status vf_rng_seed(vf_ctx* ctx, uint32_t seed)
+{
+    VF_REQUIRE(ctx != nullptr, VF_ERR_INVALID_ARGUMENT, "null context");
+    ctx->rng.seed(seed);
+    return VF_OK;
+}
+extern "C" float vf_rng_uniform(vf_ctx* ctx) { return ctx->rng.uniform(); }
+extern "C" uint32_t vf_rng_raw(vf_ctx* ctx) { return ctx->rng.next(); }
+extern "C" vf_status vf_fill_noise(vf_ctx* ctx, float* noise, uint32_t n)
+{
+    VF_REQUIRE(ctx && noise, VF_ERR_INVALID_ARGUMENT, "null argument");
+    for (uint32_t i = 0; i < n; ++i) noise[i] = ctx->rng.uniform(.0f, 1.0f);  // RegularGrid.cpp:238-244, serial order
+    return VF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- grid
+extern "C" vf_status vf_grid_create(vf_ctx* ctx, uint32_t X, uint32_t Y, uint32_t Z, vf_grid** out)
+{
+    VF_TRY(vf_enter(ctx));
+    VF_REQUIRE(out && X && Y && Z, VF_ERR_INVALID_ARGUMENT, "bad grid dims %ux%ux%u", X, Y, Z);
+    VF_REQUIRE(X <= 65535 && Y <= 65535 && Z <= 65535, VF_ERR_CAPACITY, "grid axis > 65535");
+    vf_grid* g = new (std::nothrow) vf_grid();
+    VF_REQUIRE(g != nullptr, VF_ERR_CAPACITY, "out of host memory");
+    g->ctx = ctx;
+    g->X = X, g->Y = Y, g->Z = Z;
+    g->capacity = g->n();
+    g->own = true;
+    cudaError_t e = cudaMalloc(&g->d, g->capacity * sizeof(uint16_t) + 64);
+    if (e != cudaSuccess) {
+        const size_t want = g->capacity * 2;
+        delete g;
+        return vf_set_error(VF_ERR_CUDA, "cudaMalloc(%zu B): %s", want, cudaGetErrorString(e));
+    }
+    e = cudaMemsetAsync(g->d, 0, g->capacity * sizeof(uint16_t), ctx->stream);  // RegularGrid::buildGrid: all EMPTY
+    if (e != cudaSuccess) {
+        cudaFree(g->d);
+        delete g;
+        return vf_set_error(VF_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+    }
+    *out = g;
+    return VF_OK;
+}
+
+extern "C" vf_status vf_grid_wrap(vf_ctx* ctx, void* dptr, uint32_t X, uint32_t Y, uint32_t Z, vf_grid** out)
+{
+    VF_TRY(vf_enter(ctx));
+    VF_REQUIRE(out && dptr && X && Y && Z, VF_ERR_INVALID_ARGUMENT, "bad arguments");
+    VF_REQUIRE(((uintptr_t)dptr & 15) == 0, VF_ERR_INVALID_ARGUMENT, "device pointer must be 16-byte aligned");
+    VF_REQUIRE(X <= 65535 && Y <= 65535 && Z <= 65535, VF_ERR_CAPACITY, "grid axis > 65535");
+    vf_grid* g = new (std::nothrow) vf_grid();
+    VF_REQUIRE(g != nullptr, VF_ERR_CAPACITY, "out of host memory");
+    g->ctx = ctx;
+    g->d = (uint16_t*)dptr;
+    g->X = X, g->Y = Y, g->Z = Z;
+    g->capacity = g->n();
+    g->own = false;
+    *out = g;
+    return VF_OK;
+}
+
+extern "C" void vf_grid_destroy(vf_grid* g)
+{
+    if (!g) return;
+    if (g->own && g->d) {
+        cudaSetDevice(g->ctx->device);
+        cudaStreamSynchronize(g->ctx->stream);
+        cudaFree(g->d);
+    }
+    delete g;
+}
+
+extern "C" vf_status vf_grid_set_aabb(vf_grid* g, const float mn[3], const float mx[3], uint32_t X, uint32_t Y, uint32_t Z)
+{
+    // RegularGrid::setAABB (:426-441): re-dimension inside the existing allocation (dataset mode allocates once at the
+    // clamp size, CADScene.cpp:529-543) and cleanGrid (:591-599)
+    VF_REQUIRE(g != nullptr, VF_ERR_INVALID_ARGUMENT, "null grid");
+    VF_TRY(vf_enter(g->ctx));
+    VF_REQUIRE(X && Y && Z && (size_t)X * Y * Z <= g->capacity, VF_ERR_CAPACITY, "setAABB dims %ux%ux%u exceed the allocation (%zu voxels)",
+               X, Y, Z, g->capacity);
+    for (int i = 0; i < 3; ++i) g->aabb_min[i] = mn[i], g->aabb_max[i] = mx[i];
+    g->X = X, g->Y = Y, g->Z = Z;
+    VF_CUDA(cudaMemsetAsync(g->d, 0, g->n() * sizeof(uint16_t), g->ctx->stream));
+    return VF_OK;
+}
+
+extern "C" vf_status vf_grid_dims(const vf_grid* g, uint32_t dims[3])
+{
+    VF_REQUIRE(g && dims, VF_ERR_INVALID_ARGUMENT, "null argument");
+    dims[0] = g->X, dims[1] = g->Y, dims[2] = g->Z;
+    return VF_OK;
+}
+
+extern "C" void* vf_grid_device_ptr(vf_grid* g) { return g ? g->d : nullptr; }
+
+extern "C" vf_status vf_grid_upload_async(vf_grid* g, const uint16_t* host)
+{
+    VF_REQUIRE(g && host, VF_ERR_INVALID_ARGUMENT, "null argument");
+    VF_TRY(vf_enter(g->ctx));
+    VF_CUDA(cudaMemcpyAsync(g->d, host, g->n() * sizeof(uint16_t), cudaMemcpyHostToDevice, g->ctx->stream));
+    return VF_OK;
+}
+extern "C" vf_status vf_grid_download_async(vf_grid* g, uint16_t* host)
+{
+    VF_REQUIRE(g && host, VF_ERR_INVALID_ARGUMENT, "null argument");
+    VF_TRY(vf_enter(g->ctx));
+    VF_CUDA(cudaMemcpyAsync(host, g->d, g->n() * sizeof(uint16_t), cudaMemcpyDeviceToHost, g->ctx->stream));
+    return VF_OK;
+}
+extern "C" vf_status vf_grid_upload(vf_grid* g, const uint16_t* host)
+{
+    VF_TRY(vf_grid_upload_async(g, host));
+    VF_CUDA(cudaStreamSynchronize(g->ctx->stream));
+    return VF_OK;
+}
+extern "C" vf_status vf_grid_download(vf_grid* g, uint16_t* host)
+{
+    VF_TRY(vf_grid_download_async(g, host));
+    VF_CUDA(cudaStreamSynchronize(g->ctx->stream));
+    return VF_OK;
+}
+
+extern "C" void vf_dims_rule(const float mn[3], const float mx[3], uint32_t maxVoxels, uint32_t out[3])
+{
+    // CADScene::allocateMeshGrid, CADScene.cpp:545-556 (float32 arithmetic as written)
+    float size[3], maxSize = 0.0f;
+    for (int i = 0; i < 3; ++i) {
+        size[i] = mx[i] - mn[i];
+        maxSize = fmaxf(maxSize, size[i]);
+    }
+    for (int i = 0; i < 3; ++i) {
+        int v = (int)floorf((float)maxVoxels * size[i] / maxSize);
+        while (v % 4 != 0) ++v;
+        while (v % 4 != 0 || v > (int)maxVoxels) --v;
+        out[i] = (uint32_t)v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- seeds
+vf_status vf_upload_seeds(vf_ctx* ctx, const uint32_t* seeds, uint32_t n, uint32_t X, uint32_t Y, uint32_t Z, ushort4** d_out)
+{
+    VF_REQUIRE(seeds && n > 0, VF_ERR_INVALID_ARGUMENT, "no seeds");
+    VF_REQUIRE((size_t)n * sizeof(ushort4) <= ctx->pinned_bytes, VF_ERR_CAPACITY, "too many seeds (%u)", n);
+    VF_TRY(vf_scratch_reserve(ctx, ctx->small, 1 << 20));
+    // the pinned mailbox may still be in flight from a previous call on this stream
+    VF_CUDA(cudaStreamSynchronize(ctx->stream));
+    ushort4* h = (ushort4*)ctx->pinned;
+    for (uint32_t i = 0; i < n; ++i) {
+        VF_REQUIRE(seeds[4 * i] < X && seeds[4 * i + 1] < Y && seeds[4 * i + 2] < Z, VF_ERR_INVALID_ARGUMENT,
+                   "seed %u (%u,%u,%u) outside the %ux%ux%u grid", i, seeds[4 * i], seeds[4 * i + 1], seeds[4 * i + 2], X, Y, Z);
+        VF_REQUIRE(seeds[4 * i + 3] <= 0xFFFFu, VF_ERR_CAPACITY, "seed %u label %u does not fit the uint16 cell", i, seeds[4 * i + 3]);
+        h[i] = make_ushort4((unsigned short)seeds[4 * i], (unsigned short)seeds[4 * i + 1], (unsigned short)seeds[4 * i + 2],
+                            (unsigned short)seeds[4 * i + 3]);
+    }
+    VF_CUDA(cudaMemcpyAsync(ctx->small.ptr, h, (size_t)n * sizeof(ushort4), cudaMemcpyHostToDevice, ctx->stream));
+    *d_out = (ushort4*)ctx->small.ptr;
+    return VF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- pointwise passes (C4)
+// undoMask (undoMask-comp.glsl:19-37), resetFilling (RegularGrid.cpp:412-418), homogenize (:533-541), fill.
+// 2 B read + 2 B write per voxel, 128-bit vectors, grid-stride; nothing to tile.
+template <int OP>
+__device__ __forceinline__ uint32_t pw2(uint32_t v, uint32_t fillv)
+{
+    if (OP == VF_PW_UNMASK15) return v & 0x7FFF7FFFu;
+    if (OP == VF_PW_RIGHTMOST8) return v & 0x00FF00FFu;
+    if (OP == VF_PW_RESET_FILLING) {
+        const uint32_t lo = min(v & 0xFFFFu, 2u), hi = min(v >> 16, 2u);
+        return lo | (hi << 16);
+    }
+    if (OP == VF_PW_HOMOGENIZE) return ((v & 0xFFFFu) ? 1u : 0u) | ((v >> 16) ? 0x10000u : 0u);
+    return fillv;
+}
+
+template <int OP>
+__global__ void __launch_bounds__(256) pointwise_kernel(uint16_t* __restrict__ grid, size_t n, uint32_t fillv)
+{
+    const size_t nvec = n / 8;
+    uint4* g4 = reinterpret_cast<uint4*>(grid);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+        uint4 v = OP == 4 ? make_uint4(0, 0, 0, 0) : vf_ldg_stream(g4 + i);
+        v.x = pw2<OP>(v.x, fillv), v.y = pw2<OP>(v.y, fillv), v.z = pw2<OP>(v.z, fillv), v.w = pw2<OP>(v.w, fillv);
+        vf_stg_stream(g4 + i, v);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < n % 8) {
+        const size_t i = nvec * 8 + threadIdx.x;
+        uint32_t v = grid[i];
+        v = pw2<OP>(v, fillv) & 0xFFFFu;
+        grid[i] = (uint16_t)v;
+    }
+}
+
+vf_status vf_k_pointwise(vf_grid* g, int op)
+{
+    vf_ctx* c = g->ctx;
+    const size_t n = g->n();
+    const int blocks = (int)min((size_t)c->num_sms * 8, (n / 8 + 255) / 256 + 1);
+    switch (op) {
+    case VF_PW_UNMASK15: pointwise_kernel<VF_PW_UNMASK15><<<blocks, 256, 0, c->stream>>>(g->d, n, 0); break;
+    case VF_PW_RIGHTMOST8: pointwise_kernel<VF_PW_RIGHTMOST8><<<blocks, 256, 0, c->stream>>>(g->d, n, 0); break;
+    case VF_PW_RESET_FILLING: pointwise_kernel<VF_PW_RESET_FILLING><<<blocks, 256, 0, c->stream>>>(g->d, n, 0); break;
+    case VF_PW_HOMOGENIZE: pointwise_kernel<VF_PW_HOMOGENIZE><<<blocks, 256, 0, c->stream>>>(g->d, n, 0); break;
+    default: return vf_set_error(VF_ERR_INVALID_ARGUMENT, "bad pointwise op %d", op);
+    }
+    VF_LAUNCHED(c);
+    return VF_OK;
+}
+
+extern "C" vf_status vf_grid_fill(vf_grid* g, uint16_t value)
+{
+    VF_REQUIRE(g != nullptr, VF_ERR_INVALID_ARGUMENT, "null grid");
+    VF_TRY(vf_enter(g->ctx));
+    vf_ctx* c = g->ctx;
+    const size_t n = g->n();
+    const int blocks = (int)min((size_t)c->num_sms * 8, (n / 8 + 255) / 256 + 1);
+    pointwise_kernel<4><<<blocks, 256, 0, c->stream>>>(g->d, n, (uint32_t)value | ((uint32_t)value << 16));
+    VF_LAUNCHED(c);
+    return VF_OK;
+}
+
+extern "C" vf_status vf_undo_mask(vf_grid* g)
+{
+    VF_REQUIRE(g != nullptr, VF_ERR_INVALID_ARGUMENT, "null grid");
+    VF_TRY(vf_enter(g->ctx));
+    return vf_k_pointwise(g, VF_PW_UNMASK15);
+}
+extern "C" vf_status vf_reset_filling(vf_grid* g)
+{
+    VF_REQUIRE(g != nullptr, VF_ERR_INVALID_ARGUMENT, "null grid");
+    VF_TRY(vf_enter(g->ctx));
+    return vf_k_pointwise(g, VF_PW_RESET_FILLING);
+}
+extern "C" vf_status vf_homogenize(vf_grid* g)
+{
+    VF_REQUIRE(g != nullptr, VF_ERR_INVALID_ARGUMENT, "null grid");
+    VF_TRY(vf_enter(g->ctx));
+    return vf_k_pointwise(g, VF_PW_HOMOGENIZE);
+}
