@@ -1,0 +1,163 @@
+"""F2/F3/C1 parity: CUDA tile-worklist flood and connected-to-seed cleanup vs the oracle, bit-exact labels."""
+import numpy as np
+import pytest
+
+from conftest import pick_seeds, random_blob_grid
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import voxelfragmentml_b200 as vf
+
+    c = vf.Context(0)
+    yield c
+    c.close()
+
+
+def _run_flood(ctx, grid, seeds, dfunc, id_bits=0):
+    import voxelfragmentml_b200 as vf
+
+    g = vf.RegularGrid(ctx, grid.shape)
+    g.updateSSBO(grid)
+    f = vf.FloodFracturer()
+    assert f.setDistanceFunction(dfunc)
+    f.build(g, seeds, id_bits=id_bits)
+    out = g.updateGrid()
+    g.close()
+    return out, f.last_stats
+
+
+@pytest.mark.parametrize("dfunc", [1, 2, 0])
+def test_vessel_fixture_16_seeds(ctx, orc, vessel_grid, dfunc):
+    seeds, _ = orc.seed_uniform(orc.Rng(80), vessel_grid, 16)
+    want, st = orc.flood(vessel_grid.copy(), seeds, dfunc)
+    got, gst = _run_flood(ctx, vessel_grid, seeds, dfunc)
+    assert np.array_equal(got, want)
+    assert gst.max_dist == st.max_dist and gst.disjoint_rounds == 1 and gst.freed_voxels == 0
+    assert gst.tile_rounds >= 1 and gst.tile_visits >= gst.tile_rounds
+
+
+@pytest.mark.parametrize("shape", [(40, 36, 64), (33, 21, 76), (17, 19, 35), (13, 11, 7), (5, 6, 130), (70, 9, 33)])
+@pytest.mark.parametrize("dfunc", [1, 2])
+def test_ragged_shapes_and_partial_tiles(ctx, orc, shape, dfunc):
+    g = random_blob_grid(shape, 11, fill=0.5, smooth=1)
+    seeds = pick_seeds(g, 6, 2)
+    want, _ = orc.flood(g.copy(), seeds, dfunc)
+    got, _ = _run_flood(ctx, g, seeds, dfunc)
+    assert np.array_equal(got, want)
+
+
+def test_labyrinth_long_geodesics(ctx, orc):
+    """A serpentine corridor: geodesic distance ~ 20x the grid diameter, crosses every tile many times."""
+    g = np.zeros((48, 40, 96), np.uint16)
+    for x in range(0, 48, 2):
+        g[x, :, :] = 1
+    for i, x in enumerate(range(1, 47, 2)):
+        g[x, 39 if i % 2 == 0 else 0, :] = 1
+    seeds = np.array([[0, 0, 0, 2], [46, 0, 95, 3], [24, 20, 50, 4]], np.uint32)
+    for dfunc in (1, 2):
+        want, st = orc.flood(g.copy(), seeds, dfunc)
+        got, gst = _run_flood(ctx, g, seeds, dfunc)
+        assert np.array_equal(got, want)
+        assert gst.max_dist == st.max_dist and st.max_dist > 300
+
+
+def test_unreachable_cells_stay_free_and_seed_on_empty_cell(ctx, orc):
+    g = np.zeros((20, 20, 40), np.uint16)
+    g[2:8, 2:8, 2:30] = 1
+    g[12:18, 12:18, 5:35] = 1      # island without a seed: must stay FREE (1)
+    seeds = np.array([[3, 3, 3, 2], [7, 7, 29, 3], [10, 10, 10, 4]], np.uint32)  # third seed sits on an EMPTY cell
+    want, _ = orc.flood(g.copy(), seeds, 1)
+    got, _ = _run_flood(ctx, g, seeds, 1)
+    assert np.array_equal(got, want)
+    assert (got[12:18, 12:18, 5:35] == 1).all() and got[10, 10, 10] == 4
+
+
+@pytest.mark.parametrize("dfunc", [1, 2])
+def test_extra_seeds_disjoint_rounds(ctx, orc, vessel_grid, dfunc):
+    """F3: numExtraSeeds = 2*numSeeds as in dataset generation (FragmentationProcedure.h:12-13, CADScene.cpp:298-299)."""
+    two_rounds = 0
+    for trial, nf in enumerate([2, 4, 7, 10]):
+        seeds = orc.make_seeds(orc.Rng(80 + trial), vessel_grid, nf, 2 * nf, merge_dfunc=0)
+        want, st = orc.flood(vessel_grid.copy(), seeds, dfunc)
+        got, gst = _run_flood(ctx, vessel_grid, seeds, dfunc)
+        assert np.array_equal(got, want), f"nf={nf}"
+        assert gst.freed_voxels == st.freed_voxels and gst.disjoint_rounds == st.rounds
+        two_rounds += st.rounds == 2
+        assert set(np.unique(got)) <= set(range(0, nf + 2))
+    assert two_rounds >= 1  # the dissolve-and-reflood path was exercised
+
+
+def test_extra_seeds_on_random_blobs(ctx, orc):
+    for trial in range(6):
+        g = random_blob_grid((37, 29, 45), 200 + trial, fill=0.5, smooth=1)
+        seeds = orc.make_seeds(orc.Rng(trial), g, 3, 9, merge_dfunc=trial % 3)
+        for dfunc in (1, 2):
+            want, st = orc.flood(g.copy(), seeds, dfunc)
+            got, gst = _run_flood(ctx, g, seeds, dfunc)
+            assert np.array_equal(got, want)
+            assert gst.freed_voxels == st.freed_voxels
+
+
+def test_id_bits_15_many_labels(ctx, orc):
+    """cfg5's label space: 256+ seeds need ids beyond 8 bits (SURVEY finding 7) -> whole word is the id, no prefixes."""
+    g = random_blob_grid((64, 64, 64), 5, fill=0.6, smooth=1)
+    seeds = pick_seeds(g, 300, 9)
+    want, _ = orc.flood(g.copy(), seeds, 1, id_bits=15)
+    got, _ = _run_flood(ctx, g, seeds, 1, id_bits=15)
+    assert np.array_equal(got, want) and got.max() == 301
+
+
+def test_full_size_256_upsampled_vessel(ctx, orc, vessel_grid):
+    """cfg2 size: the reference vessel upsampled x2 (256x220x256, 889k*8 occupied cells), Manhattan, 16 seeds."""
+    big = np.ascontiguousarray(np.kron(vessel_grid, np.ones((2, 2, 2), np.uint16)))
+    seeds, _ = orc.seed_uniform(orc.Rng(80), big, 16)
+    want, st = orc.flood(big.copy(), seeds, 1)
+    got, gst = _run_flood(ctx, big, seeds, 1)
+    assert np.array_equal(got, want) and gst.max_dist == st.max_dist
+    # running twice on the labelled grid re-homogenises and gives the same result (FloodFracturer.cpp:99)
+    import voxelfragmentml_b200 as vf
+
+    g = vf.RegularGrid(ctx, big.shape)
+    g.updateSSBO(got)
+    f = vf.FloodFracturer()
+    f.build(g, seeds)
+    assert np.array_equal(g.updateGrid(), want)
+    g.close()
+
+
+# ------------------------------------------------------------------------------------------------ C1
+def _run_c1(ctx, grid, seeds):
+    import voxelfragmentml_b200 as vf
+
+    g = vf.RegularGrid(ctx, grid.shape)
+    g.updateSSBO(grid)
+    vf.NaiveFracturer.removeIsolatedRegions(g, seeds)
+    out = g.updateGrid()
+    g.close()
+    return out
+
+
+@pytest.mark.parametrize("dfunc", [0, 1, 2])
+def test_c1_after_naive_on_vessel(ctx, orc, vessel_grid, dfunc):
+    seeds, _ = orc.seed_uniform(orc.Rng(80), vessel_grid, 12)
+    lab = orc.naive(vessel_grid.copy(), seeds, dfunc)
+    want = orc.remove_isolated_regions_cpu(lab.copy(), seeds)
+    got = _run_c1(ctx, lab, seeds)
+    assert np.array_equal(got, want)
+
+
+def test_c1_islands_free_cells_and_foreign_seed_cell(ctx, orc):
+    for trial in range(5):
+        g = random_blob_grid((35, 33, 70), 300 + trial, fill=0.45, smooth=1)
+        seeds = pick_seeds(g, 8, trial)
+        lab = orc.naive(g.copy(), seeds, 1)  # Manhattan cells are not convex: islands appear in porous blobs
+        lab[1:3, 1:3, 1:3] = 1               # stray FREE cells are dropped too (output is rebuilt from an EMPTY grid)
+        s2 = seeds.copy()
+        s2[0, :3] = np.argwhere(lab == s2[1, 3])[0]  # seed 0 sits on a cell labelled by seed 1: its cell still becomes s2[0].w
+        for sd in (seeds, s2):
+            want = orc.remove_isolated_regions_cpu(lab.copy(), sd)
+            got = _run_c1(ctx, lab, sd)
+            assert np.array_equal(got, want)

@@ -69,7 +69,7 @@ def test_ties_go_to_lowest_seed_index(ctx, orc):
         want = orc.naive(g.copy(), seeds, dfunc)
         got = _run_naive(ctx, g, seeds, dfunc)
         assert np.array_equal(got, want)
-        assert got[4, 4, 5] == 7 and got[4, 4, 9] == 9  # equidistant cells: seed 0 beats 2, seed 2 beats... index order
+        assert got[4, 4, 5] == 7 and got[4, 4, 9] == 5  # equidistant cells: index 0 beats index 2, index 1 beats index 2
 
 
 def test_prelabelled_and_empty_cells(ctx, orc):

@@ -98,7 +98,7 @@ static vf_status ctx_create(int device, void* stream, bool borrow, vf_ctx** out)
     }
     VF_CUDA(cudaEventCreate(&c->ev_start));
     VF_CUDA(cudaEventCreate(&c->ev_stop));
-    c->pinned_bytes = 1 << 16;
+    c->pinned_bytes = 1 << 17;  // [0, 64K) seed staging, [64K, 128K) counter mailbox
     VF_CUDA(cudaMallocHost(&c->pinned, c->pinned_bytes));
     c->rng.seed(80);  // FractureParameters::_seed default (FractureParameters.h:116), applied at CADScene.cpp:36-37
     *out = c;
@@ -314,7 +314,7 @@ extern "C" void vf_dims_rule(const float mn[3], const float mx[3], uint32_t maxV
 vf_status vf_upload_seeds(vf_ctx* ctx, const uint32_t* seeds, uint32_t n, uint32_t X, uint32_t Y, uint32_t Z, ushort4** d_out)
 {
     VF_REQUIRE(seeds && n > 0, VF_ERR_INVALID_ARGUMENT, "no seeds");
-    VF_REQUIRE((size_t)n * sizeof(ushort4) <= ctx->pinned_bytes, VF_ERR_CAPACITY, "too many seeds (%u)", n);
+    VF_REQUIRE((size_t)n * sizeof(ushort4) <= 65536, VF_ERR_CAPACITY, "too many seeds (%u)", n);
     VF_TRY(vf_scratch_reserve(ctx, ctx->small, 1 << 20));
     // the pinned mailbox may still be in flight from a previous call on this stream
     VF_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -1,0 +1,635 @@
+// flood.cu — F2/F3 flood-fill fragmentation and C1 connected-to-seed cleanup.
+//
+// Replaces FloodFracturer::build (SRC/Fracturer/FloodFracturer.cpp:98-191; shaders floodFracturer-comp.glsl:24-64,
+// disjointSet-comp.glsl:17-24, disjointSetStack-comp.glsl:20-37, undoMask-comp.glsl) and the intended semantics of
+// NaiveFracturer::removeIsolatedRegions (removeIsolatedRegionsCPU, NaiveFracturer.cpp:111-150).
+//
+// Deterministic rule (the reference's plain-store claims are racy): every FREE cell takes the word of the
+// source minimising (geodesic distance through non-EMPTY cells under the 6/26 neighbourhood, index in the seeds vector).
+// That is the unique least fixed point of  key(v) = min(key(v), min_{u ~ v} key(u) + 1 level)  over 32-bit keys
+// (dist << 15 | order), which makes the result independent of the evaluation schedule: tiles can be relaxed in any order,
+// concurrently, on any number of GPUs, and still give bit-identical labels.
+//
+// F3 (extra seeds, words = fragId | prefix << 8): the reference's in-flood prefix merge converges, inside every connected set
+// of equal-fragId cells, to the lowest prefix present; the disjoint step then frees every cell whose prefix is not its
+// fragment's minimum and re-floods from all labelled cells.  Restated: keep, per fragment id, only the component (under the
+// flood neighbourhood, through equal-fragId cells) that contains the fragment's lowest-prefix source; free the rest; re-flood
+// with order(cell) = index of that source.  One such round reaches the reference loop's fixed point (numDisjointVoxels == 0).
+#include <algorithm>
+#include <vector>
+
+#include "tiles.cuh"
+
+using namespace vft;
+
+namespace {
+
+constexpr uint32_t KEY_WALL = 0xFFFFFFFFu, KEY_UNREACHED = 0xFFFFFFFEu;
+constexpr int KEY_SHIFT = 15;
+constexpr uint32_t KEY_LEVEL = 1u << KEY_SHIFT;
+constexpr uint32_t KEY_LIMIT = 0xFFFF0000u;  // keys at or above this cannot take another level (dist >= 2^17 - 2)
+constexpr uint32_t MARK = 0x8000u;           // reach marker = bit 15 of the label word (clear on entry by contract)
+
+enum { ST_VISITS = 0, ST_ROUNDS = 1, ST_ERROR = 2, ST_FREED = 3, ST_MAXDIST = 4 };
+enum { REACH_C1 = 0, REACH_F3 = 1 };
+
+constexpr size_t kSmemBytes = (size_t)(kCells + 3 * kThreads + 8) * sizeof(uint32_t);
+
+// ------------------------------------------------------------------------------------------------ key field set-up
+// phase 1: homogenize (FloodFracturer.cpp:99) folded in: EMPTY -> WALL, anything else -> UNREACHED.
+// phase 2: surviving words -> (0, order of their fragment's principal source); FREE -> UNREACHED.
+template <bool PHASE2>
+__global__ void __launch_bounds__(256) flood_init_keys_kernel(const uint16_t* __restrict__ grid, uint32_t* __restrict__ keys, TileGeom g,
+                                                              uint8_t* __restrict__ occ, const uint16_t* __restrict__ order_of_frag)
+{
+    const size_t n = (size_t)g.X * g.Y * g.Z;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t v = grid[i];
+        uint32_t k;
+        if (v == VF_VOXEL_EMPTY) k = KEY_WALL;
+        else if (!PHASE2 || v == VF_VOXEL_FREE) k = KEY_UNREACHED;
+        else k = order_of_frag[v & 0xFFu];
+        keys[i] = k;
+        if (v != VF_VOXEL_EMPTY) {
+            const int z = (int)(i % g.Z);
+            const size_t r = i / g.Z;
+            const int y = (int)(r % g.Y), x = (int)(r / g.Y);
+            const uint32_t tile = ((uint32_t)(x / TX) * g.nty + y / TY) * g.ntz + z / TZ;
+            if (!occ[tile]) occ[tile] = 1;
+        }
+    }
+}
+
+// FloodFracturer.cpp:102-103,127-132: seeds written in order (a later seed on the same cell overwrites), their cells pushed.
+__global__ void flood_seed_kernel(uint32_t* __restrict__ keys, TileGeom g, Worklist wl, const ushort4* __restrict__ seeds, int S, uint32_t round)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int s = 0; s < S; ++s) {
+        const ushort4 sd = seeds[s];
+        keys[((size_t)sd.x * g.Y + sd.y) * g.Z + sd.z] = (uint32_t)s;  // dist 0, order s
+        const uint32_t tile = ((uint32_t)(sd.x / TX) * g.nty + sd.y / TY) * g.ntz + sd.z / TZ;
+        wl.occ[tile] = 1;
+        enqueue_tile(wl, tile, round);
+    }
+}
+
+// phase 2 worklist: every tile that holds a freed (FREE) cell next to... simply every tile holding a FREE cell.
+__global__ void __launch_bounds__(256) enqueue_tiles_with_free_kernel(const uint16_t* __restrict__ grid, TileGeom g, Worklist wl, uint32_t round)
+{
+    const size_t n = (size_t)g.X * g.Y * g.Z;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (grid[i] != VF_VOXEL_FREE) continue;
+        const int z = (int)(i % g.Z);
+        const size_t r = i / g.Z;
+        const int y = (int)(r % g.Y), x = (int)(r / g.Y);
+        const uint32_t tile = ((uint32_t)(x / TX) * g.nty + y / TY) * g.ntz + z / TZ;
+        if (wl.stamp[tile] != round) enqueue_tile(wl, tile, round);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ tile load helpers
+template <int NNEIGH, typename T, typename LoadF>
+__device__ __forceinline__ void load_tile(uint32_t* sk, const T* __restrict__ src, const TileGeom& g, int gx0, int gy0, int gz0, uint32_t outside,
+                                          LoadF conv)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int row = warp; row < (TX + 2) * SY; row += kThreads / 32) {
+        const int x = row / SY - 1, y = row % SY - 1;
+        const int gx = gx0 + x, gy = gy0 + y;
+        bool rowin = gx >= 0 && gx < g.X && gy >= 0 && gy < g.Y;
+        if (NNEIGH == 6 && (x < 0 || x >= TX) && (y < 0 || y >= TY)) rowin = false;  // corner columns are never read
+        const T* base = src + ((size_t)(rowin ? gx : 0) * g.Y + (rowin ? gy : 0)) * g.Z;
+        const int gz = gz0 + lane;
+        sk[sidx(x, y, lane)] = (rowin && gz < g.Z) ? conv(base[gz]) : outside;
+        if (lane < 2) {
+            const int hz = lane ? gz0 + TZ : gz0 - 1;
+            sk[sidx(x, y, lane ? TZ : -1)] = (rowin && hz >= 0 && hz < g.Z) ? conv(base[hz]) : outside;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ F2: key relaxation round
+template <int NNEIGH>
+__global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __restrict__ keys, TileGeom g, Worklist wl, uint32_t round)
+{
+    extern __shared__ uint32_t sm[];
+    uint32_t* sk = sm;
+    uint32_t* act = sm + kCells;        // [2][kThreads] wavefront bitmasks, one word per z-row
+    uint32_t* chg = act + 2 * kThreads;  // [kThreads]    cells whose key was lowered during this visit
+    uint32_t* misc = chg + kThreads;     // [0..2] rotating wavefront population, [3] neighbour-tile mask
+
+    const uint32_t count = wl.count[round % 3];
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    if (blockIdx.x == 0 && t == 0) {
+        wl.count[(round + 2) % 3] = 0;
+        if (count) atomicAdd(&wl.stats[ST_ROUNDS], 1u);
+    }
+    for (uint32_t wi = blockIdx.x; wi < count; wi += gridDim.x) {
+        const uint32_t tile = wl.list[round & 1][wi];
+        const int tz = tile % g.ntz, ty = (tile / g.ntz) % g.nty, tx = tile / (g.ntz * g.nty);
+        const int gx0 = tx * TX, gy0 = ty * TY, gz0 = tz * TZ;
+
+        load_tile<NNEIGH>(sk, keys, g, gx0, gy0, gz0, KEY_WALL, [](uint32_t v) { return v; });
+        act[t] = 0, act[kThreads + t] = 0, chg[t] = 0;
+        if (t < 4) misc[t] = 0;
+        __syncthreads();
+
+        // ---- entry pass, warp per z-row, lane = z: repair every violated edge that ends in this tile; lowered cells form
+        //      the first wavefront (ballot -> one mask word per row)
+        {
+            unsigned lowered_total = 0;
+            bool overflow = false;
+            for (int r = warp * 32; r < warp * 32 + 32; ++r) {
+                const int x = r / TY, y = r % TY, z = lane;
+                const uint32_t v = sk[sidx(x, y, z)];
+                bool lowered = false;
+                if (v != KEY_WALL) {
+                    uint32_t m = KEY_WALL;
+                    if (NNEIGH == 6) {
+                        m = min(min(sk[sidx(x - 1, y, z)], sk[sidx(x + 1, y, z)]), min(sk[sidx(x, y - 1, z)], sk[sidx(x, y + 1, z)]));
+                        m = min(m, min(sk[sidx(x, y, z - 1)], sk[sidx(x, y, z + 1)]));
+                    } else {
+#pragma unroll
+                        for (int dx = -1; dx <= 1; ++dx)
+#pragma unroll
+                            for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                                for (int dz = -1; dz <= 1; ++dz)
+                                    if (dx | dy | dz) m = min(m, sk[sidx(x + dx, y + dy, z + dz)]);
+                    }
+                    if (m < KEY_LIMIT) {
+                        const uint32_t c = m + KEY_LEVEL;
+                        if (c < v) {
+                            sk[sidx(x, y, z)] = c;
+                            lowered = true;
+                        }
+                    } else if (m < KEY_UNREACHED) {
+                        overflow = true;
+                    }
+                }
+                const unsigned b = __ballot_sync(kFull, lowered);
+                if (lane == 0 && b) {
+                    act[r] = b;
+                    chg[r] = b;
+                    lowered_total += __popc(b);
+                }
+            }
+            if (lane == 0 && lowered_total) atomicAdd(&misc[0], lowered_total);
+            if (overflow) atomicOr(&wl.stats[ST_ERROR], 1u);
+        }
+        __syncthreads();
+
+        // ---- wavefront iterations in shared memory, thread per z-row; one barrier per step
+        for (int it = 0; it < TX * TY * TZ; ++it) {
+            if (misc[it % 3] == 0) break;
+            if (t == 0) misc[(it + 2) % 3] = 0;
+            const int cur = it & 1;
+            unsigned word = act[cur * kThreads + t];
+            act[cur * kThreads + t] = 0;
+            const int x = t / TY, y = t % TY;
+            uint32_t* nxt = act + (cur ^ 1) * kThreads;
+            while (word) {
+                const int z = __ffs(word) - 1;
+                word &= word - 1;
+                const uint32_t kv = sk[sidx(x, y, z)];
+                if (kv >= KEY_LIMIT) {
+                    atomicOr(&wl.stats[ST_ERROR], 1u);
+                    continue;
+                }
+                const uint32_t kb = kv + KEY_LEVEL;
+                auto relax = [&](int nx, int ny, int nz) {
+                    if (nx < 0 || nx >= TX || ny < 0 || ny >= TY || nz < 0 || nz >= TZ) return;  // halo cells belong to other tiles
+                    uint32_t* p = &sk[sidx(nx, ny, nz)];
+                    const uint32_t c = *p;
+                    if (c != KEY_WALL && kb < c) {
+                        const uint32_t old = atomicMin(p, kb);
+                        if (kb < old) {
+                            const int r2 = nx * TY + ny;
+                            const unsigned bit = 1u << nz;
+                            const unsigned o = atomicOr(&nxt[r2], bit);
+                            if (!(o & bit)) atomicAdd(&misc[(it + 1) % 3], 1u);
+                            atomicOr(&chg[r2], bit);
+                        }
+                    }
+                };
+                if (NNEIGH == 6) {
+                    relax(x - 1, y, z), relax(x + 1, y, z), relax(x, y - 1, z), relax(x, y + 1, z), relax(x, y, z - 1), relax(x, y, z + 1);
+                } else {
+#pragma unroll
+                    for (int dx = -1; dx <= 1; ++dx)
+#pragma unroll
+                        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                            for (int dz = -1; dz <= 1; ++dz)
+                                if (dx | dy | dz) relax(x + dx, y + dy, z + dz);
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- write back the rows that changed (warp per row: one 128-byte line), wake the neighbours that saw them change
+        for (int r = warp * 32; r < warp * 32 + 32; ++r) {
+            if (chg[r]) {
+                const int x = r / TY, y = r % TY, gz = gz0 + lane;
+                if (gz < g.Z && gx0 + x < g.X && gy0 + y < g.Y) keys[((size_t)(gx0 + x) * g.Y + gy0 + y) * g.Z + gz] = sk[sidx(x, y, lane)];
+            }
+        }
+        if (t == 0) atomicAdd(&wl.stats[ST_VISITS], 1u);
+        enqueue_neighbours<NNEIGH>(g, wl, tx, ty, tz, chg[t], &misc[3], round + 1);
+        __syncthreads();
+    }
+}
+
+// keys -> label words.  order -> seeds[order].w & mask; unreached non-empty cells stay FREE (never claimed in the reference).
+__global__ void __launch_bounds__(256) flood_finalize_kernel(const uint32_t* __restrict__ keys, uint16_t* __restrict__ grid, size_t n,
+                                                             const ushort4* __restrict__ seeds, uint32_t mask, uint32_t* __restrict__ stats)
+{
+    uint32_t maxd = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t k = keys[i];
+        uint16_t v;
+        if (k == KEY_WALL) v = VF_VOXEL_EMPTY;
+        else if (k == KEY_UNREACHED) v = VF_VOXEL_FREE;
+        else {
+            v = (uint16_t)(seeds[k & (KEY_LEVEL - 1)].w & mask);
+            maxd = max(maxd, k >> KEY_SHIFT);
+        }
+        grid[i] = v;
+    }
+    maxd = __reduce_max_sync(kFull, maxd);
+    if ((threadIdx.x & 31) == 0 && maxd) atomicMax(&stats[ST_MAXDIST], maxd);
+}
+
+// ------------------------------------------------------------------------------------------------ C1 / F3: reachability
+template <int MODE>
+__device__ __forceinline__ bool same_region(uint32_t a, uint32_t b)
+{
+    return MODE == REACH_C1 ? ((a ^ b) & 0x7FFFu) == 0 : ((a ^ b) & 0xFFu) == 0;
+}
+
+// start cells: C1 writes seed.w into the cell whatever it held (newGrid[seed] = seed.w, NaiveFracturer.cpp:120-123);
+// F3 marks the cell of each fragment's principal source.
+template <int MODE>
+__global__ void reach_seed_kernel(uint16_t* __restrict__ grid, TileGeom g, Worklist wl, const ushort4* __restrict__ starts, int S, uint32_t round)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int s = 0; s < S; ++s) {
+        const ushort4 sd = starts[s];
+        uint16_t* p = &grid[((size_t)sd.x * g.Y + sd.y) * g.Z + sd.z];
+        *p = MODE == REACH_C1 ? (uint16_t)(sd.w | MARK) : (uint16_t)(*p | MARK);
+        const uint32_t tile = ((uint32_t)(sd.x / TX) * g.nty + sd.y / TY) * g.ntz + sd.z / TZ;
+        wl.occ[tile] = 1;
+        enqueue_tile(wl, tile, round);
+    }
+}
+
+__global__ void __launch_bounds__(256) tile_occupancy_kernel(const uint16_t* __restrict__ grid, TileGeom g, uint8_t* __restrict__ occ)
+{
+    const size_t n = (size_t)g.X * g.Y * g.Z;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (grid[i] <= VF_VOXEL_FREE) continue;
+        const int z = (int)(i % g.Z);
+        const size_t r = i / g.Z;
+        const int y = (int)(r % g.Y), x = (int)(r / g.Y);
+        const uint32_t tile = ((uint32_t)(x / TX) * g.nty + y / TY) * g.ntz + z / TZ;
+        if (!occ[tile]) occ[tile] = 1;
+    }
+}
+
+template <int MODE, int NNEIGH>
+__global__ void __launch_bounds__(kThreads, 4) reach_round_kernel(uint16_t* __restrict__ grid, TileGeom g, Worklist wl, uint32_t round)
+{
+    extern __shared__ uint32_t sm[];
+    uint32_t* sw = sm;
+    uint32_t* act = sm + kCells;
+    uint32_t* chg = act + 2 * kThreads;
+    uint32_t* misc = chg + kThreads;
+
+    const uint32_t count = wl.count[round % 3];
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    if (blockIdx.x == 0 && t == 0) {
+        wl.count[(round + 2) % 3] = 0;
+        if (count) atomicAdd(&wl.stats[ST_ROUNDS], 1u);
+    }
+    for (uint32_t wi = blockIdx.x; wi < count; wi += gridDim.x) {
+        const uint32_t tile = wl.list[round & 1][wi];
+        const int tz = tile % g.ntz, ty = (tile / g.ntz) % g.nty, tx = tile / (g.ntz * g.nty);
+        const int gx0 = tx * TX, gy0 = ty * TY, gz0 = tz * TZ;
+
+        load_tile<NNEIGH>(sw, grid, g, gx0, gy0, gz0, 0u, [](uint16_t v) { return (uint32_t)v; });
+        act[t] = 0, act[kThreads + t] = 0, chg[t] = 0;
+        if (t < 4) misc[t] = 0;
+        __syncthreads();
+
+        // entry pass: an unmarked labelled cell next to a marked cell of its own region becomes marked
+        {
+            unsigned total = 0;
+            for (int r = warp * 32; r < warp * 32 + 32; ++r) {
+                const int x = r / TY, y = r % TY, z = lane;
+                const uint32_t v = sw[sidx(x, y, z)];
+                bool hit = false;
+                if ((v & 0x7FFFu) > VF_VOXEL_FREE && !(v & MARK)) {
+                    auto probe = [&](int nx, int ny, int nz) {
+                        const uint32_t u = sw[sidx(nx, ny, nz)];
+                        hit = hit || ((u & MARK) && same_region<MODE>(u, v));
+                    };
+                    if (NNEIGH == 6) {
+                        probe(x - 1, y, z), probe(x + 1, y, z), probe(x, y - 1, z), probe(x, y + 1, z), probe(x, y, z - 1), probe(x, y, z + 1);
+                    } else {
+#pragma unroll
+                        for (int dx = -1; dx <= 1; ++dx)
+#pragma unroll
+                            for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                                for (int dz = -1; dz <= 1; ++dz)
+                                    if (dx | dy | dz) probe(x + dx, y + dy, z + dz);
+                    }
+                    if (hit) sw[sidx(x, y, z)] = v | MARK;
+                }
+                const unsigned b = __ballot_sync(kFull, hit);
+                if (lane == 0 && b) {
+                    act[r] = b;
+                    chg[r] = b;
+                    total += __popc(b);
+                }
+            }
+            if (lane == 0 && total) atomicAdd(&misc[0], total);
+        }
+        __syncthreads();
+
+        for (int it = 0; it < TX * TY * TZ; ++it) {
+            if (misc[it % 3] == 0) break;
+            if (t == 0) misc[(it + 2) % 3] = 0;
+            const int cur = it & 1;
+            unsigned word = act[cur * kThreads + t];
+            act[cur * kThreads + t] = 0;
+            const int x = t / TY, y = t % TY;
+            uint32_t* nxt = act + (cur ^ 1) * kThreads;
+            while (word) {
+                const int z = __ffs(word) - 1;
+                word &= word - 1;
+                const uint32_t mine = sw[sidx(x, y, z)];
+                auto spread = [&](int nx, int ny, int nz) {
+                    if (nx < 0 || nx >= TX || ny < 0 || ny >= TY || nz < 0 || nz >= TZ) return;
+                    uint32_t* p = &sw[sidx(nx, ny, nz)];
+                    const uint32_t u = *p;
+                    if (!(u & MARK) && (u & 0x7FFFu) > VF_VOXEL_FREE && same_region<MODE>(u, mine)) {
+                        const uint32_t old = atomicOr(p, MARK);
+                        if (!(old & MARK)) {
+                            const int r2 = nx * TY + ny;
+                            atomicOr(&nxt[r2], 1u << nz);
+                            atomicOr(&chg[r2], 1u << nz);
+                            atomicAdd(&misc[(it + 1) % 3], 1u);
+                        }
+                    }
+                };
+                if (NNEIGH == 6) {
+                    spread(x - 1, y, z), spread(x + 1, y, z), spread(x, y - 1, z), spread(x, y + 1, z), spread(x, y, z - 1), spread(x, y, z + 1);
+                } else {
+#pragma unroll
+                    for (int dx = -1; dx <= 1; ++dx)
+#pragma unroll
+                        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                            for (int dz = -1; dz <= 1; ++dz)
+                                if (dx | dy | dz) spread(x + dx, y + dy, z + dz);
+                }
+            }
+            __syncthreads();
+        }
+
+        for (int r = warp * 32; r < warp * 32 + 32; ++r) {
+            if (chg[r]) {
+                const int x = r / TY, y = r % TY, gz = gz0 + lane;
+                if (gz < g.Z && gx0 + x < g.X && gy0 + y < g.Y) grid[((size_t)(gx0 + x) * g.Y + gy0 + y) * g.Z + gz] = (uint16_t)sw[sidx(x, y, lane)];
+            }
+        }
+        if (t == 0) atomicAdd(&wl.stats[ST_VISITS], 1u);
+        enqueue_neighbours<NNEIGH>(g, wl, tx, ty, tz, chg[t], &misc[3], round + 1);
+        __syncthreads();
+    }
+}
+
+// F3: unmarked labelled cells -> FREE (disjointSetStack-comp.glsl:27-31), counted.  C1: everything unmarked -> EMPTY, because the
+// reference rebuilds the grid from an all-EMPTY one (NaiveFracturer.cpp:115-116,149).  Marked cells lose the marker.
+template <int MODE>
+__global__ void __launch_bounds__(256) reach_prune_kernel(uint16_t* __restrict__ grid, size_t n, uint32_t* __restrict__ stats)
+{
+    unsigned freed = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint16_t v = grid[i];
+        if (v & MARK) {
+            grid[i] = v & 0x7FFFu;
+        } else if (MODE == REACH_C1) {
+            if (v != VF_VOXEL_EMPTY) {
+                grid[i] = VF_VOXEL_EMPTY;
+                ++freed;
+            }
+        } else if (v > VF_VOXEL_FREE) {
+            grid[i] = VF_VOXEL_FREE;
+            ++freed;
+        }
+    }
+    freed = __reduce_add_sync(kFull, freed);
+    if ((threadIdx.x & 31) == 0 && freed) atomicAdd(&stats[ST_FREED], freed);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct Job {
+    vf_ctx* c;
+    TileGeom g;
+    Worklist wl;
+    uint32_t round;       // next round id
+    uint32_t* h_mail;     // pinned mailbox
+    int blocks_stream;    // grid for streaming kernels
+    int blocks_tiles;     // grid for tile kernels
+};
+
+vf_status job_begin(vf_grid* grid, Job& j)
+{
+    vf_ctx* c = grid->ctx;
+    j.c = c;
+    j.g = make_geom(grid->X, grid->Y, grid->Z);
+    const size_t nt = (size_t)j.g.ntiles();
+    // layout: stats[8] count[3]+pad | list0 | list1 | stamp | occ
+    const size_t words = 16 + 3 * nt;
+    VF_TRY(vf_scratch_reserve(c, c->tiles, words * 4 + nt + 256));
+    uint32_t* base = (uint32_t*)c->tiles.ptr;
+    j.wl.stats = base;
+    j.wl.count = base + 8;
+    j.wl.list[0] = base + 16;
+    j.wl.list[1] = base + 16 + nt;
+    j.wl.stamp = base + 16 + 2 * nt;
+    j.wl.occ = (uint8_t*)(base + 16 + 3 * nt);
+    VF_CUDA(cudaMemsetAsync(base, 0, 16 * 4, c->stream));
+    VF_CUDA(cudaMemsetAsync(j.wl.stamp, 0, nt * 4 + nt, c->stream));
+    j.round = 1;
+    j.h_mail = (uint32_t*)((char*)c->pinned + 65536);  // upper half of the mailbox; the lower half carries seeds
+    j.blocks_stream = c->num_sms * 8;
+    j.blocks_tiles = c->num_sms * 4;
+    return VF_OK;
+}
+
+// run worklist rounds until the list for the next round is empty; `launch(round)` issues one round kernel
+template <typename LaunchF>
+vf_status run_rounds(Job& j, LaunchF launch)
+{
+    vf_ctx* c = j.c;
+    int batch = 4;
+    for (int guard = 0; guard < 100000; ++guard) {
+        for (int b = 0; b < batch; ++b) {
+            launch(j.round + b);
+            VF_LAUNCHED(c);
+        }
+        j.round += batch;
+        VF_CUDA(cudaMemcpyAsync(j.h_mail, j.wl.count + (j.round % 3), 4, cudaMemcpyDeviceToHost, c->stream));
+        VF_CUDA(cudaStreamSynchronize(c->stream));
+        if (j.h_mail[0] == 0) return VF_OK;
+        batch = std::min(batch * 2, 32);
+    }
+    return vf_set_error(VF_ERR_CAPACITY, "tile worklist did not drain");
+}
+
+vf_status read_stats(Job& j, uint32_t out[8])
+{
+    VF_CUDA(cudaMemcpyAsync(j.h_mail, j.wl.stats, 32, cudaMemcpyDeviceToHost, j.c->stream));
+    VF_CUDA(cudaStreamSynchronize(j.c->stream));
+    for (int i = 0; i < 8; ++i) out[i] = j.h_mail[i];
+    return VF_OK;
+}
+
+template <int NNEIGH>
+vf_status flood_phase(Job& j, uint32_t* keys)
+{
+    auto kern = flood_round_kernel<NNEIGH>;
+    VF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    return run_rounds(j, [&](uint32_t r) { kern<<<j.blocks_tiles, kThreads, kSmemBytes, j.c->stream>>>(keys, j.g, j.wl, r); });
+}
+
+template <int MODE, int NNEIGH>
+vf_status reach_phase(Job& j, uint16_t* grid)
+{
+    auto kern = reach_round_kernel<MODE, NNEIGH>;
+    VF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    return run_rounds(j, [&](uint32_t r) { kern<<<j.blocks_tiles, kThreads, kSmemBytes, j.c->stream>>>(grid, j.g, j.wl, r); });
+}
+
+}  // namespace
+
+extern "C" vf_status vf_fracture_flood(vf_grid* grid, const uint32_t* seeds, uint32_t nseeds, int dfunc, int id_bits, vf_flood_stats* stats_out)
+{
+    VF_REQUIRE(grid != nullptr, VF_ERR_INVALID_ARGUMENT, "null grid");
+    vf_ctx* c = grid->ctx;
+    VF_TRY(vf_enter(c));
+    VF_REQUIRE(dfunc >= 0 && dfunc <= 2, VF_ERR_INVALID_DISTANCE, "Invalid distance function %d", dfunc);
+    if (id_bits == 0) id_bits = 8;
+    VF_REQUIRE(id_bits == 8 || id_bits == 15, VF_ERR_INVALID_ARGUMENT, "id_bits must be 0/8 or 15");
+    VF_REQUIRE(nseeds >= 1 && nseeds < 32768 && nseeds <= 4096, VF_ERR_CAPACITY, "flood: seed count %u out of range [1, 4096]", nseeds);
+    const int nneigh = dfunc == VF_MANHATTAN ? 6 : 26;  // FloodFracturer.cpp:114
+    const size_t n = grid->n();
+
+    ushort4* d_seeds = nullptr;
+    VF_TRY(vf_upload_seeds(c, seeds, nseeds, grid->X, grid->Y, grid->Z, &d_seeds));
+    VF_TRY(vf_scratch_reserve(c, c->keys, n * 4));
+    uint32_t* keys = (uint32_t*)c->keys.ptr;
+    Job j;
+    VF_TRY(job_begin(grid, j));
+    vf_flood_stats st = { 0, 0, 0, 0, 0 };
+    uint32_t hs[8];
+
+    // F3 bookkeeping on the host: effective source per cell (later seed wins), principal (lowest-prefix) source per fragment id
+    bool prefixes = false;
+    std::vector<int> principal(256, -1);
+    if (id_bits == 8) {
+        std::vector<std::pair<uint64_t, int>> cells(nseeds);
+        for (uint32_t s = 0; s < nseeds; ++s) {
+            const uint64_t lin = ((uint64_t)seeds[4 * s] * grid->Y + seeds[4 * s + 1]) * grid->Z + seeds[4 * s + 2];
+            cells[s] = std::make_pair(lin, (int)s);
+        }
+        std::sort(cells.begin(), cells.end());
+        for (uint32_t i = 0; i < nseeds; ++i) {
+            if (i + 1 < nseeds && cells[i + 1].first == cells[i].first) continue;  // overwritten by a later seed on the same cell
+            const int s = cells[i].second;
+            const uint32_t w = seeds[4 * s + 3], frag = w & 0xFFu, pre = w >> VF_ID_POSITION;
+            if (pre) prefixes = true;
+            const int cur = principal[frag];
+            if (cur < 0 || pre < (seeds[4 * cur + 3] >> VF_ID_POSITION) || (pre == (seeds[4 * cur + 3] >> VF_ID_POSITION) && s < cur)) principal[frag] = s;
+        }
+    }
+
+    // ---- phase 1
+    flood_init_keys_kernel<false><<<j.blocks_stream, 256, 0, c->stream>>>(grid->d, keys, j.g, j.wl.occ, nullptr);
+    VF_LAUNCHED(c);
+    flood_seed_kernel<<<1, 32, 0, c->stream>>>(keys, j.g, j.wl, d_seeds, (int)nseeds, j.round);
+    VF_LAUNCHED(c);
+    VF_TRY(nneigh == 6 ? flood_phase<6>(j, keys) : flood_phase<26>(j, keys));
+    const bool need_f3 = id_bits == 8 && prefixes;
+    flood_finalize_kernel<<<j.blocks_stream, 256, 0, c->stream>>>(keys, grid->d, n, d_seeds, (id_bits == 8 && !need_f3) ? 0xFFu : 0xFFFFu, j.wl.stats);
+    VF_LAUNCHED(c);
+    st.disjoint_rounds = 1;
+
+    if (need_f3) {
+        // ---- disjoint step: keep the component of each fragment's principal source, free the rest
+        ushort4* h = (ushort4*)c->pinned;
+        uint16_t* h_order = (uint16_t*)(h + 256);
+        int nstart = 0;
+        VF_CUDA(cudaStreamSynchronize(c->stream));  // the mailbox still carries the seed upload
+        for (int f = 0; f < 256; ++f) {
+            h_order[f] = 0;
+            if (principal[f] < 0) continue;
+            const int s = principal[f];
+            h[nstart++] = make_ushort4((unsigned short)seeds[4 * s], (unsigned short)seeds[4 * s + 1], (unsigned short)seeds[4 * s + 2],
+                                       (unsigned short)seeds[4 * s + 3]);
+            h_order[f] = (uint16_t)s;
+        }
+        ushort4* d_starts = d_seeds + ((nseeds + 255) & ~255u);
+        uint16_t* d_order = (uint16_t*)(d_starts + 256);
+        VF_CUDA(cudaMemcpyAsync(d_starts, h, 256 * sizeof(ushort4) + 256 * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+        reach_seed_kernel<REACH_F3><<<1, 32, 0, c->stream>>>(grid->d, j.g, j.wl, d_starts, nstart, j.round);
+        VF_LAUNCHED(c);
+        VF_TRY(nneigh == 6 ? (reach_phase<REACH_F3, 6>(j, grid->d)) : (reach_phase<REACH_F3, 26>(j, grid->d)));
+        reach_prune_kernel<REACH_F3><<<j.blocks_stream, 256, 0, c->stream>>>(grid->d, n, j.wl.stats);
+        VF_LAUNCHED(c);
+        VF_TRY(read_stats(j, hs));
+        st.freed_voxels = hs[ST_FREED];
+        if (hs[ST_FREED] != 0) {
+            // ---- phase 2: re-flood from every labelled cell (FloodFracturer.cpp:135-177, second trip of the loop)
+            flood_init_keys_kernel<true><<<j.blocks_stream, 256, 0, c->stream>>>(grid->d, keys, j.g, j.wl.occ, d_order);
+            VF_LAUNCHED(c);
+            enqueue_tiles_with_free_kernel<<<j.blocks_stream, 256, 0, c->stream>>>(grid->d, j.g, j.wl, j.round);
+            VF_LAUNCHED(c);
+            VF_TRY(nneigh == 6 ? flood_phase<6>(j, keys) : flood_phase<26>(j, keys));
+            flood_finalize_kernel<<<j.blocks_stream, 256, 0, c->stream>>>(keys, grid->d, n, d_seeds, 0xFFu, j.wl.stats);
+            VF_LAUNCHED(c);
+            st.disjoint_rounds = 2;
+        } else {
+            VF_TRY(vf_k_pointwise(grid, VF_PW_RIGHTMOST8));  // FloodFracturer.cpp:180-186
+        }
+    }
+    VF_TRY(read_stats(j, hs));
+    VF_REQUIRE(hs[ST_ERROR] == 0, VF_ERR_CAPACITY, "flood: geodesic distance exceeds the 17-bit key field");
+    st.tile_visits = hs[ST_VISITS];
+    st.tile_rounds = hs[ST_ROUNDS];
+    st.max_dist = hs[ST_MAXDIST];
+    if (stats_out) *stats_out = st;
+    return VF_OK;
+}
+
+extern "C" vf_status vf_remove_isolated_regions(vf_grid* grid, const uint32_t* seeds, uint32_t nseeds)
+{
+    VF_REQUIRE(grid != nullptr, VF_ERR_INVALID_ARGUMENT, "null grid");
+    vf_ctx* c = grid->ctx;
+    VF_TRY(vf_enter(c));
+    ushort4* d_seeds = nullptr;
+    VF_TRY(vf_upload_seeds(c, seeds, nseeds, grid->X, grid->Y, grid->Z, &d_seeds));
+    Job j;
+    VF_TRY(job_begin(grid, j));
+    tile_occupancy_kernel<<<j.blocks_stream, 256, 0, c->stream>>>(grid->d, j.g, j.wl.occ);
+    VF_LAUNCHED(c);
+    reach_seed_kernel<REACH_C1><<<1, 32, 0, c->stream>>>(grid->d, j.g, j.wl, d_seeds, (int)nseeds, j.round);
+    VF_LAUNCHED(c);
+    VF_TRY((reach_phase<REACH_C1, 6>(j, grid->d)));
+    reach_prune_kernel<REACH_C1><<<j.blocks_stream, 256, 0, c->stream>>>(grid->d, grid->n(), j.wl.stats);
+    VF_LAUNCHED(c);
+    return VF_OK;
+}

@@ -190,26 +190,58 @@ naive_brick_kernel(uint16_t* __restrict__ grid, int X, int Y, int Z, const ushor
             const int x = x0 + it;
             unsigned short lab[VEC];
             if (C <= kCMax) {
+                // For EUCLIDEAN and MANHATTAN the difference of two seeds' distances along an axis-parallel line is monotone,
+                // so the set of z where one seed is the (lowest-index) winner is an interval: when both ends of the chunk have
+                // the same winner the whole chunk has it, and only chunks that straddle a cell boundary evaluate every voxel.
+                // (Not true for CHEBYSHEV: max(c, |dz|) plateaus let a lower-index seed win two disjoint tie ranges.)
                 unsigned key[VEC];
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) key[k] = 0xFFFFFFFFu;
-                for (int slot = 0; slot < C; ++slot) {
-                    const ushort4 sd = cand[slot];
-                    const int dx = x - (int)sd.x, dy = y - (int)sd.y;
-                    if (DF == VF_EUCLIDEAN) {
-                        const unsigned base = ((unsigned)(dx * dx + dy * dy) << 8) | (unsigned)slot;
-                        const int zs = (z - (int)sd.z) * 16;  // (16*dz)^2 = dz^2 << 8
-#pragma unroll
-                        for (int k = 0; k < VEC; ++k) {
-                            const int dzs = zs + 16 * k;
-                            key[k] = min(key[k], base + (unsigned)(dzs * dzs));
+                if (DF != VF_CHEBYSHEV) {
+                    unsigned k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu;
+                    for (int slot = 0; slot < C; ++slot) {
+                        const ushort4 sd = cand[slot];
+                        const int dx = x - (int)sd.x, dy = y - (int)sd.y;
+                        if (DF == VF_EUCLIDEAN) {
+                            const unsigned base = ((unsigned)(dx * dx + dy * dy) << 8) | (unsigned)slot;
+                            const int zs = (z - (int)sd.z) * 16, ze = zs + 16 * (VEC - 1);
+                            k0 = min(k0, base + (unsigned)(zs * zs));
+                            k1 = min(k1, base + (unsigned)(ze * ze));
+                        } else {
+                            const unsigned base = ((unsigned)(iabs(dx) + iabs(dy)) << 8) | (unsigned)slot;
+                            const int zs = (z - (int)sd.z) * 256;
+                            k0 = min(k0, base + (unsigned)iabs(zs));
+                            k1 = min(k1, base + (unsigned)iabs(zs + 256 * (VEC - 1)));
                         }
-                    } else if (DF == VF_MANHATTAN) {
-                        const unsigned base = ((unsigned)(iabs(dx) + iabs(dy)) << 8) | (unsigned)slot;
-                        const int zs = (z - (int)sd.z) * 256;
+                    }
+                    if ((k0 & 0xFFu) == (k1 & 0xFFu)) {
 #pragma unroll
-                        for (int k = 0; k < VEC; ++k) key[k] = min(key[k], base + (unsigned)iabs(zs + 256 * k));
+                        for (int k = 0; k < VEC; ++k) key[k] = k0;
                     } else {
+                        key[0] = k0, key[VEC - 1] = k1;
+                        for (int slot = 0; slot < C; ++slot) {
+                            const ushort4 sd = cand[slot];
+                            const int dx = x - (int)sd.x, dy = y - (int)sd.y;
+                            if (DF == VF_EUCLIDEAN) {
+                                const unsigned base = ((unsigned)(dx * dx + dy * dy) << 8) | (unsigned)slot;
+                                const int zs = (z - (int)sd.z) * 16;  // (16*dz)^2 = dz^2 << 8
+#pragma unroll
+                                for (int k = 1; k < VEC - 1; ++k) {
+                                    const int dzs = zs + 16 * k;
+                                    key[k] = min(key[k], base + (unsigned)(dzs * dzs));
+                                }
+                            } else {
+                                const unsigned base = ((unsigned)(iabs(dx) + iabs(dy)) << 8) | (unsigned)slot;
+                                const int zs = (z - (int)sd.z) * 256;
+#pragma unroll
+                                for (int k = 1; k < VEC - 1; ++k) key[k] = min(key[k], base + (unsigned)iabs(zs + 256 * k));
+                            }
+                        }
+                    }
+                } else {
+                    for (int slot = 0; slot < C; ++slot) {
+                        const ushort4 sd = cand[slot];
+                        const int dx = x - (int)sd.x, dy = y - (int)sd.y;
                         const unsigned base = ((unsigned)max(iabs(dx), iabs(dy)) << 8) | (unsigned)slot;
                         const int zs = (z - (int)sd.z) * 256;
 #pragma unroll

@@ -8,8 +8,6 @@ VF_STUB(vf_voxelize, vf_grid*, const float*, uint32_t, const uint32_t*, uint32_t
 VF_STUB(vf_seed_uniform, vf_grid*, uint32_t, int, int, uint32_t*, uint32_t*)
 VF_STUB(vf_merge_seeds, const uint32_t*, uint32_t, uint32_t*, uint32_t, int)
 VF_STUB(vf_make_seeds, vf_grid*, uint32_t, uint32_t, int, int, uint32_t*, uint32_t, uint32_t*)
-VF_STUB(vf_fracture_flood, vf_grid*, const uint32_t*, uint32_t, int, int, vf_flood_stats*)
-VF_STUB(vf_remove_isolated_regions, vf_grid*, const uint32_t*, uint32_t)
 VF_STUB(vf_detect_boundaries, vf_grid*, int)
 VF_STUB(vf_erode, vf_grid*, int, uint32_t, uint32_t, float, float, const float*, uint32_t, int)
 VF_STUB(vf_remove_isolated_regions_grid, vf_grid*)
