@@ -93,3 +93,36 @@ def test_rng_stream_matches_oracle(orc):
     # the RNG lives in a context, which needs a device; exercise the recipe through the noise filler when possible
     if vf._capi.load().vf_device_count() == 0:
         pytest.skip("context creation needs a device; covered by the gpu suite")
+
+
+def test_host_encoders_reproduce_reference_rle_bytes(golden_rle_bytes, orc):
+    """vf_encode_rle / vf_encode_bing_squared are host code: checked on CPU against the reference's own .rle fixture."""
+    import numpy as np
+
+    import voxelfragmentml_b200 as vf
+
+    lib = vf._capi.load()
+    grid = orc.decode_rle(golden_rle_bytes)
+    dims = np.asarray(grid.shape, np.uint32)
+    need = lib.vf_encode_rle(grid.ctypes.data, dims.ctypes.data, None, 0)
+    assert need == len(golden_rle_bytes)
+    buf = np.zeros(need, np.uint8)
+    lib.vf_encode_rle(grid.ctypes.data, dims.ctypes.data, buf.ctypes.data, need)
+    assert buf.tobytes() == golden_rle_bytes
+    need = lib.vf_encode_bing_squared(grid.ctypes.data, dims.ctypes.data, None, 0)
+    buf = np.zeros(need, np.uint8)
+    lib.vf_encode_bing_squared(grid.ctypes.data, dims.ctypes.data, buf.ctypes.data, need)
+    assert buf.tobytes() == orc.encode_bing_squared(grid)
+
+
+def test_merge_seeds_host_matches_oracle(orc):
+    import numpy as np
+
+    import voxelfragmentml_b200 as vf
+
+    rs = np.random.RandomState(3)
+    for dfunc in (0, 1, 2):
+        frags = np.concatenate([rs.randint(0, 60, size=(7, 3)), np.arange(2, 9)[:, None]], 1).astype(np.uint32)
+        extra = np.concatenate([rs.randint(0, 60, size=(20, 3)), np.zeros((20, 1), int)], 1).astype(np.uint32)
+        seeds = np.concatenate([frags, extra])
+        assert np.array_equal(vf.Seeder.mergeSeeds(frags, seeds, dfunc), orc.merge_seeds(frags, seeds, dfunc))

@@ -1,0 +1,214 @@
+"""C2-C4 / H1 / S1-S2 / X1 / fractureModel parity on the GPU against the oracle (bit-exact)."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from conftest import pick_seeds, random_blob_grid
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import voxelfragmentml_b200 as vf
+
+    c = vf.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def labelled_vessel(orc, vessel_grid):
+    seeds, _ = orc.seed_uniform(orc.Rng(80), vessel_grid, 8)
+    return orc.naive(vessel_grid.copy(), seeds, 0), seeds
+
+
+def _grid(ctx, host):
+    import voxelfragmentml_b200 as vf
+
+    g = vf.RegularGrid(ctx, host.shape)
+    g.updateSSBO(host)
+    return g
+
+
+def test_detect_boundaries_twice_and_undo_mask(ctx, orc, labelled_vessel):
+    lab, _ = labelled_vessel
+    g = _grid(ctx, lab)
+    g.detectBoundaries(1)
+    want = orc.detect_boundaries(lab.copy(), 1)
+    got = g.updateGrid()
+    assert np.array_equal(got, want) and (got & 0x8000).any()
+    g.detectBoundaries(1)  # erode re-applies it without undoMask (RegularGrid.cpp:133-135)
+    assert np.array_equal(g.updateGrid(), orc.detect_boundaries(want.copy(), 1))
+    g.undoMask()
+    assert np.array_equal(g.updateGrid(), lab)
+    g.close()
+
+
+@pytest.mark.parametrize("shape", [(19, 23, 70), (8, 8, 64), (9, 17, 65), (3, 2, 5)])
+def test_detect_boundaries_ragged(ctx, orc, shape):
+    g0 = random_blob_grid(shape, 1, fill=0.6, smooth=0)
+    lab = orc.naive(g0.copy(), pick_seeds(g0, min(5, int((g0 != 0).sum())), 3), 1)
+    g = _grid(ctx, lab)
+    g.detectBoundaries(1)
+    assert np.array_equal(g.updateGrid(), orc.detect_boundaries(lab.copy(), 1))
+    g.close()
+
+
+@pytest.mark.parametrize("etype,size,iters,mode", [(1, 3, 3, 0), (2, 3, 3, 0), (0, 3, 2, 0), (1, 3, 1, 1), (1, 5, 2, 0), (0, 4, 1, 0), (1, 3, 0, 0)])
+def test_erode(ctx, orc, labelled_vessel, etype, size, iters, mode):
+    lab, _ = labelled_vessel
+    noise = orc.Rng(80).fill_noise(100003)
+    want = orc.erode(lab.copy(), noise, etype, size, iters, 0.5, 0.5, boundary_mode=mode)
+    g = _grid(ctx, lab)
+    g.erode(etype, size, iters, 0.5, 0.5, noise=noise, boundaryMode=mode)
+    got = g.updateGrid()
+    assert np.array_equal(got, want)
+    if iters and mode == 0:
+        assert (got != lab).any()
+    g.close()
+
+
+def test_erode_probability_threshold_variants(ctx, orc):
+    g0 = random_blob_grid((30, 26, 70), 8, fill=0.55, smooth=1)
+    lab = orc.naive(g0.copy(), pick_seeds(g0, 6, 1), 0)
+    noise = orc.Rng(5).fill_noise(4099)
+    for prob, thr in [(0.1, 0.9), (1.0, 0.3), (0.7, 0.7)]:
+        want = orc.erode(lab.copy(), noise, 1, 3, 3, prob, thr)
+        g = _grid(ctx, lab)
+        g.erode(1, 3, 3, prob, thr, noise=noise)
+        assert np.array_equal(g.updateGrid(), want)
+        g.close()
+
+
+def test_remove_isolated_regions_grid(ctx, orc, labelled_vessel):
+    lab, _ = labelled_vessel
+    speck = lab.copy()
+    speck[::7, ::5, ::3] = 9  # isolated voxels of a foreign label
+    g = _grid(ctx, speck)
+    g.removeIsolatedRegions()
+    assert np.array_equal(g.updateGrid(), orc.remove_isolated_regions_grid(speck.copy()))
+    g.close()
+
+
+def test_pointwise_passes(ctx, orc):
+    rs = np.random.RandomState(0)
+    host = rs.randint(0, 65536, size=(7, 9, 13)).astype(np.uint16)  # 819 cells: exercises the vector tail
+    for name, fn in [("undoMask", lambda a: orc.undo_mask(a, 15, False)), ("resetFilling", orc.reset_filling), ("homogenize", orc.homogenize)]:
+        g = _grid(ctx, host)
+        getattr(g, name)()
+        assert np.array_equal(g.updateGrid(), fn(host.copy())), name
+        g.close()
+
+
+def test_histogram(ctx, orc, labelled_vessel):
+    lab, _ = labelled_vessel
+    tagged = orc.detect_boundaries(lab.copy(), 1)
+    for host in (lab, tagged):
+        g = _grid(ctx, host)
+        counts, occ = g.countValues()
+        wc, wo = orc.count_values(host)
+        assert occ == wo and np.array_equal(counts, wc)
+        assert g.numOccupiedVoxels() == wo
+        g.close()
+    big = (np.random.RandomState(1).randint(0, 20000, size=(31, 17, 9)).astype(np.uint16))  # ids beyond the shared-memory bins
+    g = _grid(ctx, big)
+    counts, occ = g.countValues()
+    wc, wo = orc.count_values(big)
+    assert occ == wo and np.array_equal(counts, wc)
+    g.close()
+
+
+def test_rng_stream_and_noise(ctx, orc):
+    ctx.initSeed(80)
+    r = orc.Rng(80)
+    assert [ctx.rng_raw() for _ in range(1000)] == [r.raw() for _ in range(1000)]
+    assert [ctx.getUniformRandom() for _ in range(1000)] == [r.uniform() for _ in range(1000)]
+    ctx.initSeed(7)
+    assert np.array_equal(ctx.fillNoiseBuffer(5000), orc.Rng(7).fill_noise(5000))
+
+
+@pytest.mark.parametrize("location", [0, 1, 2])
+def test_seed_uniform_matches_reference_stream(ctx, orc, vessel_grid, location):
+    import voxelfragmentml_b200 as vf
+
+    g = _grid(ctx, vessel_grid)
+    for n in (1, 8, 64):
+        ctx.initSeed(80 + n)
+        r = orc.Rng(80 + n)
+        got, att = vf.Seeder.uniform(g, n, location=location, return_attempts=True)
+        want, watt = orc.seed_uniform(r, vessel_grid, n, location=location)
+        assert np.array_equal(got, want) and att == watt
+        assert ctx.rng_raw() == r.raw()  # generator left exactly where the reference's would be
+    g.close()
+
+
+def test_make_seeds_with_extras_and_exhaustion(ctx, orc, vessel_grid):
+    import voxelfragmentml_b200 as vf
+
+    g = _grid(ctx, vessel_grid)
+    for n, ne, md in [(8, 16, 0), (3, 6, 1), (10, 20, 2)]:
+        ctx.initSeed(123)
+        got = vf.Seeder.make(g, n, ne, mergeDFunc=md)
+        want = orc.make_seeds(orc.Rng(123), vessel_grid, n, ne, merge_dfunc=md)
+        assert np.array_equal(got, want)
+    g.close()
+    empty = vf.RegularGrid(ctx, (16, 16, 16))
+    with pytest.raises(vf.SeederSearchError):
+        vf.Seeder.uniform(empty, 1)
+    empty.close()
+    with pytest.raises(vf.VoxFragError) as e:
+        vf.Seeder.uniform(_grid(ctx, vessel_grid), 2, randomSeedFunction=vf.RandomUniformType.HALTON)
+    assert e.value.status == 7
+
+
+def test_fracture_model_flood_defaults(ctx, orc, vessel_grid):
+    """CADScene::fractureModel with the reference defaults: FLOOD + CHEBYSHEV, 8 seeds + 16 extra, detectBoundaries(1)."""
+    import voxelfragmentml_b200 as vf
+
+    p = vf.FractureParameters()
+    g = _grid(ctx, vessel_grid)
+    ctx.initSeed(p._seed)
+    seeds, st = vf.fracture_model(g, p)
+    r = orc.Rng(80)
+    wseeds = orc.make_seeds(r, vessel_grid, 8, 16, merge_dfunc=0)
+    assert np.array_equal(seeds, wseeds)
+    want, wst = orc.flood(vessel_grid.copy(), wseeds, orc.CHEBYSHEV)
+    want = orc.detect_boundaries(want, 1)
+    assert np.array_equal(g.updateGrid(), want)
+    assert st.disjoint_rounds == wst.rounds
+    g.close()
+
+
+def test_fracture_model_naive_erode(ctx, orc, vessel_grid):
+    import voxelfragmentml_b200 as vf
+
+    p = vf.FractureParameters(_fractureAlgorithm=vf.FractureAlgorithm.NAIVE, _distanceFunction=vf.DistanceFunction.EUCLIDEAN, _numSeeds=6,
+                              _numExtraSeeds=0, _erode=1)
+    g = _grid(ctx, vessel_grid)
+    ctx.initSeed(80)
+    seeds, _ = vf.fracture_model(g, p)
+    r = orc.Rng(80)
+    wseeds = orc.make_seeds(r, vessel_grid, 6, 0)
+    want = orc.naive(vessel_grid.copy(), wseeds, 0)
+    want = orc.remove_isolated_regions_cpu(want, wseeds)
+    want = orc.erode(want, r.fill_noise(1000000), 1, 3, 3, 0.5, 0.5)
+    assert np.array_equal(seeds, wseeds) and np.array_equal(g.updateGrid(), want)
+    g.close()
+
+
+def test_export_rle_and_bing(ctx, orc, labelled_vessel, tmp_path):
+    import voxelfragmentml_b200 as vf
+
+    lab, _ = labelled_vessel
+    g = _grid(ctx, lab)
+    base = str(tmp_path / "AL_12B_8f_128r_0it")
+    g.exportGrid(base, True, vf.ExportGrid.RLE)
+    assert open(base + ".rle", "rb").read() == orc.encode_rle(lab)
+    g.exportGrid(base, True, vf.ExportGrid.UNCOMPRESSED_BINARY)
+    assert open(base + ".bing", "rb").read() == orc.encode_bing_squared(lab)
+    with pytest.raises(vf.VoxFragError):
+        g.exportGrid(base, True, vf.ExportGrid.QUADSTACK)
+    g.close()

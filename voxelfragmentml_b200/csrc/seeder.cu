@@ -1,0 +1,190 @@
+// seeder.cu — S1/S2 seed placement and the caller's block CADScene::fractureModel.
+//
+// Replaces fracturer::Seeder::uniform / mergeSeeds (SRC/Fracturer/Seeder.cpp:154-208, 115-152) and the seed + build + cleanup
+// sequence of CADScene::fractureModel (SRC/Graphics/Application/CADScene.cpp:624-691).
+//
+// The reference samples on the host against the host copy of the grid, which forces a full-grid readback after voxelization.
+// Here the grid stays on the device: the host draws candidate cells in exactly the reference's order (three draws per attempt,
+// consumed even when rejected), a small kernel evaluates isOccupied / isBoundary (RegularGrid.cpp:543-564) for a batch of
+// candidates, and the host replays the acceptance rule on the flags.  When the n-th seed is found mid-batch the generator is
+// rewound to the state the reference's would have, so everything drawn afterwards (extra seeds, erosion noise) matches.
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <set>
+#include <vector>
+
+#include "vf_internal.h"
+
+namespace {
+
+constexpr int kBatch = 4096;
+constexpr uint32_t kMaxTries = 1000000;  // Seeder.h:48
+
+__global__ void __launch_bounds__(128) seed_probe_kernel(const uint16_t* __restrict__ grid, int X, int Y, int Z, const ushort4* __restrict__ cand,
+                                                         int n, uint8_t* __restrict__ flags)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ushort4 c = cand[i];
+    const int x = c.x, y = c.y, z = c.z;
+    const bool occupied = grid[((size_t)x * Y + y) * Z + z] != VF_VOXEL_EMPTY;  // RegularGrid.cpp:561-564
+    bool boundary = false;                                                      // RegularGrid.cpp:543-559, neighbourhoodSize 1
+    const int x0 = max(x - 1, 0), x1 = min(x + 1, X - 1), y0 = max(y - 1, 0), y1 = min(y + 1, Y - 1), z0 = max(z - 1, 0), z1 = min(z + 1, Z - 1);
+    for (int a = x0; a <= x1; ++a)
+        for (int b = y0; b <= y1; ++b)
+            for (int d = z0; d <= z1; ++d) boundary = boundary || grid[((size_t)a * Y + b) * Z + d] == VF_VOXEL_EMPTY;
+    flags[i] = (occupied ? 1 : 0) | (boundary ? 2 : 0);
+}
+
+struct U3 {
+    uint32_t x, y, z;
+    bool operator<(const U3& r) const
+    {
+        if (x != r.x) return x < r.x;
+        if (y != r.y) return y < r.y;
+        return z < r.z;
+    }
+};
+
+}  // namespace
+
+extern "C" vf_status vf_seed_uniform(vf_grid* g, uint32_t n, int random_mode, int location, uint32_t* out, uint32_t* attempts_out)
+{
+    VF_REQUIRE(g != nullptr && out != nullptr, VF_ERR_INVALID_ARGUMENT, "null argument");
+    vf_ctx* c = g->ctx;
+    VF_TRY(vf_enter(c));
+    VF_REQUIRE(random_mode == VF_STD_UNIFORM, VF_ERR_UNSUPPORTED,
+               "seeding mode %d: only STD_UNIFORM is implemented (HALTON / BOOST_NORMAL are parity-unpinned, SURVEY §8a S3)", random_mode);
+    VF_REQUIRE(location >= 0 && location <= 2, VF_ERR_INVALID_ARGUMENT, "bad seed location %d", location);
+    VF_REQUIRE(g->X >= 2 && g->Y >= 2 && g->Z >= 2, VF_ERR_INVALID_ARGUMENT, "grid too small to seed");
+    VF_TRY(vf_scratch_reserve(c, c->small, 1 << 20));
+    ushort4* d_cand = (ushort4*)((char*)c->small.ptr + (768 << 10));
+    uint8_t* d_flags = (uint8_t*)(d_cand + kBatch);
+    ushort4* h_cand = (ushort4*)c->pinned;
+    uint8_t* h_flags = (uint8_t*)c->pinned + 65536;
+
+    std::set<U3> seeds;  // Seeder.cpp:163 std::set with the lexicographic comparator
+    const int ndx = (int)g->X - 2, ndy = (int)g->Y - 2, ndz = (int)g->Z - 2;  // :165
+    uint32_t attempt = 0;
+    while (seeds.size() != n) {
+        VF_CUDA(cudaStreamSynchronize(c->stream));  // the pinned staging areas may still be in flight
+        const VfMt19937 saved = c->rng;
+        const int batch = (int)std::min<uint32_t>(kBatch, kMaxTries - attempt);
+        if (batch == 0) {
+            if (attempts_out) *attempts_out = attempt;
+            return vf_set_error(VF_ERR_SEEDER_EXHAUSTED, "Max. number of tries surpassed (%u)", kMaxTries);  // :173-174
+        }
+        for (int i = 0; i < batch; ++i) {  // :177-179
+            const int x = c->rng.uniform_int(0, ndx + 1), y = c->rng.uniform_int(0, ndy + 1), z = c->rng.uniform_int(0, ndz + 1);
+            h_cand[i] = make_ushort4((unsigned short)x, (unsigned short)y, (unsigned short)z, 0);
+        }
+        VF_CUDA(cudaMemcpyAsync(d_cand, h_cand, batch * sizeof(ushort4), cudaMemcpyHostToDevice, c->stream));
+        seed_probe_kernel<<<(batch + 127) / 128, 128, 0, c->stream>>>(g->d, (int)g->X, (int)g->Y, (int)g->Z, d_cand, batch, d_flags);
+        VF_LAUNCHED(c);
+        VF_CUDA(cudaMemcpyAsync(h_flags, d_flags, batch, cudaMemcpyDeviceToHost, c->stream));
+        VF_CUDA(cudaStreamSynchronize(c->stream));
+        int used = batch;
+        for (int i = 0; i < batch; ++i) {
+            const U3 v = { h_cand[i].x, h_cand[i].y, h_cand[i].z };
+            const bool occupied = h_flags[i] & 1, boundary = h_flags[i] & 2;
+            const bool isFree = seeds.find(v) == seeds.end();
+            if (occupied && isFree)
+                if ((location == VF_OUTER && boundary) || (location == VF_INNER && !boundary) || location == VF_BOTH) seeds.insert(v);  // :190-192
+            if (seeds.size() == n) {
+                used = i + 1;
+                break;
+            }
+        }
+        attempt += used;
+        if (used != batch) {  // rewind to the reference's RNG position: exactly 3 draws per attempt
+            c->rng = saved;
+            for (int i = 0; i < 3 * used; ++i) c->rng.next();
+        }
+    }
+    uint32_t label = VF_VOXEL_FREE + 1, k = 0;  // :202
+    for (const U3& s : seeds) {
+        out[4 * k] = s.x, out[4 * k + 1] = s.y, out[4 * k + 2] = s.z, out[4 * k + 3] = label++;
+        ++k;
+    }
+    if (attempts_out) *attempts_out = attempt;
+    return VF_OK;
+}
+
+extern "C" vf_status vf_merge_seeds(const uint32_t* frags, uint32_t nfrags, uint32_t* seeds, uint32_t nseeds, int dfunc)
+{
+    // Seeder.cpp:115-152, float32 distances on integer coordinates, strict '<' (lowest fragment index wins ties)
+    VF_REQUIRE(frags && seeds && nfrags > 0, VF_ERR_INVALID_ARGUMENT, "mergeSeeds: null or empty input");
+    VF_REQUIRE(dfunc >= 0 && dfunc <= 2, VF_ERR_INVALID_DISTANCE, "Invalid distance function %d", dfunc);
+    int idFragment[1 << VF_ID_POSITION];
+    std::memset(idFragment, 0, sizeof(idFragment));
+    for (uint32_t si = 0; si < nseeds; ++si) {
+        uint32_t* seed = seeds + 4 * si;
+        float mn = FLT_MAX;
+        int nearest = -1;
+        for (uint32_t i = 0; i < nfrags; ++i) {
+            const float dx = (float)seed[0] - (float)frags[4 * i], dy = (float)seed[1] - (float)frags[4 * i + 1], dz = (float)seed[2] - (float)frags[4 * i + 2];
+            float dist;
+            if (dfunc == VF_EUCLIDEAN) dist = sqrtf(dx * dx + dy * dy + dz * dz);
+            else if (dfunc == VF_MANHATTAN) dist = fabsf(dx) + fabsf(dy) + fabsf(dz);
+            else dist = fmaxf(fabsf(dx), fmaxf(fabsf(dy), fabsf(dz)));
+            if (dist < mn) mn = dist, nearest = (int)i;
+        }
+        const uint32_t fw = frags[4 * nearest + 3];
+        seed[3] = fw | ((uint32_t)(++idFragment[fw & 0xFFu]) << VF_ID_POSITION);  // :150
+    }
+    return VF_OK;
+}
+
+extern "C" vf_status vf_make_seeds(vf_grid* g, uint32_t n, uint32_t n_extra, int random_mode, int merge_dfunc, uint32_t* out, uint32_t cap,
+                                   uint32_t* count_out)
+{
+    // CADScene.cpp:626-655, numImpacts == 0 branch
+    VF_REQUIRE(g && out && count_out, VF_ERR_INVALID_ARGUMENT, "null argument");
+    const uint32_t total = n + (n_extra ? n + n_extra : 0);
+    VF_REQUIRE(total <= cap, VF_ERR_CAPACITY, "seed buffer too small (%u < %u)", cap, total);
+    VF_TRY(vf_seed_uniform(g, n, random_mode, VF_OUTER, out, nullptr));
+    if (n_extra > 0) {
+        std::vector<uint32_t> extra(4 * (size_t)(n + n_extra));
+        VF_TRY(vf_seed_uniform(g, n_extra, random_mode, VF_BOTH, extra.data() + 4 * n, nullptr));
+        std::memcpy(extra.data(), out, 16 * (size_t)n);                              // :651
+        VF_TRY(vf_merge_seeds(out, n, extra.data(), n + n_extra, merge_dfunc));       // :653
+        std::memcpy(out + 4 * (size_t)n, extra.data(), 16 * (size_t)(n + n_extra));  // :654
+    }
+    *count_out = total;
+    return VF_OK;
+}
+
+extern "C" vf_status vf_fracture_model(vf_grid* g, const vf_params* p, uint32_t* seeds_out, uint32_t* nseeds_out, vf_flood_stats* stats)
+{
+    VF_REQUIRE(g && p, VF_ERR_INVALID_ARGUMENT, "null argument");
+    vf_ctx* c = g->ctx;
+    VF_TRY(vf_enter(c));
+    VF_REQUIRE(p->numImpacts == 0, VF_ERR_UNSUPPORTED, "nearSeeds (numImpacts > 0) uses C rand(): parity-unpinned, not implemented (SURVEY §8a S3)");
+    VF_REQUIRE(p->numSeeds > 0 && p->numExtraSeeds >= 0, VF_ERR_INVALID_ARGUMENT, "bad seed counts");
+    const uint32_t cap = (uint32_t)p->numSeeds * 2 + (uint32_t)p->numExtraSeeds;
+    std::vector<uint32_t> seeds(4 * (size_t)cap);
+    uint32_t ns = 0;
+    VF_TRY(vf_make_seeds(g, (uint32_t)p->numSeeds, (uint32_t)p->numExtraSeeds, p->seedingRandom, p->mergeSeedsDistanceFunction, seeds.data(), cap, &ns));
+    if (p->fractureAlgorithm == VF_NAIVE) {
+        VF_REQUIRE(p->distanceFunction >= 0 && p->distanceFunction <= 2, VF_ERR_INVALID_DISTANCE, "Invalid distance function");  // CADScene.cpp:665
+        VF_TRY(vf_fracture_naive(g, seeds.data(), ns, p->distanceFunction));
+        if (p->removeIsolatedRegions) VF_TRY(vf_remove_isolated_regions(g, seeds.data(), ns));  // NaiveFracturer.cpp:100-103 (CPU semantics)
+    } else if (p->fractureAlgorithm == VF_FLOOD) {
+        VF_REQUIRE(p->distanceFunction >= 0 && p->distanceFunction <= 2, VF_ERR_INVALID_DISTANCE, "Invalid distance function");
+        VF_TRY(vf_fracture_flood(g, seeds.data(), ns, p->distanceFunction, p->floodIdBits, stats));
+    } else {
+        return vf_set_error(VF_ERR_UNSUPPORTED, "VORONOI (CGAL Delaunay, SRC/Graphics/Core/Voronoi.cpp) is outside the hot path");
+    }
+    if (p->erode) {  // CADScene.cpp:679-684
+        std::vector<float> noise(1000000);  // RegularGrid.cpp:126
+        VF_TRY(vf_fill_noise(c, noise.data(), (uint32_t)noise.size()));
+        VF_TRY(vf_erode(g, p->erosionConvolution, (uint32_t)p->erosionSize, (uint32_t)p->erosionIterations, p->erosionProbability, p->erosionThreshold,
+                        noise.data(), (uint32_t)noise.size(), p->erodeBoundaryMode));
+    } else {
+        VF_TRY(vf_detect_boundaries(g, 1));  // :687
+    }
+    if (seeds_out) std::memcpy(seeds_out, seeds.data(), 16 * (size_t)ns);
+    if (nseeds_out) *nseeds_out = ns;
+    return VF_OK;
+}

@@ -1,0 +1,340 @@
+// stencil.cu — C2/C3: boundary marking, erosion ("boundary noise") and the 3^3 isolated-voxel sweep; H1: histogram.
+//
+// Replaces RegularGrid::detectBoundaries (SRC/DataStructures/RegularGrid.cpp:64-80, detectBoundaries-comp.glsl:18-43),
+// RegularGrid::erode (:82-159, erodeGrid-comp.glsl:26-59, copyGrid-comp.glsl), RegularGrid::removeIsolatedRegions
+// (:1006-1015, removeIsolatedRegionsGrid-comp.glsl:16-39) and RegularGrid::countValues / numOccupiedVoxels (:601-625, 280-287).
+//
+// All three stencils are 3^3 neighbourhoods over 2-byte labels: a CTA stages an 8 x 8 x 64 tile plus a 1-cell halo in shared
+// memory (coalesced z-rows), so HBM sees each label once per pass (2 B read + 2 B written per voxel) instead of up to 27
+// scattered 2-byte loads per voxel as in the shaders.  Erosion ping-pongs between the grid and one scratch grid, which
+// removes the reference's copyGrid pass; the final sweep reads a snapshot and writes the other buffer (the reference's
+// in-place sweep is racy; DESIGN.md defines snapshot semantics).  Erosion masks larger than 3^3 take a direct global-memory path.
+#include <cmath>
+#include <vector>
+
+#include "vf_internal.h"
+
+namespace {
+
+constexpr int SX = 8, SYT = 8, SZT = 64;  // tile
+constexpr int HX = SX + 2, HY = SYT + 2, HZ = SZT + 2;
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+struct Dims {
+    int X, Y, Z;
+};
+
+__device__ __forceinline__ int s_at(int x, int y, int z) { return ((x + 1) * HY + (y + 1)) * HZ + (z + 1); }
+
+// stage tile + halo; cells outside the grid read as `outside`
+__device__ __forceinline__ void stage(uint16_t* s, const uint16_t* __restrict__ src, Dims d, int gx0, int gy0, int gz0, uint16_t outside)
+{
+    for (int i = threadIdx.x; i < HX * HY * HZ; i += blockDim.x) {
+        const int z = i % HZ - 1, r = i / HZ;
+        const int y = r % HY - 1, x = r / HY - 1;
+        const int gx = gx0 + x, gy = gy0 + y, gz = gz0 + z;
+        uint16_t v = outside;
+        if (gx >= 0 && gx < d.X && gy >= 0 && gy < d.Y && gz >= 0 && gz < d.Z) v = src[((size_t)gx * d.Y + gy) * d.Z + gz];
+        s[i] = v;
+    }
+}
+
+enum { OP_DETECT = 0, OP_ERODE3 = 1, OP_SWEEP = 2 };
+
+struct ErodeArgs {
+    const float* noise;
+    unsigned nnoise;
+    float prob, thr, activations;
+    int boundary_mode;
+    unsigned maskbits;  // 27-bit mask of the 3^3 convolution (bit = (dx+1)*9 + (dy+1)*3 + (dz+1))
+};
+
+// 0xFFFF never equals a real label word produced by the path (ids < 0x8000, bit 15 only together with an id), so halo cells
+// outside the grid can be staged as 0xFFFF for the equality stencils and excluded from "visited" counts arithmetically.
+constexpr uint16_t kOutside = 0xFFFFu;
+
+template <int OP>
+__global__ void __launch_bounds__(256) stencil_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, Dims d, int ntx, int nty, int ntz,
+                                                      ErodeArgs ea)
+{
+    __shared__ uint16_t s[HX * HY * HZ];
+    const int tile = blockIdx.x;
+    const int tz = tile % ntz, ty = (tile / ntz) % nty, tx = tile / (ntz * nty);
+    const int gx0 = tx * SX, gy0 = ty * SYT, gz0 = tz * SZT;
+    stage(s, src, d, gx0, gy0, gz0, kOutside);
+    __syncthreads();
+    const int z = threadIdx.x % SZT, grp = threadIdx.x / SZT;  // 4 groups of 64 lanes; each walks 16 (x,y) columns
+    const int gz = gz0 + z;
+    if (gz >= d.Z) return;
+    for (int c = grp; c < SX * SYT; c += 4) {
+        const int x = c / SYT, y = c % SYT;
+        const int gx = gx0 + x, gy = gy0 + y;
+        if (gx >= d.X || gy >= d.Y) continue;
+        const size_t gi = ((size_t)gx * d.Y + gy) * d.Z + gz;
+        const uint16_t own = s[s_at(x, y, z)];
+        if (OP == OP_DETECT) {
+            // detectBoundaries-comp.glsl:21-42 (in place: neighbours are read with bit 15 cleared, so the result does not
+            // depend on which neighbours were already tagged by this pass)
+            if (own <= VF_VOXEL_FREE) continue;
+            bool boundary = false;
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx)
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                    for (int dz = -1; dz <= 1; ++dz) {
+                        const uint16_t raw = s[s_at(x + dx, y + dy, z + dz)];
+                        const uint16_t v = raw & 0x7FFFu;
+                        boundary = boundary || (raw != kOutside && v > VF_VOXEL_FREE && v != own);
+                    }
+            if (boundary) dst[gi] = own | 0x8000u;
+        } else if (OP == OP_ERODE3) {
+            // erodeGrid-comp.glsl:31-58 for maskSize 3
+            uint16_t out = own;
+            const bool isB = ea.boundary_mode == 0 ? (own & 0x7FFFu) != 0 : (own >> 15) != 0;
+            if (own > VF_VOXEL_FREE && isB && ea.noise[gi % ea.nnoise] < ea.prob) {
+                unsigned count = 0, visited = 0;
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx)
+#pragma unroll
+                    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                        for (int dz = -1; dz <= 1; ++dz) {
+                            const uint16_t raw = s[s_at(x + dx, y + dy, z + dz)];
+                            const bool inside = gx + dx >= 0 && gx + dx < d.X && gy + dy >= 0 && gy + dy < d.Y && gz + dz >= 0 && gz + dz < d.Z;
+                            visited += inside;
+                            const unsigned bit = (dx + 1) * 9 + (dy + 1) * 3 + (dz + 1);
+                            count += (inside && raw == own && (ea.maskbits >> bit & 1u));
+                        }
+                const float activation = __fdiv_rn((float)count, (float)visited);
+                if (activation < __fmul_rn(ea.activations, ea.thr)) out = VF_VOXEL_EMPTY;
+            }
+            dst[gi] = out;
+        } else {
+            // removeIsolatedRegionsGrid-comp.glsl:24-38, snapshot semantics
+            int count = -1;
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx)
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                    for (int dz = -1; dz <= 1; ++dz) {
+                        const bool inside = gx + dx >= 0 && gx + dx < d.X && gy + dy >= 0 && gy + dy < d.Y && gz + dz >= 0 && gz + dz < d.Z;
+                        count += (inside && s[s_at(x + dx, y + dy, z + dz)] == own);
+                    }
+            dst[gi] = count < 6 ? (uint16_t)VF_VOXEL_EMPTY : own;
+        }
+    }
+}
+
+// erosion with an arbitrary odd mask size k > 3: direct global reads (rare path; GUI lets the user pick larger kernels)
+__global__ void __launch_bounds__(256) erode_generic_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, Dims d,
+                                                            const float* __restrict__ mask, int k, ErodeArgs ea)
+{
+    const size_t n = (size_t)d.X * d.Y * d.Z;
+    const int k2 = k / 2;
+    for (size_t gi = blockIdx.x * (size_t)blockDim.x + threadIdx.x; gi < n; gi += (size_t)gridDim.x * blockDim.x) {
+        const uint16_t own = src[gi];
+        uint16_t out = own;
+        const bool isB = ea.boundary_mode == 0 ? (own & 0x7FFFu) != 0 : (own >> 15) != 0;
+        if (own > VF_VOXEL_FREE && isB && ea.noise[gi % ea.nnoise] < ea.prob) {
+            const int z = (int)(gi % d.Z);
+            const size_t r = gi / d.Z;
+            const int y = (int)(r % d.Y), x = (int)(r / d.Y);
+            const int mnx = x - k2, mny = y - k2, mnz = z - k2;
+            const int x0 = max(mnx, 0), x1 = min(x + k2, d.X - 1), y0 = max(mny, 0), y1 = min(y + k2, d.Y - 1), z0 = max(mnz, 0), z1 = min(z + k2, d.Z - 1);
+            unsigned count = 0, visited = 0;
+            for (int a = x0; a <= x1; ++a)
+                for (int b = y0; b <= y1; ++b)
+                    for (int c = z0; c <= z1; ++c) {
+                        const float w = mask[((a - mnx) * k + (b - mny)) * k + (c - mnz)];
+                        count += (unsigned)__fmul_rn((float)(unsigned)(src[((size_t)a * d.Y + b) * d.Z + c] == own), w);
+                        ++visited;
+                    }
+            const float activation = __fdiv_rn((float)count, (float)visited);
+            if (activation < __fmul_rn(ea.activations, ea.thr)) out = VF_VOXEL_EMPTY;
+        }
+        dst[gi] = out;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ H1 histogram
+// one pass over 2 B/voxel; per-thread run-length accumulation (neighbouring voxels share a label), then shared-memory
+// bins for ids < 4096 and global atomics beyond.
+constexpr int kSmemBins = 4096;
+__global__ void __launch_bounds__(256) histogram_kernel(const uint16_t* __restrict__ grid, size_t n, uint32_t* __restrict__ counts,
+                                                        unsigned long long* __restrict__ occupied)
+{
+    __shared__ uint32_t bins[kSmemBins];
+    for (int i = threadIdx.x; i < kSmemBins; i += blockDim.x) bins[i] = 0;
+    __syncthreads();
+    unsigned occ = 0;
+    const size_t nvec = n / 8;
+    const uint4* g4 = reinterpret_cast<const uint4*>(grid);
+    auto add = [&](uint32_t label, uint32_t c) {
+        if (label < kSmemBins) atomicAdd(&bins[label], c);
+        else atomicAdd(&counts[label], c);
+    };
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = vf_ldg_stream(g4 + i);
+        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+        uint32_t run_label = 0xFFFFFFFFu, run = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t raw = (w[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
+            if (raw > VF_VOXEL_FREE) {  // RegularGrid.cpp:612: raw value > FREE, then unmask
+                const uint32_t label = raw & 0x7FFFu;
+                ++occ;
+                if (label == run_label) ++run;
+                else {
+                    if (run) add(run_label, run);
+                    run_label = label, run = 1;
+                }
+            }
+        }
+        if (run) add(run_label, run);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < n % 8) {
+        const uint32_t raw = grid[nvec * 8 + threadIdx.x];
+        if (raw > VF_VOXEL_FREE) {
+            ++occ;
+            add(raw & 0x7FFFu, 1);
+        }
+    }
+    occ = __reduce_add_sync(kFull, occ);
+    if ((threadIdx.x & 31) == 0 && occ) atomicAdd(occupied, (unsigned long long)occ);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSmemBins; i += blockDim.x)
+        if (bins[i]) atomicAdd(&counts[i], bins[i]);
+}
+
+vf_status launch_stencil(vf_grid* g, int op, const uint16_t* src, uint16_t* dst, const ErodeArgs& ea)
+{
+    vf_ctx* c = g->ctx;
+    Dims d = { (int)g->X, (int)g->Y, (int)g->Z };
+    const int ntx = (d.X + SX - 1) / SX, nty = (d.Y + SYT - 1) / SYT, ntz = (d.Z + SZT - 1) / SZT;
+    const int blocks = ntx * nty * ntz;
+    switch (op) {
+    case OP_DETECT: stencil_kernel<OP_DETECT><<<blocks, 256, 0, c->stream>>>(src, dst, d, ntx, nty, ntz, ea); break;
+    case OP_ERODE3: stencil_kernel<OP_ERODE3><<<blocks, 256, 0, c->stream>>>(src, dst, d, ntx, nty, ntz, ea); break;
+    default: stencil_kernel<OP_SWEEP><<<blocks, 256, 0, c->stream>>>(src, dst, d, ntx, nty, ntz, ea); break;
+    }
+    VF_LAUNCHED(c);
+    return VF_OK;
+}
+
+// RegularGrid.cpp:84-122 — erosion mask and the "activations" normalisation quirks, float32 as written
+void build_mask(int type, uint32_t& size, std::vector<float>& mask, float& activations)
+{
+    if (!(size % 2)) ++size;
+    const uint32_t k = size, maskSize = k * k * k, cc = (uint32_t)floorf(k / 2.0f);
+    mask.assign(maskSize, 0.0f);
+    activations = 0;
+    if (type == VF_SQUARE) {
+        std::fill(mask.begin(), mask.end(), 1.0f);
+        activations = (float)maskSize;
+    } else if (type == VF_CROSS) {
+        for (uint32_t x = 0; x < k; ++x) mask[x * k * k + cc * k + cc] = 1.0f;
+        for (uint32_t y = 0; y < k; ++y) mask[cc * k * k + y * k + cc] = 1.0f;
+        for (uint32_t z = 0; z < k; ++z) mask[cc * k * k + cc * k + z] = 1.0f;
+        activations = 1.0f / 3.0f * maskSize;
+    } else if (type == VF_ELLIPSE) {
+        for (uint32_t x = 0; x < k; ++x)
+            for (uint32_t y = 0; y < k; ++y)
+                for (uint32_t z = 0; z < k; ++z) {
+                    const float dx = (float)x - (float)cc, dy = (float)y - (float)cc, dz = (float)z - (float)cc;
+                    if (sqrtf(dx * dx + dy * dy + dz * dz) < (float)cc + 1.1920929e-07f) {  // glm::epsilon<float>()
+                        mask[x * k * k + y * k + z] = 1.0f;
+                        ++activations;
+                    }
+                }
+    }
+    activations /= maskSize;
+}
+
+}  // namespace
+
+extern "C" vf_status vf_detect_boundaries(vf_grid* g, int boundary_size)
+{
+    VF_REQUIRE(g != nullptr, VF_ERR_INVALID_ARGUMENT, "null grid");
+    VF_TRY(vf_enter(g->ctx));
+    VF_REQUIRE(boundary_size == 1, VF_ERR_UNSUPPORTED, "detectBoundaries: only boundarySize 1 is used by the reference (CADScene.cpp:687, RegularGrid.cpp:135)");
+    ErodeArgs ea = {};
+    return launch_stencil(g, OP_DETECT, g->d, g->d, ea);
+}
+
+extern "C" vf_status vf_remove_isolated_regions_grid(vf_grid* g)
+{
+    VF_REQUIRE(g != nullptr, VF_ERR_INVALID_ARGUMENT, "null grid");
+    vf_ctx* c = g->ctx;
+    VF_TRY(vf_enter(c));
+    VF_TRY(vf_scratch_reserve(c, c->grid2, g->n() * 2));
+    ErodeArgs ea = {};
+    VF_TRY(launch_stencil(g, OP_SWEEP, g->d, (uint16_t*)c->grid2.ptr, ea));
+    VF_CUDA(cudaMemcpyAsync(g->d, c->grid2.ptr, g->n() * 2, cudaMemcpyDeviceToDevice, c->stream));
+    return VF_OK;
+}
+
+extern "C" vf_status vf_erode(vf_grid* g, int type, uint32_t size, uint32_t iterations, float prob, float thr, const float* noise, uint32_t nnoise,
+                              int boundary_mode)
+{
+    VF_REQUIRE(g != nullptr && noise != nullptr && nnoise > 0, VF_ERR_INVALID_ARGUMENT, "erode: null grid or noise table");
+    VF_REQUIRE(type >= 0 && type <= 2, VF_ERR_INVALID_ARGUMENT, "erode: bad convolution type %d", type);
+    vf_ctx* c = g->ctx;
+    VF_TRY(vf_enter(c));
+    std::vector<float> mask;
+    float activations;
+    build_mask(type, size, mask, activations);
+    const size_t n = g->n();
+    VF_TRY(vf_scratch_reserve(c, c->grid2, n * 2));
+    VF_TRY(vf_scratch_reserve(c, c->noise, (size_t)nnoise * 4 + mask.size() * 4 + 256));
+    float* d_noise = (float*)c->noise.ptr;
+    float* d_mask = d_noise + nnoise;
+    VF_CUDA(cudaMemcpyAsync(d_noise, noise, (size_t)nnoise * 4, cudaMemcpyHostToDevice, c->stream));
+    VF_CUDA(cudaMemcpyAsync(d_mask, mask.data(), mask.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    VF_CUDA(cudaStreamSynchronize(c->stream));  // `mask` is a host temporary
+    ErodeArgs ea = { d_noise, nnoise, prob, thr, activations, boundary_mode, 0u };
+    if (size == 3)
+        for (int i = 0; i < 27; ++i)
+            if (mask[i] != 0.0f) ea.maskbits |= 1u << i;
+    Dims d = { (int)g->X, (int)g->Y, (int)g->Z };
+    uint16_t* a = g->d;
+    uint16_t* b = (uint16_t*)c->grid2.ptr;
+    vf_grid view = *g;  // shallow view used to run passes on either buffer
+    for (uint32_t it = 0; it < iterations; ++it) {
+        view.d = a;
+        VF_TRY(launch_stencil(&view, OP_DETECT, a, a, ea));  // RegularGrid.cpp:135
+        if (size == 3) {
+            VF_TRY(launch_stencil(&view, OP_ERODE3, a, b, ea));
+        } else {
+            erode_generic_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>(a, b, d, d_mask, (int)size, ea);
+            VF_LAUNCHED(c);
+        }
+        std::swap(a, b);  // replaces copyGrid (:149-152): the eroded grid becomes the current one
+    }
+    view.d = a;
+    VF_TRY(launch_stencil(&view, OP_SWEEP, a, b, ea));  // RegularGrid.cpp:155
+    if (b != g->d) VF_CUDA(cudaMemcpyAsync(g->d, b, n * 2, cudaMemcpyDeviceToDevice, c->stream));
+    return VF_OK;
+}
+
+extern "C" vf_status vf_histogram(vf_grid* g, uint32_t* counts, uint64_t* occupied)
+{
+    VF_REQUIRE(g != nullptr && counts != nullptr, VF_ERR_INVALID_ARGUMENT, "null argument");
+    vf_ctx* c = g->ctx;
+    VF_TRY(vf_enter(c));
+    VF_TRY(vf_scratch_reserve(c, c->small, 1 << 20));
+    // device bins live after the seed area of the small arena
+    uint32_t* d_counts = (uint32_t*)((char*)c->small.ptr + (512 << 10));
+    unsigned long long* d_occ = (unsigned long long*)(d_counts + VF_HISTOGRAM_BINS);
+    VF_CUDA(cudaMemsetAsync(d_counts, 0, VF_HISTOGRAM_BINS * 4 + 8, c->stream));
+    const int blocks = (int)std::min((size_t)c->num_sms * 4, (g->n() / 8 + 255) / 256 + 1);
+    histogram_kernel<<<blocks, 256, 0, c->stream>>>(g->d, g->n(), d_counts, d_occ);
+    VF_LAUNCHED(c);
+    VF_CUDA(cudaMemcpyAsync(counts, d_counts, VF_HISTOGRAM_BINS * 4, cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long h_occ = 0;
+    VF_CUDA(cudaMemcpyAsync(&h_occ, d_occ, 8, cudaMemcpyDeviceToHost, c->stream));
+    VF_CUDA(cudaStreamSynchronize(c->stream));
+    if (occupied) *occupied = h_occ;
+    return VF_OK;
+}
