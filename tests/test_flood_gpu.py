@@ -78,16 +78,33 @@ def test_unreachable_cells_stay_free_and_seed_on_empty_cell(ctx, orc):
 @pytest.mark.parametrize("dfunc", [1, 2])
 def test_extra_seeds_disjoint_rounds(ctx, orc, vessel_grid, dfunc):
     """F3: numExtraSeeds = 2*numSeeds as in dataset generation (FragmentationProcedure.h:12-13, CADScene.cpp:298-299)."""
-    two_rounds = 0
     for trial, nf in enumerate([2, 4, 7, 10]):
         seeds = orc.make_seeds(orc.Rng(80 + trial), vessel_grid, nf, 2 * nf, merge_dfunc=0)
         want, st = orc.flood(vessel_grid.copy(), seeds, dfunc)
         got, gst = _run_flood(ctx, vessel_grid, seeds, dfunc)
         assert np.array_equal(got, want), f"nf={nf}"
         assert gst.freed_voxels == st.freed_voxels and gst.disjoint_rounds == st.rounds
-        two_rounds += st.rounds == 2
         assert set(np.unique(got)) <= set(range(0, nf + 2))
-    assert two_rounds >= 1  # the dissolve-and-reflood path was exercised
+
+
+@pytest.mark.parametrize("dfunc", [1, 2])
+def test_orphaned_extra_seed_is_dissolved_and_reflooded(ctx, orc, dfunc):
+    """U-shaped corridor: an extra seed that is Euclidean-nearest to fragment 2 but geodesically behind fragment 3 grows a
+    region that is not connected to fragment 2's own; the disjoint step frees it and the re-flood hands it to fragment 3."""
+    g = np.zeros((5, 9, 100), np.uint16)
+    g[1:4, 1:4, :] = 1          # outbound corridor
+    g[1:4, 5:8, :] = 1          # return corridor
+    g[1:4, 1:8, 96:100] = 1     # the turn
+    frags = np.array([[2, 2, 3, 2], [2, 4, 98, 3]], np.uint32)
+    extra = np.array([[2, 6, 3, 0]], np.uint32)
+    seeds = np.concatenate([frags, orc.merge_seeds(frags, np.concatenate([frags, extra]), 0)])
+    assert list(seeds[:, 3]) == [2, 3, 2 | 1 << 8, 3 | 1 << 8, 2 | 2 << 8]
+    want, st = orc.flood(g.copy(), seeds, dfunc)
+    got, gst = _run_flood(ctx, g, seeds, dfunc)
+    assert st.rounds == 2 and st.freed_voxels > 100
+    assert np.array_equal(got, want)
+    assert gst.disjoint_rounds == 2 and gst.freed_voxels == st.freed_voxels
+    assert got[2, 6, 3] == 3 and got[2, 2, 3] == 2
 
 
 def test_extra_seeds_on_random_blobs(ctx, orc):
