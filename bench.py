@@ -294,6 +294,7 @@ def oracle_pipeline(orc, grid, seeds, noise, stages):
 def cpu_baseline(n, stages, steps=1):
     import oracle as orc
 
+    orc.use_all_cores()
     seeds = synth_seeds_dense(n, CFG3["nseeds"], rng_uniform_stream(CFG3["rng_seed"]))
     noise = noise_table(CFG3["rng_seed"] + 1000, CFG3["nnoise"])
     best = None
@@ -316,6 +317,7 @@ def run_reference(args):
         return
     import oracle as orc
 
+    orc.use_all_cores()
     n = args.cpu_size
     seeds = synth_seeds_dense(n, CFG3["nseeds"], rng_uniform_stream(CFG3["rng_seed"]))
     noise = noise_table(CFG3["rng_seed"] + 1000, CFG3["nnoise"])

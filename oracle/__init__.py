@@ -105,6 +105,7 @@ def _declare(L):
     L.orc_encode_bing_squared.restype = C.c_uint64
     L.orc_encode_bing_squared.argtypes = [_u16p, _u32p, C.c_void_p, C.c_uint64]
     L.orc_num_threads.restype = C.c_int
+    L.orc_set_num_threads.argtypes = [C.c_int]
 
 
 class OracleError(RuntimeError):
@@ -324,3 +325,10 @@ def encode_bing_squared(grid) -> bytes:
 
 def num_threads() -> int:
     return lib().orc_num_threads()
+
+
+def use_all_cores() -> int:
+    """torchrun exports OMP_NUM_THREADS=1: ask OpenMP for every host core the process may run on."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().orc_set_num_threads(n)
+    return n

@@ -959,6 +959,13 @@ extern "C" uint64_t orc_encode_bing_squared(const uint16_t* grid, const uint32_t
     return pos;
 }
 
+extern "C" void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#endif
+}
+
 extern "C" int orc_num_threads(void)
 {
 #ifdef _OPENMP

@@ -130,6 +130,7 @@ uint64_t orc_encode_bing_squared(const uint16_t* grid, const uint32_t dims[3], u
 
 /* ---- composite used by the CPU baseline (bench.py): cfg3 pipeline on one grid ---- */
 int orc_num_threads(void);
+void orc_set_num_threads(int n); /* torchrun exports OMP_NUM_THREADS=1; the CPU baseline asks for all host cores explicitly */
 
 #ifdef __cplusplus
 }
