@@ -4,15 +4,22 @@
 // (:26-68) == naiveFracturer-comp.glsl:19-43 with the metrics of distance.glsl:5-21:
 //     label(v) = seeds[argmin_i d(v, seed_i)].w   over non-EMPTY cells, strict '<' with i ascending (lowest index wins ties).
 //
-// B200 design (HBM bound: 2 B read + 2 B written per voxel; SURVEY §7 "naive kernel is ALU-bound unless seeds are culled"):
-//   * one warp owns a 4(x) x 4(y) x 8*VEC(z) brick; each lane moves 128-bit (VEC=8) or 64-bit (VEC=4) vectors of labels,
-//     eight lanes cover one 128-byte line of a z-row, four rows per instruction, four x-planes in flight per lane;
-//   * while those loads are in flight the warp culls the seed set against the brick: seed s survives iff
-//     minDist(s, brick) <= min_s' maxDist(s', brick)   (exact: a culled seed is strictly worse than s' for every voxel of
-//     the brick), survivors are compacted with ballot/popc in ascending seed order into a per-warp shared-memory list;
+// B200 design (HBM bound: 2 B read + 2 B written per voxel; a per-voxel loop over all seeds is ALU bound):
+//   * one warp owns an 8(x) x 4(y) x 8*VEC(z) brick; each lane moves 128-bit (VEC=8) or 64-bit (VEC=4) vectors of labels,
+//     eight lanes cover one 128-byte line of a z-row, four rows per instruction, eight x-planes in flight per lane;
+//   * while those loads are in flight the warp culls the seed set against the brick with an exact pairwise DOMINANCE test:
+//     let s* be the seed nearest to the brick centre; seed s is dropped iff s* beats s (smaller distance, or equal distance and
+//     lower index) at every point of the brick.  For EUCLIDEAN d^2(c,s) - d^2(c,s*) is linear in c, for MANHATTAN it is a sum of
+//     per-axis monotone functions, so its minimum over the box is attained at box ends per axis and the test costs ~30 integer
+//     ops per seed.  Bricks inside one Voronoi cell end up with exactly one candidate and need no per-voxel arithmetic at all;
+//     bricks on a cell boundary typically keep 2-3.  (CHEBYSHEV is not separable: it keeps the weaker but still exact
+//     minDist(s) <= min_s' maxDist(s') rule.)  Survivors are compacted with ballot/popc in ascending seed order;
 //   * distances are evaluated in integers, which is exact for the reference's float32 compare: d^2 < 2^24 and float sqrt is
 //     injective on integer d^2 up to 3*1181^2, Manhattan/Chebyshev are integers outright.  The running best is one
 //     32-bit key  (d << 8 | slot)  so that a single min keeps the lowest-index seed on ties;
+//   * the brick's label vectors are staged in shared memory with cp.async (no registers held while the warp culls), pass 1
+//     evaluates only the two end voxels of each 8-voxel chunk (winner intervals are convex along z), chunks that straddle a cell
+//     boundary are compacted with ballot/popc and dealt evenly to the lanes in pass 2;
 //   * seeds live in shared memory (loaded once per CTA), CTAs are persistent over bricks.
 // Grids that do not meet the fast path's preconditions (Z % 4 != 0, or Euclidean with an axis > 1182 where float sqrt stops
 // being injective) take the generic kernel, which compares float32 distances exactly like buildCPU.
@@ -21,6 +28,7 @@
 namespace {
 
 constexpr int kWarps = 8;
+constexpr int kIts = 8;    // x-planes per brick
 constexpr int kCMax = 64;  // candidate slots per warp brick (slot index must fit the key's low 8 bits)
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
@@ -33,12 +41,19 @@ __device__ __forceinline__ void axis_range(int lo, int hi, int p, int& dmin, int
     dmax = max(iabs(p - lo), iabs(p - hi));
 }
 
+// min over c in {lo, hi} of  f(c, s) - f(c, t)   with f = squared difference (EUCLIDEAN) or absolute difference (MANHATTAN).
+// Both are monotone in c (linear resp. clamp-shaped), so the minimum over the whole interval [lo, hi] is at an end.
 template <int DF>
-__device__ __forceinline__ unsigned combine(int a, int b, int c)
+__device__ __forceinline__ int axis_gap_min(int lo, int hi, int s, int t)
 {
-    if (DF == VF_EUCLIDEAN) return (unsigned)(a * a + b * b + c * c);
-    if (DF == VF_MANHATTAN) return (unsigned)(a + b + c);
-    return (unsigned)max(a, max(b, c));
+    if (DF == VF_EUCLIDEAN) {
+        const int a = (lo - s) * (lo - s) - (lo - t) * (lo - t);
+        const int b = (hi - s) * (hi - s) - (hi - t) * (hi - t);
+        return min(a, b);
+    }
+    const int a = iabs(lo - s) - iabs(lo - t);
+    const int b = iabs(hi - s) - iabs(hi - t);
+    return min(a, b);
 }
 
 // exact float32 restatement of NaiveFracturer.cpp:12-23 for one voxel against every seed (slow path)
@@ -103,167 +118,248 @@ __device__ __forceinline__ uint2 pack<4>(const unsigned (&w)[2])
     return make_uint2(w[0], w[1]);
 }
 
+// 0xFFFF in each 16-bit half of w that is non-zero
+__device__ __forceinline__ unsigned nonzero_halves(unsigned w)
+{
+    return ((w & 0xFFFFu) ? 0xFFFFu : 0u) | ((w >> 16) ? 0xFFFF0000u : 0u);
+}
+
+// exact division by a runtime constant for the brick index decode (d < 2^16, n < 2^31)
+struct FastDiv {
+    unsigned d, m;
+    __host__ FastDiv(unsigned div = 1) : d(div), m((unsigned)(((1ull << 32) + div - 1) / div)) {}
+    __device__ __forceinline__ unsigned div(unsigned n) const { return d == 1 ? n : __umulhi(n, m); }
+};
+
+__device__ __forceinline__ void cp_async(void* smem, const void* gmem, int bytes16)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    if (bytes16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
+
+// evaluate the candidates for the VEC voxels of one chunk (x, y fixed, z .. z+VEC-1); returns per-voxel labels packed 2 per word
+template <int DF, int VEC>
+__device__ __forceinline__ void eval_chunk(const ushort4* __restrict__ cand, int C, int x, int y, int z, unsigned (&lab2)[VEC / 2])
+{
+    unsigned key[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) key[k] = 0xFFFFFFFFu;
+    for (int slot = 0; slot < C; ++slot) {
+        const ushort4 sd = cand[slot];
+        const int dx = x - (int)sd.x, dy = y - (int)sd.y;
+        if (DF == VF_EUCLIDEAN) {
+            const unsigned base = ((unsigned)(dx * dx + dy * dy) << 8) | (unsigned)slot;
+            const int zs = (z - (int)sd.z) * 16;  // (16*dz)^2 = dz^2 << 8
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                const int dzs = zs + 16 * k;
+                key[k] = min(key[k], base + (unsigned)(dzs * dzs));
+            }
+        } else if (DF == VF_MANHATTAN) {
+            const unsigned base = ((unsigned)(iabs(dx) + iabs(dy)) << 8) | (unsigned)slot;
+            const int zs = (z - (int)sd.z) * 256;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) key[k] = min(key[k], base + (unsigned)iabs(zs + 256 * k));
+        } else {
+            const unsigned base = ((unsigned)max(iabs(dx), iabs(dy)) << 8) | (unsigned)slot;
+            const int zs = (z - (int)sd.z) * 256;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) key[k] = min(key[k], max(base, (unsigned)iabs(zs + 256 * k) | (unsigned)slot));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < VEC / 2; ++k) lab2[k] = (unsigned)cand[key[2 * k] & 0xFFu].w | ((unsigned)cand[key[2 * k + 1] & 0xFFu].w << 16);
+}
+
+template <int DF, int VEC>
+__device__ __noinline__ void scan_chunk(const ushort4* __restrict__ seeds, int S, int x, int y, int z, unsigned (&lab2)[VEC / 2])
+{
+    for (int k = 0; k < VEC / 2; ++k)
+        lab2[k] = (unsigned)scan_all_seeds<DF>(x, y, z + 2 * k, seeds, S, 0) | ((unsigned)scan_all_seeds<DF>(x, y, z + 2 * k + 1, seeds, S, 0) << 16);
+}
+
 template <int DF, int VEC>
 __global__ void __launch_bounds__(kWarps * 32, 4)
-naive_brick_kernel(uint16_t* __restrict__ grid, int X, int Y, int Z, const ushort4* __restrict__ seeds_g, int S, int nby, int nbz,
+naive_brick_kernel(uint16_t* __restrict__ grid, int X, int Y, int Z, const ushort4* __restrict__ seeds_g, int S, FastDiv div_nbz, FastDiv div_nby,
                    unsigned total_bricks)
 {
     typedef typename VecT<VEC>::type V;
     constexpr int BZ = 8 * VEC;  // brick extent along z
-    extern __shared__ ushort4 smem[];
-    ushort4* sseeds = smem;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: staging [kWarps][kIts][32] vectors | seeds [S] | candidates [kWarps][kCMax] | task lists [kWarps][kIts*32] bytes
+    V* stage_all = reinterpret_cast<V*>(smem_raw);
+    ushort4* sseeds = reinterpret_cast<ushort4*>(smem_raw + sizeof(V) * kWarps * kIts * 32);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    ushort4* cand = smem + ((S + 3) & ~3) + warp * kCMax;
+    ushort4* cand = sseeds + ((S + 3) & ~3) + warp * kCMax;
+    unsigned char* tasks = reinterpret_cast<unsigned char*>(sseeds + ((S + 3) & ~3) + kWarps * kCMax) + warp * kIts * 32;
+    V* stage = stage_all + warp * kIts * 32;
 
     for (int i = threadIdx.x; i < S; i += blockDim.x) sseeds[i] = seeds_g[i];
     __syncthreads();
 
     const int ly = lane >> 3, lz = lane & 7;
+    const size_t xstride = (size_t)Y * Z / VEC;  // in vectors
     for (unsigned brick = blockIdx.x * kWarps + warp; brick < total_bricks; brick += gridDim.x * kWarps) {
-        const int bz = brick % nbz;
-        const unsigned t = brick / nbz;
-        const int by = t % nby, bx = t / nby;
-        const int x0 = bx * 4, y0 = by * 4, z0 = bz * BZ;
+        const unsigned t = div_nbz.div(brick);
+        const int bz = brick - t * div_nbz.d;
+        const unsigned bx = div_nby.div(t);
+        const int by = t - bx * div_nby.d;
+        const int x0 = bx * kIts, y0 = by * 4, z0 = bz * BZ;
         const int y = y0 + ly, z = z0 + lz * VEC;
         const bool rowvalid = (y < Y) && (z < Z);  // Z % VEC == 0, so a valid chunk is entirely inside the row
+        const int nits = min(kIts, X - x0);
 
-        // ---- 1. put four 128-bit (64-bit) loads in flight
-        V raw[4];
-        bool valid[4];
-        V* ptr[4];
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const int x = x0 + it;
-            valid[it] = rowvalid && (x < X);
-            ptr[it] = reinterpret_cast<V*>(grid + ((size_t)x * Y + y) * Z + z);
-            if (valid[it]) raw[it] = vf_ldg_stream(ptr[it]);
-        }
+        // ---- 1. eight asynchronous 128-bit (64-bit) copies per lane, global -> shared, no registers held
+        V* ptr0 = reinterpret_cast<V*>(grid + ((size_t)x0 * Y + y) * Z + z);
+        if (rowvalid)
+            for (int it = 0; it < nits; ++it) cp_async(&stage[it * 32 + lane], ptr0 + it * xstride, VEC == 8);
+        asm volatile("cp.async.commit_group;" ::: "memory");
 
-        // ---- 2. cull the seed set against the brick while the loads fly
-        const int x1 = min(x0 + 3, X - 1), y1 = min(y0 + 3, Y - 1), z1 = min(z0 + BZ - 1, Z - 1);
-        unsigned bound = 0xFFFFFFFFu;
-        for (int base = 0; base < S; base += 32) {
-            const int s = base + lane;
-            if (s < S) {
-                const ushort4 sd = sseeds[s];
-                int a0, a1, b0, b1, c0, c1;
-                axis_range(x0, x1, sd.x, a0, a1);
-                axis_range(y0, y1, sd.y, b0, b1);
-                axis_range(z0, z1, sd.z, c0, c1);
-                bound = min(bound, combine<DF>(a1, b1, c1));
-            }
-        }
-        bound = __reduce_min_sync(kFull, bound);
+        // ---- 2. cull the seed set against the brick while the copies fly
+        const int x1 = min(x0 + kIts - 1, X - 1), y1 = min(y0 + 3, Y - 1), z1 = min(z0 + BZ - 1, Z - 1);
         int C = 0;
-        for (int base = 0; base < S; base += 32) {
-            const int s = base + lane;
-            bool keep = false;
-            ushort4 sd = make_ushort4(0, 0, 0, 0);
-            if (s < S) {
-                sd = sseeds[s];
-                int a0, a1, b0, b1, c0, c1;
-                axis_range(x0, x1, sd.x, a0, a1);
-                axis_range(y0, y1, sd.y, b0, b1);
-                axis_range(z0, z1, sd.z, c0, c1);
-                keep = combine<DF>(a0, b0, c0) <= bound;
+        if (DF != VF_CHEBYSHEV) {
+            // s* = seed nearest (L1, doubled coordinates) to the brick centre, lowest index on ties.  The choice of s* affects
+            // only how many seeds survive, never the result.
+            const int cx2 = x0 + x1, cy2 = y0 + y1, cz2 = z0 + z1;
+            unsigned best = 0xFFFFFFFFu;
+            for (int base = 0; base < S; base += 32) {
+                const int s = base + lane;
+                if (s < S) {
+                    const ushort4 sd = sseeds[s];
+                    const unsigned d = (unsigned)(iabs(2 * (int)sd.x - cx2) + iabs(2 * (int)sd.y - cy2) + iabs(2 * (int)sd.z - cz2));
+                    best = min(best, (d << 13) | (unsigned)s);  // d < 2^19 (3 * 2 * 65535), s < 2^13
+                }
             }
-            const unsigned m = __ballot_sync(kFull, keep);
-            if (keep) {
-                const int slot = C + __popc(m & ((1u << lane) - 1));
-                if (slot < kCMax) cand[slot] = sd;
+            const int star = (int)(__reduce_min_sync(kFull, best) & 0x1FFFu);
+            const ushort4 st = sseeds[star];
+            for (int base = 0; base < S; base += 32) {
+                const int s = base + lane;
+                bool keep = false;
+                ushort4 sd = make_ushort4(0, 0, 0, 0);
+                if (s < S) {
+                    sd = sseeds[s];
+                    // g(c) = d(c, s) - d(c, s*); s* beats s at c iff g > 0, or g == 0 and star < s
+                    const int g = axis_gap_min<DF>(x0, x1, sd.x, st.x) + axis_gap_min<DF>(y0, y1, sd.y, st.y) + axis_gap_min<DF>(z0, z1, sd.z, st.z);
+                    keep = (s == star) || !(g > 0 || (g == 0 && star < s));
+                }
+                const unsigned m = __ballot_sync(kFull, keep);
+                if (keep) {
+                    const int slot = C + __popc(m & ((1u << lane) - 1));
+                    if (slot < kCMax) cand[slot] = sd;
+                }
+                C += __popc(m);
             }
-            C += __popc(m);
+        } else {
+            unsigned bound = 0xFFFFFFFFu;
+            for (int base = 0; base < S; base += 32) {
+                const int s = base + lane;
+                if (s < S) {
+                    const ushort4 sd = sseeds[s];
+                    int a0, a1, b0, b1, c0, c1;
+                    axis_range(x0, x1, sd.x, a0, a1);
+                    axis_range(y0, y1, sd.y, b0, b1);
+                    axis_range(z0, z1, sd.z, c0, c1);
+                    bound = min(bound, (unsigned)max(a1, max(b1, c1)));
+                }
+            }
+            bound = __reduce_min_sync(kFull, bound);
+            for (int base = 0; base < S; base += 32) {
+                const int s = base + lane;
+                bool keep = false;
+                ushort4 sd = make_ushort4(0, 0, 0, 0);
+                if (s < S) {
+                    sd = sseeds[s];
+                    int a0, a1, b0, b1, c0, c1;
+                    axis_range(x0, x1, sd.x, a0, a1);
+                    axis_range(y0, y1, sd.y, b0, b1);
+                    axis_range(z0, z1, sd.z, c0, c1);
+                    keep = (unsigned)max(a0, max(b0, c0)) <= bound;
+                }
+                const unsigned m = __ballot_sync(kFull, keep);
+                if (keep) {
+                    const int slot = C + __popc(m & ((1u << lane) - 1));
+                    if (slot < kCMax) cand[slot] = sd;
+                }
+                C += __popc(m);
+            }
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
+        const unsigned only = (unsigned)cand[0].w * 0x10001u;  // C == 1: the whole brick lies in one Voronoi cell
 
-        // ---- 3. label the four x-planes of the brick
+        // ---- 3. pass 1: every lane walks its own chunks.  C == 1 needs no arithmetic.  Otherwise only the two end voxels of the
+        //      chunk are evaluated: for EUCLIDEAN / MANHATTAN the difference of two seeds' distances is monotone along an
+        //      axis-parallel line, so the z-range a seed wins is an interval and equal winners at both ends label the whole chunk.
+        //      Chunks that straddle a cell boundary (and every chunk under CHEBYSHEV, whose max() plateaus break that property)
+        //      are queued for pass 2.
+        int ntasks = 0;
+        for (int it = 0; it < nits; ++it) {
+            bool slow = false;
+            if (rowvalid) {
+                unsigned w[VEC / 2];
+                unpack<VEC>(stage[it * 32 + lane], w);
+                unsigned any = 0;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            unsigned w[VEC / 2];
-            bool any = false;
-            if (valid[it]) {
-                unpack<VEC>(raw[it], w);
-#pragma unroll
-                for (int k = 0; k < VEC / 2; ++k) any = any || (w[k] != 0);
-            }
-            if (!any) continue;  // nothing occupied in this chunk: no store (2*N_occ write bytes)
-            const int x = x0 + it;
-            unsigned short lab[VEC];
-            if (C <= kCMax) {
-                // For EUCLIDEAN and MANHATTAN the difference of two seeds' distances along an axis-parallel line is monotone,
-                // so the set of z where one seed is the (lowest-index) winner is an interval: when both ends of the chunk have
-                // the same winner the whole chunk has it, and only chunks that straddle a cell boundary evaluate every voxel.
-                // (Not true for CHEBYSHEV: max(c, |dz|) plateaus let a lower-index seed win two disjoint tie ranges.)
-                unsigned key[VEC];
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) key[k] = 0xFFFFFFFFu;
-                if (DF != VF_CHEBYSHEV) {
-                    unsigned k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu;
-                    for (int slot = 0; slot < C; ++slot) {
-                        const ushort4 sd = cand[slot];
-                        const int dx = x - (int)sd.x, dy = y - (int)sd.y;
-                        if (DF == VF_EUCLIDEAN) {
-                            const unsigned base = ((unsigned)(dx * dx + dy * dy) << 8) | (unsigned)slot;
-                            const int zs = (z - (int)sd.z) * 16, ze = zs + 16 * (VEC - 1);
-                            k0 = min(k0, base + (unsigned)(zs * zs));
-                            k1 = min(k1, base + (unsigned)(ze * ze));
-                        } else {
-                            const unsigned base = ((unsigned)(iabs(dx) + iabs(dy)) << 8) | (unsigned)slot;
-                            const int zs = (z - (int)sd.z) * 256;
-                            k0 = min(k0, base + (unsigned)iabs(zs));
-                            k1 = min(k1, base + (unsigned)iabs(zs + 256 * (VEC - 1)));
-                        }
-                    }
-                    if ((k0 & 0xFFu) == (k1 & 0xFFu)) {
-#pragma unroll
-                        for (int k = 0; k < VEC; ++k) key[k] = k0;
-                    } else {
-                        key[0] = k0, key[VEC - 1] = k1;
+                for (int k = 0; k < VEC / 2; ++k) any |= w[k];
+                if (any) {  // nothing occupied in this chunk: no store (2*N_occ write bytes)
+                    unsigned lab = only;
+                    bool done = C == 1;
+                    if (!done && C <= kCMax && DF != VF_CHEBYSHEV) {
+                        const int x = x0 + it;
+                        unsigned k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu;
                         for (int slot = 0; slot < C; ++slot) {
                             const ushort4 sd = cand[slot];
                             const int dx = x - (int)sd.x, dy = y - (int)sd.y;
                             if (DF == VF_EUCLIDEAN) {
                                 const unsigned base = ((unsigned)(dx * dx + dy * dy) << 8) | (unsigned)slot;
-                                const int zs = (z - (int)sd.z) * 16;  // (16*dz)^2 = dz^2 << 8
-#pragma unroll
-                                for (int k = 1; k < VEC - 1; ++k) {
-                                    const int dzs = zs + 16 * k;
-                                    key[k] = min(key[k], base + (unsigned)(dzs * dzs));
-                                }
+                                const int zs = (z - (int)sd.z) * 16, ze = zs + 16 * (VEC - 1);
+                                k0 = min(k0, base + (unsigned)(zs * zs));
+                                k1 = min(k1, base + (unsigned)(ze * ze));
                             } else {
                                 const unsigned base = ((unsigned)(iabs(dx) + iabs(dy)) << 8) | (unsigned)slot;
                                 const int zs = (z - (int)sd.z) * 256;
-#pragma unroll
-                                for (int k = 1; k < VEC - 1; ++k) key[k] = min(key[k], base + (unsigned)iabs(zs + 256 * k));
+                                k0 = min(k0, base + (unsigned)iabs(zs));
+                                k1 = min(k1, base + (unsigned)iabs(zs + 256 * (VEC - 1)));
                             }
                         }
+                        done = (k0 & 0xFFu) == (k1 & 0xFFu);
+                        lab = (unsigned)cand[k0 & 0xFFu].w * 0x10001u;
                     }
-                } else {
-                    for (int slot = 0; slot < C; ++slot) {
-                        const ushort4 sd = cand[slot];
-                        const int dx = x - (int)sd.x, dy = y - (int)sd.y;
-                        const unsigned base = ((unsigned)max(iabs(dx), iabs(dy)) << 8) | (unsigned)slot;
-                        const int zs = (z - (int)sd.z) * 256;
+                    if (done) {
 #pragma unroll
-                        for (int k = 0; k < VEC; ++k) key[k] = min(key[k], max(base, (unsigned)iabs(zs + 256 * k) | (unsigned)slot));
+                        for (int k = 0; k < VEC / 2; ++k) w[k] = nonzero_halves(w[k]) & lab;
+                        vf_stg_stream(ptr0 + it * xstride, pack<VEC>(w));
+                    } else {
+                        slow = true;
                     }
                 }
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) lab[k] = cand[key[k] & 0xFFu].w;
-            } else {
-                // more survivors than slots (brick equidistant to many seeds): exact scan of the whole seed set
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) lab[k] = scan_all_seeds<DF>(x, y, z + k, sseeds, S, 0);
             }
-#pragma unroll
-            for (int k = 0; k < VEC / 2; ++k) {
-                const unsigned lo = (w[k] & 0xFFFFu) ? (unsigned)lab[2 * k] : 0u;
-                const unsigned hi = (w[k] >> 16) ? (unsigned)lab[2 * k + 1] : 0u;
-                w[k] = lo | (hi << 16);
+            if (C > 1) {  // warp-uniform
+                const unsigned m = __ballot_sync(kFull, slow);
+                if (slow) tasks[ntasks + __popc(m & ((1u << lane) - 1))] = (unsigned char)(it * 32 + lane);
+                ntasks += __popc(m);
             }
-            vf_stg_stream(ptr[it], pack<VEC>(w));
         }
-        __syncwarp();  // cand[] is rewritten by the next brick
+
+        // ---- 4. pass 2: the queued chunks are dealt round-robin to the lanes (any lane can serve any chunk: the data sits in
+        //      shared memory), so a brick with a few boundary chunks costs a few balanced rounds instead of stalling whole planes
+        if (ntasks) {
+            __syncwarp();
+            for (int q = lane; q < ntasks; q += 32) {
+                const int id = tasks[q], it = id >> 5, src = id & 31;
+                const int tx = x0 + it, ty = y0 + (src >> 3), tz = z0 + (src & 7) * VEC;
+                unsigned w[VEC / 2], lab2[VEC / 2];
+                unpack<VEC>(stage[id], w);
+                if (C <= kCMax) eval_chunk<DF, VEC>(cand, C, tx, ty, tz, lab2);
+                else scan_chunk<DF, VEC>(sseeds, S, tx, ty, tz, lab2);  // more survivors than slots: exact scan of the whole seed set
+#pragma unroll
+                for (int k = 0; k < VEC / 2; ++k) w[k] = nonzero_halves(w[k]) & lab2[k];
+                vf_stg_stream(reinterpret_cast<V*>(grid + ((size_t)tx * Y + ty) * Z + tz), pack<VEC>(w));
+            }
+        }
+        __syncwarp();  // cand[], tasks[] and stage[] are rewritten by the next brick
     }
 }
 
@@ -289,13 +385,14 @@ template <int DF, int VEC>
 vf_status launch_brick(vf_grid* g, const ushort4* d_seeds, int S)
 {
     vf_ctx* c = g->ctx;
-    const int nbx = (g->X + 3) / 4, nby = (g->Y + 3) / 4, nbz = (g->Z + 8 * VEC - 1) / (8 * VEC);
+    const int nbx = (g->X + kIts - 1) / kIts, nby = (g->Y + 3) / 4, nbz = (g->Z + 8 * VEC - 1) / (8 * VEC);
     const unsigned total = (unsigned)nbx * nby * nbz;
-    const size_t smem = ((size_t)((S + 3) & ~3) + kWarps * kCMax) * sizeof(ushort4);
+    VF_REQUIRE((uint64_t)total * (uint64_t)max(nbz, nby) < (1ull << 32), VF_ERR_CAPACITY, "naive: grid too large for the brick index decode");
+    const size_t smem = (size_t)kWarps * kIts * 32 * (VEC * 2) + ((size_t)((S + 3) & ~3) + kWarps * kCMax) * sizeof(ushort4) + (size_t)kWarps * kIts * 32;
     auto kern = naive_brick_kernel<DF, VEC>;
     if (smem > 48 * 1024) VF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned blocks = min((total + kWarps - 1) / kWarps, (unsigned)c->num_sms * 8u);
-    kern<<<blocks, kWarps * 32, smem, c->stream>>>(g->d, (int)g->X, (int)g->Y, (int)g->Z, d_seeds, S, nby, nbz, total);
+    const unsigned blocks = min((total + kWarps - 1) / kWarps, (unsigned)c->num_sms * 4u);
+    kern<<<blocks, kWarps * 32, smem, c->stream>>>(g->d, (int)g->X, (int)g->Y, (int)g->Z, d_seeds, S, FastDiv((unsigned)nbz), FastDiv((unsigned)nby), total);
     VF_LAUNCHED(c);
     return VF_OK;
 }
@@ -328,7 +425,7 @@ vf_status dispatch(vf_grid* g, const ushort4* d_seeds, int S)
 
 vf_status vf_k_naive(vf_grid* g, const ushort4* d_seeds, uint32_t nseeds, int dfunc)
 {
-    VF_REQUIRE(nseeds <= 16384, VF_ERR_CAPACITY, "naive: %u seeds exceed the shared-memory seed table (16384)", nseeds);
+    VF_REQUIRE(nseeds <= 8192, VF_ERR_CAPACITY, "naive: %u seeds exceed the shared-memory seed table (8192)", nseeds);
     switch (dfunc) {
     case VF_EUCLIDEAN: return dispatch<VF_EUCLIDEAN>(g, d_seeds, (int)nseeds);
     case VF_MANHATTAN: return dispatch<VF_MANHATTAN>(g, d_seeds, (int)nseeds);
