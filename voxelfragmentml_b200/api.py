@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import enum
+import weakref
 
 import numpy as np
 
@@ -98,9 +99,12 @@ class Context:
             check(self._lib.vf_ctx_create_on_stream(device, C.c_void_p(stream), C.byref(h)))
         self._h = h
         self.device = device
+        self._grids = weakref.WeakSet()  # grids must be destroyed before their context (they borrow its device and stream)
 
     def close(self):
         if getattr(self, "_h", None):
+            for g in list(self._grids):
+                g.close()
             self._lib.vf_ctx_destroy(self._h)
             self._h = None
 
@@ -168,6 +172,7 @@ class RegularGrid:
         else:
             check(self._lib.vf_grid_wrap(ctx._h, C.c_void_p(device_ptr), X, Y, Z, C.byref(h)))
         self._h = h
+        ctx._grids.add(self)
 
     def close(self):
         if getattr(self, "_h", None):

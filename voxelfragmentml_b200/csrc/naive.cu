@@ -17,9 +17,9 @@
 //   * distances are evaluated in integers, which is exact for the reference's float32 compare: d^2 < 2^24 and float sqrt is
 //     injective on integer d^2 up to 3*1181^2, Manhattan/Chebyshev are integers outright.  The running best is one
 //     32-bit key  (d << 8 | slot)  so that a single min keeps the lowest-index seed on ties;
-//   * the brick's label vectors are staged in shared memory with cp.async (no registers held while the warp culls), pass 1
-//     evaluates only the two end voxels of each 8-voxel chunk (winner intervals are convex along z), chunks that straddle a cell
-//     boundary are compacted with ballot/popc and dealt evenly to the lanes in pass 2;
+//   * the brick's label vectors are staged in shared memory with cp.async (no registers held while the warp culls); in bricks cut
+//     by a cell boundary every lane repeats the dominance test on its own 8 x 1 x VEC box, so only lanes whose box is cut evaluate
+//     voxels, and their chunks are compacted with ballot/popc and dealt evenly to the lanes in pass 2;
 //   * seeds live in shared memory (loaded once per CTA), CTAs are persistent over bricks.
 // Grids that do not meet the fast path's preconditions (Z % 4 != 0, or Euclidean with an axis > 1182 where float sqrt stops
 // being injective) take the generic kernel, which compares float32 distances exactly like buildCPU.
@@ -212,8 +212,10 @@ naive_brick_kernel(uint16_t* __restrict__ grid, int X, int Y, int Z, const ushor
 
         // ---- 1. eight asynchronous 128-bit (64-bit) copies per lane, global -> shared, no registers held
         V* ptr0 = reinterpret_cast<V*>(grid + ((size_t)x0 * Y + y) * Z + z);
-        if (rowvalid)
-            for (int it = 0; it < nits; ++it) cp_async(&stage[it * 32 + lane], ptr0 + it * xstride, VEC == 8);
+        if (rowvalid) {
+            const V* gq = ptr0;
+            for (int it = 0; it < nits; ++it, gq += xstride) cp_async(&stage[it * 32 + lane], gq, VEC == 8);
+        }
         asm volatile("cp.async.commit_group;" ::: "memory");
 
         // ---- 2. cull the seed set against the brick while the copies fly
@@ -285,52 +287,62 @@ naive_brick_kernel(uint16_t* __restrict__ grid, int X, int Y, int Z, const ushor
                 C += __popc(m);
             }
         }
+        __syncwarp();
+
+        // ---- 3. per-lane refinement (C >= 2): a lane owns the box  x0..x1 x {y} x z..z+VEC-1  (its chunk in every plane).  One point
+        //      evaluation picks the winner w at the box corner; if w dominates every other candidate over the box (same separable
+        //      minimum as above) the lane's chunks all take w's label without further arithmetic.  Lanes whose box is cut by a cell
+        //      boundary queue their chunks for pass 2.  (CHEBYSHEV is not separable: with C >= 2 every chunk goes to pass 2.)
+        unsigned lab = (unsigned)cand[0].w * 0x10001u;  // C == 1: the whole brick lies in one Voronoi cell
+        bool lane_uniform = C == 1;
+        if (C > 1 && C <= kCMax && DF != VF_CHEBYSHEV && rowvalid) {
+            unsigned kbest = 0xFFFFFFFFu;
+            for (int slot = 0; slot < C; ++slot) {
+                const ushort4 sd = cand[slot];
+                const int dx = x0 - (int)sd.x, dy = y - (int)sd.y, dz = z - (int)sd.z;
+                const unsigned d = DF == VF_EUCLIDEAN ? (unsigned)(dx * dx + dy * dy + dz * dz) : (unsigned)(iabs(dx) + iabs(dy) + iabs(dz));
+                kbest = min(kbest, (d << 8) | (unsigned)slot);
+            }
+            const int ws = (int)(kbest & 0xFFu);
+            const ushort4 wn = cand[ws];
+            bool all_dominated = true;
+            for (int slot = 0; slot < C; ++slot) {
+                const ushort4 sd = cand[slot];
+                const int g = axis_gap_min<DF>(x0, x1, sd.x, wn.x) + axis_gap_min<DF>(y, y, sd.y, wn.y) + axis_gap_min<DF>(z, z + VEC - 1, sd.z, wn.z);
+                all_dominated = all_dominated && (slot == ws || g > 0 || (g == 0 && ws < slot));  // slots are in seed-index order
+            }
+            lane_uniform = all_dominated;
+            lab = (unsigned)wn.w * 0x10001u;
+        }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
-        const unsigned only = (unsigned)cand[0].w * 0x10001u;  // C == 1: the whole brick lies in one Voronoi cell
 
-        // ---- 3. pass 1: every lane walks its own chunks.  C == 1 needs no arithmetic.  Otherwise only the two end voxels of the
-        //      chunk are evaluated: for EUCLIDEAN / MANHATTAN the difference of two seeds' distances is monotone along an
-        //      axis-parallel line, so the z-range a seed wins is an interval and equal winners at both ends label the whole chunk.
-        //      Chunks that straddle a cell boundary (and every chunk under CHEBYSHEV, whose max() plateaus break that property)
-        //      are queued for pass 2.
+        // ---- pass 1: label the chunks whose lane box is uniform; queue the rest
         int ntasks = 0;
-        for (int it = 0; it < nits; ++it) {
+        V* gp = ptr0;
+        for (int it = 0; it < nits; ++it, gp += xstride) {
             bool slow = false;
             if (rowvalid) {
                 unsigned w[VEC / 2];
                 unpack<VEC>(stage[it * 32 + lane], w);
-                unsigned any = 0;
+                // SWAR: bit 15 / 31 of t is set iff the corresponding 16-bit half of w is non-zero
+                unsigned all = 0x80008000u, any = 0;
 #pragma unroll
-                for (int k = 0; k < VEC / 2; ++k) any |= w[k];
+                for (int k = 0; k < VEC / 2; ++k) {
+                    const unsigned t = ((w[k] & 0x7FFF7FFFu) + 0x7FFF7FFFu) | w[k];
+                    all &= t;
+                    any |= w[k];
+                }
                 if (any) {  // nothing occupied in this chunk: no store (2*N_occ write bytes)
-                    unsigned lab = only;
-                    bool done = C == 1;
-                    if (!done && C <= kCMax && DF != VF_CHEBYSHEV) {
-                        const int x = x0 + it;
-                        unsigned k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu;
-                        for (int slot = 0; slot < C; ++slot) {
-                            const ushort4 sd = cand[slot];
-                            const int dx = x - (int)sd.x, dy = y - (int)sd.y;
-                            if (DF == VF_EUCLIDEAN) {
-                                const unsigned base = ((unsigned)(dx * dx + dy * dy) << 8) | (unsigned)slot;
-                                const int zs = (z - (int)sd.z) * 16, ze = zs + 16 * (VEC - 1);
-                                k0 = min(k0, base + (unsigned)(zs * zs));
-                                k1 = min(k1, base + (unsigned)(ze * ze));
-                            } else {
-                                const unsigned base = ((unsigned)(iabs(dx) + iabs(dy)) << 8) | (unsigned)slot;
-                                const int zs = (z - (int)sd.z) * 256;
-                                k0 = min(k0, base + (unsigned)iabs(zs));
-                                k1 = min(k1, base + (unsigned)iabs(zs + 256 * (VEC - 1)));
-                            }
-                        }
-                        done = (k0 & 0xFFu) == (k1 & 0xFFu);
-                        lab = (unsigned)cand[k0 & 0xFFu].w * 0x10001u;
-                    }
-                    if (done) {
+                    if (lane_uniform) {
+                        if (all == 0x80008000u) {
 #pragma unroll
-                        for (int k = 0; k < VEC / 2; ++k) w[k] = nonzero_halves(w[k]) & lab;
-                        vf_stg_stream(ptr0 + it * xstride, pack<VEC>(w));
+                            for (int k = 0; k < VEC / 2; ++k) w[k] = lab;
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < VEC / 2; ++k) w[k] = nonzero_halves(w[k]) & lab;
+                        }
+                        vf_stg_stream(gp, pack<VEC>(w));
                     } else {
                         slow = true;
                     }
