@@ -174,11 +174,14 @@ def run_cuda(args):
                 if e.status != 7:  # VF_ERR_UNSUPPORTED: stage not built yet
                     raise
 
+        # reference call order (CADScene::fractureModel, CADScene.cpp:657-688, then prepareScene :791-813):
+        # NaiveFracturer::build = naive + removeIsolatedRegions, then erode, then countValues, then undoMask
         stage("naive", lambda: naive.build(grid, seeds))
+        stage("remove_isolated", lambda: vf.NaiveFracturer.removeIsolatedRegions(grid, seeds))
         et, es, ei, ep, eth = CFG3["erosion"]
         stage("erode", lambda: grid.erode(et, es, ei, ep, eth, noise=noise))
-        stage("remove_isolated", lambda: vf.NaiveFracturer.removeIsolatedRegions(grid, seeds))
         stage("histogram", lambda: grid.countValues())
+        stage("undo_mask", lambda: grid.undoMask())
         if record is not None:
             record.append(t)
 
@@ -259,8 +262,8 @@ def run_cuda(args):
         "metric": "Gvoxels/s fragmented at 512^3", "value": world * N * args.steps / (total_ms * 1e-3) / 1e9, "unit": "Gvoxels/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u16 labels / int32 distance keys", "data": "synthetic",
-        "config": {"workload": f"cfg3-dense: {n}^3 all-occupied grid, NAIVE EUCLIDEAN {CFG3['nseeds']} seeds + erode(ELLIPSE,3,3it,p.5,thr.5)"
-                               " + connected-to-seed cleanup + histogram", "stages": stages_run, "grid": list(dims),
+        "config": {"workload": f"cfg3-dense: {n}^3 all-occupied grid, NAIVE EUCLIDEAN {CFG3['nseeds']} seeds + connected-to-seed cleanup"
+                               " + erode(ELLIPSE,3,3it,p.5,thr.5) + histogram + undoMask", "stages": stages_run, "grid": list(dims),
                    "l2": "inputs (256 MiB at 512^3) larger than L2 (126 MB); no explicit flush", "parallelism": f"replicas x{world} (one grid per GPU)"},
         "stage_ms": stage_ms,
         "roofline": {"kernel": "naive_brick_kernel<EUCLIDEAN,8>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -282,13 +285,15 @@ def run_cuda(args):
 def oracle_pipeline(orc, grid, seeds, noise, stages):
     if "naive" in stages:
         orc.naive(grid, seeds, CFG3["dfunc"])
+    if "remove_isolated" in stages:
+        orc.remove_isolated_regions_cpu(grid, seeds)
     if "erode" in stages:
         et, es, ei, ep, eth = CFG3["erosion"]
         orc.erode(grid, noise, et, es, ei, ep, eth)
-    if "remove_isolated" in stages:
-        orc.remove_isolated_regions_cpu(grid, seeds)
     if "histogram" in stages:
         orc.count_values(grid)
+    if "undo_mask" in stages:
+        orc.undo_mask(grid, 15, False)
 
 
 def cpu_baseline(n, stages, steps=1):
@@ -308,7 +313,7 @@ def cpu_baseline(n, stages, steps=1):
             "sample": f"{n}^3 dense grid, same pipeline and seed count (stages {stages}), {best:.2f} s", "seconds": best}
 
 
-ALL_STAGES = ["naive", "erode", "remove_isolated", "histogram"]
+ALL_STAGES = ["naive", "remove_isolated", "erode", "histogram", "undo_mask"]
 
 
 def run_reference(args):

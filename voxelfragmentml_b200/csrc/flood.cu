@@ -1,4 +1,4 @@
-// flood.cu — F2/F3 flood-fill fragmentation and C1 connected-to-seed cleanup.
+// flood.cu — F2/F3 flood-fill fragmentation (the connected-component step of F3 and C1 live in ccl.cu).
 //
 // Replaces FloodFracturer::build (SRC/Fracturer/FloodFracturer.cpp:98-191; shaders floodFracturer-comp.glsl:24-64,
 // disjointSet-comp.glsl:17-24, disjointSetStack-comp.glsl:20-37, undoMask-comp.glsl) and the intended semantics of
@@ -28,10 +28,8 @@ constexpr uint32_t KEY_WALL = 0xFFFFFFFFu, KEY_UNREACHED = 0xFFFFFFFEu;
 constexpr int KEY_SHIFT = 15;
 constexpr uint32_t KEY_LEVEL = 1u << KEY_SHIFT;
 constexpr uint32_t KEY_LIMIT = 0xFFFF0000u;  // keys at or above this cannot take another level (dist >= 2^17 - 2)
-constexpr uint32_t MARK = 0x8000u;           // reach marker = bit 15 of the label word (clear on entry by contract)
 
 enum { ST_VISITS = 0, ST_ROUNDS = 1, ST_ERROR = 2, ST_FREED = 3, ST_MAXDIST = 4 };
-enum { REACH_C1 = 0, REACH_F3 = 1 };
 
 constexpr size_t kSmemBytes = (size_t)(kCells + 3 * kThreads + 8) * sizeof(uint32_t);
 
@@ -260,180 +258,6 @@ __global__ void __launch_bounds__(256) flood_finalize_kernel(const uint32_t* __r
     if ((threadIdx.x & 31) == 0 && maxd) atomicMax(&stats[ST_MAXDIST], maxd);
 }
 
-// ------------------------------------------------------------------------------------------------ C1 / F3: reachability
-template <int MODE>
-__device__ __forceinline__ bool same_region(uint32_t a, uint32_t b)
-{
-    return MODE == REACH_C1 ? ((a ^ b) & 0x7FFFu) == 0 : ((a ^ b) & 0xFFu) == 0;
-}
-
-// start cells: C1 writes seed.w into the cell whatever it held (newGrid[seed] = seed.w, NaiveFracturer.cpp:120-123);
-// F3 marks the cell of each fragment's principal source.
-template <int MODE>
-__global__ void reach_seed_kernel(uint16_t* __restrict__ grid, TileGeom g, Worklist wl, const ushort4* __restrict__ starts, int S, uint32_t round)
-{
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    for (int s = 0; s < S; ++s) {
-        const ushort4 sd = starts[s];
-        uint16_t* p = &grid[((size_t)sd.x * g.Y + sd.y) * g.Z + sd.z];
-        *p = MODE == REACH_C1 ? (uint16_t)(sd.w | MARK) : (uint16_t)(*p | MARK);
-        const uint32_t tile = ((uint32_t)(sd.x / TX) * g.nty + sd.y / TY) * g.ntz + sd.z / TZ;
-        wl.occ[tile] = 1;
-        enqueue_tile(wl, tile, round);
-    }
-}
-
-__global__ void __launch_bounds__(256) tile_occupancy_kernel(const uint16_t* __restrict__ grid, TileGeom g, uint8_t* __restrict__ occ)
-{
-    const size_t n = (size_t)g.X * g.Y * g.Z;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        if (grid[i] <= VF_VOXEL_FREE) continue;
-        const int z = (int)(i % g.Z);
-        const size_t r = i / g.Z;
-        const int y = (int)(r % g.Y), x = (int)(r / g.Y);
-        const uint32_t tile = ((uint32_t)(x / TX) * g.nty + y / TY) * g.ntz + z / TZ;
-        if (!occ[tile]) occ[tile] = 1;
-    }
-}
-
-template <int MODE, int NNEIGH>
-__global__ void __launch_bounds__(kThreads, 4) reach_round_kernel(uint16_t* __restrict__ grid, TileGeom g, Worklist wl, uint32_t round)
-{
-    extern __shared__ uint32_t sm[];
-    uint32_t* sw = sm;
-    uint32_t* act = sm + kCells;
-    uint32_t* chg = act + 2 * kThreads;
-    uint32_t* misc = chg + kThreads;
-
-    const uint32_t count = wl.count[round % 3];
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    if (blockIdx.x == 0 && t == 0) {
-        wl.count[(round + 2) % 3] = 0;
-        if (count) atomicAdd(&wl.stats[ST_ROUNDS], 1u);
-    }
-    for (uint32_t wi = blockIdx.x; wi < count; wi += gridDim.x) {
-        const uint32_t tile = wl.list[round & 1][wi];
-        const int tz = tile % g.ntz, ty = (tile / g.ntz) % g.nty, tx = tile / (g.ntz * g.nty);
-        const int gx0 = tx * TX, gy0 = ty * TY, gz0 = tz * TZ;
-
-        load_tile<NNEIGH>(sw, grid, g, gx0, gy0, gz0, 0u, [](uint16_t v) { return (uint32_t)v; });
-        act[t] = 0, act[kThreads + t] = 0, chg[t] = 0;
-        if (t < 4) misc[t] = 0;
-        __syncthreads();
-
-        // entry pass: an unmarked labelled cell next to a marked cell of its own region becomes marked
-        {
-            unsigned total = 0;
-            for (int r = warp * 32; r < warp * 32 + 32; ++r) {
-                const int x = r / TY, y = r % TY, z = lane;
-                const uint32_t v = sw[sidx(x, y, z)];
-                bool hit = false;
-                if ((v & 0x7FFFu) > VF_VOXEL_FREE && !(v & MARK)) {
-                    auto probe = [&](int nx, int ny, int nz) {
-                        const uint32_t u = sw[sidx(nx, ny, nz)];
-                        hit = hit || ((u & MARK) && same_region<MODE>(u, v));
-                    };
-                    if (NNEIGH == 6) {
-                        probe(x - 1, y, z), probe(x + 1, y, z), probe(x, y - 1, z), probe(x, y + 1, z), probe(x, y, z - 1), probe(x, y, z + 1);
-                    } else {
-#pragma unroll
-                        for (int dx = -1; dx <= 1; ++dx)
-#pragma unroll
-                            for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                                for (int dz = -1; dz <= 1; ++dz)
-                                    if (dx | dy | dz) probe(x + dx, y + dy, z + dz);
-                    }
-                    if (hit) sw[sidx(x, y, z)] = v | MARK;
-                }
-                const unsigned b = __ballot_sync(kFull, hit);
-                if (lane == 0 && b) {
-                    act[r] = b;
-                    chg[r] = b;
-                    total += __popc(b);
-                }
-            }
-            if (lane == 0 && total) atomicAdd(&misc[0], total);
-        }
-        __syncthreads();
-
-        for (int it = 0; it < TX * TY * TZ; ++it) {
-            if (misc[it % 3] == 0) break;
-            if (t == 0) misc[(it + 2) % 3] = 0;
-            const int cur = it & 1;
-            unsigned word = act[cur * kThreads + t];
-            act[cur * kThreads + t] = 0;
-            const int x = t / TY, y = t % TY;
-            uint32_t* nxt = act + (cur ^ 1) * kThreads;
-            while (word) {
-                const int z = __ffs(word) - 1;
-                word &= word - 1;
-                const uint32_t mine = sw[sidx(x, y, z)];
-                auto spread = [&](int nx, int ny, int nz) {
-                    if (nx < 0 || nx >= TX || ny < 0 || ny >= TY || nz < 0 || nz >= TZ) return;
-                    uint32_t* p = &sw[sidx(nx, ny, nz)];
-                    const uint32_t u = *p;
-                    if (!(u & MARK) && (u & 0x7FFFu) > VF_VOXEL_FREE && same_region<MODE>(u, mine)) {
-                        const uint32_t old = atomicOr(p, MARK);
-                        if (!(old & MARK)) {
-                            const int r2 = nx * TY + ny;
-                            atomicOr(&nxt[r2], 1u << nz);
-                            atomicOr(&chg[r2], 1u << nz);
-                            atomicAdd(&misc[(it + 1) % 3], 1u);
-                        }
-                    }
-                };
-                if (NNEIGH == 6) {
-                    spread(x - 1, y, z), spread(x + 1, y, z), spread(x, y - 1, z), spread(x, y + 1, z), spread(x, y, z - 1), spread(x, y, z + 1);
-                } else {
-#pragma unroll
-                    for (int dx = -1; dx <= 1; ++dx)
-#pragma unroll
-                        for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                            for (int dz = -1; dz <= 1; ++dz)
-                                if (dx | dy | dz) spread(x + dx, y + dy, z + dz);
-                }
-            }
-            __syncthreads();
-        }
-
-        for (int r = warp * 32; r < warp * 32 + 32; ++r) {
-            if (chg[r]) {
-                const int x = r / TY, y = r % TY, gz = gz0 + lane;
-                if (gz < g.Z && gx0 + x < g.X && gy0 + y < g.Y) grid[((size_t)(gx0 + x) * g.Y + gy0 + y) * g.Z + gz] = (uint16_t)sw[sidx(x, y, lane)];
-            }
-        }
-        if (t == 0) atomicAdd(&wl.stats[ST_VISITS], 1u);
-        enqueue_neighbours<NNEIGH>(g, wl, tx, ty, tz, chg[t], &misc[3], round + 1);
-        __syncthreads();
-    }
-}
-
-// F3: unmarked labelled cells -> FREE (disjointSetStack-comp.glsl:27-31), counted.  C1: everything unmarked -> EMPTY, because the
-// reference rebuilds the grid from an all-EMPTY one (NaiveFracturer.cpp:115-116,149).  Marked cells lose the marker.
-template <int MODE>
-__global__ void __launch_bounds__(256) reach_prune_kernel(uint16_t* __restrict__ grid, size_t n, uint32_t* __restrict__ stats)
-{
-    unsigned freed = 0;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const uint16_t v = grid[i];
-        if (v & MARK) {
-            grid[i] = v & 0x7FFFu;
-        } else if (MODE == REACH_C1) {
-            if (v != VF_VOXEL_EMPTY) {
-                grid[i] = VF_VOXEL_EMPTY;
-                ++freed;
-            }
-        } else if (v > VF_VOXEL_FREE) {
-            grid[i] = VF_VOXEL_FREE;
-            ++freed;
-        }
-    }
-    freed = __reduce_add_sync(kFull, freed);
-    if ((threadIdx.x & 31) == 0 && freed) atomicAdd(&stats[ST_FREED], freed);
-}
-
 // ------------------------------------------------------------------------------------------------ host side
 struct Job {
     vf_ctx* c;
@@ -504,14 +328,6 @@ vf_status flood_phase(Job& j, uint32_t* keys)
     auto kern = flood_round_kernel<NNEIGH>;
     VF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     return run_rounds(j, [&](uint32_t r) { kern<<<j.blocks_tiles, kThreads, kSmemBytes, j.c->stream>>>(keys, j.g, j.wl, r); });
-}
-
-template <int MODE, int NNEIGH>
-vf_status reach_phase(Job& j, uint16_t* grid)
-{
-    auto kern = reach_round_kernel<MODE, NNEIGH>;
-    VF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    return run_rounds(j, [&](uint32_t r) { kern<<<j.blocks_tiles, kThreads, kSmemBytes, j.c->stream>>>(grid, j.g, j.wl, r); });
 }
 
 }  // namespace
@@ -585,11 +401,7 @@ extern "C" vf_status vf_fracture_flood(vf_grid* grid, const uint32_t* seeds, uin
         ushort4* d_starts = d_seeds + ((nseeds + 255) & ~255u);
         uint16_t* d_order = (uint16_t*)(d_starts + 256);
         VF_CUDA(cudaMemcpyAsync(d_starts, h, 256 * sizeof(ushort4) + 256 * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
-        reach_seed_kernel<REACH_F3><<<1, 32, 0, c->stream>>>(grid->d, j.g, j.wl, d_starts, nstart, j.round);
-        VF_LAUNCHED(c);
-        VF_TRY(nneigh == 6 ? (reach_phase<REACH_F3, 6>(j, grid->d)) : (reach_phase<REACH_F3, 26>(j, grid->d)));
-        reach_prune_kernel<REACH_F3><<<j.blocks_stream, 256, 0, c->stream>>>(grid->d, n, j.wl.stats);
-        VF_LAUNCHED(c);
+        VF_TRY(vf_k_keep_seed_components(grid, d_starts, nstart, 1, nneigh, j.wl.stats + ST_FREED));  // union-find (ccl.cu); reuses the key scratch
         VF_TRY(read_stats(j, hs));
         st.freed_voxels = hs[ST_FREED];
         if (hs[ST_FREED] != 0) {
@@ -622,14 +434,5 @@ extern "C" vf_status vf_remove_isolated_regions(vf_grid* grid, const uint32_t* s
     VF_TRY(vf_enter(c));
     ushort4* d_seeds = nullptr;
     VF_TRY(vf_upload_seeds(c, seeds, nseeds, grid->X, grid->Y, grid->Z, &d_seeds));
-    Job j;
-    VF_TRY(job_begin(grid, j));
-    tile_occupancy_kernel<<<j.blocks_stream, 256, 0, c->stream>>>(grid->d, j.g, j.wl.occ);
-    VF_LAUNCHED(c);
-    reach_seed_kernel<REACH_C1><<<1, 32, 0, c->stream>>>(grid->d, j.g, j.wl, d_seeds, (int)nseeds, j.round);
-    VF_LAUNCHED(c);
-    VF_TRY((reach_phase<REACH_C1, 6>(j, grid->d)));
-    reach_prune_kernel<REACH_C1><<<j.blocks_stream, 256, 0, c->stream>>>(grid->d, grid->n(), j.wl.stats);
-    VF_LAUNCHED(c);
-    return VF_OK;
+    return vf_k_keep_seed_components(grid, d_seeds, (int)nseeds, 0, 6, nullptr);
 }

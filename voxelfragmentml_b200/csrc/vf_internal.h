@@ -119,6 +119,7 @@ vf_status vf_upload_seeds(vf_ctx* ctx, const uint32_t* seeds, uint32_t n, uint32
 
 // ---------------------------------------------------------------------------------------------- kernels (one per file)
 vf_status vf_k_naive(vf_grid* g, const ushort4* d_seeds, uint32_t nseeds, int dfunc);
+vf_status vf_k_keep_seed_components(vf_grid* grid, const ushort4* d_starts, int nstarts, int mode, int nneigh, uint32_t* d_freed);  // ccl.cu
 vf_status vf_k_pointwise(vf_grid* g, int op);  // 0 undoMask(bit15) 1 undoMask(rightmost 8) 2 resetFilling 3 homogenize
 enum { VF_PW_UNMASK15 = 0, VF_PW_RIGHTMOST8 = 1, VF_PW_RESET_FILLING = 2, VF_PW_HOMOGENIZE = 3 };
 
