@@ -129,16 +129,38 @@ __global__ void __launch_bounds__(256) ccl_tile_kernel(const uint16_t* __restric
     const int gx0 = tx * LX, gy0 = ty * LY, gz0 = tz * LZ;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    // (a) warp per row, lane = z: labels, masks, run-start parents
+    // (a1) stage the tile's labels: 16-byte asynchronous copies when rows are 16-byte aligned (Z % 8 == 0), so that all of a
+    //      thread's loads are in flight at once; scalar loads otherwise.  Cells outside the grid read as EMPTY.
+    const bool vec_ok = (g.Z % 8 == 0) && ((reinterpret_cast<uintptr_t>(grid) & 15) == 0);
+    if (vec_ok) {
+        for (int q = threadIdx.x; q < LROWS * 4; q += 256) {  // 4 chunks of 8 cells per row
+            const int r = q >> 2, ch = q & 3;
+            const int gx = gx0 + r / LY, gy = gy0 + r % LY, gz = gz0 + ch * 8;
+            uint16_t* dst = &lab[r * LZ + ch * 8];
+            if (gx < g.X && gy < g.Y && gz < g.Z) {
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(grid + ((size_t)gx * g.Y + gy) * g.Z + gz) : "memory");
+            } else {
+                *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else {
+        for (int r = warp; r < LROWS; r += 8) {
+            const int gx = gx0 + r / LY, gy = gy0 + r % LY, gz = gz0 + lane;
+            lab[r * LZ + lane] = (gx < g.X && gy < g.Y && gz < g.Z) ? grid[((size_t)gx * g.Y + gy) * g.Z + gz] : (uint16_t)0;
+        }
+    }
+    __syncthreads();
+    // (a2) warp per row, lane = z: masks, run-start parents
     for (int r = warp; r < LROWS; r += 8) {
-        const int gx = gx0 + r / LY, gy = gy0 + r % LY, gz = gz0 + lane;
-        const bool in = gx < g.X && gy < g.Y && gz < g.Z;
-        const uint32_t v = in ? grid[((size_t)gx * g.Y + gy) * g.Z + gz] : 0u;
+        const int gx = gx0 + r / LY, gy = gy0 + r % LY;
+        const uint32_t v = lab[r * LZ + lane];
         const bool act = active<MODE>(v);
         const uint32_t vp = __shfl_up_sync(kFull, v, 1);
         const bool cont = lane > 0 && act && active<MODE>(vp) && same<MODE>(v, vp);
         const unsigned A = __ballot_sync(kFull, act), S = ~__ballot_sync(kFull, cont);
-        lab[r * LZ + lane] = (uint16_t)v;
         par[r * LZ + lane] = r * LZ + lane;
         if (lane == 0) {
             sA[r] = A;
@@ -272,20 +294,28 @@ template <int MODE>
 __global__ void __launch_bounds__(256) ccl_select_kernel(uint16_t* __restrict__ grid, const uint32_t* __restrict__ P, const uint2* __restrict__ masks, Geo g,
                                                          uint32_t* __restrict__ freed_out)
 {
-    const int lane = threadIdx.x & 31;
+    // thread per 32-cell segment: resolve each run's root once, build the mask of cells to clear; only segments that lose
+    // cells touch the grid (2 B written per removed cell)
     unsigned freed = 0;
-    for (uint32_t sg = blockIdx.x * 8 + (threadIdx.x >> 5); sg < g.nsegs; sg += gridDim.x * 8) {
-        const int seg = sg % g.segs;
-        const uint32_t row = sg / g.segs;
-        const int z = seg * 32 + lane;
+    for (uint32_t sg = blockIdx.x * blockDim.x + threadIdx.x; sg < g.nsegs; sg += gridDim.x * blockDim.x) {
         const uint2 mm = masks[sg];
-        const uint32_t i = row * (uint32_t)g.Z + z;
-        // the run start resolves the root for its run; the other lanes of the run fetch the verdict with a shuffle
-        const bool act = mm.x >> lane & 1u;
-        const int s = act ? run_start(mm.y, lane) : lane;
-        bool keep = false;
-        if (act && s == lane) {
-            uint32_t r = P[i] & ~KEEP;
+        const int seg = sg % g.segs;
+        const uint32_t base = (sg / g.segs) * (uint32_t)g.Z + seg * 32;
+        const int ncell = min(32, g.Z - seg * 32);
+        const unsigned valid = ncell == 32 ? 0xFFFFFFFFu : ((1u << ncell) - 1);
+        unsigned dead = MODE == MODE_C1 ? valid & ~mm.x : 0u;  // C1: inactive non-EMPTY cells (FREE) are dropped as well
+        unsigned starts = mm.y & mm.x;
+        // run starts among the active cells: a start bit on an inactive cell opens no run
+        unsigned todo = mm.x;
+        while (todo) {
+            const int z = __ffs(todo) - 1;
+            // the run containing z: from z up to (excluding) the next start bit or the next inactive cell
+            unsigned after = (mm.y | ~mm.x) & ~((2u << z) - 1);
+            const int end = after ? __ffs(after) - 1 : 32;
+            const unsigned runmask = (end == 32 ? 0xFFFFFFFFu : ((1u << end) - 1)) & ~((1u << z) - 1);
+            todo &= ~runmask;
+            uint32_t r = P[base + z] & ~KEEP;
+            bool keep;
             while (true) {
                 const uint32_t q = __ldg(&P[r]);
                 if ((q & ~KEEP) == r) {
@@ -294,19 +324,21 @@ __global__ void __launch_bounds__(256) ccl_select_kernel(uint16_t* __restrict__ 
                 }
                 r = q & ~KEEP;
             }
+            if (!keep) dead |= runmask;
         }
-        __syncwarp();
-        keep = __shfl_sync(kFull, keep, s) && act;
-        if (z < g.Z && !keep) {
-            const uint16_t v = grid[i];
+        (void)starts;
+        while (dead) {
+            const int z = __ffs(dead) - 1;
+            dead &= dead - 1;
+            const uint16_t v = grid[base + z];
             if (MODE == MODE_C1 ? v != VF_VOXEL_EMPTY : v > VF_VOXEL_FREE) {
-                grid[i] = MODE == MODE_C1 ? VF_VOXEL_EMPTY : VF_VOXEL_FREE;
+                grid[base + z] = MODE == MODE_C1 ? VF_VOXEL_EMPTY : VF_VOXEL_FREE;
                 ++freed;
             }
         }
     }
     freed = __reduce_add_sync(kFull, freed);
-    if (lane == 0 && freed) atomicAdd(freed_out, freed);
+    if ((threadIdx.x & 31) == 0 && freed) atomicAdd(freed_out, freed);
 }
 
 constexpr size_t kTileSmem = (size_t)LCELLS * 4 + (size_t)LROWS * 8 + (size_t)LCELLS * 2;
@@ -362,9 +394,8 @@ vf_status vf_k_keep_seed_components(vf_grid* grid, const ushort4* d_starts, int 
     }
     ccl_mark_kernel<<<(nstarts + 127) / 128, 128, 0, c->stream>>>(P, g, d_starts, nstarts);
     VF_LAUNCHED(c);
-    const int blocks_seg = (int)std::min<size_t>((g.nsegs + 7) / 8, (size_t)c->num_sms * 16);
-    if (mode == MODE_C1) ccl_select_kernel<MODE_C1><<<blocks_seg, 256, 0, c->stream>>>(grid->d, P, masks, g, d_freed);
-    else ccl_select_kernel<MODE_F3><<<blocks_seg, 256, 0, c->stream>>>(grid->d, P, masks, g, d_freed);
+    if (mode == MODE_C1) ccl_select_kernel<MODE_C1><<<blocks_lin, 256, 0, c->stream>>>(grid->d, P, masks, g, d_freed);
+    else ccl_select_kernel<MODE_F3><<<blocks_lin, 256, 0, c->stream>>>(grid->d, P, masks, g, d_freed);
     VF_LAUNCHED(c);
     return VF_OK;
 }
