@@ -201,13 +201,25 @@ __global__ void __launch_bounds__(256) ccl_tile_kernel(const uint16_t* __restric
     }
     __syncthreads();
 
+    // (b2) thread per row: flatten the run starts of my row, so that (c) is one shared-memory read per cell
+    {
+        const int r = threadIdx.x;
+        unsigned st = sS[r] & sA[r];
+        while (st) {
+            const int z = __ffs(st) - 1;
+            st &= st - 1;
+            par[r * LZ + z] = find_local(par, r * LZ + z);  // writes an ancestor: safe against concurrent finds
+        }
+    }
+    __syncthreads();
+
     // (c) warp per row: every active cell points at the global index of its tile-local root
     for (int r = warp; r < LROWS; r += 8) {
         const int gx = gx0 + r / LY, gy = gy0 + r % LY, gz = gz0 + lane;
         if (!(gx < g.X && gy < g.Y && gz < g.Z)) continue;
         uint32_t out = NONE;
         if (sA[r] >> lane & 1u) {
-            const uint32_t root = find_local(par, r * LZ + run_start(sS[r], lane));
+            const uint32_t root = par[r * LZ + run_start(sS[r], lane)];
             const int rz = root % LZ, rr = root / LZ;
             out = ((uint32_t)(gx0 + rr / LY) * g.Y + gy0 + rr % LY) * g.Z + gz0 + rz;
         }
@@ -229,10 +241,24 @@ __global__ void __launch_bounds__(256) ccl_border_kernel(const uint16_t* __restr
         const unsigned Am = mm.x, Sm = mm.y;
         if (!Am) continue;
         const uint32_t base = row * (uint32_t)g.Z + seg * 32;
+        // A pair (i, n) that straddles a tile border need not be united when a "witness" pair one row (or plane) back, inside the
+        // same two tiles, carries the same labels: stage 1 united i with its witness and n with its witness, and the witness pair
+        // is handled by its own thread (induction on (x, y)).  Only rows on a tile edge, or rows where the labels change, pay.
+        const int YZ = g.Y * g.Z;
+        auto witnessed = [&](uint32_t i, uint32_t n, uint32_t vi, uint32_t vn, int back) {
+            const uint32_t wi = grid[i - back], wn = grid[n - back];
+            return active<MODE>(wi) && active<MODE>(wn) && same<MODE>(vi, wi) && same<MODE>(vn, wn);
+        };
         // same row, previous segment (always another tile because LZ == 32)
         if (seg > 0 && (Am & 1u)) {
             const uint2 pm = masks[sg - 1];
-            if ((pm.x >> 31) && same<MODE>(grid[base], grid[base - 1])) unite(P, base, base - 32 + run_start(pm.y, 31));
+            if (pm.x >> 31) {
+                const uint32_t vi = grid[base], vn = grid[base - 1];
+                if (same<MODE>(vi, vn)) {
+                    const bool skip = (y % LY != 0 && witnessed(base, base - 1, vi, vn, g.Z)) || (x % LX != 0 && witnessed(base, base - 1, vi, vn, YZ));
+                    if (!skip) unite(P, base, base - 1);
+                }
+            }
         }
         auto against = [&](int nx, int ny, int dz) {
             if (nx < 0 || ny < 0 || ny >= g.Y) return;
@@ -256,7 +282,15 @@ __global__ void __launch_bounds__(256) ccl_border_kernel(const uint16_t* __restr
                 const int z = __ffs(m) - 1;
                 m &= m - 1;
                 const uint32_t i = base + z, n = nbase + z + dz;
-                if (same<MODE>(grid[i], grid[n])) unite(P, i, n);  // P[cell] is the cell's tile-local root: depth-1 entry points
+                const uint32_t vi = grid[i], vn = grid[n];
+                if (!same<MODE>(vi, vn)) continue;
+                // witness one plane back (pair crosses a y border only) or one row back (pair crosses an x border only)
+                bool skip = false;
+                if (NNEIGH == 6) {
+                    if (ny != y && x % LX != 0) skip = witnessed(i, n, vi, vn, YZ);
+                    else if (nx != x && y % LY != 0) skip = witnessed(i, n, vi, vn, g.Z);
+                }
+                if (!skip) unite(P, i, n);  // P[cell] is the cell's tile-local root: depth-1 entry points
             }
         };
         against(x, y - 1, 0), against(x - 1, y, 0);
