@@ -220,45 +220,43 @@ constexpr int FRS = 80;                 // staged row stride in cells: z = -1 at
 constexpr int FROWS = HX * HY;          // 100 staged rows
 __device__ __forceinline__ int f_at(int x, int y, int z) { return ((x + 1) * HY + (y + 1)) * FRS + z + 8; }
 
+// shared-memory offset of window cell `bit` = (dx+1)*9 + (dy+1)*3 + (dz+1) relative to the centre
+__constant__ int c_win_off[27] = {
+    (-1 * HY - 1) * FRS - 1, (-1 * HY - 1) * FRS, (-1 * HY - 1) * FRS + 1, (-1 * HY) * FRS - 1, (-1 * HY) * FRS, (-1 * HY) * FRS + 1,
+    (-1 * HY + 1) * FRS - 1, (-1 * HY + 1) * FRS, (-1 * HY + 1) * FRS + 1,
+    (-1) * FRS - 1, (-1) * FRS, (-1) * FRS + 1, -1, 0, 1, FRS - 1, FRS, FRS + 1,
+    (HY - 1) * FRS - 1, (HY - 1) * FRS, (HY - 1) * FRS + 1, HY * FRS - 1, HY * FRS, HY * FRS + 1,
+    (HY + 1) * FRS - 1, (HY + 1) * FRS, (HY + 1) * FRS + 1
+};
+
+// exact per-voxel stencils on the staged tile.  Cells outside the grid hold kOutside, which never equals a label word, so the
+// equality counts need no bounds tests; only erosion's "visited" (cells of the clamped box) is computed from the coordinates.
 template <int OP>
 __device__ __forceinline__ uint16_t stencil_voxel(const uint16_t* s, const Dims& d, int x, int y, int z, int gx, int gy, int gz, size_t gi, const ErodeArgs& ea,
                                                   bool& changed)
 {
-    const uint16_t own = s[f_at(x, y, z)];
+    const uint16_t* ctr = s + f_at(x, y, z);
+    const uint16_t own = *ctr;
     changed = false;
     if (OP == OP_DETECT) {
-        if (own <= VF_VOXEL_FREE) return own;
+        if (own <= VF_VOXEL_FREE || (own & 0x8000u)) return own;  // unlabelled, or already tagged (stays tagged whatever the window holds)
         bool boundary = false;
 #pragma unroll
-        for (int dx = -1; dx <= 1; ++dx)
-#pragma unroll
-            for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                for (int dz = -1; dz <= 1; ++dz) {
-                    const uint16_t raw = s[f_at(x + dx, y + dy, z + dz)];
-                    const uint16_t v = raw & 0x7FFFu;
-                    boundary = boundary || (raw != kOutside && v > VF_VOXEL_FREE && v != own);
-                }
-        changed = boundary && !(own & 0x8000u);
+        for (int b = 0; b < 27; ++b) {
+            const unsigned raw = ctr[c_win_off[b]];
+            const unsigned v = raw & 0x7FFFu;
+            boundary = boundary || (raw != kOutside && v > VF_VOXEL_FREE && v != own);
+        }
+        changed = boundary;
         return boundary ? (uint16_t)(own | 0x8000u) : own;
     } else if (OP == OP_ERODE3) {
         uint16_t out = own;
         const bool isB = ea.boundary_mode == 0 ? (own & 0x7FFFu) != 0 : (own >> 15) != 0;
         if (own > VF_VOXEL_FREE && isB && ea.noise[gi % ea.nnoise] < ea.prob) {
-            unsigned count = 0, visited = 0;
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx)
-#pragma unroll
-                for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                    for (int dz = -1; dz <= 1; ++dz) {
-                        const uint16_t raw = s[f_at(x + dx, y + dy, z + dz)];
-                        const bool inside = gx + dx >= 0 && gx + dx < d.X && gy + dy >= 0 && gy + dy < d.Y && gz + dz >= 0 && gz + dz < d.Z;
-                        visited += inside;
-                        const unsigned bit = (dx + 1) * 9 + (dy + 1) * 3 + (dz + 1);
-                        count += (inside && raw == own && (ea.maskbits >> bit & 1u));
-                    }
-            const float activation = __fdiv_rn((float)count, (float)visited);
+            unsigned count = 0;
+            for (unsigned m = ea.maskbits; m; m &= m - 1) count += ctr[c_win_off[__ffs(m) - 1]] == own;  // mask bits are warp-uniform
+            const int vx = 1 + (gx > 0) + (gx < d.X - 1), vy = 1 + (gy > 0) + (gy < d.Y - 1), vz = 1 + (gz > 0) + (gz < d.Z - 1);
+            const float activation = __fdiv_rn((float)count, (float)(vx * vy * vz));
             if (activation < __fmul_rn(ea.activations, ea.thr)) out = VF_VOXEL_EMPTY;
         }
         changed = true;
@@ -266,14 +264,7 @@ __device__ __forceinline__ uint16_t stencil_voxel(const uint16_t* s, const Dims&
     } else {
         int count = -1;
 #pragma unroll
-        for (int dx = -1; dx <= 1; ++dx)
-#pragma unroll
-            for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                for (int dz = -1; dz <= 1; ++dz) {
-                    const bool inside = gx + dx >= 0 && gx + dx < d.X && gy + dy >= 0 && gy + dy < d.Y && gz + dz >= 0 && gz + dz < d.Z;
-                    count += (inside && s[f_at(x + dx, y + dy, z + dz)] == own);
-                }
+        for (int b = 0; b < 27; ++b) count += ctr[c_win_off[b]] == own;
         changed = true;
         return count < 6 ? (uint16_t)VF_VOXEL_EMPTY : own;
     }
@@ -334,7 +325,7 @@ __global__ void __launch_bounds__(256) stencil_fast_kernel(const uint16_t* __res
         const int gx = gx0 + x, gy = gy0 + y, gz = gz0 + zc * 8;
         if (gx >= d.X || gy >= d.Y || gz >= d.Z) continue;
         const unsigned su = summ[((x + 1) * HY + (y + 1)) * 8 + zc];
-        bool uniform = (su >> 16) != 0;
+        bool uniform = (su & 0x10000u) != 0;
 #pragma unroll
         for (int dx = 0; dx <= 2; ++dx)
 #pragma unroll
@@ -348,9 +339,9 @@ __global__ void __launch_bounds__(256) stencil_fast_kernel(const uint16_t* __res
     }
     __syncthreads();
 
-    // ---- queued chunks: exact per-voxel stencil, one voxel per thread per round
-    const int nt = ntasks * 8;
-    for (int q = t; q < nt; q += 256) {
+    // ---- queued chunks: exact per-voxel stencil, one voxel per thread per round (balanced across the CTA)
+    const int nq = ntasks;
+    for (int q = t; q < nq * 8; q += 256) {
         const int c = tasks[q >> 3], k = q & 7;
         const int zc = c & 7, y = (c >> 3) & 7, x = c >> 6, z = zc * 8 + k;
         const int gx = gx0 + x, gy = gy0 + y, gz = gz0 + z;
