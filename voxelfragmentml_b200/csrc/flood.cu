@@ -16,6 +16,7 @@
 // flood neighbourhood, through equal-fragId cells) that contains the fragment's lowest-prefix source; free the rest; re-flood
 // with order(cell) = index of that source.  One such round reaches the reference loop's fixed point (numDisjointVoxels == 0).
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "tiles.cuh"
@@ -31,7 +32,7 @@ constexpr uint32_t KEY_LIMIT = 0xFFFF0000u;  // keys at or above this cannot tak
 
 enum { ST_VISITS = 0, ST_ROUNDS = 1, ST_ERROR = 2, ST_FREED = 3, ST_MAXDIST = 4 };
 
-constexpr size_t kSmemBytes = (size_t)(kCells + 3 * kThreads + 8) * sizeof(uint32_t);
+constexpr size_t kSmemBytes = (size_t)(kCells + 4 * kThreads + 8) * sizeof(uint32_t);
 
 // ------------------------------------------------------------------------------------------------ key field set-up
 // phase 1: homogenize (FloodFracturer.cpp:99) folded in: EMPTY -> WALL, anything else -> UNREACHED.
@@ -86,9 +87,10 @@ __global__ void __launch_bounds__(256) enqueue_tiles_with_free_kernel(const uint
 }
 
 // ------------------------------------------------------------------------------------------------ tile load helpers
-template <int NNEIGH, typename T, typename LoadF>
-__device__ __forceinline__ void load_tile(uint32_t* sk, const T* __restrict__ src, const TileGeom& g, int gx0, int gy0, int gz0, uint32_t outside,
-                                          LoadF conv)
+// Stages tile + halo keys with 4-byte cp.async: a warp covers one 128-byte z-row per instruction and all ~40 rows of a warp
+// are in flight at once (a plain load -> store loop serialises one global round trip per row).  Caller waits + syncs.
+template <int NNEIGH>
+__device__ __forceinline__ void load_tile_async(uint32_t* sk, const uint32_t* __restrict__ src, const TileGeom& g, int gx0, int gy0, int gz0, uint32_t outside)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int row = warp; row < (TX + 2) * SY; row += kThreads / 32) {
@@ -96,17 +98,51 @@ __device__ __forceinline__ void load_tile(uint32_t* sk, const T* __restrict__ sr
         const int gx = gx0 + x, gy = gy0 + y;
         bool rowin = gx >= 0 && gx < g.X && gy >= 0 && gy < g.Y;
         if (NNEIGH == 6 && (x < 0 || x >= TX) && (y < 0 || y >= TY)) rowin = false;  // corner columns are never read
-        const T* base = src + ((size_t)(rowin ? gx : 0) * g.Y + (rowin ? gy : 0)) * g.Z;
+        const uint32_t* base = src + ((size_t)(rowin ? gx : 0) * g.Y + (rowin ? gy : 0)) * g.Z;
         const int gz = gz0 + lane;
-        sk[sidx(x, y, lane)] = (rowin && gz < g.Z) ? conv(base[gz]) : outside;
+        uint32_t* dst = &sk[sidx(x, y, lane)];
+        if (rowin && gz < g.Z) {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(base + gz) : "memory");
+        } else {
+            *dst = outside;
+        }
         if (lane < 2) {
             const int hz = lane ? gz0 + TZ : gz0 - 1;
-            sk[sidx(x, y, lane ? TZ : -1)] = (rowin && hz >= 0 && hz < g.Z) ? conv(base[hz]) : outside;
+            uint32_t* hd = &sk[sidx(x, y, lane ? TZ : -1)];
+            if (rowin && hz >= 0 && hz < g.Z) {
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(hd);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(base + hz) : "memory");
+            } else {
+                *hd = outside;
+            }
         }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ F2: key relaxation round
+template <int NNEIGH>
+__device__ __forceinline__ uint32_t min_neighbour_key(const uint32_t* sk, int x, int y, int z)
+{
+    uint32_t m;
+    if (NNEIGH == 6) {
+        m = min(min(sk[sidx(x - 1, y, z)], sk[sidx(x + 1, y, z)]), min(sk[sidx(x, y - 1, z)], sk[sidx(x, y + 1, z)]));
+        m = min(m, min(sk[sidx(x, y, z - 1)], sk[sidx(x, y, z + 1)]));
+    } else {
+        m = KEY_WALL;
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx)
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                for (int dz = -1; dz <= 1; ++dz)
+                    if (dx | dy | dz) m = min(m, sk[sidx(x + dx, y + dy, z + dz)]);
+    }
+    return m;
+}
+
 template <int NNEIGH>
 __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __restrict__ keys, TileGeom g, Worklist wl, uint32_t round)
 {
@@ -114,7 +150,8 @@ __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __re
     uint32_t* sk = sm;
     uint32_t* act = sm + kCells;        // [2][kThreads] wavefront bitmasks, one word per z-row
     uint32_t* chg = act + 2 * kThreads;  // [kThreads]    cells whose key was lowered during this visit
-    uint32_t* misc = chg + kThreads;     // [0..2] rotating wavefront population, [3] neighbour-tile mask
+    uint32_t* nw = chg + kThreads;       // [kThreads]    cells that are not walls
+    uint32_t* misc = nw + kThreads;      // [3] neighbour-tile mask
 
     const uint32_t count = wl.count[round % 3];
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -127,34 +164,20 @@ __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __re
         const int tz = tile % g.ntz, ty = (tile / g.ntz) % g.nty, tx = tile / (g.ntz * g.nty);
         const int gx0 = tx * TX, gy0 = ty * TY, gz0 = tz * TZ;
 
-        load_tile<NNEIGH>(sk, keys, g, gx0, gy0, gz0, KEY_WALL, [](uint32_t v) { return v; });
-        act[t] = 0, act[kThreads + t] = 0, chg[t] = 0;
+        load_tile_async<NNEIGH>(sk, keys, g, gx0, gy0, gz0, KEY_WALL);
         if (t < 4) misc[t] = 0;
         __syncthreads();
 
-        // ---- entry pass, warp per z-row, lane = z: repair every violated edge that ends in this tile; lowered cells form
-        //      the first wavefront (ballot -> one mask word per row)
+        // ---- entry pass, warp per z-row, lane = z: repair every violated edge that ends in this tile (sources may sit in the
+        //      halo); lowered cells form the first wavefront (ballot -> one mask word per row)
         {
-            unsigned lowered_total = 0;
             bool overflow = false;
             for (int r = warp * 32; r < warp * 32 + 32; ++r) {
                 const int x = r / TY, y = r % TY, z = lane;
                 const uint32_t v = sk[sidx(x, y, z)];
                 bool lowered = false;
                 if (v != KEY_WALL) {
-                    uint32_t m = KEY_WALL;
-                    if (NNEIGH == 6) {
-                        m = min(min(sk[sidx(x - 1, y, z)], sk[sidx(x + 1, y, z)]), min(sk[sidx(x, y - 1, z)], sk[sidx(x, y + 1, z)]));
-                        m = min(m, min(sk[sidx(x, y, z - 1)], sk[sidx(x, y, z + 1)]));
-                    } else {
-#pragma unroll
-                        for (int dx = -1; dx <= 1; ++dx)
-#pragma unroll
-                            for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                                for (int dz = -1; dz <= 1; ++dz)
-                                    if (dx | dy | dz) m = min(m, sk[sidx(x + dx, y + dy, z + dz)]);
-                    }
+                    const uint32_t m = min_neighbour_key<NNEIGH>(sk, x, y, z);
                     if (m < KEY_LIMIT) {
                         const uint32_t c = m + KEY_LEVEL;
                         if (c < v) {
@@ -165,64 +188,76 @@ __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __re
                         overflow = true;
                     }
                 }
-                const unsigned b = __ballot_sync(kFull, lowered);
-                if (lane == 0 && b) {
+                const unsigned b = __ballot_sync(kFull, lowered), w = __ballot_sync(kFull, v != KEY_WALL);
+                if (lane == 0) {
                     act[r] = b;
                     chg[r] = b;
-                    lowered_total += __popc(b);
+                    nw[r] = w;
                 }
             }
-            if (lane == 0 && lowered_total) atomicAdd(&misc[0], lowered_total);
             if (overflow) atomicOr(&wl.stats[ST_ERROR], 1u);
         }
         __syncthreads();
 
-        // ---- wavefront iterations in shared memory, thread per z-row; one barrier per step
-        for (int it = 0; it < TX * TY * TZ; ++it) {
-            if (misc[it % 3] == 0) break;
-            if (t == 0) misc[(it + 2) % 3] = 0;
-            const int cur = it & 1;
-            unsigned word = act[cur * kThreads + t];
-            act[cur * kThreads + t] = 0;
-            const int x = t / TY, y = t % TY;
-            uint32_t* nxt = act + (cur ^ 1) * kThreads;
-            while (word) {
-                const int z = __ffs(word) - 1;
-                word &= word - 1;
-                const uint32_t kv = sk[sidx(x, y, z)];
-                if (kv >= KEY_LIMIT) {
-                    atomicOr(&wl.stats[ST_ERROR], 1u);
-                    continue;
-                }
-                const uint32_t kb = kv + KEY_LEVEL;
-                auto relax = [&](int nx, int ny, int nz) {
-                    if (nx < 0 || nx >= TX || ny < 0 || ny >= TY || nz < 0 || nz >= TZ) return;  // halo cells belong to other tiles
-                    uint32_t* p = &sk[sidx(nx, ny, nz)];
-                    const uint32_t c = *p;
-                    if (c != KEY_WALL && kb < c) {
-                        const uint32_t old = atomicMin(p, kb);
-                        if (kb < old) {
-                            const int r2 = nx * TY + ny;
-                            const unsigned bit = 1u << nz;
-                            const unsigned o = atomicOr(&nxt[r2], bit);
-                            if (!(o & bit)) atomicAdd(&misc[(it + 1) % 3], 1u);
-                            atomicOr(&chg[r2], bit);
+        // ---- wavefront steps in shared memory, pull style, no atomics, one barrier per step.  Thread t owns row t % 8 * 32 ... i.e.
+        //      row (lane * 8 + warp): rows are dealt round-robin so that a flat front (16 rows of one x-plane) spreads over all
+        //      warps.  Step: candidates of my row = (wavefront of my row shifted by +-1 in z | wavefronts of the neighbouring
+        //      rows) & not-wall; every candidate cell takes min(neighbour keys) + 1 level; the cells that got lower are the next
+        //      wavefront (ballot).  Keys only decrease and every written value is the key of a real path, so reading a neighbour
+        //      while another warp lowers it is harmless; the fixed point is the same.
+        {
+            const int myrow = lane * 8 + warp, mx = myrow / TY, my = myrow % TY;
+            for (int it = 0; it < TX * TY * TZ; ++it) {
+                const uint32_t* cur = act + (it & 1) * kThreads;
+                uint32_t* nxt = act + ((it & 1) ^ 1) * kThreads;
+                unsigned a = cur[myrow];
+                unsigned cand = (a << 1) | (a >> 1);
+                if (NNEIGH == 26) cand |= a;
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx)
+#pragma unroll
+                    for (int dy = -1; dy <= 1; ++dy) {
+                        if ((dx | dy) == 0) continue;
+                        if (NNEIGH == 6 && dx != 0 && dy != 0) continue;
+                        const int nx = mx + dx, ny = my + dy;
+                        if (nx < 0 || nx >= TX || ny < 0 || ny >= TY) continue;
+                        const unsigned an = cur[nx * TY + ny];
+                        cand |= NNEIGH == 26 ? (an | (an << 1) | (an >> 1)) : an;
+                    }
+                cand &= nw[myrow];
+                nxt[myrow] = 0;
+                unsigned rows = __ballot_sync(kFull, cand != 0);  // bit l <-> row l * 8 + warp
+                bool any = false, overflow = false;
+                while (rows) {
+                    const int l = __ffs(rows) - 1;
+                    rows &= rows - 1;
+                    const unsigned cw = __shfl_sync(kFull, cand, l);
+                    const int r = l * 8 + warp, x = r / TY, y = r % TY, z = lane;
+                    bool lowered = false;
+                    if (cw >> lane & 1u) {
+                        const uint32_t m = min_neighbour_key<NNEIGH>(sk, x, y, z);
+                        if (m < KEY_LIMIT) {
+                            const uint32_t c = m + KEY_LEVEL;
+                            if (c < sk[sidx(x, y, z)]) {
+                                sk[sidx(x, y, z)] = c;
+                                lowered = true;
+                            }
+                        } else if (m < KEY_UNREACHED) {
+                            overflow = true;
                         }
                     }
-                };
-                if (NNEIGH == 6) {
-                    relax(x - 1, y, z), relax(x + 1, y, z), relax(x, y - 1, z), relax(x, y + 1, z), relax(x, y, z - 1), relax(x, y, z + 1);
-                } else {
-#pragma unroll
-                    for (int dx = -1; dx <= 1; ++dx)
-#pragma unroll
-                        for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                            for (int dz = -1; dz <= 1; ++dz)
-                                if (dx | dy | dz) relax(x + dx, y + dy, z + dz);
+                    const unsigned b = __ballot_sync(kFull, lowered);
+                    if (b) {
+                        any = true;
+                        if (lane == 0) {
+                            nxt[r] = b;
+                            chg[r] |= b;
+                        }
+                    }
                 }
+                if (overflow) atomicOr(&wl.stats[ST_ERROR], 1u);
+                if (!__syncthreads_or(any)) break;
             }
-            __syncthreads();
         }
 
         // ---- write back the rows that changed (warp per row: one 128-byte line), wake the neighbours that saw them change
