@@ -165,6 +165,23 @@ vf_status vf_fracture_naive(vf_grid* g, const uint32_t* seeds, uint32_t nseeds, 
  * dfunc MANHATTAN -> 6-neighbourhood, otherwise 26 (FloodFracturer.cpp:114).  id_bits 0/8 or 15 (see vf_params). */
 vf_status vf_fracture_flood(vf_grid* g, const uint32_t* seeds, uint32_t nseeds, int dfunc, int id_bits, vf_flood_stats* stats);
 
+/* ------------------------------------------------------------------ F2 on one grid split into x-slabs over several GPUs (new: the reference is single-GPU) */
+/* A slab is an ordinary vf_grid of (xs + 2) x Y x Z cells: xs owned planes plus one halo plane on each side that mirrors the
+ * neighbour GPU's boundary plane (EMPTY where the global grid ends).  keys_dev is caller-owned device memory of the same shape
+ * (uint32 per cell) so that the host layer can hand its boundary planes to NCCL.  seeds_local = uint32[n][4] {slab-local x
+ * (halo planes included), y, z, ORDER in the global seed list}.  Protocol: init; repeat { relax; send the two owned boundary
+ * planes (vf_flood_slab_boundary_ptr) to the neighbours; ingest what they sent; all-reduce the change counts } until zero;
+ * finalize writes labels (seeds_global[order].w) into the slab grid.  Only the 15-bit id layout is supported (no extra seeds).
+ * A slab session uses its context's tile scratch: do not interleave other flood / cleanup calls on the same context. */
+typedef struct vf_slab vf_slab;
+vf_status vf_flood_slab_init(vf_grid* slab_grid, uint32_t* keys_dev, const uint32_t* seeds_local, uint32_t nseeds, int dfunc, int has_lo, int has_hi,
+                             vf_slab** out);
+vf_status vf_flood_slab_relax(vf_slab* s, uint64_t* changed_cells);
+void*     vf_flood_slab_boundary_ptr(vf_slab* s, int side /* 0 = towards lower x, 1 = towards higher x */);
+vf_status vf_flood_slab_ingest(vf_slab* s, int side, const uint32_t* plane_dev, uint64_t* changed_cells);
+vf_status vf_flood_slab_finalize(vf_slab* s, const uint32_t* seeds_global, uint32_t nseeds_total, uint32_t* max_dist);
+void      vf_flood_slab_destroy(vf_slab* s);
+
 /* ------------------------------------------------------------------ C1..C4: cleanup */
 vf_status vf_remove_isolated_regions(vf_grid* g, const uint32_t* seeds, uint32_t nseeds); /* NaiveFracturer::removeIsolatedRegionsCPU semantics, NaiveFracturer.cpp:111-150 */
 vf_status vf_detect_boundaries(vf_grid* g, int boundary_size);           /* RegularGrid::detectBoundaries, RegularGrid.cpp:64-80 */

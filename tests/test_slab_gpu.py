@@ -1,0 +1,60 @@
+"""cfg5 in miniature: slab-partitioned flood with the CUDA slab kernels (several slabs on one GPU, exchange by device copies)
+against the single-address-space oracle, bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import pick_seeds, random_blob_grid
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import voxelfragmentml_b200 as vf
+
+    c = vf.Context(0)
+    yield c
+    c.close()
+
+
+def _run(ctx, g, seeds, dfunc, nslabs):
+    from voxelfragmentml_b200 import slab
+
+    parts = slab.partition(g.shape[0], nslabs)
+    slabs = [slab.GpuSlab(ctx, slab.slab_with_halo(g, x0, x1), seeds, x0, x1, g.shape[0], dfunc) for x0, x1 in parts]
+    iters, moved = slab.run_local(slabs)
+    got = np.concatenate([s.finalize() for s in slabs])
+    for s in slabs:
+        s.close()
+    return got, iters, moved
+
+
+@pytest.mark.parametrize("dfunc", [1, 2])
+@pytest.mark.parametrize("nslabs", [2, 3, 8])
+def test_vessel_slabs(ctx, orc, vessel_grid, dfunc, nslabs):
+    seeds, _ = orc.seed_uniform(orc.Rng(80), vessel_grid, 16)
+    want, st = orc.flood(vessel_grid.copy(), seeds, dfunc, id_bits=15)
+    got, iters, moved = _run(ctx, vessel_grid, seeds, dfunc, nslabs)
+    assert np.array_equal(got, want)
+    assert iters >= 2
+
+
+def test_many_labels_and_detours(ctx, orc):
+    g = random_blob_grid((70, 40, 48), 31, fill=0.5, smooth=1)
+    g[34:36, :, :30] = 0  # wall at the slab border: shortest paths leave the slab and come back
+    seeds = pick_seeds(g, 300, 2)  # > 254 labels: 15-bit ids (cfg5 uses 256 seeds)
+    for dfunc in (1, 2):
+        want, _ = orc.flood(g.copy(), seeds, dfunc, id_bits=15)
+        got, iters, _ = _run(ctx, g, seeds, dfunc, 2)
+        assert np.array_equal(got, want)
+
+
+def test_solid_vessel_256_seeds(ctx, orc):
+    """the cfg5 workload at 1/16 linear scale: analytic solid vessel, Manhattan, 256 seeds, 8 slabs"""
+    from voxelfragmentml_b200 import synth
+
+    g = synth.solid_vessel_grid(128)
+    seeds, _ = orc.seed_uniform(orc.Rng(80), g, 256, location=orc.BOTH)
+    want, _ = orc.flood(g.copy(), seeds, 1, id_bits=15)
+    got, iters, moved = _run(ctx, g, seeds, 1, 8)
+    assert np.array_equal(got, want) and got.max() == 257

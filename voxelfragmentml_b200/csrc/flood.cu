@@ -30,7 +30,7 @@ constexpr int KEY_SHIFT = 15;
 constexpr uint32_t KEY_LEVEL = 1u << KEY_SHIFT;
 constexpr uint32_t KEY_LIMIT = 0xFFFF0000u;  // keys at or above this cannot take another level (dist >= 2^17 - 2)
 
-enum { ST_VISITS = 0, ST_ROUNDS = 1, ST_ERROR = 2, ST_FREED = 3, ST_MAXDIST = 4 };
+enum { ST_VISITS = 0, ST_ROUNDS = 1, ST_ERROR = 2, ST_FREED = 3, ST_MAXDIST = 4, ST_CHANGED = 5 };
 
 constexpr size_t kSmemBytes = (size_t)(kCells + 4 * kThreads + 8) * sizeof(uint32_t);
 
@@ -72,7 +72,20 @@ __global__ void flood_seed_kernel(uint32_t* __restrict__ keys, TileGeom g, Workl
     }
 }
 
-// phase 2 worklist: every tile that holds a freed (FREE) cell next to... simply every tile holding a FREE cell.
+// slab mode: the seed's order in the GLOBAL seed list travels in .w
+__global__ void flood_seed_order_kernel(uint32_t* __restrict__ keys, TileGeom g, Worklist wl, const ushort4* __restrict__ seeds, int S, uint32_t round)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int s = 0; s < S; ++s) {
+        const ushort4 sd = seeds[s];
+        keys[((size_t)sd.x * g.Y + sd.y) * g.Z + sd.z] = (uint32_t)sd.w;
+        const uint32_t tile = ((uint32_t)(sd.x / TX) * g.nty + sd.y / TY) * g.ntz + sd.z / TZ;
+        wl.occ[tile] = 1;
+        enqueue_tile(wl, tile, round);
+    }
+}
+
+// phase 2 worklist: every tile that holds a freed (FREE) cell.
 __global__ void __launch_bounds__(256) enqueue_tiles_with_free_kernel(const uint16_t* __restrict__ grid, TileGeom g, Worklist wl, uint32_t round)
 {
     const size_t n = (size_t)g.X * g.Y * g.Z;
@@ -175,8 +188,11 @@ __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __re
             for (int r = warp * 32; r < warp * 32 + 32; ++r) {
                 const int x = r / TY, y = r % TY, z = lane;
                 const uint32_t v = sk[sidx(x, y, z)];
+                // slab mode: halo planes are copies of a neighbour GPU's cells — sources only
+                const bool fixed = (g.fix_lo && gx0 + x == 0) || (g.fix_hi && gx0 + x == g.X - 1);
+                const bool relaxable = v != KEY_WALL && !fixed;
                 bool lowered = false;
-                if (v != KEY_WALL) {
+                if (relaxable) {
                     const uint32_t m = min_neighbour_key<NNEIGH>(sk, x, y, z);
                     if (m < KEY_LIMIT) {
                         const uint32_t c = m + KEY_LEVEL;
@@ -188,7 +204,7 @@ __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __re
                         overflow = true;
                     }
                 }
-                const unsigned b = __ballot_sync(kFull, lowered), w = __ballot_sync(kFull, v != KEY_WALL);
+                const unsigned b = __ballot_sync(kFull, lowered), w = __ballot_sync(kFull, relaxable);
                 if (lane == 0) {
                     act[r] = b;
                     chg[r] = b;
@@ -261,12 +277,15 @@ __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __re
         }
 
         // ---- write back the rows that changed (warp per row: one 128-byte line), wake the neighbours that saw them change
+        unsigned nchanged = 0;
         for (int r = warp * 32; r < warp * 32 + 32; ++r) {
             if (chg[r]) {
                 const int x = r / TY, y = r % TY, gz = gz0 + lane;
                 if (gz < g.Z && gx0 + x < g.X && gy0 + y < g.Y) keys[((size_t)(gx0 + x) * g.Y + gy0 + y) * g.Z + gz] = sk[sidx(x, y, lane)];
+                nchanged += __popc(chg[r]);
             }
         }
+        if (lane == 0 && nchanged) atomicAdd(&wl.stats[ST_CHANGED], nchanged);
         if (t == 0) atomicAdd(&wl.stats[ST_VISITS], 1u);
         enqueue_neighbours<NNEIGH>(g, wl, tx, ty, tz, chg[t], &misc[3], round + 1);
         __syncthreads();
@@ -471,3 +490,149 @@ extern "C" vf_status vf_remove_isolated_regions(vf_grid* grid, const uint32_t* s
     VF_TRY(vf_upload_seeds(c, seeds, nseeds, grid->X, grid->Y, grid->Z, &d_seeds));
     return vf_k_keep_seed_components(grid, d_seeds, (int)nseeds, 0, 6, nullptr);
 }
+
+
+// ================================================================================================ slab-partitioned flood (multi-GPU)
+// One very large grid is cut into slabs of the slowest axis x (contiguous in the reference layout; BASELINE.json calls them
+// "z-slabs").  Each GPU holds its slab plus one halo plane on either side as an ordinary grid of (xs + 2) x Y x Z
+// cells and a key field of the same shape (caller-owned device memory, so the host layer can hand the boundary planes to NCCL).
+// Because the key field's fixed point is schedule independent, the protocol is simply: relax the slab to a local fixed point with
+// the halo planes held fixed, send the two owned boundary planes to the neighbours, ingest the planes received (lower the halo
+// copy, wake the tiles next to it), repeat until an all-reduced change counter is zero.  Collectives stay outside this library:
+// vf_flood_slab_boundary_ptr / vf_flood_slab_ingest take and return raw device pointers.
+struct vf_slab {
+    vf_grid* grid;
+    uint32_t* keys;
+    Job job;
+    int nneigh;
+    uint32_t* d_changed;  // ingest counter
+};
+
+namespace {
+
+__global__ void __launch_bounds__(256) slab_ingest_kernel(uint32_t* __restrict__ halo, const uint32_t* __restrict__ recv, TileGeom g, Worklist wl, int tx,
+                                                          uint32_t round, uint32_t* __restrict__ changed)
+{
+    const size_t n = (size_t)g.Y * g.Z;
+    unsigned c = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t r = recv[i];
+        if (r < halo[i]) {
+            halo[i] = r;
+            ++c;
+            const int z = (int)(i % g.Z), y = (int)(i / g.Z);
+            const uint32_t tile = ((uint32_t)tx * g.nty + y / TY) * g.ntz + z / TZ;
+            if (wl.stamp[tile] != round) {
+                wl.occ[tile] = 1;
+                enqueue_tile(wl, tile, round);
+            }
+        }
+    }
+    c = __reduce_add_sync(kFull, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(changed, c);
+}
+
+// labels of the halo planes decide wall / not wall there: the caller uploads the neighbours' boundary label planes with the slab
+}  // namespace
+
+extern "C" vf_status vf_flood_slab_init(vf_grid* slab_grid, uint32_t* keys_dev, const uint32_t* seeds_local, uint32_t nseeds, int dfunc, int has_lo, int has_hi,
+                                        vf_slab** out)
+{
+    VF_REQUIRE(slab_grid && keys_dev && out, VF_ERR_INVALID_ARGUMENT, "null argument");
+    vf_ctx* c = slab_grid->ctx;
+    VF_TRY(vf_enter(c));
+    VF_REQUIRE(dfunc >= 0 && dfunc <= 2, VF_ERR_INVALID_DISTANCE, "Invalid distance function %d", dfunc);
+    VF_REQUIRE(nseeds < 32768, VF_ERR_CAPACITY, "flood: too many seeds");
+    VF_REQUIRE(slab_grid->X >= 3, VF_ERR_INVALID_ARGUMENT, "slab needs at least one owned plane between its halo planes");
+    vf_slab* s = new vf_slab();
+    s->grid = slab_grid;
+    s->keys = keys_dev;
+    s->nneigh = dfunc == VF_MANHATTAN ? 6 : 26;
+    VF_TRY(job_begin(slab_grid, s->job));
+    s->job.g.fix_lo = has_lo ? 1 : 0;
+    s->job.g.fix_hi = has_hi ? 1 : 0;
+    VF_TRY(vf_scratch_reserve(c, c->small, 1 << 20));
+    s->d_changed = (uint32_t*)((char*)c->small.ptr + (704 << 10));
+    flood_init_keys_kernel<false><<<s->job.blocks_stream, 256, 0, c->stream>>>(slab_grid->d, keys_dev, s->job.g, s->job.wl.occ, nullptr);
+    VF_LAUNCHED(c);
+    if (nseeds) {
+        // seeds_local: {x (slab-local, halo planes included), y, z, GLOBAL order}.  The order goes into the key, labels are
+        // looked up at finalize time from the global seed list.
+        VF_REQUIRE((size_t)nseeds * sizeof(ushort4) <= 65536, VF_ERR_CAPACITY, "too many seeds in one slab");
+        VF_CUDA(cudaStreamSynchronize(c->stream));
+        ushort4* h = (ushort4*)c->pinned;
+        for (uint32_t i = 0; i < nseeds; ++i) {
+            VF_REQUIRE(seeds_local[4 * i] < slab_grid->X && seeds_local[4 * i + 1] < slab_grid->Y && seeds_local[4 * i + 2] < slab_grid->Z, VF_ERR_INVALID_ARGUMENT,
+                       "slab seed %u outside the slab", i);
+            h[i] = make_ushort4((unsigned short)seeds_local[4 * i], (unsigned short)seeds_local[4 * i + 1], (unsigned short)seeds_local[4 * i + 2],
+                                (unsigned short)seeds_local[4 * i + 3]);
+        }
+        ushort4* d_seeds = (ushort4*)c->small.ptr;
+        VF_CUDA(cudaMemcpyAsync(d_seeds, h, (size_t)nseeds * sizeof(ushort4), cudaMemcpyHostToDevice, c->stream));
+        flood_seed_order_kernel<<<1, 32, 0, c->stream>>>(keys_dev, s->job.g, s->job.wl, d_seeds, (int)nseeds, s->job.round);
+        VF_LAUNCHED(c);
+    }
+    *out = s;
+    return VF_OK;
+}
+
+extern "C" vf_status vf_flood_slab_relax(vf_slab* s, uint64_t* changed)
+{
+    VF_REQUIRE(s != nullptr, VF_ERR_INVALID_ARGUMENT, "null slab");
+    vf_ctx* c = s->grid->ctx;
+    VF_TRY(vf_enter(c));
+    VF_CUDA(cudaMemsetAsync(s->job.wl.stats + ST_CHANGED, 0, 4, c->stream));
+    VF_TRY(s->nneigh == 6 ? flood_phase<6>(s->job, s->keys) : flood_phase<26>(s->job, s->keys));
+    uint32_t hs[8];
+    VF_TRY(read_stats(s->job, hs));
+    VF_REQUIRE(hs[ST_ERROR] == 0, VF_ERR_CAPACITY, "flood: geodesic distance exceeds the 17-bit key field");
+    if (changed) *changed = hs[ST_CHANGED];
+    return VF_OK;
+}
+
+extern "C" void* vf_flood_slab_boundary_ptr(vf_slab* s, int side)
+{
+    if (!s) return nullptr;
+    const size_t plane = (size_t)s->grid->Y * s->grid->Z;
+    return side == 0 ? (void*)(s->keys + plane) : (void*)(s->keys + plane * (s->grid->X - 2));  // owned plane next to the lo / hi halo
+}
+
+extern "C" vf_status vf_flood_slab_ingest(vf_slab* s, int side, const uint32_t* plane_dev, uint64_t* changed)
+{
+    VF_REQUIRE(s && plane_dev, VF_ERR_INVALID_ARGUMENT, "null argument");
+    vf_ctx* c = s->grid->ctx;
+    VF_TRY(vf_enter(c));
+    const size_t plane = (size_t)s->grid->Y * s->grid->Z;
+    uint32_t* halo = side == 0 ? s->keys : s->keys + plane * (s->grid->X - 1);
+    VF_CUDA(cudaMemsetAsync(s->d_changed, 0, 4, c->stream));
+    slab_ingest_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>(halo, plane_dev, s->job.g, s->job.wl, side == 0 ? 0 : s->job.g.ntx - 1, s->job.round, s->d_changed);
+    VF_LAUNCHED(c);
+    VF_CUDA(cudaMemcpyAsync(s->job.h_mail, s->d_changed, 4, cudaMemcpyDeviceToHost, c->stream));
+    VF_CUDA(cudaStreamSynchronize(c->stream));
+    if (changed) *changed = s->job.h_mail[0];
+    return VF_OK;
+}
+
+extern "C" vf_status vf_flood_slab_finalize(vf_slab* s, const uint32_t* seeds_global, uint32_t nseeds_total, uint32_t* max_dist)
+{
+    VF_REQUIRE(s && seeds_global, VF_ERR_INVALID_ARGUMENT, "null argument");
+    vf_ctx* c = s->grid->ctx;
+    VF_TRY(vf_enter(c));
+    ushort4* d_seeds = nullptr;
+    // only .w is read by the finalize kernel; coordinates are global and may exceed the slab, so upload without range checks
+    VF_REQUIRE((size_t)nseeds_total * sizeof(ushort4) <= 65536, VF_ERR_CAPACITY, "too many seeds");
+    VF_CUDA(cudaStreamSynchronize(c->stream));
+    ushort4* h = (ushort4*)c->pinned;
+    for (uint32_t i = 0; i < nseeds_total; ++i) h[i] = make_ushort4(0, 0, 0, (unsigned short)seeds_global[4 * i + 3]);
+    d_seeds = (ushort4*)c->small.ptr;
+    VF_CUDA(cudaMemcpyAsync(d_seeds, h, (size_t)nseeds_total * sizeof(ushort4), cudaMemcpyHostToDevice, c->stream));
+    VF_CUDA(cudaMemsetAsync(s->job.wl.stats + ST_MAXDIST, 0, 4, c->stream));
+    flood_finalize_kernel<<<s->job.blocks_stream, 256, 0, c->stream>>>(s->keys, s->grid->d, s->grid->n(), d_seeds, 0xFFFFu, s->job.wl.stats);
+    VF_LAUNCHED(c);
+    uint32_t hs[8];
+    VF_TRY(read_stats(s->job, hs));
+    if (max_dist) *max_dist = hs[ST_MAXDIST];
+    return VF_OK;
+}
+
+extern "C" void vf_flood_slab_destroy(vf_slab* s) { delete s; }

@@ -22,6 +22,7 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 struct TileGeom {
     int X, Y, Z;        // grid dims
     int ntx, nty, ntz;  // tiles per axis
+    int fix_lo, fix_hi; // slab mode: plane x = 0 / x = X-1 is a halo copy owned by a neighbour GPU: readable, never relaxed here
     __host__ __device__ int ntiles() const { return ntx * nty * ntz; }
 };
 
@@ -30,6 +31,7 @@ inline TileGeom make_geom(uint32_t X, uint32_t Y, uint32_t Z)
     TileGeom g;
     g.X = (int)X, g.Y = (int)Y, g.Z = (int)Z;
     g.ntx = (g.X + TX - 1) / TX, g.nty = (g.Y + TY - 1) / TY, g.ntz = (g.Z + TZ - 1) / TZ;
+    g.fix_lo = g.fix_hi = 0;
     return g;
 }
 

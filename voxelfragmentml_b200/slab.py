@@ -1,0 +1,141 @@
+"""Slab-partitioned flood fill over several GPUs (BASELINE config 5; new — the reference is single-GPU).
+
+The grid is cut into slabs of the slowest axis x.  The flood's key field has a schedule-independent fixed point, so every rank
+relaxes its slab to a local fixed point, the owned boundary planes travel to the neighbours (NCCL send/recv over NVLink through
+torch.distributed, or plain copies when several slabs live in one process), the received planes are ingested, and the loop ends
+when an all-reduced change counter is zero.  This module holds the host logic only; every cell is touched by libvoxfrag kernels
+(or, in the CPU tests, by a stand-in backend with the same four methods)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import check, ptr
+
+
+def partition(X: int, world: int):
+    """Balanced contiguous x-ranges [(x0, x1), ...], every rank gets at least one plane."""
+    if world > X:
+        raise ValueError("more slabs than planes")
+    base, rem = divmod(X, world)
+    out, x = [], 0
+    for r in range(world):
+        n = base + (1 if r < rem else 0)
+        out.append((x, x + n))
+        x += n
+    return out
+
+
+def localise_seeds(seeds_global, x0: int, x1: int):
+    """Seeds whose x lies in the slab or its halo planes -> {local x (halo included), y, z, global order}."""
+    s = np.asarray(seeds_global, dtype=np.int64)
+    order = np.arange(len(s))
+    keep = (s[:, 0] >= x0 - 1) & (s[:, 0] <= x1)
+    loc = np.stack([s[keep, 0] - (x0 - 1), s[keep, 1], s[keep, 2], order[keep]], axis=1)
+    return np.ascontiguousarray(loc, dtype=np.uint32)
+
+
+def slab_with_halo(grid_global: np.ndarray, x0: int, x1: int) -> np.ndarray:
+    """Planes x0-1 .. x1 of a host grid, EMPTY where the global grid ends (test / small-scale helper)."""
+    X = grid_global.shape[0]
+    out = np.zeros((x1 - x0 + 2,) + grid_global.shape[1:], dtype=grid_global.dtype)
+    lo, hi = max(x0 - 1, 0), min(x1 + 1, X)
+    out[lo - (x0 - 1) : hi - (x0 - 1)] = grid_global[lo:hi]
+    return out
+
+
+class GpuSlab:
+    """One slab on one GPU.  `labels_with_halo`: host uint16 [(xs+2), Y, Z]; keys live in a torch tensor so NCCL can send planes."""
+
+    def __init__(self, ctx, labels_with_halo: np.ndarray, seeds_global, x0: int, x1: int, X: int, dfunc: int):
+        import torch
+
+        from .api import RegularGrid
+
+        self.ctx, self.x0, self.x1 = ctx, x0, x1
+        self.seeds_global = np.ascontiguousarray(seeds_global, dtype=np.uint32)
+        self.shape = tuple(labels_with_halo.shape)
+        self.grid = RegularGrid(ctx, self.shape)
+        self.grid.updateSSBO(labels_with_halo)
+        self.plane = self.shape[1] * self.shape[2]
+        self.keys = torch.empty(self.shape[0] * self.plane, dtype=torch.int32, device=f"cuda:{ctx.device}")
+        self.recv = [torch.empty(self.plane, dtype=torch.int32, device=self.keys.device) for _ in range(2)]
+        loc = localise_seeds(self.seeds_global, x0, x1)
+        h = C.c_void_p()
+        check(ctx._lib.vf_flood_slab_init(self.grid._h, C.c_void_p(self.keys.data_ptr()), ptr(loc) if len(loc) else None, len(loc), int(dfunc),
+                                          int(x0 > 0), int(x1 < X), C.byref(h)))
+        self._h = h
+
+    def relax(self) -> int:
+        n = C.c_uint64(0)
+        check(self.ctx._lib.vf_flood_slab_relax(self._h, C.byref(n)))
+        return int(n.value)
+
+    def boundary(self, side: int):
+        """owned plane next to the lo (0) / hi (1) halo, as a contiguous torch view of the key field"""
+        k = self.keys.view(self.shape[0], self.plane)
+        return k[1] if side == 0 else k[self.shape[0] - 2]
+
+    def ingest(self, side: int, plane) -> int:
+        n = C.c_uint64(0)
+        check(self.ctx._lib.vf_flood_slab_ingest(self._h, side, C.c_void_p(plane.data_ptr()), C.byref(n)))
+        return int(n.value)
+
+    def finalize(self) -> np.ndarray:
+        md = C.c_uint32(0)
+        check(self.ctx._lib.vf_flood_slab_finalize(self._h, ptr(self.seeds_global), len(self.seeds_global), C.byref(md)))
+        self.max_dist = md.value
+        return self.grid.updateGrid()[1:-1]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.ctx._lib.vf_flood_slab_destroy(self._h)
+            self._h = None
+            self.grid.close()
+
+
+def run_local(slabs):
+    """All slabs in one process (one GPU or a CPU stand-in): exchange = direct copies.  Returns (iterations, halo bytes moved)."""
+    iters, moved = 0, 0
+    while True:
+        iters += 1
+        changed = sum(s.relax() for s in slabs)
+        for r in range(len(slabs) - 1):
+            up, dn = slabs[r].boundary(1), slabs[r + 1].boundary(0)
+            moved += 2 * up.numel() * 4
+            changed += slabs[r + 1].ingest(0, up)
+            changed += slabs[r].ingest(1, dn)
+        if changed == 0:
+            return iters, moved
+
+
+def run_distributed(slab, rank: int, world: int, dist, make_recv=None):
+    """One slab per rank; planes travel with dist.batch_isend_irecv, the change counter with all_reduce.
+    `slab` needs relax / boundary / ingest; `make_recv(side)` returns a receive buffer (defaults to slab.recv[side])."""
+    import torch
+
+    iters, moved = 0, 0
+    while True:
+        iters += 1
+        changed = slab.relax()
+        ops, got = [], []
+        for side, peer in ((0, rank - 1), (1, rank + 1)):
+            if 0 <= peer < world:
+                buf = slab.recv[side] if make_recv is None else make_recv(side)
+                ops.append(dist.P2POp(dist.isend, slab.boundary(side), peer))
+                ops.append(dist.P2POp(dist.irecv, buf, peer))
+                got.append((side, buf))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            if got and got[0][1].is_cuda:
+                torch.cuda.synchronize()
+        for side, buf in got:
+            moved += buf.numel() * 4
+            changed += slab.ingest(side, buf)
+        t = torch.tensor([changed], dtype=torch.int64, device=got[0][1].device if got else "cpu")
+        dist.all_reduce(t)
+        if int(t.item()) == 0:
+            return iters, moved
