@@ -348,6 +348,143 @@ def run_reference(args):
     }))
 
 
+
+# ------------------------------------------------------------------------------------------------ secondary workloads (not the driver's default)
+def _dist_setup():
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    return rank, local_rank, world, dist
+
+
+def run_slab(args):
+    """BASELINE config 5: one n^3 analytic solid, FLOOD MANHATTAN, 256 seeds (15-bit ids), x-slabs over the ranks with key-plane
+    exchange over NCCL.  Labels are bit-exact against the single-address-space oracle at small n (tests/test_slab_gpu.py)."""
+    import torch
+
+    import voxelfragmentml_b200 as vf
+    from voxelfragmentml_b200 import slab, synth
+
+    rank, local_rank, world, dist = _dist_setup()
+    ctx = vf.Context(local_rank)
+    n = args.size
+    params = synth.solid_vessel_params(0)
+    seeds = synth.solid_vessel_seeds(n, args.seeds, params, 80)
+    x0, x1 = slab.partition(n, world)[rank]
+    lib = vf._capi.load()
+
+    def fill(grid):
+        vf._capi.check(lib.vf_synth_solid_vessel(grid._h, x0 - 1, n, *params))
+
+    times, iters, moved, maxd = [], 0, 0, 0
+    for it in range(args.warmup + args.steps):
+        s = slab.GpuSlab(ctx, fill, seeds, x0, x1, n, 1, shape=(x1 - x0 + 2, n, n))  # init: keys + seeds (timed below from relax on)
+        ctx.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if world > 1:
+            iters, moved = slab.run_distributed(s, rank, world, dist)
+        else:
+            iters, moved = slab.run_local([s])
+        s.finalize(download=False)
+        ctx.synchronize()
+        dt = time.perf_counter() - t0
+        maxd = s.max_dist
+        s.close()
+        if it >= args.warmup:
+            times.append(dt)
+    total = float(sum(times))
+    if dist is not None:
+        tt = torch.tensor([total, float(moved), float(maxd)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total, moved, maxd = float(tt[0]), float(tt[1]), float(tt[2])
+    if rank == 0:
+        print(json.dumps({
+            "metric": "Gvoxels/s flood-fragmented, one grid over N GPUs", "value": n**3 * args.steps / total / 1e9, "unit": "Gvoxels/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32 keys (dist<<15|order)", "data": "synthetic",
+            "config": {"workload": f"cfg5-slab: {n}^3 analytic solid vessel, FLOOD MANHATTAN, {args.seeds} seeds, {world} x-slabs, NCCL key-plane exchange",
+                       "exchange_iterations": iters, "halo_bytes_per_rank": moved, "max_geodesic_distance": maxd},
+        }))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_batch(args):
+    """BASELINE config 4: dataset generation — per mesh: SAT voxelization at 256-max, then 10 fragmentations with the reference's
+    dataset defaults (FLOOD + CHEBYSHEV, numSeeds = nf cycling 2..10, numExtraSeeds = 2 nf, detectBoundaries, histogram, undoMask;
+    CADScene.cpp:294-332, FragmentationProcedure.h:12-13).  Mesh m goes to rank m mod N with RNG seed 80 + m, so results do not
+    depend on N.  No collective on the data path."""
+    import torch
+
+    import voxelfragmentml_b200 as vf
+    from voxelfragmentml_b200 import synth
+
+    rank, local_rank, world, dist = _dist_setup()
+    ctx = vf.Context(local_rank)
+    pool = [synth.vessel_mesh(i) for i in range(args.mesh_pool)]  # distinct shapes, generated once outside the timed region
+    lib = vf._capi.load()
+    grid = vf.RegularGrid(ctx, (256, 256, 256))  # allocated once at the clamp size, re-dimensioned per model (CADScene.cpp:529-543)
+    ctx.reserve((256, 256, 256))
+    my = [m for m in range(args.meshes) if m % world == rank]
+    checksum = 0
+
+    def one_mesh(m):
+        nonlocal checksum
+        v, f = pool[m % len(pool)]
+        mn, mx = synth.mesh_aabb(v)
+        dims = np.zeros(3, np.uint32)
+        lib.vf_dims_rule(mn.ctypes.data, mx.ctypes.data, 256, dims.ctypes.data)
+        grid.setAABB(mn, mx, tuple(int(d) for d in dims))
+        grid.fill(v, f)
+        ctx.initSeed(80 + m)
+        for k in range(10):
+            nf = 2 + (k % 9)
+            p = vf.FractureParameters(_numSeeds=nf, _numExtraSeeds=2 * nf)
+            grid.homogenize()  # resetFilling/homogenize between fragmentations (CADScene::rebuildGrid, FloodFracturer.cpp:99)
+            vf.fracture_model(grid, p)
+            counts, occ = grid.countValues()
+            grid.undoMask()
+            checksum += int(occ)
+
+    for m in my[: args.warmup]:
+        one_mesh(m)
+    ctx.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for m in my:
+        one_mesh(m)
+    ctx.synchronize()
+    dt = time.perf_counter() - t0
+    if dist is not None:
+        tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt[0])
+    if rank == 0:
+        print(json.dumps({
+            "metric": "models/s batch voxelize+fragment", "value": args.meshes / dt, "unit": "models/s", "n_gpus": world, "steps": args.meshes,
+            "warmup": args.warmup, "ms_per_step": dt / args.meshes * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u16 labels", "data": "synthetic",
+            "config": {"workload": f"cfg4-batch: {args.meshes} synthetic vessels (pool of {len(pool)} shapes) x 10 fragmentations at 256-max, FLOOD CHEBYSHEV, "
+                                   "nf 2..10, 2*nf extra seeds, per-mesh RNG seed 80+m, mesh m -> rank m mod N", "fragmentations_per_s": args.meshes * 10 / dt},
+        }))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -357,9 +494,17 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--cpu-size", type=int, default=192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "slab", "batch"], help="cfg3 = the driver's default; slab = cfg5; batch = cfg4")
+    ap.add_argument("--seeds", type=int, default=256, help="slab workload: number of seeds")
+    ap.add_argument("--meshes", type=int, default=64, help="batch workload: number of meshes")
+    ap.add_argument("--mesh-pool", type=int, default=8, help="batch workload: distinct synthetic shapes generated up front")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "slab":
+        run_slab(args)
+    elif args.workload == "batch":
+        run_batch(args)
     else:
         args.warmup = max(args.warmup, 3)
         run_cuda(args)

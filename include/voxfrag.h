@@ -204,6 +204,10 @@ vf_status vf_export(vf_grid* g, const char* path_without_extension, int export_t
 uint64_t  vf_encode_rle(const uint16_t* grid, const uint32_t dims[3], uint8_t* out, uint64_t cap);          /* exportRLE :672-714 */
 uint64_t  vf_encode_bing_squared(const uint16_t* grid, const uint32_t dims[3], uint8_t* out, uint64_t cap); /* exportRawCompressed squared :638-666 */
 
+/* ------------------------------------------------------------------ benchmark input synthesis (no reference counterpart) */
+/* analytic solid vessel of revolution sampled at cell centres of an n^3 grid; the grid holds planes x_offset .. x_offset + X - 1 */
+vf_status vf_synth_solid_vessel(vf_grid* g, int x_offset, uint32_t n, float base, float a1, float a2);
+
 /* ------------------------------------------------------------------ the caller's block: CADScene::fractureModel */
 /* CADScene.cpp:624-691: seeds -> Fracturer::build -> erode | detectBoundaries(1).  seeds_out (optional, capacity
  * numSeeds*2+numExtraSeeds entries of uint32[4]) receives the seed list used. */

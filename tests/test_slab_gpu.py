@@ -20,12 +20,18 @@ def ctx():
 def _run(ctx, g, seeds, dfunc, nslabs):
     from voxelfragmentml_b200 import slab
 
+    import voxelfragmentml_b200 as vf
+
     parts = slab.partition(g.shape[0], nslabs)
-    slabs = [slab.GpuSlab(ctx, slab.slab_with_halo(g, x0, x1), seeds, x0, x1, g.shape[0], dfunc) for x0, x1 in parts]
+    # a slab session owns its context's tile scratch, so every slab gets its own context (as it would on its own GPU)
+    ctxs = [vf.Context(0) for _ in parts]
+    slabs = [slab.GpuSlab(c, slab.slab_with_halo(g, x0, x1), seeds, x0, x1, g.shape[0], dfunc) for c, (x0, x1) in zip(ctxs, parts)]
     iters, moved = slab.run_local(slabs)
     got = np.concatenate([s.finalize() for s in slabs])
     for s in slabs:
         s.close()
+    for c in ctxs:
+        c.close()
     return got, iters, moved
 
 

@@ -49,16 +49,21 @@ def slab_with_halo(grid_global: np.ndarray, x0: int, x1: int) -> np.ndarray:
 class GpuSlab:
     """One slab on one GPU.  `labels_with_halo`: host uint16 [(xs+2), Y, Z]; keys live in a torch tensor so NCCL can send planes."""
 
-    def __init__(self, ctx, labels_with_halo: np.ndarray, seeds_global, x0: int, x1: int, X: int, dfunc: int):
+    def __init__(self, ctx, labels_with_halo, seeds_global, x0: int, x1: int, X: int, dfunc: int, shape=None):
+        """labels_with_halo: host uint16 [(xs+2), Y, Z], or a callable fill(grid) that writes the slab on the device (then pass
+        `shape` = ((xs+2), Y, Z))."""
         import torch
 
         from .api import RegularGrid
 
         self.ctx, self.x0, self.x1 = ctx, x0, x1
         self.seeds_global = np.ascontiguousarray(seeds_global, dtype=np.uint32)
-        self.shape = tuple(labels_with_halo.shape)
+        self.shape = tuple(shape) if callable(labels_with_halo) else tuple(labels_with_halo.shape)
         self.grid = RegularGrid(ctx, self.shape)
-        self.grid.updateSSBO(labels_with_halo)
+        if callable(labels_with_halo):
+            labels_with_halo(self.grid)
+        else:
+            self.grid.updateSSBO(labels_with_halo)
         self.plane = self.shape[1] * self.shape[2]
         self.keys = torch.empty(self.shape[0] * self.plane, dtype=torch.int32, device=f"cuda:{ctx.device}")
         self.recv = [torch.empty(self.plane, dtype=torch.int32, device=self.keys.device) for _ in range(2)]
@@ -83,11 +88,11 @@ class GpuSlab:
         check(self.ctx._lib.vf_flood_slab_ingest(self._h, side, C.c_void_p(plane.data_ptr()), C.byref(n)))
         return int(n.value)
 
-    def finalize(self) -> np.ndarray:
+    def finalize(self, download: bool = True):
         md = C.c_uint32(0)
         check(self.ctx._lib.vf_flood_slab_finalize(self._h, ptr(self.seeds_global), len(self.seeds_global), C.byref(md)))
         self.max_dist = md.value
-        return self.grid.updateGrid()[1:-1]
+        return self.grid.updateGrid()[1:-1] if download else None
 
     def close(self):
         if getattr(self, "_h", None):

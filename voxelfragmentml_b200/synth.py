@@ -84,6 +84,36 @@ def mesh_aabb(verts):
     return verts.min(0).astype(np.float32), verts.max(0).astype(np.float32)
 
 
+def solid_vessel_params(mesh_idx: int = 0):
+    """(base, a1, a2) of the analytic solid's outer profile, per-mesh perturbed like vessel_mesh."""
+    u = _uniform_stream(1000 + mesh_idx)
+    base = np.float32(0.18) * (1 + np.float32(0.2) * (u() - np.float32(0.5)))
+    a1 = np.float32(0.14) * (1 + np.float32(0.3) * (u() - np.float32(0.5)))
+    a2 = np.float32(0.06) * (1 + np.float32(0.6) * (u() - np.float32(0.5)))
+    return float(base), float(a1), float(a2)
+
+
+def solid_vessel_inside(x, y, z, params):
+    """analytic inside-test at normalised coordinates (x, z in [-.5, .5], y in [0, 1]); numpy arrays or scalars"""
+    base, a1, a2 = params
+    r = np.sqrt(x * x + z * z) / 0.6
+    ro = base + a1 * np.maximum(np.sin(np.pi * y), 0) ** 0.8 + a2 * np.sin(3 * np.pi * y)
+    return (r <= ro) & ((r >= ro - 0.06) | (y < 0.08))
+
+
+def solid_vessel_seeds(n: int, nseeds: int, params, seed: int = 80):
+    """nseeds distinct cells inside the analytic solid of an n^3 grid, by rejection sampling with the reference RNG recipe
+    (three draws per attempt), sorted like Seeder::uniform's std::set, labels 2.."""
+    u = _uniform_stream(seed)
+    got = set()
+    while len(got) < nseeds:
+        x, y, z = (int(np.float32(n - 1) * u()) for _ in range(3))
+        if solid_vessel_inside((x + 0.5) / n - 0.5, (y + 0.5) / n, (z + 0.5) / n - 0.5, params):
+            got.add((x, y, z))
+    pts = sorted(got)
+    return np.array([[x, y, z, 2 + i] for i, (x, y, z) in enumerate(pts)], dtype=np.uint32)
+
+
 def solid_vessel_grid(n: int, mesh_idx: int = 0) -> np.ndarray:
     """Analytic inside-test of the same vessel wall (between outer and inner profile) sampled at cell centres of an n^3
     grid: the solid used for cfg5-style flood tests where a 20k-triangle SAT at billions of cells is pointless."""
