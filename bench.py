@@ -51,7 +51,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except Exception:
@@ -232,6 +232,13 @@ def run_cuda(args):
     naive_t = float(np.median(naive_ms)) * 1e-3
     algo_bytes = 4.0 * N  # dense: read 2N + write 2N
     achieved = algo_bytes / naive_t / 1e9
+    # per-stage achieved GB/s on algorithmic bytes (B = 2N read + 2 N_w written; dense grid => N_w = N for the stages
+    # that rewrite labels, 0 for the histogram; erode = 3 x (detect + erode) + sweep counted as 7 passes of one read each and
+    # 4 passes that rewrite every label)
+    passes = {"naive": (1, 1), "remove_isolated": (1, 0), "erode": (7, 4), "histogram": (1, 0), "undo_mask": (1, 1)}
+    stage_roofline = {k: {"algorithmic_bytes": 2.0 * N * (passes[k][0] + passes[k][1]), "achieved_gbs": 2.0 * N * (passes[k][0] + passes[k][1]) / (v * 1e-3) / 1e9,
+                          "frac": 2.0 * N * (passes[k][0] + passes[k][1]) / (v * 1e-3) / 1e9 / peak, "share_of_step": v / sum(stage_ms.values())}
+                      for k, v in stage_ms.items() if k in passes}
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "naive_traffic.json")
     if os.path.exists(tpath):
@@ -266,6 +273,8 @@ def run_cuda(args):
                                " + erode(ELLIPSE,3,3it,p.5,thr.5) + histogram + undoMask", "stages": stages_run, "grid": list(dims),
                    "l2": "inputs (256 MiB at 512^3) larger than L2 (126 MB); no explicit flush", "parallelism": f"replicas x{world} (one grid per GPU)"},
         "stage_ms": stage_ms,
+        "stage_roofline": stage_roofline,
+        "fragmentation_only": {"value": world * N / naive_t / 1e9, "unit": "Gvoxels/s", "note": "F1 operator alone (NaiveFracturer::build without cleanup), CUDA events"},
         "roofline": {"kernel": "naive_brick_kernel<EUCLIDEAN,8>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": algo_bytes,
                      "kernel_ms": naive_t * 1e3},
@@ -274,7 +283,7 @@ def run_cuda(args):
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if rank == 0 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(args.cpu_size, stages_run)
+        out["cpu_baseline"] = cpu_baseline(args.cpu_size or 512, stages_run)
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
@@ -323,7 +332,7 @@ def run_reference(args):
     import oracle as orc
 
     orc.use_all_cores()
-    n = args.cpu_size
+    n = args.cpu_size or 384
     seeds = synth_seeds_dense(n, CFG3["nseeds"], rng_uniform_stream(CFG3["rng_seed"]))
     noise = noise_table(CFG3["rng_seed"] + 1000, CFG3["nnoise"])
     for _ in range(min(args.warmup, 1)):
@@ -492,7 +501,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--size", type=int, default=512)
-    ap.add_argument("--cpu-size", type=int, default=192)
+    ap.add_argument("--cpu-size", type=int, default=0, help="edge of the CPU sample grid (default: 512 once for cpu_baseline, 384 per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="cfg3", choices=["cfg3", "slab", "batch"], help="cfg3 = the driver's default; slab = cfg5; batch = cfg4")
     ap.add_argument("--seeds", type=int, default=256, help="slab workload: number of seeds")
