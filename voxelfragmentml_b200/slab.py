@@ -49,7 +49,7 @@ def slab_with_halo(grid_global: np.ndarray, x0: int, x1: int) -> np.ndarray:
 class GpuSlab:
     """One slab on one GPU.  `labels_with_halo`: host uint16 [(xs+2), Y, Z]; keys live in a torch tensor so NCCL can send planes."""
 
-    def __init__(self, ctx, labels_with_halo, seeds_global, x0: int, x1: int, X: int, dfunc: int, shape=None):
+    def __init__(self, ctx, labels_with_halo, seeds_global, x0: int, x1: int, X: int, dfunc: int, shape=None, defer_init: bool = False):
         """labels_with_halo: host uint16 [(xs+2), Y, Z], or a callable fill(grid) that writes the slab on the device (then pass
         `shape` = ((xs+2), Y, Z))."""
         import torch
@@ -67,10 +67,18 @@ class GpuSlab:
         self.plane = self.shape[1] * self.shape[2]
         self.keys = torch.empty(self.shape[0] * self.plane, dtype=torch.int32, device=f"cuda:{ctx.device}")
         self.recv = [torch.empty(self.plane, dtype=torch.int32, device=self.keys.device) for _ in range(2)]
-        loc = localise_seeds(self.seeds_global, x0, x1)
+        self._init_args = (int(dfunc), int(x0 > 0), int(x1 < X))
+        self._h = None
+        if not defer_init:
+            self.start()
+
+    def start(self):
+        """key-field initialisation + seed planting (FloodFracturer.cpp:99-132); separate so that benchmarks can time it"""
+        loc = localise_seeds(self.seeds_global, self.x0, self.x1)
         h = C.c_void_p()
-        check(ctx._lib.vf_flood_slab_init(self.grid._h, C.c_void_p(self.keys.data_ptr()), ptr(loc) if len(loc) else None, len(loc), int(dfunc),
-                                          int(x0 > 0), int(x1 < X), C.byref(h)))
+        dfunc, has_lo, has_hi = self._init_args
+        check(self.ctx._lib.vf_flood_slab_init(self.grid._h, C.c_void_p(self.keys.data_ptr()), ptr(loc) if len(loc) else None, len(loc), dfunc, has_lo, has_hi,
+                                               C.byref(h)))
         self._h = h
 
     def relax(self) -> int:
