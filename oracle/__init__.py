@@ -102,6 +102,8 @@ def _declare(L):
     L.orc_encode_rle.argtypes = [_u16p, _u32p, C.c_void_p, C.c_uint64]
     L.orc_decode_rle.restype = C.c_int
     L.orc_decode_rle.argtypes = [C.c_char_p, C.c_uint64, _u32p, C.c_void_p, C.c_uint64]
+    L.orc_encode_vox.restype = C.c_uint64
+    L.orc_encode_vox.argtypes = [_u16p, _u32p, C.c_int, C.c_void_p, C.c_uint64]
     L.orc_encode_bing_squared.restype = C.c_uint64
     L.orc_encode_bing_squared.argtypes = [_u16p, _u32p, C.c_void_p, C.c_uint64]
     L.orc_num_threads.restype = C.c_int
@@ -320,6 +322,14 @@ def encode_bing_squared(grid) -> bytes:
     need = lib().orc_encode_bing_squared(grid, d, None, 0)
     buf = np.empty(need, dtype=np.uint8)
     lib().orc_encode_bing_squared(grid, d, buf.ctypes.data, need)
+    return buf.tobytes()
+
+
+def encode_vox(grid, squared: bool) -> bytes:
+    d = _dims(grid)
+    need = lib().orc_encode_vox(grid, d, int(bool(squared)), None, 0)
+    buf = np.empty(need, dtype=np.uint8)
+    lib().orc_encode_vox(grid, d, int(bool(squared)), buf.ctypes.data, need)
     return buf.tobytes()
 
 

@@ -7,15 +7,18 @@
 #include "vf_oracle.h"
 
 #include <algorithm>
+#include <array>
 #include <cfloat>
 #include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <deque>
+#include <map>
 #include <queue>
 #include <random>
 #include <set>
+#include <string>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -957,6 +960,119 @@ extern "C" uint64_t orc_encode_bing_squared(const uint16_t* grid, const uint32_t
                 pos += 2;
             }
     return pos;
+}
+
+/* ---- .vox: RegularGrid::exportVox (RegularGrid.cpp:740-798) over VoxWriter (Libraries/MagicaVoxel_File_Writer/VoxWriter.cpp).
+ * A call-by-call restatement: an AddVoxel per cell in the reference's order, cubes in a map in order of first appearance,
+ * SaveToFile's chunk sequence.  Pinned byte-for-byte against the reference's own VoxWriter.cpp (tests/test_oracle_vs_ref.py). */
+namespace {
+struct VoxCubeO {
+    int tx, ty, tz;
+    std::vector<uint8_t> voxels;
+};
+struct VoxWriterO {
+    static constexpr size_t L = 126;             /* VoxWriter.h:451 */
+    size_t minX = 10000000, minY = 10000000, minZ = 10000000; /* VoxWriter.h:428-430 */
+    double lo[3] = { 1e7, 1e7, 1e7 }, hi[3] = { -1e7, -1e7, -1e7 }; /* maxVolume, VoxWriter.h:432 */
+    std::map<std::array<size_t, 3>, size_t> ids; /* cubesId */
+    std::vector<VoxCubeO> cubes;
+    void add(size_t vx, size_t vy, size_t vz, uint8_t colour)
+    {
+        /* AddVoxel, VoxWriter.cpp:449-461 (positions are never repeated by exportVox, so the voxelId lookup is dropped) */
+        const size_t ox = vx / L, oy = vy / L, oz = vz / L;
+        minX = std::min(minX, ox);
+        minY = std::min(minX, oy); /* sic: against minCubeX */
+        minZ = std::min(minX, oz); /* sic */
+        auto it = ids.find({ ox, oy, oz });
+        if (it == ids.end()) {
+            it = ids.emplace(std::array<size_t, 3>{ ox, oy, oz }, cubes.size()).first;
+            cubes.push_back({ (int)ox, (int)oy, (int)oz, {} });
+        }
+        const double p[3] = { (double)vx, (double)vy, (double)vz };
+        for (int a = 0; a < 3; ++a) lo[a] = std::min(lo[a], p[a]), hi[a] = std::max(hi[a], p[a]);
+        auto& v = cubes[it->second].voxels;
+        v.push_back((uint8_t)(vx % L)), v.push_back((uint8_t)(vy % L)), v.push_back((uint8_t)(vz % L)), v.push_back(colour);
+    }
+};
+struct ByteSink {
+    uint8_t* out;
+    uint64_t cap, pos;
+    void put(const void* p, uint64_t n)
+    {
+        if (out && pos + n <= cap) std::memcpy(out + pos, p, n);
+        pos += n;
+    }
+    void i32(int32_t v) { put(&v, 4); }
+    void tag(const char* t) { put(t, 4); }
+    void dict(const std::vector<std::pair<std::string, std::string>>& kv)
+    {
+        i32((int32_t)kv.size());
+        for (auto& e : kv) i32((int32_t)e.first.size()), put(e.first.data(), e.first.size()), i32((int32_t)e.second.size()), put(e.second.data(), e.second.size());
+    }
+};
+uint64_t dict_size(const std::vector<std::pair<std::string, std::string>>& kv)
+{
+    uint64_t s = 4;
+    for (auto& e : kv) s += 8 + e.first.size() + e.second.size();
+    return s;
+}
+int to_int_x86(double v) { return (v >= -2147483648.0 && v < 2147483648.0) ? (int)v : INT_MIN; }
+}  // namespace
+
+extern "C" uint64_t orc_encode_vox(const uint16_t* grid, const uint32_t dims[3], int squared, uint8_t* out, uint64_t cap)
+{
+    VoxWriterO vw;
+    if (squared) { /* RegularGrid.cpp:747-768 */
+        const int M = (int)std::max(dims[0], std::max(dims[1], dims[2]));
+        const int start[3] = { (int)((M - dims[0]) / 2), (int)((M - dims[1]) / 2), (int)((M - dims[2]) / 2) };
+        for (int x = 0; x < M; ++x)
+            for (int y = 0; y < M; ++y)
+                for (int z = 0; z < M; ++z) {
+                    const int cx = x - start[0], cy = y - start[1], cz = z - start[2];
+                    vw.add(x, z, y, inside(dims, cx, cy, cz) ? (uint8_t)grid[lin(cx, cy, cz, dims)] : (uint8_t)ORC_VOXEL_EMPTY);
+                }
+    } else { /* :770-785 */
+        for (int x = 0; x < (int)dims[0]; ++x)
+            for (int y = 0; y < (int)dims[1]; ++y)
+                for (int z = 0; z < (int)dims[2]; ++z) {
+                    const uint16_t v = grid[lin(x, y, z, dims)];
+                    if (v > ORC_VOXEL_FREE) vw.add(x, z, y, (uint8_t)(v - ORC_VOXEL_FREE));
+                }
+    }
+    /* SaveToFile, VoxWriter.cpp:462-540 */
+    ByteSink w{ out, cap, 0 };
+    w.tag("VOX "), w.i32(150), w.tag("MAIN"), w.i32(0);
+    const uint64_t patch = w.pos;
+    w.i32(0);
+    const uint64_t header = w.pos;
+    typedef std::vector<std::pair<std::string, std::string>> Dict;
+    std::vector<Dict> frames;
+    for (auto& c : vw.cubes) {
+        w.tag("SIZE"), w.i32(12), w.i32(0), w.i32(126), w.i32(126), w.i32(126);
+        const int32_t nvox = (int32_t)c.voxels.size() / 4;
+        w.tag("XYZI"), w.i32(4 * (1 + nvox)), w.i32(0), w.i32(nvox), w.put(c.voxels.data(), c.voxels.size());
+        /* :489-491, with minCube* being size_t: the subtraction is unsigned, then float, then double */
+        c.tx = to_int_x86(std::floor(((size_t)c.tx - vw.minX + 0.5f) * VoxWriterO::L - vw.lo[0] - (vw.hi[0] - vw.lo[0]) * 0.5));
+        c.ty = to_int_x86(std::floor(((size_t)c.ty - vw.minY + 0.5f) * VoxWriterO::L - vw.lo[1] - (vw.hi[1] - vw.lo[1]) * 0.5));
+        c.tz = to_int_x86(std::floor(((size_t)c.tz - vw.minZ + 0.5f) * VoxWriterO::L));
+        frames.push_back({ { "_t", std::to_string(c.tx) + " " + std::to_string(c.ty) + " " + std::to_string(c.tz) } });
+    }
+    const int32_t n = (int32_t)vw.cubes.size();
+    const Dict none, keyframe = { { "_f", "0" } };
+    w.tag("nTRN"), w.i32((int32_t)(20 + dict_size(none) + dict_size(none))), w.i32(0);
+    w.i32(0), w.dict(none), w.i32(1), w.i32(-1), w.i32(-1), w.i32(1), w.dict(none);
+    w.tag("nGRP"), w.i32((int32_t)(4 * (2 + n) + dict_size(none))), w.i32(0);
+    w.i32(1), w.dict(none), w.i32(n);
+    for (int32_t i = 0; i < n; ++i) w.i32(2 + 2 * i);
+    for (int32_t i = 0; i < n; ++i) {
+        w.tag("nTRN"), w.i32((int32_t)(20 + dict_size(none) + dict_size(frames[i]))), w.i32(0);
+        w.i32(2 + 2 * i), w.dict(none), w.i32(3 + 2 * i), w.i32(-1), w.i32(0), w.i32(1), w.dict(frames[i]);
+        w.tag("nSHP"), w.i32((int32_t)(8 + dict_size(none) + 4 + dict_size(keyframe))), w.i32(0);
+        w.i32(3 + 2 * i), w.dict(none), w.i32(1), w.i32(i), w.dict(keyframe);
+    }
+    const uint32_t children = (uint32_t)(w.pos - header);
+    if (out && w.pos <= cap) std::memcpy(out + patch, &children, 4);
+    return w.pos;
 }
 
 extern "C" void orc_set_num_threads(int n)

@@ -127,6 +127,8 @@ uint64_t orc_count_values(const uint16_t* grid, uint64_t n, uint32_t* counts);
 uint64_t orc_encode_rle(const uint16_t* grid, const uint32_t dims[3], uint8_t* out, uint64_t cap);
 int      orc_decode_rle(const uint8_t* data, uint64_t len, uint32_t dims_out[3], uint16_t* grid, uint64_t grid_cap);
 uint64_t orc_encode_bing_squared(const uint16_t* grid, const uint32_t dims[3], uint8_t* out, uint64_t cap);
+/* RegularGrid::exportVox (RegularGrid.cpp:740-798) through VoxWriter (Libraries/MagicaVoxel_File_Writer/VoxWriter.cpp:449-540) */
+uint64_t orc_encode_vox(const uint16_t* grid, const uint32_t dims[3], int squared, uint8_t* out, uint64_t cap);
 
 /* ---- composite used by the CPU baseline (bench.py): cfg3 pipeline on one grid ---- */
 int orc_num_threads(void);

@@ -115,6 +115,34 @@ def test_host_encoders_reproduce_reference_rle_bytes(golden_rle_bytes, orc):
     assert buf.tobytes() == orc.encode_bing_squared(grid)
 
 
+def test_host_vox_encoder_reproduces_reference_writer_hashes():
+    """vf_encode_vox is host code: checked on CPU against hashes of the reference VoxWriter's own output (no oracle involved)."""
+    import hashlib
+    import json
+
+    import numpy as np
+    from conftest import GOLDEN
+    from vox_cases import all_vox_cases
+
+    import voxelfragmentml_b200 as vf
+
+    lib = vf._capi.load()
+    gold = json.load(open(os.path.join(GOLDEN, "vox_golden.json")))
+    for name, grid in all_vox_cases():
+        dims = np.asarray(grid.shape, np.uint32)
+        for squared in (0, 1):
+            want = gold[f"{name}/{'squared' if squared else 'tight'}"]
+            need = lib.vf_encode_vox(grid.ctypes.data, dims.ctypes.data, squared, None, 0)
+            assert need == want["bytes"]
+            buf = np.zeros(need, np.uint8)
+            # a too-small buffer must not be written past its end
+            small = np.zeros(64, np.uint8)
+            assert lib.vf_encode_vox(grid.ctypes.data, dims.ctypes.data, squared, small.ctypes.data, 32) == need
+            assert not small[32:].any()
+            lib.vf_encode_vox(grid.ctypes.data, dims.ctypes.data, squared, buf.ctypes.data, need)
+            assert hashlib.sha256(buf.tobytes()).hexdigest() == want["sha256"], (name, squared)
+
+
 def test_merge_seeds_host_matches_oracle(orc):
     import numpy as np
 

@@ -209,6 +209,9 @@ def test_export_rle_and_bing(ctx, orc, labelled_vessel, tmp_path):
     assert open(base + ".rle", "rb").read() == orc.encode_rle(lab)
     g.exportGrid(base, True, vf.ExportGrid.UNCOMPRESSED_BINARY)
     assert open(base + ".bing", "rb").read() == orc.encode_bing_squared(lab)
+    for squared in (False, True):
+        g.exportGrid(base, squared, vf.ExportGrid.VOX)
+        assert open(base + ".vox", "rb").read() == orc.encode_vox(lab, squared)
     with pytest.raises(vf.VoxFragError):
         g.exportGrid(base, True, vf.ExportGrid.QUADSTACK)
     g.close()

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from conftest import ROOT, pick_seeds, random_blob_grid
+from vox_cases import vox_cases
 
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libvf_ref.so")
 pytestmark = pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref not built (needs /root/reference)")
@@ -116,3 +117,32 @@ def test_sat_predicate_matches_reference_bit_for_bit(ref, orc):
         assert a == int(b), (i, tri, bmin, bmax)
         hits += a
     assert 20000 < hits < 180000
+
+
+def _ref_vox(ref, grid, squared, tmp_path):
+    ref.ref_export_vox.argtypes = [_u16, _u32, C.c_int, C.c_char_p]
+    ref.ref_export_vox.restype = None
+    path = str(tmp_path / "ref.vox")
+    if os.path.exists(path):
+        os.remove(path)
+    ref.ref_export_vox(np.ascontiguousarray(grid), _dims(grid), int(squared), path.encode())
+    return open(path, "rb").read()
+
+
+@pytest.mark.parametrize("name,grid", vox_cases(), ids=[c[0] for c in vox_cases()])
+@pytest.mark.parametrize("squared", [False, True])
+def test_vox_bytes_match_reference_writer(ref, orc, tmp_path, name, grid, squared):
+    """orc_encode_vox and the product's vf_encode_vox (host code) == the bytes the reference's VoxWriter.cpp writes."""
+    import voxelfragmentml_b200 as vf
+
+    want = _ref_vox(ref, grid, squared, tmp_path)
+    assert want[:4] == b"VOX " and len(want) >= 20
+    got = orc.encode_vox(grid, squared)
+    assert got == want
+    lib = vf._capi.load()
+    d = _dims(grid)
+    need = lib.vf_encode_vox(grid.ctypes.data, d.ctypes.data, int(squared), None, 0)
+    assert need == len(want)
+    buf = np.zeros(need, np.uint8)
+    assert lib.vf_encode_vox(grid.ctypes.data, d.ctypes.data, int(squared), buf.ctypes.data, need) == need
+    assert buf.tobytes() == want
