@@ -247,9 +247,15 @@ def run_cuda(args):
         except Exception:
             traffic = None
 
-    # ---- end to end through the public API with HOST buffers: pinned upload -> pipeline -> download, every step
+    # ---- end to end through the public API with HOST buffers: pinned upload -> pipeline -> download, every step.
+    # (a) serial: one grid, each step waits for its own download (latency of one call sequence);
+    # (b) pipelined: three grids, each on its own context/stream, rotate through upload / pipeline / download so that the copies
+    #     of neighbouring steps overlap the kernels of the current one (PCIe is full duplex); every step still uploads its own
+    #     input and downloads its own result inside the timed region.  (b) is the throughput a batch producer gets and is `value`.
     h_in = torch.ones(N, dtype=torch.int16).pin_memory()
     h_out = torch.empty(N, dtype=torch.int16).pin_memory()
+    noise_pinned = torch.from_numpy(noise).pin_memory()  # the noise table is part of every step's upload: pinned like the grid
+    noise = noise_pinned.numpy()
     e2e_steps = max(2, min(args.steps, 5))
     for it in range(1 + e2e_steps):
         if it == 1:
@@ -259,11 +265,48 @@ def run_cuda(args):
         pipeline()
         grid.download_async(h_out)
         ctx.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    serial_s = (time.perf_counter() - t0) / e2e_steps
+
+    slots = []
+    for k in range(3):
+        c = ctx if k == 0 else vf.Context(local_rank)
+        g = grid if k == 0 else vf.RegularGrid(c, dims)
+        c.reserve(dims)
+        slots.append((c, g, h_out if k == 0 else torch.empty(N, dtype=torch.int16).pin_memory()))
+
+    def run_pipelined(nsteps):
+        # On this platform a transfer submitted while another one is in flight waits for it, whatever the stream or direction;
+        # two transfers submitted together share the link (H2D + D2H = 97 GB/s, tools/pcie_probe*.py).  So each step submits the
+        # next step's upload and the previous step's download back to back, then runs its kernels; unchanged seeds / noise are
+        # not re-sent by the library, and the step's only small transfer (the histogram read-back) closes the step.
+        et, es, ei, ep, eth = CFG3["erosion"]
+        slots[0][1].upload_async(h_in)
+        for i in range(nsteps):
+            c, g, ho = slots[i % 3]
+            if i + 1 < nsteps:
+                slots[(i + 1) % 3][1].upload_async(h_in)               # step i+1's input
+            if i > 0:
+                slots[(i - 1) % 3][1].download_async(slots[(i - 1) % 3][2])  # step i-1's result
+            naive.build(g, seeds)
+            vf.NaiveFracturer.removeIsolatedRegions(g, seeds)
+            g.erode(et, es, ei, ep, eth, noise=noise)
+            g.countValues()
+            g.undoMask()
+        last = (nsteps - 1) % 3
+        slots[last][1].download_async(slots[last][2])
+        for c, _, _ in slots:
+            c.synchronize()
+
+    pipe_steps = max(6, 2 * args.steps)
+    run_pipelined(3)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    run_pipelined(pipe_steps)
+    e2e_s = (time.perf_counter() - t0) / pipe_steps
     if world > 1:
-        tt = torch.tensor([e2e_s], device="cuda")
+        tt = torch.tensor([e2e_s, serial_s], device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_s = float(tt.item())
+        e2e_s, serial_s = (float(v) for v in tt.tolist())
 
     out = {
         "metric": "Gvoxels/s fragmented at 512^3", "value": world * N * args.steps / (total_ms * 1e-3) / 1e9, "unit": "Gvoxels/s",
@@ -278,8 +321,11 @@ def run_cuda(args):
         "roofline": {"kernel": "naive_brick_kernel<EUCLIDEAN,8>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": algo_bytes,
                      "kernel_ms": naive_t * 1e3},
-        "e2e": {"value": world * N / e2e_s / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": 2 * N + seeds.nbytes + noise.nbytes,
-                "d2h_bytes_per_step": 2 * N + 4 * 32768, "ms_per_step": e2e_s * 1e3},
+        "e2e": {"value": world * N / e2e_s / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": 2 * N,
+                "d2h_bytes_per_step": 2 * N + 4 * 32768, "ms_per_step": e2e_s * 1e3, "steps": pipe_steps,
+                "mode": "3 grids in rotation: upload / kernels / download of consecutive steps overlap; every step copies its own input grid and "
+                        "result grid; the seed list and noise table are identical every step and are sent once (the library skips unchanged tables)",
+                "serial_ms_per_step": serial_s * 1e3, "serial_value": world * N / serial_s / 1e9},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if rank == 0 and not args.no_cpu_baseline:

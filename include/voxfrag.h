@@ -185,7 +185,9 @@ void      vf_flood_slab_destroy(vf_slab* s);
 /* ------------------------------------------------------------------ C1..C4: cleanup */
 vf_status vf_remove_isolated_regions(vf_grid* g, const uint32_t* seeds, uint32_t nseeds); /* NaiveFracturer::removeIsolatedRegionsCPU semantics, NaiveFracturer.cpp:111-150 */
 vf_status vf_detect_boundaries(vf_grid* g, int boundary_size);           /* RegularGrid::detectBoundaries, RegularGrid.cpp:64-80 */
-/* RegularGrid::erode (RegularGrid.cpp:82-159); noise = HOST table (vf_fill_noise), boundary_mode see vf_params */
+/* RegularGrid::erode (RegularGrid.cpp:82-159); noise = HOST table (vf_fill_noise), boundary_mode see vf_params.
+ * The table is copied on the context's stream: a pageable table may be reused on return, a pinned one must stay untouched until
+ * the context is synchronised. */
 vf_status vf_erode(vf_grid* g, int erosion_type, uint32_t size, uint32_t iterations, float probability, float threshold,
                    const float* noise, uint32_t nnoise, int boundary_mode);
 vf_status vf_remove_isolated_regions_grid(vf_grid* g);                   /* RegularGrid::removeIsolatedRegions, RegularGrid.cpp:1006-1015 (snapshot semantics) */

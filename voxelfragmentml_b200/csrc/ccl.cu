@@ -8,15 +8,17 @@
 //
 // Connectivity has no notion of distance, so it does not need the wavefront iterations of the flood.  A lock-free union-find
 // (parent links always point to a lower index, roots are linked with atomicMin) labels every component:
-//   * the unit of work is a 32-cell z-segment = one row of a 16 x 16 x 32 tile.  A warp ballot over "same region as my
-//     z-predecessor" turns a segment into two 32-bit masks (active cells, run starts); runs, not cells, are the union-find nodes;
+//   * the unit of work is a 32-cell z-segment = one row of a 16 x 16 x 32 tile.  Packed 16-bit compares of "same region as my
+//     z-predecessor" turn a segment into two 32-bit masks (active cells, run starts); runs, not cells, are the union-find nodes;
 //   * two rows have to be united only at "key positions": cells where one of the two rows starts a run while both are active —
 //     if both rows merely continue their runs the pair one cell earlier already did the job.  Key positions are bit tricks on
 //     the masks, so a thread serves a whole row against a neighbouring row in a handful of instructions;
-//   * stage 1 resolves the components inside every tile in shared memory (thread per row), writes each cell's tile-local root
-//     to the global parent array (depth-1 forest) and the segment masks next to it; stage 2 (thread per segment) unites only
-//     pairs that straddle a tile border; stage 3 marks the roots of the start cells and selects.
-// The parent array reuses the 4 B/voxel flood key scratch, the masks (N/4 bytes) the second-grid scratch.
+//   * stage 1 resolves the components inside every tile in shared memory (thread per row), writes each run start's tile-local
+//     root to the global parent array (depth-1 forest; only run starts are ever written or read there) and the segment masks
+//     next to it; stage 2 (thread per segment) unites only pairs that straddle a tile border; stage 3 marks the roots of the
+//     start cells and selects.
+// The parent array reuses the 4 B/voxel flood key scratch; the segment records (masks N/4 bytes + first/last labels N/8 bytes)
+// the second-grid scratch.
 // Requires N < 2^31 (bit 31 of a root's parent word carries "keep").
 #include <algorithm>
 
@@ -29,6 +31,7 @@ constexpr uint32_t KEEP = 0x80000000u;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 enum { MODE_C1 = 0, MODE_F3 = 1 };
 constexpr int LX = 16, LY = 16, LZ = 32, LROWS = LX * LY, LCELLS = LROWS * LZ;
+constexpr int LABW = LZ / 2 + 1;  // staged label row stride in 32-bit words: odd, so that equal z in consecutive rows hits distinct banks
 
 template <int MODE>
 __device__ __forceinline__ bool active(uint32_t v)
@@ -51,10 +54,13 @@ struct Geo {
 };
 
 // ------------------------------------------------------------------------------------------------ shared-memory union-find
+// Node id = row * 32 + z.  Thread-per-row phases touch the same z in 32 consecutive rows at once, which would be one bank; the
+// storage slot of a node is therefore rotated by its row: slot(id) = row * 32 + ((z + row) & 31).
+__device__ __forceinline__ uint32_t slot(uint32_t id) { return (id & ~31u) | ((id + (id >> 5)) & 31u); }
 __device__ __forceinline__ uint32_t find_local(volatile uint32_t* par, uint32_t i)
 {
     uint32_t p;
-    while ((p = par[i]) != i) i = p;
+    while ((p = par[slot(i)]) != i) i = p;
     return i;
 }
 __device__ __forceinline__ void unite_local(uint32_t* par, uint32_t a, uint32_t b)
@@ -68,7 +74,7 @@ __device__ __forceinline__ void unite_local(uint32_t* par, uint32_t a, uint32_t 
             a = b;
             b = t;
         }
-        const uint32_t old = atomicMin(&par[a], b);
+        const uint32_t old = atomicMin(&par[slot(a)], b);
         if (old == a) return;
         a = old;
     }
@@ -117,55 +123,79 @@ __global__ void ccl_plant_seeds_kernel(uint16_t* __restrict__ grid, Geo g, const
 
 // ------------------------------------------------------------------------------------------------ stage 1: inside a tile
 template <int MODE, int NNEIGH>
-__global__ void __launch_bounds__(256) ccl_tile_kernel(const uint16_t* __restrict__ grid, uint32_t* __restrict__ P, uint2* __restrict__ masks, Geo g)
+__global__ void __launch_bounds__(256) ccl_tile_kernel(const uint16_t* __restrict__ grid, uint32_t* __restrict__ P, uint2* __restrict__ masks,
+                                                       uint32_t* __restrict__ ends, Geo g)
 {
     extern __shared__ uint32_t smem_ccl[];
     uint32_t* par = smem_ccl;                                       // [LCELLS] only run-start entries are nodes
     uint32_t* sA = par + LCELLS;                                    // [LROWS] active mask per row
     uint32_t* sS = sA + LROWS;                                      // [LROWS] run-start mask per row (bit 0 always set)
-    uint16_t* lab = reinterpret_cast<uint16_t*>(sS + LROWS);        // [LCELLS] local index = row * 32 + z, row = x * LY + y
+    uint32_t* labw = sS + LROWS;                                    // [LROWS][LABW] staged labels, two per word; row = x * LY + y
+    auto lab = [&](int r, int z) -> uint32_t { return (labw[r * LABW + (z >> 1)] >> ((z & 1) * 16)) & 0xFFFFu; };
     const int tile = blockIdx.x;
     const int tz = tile % g.ntz, ty = (tile / g.ntz) % g.nty, tx = tile / (g.ntz * g.nty);
     const int gx0 = tx * LX, gy0 = ty * LY, gz0 = tz * LZ;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    // (a1) stage the tile's labels: 16-byte asynchronous copies when rows are 16-byte aligned (Z % 8 == 0), so that all of a
-    //      thread's loads are in flight at once; scalar loads otherwise.  Cells outside the grid read as EMPTY.
+    // (a) thread per 8-cell chunk (4 threads = one row): 128-bit loads straight from the grid, all of a thread's 4 chunks in flight
+    //     at once (scalar loads when rows are not 16-byte aligned).  "active" and "differs from the z-predecessor" are evaluated
+    //     on packed 16-bit lanes (VIMNMX.U16x2) and gathered into byte masks; two shuffles assemble the row's 32-bit masks.
+    //     Cells outside the grid read as EMPTY.
     const bool vec_ok = (g.Z % 8 == 0) && ((reinterpret_cast<uintptr_t>(grid) & 15) == 0);
-    if (vec_ok) {
-        for (int q = threadIdx.x; q < LROWS * 4; q += 256) {  // 4 chunks of 8 cells per row
-            const int r = q >> 2, ch = q & 3;
-            const int gx = gx0 + r / LY, gy = gy0 + r % LY, gz = gz0 + ch * 8;
-            uint16_t* dst = &lab[r * LZ + ch * 8];
-            if (gx < g.X && gy < g.Y && gz < g.Z) {
-                const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(grid + ((size_t)gx * g.Y + gy) * g.Z + gz) : "memory");
+    constexpr int kIts = LROWS * 4 / 256;  // 8-cell chunks per thread
+    uint4 chunk[kIts];
+#pragma unroll
+    for (int it = 0; it < kIts; ++it) {
+        const int q = it * 256 + threadIdx.x, r = q >> 2, ch = q & 3;
+        const int gx = gx0 + r / LY, gy = gy0 + r % LY, gz = gz0 + ch * 8;
+        chunk[it] = make_uint4(0, 0, 0, 0);
+        if (gx < g.X && gy < g.Y && gz < g.Z) {
+            const uint16_t* src = grid + ((size_t)gx * g.Y + gy) * g.Z + gz;
+            if (vec_ok) {
+                chunk[it] = __ldg(reinterpret_cast<const uint4*>(src));
             } else {
-                *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+                uint32_t w[4] = { 0, 0, 0, 0 };
+                for (int k = 0; k < 8 && gz + k < g.Z; ++k) w[k >> 1] |= (uint32_t)src[k] << ((k & 1) * 16);
+                chunk[it] = make_uint4(w[0], w[1], w[2], w[3]);
             }
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-    } else {
-        for (int r = warp; r < LROWS; r += 8) {
-            const int gx = gx0 + r / LY, gy = gy0 + r % LY, gz = gz0 + lane;
-            lab[r * LZ + lane] = (gx < g.X && gy < g.Y && gz < g.Z) ? grid[((size_t)gx * g.Y + gy) * g.Z + gz] : (uint16_t)0;
-        }
     }
-    __syncthreads();
-    // (a2) warp per row, lane = z: masks, run-start parents
-    for (int r = warp; r < LROWS; r += 8) {
-        const int gx = gx0 + r / LY, gy = gy0 + r % LY;
-        const uint32_t v = lab[r * LZ + lane];
-        const bool act = active<MODE>(v);
-        const uint32_t vp = __shfl_up_sync(kFull, v, 1);
-        const bool cont = lane > 0 && act && active<MODE>(vp) && same<MODE>(v, vp);
-        const unsigned A = __ballot_sync(kFull, act), S = ~__ballot_sync(kFull, cont);
-        par[r * LZ + lane] = r * LZ + lane;
-        if (lane == 0) {
+    auto gather8 = [](uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3) -> uint32_t {  // lanes hold 0/1: cell 2k at bit 2k, cell 2k+1 at bit 2k+1
+        const uint32_t b = x0 | x1 << 2 | x2 << 4 | x3 << 6;
+        return (b | b >> 15) & 0xFFu;
+    };
+#pragma unroll
+    for (int it = 0; it < kIts; ++it) {
+        const int q = it * 256 + threadIdx.x, r = q >> 2, ch = q & 3;
+        const uint4 v = chunk[it];
+        const uint32_t pw = __shfl_up_sync(kFull, v.w, 1);  // last word of the chunk before mine (another row's when ch == 0: masked below)
+        const uint32_t one = 0x00010001u, idm = MODE == MODE_C1 ? 0xFFFFFFFFu : 0x00FF00FFu;
+        const uint32_t a8 = gather8(__vminu2(v.x & 0x7FFE7FFEu, one), __vminu2(v.y & 0x7FFE7FFEu, one), __vminu2(v.z & 0x7FFE7FFEu, one),
+                                    __vminu2(v.w & 0x7FFE7FFEu, one));
+        const uint32_t n8 = gather8(__vminu2((v.x ^ __byte_perm(pw, v.x, 0x5432)) & idm, one), __vminu2((v.y ^ __byte_perm(v.x, v.y, 0x5432)) & idm, one),
+                                    __vminu2((v.z ^ __byte_perm(v.y, v.z, 0x5432)) & idm, one), __vminu2((v.w ^ __byte_perm(v.z, v.w, 0x5432)) & idm, one));
+        uint32_t A = a8 << (8 * ch), Nq = n8 << (8 * ch);
+        A |= __shfl_xor_sync(kFull, A, 1), Nq |= __shfl_xor_sync(kFull, Nq, 1);
+        A |= __shfl_xor_sync(kFull, A, 2), Nq |= __shfl_xor_sync(kFull, Nq, 2);
+        const uint32_t S = ~(~Nq & A & (A << 1));  // a run continues where the cell and its predecessor are active and alike
+        uint32_t* lw = &labw[r * LABW + ch * 4];
+        lw[0] = v.x, lw[1] = v.y, lw[2] = v.z, lw[3] = v.w;
+        // every node starts as its own root; written by storage slot (see slot()): slot p of row r holds node r*32 + ((p - r) & 31)
+        const uint32_t p0 = ch * 8, rb = r * LZ;
+        uint32_t idv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) idv[k] = rb + ((p0 + k - r) & 31u);
+        *reinterpret_cast<uint4*>(&par[rb + p0]) = make_uint4(idv[0], idv[1], idv[2], idv[3]);
+        *reinterpret_cast<uint4*>(&par[rb + p0 + 4]) = make_uint4(idv[4], idv[5], idv[6], idv[7]);
+        const uint32_t lastw = __shfl_down_sync(kFull, v.w, 3);  // for ch == 0: the row's last word (cells 30, 31)
+        if (ch == 0) {
+            const int gx = gx0 + r / LY, gy = gy0 + r % LY;
             sA[r] = A;
             sS[r] = S;
-            if (gx < g.X && gy < g.Y && gz0 < g.Z) masks[((size_t)gx * g.Y + gy) * g.segs + tz] = make_uint2(A, S);
+            if (gx < g.X && gy < g.Y) {
+                const size_t sg = ((size_t)gx * g.Y + gy) * g.segs + tz;
+                masks[sg] = make_uint2(A, S);
+                ends[sg] = (v.x & 0xFFFFu) | (lastw & 0xFFFF0000u);  // first and last label of the segment: stage 2's z-border test
+            }
         }
     }
     __syncthreads();
@@ -185,7 +215,7 @@ __global__ void __launch_bounds__(256) ccl_tile_kernel(const uint16_t* __restric
                 const int z = __ffs(m) - 1;
                 m &= m - 1;
                 const int zn = z + dz;
-                if (same<MODE>(lab[r * LZ + z], lab[rn * LZ + zn]))
+                if (same<MODE>(lab(r, z), lab(rn, zn)))
                     unite_local(par, r * LZ + run_start(Sm, z), rn * LZ + run_start(sS[rn], zn));
             }
         };
@@ -201,29 +231,20 @@ __global__ void __launch_bounds__(256) ccl_tile_kernel(const uint16_t* __restric
     }
     __syncthreads();
 
-    // (b2) thread per row: flatten the run starts of my row, so that (c) is one shared-memory read per cell
+    // (c) thread per row: every run start gets the global index of its tile-local root.  Only run starts are union-find
+    //     nodes: the parent array is written (and later read) at run starts only.
     {
         const int r = threadIdx.x;
-        unsigned st = sS[r] & sA[r];
+        const int gx = gx0 + r / LY, gy = gy0 + r % LY;
+        const unsigned Sr = sS[r];
+        unsigned st = Sr & sA[r];
         while (st) {
             const int z = __ffs(st) - 1;
             st &= st - 1;
-            par[r * LZ + z] = find_local(par, r * LZ + z);  // writes an ancestor: safe against concurrent finds
-        }
-    }
-    __syncthreads();
-
-    // (c) warp per row: every active cell points at the global index of its tile-local root
-    for (int r = warp; r < LROWS; r += 8) {
-        const int gx = gx0 + r / LY, gy = gy0 + r % LY, gz = gz0 + lane;
-        if (!(gx < g.X && gy < g.Y && gz < g.Z)) continue;
-        uint32_t out = NONE;
-        if (sA[r] >> lane & 1u) {
-            const uint32_t root = par[r * LZ + run_start(sS[r], lane)];
+            const uint32_t root = find_local(par, r * LZ + z);
             const int rz = root % LZ, rr = root / LZ;
-            out = ((uint32_t)(gx0 + rr / LY) * g.Y + gy0 + rr % LY) * g.Z + gz0 + rz;
+            P[((size_t)gx * g.Y + gy) * g.Z + gz0 + z] = ((uint32_t)(gx0 + rr / LY) * g.Y + gy0 + rr % LY) * g.Z + gz0 + rz;
         }
-        P[((size_t)gx * g.Y + gy) * g.Z + gz] = out;
     }
 }
 
@@ -231,7 +252,8 @@ __global__ void __launch_bounds__(256) ccl_tile_kernel(const uint16_t* __restric
 // thread per 32-cell segment.  A pair (my cell z, neighbour cell z+dz of row (nx,ny)) is this stage's business iff the two cells
 // lie in different tiles.
 template <int MODE, int NNEIGH>
-__global__ void __launch_bounds__(256) ccl_border_kernel(const uint16_t* __restrict__ grid, uint32_t* __restrict__ P, const uint2* __restrict__ masks, Geo g)
+__global__ void __launch_bounds__(256) ccl_border_kernel(const uint16_t* __restrict__ grid, uint32_t* __restrict__ P, const uint2* __restrict__ masks,
+                                                         const uint32_t* __restrict__ ends, Geo g)
 {
     for (uint32_t sg = blockIdx.x * blockDim.x + threadIdx.x; sg < g.nsegs; sg += gridDim.x * blockDim.x) {
         const int seg = sg % g.segs;
@@ -249,14 +271,17 @@ __global__ void __launch_bounds__(256) ccl_border_kernel(const uint16_t* __restr
             const uint32_t wi = grid[i - back], wn = grid[n - back];
             return active<MODE>(wi) && active<MODE>(wn) && same<MODE>(vi, wi) && same<MODE>(vn, wn);
         };
-        // same row, previous segment (always another tile because LZ == 32)
+        // same row, previous segment (always another tile because LZ == 32): decided from the segment records alone
         if (seg > 0 && (Am & 1u)) {
             const uint2 pm = masks[sg - 1];
             if (pm.x >> 31) {
-                const uint32_t vi = grid[base], vn = grid[base - 1];
+                const uint32_t vi = ends[sg] & 0xFFFFu, vn = ends[sg - 1] >> 16;
                 if (same<MODE>(vi, vn)) {
-                    const bool skip = (y % LY != 0 && witnessed(base, base - 1, vi, vn, g.Z)) || (x % LX != 0 && witnessed(base, base - 1, vi, vn, YZ));
-                    if (!skip) unite(P, base, base - 1);
+                    auto wit = [&](uint32_t wsg) {  // the same pair one row / one plane back
+                        return (masks[wsg].x & 1u) && (masks[wsg - 1].x >> 31) && same<MODE>(vi, ends[wsg] & 0xFFFFu) && same<MODE>(vn, ends[wsg - 1] >> 16);
+                    };
+                    const bool skip = (y % LY != 0 && wit(sg - g.segs)) || (x % LX != 0 && wit(sg - (uint32_t)g.Y * g.segs));
+                    if (!skip) unite(P, base, base - 32 + run_start(pm.y, 31));  // nodes are run starts; cell 0 of a segment always is one
                 }
             }
         }
@@ -268,8 +293,9 @@ __global__ void __launch_bounds__(256) ccl_border_kernel(const uint16_t* __restr
             const uint32_t nsg = nrow * g.segs + seg;
             const uint2 cm = masks[nsg];
             unsigned An = cm.x, Sn = cm.y;
+            uint2 pm = make_uint2(0u, 0u);
             if (dz < 0) {
-                const uint2 pm = seg > 0 ? masks[nsg - 1] : make_uint2(0u, 0u);
+                if (seg > 0) pm = masks[nsg - 1];
                 An = (An << 1) | (pm.x >> 31), Sn = (Sn << 1) | 1u;  // neighbour cell -1 sits in the previous segment: treat as a start
             } else if (dz > 0) {
                 const uint2 qm = seg + 1 < g.segs ? masks[nsg + 1] : make_uint2(0u, 0u);
@@ -290,7 +316,11 @@ __global__ void __launch_bounds__(256) ccl_border_kernel(const uint16_t* __restr
                     if (ny != y && x % LX != 0) skip = witnessed(i, n, vi, vn, YZ);
                     else if (nx != x && y % LY != 0) skip = witnessed(i, n, vi, vn, g.Z);
                 }
-                if (!skip) unite(P, i, n);  // P[cell] is the cell's tile-local root: depth-1 entry points
+                if (skip) continue;
+                // union-find nodes are run starts: translate both cells (P[run start] is its tile-local root: depth-1 entry points)
+                const int zn = z + dz;
+                const uint32_t nrs = zn < 0 ? nbase - 32 + run_start(pm.y, 31) : zn > 31 ? nbase + 32 : nbase + run_start(cm.y, zn);
+                unite(P, base + run_start(Sm, z), nrs);
             }
         };
         against(x, y - 1, 0), against(x - 1, y, 0);
@@ -304,15 +334,17 @@ __global__ void __launch_bounds__(256) ccl_border_kernel(const uint16_t* __restr
 }
 
 // mark the root of each start cell's component
-__global__ void ccl_mark_kernel(uint32_t* __restrict__ P, Geo g, const ushort4* __restrict__ starts, int S)
+__global__ void ccl_mark_kernel(uint32_t* __restrict__ P, const uint2* __restrict__ masks, Geo g, const ushort4* __restrict__ starts, int S)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     const ushort4 sd = starts[s];
-    const uint32_t c = ((uint32_t)sd.x * g.Y + sd.y) * g.Z + sd.z;
-    uint32_t r = P[c];
-    if (r == NONE) return;
-    r &= ~KEEP;  // the start cell may itself be a root that another start already marked
+    const uint32_t row = (uint32_t)sd.x * g.Y + sd.y;
+    const int seg = sd.z / 32, z = sd.z % 32;
+    const uint2 mm = masks[(size_t)row * g.segs + seg];
+    if (!(mm.x >> z & 1u)) return;  // the start cell is not part of any region
+    uint32_t r = P[row * (uint32_t)g.Z + seg * 32 + run_start(mm.y, z)];
+    r &= ~KEEP;  // the run start may itself be a root that another start already marked
     while (true) {
         const uint32_t q = __ldcg(&P[r]) & ~KEEP;
         if (q == r) break;
@@ -375,17 +407,17 @@ __global__ void __launch_bounds__(256) ccl_select_kernel(uint16_t* __restrict__ 
     if ((threadIdx.x & 31) == 0 && freed) atomicAdd(freed_out, freed);
 }
 
-constexpr size_t kTileSmem = (size_t)LCELLS * 4 + (size_t)LROWS * 8 + (size_t)LCELLS * 2;
+constexpr size_t kTileSmem = (size_t)LCELLS * 4 + (size_t)LROWS * 8 + (size_t)LROWS * LABW * 4;
 
 template <int MODE, int NNEIGH>
-vf_status run_ccl(vf_grid* grid, const Geo& g, uint32_t* P, uint2* masks, int blocks_lin)
+vf_status run_ccl(vf_grid* grid, const Geo& g, uint32_t* P, uint2* masks, uint32_t* ends, int blocks_lin)
 {
     vf_ctx* c = grid->ctx;
     auto tk = ccl_tile_kernel<MODE, NNEIGH>;
     VF_CUDA(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem));
-    tk<<<g.ntx * g.nty * g.ntz, 256, kTileSmem, c->stream>>>(grid->d, P, masks, g);
+    tk<<<g.ntx * g.nty * g.ntz, 256, kTileSmem, c->stream>>>(grid->d, P, masks, ends, g);
     VF_LAUNCHED(c);
-    ccl_border_kernel<MODE, NNEIGH><<<blocks_lin, 256, 0, c->stream>>>(grid->d, P, masks, g);
+    ccl_border_kernel<MODE, NNEIGH><<<blocks_lin, 256, 0, c->stream>>>(grid->d, P, masks, ends, g);
     VF_LAUNCHED(c);
     return VF_OK;
 }
@@ -408,25 +440,26 @@ vf_status vf_k_keep_seed_components(vf_grid* grid, const ushort4* d_starts, int 
     g.ntx = (g.X + LX - 1) / LX, g.nty = (g.Y + LY - 1) / LY, g.ntz = g.segs;
     g.nsegs = (uint32_t)((size_t)g.X * g.Y * g.segs);
     VF_TRY(vf_scratch_reserve(c, c->keys, n * 4));
-    VF_TRY(vf_scratch_reserve(c, c->grid2, std::max(n * 2, (size_t)g.nsegs * 8)));
+    VF_TRY(vf_scratch_reserve(c, c->grid2, std::max(n * 2, (size_t)g.nsegs * 12)));
     uint32_t* P = (uint32_t*)c->keys.ptr;
     uint2* masks = (uint2*)c->grid2.ptr;
+    uint32_t* ends = (uint32_t*)(masks + g.nsegs);
     const int blocks_lin = c->num_sms * 8;
     VF_TRY(vf_scratch_reserve(c, c->small, 1 << 20));
     if (!d_freed) {
         d_freed = (uint32_t*)((char*)c->small.ptr + (700 << 10));
-        VF_CUDA(cudaMemsetAsync(d_freed, 0, 4, c->stream));
+        VF_TRY(vf_k_zero(c, d_freed, 4));
     }
     if (mode == MODE_C1) {
         ccl_plant_seeds_kernel<<<(nstarts + 127) / 128, 128, 0, c->stream>>>(grid->d, g, d_starts, nstarts);
         VF_LAUNCHED(c);
-        VF_TRY((run_ccl<MODE_C1, 6>(grid, g, P, masks, blocks_lin)));
+        VF_TRY((run_ccl<MODE_C1, 6>(grid, g, P, masks, ends, blocks_lin)));
     } else if (nneigh == 6) {
-        VF_TRY((run_ccl<MODE_F3, 6>(grid, g, P, masks, blocks_lin)));
+        VF_TRY((run_ccl<MODE_F3, 6>(grid, g, P, masks, ends, blocks_lin)));
     } else {
-        VF_TRY((run_ccl<MODE_F3, 26>(grid, g, P, masks, blocks_lin)));
+        VF_TRY((run_ccl<MODE_F3, 26>(grid, g, P, masks, ends, blocks_lin)));
     }
-    ccl_mark_kernel<<<(nstarts + 127) / 128, 128, 0, c->stream>>>(P, g, d_starts, nstarts);
+    ccl_mark_kernel<<<(nstarts + 127) / 128, 128, 0, c->stream>>>(P, masks, g, d_starts, nstarts);
     VF_LAUNCHED(c);
     if (mode == MODE_C1) ccl_select_kernel<MODE_C1><<<blocks_lin, 256, 0, c->stream>>>(grid->d, P, masks, g, d_freed);
     else ccl_select_kernel<MODE_F3><<<blocks_lin, 256, 0, c->stream>>>(grid->d, P, masks, g, d_freed);

@@ -5,6 +5,8 @@
 #include <cstring>
 #include <new>
 
+#include <algorithm>
+
 #include "vf_internal.h"
 
 // ---------------------------------------------------------------------------------------------- errors
@@ -126,6 +128,8 @@ extern "C" void vf_ctx_destroy(vf_ctx* c)
 vf_status vf_scratch_reserve(vf_ctx* ctx, VfScratch& s, size_t bytes)
 {
     if (s.bytes >= bytes) return VF_OK;
+    if (&s == &ctx->small) ctx->seed_shadow.clear();   // the arena moves: what the shadows describe is gone
+    if (&s == &ctx->noise) ctx->noise_shadow.clear();
     if (s.ptr) {
         VF_CUDA(cudaStreamSynchronize(ctx->stream));
         VF_CUDA(cudaFree(s.ptr));
@@ -267,19 +271,28 @@ extern "C" vf_status vf_grid_dims(const vf_grid* g, uint32_t dims[3])
 
 extern "C" void* vf_grid_device_ptr(vf_grid* g) { return g ? g->d : nullptr; }
 
+// Whole-grid copies are issued in 8 MiB pieces: a copy engine serves its queue in order, so one 256 MiB transfer of another
+// context (the next model's upload in a pipelined producer) would otherwise hold back this context's small transfers — the seed
+// list, the noise table, the histogram read-back — for its full duration.
+static vf_status copy_in_pieces(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t stream)
+{
+    constexpr size_t kPiece = 8u << 20;
+    for (size_t off = 0; off < bytes; off += kPiece)
+        VF_CUDA(cudaMemcpyAsync((char*)dst + off, (const char*)src + off, std::min(kPiece, bytes - off), kind, stream));
+    return VF_OK;
+}
+
 extern "C" vf_status vf_grid_upload_async(vf_grid* g, const uint16_t* host)
 {
     VF_REQUIRE(g && host, VF_ERR_INVALID_ARGUMENT, "null argument");
     VF_TRY(vf_enter(g->ctx));
-    VF_CUDA(cudaMemcpyAsync(g->d, host, g->n() * sizeof(uint16_t), cudaMemcpyHostToDevice, g->ctx->stream));
-    return VF_OK;
+    return copy_in_pieces(g->d, host, g->n() * sizeof(uint16_t), cudaMemcpyHostToDevice, g->ctx->stream);
 }
 extern "C" vf_status vf_grid_download_async(vf_grid* g, uint16_t* host)
 {
     VF_REQUIRE(g && host, VF_ERR_INVALID_ARGUMENT, "null argument");
     VF_TRY(vf_enter(g->ctx));
-    VF_CUDA(cudaMemcpyAsync(host, g->d, g->n() * sizeof(uint16_t), cudaMemcpyDeviceToHost, g->ctx->stream));
-    return VF_OK;
+    return copy_in_pieces(host, g->d, g->n() * sizeof(uint16_t), cudaMemcpyDeviceToHost, g->ctx->stream);
 }
 extern "C" vf_status vf_grid_upload(vf_grid* g, const uint16_t* host)
 {
@@ -316,18 +329,35 @@ vf_status vf_upload_seeds(vf_ctx* ctx, const uint32_t* seeds, uint32_t n, uint32
     VF_REQUIRE(seeds && n > 0, VF_ERR_INVALID_ARGUMENT, "no seeds");
     VF_REQUIRE((size_t)n * sizeof(ushort4) <= 65536, VF_ERR_CAPACITY, "too many seeds (%u)", n);
     VF_TRY(vf_scratch_reserve(ctx, ctx->small, 1 << 20));
-    // the pinned mailbox may still be in flight from a previous call on this stream
-    VF_CUDA(cudaStreamSynchronize(ctx->stream));
-    ushort4* h = (ushort4*)ctx->pinned;
+    std::vector<ushort4> packed(n);
     for (uint32_t i = 0; i < n; ++i) {
         VF_REQUIRE(seeds[4 * i] < X && seeds[4 * i + 1] < Y && seeds[4 * i + 2] < Z, VF_ERR_INVALID_ARGUMENT,
                    "seed %u (%u,%u,%u) outside the %ux%ux%u grid", i, seeds[4 * i], seeds[4 * i + 1], seeds[4 * i + 2], X, Y, Z);
         VF_REQUIRE(seeds[4 * i + 3] <= 0xFFFFu, VF_ERR_CAPACITY, "seed %u label %u does not fit the uint16 cell", i, seeds[4 * i + 3]);
-        h[i] = make_ushort4((unsigned short)seeds[4 * i], (unsigned short)seeds[4 * i + 1], (unsigned short)seeds[4 * i + 2],
-                            (unsigned short)seeds[4 * i + 3]);
+        packed[i] = make_ushort4((unsigned short)seeds[4 * i], (unsigned short)seeds[4 * i + 1], (unsigned short)seeds[4 * i + 2],
+                                 (unsigned short)seeds[4 * i + 3]);
     }
-    VF_CUDA(cudaMemcpyAsync(ctx->small.ptr, h, (size_t)n * sizeof(ushort4), cudaMemcpyHostToDevice, ctx->stream));
     *d_out = (ushort4*)ctx->small.ptr;
+    if (ctx->seed_shadow.size() == n && std::memcmp(ctx->seed_shadow.data(), packed.data(), (size_t)n * sizeof(ushort4)) == 0) return VF_OK;  // already there
+    // the pinned mailbox may still be in flight from a previous call on this stream
+    VF_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(ctx->pinned, packed.data(), (size_t)n * sizeof(ushort4));
+    ctx->seed_shadow.clear();
+    VF_CUDA(cudaMemcpyAsync(ctx->small.ptr, ctx->pinned, (size_t)n * sizeof(ushort4), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->seed_shadow = std::move(packed);
+    return VF_OK;
+}
+
+__global__ void zero_kernel(uint32_t* __restrict__ p, size_t nwords)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) p[i] = 0u;
+}
+vf_status vf_k_zero(vf_ctx* ctx, void* d, size_t bytes)
+{
+    const size_t nwords = bytes / 4;
+    const int blocks = (int)std::min<size_t>((nwords + 255) / 256, (size_t)ctx->num_sms * 4);
+    zero_kernel<<<blocks, 256, 0, ctx->stream>>>((uint32_t*)d, nwords);
+    VF_LAUNCHED(ctx);
     return VF_OK;
 }
 

@@ -568,6 +568,7 @@ extern "C" vf_status vf_flood_slab_init(vf_grid* slab_grid, uint32_t* keys_dev, 
                                 (unsigned short)seeds_local[4 * i + 3]);
         }
         ushort4* d_seeds = (ushort4*)c->small.ptr;
+        c->seed_shadow.clear();  // the seed area is overwritten behind vf_upload_seeds' back
         VF_CUDA(cudaMemcpyAsync(d_seeds, h, (size_t)nseeds * sizeof(ushort4), cudaMemcpyHostToDevice, c->stream));
         flood_seed_order_kernel<<<1, 32, 0, c->stream>>>(keys_dev, s->job.g, s->job.wl, d_seeds, (int)nseeds, s->job.round);
         VF_LAUNCHED(c);
@@ -625,6 +626,7 @@ extern "C" vf_status vf_flood_slab_finalize(vf_slab* s, const uint32_t* seeds_gl
     ushort4* h = (ushort4*)c->pinned;
     for (uint32_t i = 0; i < nseeds_total; ++i) h[i] = make_ushort4(0, 0, 0, (unsigned short)seeds_global[4 * i + 3]);
     d_seeds = (ushort4*)c->small.ptr;
+    c->seed_shadow.clear();
     VF_CUDA(cudaMemcpyAsync(d_seeds, h, (size_t)nseeds_total * sizeof(ushort4), cudaMemcpyHostToDevice, c->stream));
     VF_CUDA(cudaMemsetAsync(s->job.wl.stats + ST_MAXDIST, 0, 4, c->stream));
     flood_finalize_kernel<<<s->job.blocks_stream, 256, 0, c->stream>>>(s->keys, s->grid->d, s->grid->n(), d_seeds, 0xFFFFu, s->job.wl.stats);

@@ -10,6 +10,7 @@
 // removes the reference's copyGrid pass; the final sweep reads a snapshot and writes the other buffer (the reference's
 // in-place sweep is racy; DESIGN.md defines snapshot semantics).  Erosion masks larger than 3^3 take a direct global-memory path.
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 #include "vf_internal.h"
@@ -47,11 +48,23 @@ struct ErodeArgs {
     float prob, thr, activations;
     int boundary_mode;
     unsigned maskbits;  // 27-bit mask of the 3^3 convolution (bit = (dx+1)*9 + (dy+1)*3 + (dz+1))
+    // erodes[visited] bit `count` = (float(count) / float(visited) < activations * thr), evaluated on the host with the same
+    // IEEE float32 expression as erodeGrid-comp.glsl:55-56; visited <= 27 cells of the clamped 3^3 box
+    unsigned erodes[28];
+    unsigned long long nn_magic;  // 2^64 / nnoise + 1: exact 32-bit modulo by multiplication when the grid has < 2^32 cells
+    int idx32;
 };
 
-// 0xFFFF never equals a real label word produced by the path (ids < 0x8000, bit 15 only together with an id), so halo cells
-// outside the grid can be staged as 0xFFFF for the equality stencils and excluded from "visited" counts arithmetically.
-constexpr uint16_t kOutside = 0xFFFFu;
+__device__ __forceinline__ unsigned noise_index(const ErodeArgs& ea, size_t gi)
+{
+    if (ea.idx32) return (unsigned)__umul64hi(ea.nn_magic * (unsigned)gi, (unsigned long long)ea.nnoise);
+    return (unsigned)(gi % ea.nnoise);
+}
+
+// Halo cells outside the grid are staged as EMPTY.  That is exact for all three stencils: detect only looks for labels
+// (> FREE); erosion only acts on labelled voxels, which never equal EMPTY, and takes "visited" from the coordinates; the sweep
+// compares with `own`, and a voxel whose own word is EMPTY comes out EMPTY whatever it counts.
+constexpr uint16_t kOutside = 0u;
 
 template <int OP>
 __global__ void __launch_bounds__(256) stencil_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, Dims d, int ntx, int nty, int ntz,
@@ -85,7 +98,7 @@ __global__ void __launch_bounds__(256) stencil_kernel(const uint16_t* __restrict
                     for (int dz = -1; dz <= 1; ++dz) {
                         const uint16_t raw = s[s_at(x + dx, y + dy, z + dz)];
                         const uint16_t v = raw & 0x7FFFu;
-                        boundary = boundary || (raw != kOutside && v > VF_VOXEL_FREE && v != own);
+                        boundary = boundary || (v > VF_VOXEL_FREE && v != own);
                     }
             if (boundary) dst[gi] = own | 0x8000u;
         } else if (OP == OP_ERODE3) {
@@ -229,45 +242,102 @@ __constant__ int c_win_off[27] = {
     (HY + 1) * FRS - 1, (HY + 1) * FRS, (HY + 1) * FRS + 1
 };
 
-// exact per-voxel stencils on the staged tile.  Cells outside the grid hold kOutside, which never equals a label word, so the
-// equality counts need no bounds tests; only erosion's "visited" (cells of the clamped box) is computed from the coordinates.
+// Exact stencils for a PAIR of z-adjacent voxels A = (x, y, z), B = (x, y, z + 1), z even, on packed 16-bit lanes.
+// Per staged row three aligned words W0 = cells (z-2, z-1), W1 = (z, z+1), W2 = (z+2, z+3) give the three compare words
+//   C1 = (z-1, z)   both lanes neighbours of A,      C2 = (z+1, z+2)  both lanes neighbours of B,
+//   C3 = W1         lane z is a neighbour of B, lane z+1 a neighbour of A,
+// so the 2 x 27 comparisons of the pair cost 27 packed ones.  "differs from own" per lane is min(word ^ own, 1) (VIMNMX.U16x2),
+// accumulated with a plain add (<= 27 per lane).  Cells outside the grid hold EMPTY (see kOutside).
+__device__ __forceinline__ unsigned ne2(unsigned w, unsigned own2) { return __vminu2(w ^ own2, 0x00010001u); }
+// detect: lane != 0 iff the cell holds a label (> FREE, tag ignored) different from own (own2m = own without tags)
+__device__ __forceinline__ unsigned other2(unsigned w, unsigned own2m) { return __vminu2(w & 0x7FFE7FFEu, (w & 0x7FFF7FFFu) ^ own2m); }
+
+struct PairAcc {
+    unsigned a1 = 0, a2 = 0, a3 = 0, a4 = 0;  // C1 (A|A), C2 (B|B), C3 (B|A), face rows (A|B)
+};
+
+constexpr unsigned kStarMask = 0x00417410u;  // centre + 6 face neighbours (ELLIPSE / CROSS of size 3)
+constexpr unsigned kFullMask = 0x07FFFFFFu;
+
 template <int OP>
-__device__ __forceinline__ uint16_t stencil_voxel(const uint16_t* s, const Dims& d, int x, int y, int z, int gx, int gy, int gz, size_t gi, const ErodeArgs& ea,
-                                                  bool& changed)
+__device__ __forceinline__ void pair_row(const uint16_t* p, unsigned AA, unsigned BB, unsigned BA, PairAcc& acc)
+{
+    const unsigned W0 = *reinterpret_cast<const unsigned*>(p - 2), W1 = *reinterpret_cast<const unsigned*>(p), W2 = *reinterpret_cast<const unsigned*>(p + 2);
+    const unsigned C1 = __byte_perm(W0, W1, 0x5432), C2 = __byte_perm(W1, W2, 0x5432);
+    if (OP == OP_DETECT) {
+        acc.a1 |= other2(C1, AA), acc.a2 |= other2(C2, BB), acc.a3 |= other2(W1, BA);
+    } else {
+        acc.a1 += ne2(C1, AA), acc.a2 += ne2(C2, BB), acc.a3 += ne2(W1, BA);
+    }
+}
+
+// generic 3^3 erosion mask (anything but the star and the full cube): per-voxel count over the set bits
+__device__ __forceinline__ unsigned masked_count(const uint16_t* ctr, unsigned maskbits)
+{
+    const unsigned own = *ctr;
+    unsigned count = 0;
+    for (unsigned m = maskbits; m; m &= m - 1) count += ctr[c_win_off[__ffs(m) - 1]] == own;  // mask bits are warp-uniform
+    return count;
+}
+
+template <int OP>
+__device__ __forceinline__ void stencil_pair(const uint16_t* s, const Dims& d, int x, int y, int z, int gx, int gy, int gz, size_t gi, const ErodeArgs& ea,
+                                             uint16_t* __restrict__ dst)
 {
     const uint16_t* ctr = s + f_at(x, y, z);
-    const uint16_t own = *ctr;
-    changed = false;
+    const unsigned own2 = *reinterpret_cast<const unsigned*>(ctr);
+    const unsigned ownA = own2 & 0xFFFFu, ownB = own2 >> 16;
+    PairAcc acc;
     if (OP == OP_DETECT) {
-        if (own <= VF_VOXEL_FREE || (own & 0x8000u)) return own;  // unlabelled, or already tagged (stays tagged whatever the window holds)
-        bool boundary = false;
+        // detectBoundaries-comp.glsl:21-42; in place: neighbours are compared with bit 15 cleared, so the result does not depend
+        // on which neighbours this pass has already tagged
+        const unsigned m2 = own2 & 0x7FFF7FFFu;
+        const unsigned AA = __byte_perm(m2, 0, 0x1010), BB = __byte_perm(m2, 0, 0x3232), BA = __byte_perm(m2, 0, 0x1032);
 #pragma unroll
-        for (int b = 0; b < 27; ++b) {
-            const unsigned raw = ctr[c_win_off[b]];
-            const unsigned v = raw & 0x7FFFu;
-            boundary = boundary || (raw != kOutside && v > VF_VOXEL_FREE && v != own);
-        }
-        changed = boundary;
-        return boundary ? (uint16_t)(own | 0x8000u) : own;
-    } else if (OP == OP_ERODE3) {
-        uint16_t out = own;
-        const bool isB = ea.boundary_mode == 0 ? (own & 0x7FFFu) != 0 : (own >> 15) != 0;
-        if (own > VF_VOXEL_FREE && isB && ea.noise[gi % ea.nnoise] < ea.prob) {
-            unsigned count = 0;
-            for (unsigned m = ea.maskbits; m; m &= m - 1) count += ctr[c_win_off[__ffs(m) - 1]] == own;  // mask bits are warp-uniform
-            const int vx = 1 + (gx > 0) + (gx < d.X - 1), vy = 1 + (gy > 0) + (gy < d.Y - 1), vz = 1 + (gz > 0) + (gz < d.Z - 1);
-            const float activation = __fdiv_rn((float)count, (float)(vx * vy * vz));
-            if (activation < __fmul_rn(ea.activations, ea.thr)) out = VF_VOXEL_EMPTY;
-        }
-        changed = true;
-        return out;
-    } else {
-        int count = -1;
-#pragma unroll
-        for (int b = 0; b < 27; ++b) count += ctr[c_win_off[b]] == own;
-        changed = true;
-        return count < 6 ? (uint16_t)VF_VOXEL_EMPTY : own;
+        for (int r = 0; r < 9; ++r) pair_row<OP>(ctr + ((r / 3 - 1) * HY + (r % 3 - 1)) * FRS, AA, BB, BA, acc);
+        const bool otherA = ((acc.a1 | (acc.a1 >> 16) | (acc.a3 >> 16)) & 0xFFFFu) != 0, otherB = ((acc.a2 | (acc.a2 >> 16) | acc.a3) & 0xFFFFu) != 0;
+        // unlabelled or already tagged voxels stay as they are
+        const bool tagA = otherA && ownA > VF_VOXEL_FREE && !(ownA & 0x8000u), tagB = otherB && ownB > VF_VOXEL_FREE && !(ownB & 0x8000u);
+        if (tagA || tagB) *reinterpret_cast<unsigned*>(dst + gi) = own2 | (tagA ? 0x8000u : 0u) | (tagB ? 0x80000000u : 0u);
+        return;
     }
+    const unsigned AA = __byte_perm(own2, 0, 0x1010), BB = __byte_perm(own2, 0, 0x3232), BA = __byte_perm(own2, 0, 0x1032);
+    if (OP == OP_SWEEP) {
+        // removeIsolatedRegionsGrid-comp.glsl:24-38, snapshot semantics: fewer than 6 equal neighbours -> EMPTY
+#pragma unroll
+        for (int r = 0; r < 9; ++r) pair_row<OP>(ctr + ((r / 3 - 1) * HY + (r % 3 - 1)) * FRS, AA, BB, BA, acc);
+        const unsigned neA = (acc.a1 & 0xFFFFu) + (acc.a1 >> 16) + (acc.a3 >> 16), neB = (acc.a2 & 0xFFFFu) + (acc.a2 >> 16) + (acc.a3 & 0xFFFFu);
+        const unsigned outA = 26u - neA < 6u ? (unsigned)VF_VOXEL_EMPTY : ownA, outB = 26u - neB < 6u ? (unsigned)VF_VOXEL_EMPTY : ownB;
+        *reinterpret_cast<unsigned*>(dst + gi) = outA | outB << 16;
+        return;
+    }
+    // erodeGrid-comp.glsl:31-58 for maskSize 3
+    unsigned countA, countB;
+    if (ea.maskbits == kStarMask) {
+        pair_row<OP>(ctr, AA, BB, BA, acc);
+        acc.a4 = ne2(*reinterpret_cast<const unsigned*>(ctr - HY * FRS), own2) + ne2(*reinterpret_cast<const unsigned*>(ctr + HY * FRS), own2) +
+                 ne2(*reinterpret_cast<const unsigned*>(ctr - FRS), own2) + ne2(*reinterpret_cast<const unsigned*>(ctr + FRS), own2);
+        countA = 7u - ((acc.a1 & 0xFFFFu) + (acc.a1 >> 16) + (acc.a3 >> 16) + (acc.a4 & 0xFFFFu));
+        countB = 7u - ((acc.a2 & 0xFFFFu) + (acc.a2 >> 16) + (acc.a3 & 0xFFFFu) + (acc.a4 >> 16));
+    } else if (ea.maskbits == kFullMask) {
+#pragma unroll
+        for (int r = 0; r < 9; ++r) pair_row<OP>(ctr + ((r / 3 - 1) * HY + (r % 3 - 1)) * FRS, AA, BB, BA, acc);
+        countA = 27u - ((acc.a1 & 0xFFFFu) + (acc.a1 >> 16) + (acc.a3 >> 16));
+        countB = 27u - ((acc.a2 & 0xFFFFu) + (acc.a2 >> 16) + (acc.a3 & 0xFFFFu));
+    } else {
+        countA = masked_count(ctr, ea.maskbits), countB = masked_count(ctr + 1, ea.maskbits);
+    }
+    const int vxy = (1 + (gx > 0) + (gx < d.X - 1)) * (1 + (gy > 0) + (gy < d.Y - 1));
+    const unsigned ia = noise_index(ea, gi), ib = ia + 1 == ea.nnoise ? 0u : ia + 1;
+    auto eroded = [&](unsigned own, unsigned count, int zz, unsigned ni) -> unsigned {
+        const bool isB = ea.boundary_mode == 0 ? (own & 0x7FFFu) != 0 : (own >> 15) != 0;
+        if (own > VF_VOXEL_FREE && isB && ea.noise[ni] < ea.prob) {
+            const int visited = vxy * (1 + (zz > 0) + (zz < d.Z - 1));
+            if (ea.erodes[visited] >> count & 1u) return VF_VOXEL_EMPTY;
+        }
+        return own;
+    };
+    *reinterpret_cast<unsigned*>(dst + gi) = eroded(ownA, countA, gz, ia) | eroded(ownB, countB, gz + 1, ib) << 16;
 }
 
 template <int OP>
@@ -293,7 +363,7 @@ __global__ void __launch_bounds__(256) stencil_fast_kernel(const uint16_t* __res
             const unsigned sa = (unsigned)__cvta_generic_to_shared(dstp);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + ((size_t)gx * d.Y + gy) * d.Z + gz) : "memory");
         } else {
-            *reinterpret_cast<uint4*>(dstp) = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            *reinterpret_cast<uint4*>(dstp) = make_uint4(0u, 0u, 0u, 0u);  // kOutside
         }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -339,16 +409,14 @@ __global__ void __launch_bounds__(256) stencil_fast_kernel(const uint16_t* __res
     }
     __syncthreads();
 
-    // ---- queued chunks: exact per-voxel stencil, one voxel per thread per round (balanced across the CTA)
+    // ---- queued chunks: exact stencil, one voxel pair per thread per round (balanced across the CTA)
     const int nq = ntasks;
-    for (int q = t; q < nq * 8; q += 256) {
-        const int c = tasks[q >> 3], k = q & 7;
-        const int zc = c & 7, y = (c >> 3) & 7, x = c >> 6, z = zc * 8 + k;
+    for (int q = t; q < nq * 4; q += 256) {
+        const int c = tasks[q >> 2], k = q & 3;
+        const int zc = c & 7, y = (c >> 3) & 7, x = c >> 6, z = zc * 8 + k * 2;
         const int gx = gx0 + x, gy = gy0 + y, gz = gz0 + z;
         const size_t gi = ((size_t)gx * d.Y + gy) * d.Z + gz;
-        bool changed;
-        const uint16_t out = stencil_voxel<OP>(s, d, x, y, z, gx, gy, gz, gi, ea, changed);
-        if (changed) dst[gi] = out;
+        stencil_pair<OP>(s, d, x, y, z, gx, gy, gz, gi, ea, dst);
     }
 }
 
@@ -450,10 +518,26 @@ extern "C" vf_status vf_erode(vf_grid* g, int type, uint32_t size, uint32_t iter
     VF_TRY(vf_scratch_reserve(c, c->noise, (size_t)nnoise * 4 + mask.size() * 4 + 256));
     float* d_noise = (float*)c->noise.ptr;
     float* d_mask = d_noise + nnoise;
-    VF_CUDA(cudaMemcpyAsync(d_noise, noise, (size_t)nnoise * 4, cudaMemcpyHostToDevice, c->stream));
-    VF_CUDA(cudaMemcpyAsync(d_mask, mask.data(), mask.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    VF_CUDA(cudaStreamSynchronize(c->stream));  // `mask` is a host temporary
-    ErodeArgs ea = { d_noise, nnoise, prob, thr, activations, boundary_mode, 0u };
+    // The noise table travels on the stream: from pageable memory the call returns once the driver has staged it; a pinned
+    // table must stay valid until the context is synchronised (documented in voxfrag.h).
+    // A table identical to the one already on the device (compared against a host shadow) is not sent again.
+    if (c->noise_shadow.size() != nnoise || std::memcmp(c->noise_shadow.data(), noise, (size_t)nnoise * 4) != 0) {
+        c->noise_shadow.clear();
+        VF_CUDA(cudaMemcpyAsync(d_noise, noise, (size_t)nnoise * 4, cudaMemcpyHostToDevice, c->stream));
+        c->noise_shadow.assign(noise, noise + nnoise);
+    }
+    if (size != 3)  // the 3^3 kernels take the mask as 27 bits; only the generic kernel reads the float mask (pageable: staged before return)
+        VF_CUDA(cudaMemcpyAsync(d_mask, mask.data(), mask.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    ErodeArgs ea = {};
+    ea.noise = d_noise, ea.nnoise = nnoise, ea.prob = prob, ea.thr = thr, ea.activations = activations, ea.boundary_mode = boundary_mode;
+    for (int visited = 1; visited <= 27; ++visited)
+        for (int count = 0; count <= 27; ++count) {
+            const volatile float activation = (float)count / (float)visited;  // float32, as erodeGrid-comp.glsl:55
+            const volatile float limit = activations * thr;
+            if (activation < limit) ea.erodes[visited] |= 1u << count;
+        }
+    ea.nn_magic = ~0ull / nnoise + 1;
+    ea.idx32 = n <= 0xFFFFFFFFull;
     if (size == 3)
         for (int i = 0; i < 27; ++i)
             if (mask[i] != 0.0f) ea.maskbits |= 1u << i;
@@ -487,7 +571,7 @@ extern "C" vf_status vf_histogram(vf_grid* g, uint32_t* counts, uint64_t* occupi
     // device bins live after the seed area of the small arena
     uint32_t* d_counts = (uint32_t*)((char*)c->small.ptr + (512 << 10));
     unsigned long long* d_occ = (unsigned long long*)(d_counts + VF_HISTOGRAM_BINS);
-    VF_CUDA(cudaMemsetAsync(d_counts, 0, VF_HISTOGRAM_BINS * 4 + 8, c->stream));
+    VF_TRY(vf_k_zero(c, d_counts, VF_HISTOGRAM_BINS * 4 + 8));
     const int blocks = (int)std::min((size_t)c->num_sms * 4, (g->n() / 8 + 255) / 256 + 1);
     histogram_kernel<<<blocks, 256, 0, c->stream>>>(g->d, g->n(), d_counts, d_occ);
     VF_LAUNCHED(c);

@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <vector>
 
 #include "../../include/voxfrag.h"
 
@@ -100,6 +101,11 @@ struct vf_ctx {
     VfScratch mesh;      // voxelizer: vertices, faces, bins
     void* pinned = nullptr;  // small pinned host mailbox for counters
     size_t pinned_bytes = 0;
+    // Host shadows of what the seed area of `small` and the `noise` arena hold on the device.  A call that brings the same
+    // seeds / noise table again (every step of a batch producer does) skips the transfer: copy engines serve transfers in
+    // submission order, so even a 1 KiB upload would wait for a neighbouring context's whole-grid copy to drain.
+    std::vector<ushort4> seed_shadow;
+    std::vector<float> noise_shadow;
 };
 
 struct vf_grid {
@@ -116,6 +122,7 @@ struct vf_grid {
 vf_status vf_scratch_reserve(vf_ctx* ctx, VfScratch& s, size_t bytes);
 vf_status vf_enter(vf_ctx* ctx);  // cudaSetDevice
 vf_status vf_upload_seeds(vf_ctx* ctx, const uint32_t* seeds, uint32_t n, uint32_t X, uint32_t Y, uint32_t Z, ushort4** d_out);
+vf_status vf_k_zero(vf_ctx* ctx, void* d, size_t bytes);  // zero-fill by kernel (bytes % 4 == 0): never queues behind a copy engine
 
 // ---------------------------------------------------------------------------------------------- kernels (one per file)
 vf_status vf_k_naive(vf_grid* g, const ushort4* d_seeds, uint32_t nseeds, int dfunc);
