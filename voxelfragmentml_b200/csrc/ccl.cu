@@ -132,9 +132,8 @@ __global__ void __launch_bounds__(256) ccl_tile_kernel(const uint16_t* __restric
     uint32_t* sS = sA + LROWS;                                      // [LROWS] run-start mask per row (bit 0 always set)
     uint32_t* labw = sS + LROWS;                                    // [LROWS][LABW] staged labels, two per word; row = x * LY + y
     auto lab = [&](int r, int z) -> uint32_t { return (labw[r * LABW + (z >> 1)] >> ((z & 1) * 16)) & 0xFFFFu; };
-    const int tile = blockIdx.x;
-    const int tz = tile % g.ntz, ty = (tile / g.ntz) % g.nty, tx = tile / (g.ntz * g.nty);
-    const int gx0 = tx * LX, gy0 = ty * LY, gz0 = tz * LZ;
+    const int tz = blockIdx.x;  // 3-D launch: no index divisions
+    const int gx0 = blockIdx.z * LX, gy0 = blockIdx.y * LY, gz0 = tz * LZ;
 
     // (a) thread per 8-cell chunk (4 threads = one row): 128-bit loads straight from the grid, all of a thread's 4 chunks in flight
     //     at once (scalar loads when rows are not 16-byte aligned).  "active" and "differs from the z-predecessor" are evaluated
@@ -219,10 +218,27 @@ __global__ void __launch_bounds__(256) ccl_tile_kernel(const uint16_t* __restric
                     unite_local(par, r * LZ + run_start(Sm, z), rn * LZ + run_start(sS[rn], zn));
             }
         };
+        // (b1) rows of one x-plane first.  The warps move in lockstep, so nearly every thread finds both runs still their own
+        //      roots and links them with one atomic: chains along y, at most LY deep.
         if (Am) {
-            against(x, y - 1, 0), against(x - 1, y, 0);
+            against(x, y - 1, 0);
+            if (NNEIGH == 26) against(x, y - 1, -1), against(x, y - 1, 1);
+        }
+        __syncthreads();
+        // (b2) flatten, so that the finds of the plane-to-plane unions below start one step from a root
+        {
+            unsigned st = Sm & Am;
+            while (st) {
+                const int z = __ffs(st) - 1;
+                st &= st - 1;
+                par[slot(r * LZ + z)] = find_local(par, r * LZ + z);  // writes an ancestor: safe against concurrent finds
+            }
+        }
+        __syncthreads();
+        // (b3) plane x against plane x-1
+        if (Am) {
+            against(x - 1, y, 0);
             if (NNEIGH == 26) {
-                against(x, y - 1, -1), against(x, y - 1, 1);
                 against(x - 1, y, -1), against(x - 1, y, 1);
 #pragma unroll
                 for (int dz = -1; dz <= 1; ++dz) against(x - 1, y - 1, dz), against(x - 1, y + 1, dz);
@@ -250,18 +266,25 @@ __global__ void __launch_bounds__(256) ccl_tile_kernel(const uint16_t* __restric
 
 // ------------------------------------------------------------------------------------------------ stage 2: across tile borders
 // thread per 32-cell segment.  A pair (my cell z, neighbour cell z+dz of row (nx,ny)) is this stage's business iff the two cells
-// lie in different tiles.
-template <int MODE, int NNEIGH>
+// lie in different tiles.  One launch per axis, z then y then x (the order of stage 1's in-tile phases): the unions of a launch
+// join trees that the previous launches left at most one tile row / tile plane deep, instead of all borders of a fragment
+// contending for the same roots at once.
+enum { AXIS_Z = 0, AXIS_Y = 1, AXIS_X = 2 };
+template <int MODE, int NNEIGH, int AXIS>
 __global__ void __launch_bounds__(256) ccl_border_kernel(const uint16_t* __restrict__ grid, uint32_t* __restrict__ P, const uint2* __restrict__ masks,
                                                          const uint32_t* __restrict__ ends, Geo g)
 {
-    for (uint32_t sg = blockIdx.x * blockDim.x + threadIdx.x; sg < g.nsegs; sg += gridDim.x * blockDim.x) {
+    {
+        const uint32_t sg = blockIdx.x * blockDim.x + threadIdx.x;
+        if (sg >= g.nsegs) return;
         const int seg = sg % g.segs;
         const uint32_t row = sg / g.segs;
         const int y = (int)(row % g.Y), x = (int)(row / g.Y);
+        if (AXIS == AXIS_Z && seg == 0) return;
+        if (NNEIGH == 6 && ((AXIS == AXIS_Y && y % LY != 0) || (AXIS == AXIS_X && x % LX != 0))) return;  // rows inside a tile: stage 1
         const uint2 mm = masks[sg];
         const unsigned Am = mm.x, Sm = mm.y;
-        if (!Am) continue;
+        if (!Am) return;
         const uint32_t base = row * (uint32_t)g.Z + seg * 32;
         // A pair (i, n) that straddles a tile border need not be united when a "witness" pair one row (or plane) back, inside the
         // same two tiles, carries the same labels: stage 1 united i with its witness and n with its witness, and the witness pair
@@ -272,7 +295,7 @@ __global__ void __launch_bounds__(256) ccl_border_kernel(const uint16_t* __restr
             return active<MODE>(wi) && active<MODE>(wn) && same<MODE>(vi, wi) && same<MODE>(vn, wn);
         };
         // same row, previous segment (always another tile because LZ == 32): decided from the segment records alone
-        if (seg > 0 && (Am & 1u)) {
+        if (AXIS == AXIS_Z && (Am & 1u)) {
             const uint2 pm = masks[sg - 1];
             if (pm.x >> 31) {
                 const uint32_t vi = ends[sg] & 0xFFFFu, vn = ends[sg - 1] >> 16;
@@ -323,12 +346,17 @@ __global__ void __launch_bounds__(256) ccl_border_kernel(const uint16_t* __restr
                 unite(P, base + run_start(Sm, z), nrs);
             }
         };
-        against(x, y - 1, 0), against(x - 1, y, 0);
-        if (NNEIGH == 26) {
-            against(x, y - 1, -1), against(x, y - 1, 1);
-            against(x - 1, y, -1), against(x - 1, y, 1);
+        if (AXIS == AXIS_Y) {
+            against(x, y - 1, 0);
+            if (NNEIGH == 26) against(x, y - 1, -1), against(x, y - 1, 1);
+        }
+        if (AXIS == AXIS_X) {
+            against(x - 1, y, 0);
+            if (NNEIGH == 26) {
+                against(x - 1, y, -1), against(x - 1, y, 1);
 #pragma unroll
-            for (int dz = -1; dz <= 1; ++dz) against(x - 1, y - 1, dz), against(x - 1, y + 1, dz);
+                for (int dz = -1; dz <= 1; ++dz) against(x - 1, y - 1, dz), against(x - 1, y + 1, dz);
+            }
         }
     }
 }
@@ -415,9 +443,14 @@ vf_status run_ccl(vf_grid* grid, const Geo& g, uint32_t* P, uint2* masks, uint32
     vf_ctx* c = grid->ctx;
     auto tk = ccl_tile_kernel<MODE, NNEIGH>;
     VF_CUDA(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem));
-    tk<<<g.ntx * g.nty * g.ntz, 256, kTileSmem, c->stream>>>(grid->d, P, masks, ends, g);
+    tk<<<dim3(g.ntz, g.nty, g.ntx), 256, kTileSmem, c->stream>>>(grid->d, P, masks, ends, g);
     VF_LAUNCHED(c);
-    ccl_border_kernel<MODE, NNEIGH><<<blocks_lin, 256, 0, c->stream>>>(grid->d, P, masks, ends, g);
+    const int blocks_seg = (int)((g.nsegs + 255) / 256);
+    ccl_border_kernel<MODE, NNEIGH, AXIS_Z><<<blocks_seg, 256, 0, c->stream>>>(grid->d, P, masks, ends, g);
+    VF_LAUNCHED(c);
+    ccl_border_kernel<MODE, NNEIGH, AXIS_Y><<<blocks_seg, 256, 0, c->stream>>>(grid->d, P, masks, ends, g);
+    VF_LAUNCHED(c);
+    ccl_border_kernel<MODE, NNEIGH, AXIS_X><<<blocks_seg, 256, 0, c->stream>>>(grid->d, P, masks, ends, g);
     VF_LAUNCHED(c);
     return VF_OK;
 }

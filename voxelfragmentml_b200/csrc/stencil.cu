@@ -341,29 +341,36 @@ __device__ __forceinline__ void stencil_pair(const uint16_t* s, const Dims& d, i
 }
 
 template <int OP>
-__global__ void __launch_bounds__(256) stencil_fast_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, Dims d, int nty, int ntz, ErodeArgs ea,
-                                                           int uniform_erodes)
+__global__ void __launch_bounds__(256) stencil_fast_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, Dims d, ErodeArgs ea, int uniform_erodes)
 {
     __shared__ __align__(16) uint16_t s[FROWS * FRS];
     __shared__ uint32_t summ[FROWS * 8];
     __shared__ uint16_t tasks[SX * SYT * 8];
     __shared__ int ntasks;
-    const int tile = blockIdx.x;
-    const int tz = tile % ntz, ty = (tile / ntz) % nty, tx = tile / (ntz * nty);
-    const int gx0 = tx * SX, gy0 = ty * SYT, gz0 = tz * SZT;
+    const int gx0 = blockIdx.z * SX, gy0 = blockIdx.y * SYT, gz0 = blockIdx.x * SZT;  // 3-D launch: no index divisions
     const int t = threadIdx.x;
     if (t == 0) ntasks = 0;
 
-    // ---- stage: 800 interior chunks (cp.async, 16 B) + 200 halo cells; outside the grid -> kOutside
-    for (int q = t; q < FROWS * 8; q += 256) {
-        const int row = q >> 3, ch = q & 7;
-        const int gx = gx0 + row / HY - 1, gy = gy0 + row % HY - 1, gz = gz0 + ch * 8;
-        uint16_t* dstp = &s[row * FRS + 8 + ch * 8];
-        if (gx >= 0 && gx < d.X && gy >= 0 && gy < d.Y && gz < d.Z) {
-            const unsigned sa = (unsigned)__cvta_generic_to_shared(dstp);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + ((size_t)gx * d.Y + gy) * d.Z + gz) : "memory");
-        } else {
-            *reinterpret_cast<uint4*>(dstp) = make_uint4(0u, 0u, 0u, 0u);  // kOutside
+    // ---- stage: 800 interior chunks (cp.async, 16 B) + 200 halo cells; outside the grid -> kOutside.
+    // Thread t copies chunk t & 7 of staged rows (t >> 3) + 32 k; (x, y) of the row advance incrementally (32 = 3 * HY + 2).
+    const int ch = t & 7;
+    const int gzc = gz0 + ch * 8;
+    {
+        int r = t >> 3, x = r / HY, y = r - x * HY;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (r < FROWS) {
+                const int gx = gx0 + x - 1, gy = gy0 + y - 1;
+                uint16_t* dstp = &s[r * FRS + 8 + ch * 8];
+                if ((unsigned)gx < (unsigned)d.X && (unsigned)gy < (unsigned)d.Y && gzc < d.Z) {
+                    const unsigned sa = (unsigned)__cvta_generic_to_shared(dstp);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + ((size_t)((unsigned)gx * (unsigned)d.Y + gy)) * d.Z + gzc) : "memory");
+                } else {
+                    *reinterpret_cast<uint4*>(dstp) = make_uint4(0u, 0u, 0u, 0u);  // kOutside
+                }
+            }
+            r += 32, x += 3, y += 2;
+            if (y >= HY) y -= HY, ++x;
         }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -371,40 +378,60 @@ __global__ void __launch_bounds__(256) stencil_fast_kernel(const uint16_t* __res
         const int row = t >> 1, side = t & 1;
         const int gx = gx0 + row / HY - 1, gy = gy0 + row % HY - 1, gz = side ? gz0 + SZT : gz0 - 1;
         uint16_t v = kOutside;
-        if (gx >= 0 && gx < d.X && gy >= 0 && gy < d.Y && gz >= 0 && gz < d.Z) v = src[((size_t)gx * d.Y + gy) * d.Z + gz];
+        if ((unsigned)gx < (unsigned)d.X && (unsigned)gy < (unsigned)d.Y && (unsigned)gz < (unsigned)d.Z) v = src[((size_t)((unsigned)gx * (unsigned)d.Y + gy)) * d.Z + gz];
         s[row * FRS + (side ? 72 : 7)] = v;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
-    // ---- chunk summaries
-    for (int q = t; q < FROWS * 8; q += 256) {
-        const int row = q >> 3, ch = q & 7;
-        const uint16_t* p = &s[row * FRS + 8 + ch * 8];
-        const uint4 v = *reinterpret_cast<const uint4*>(p);
-        const unsigned v0 = v.x & 0xFFFFu;
-        const bool u8 = v.x == v0 * 0x10001u && v.y == v.x && v.z == v.x && v.w == v.x;
-        const bool uz = u8 && p[-1] == v0 && p[8] == v0;
-        summ[q] = v0 | (uz ? 0x10000u : 0u);
+    // ---- chunk summaries; along the way: does the whole staged region hold one value?
+    const unsigned ref = s[f_at(0, 0, 0)];
+    bool all_ref = true;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int row = (t >> 3) + 32 * k;
+        if (row < FROWS) {
+            const uint16_t* p = &s[row * FRS + 8 + ch * 8];
+            const uint4 v = *reinterpret_cast<const uint4*>(p);
+            const unsigned v0 = v.x & 0xFFFFu;
+            const bool u8 = v.x == v0 * 0x10001u && v.y == v.x && v.z == v.x && v.w == v.x;
+            const bool uz = u8 && p[-1] == v0 && p[8] == v0;
+            summ[row * 8 + ch] = v0 | (uz ? 0x10000u : 0u);
+            all_ref = all_ref && uz && v0 == ref;
+        }
     }
-    __syncthreads();
+    if (__syncthreads_and(all_ref) && !(OP == OP_ERODE3 && uniform_erodes)) {
+        // one value everywhere, halo included: all three stencils are the identity on this tile
+        if (OP != OP_DETECT) {
+            const uint4 fill = make_uint4(ref * 0x10001u, ref * 0x10001u, ref * 0x10001u, ref * 0x10001u);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int y = (t >> 3) & 7, x = (t >> 6) + 4 * k;
+                const int gx = gx0 + x, gy = gy0 + y;
+                if (gx < d.X && gy < d.Y && gzc < d.Z) *reinterpret_cast<uint4*>(dst + ((size_t)((unsigned)gx * (unsigned)d.Y + gy)) * d.Z + gzc) = fill;
+            }
+        }
+        return;
+    }
 
     // ---- interior chunks: uniform window -> identity (vector copy / nothing), otherwise queue
-    for (int c = t; c < SX * SYT * 8; c += 256) {
-        const int zc = c & 7, y = (c >> 3) & 7, x = c >> 6;
-        const int gx = gx0 + x, gy = gy0 + y, gz = gz0 + zc * 8;
-        if (gx >= d.X || gy >= d.Y || gz >= d.Z) continue;
-        const unsigned su = summ[((x + 1) * HY + (y + 1)) * 8 + zc];
-        bool uniform = (su & 0x10000u) != 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int y = (t >> 3) & 7, x = (t >> 6) + 4 * k;
+        const int gx = gx0 + x, gy = gy0 + y;
+        if (gx >= d.X || gy >= d.Y || gzc >= d.Z) continue;
+        const uint32_t* sp = &summ[(x * HY + y) * 8 + ch];  // summary of staged row (x-1, y-1)
+        const unsigned su = sp[(HY + 1) * 8];
+        unsigned diff = ~su & 0x10000u;  // window not uniform along z
 #pragma unroll
         for (int dx = 0; dx <= 2; ++dx)
 #pragma unroll
-            for (int dy = 0; dy <= 2; ++dy) uniform = uniform && summ[((x + dx) * HY + (y + dy)) * 8 + zc] == su;
-        const size_t gi = ((size_t)gx * d.Y + gy) * d.Z + gz;
-        if (uniform && !(OP == OP_ERODE3 && uniform_erodes)) {
-            if (OP != OP_DETECT) *reinterpret_cast<uint4*>(dst + gi) = *reinterpret_cast<const uint4*>(&s[f_at(x, y, zc * 8)]);
+            for (int dy = 0; dy <= 2; ++dy) diff |= sp[(dx * HY + dy) * 8] ^ su;
+        if (diff == 0 && !(OP == OP_ERODE3 && uniform_erodes)) {
+            if (OP != OP_DETECT)
+                *reinterpret_cast<uint4*>(dst + ((size_t)((unsigned)gx * (unsigned)d.Y + gy)) * d.Z + gzc) = *reinterpret_cast<const uint4*>(&s[f_at(x, y, ch * 8)]);
         } else {
-            tasks[atomicAdd(&ntasks, 1)] = (uint16_t)c;
+            tasks[atomicAdd(&ntasks, 1)] = (uint16_t)((x << 6) | (y << 3) | ch);
         }
     }
     __syncthreads();
@@ -426,7 +453,7 @@ vf_status launch_stencil(vf_grid* g, int op, const uint16_t* src, uint16_t* dst,
     Dims d = { (int)g->X, (int)g->Y, (int)g->Z };
     const int ntx = (d.X + SX - 1) / SX, nty = (d.Y + SYT - 1) / SYT, ntz = (d.Z + SZT - 1) / SZT;
     const int blocks = ntx * nty * ntz;
-    if (d.Z % 8 == 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+    if (d.Z % 8 == 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0 && nty <= 65535 && ntx <= 65535) {
         // would a voxel with a completely uniform neighbourhood erode?  (count = mask population, visited = 27; true only for
         // unusual thresholds, e.g. CROSS with threshold > 0.78).  Evaluated with the kernel's float32 expression.
         int uniform_erodes = 0;
@@ -434,10 +461,11 @@ vf_status launch_stencil(vf_grid* g, int op, const uint16_t* src, uint16_t* dst,
             const float activation = (float)__builtin_popcount(ea.maskbits) / 27.0f;
             uniform_erodes = activation < ea.activations * ea.thr;
         }
+        const dim3 grid3(ntz, nty, ntx);
         switch (op) {
-        case OP_DETECT: stencil_fast_kernel<OP_DETECT><<<blocks, 256, 0, c->stream>>>(src, dst, d, nty, ntz, ea, 0); break;
-        case OP_ERODE3: stencil_fast_kernel<OP_ERODE3><<<blocks, 256, 0, c->stream>>>(src, dst, d, nty, ntz, ea, uniform_erodes); break;
-        default: stencil_fast_kernel<OP_SWEEP><<<blocks, 256, 0, c->stream>>>(src, dst, d, nty, ntz, ea, 0); break;
+        case OP_DETECT: stencil_fast_kernel<OP_DETECT><<<grid3, 256, 0, c->stream>>>(src, dst, d, ea, 0); break;
+        case OP_ERODE3: stencil_fast_kernel<OP_ERODE3><<<grid3, 256, 0, c->stream>>>(src, dst, d, ea, uniform_erodes); break;
+        default: stencil_fast_kernel<OP_SWEEP><<<grid3, 256, 0, c->stream>>>(src, dst, d, ea, 0); break;
         }
         VF_LAUNCHED(c);
         return VF_OK;
