@@ -9,6 +9,8 @@
 // scattered 2-byte loads per voxel as in the shaders.  Erosion ping-pongs between the grid and one scratch grid, which
 // removes the reference's copyGrid pass; the final sweep reads a snapshot and writes the other buffer (the reference's
 // in-place sweep is racy; DESIGN.md defines snapshot semantics).  Erosion masks larger than 3^3 take a direct global-memory path.
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
+
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -172,9 +174,11 @@ __global__ void __launch_bounds__(256) erode_generic_kernel(const uint16_t* __re
 }
 
 // ------------------------------------------------------------------------------------------------ H1 histogram
-// one pass over 2 B/voxel; per-thread run-length accumulation (neighbouring voxels share a label), then shared-memory
-// bins for ids < 4096 and global atomics beyond.
+// one pass over 2 B/voxel.  A warp walks contiguous spans of 32 x 4 vectors (8 voxels each) with its four loads in flight;
+// every lane keeps a (label, count) run across the whole walk, so inside a fragment a lane issues one shared-memory atomic per
+// label change instead of one per vector.  Shared bins for ids < 4096, global atomics beyond.
 constexpr int kSmemBins = 4096;
+constexpr int kHistBatch = 4;
 __global__ void __launch_bounds__(256) histogram_kernel(const uint16_t* __restrict__ grid, size_t n, uint32_t* __restrict__ counts,
                                                         unsigned long long* __restrict__ occupied)
 {
@@ -188,32 +192,42 @@ __global__ void __launch_bounds__(256) histogram_kernel(const uint16_t* __restri
         if (label < kSmemBins) atomicAdd(&bins[label], c);
         else atomicAdd(&counts[label], c);
     };
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
-        const uint4 v = vf_ldg_stream(g4 + i);
-        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
-        uint32_t run_label = 0xFFFFFFFFu, run = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t raw = (w[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
-            if (raw > VF_VOXEL_FREE) {  // RegularGrid.cpp:612: raw value > FREE, then unmask
-                const uint32_t label = raw & 0x7FFFu;
-                ++occ;
-                if (label == run_label) ++run;
-                else {
-                    if (run) add(run_label, run);
-                    run_label = label, run = 1;
-                }
+    uint32_t run_label = 0xFFFFFFFFu, run = 0;
+    auto take = [&](uint32_t raw, uint32_t c) {  // c voxels holding the word `raw`
+        if (raw > VF_VOXEL_FREE) {               // RegularGrid.cpp:612: raw value > FREE, then unmask
+            const uint32_t label = raw & 0x7FFFu;
+            occ += c;
+            if (label == run_label) run += c;
+            else {
+                if (run) add(run_label, run);
+                run_label = label, run = c;
             }
         }
-        if (run) add(run_label, run);
-    }
-    if (blockIdx.x == 0 && threadIdx.x < n % 8) {
-        const uint32_t raw = grid[nvec * 8 + threadIdx.x];
-        if (raw > VF_VOXEL_FREE) {
-            ++occ;
-            add(raw & 0x7FFFu, 1);
+    };
+    const int lane = threadIdx.x & 31;
+    const size_t span = 32 * kHistBatch;
+    const size_t nwarps = (size_t)gridDim.x * (blockDim.x / 32);
+    for (size_t base = ((size_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32) * span; base < nvec; base += nwarps * span) {
+        uint4 v[kHistBatch];
+#pragma unroll
+        for (int k = 0; k < kHistBatch; ++k) {
+            const size_t i = base + k * 32 + lane;
+            v[k] = i < nvec ? vf_ldg_stream(g4 + i) : make_uint4(0, 0, 0, 0);  // EMPTY counts nowhere
+        }
+#pragma unroll
+        for (int k = 0; k < kHistBatch; ++k) {
+            const uint32_t first = v[k].x & 0xFFFFu;
+            if (v[k].x == first * 0x10001u && v[k].y == v[k].x && v[k].z == v[k].x && v[k].w == v[k].x) {
+                take(first, 8);
+            } else {
+                const uint32_t w[4] = { v[k].x, v[k].y, v[k].z, v[k].w };
+#pragma unroll
+                for (int c = 0; c < 8; ++c) take((w[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu, 1);
+            }
         }
     }
+    if (blockIdx.x == 0 && threadIdx.x < n % 8) take(grid[nvec * 8 + threadIdx.x], 1);
+    if (run) add(run_label, run);
     occ = __reduce_add_sync(kFull, occ);
     if ((threadIdx.x & 31) == 0 && occ) atomicAdd(occupied, (unsigned long long)occ);
     __syncthreads();
@@ -341,9 +355,11 @@ __device__ __forceinline__ void stencil_pair(const uint16_t* s, const Dims& d, i
 }
 
 template <int OP>
-__global__ void __launch_bounds__(256) stencil_fast_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, Dims d, ErodeArgs ea, int uniform_erodes)
+__global__ void __launch_bounds__(256) stencil_fast_kernel(const __grid_constant__ CUtensorMap src_map, uint16_t* __restrict__ dst, Dims d, ErodeArgs ea,
+                                                           int uniform_erodes)
 {
-    __shared__ __align__(16) uint16_t s[FROWS * FRS];
+    __shared__ __align__(128) uint16_t s[FROWS * FRS];
+    __shared__ __align__(8) unsigned long long tma_bar;
     __shared__ uint32_t summ[FROWS * 8];
     __shared__ uint16_t tasks[SX * SYT * 8];
     __shared__ int ntasks;
@@ -351,38 +367,27 @@ __global__ void __launch_bounds__(256) stencil_fast_kernel(const uint16_t* __res
     const int t = threadIdx.x;
     if (t == 0) ntasks = 0;
 
-    // ---- stage: 800 interior chunks (cp.async, 16 B) + 200 halo cells; outside the grid -> kOutside.
-    // Thread t copies chunk t & 7 of staged rows (t >> 3) + 32 k; (x, y) of the row advance incrementally (32 = 3 * HY + 2).
+    // ---- stage: one TMA box of 10 x 10 rows x 80 cells (z = -8 .. 71 of the tile: 160-byte rows keep every 8-cell chunk 16-byte
+    //      aligned and bring the z halo cells -1 and 64 along).  The copy engine fills cells outside the grid with zeros = kOutside,
+    //      so staging costs the CTA one instruction instead of a thousand address computations.
     const int ch = t & 7;
     const int gzc = gz0 + ch * 8;
     {
-        int r = t >> 3, x = r / HY, y = r - x * HY;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (r < FROWS) {
-                const int gx = gx0 + x - 1, gy = gy0 + y - 1;
-                uint16_t* dstp = &s[r * FRS + 8 + ch * 8];
-                if ((unsigned)gx < (unsigned)d.X && (unsigned)gy < (unsigned)d.Y && gzc < d.Z) {
-                    const unsigned sa = (unsigned)__cvta_generic_to_shared(dstp);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + ((size_t)((unsigned)gx * (unsigned)d.Y + gy)) * d.Z + gzc) : "memory");
-                } else {
-                    *reinterpret_cast<uint4*>(dstp) = make_uint4(0u, 0u, 0u, 0u);  // kOutside
-                }
-            }
-            r += 32, x += 3, y += 2;
-            if (y >= HY) y -= HY, ++x;
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&tma_bar);
+        if (t == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)(FROWS * FRS * 2)) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                             (unsigned)__cvta_generic_to_shared(s)),
+                         "l"(reinterpret_cast<unsigned long long>(&src_map)), "r"(bar), "r"(gz0 - 8), "r"(gy0 - 1), "r"(gx0 - 1)
+                         : "memory");
         }
+        __syncthreads();  // the barrier is initialised for everybody
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar) : "memory");
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    if (t < FROWS * 2) {
-        const int row = t >> 1, side = t & 1;
-        const int gx = gx0 + row / HY - 1, gy = gy0 + row % HY - 1, gz = side ? gz0 + SZT : gz0 - 1;
-        uint16_t v = kOutside;
-        if ((unsigned)gx < (unsigned)d.X && (unsigned)gy < (unsigned)d.Y && (unsigned)gz < (unsigned)d.Z) v = src[((size_t)((unsigned)gx * (unsigned)d.Y + gy)) * d.Z + gz];
-        s[row * FRS + (side ? 72 : 7)] = v;
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
 
     // ---- chunk summaries; along the way: does the whole staged region hold one value?
     const unsigned ref = s[f_at(0, 0, 0)];
@@ -447,6 +452,27 @@ __global__ void __launch_bounds__(256) stencil_fast_kernel(const uint16_t* __res
     }
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+vf_status make_grid_map(CUtensorMap* map, const uint16_t* src, const Dims& d)
+{
+    static EncodeTiledFn encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+        return (EncodeTiledFn)fn;
+    }();
+    VF_REQUIRE(encode != nullptr, VF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[3] = { (cuuint64_t)d.Z, (cuuint64_t)d.Y, (cuuint64_t)d.X };
+    const cuuint64_t strides[2] = { (cuuint64_t)d.Z * 2, (cuuint64_t)d.Z * d.Y * 2 };  // bytes; multiples of 16 because Z % 8 == 0
+    const cuuint32_t box[3] = { FRS, HY, HX }, estr[3] = { 1, 1, 1 };
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<uint16_t*>(src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VF_REQUIRE(r == CUDA_SUCCESS, VF_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %dx%dx%d grid", (int)r, d.X, d.Y, d.Z);
+    return VF_OK;
+}
+
 vf_status launch_stencil(vf_grid* g, int op, const uint16_t* src, uint16_t* dst, const ErodeArgs& ea)
 {
     vf_ctx* c = g->ctx;
@@ -461,11 +487,14 @@ vf_status launch_stencil(vf_grid* g, int op, const uint16_t* src, uint16_t* dst,
             const float activation = (float)__builtin_popcount(ea.maskbits) / 27.0f;
             uniform_erodes = activation < ea.activations * ea.thr;
         }
+        // tensor map over the source grid as (Z, Y, X) uint16 with a box of (FRS, HY, HX) cells
+        CUtensorMap map;
+        VF_TRY(make_grid_map(&map, src, d));
         const dim3 grid3(ntz, nty, ntx);
         switch (op) {
-        case OP_DETECT: stencil_fast_kernel<OP_DETECT><<<grid3, 256, 0, c->stream>>>(src, dst, d, ea, 0); break;
-        case OP_ERODE3: stencil_fast_kernel<OP_ERODE3><<<grid3, 256, 0, c->stream>>>(src, dst, d, ea, uniform_erodes); break;
-        default: stencil_fast_kernel<OP_SWEEP><<<grid3, 256, 0, c->stream>>>(src, dst, d, ea, 0); break;
+        case OP_DETECT: stencil_fast_kernel<OP_DETECT><<<grid3, 256, 0, c->stream>>>(map, dst, d, ea, 0); break;
+        case OP_ERODE3: stencil_fast_kernel<OP_ERODE3><<<grid3, 256, 0, c->stream>>>(map, dst, d, ea, uniform_erodes); break;
+        default: stencil_fast_kernel<OP_SWEEP><<<grid3, 256, 0, c->stream>>>(map, dst, d, ea, 0); break;
         }
         VF_LAUNCHED(c);
         return VF_OK;
@@ -600,7 +629,7 @@ extern "C" vf_status vf_histogram(vf_grid* g, uint32_t* counts, uint64_t* occupi
     uint32_t* d_counts = (uint32_t*)((char*)c->small.ptr + (512 << 10));
     unsigned long long* d_occ = (unsigned long long*)(d_counts + VF_HISTOGRAM_BINS);
     VF_TRY(vf_k_zero(c, d_counts, VF_HISTOGRAM_BINS * 4 + 8));
-    const int blocks = (int)std::min((size_t)c->num_sms * 4, (g->n() / 8 + 255) / 256 + 1);
+    const int blocks = (int)std::min((size_t)c->num_sms * 8, (g->n() / 8 + 255) / 256 + 1);
     histogram_kernel<<<blocks, 256, 0, c->stream>>>(g->d, g->n(), d_counts, d_occ);
     VF_LAUNCHED(c);
     VF_CUDA(cudaMemcpyAsync(counts, d_counts, VF_HISTOGRAM_BINS * 4, cudaMemcpyDeviceToHost, c->stream));
