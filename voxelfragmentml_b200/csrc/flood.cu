@@ -181,93 +181,96 @@ __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __re
         if (t < 4) misc[t] = 0;
         __syncthreads();
 
-        // ---- entry pass, warp per z-row, lane = z: repair every violated edge that ends in this tile (sources may sit in the
-        //      halo); lowered cells form the first wavefront (ballot -> one mask word per row)
+        // ---- per-row masks, thread per row (odd row stride: conflict-free): non-wall cells and the entry candidates.
+        //      A tile that was already relaxed in this phase left its own edges repaired, and its cells have not changed since
+        //      (only this tile writes them): new violations can only end in the layer of cells next to the halo.  The first visit
+        //      (seeds or phase-2 sources inside) and slab tiles that contain a neighbour GPU's plane check every cell.
+        const bool full_entry = wl.seen[tile] != wl.epoch || (g.fix_lo && tx == 0) || (g.fix_hi && tx == g.ntx - 1);
         {
-            bool overflow = false;
-            for (int r = warp * 32; r < warp * 32 + 32; ++r) {
-                const int x = r / TY, y = r % TY, z = lane;
-                const uint32_t v = sk[sidx(x, y, z)];
-                // slab mode: halo planes are copies of a neighbour GPU's cells — sources only
-                const bool fixed = (g.fix_lo && gx0 + x == 0) || (g.fix_hi && gx0 + x == g.X - 1);
-                const bool relaxable = v != KEY_WALL && !fixed;
-                bool lowered = false;
-                if (relaxable) {
-                    const uint32_t m = min_neighbour_key<NNEIGH>(sk, x, y, z);
-                    if (m < KEY_LIMIT) {
-                        const uint32_t c = m + KEY_LEVEL;
-                        if (c < v) {
-                            sk[sidx(x, y, z)] = c;
-                            lowered = true;
-                        }
-                    } else if (m < KEY_UNREACHED) {
-                        overflow = true;
-                    }
-                }
-                const unsigned b = __ballot_sync(kFull, lowered), w = __ballot_sync(kFull, relaxable);
-                if (lane == 0) {
-                    act[r] = b;
-                    chg[r] = b;
-                    nw[r] = w;
-                }
+            const int r = t, x = r / TY, y = r % TY;
+            // slab mode: halo planes are copies of a neighbour GPU's cells — sources only
+            const bool fixed = (g.fix_lo && gx0 + x == 0) || (g.fix_hi && gx0 + x == g.X - 1);
+            unsigned w = 0;
+            if (!fixed) {
+                const uint32_t* row = &sk[sidx(x, y, 0)];
+#pragma unroll
+                for (int z = 0; z < TZ; ++z) w |= (row[z] != KEY_WALL ? 1u : 0u) << z;
             }
-            if (overflow) atomicOr(&wl.stats[ST_ERROR], 1u);
+            const bool face = x == 0 || x == TX - 1 || y == 0 || y == TY - 1;
+            nw[r] = w;
+            chg[r] = 0;
+            act[r] = w & ((full_entry || face) ? 0xFFFFFFFFu : 0x80000001u);
         }
         __syncthreads();
 
-        // ---- wavefront steps in shared memory, pull style, no atomics, one barrier per step.  Thread t owns row t % 8 * 32 ... i.e.
-        //      row (lane * 8 + warp): rows are dealt round-robin so that a flat front (16 rows of one x-plane) spreads over all
-        //      warps.  Step: candidates of my row = (wavefront of my row shifted by +-1 in z | wavefronts of the neighbouring
-        //      rows) & not-wall; every candidate cell takes min(neighbour keys) + 1 level; the cells that got lower are the next
-        //      wavefront (ballot).  Keys only decrease and every written value is the key of a real path, so reading a neighbour
-        //      while another warp lowers it is harmless; the fixed point is the same.
+        // ---- relaxation steps in shared memory, pull style, one barrier per step.  Thread t owns row (lane * 8 + warp): rows are
+        //      dealt round-robin so that a flat front spreads over all warps.  Step 0 takes the entry candidates; step k > 0 takes
+        //      the cells next to the cells lowered in step k-1 (wavefront masks shifted by +-1 in z | masks of the neighbouring
+        //      rows) & not-wall.  The candidate CELLS of a warp's 32 rows are then dealt to its lanes 32 at a time (prefix sum of
+        //      the popcounts, owner by binary search, n-th set bit), so a step costs ceil(candidates / 32) neighbourhood
+        //      evaluations per warp whatever the orientation of the front.  Every candidate takes min(neighbour keys) + 1 level;
+        //      the cells that got lower are the next wavefront.  Keys only decrease and every written value is the key of a real
+        //      path, so reading a neighbour while another warp lowers it is harmless; the fixed point is the same.
         {
             const int myrow = lane * 8 + warp, mx = myrow / TY, my = myrow % TY;
             for (int it = 0; it < TX * TY * TZ; ++it) {
                 const uint32_t* cur = act + (it & 1) * kThreads;
                 uint32_t* nxt = act + ((it & 1) ^ 1) * kThreads;
-                unsigned a = cur[myrow];
-                unsigned cand = (a << 1) | (a >> 1);
-                if (NNEIGH == 26) cand |= a;
+                unsigned cand;
+                if (it == 0) {
+                    cand = cur[myrow];
+                } else {
+                    const unsigned a = cur[myrow];
+                    cand = (a << 1) | (a >> 1);
+                    if (NNEIGH == 26) cand |= a;
 #pragma unroll
-                for (int dx = -1; dx <= 1; ++dx)
+                    for (int dx = -1; dx <= 1; ++dx)
 #pragma unroll
-                    for (int dy = -1; dy <= 1; ++dy) {
-                        if ((dx | dy) == 0) continue;
-                        if (NNEIGH == 6 && dx != 0 && dy != 0) continue;
-                        const int nx = mx + dx, ny = my + dy;
-                        if (nx < 0 || nx >= TX || ny < 0 || ny >= TY) continue;
-                        const unsigned an = cur[nx * TY + ny];
-                        cand |= NNEIGH == 26 ? (an | (an << 1) | (an >> 1)) : an;
-                    }
-                cand &= nw[myrow];
+                        for (int dy = -1; dy <= 1; ++dy) {
+                            if ((dx | dy) == 0) continue;
+                            if (NNEIGH == 6 && dx != 0 && dy != 0) continue;
+                            const int nx = mx + dx, ny = my + dy;
+                            if (nx < 0 || nx >= TX || ny < 0 || ny >= TY) continue;
+                            const unsigned an = cur[nx * TY + ny];
+                            cand |= NNEIGH == 26 ? (an | (an << 1) | (an >> 1)) : an;
+                        }
+                    cand &= nw[myrow];
+                }
                 nxt[myrow] = 0;
-                unsigned rows = __ballot_sync(kFull, cand != 0);  // bit l <-> row l * 8 + warp
+                __syncwarp();
+                int incl = __popc(cand);
+#pragma unroll
+                for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                    const int up = __shfl_up_sync(kFull, incl, dlt);
+                    if (lane >= dlt) incl += up;
+                }
+                const int total = __shfl_sync(kFull, incl, 31);
                 bool any = false, overflow = false;
-                while (rows) {
-                    const int l = __ffs(rows) - 1;
-                    rows &= rows - 1;
-                    const unsigned cw = __shfl_sync(kFull, cand, l);
-                    const int r = l * 8 + warp, x = r / TY, y = r % TY, z = lane;
-                    bool lowered = false;
-                    if (cw >> lane & 1u) {
+                for (int base = 0; base < total; base += 32) {
+                    const int j = base + lane;
+                    int owner = 0;  // first lane whose inclusive prefix exceeds j
+#pragma unroll
+                    for (int sft = 16; sft >= 1; sft >>= 1) {
+                        const int v = __shfl_sync(kFull, incl, owner + sft - 1);
+                        if (v <= j) owner += sft;
+                    }
+                    owner = min(owner, 31);
+                    const unsigned cw = __shfl_sync(kFull, cand, owner);
+                    const int before = __shfl_sync(kFull, incl, owner) - __popc(cw);
+                    if (j < total) {
+                        const int z = __fns(cw, 0, j - before + 1);
+                        const int r = owner * 8 + warp, x = r / TY, y = r % TY;
                         const uint32_t m = min_neighbour_key<NNEIGH>(sk, x, y, z);
                         if (m < KEY_LIMIT) {
                             const uint32_t c = m + KEY_LEVEL;
                             if (c < sk[sidx(x, y, z)]) {
                                 sk[sidx(x, y, z)] = c;
-                                lowered = true;
+                                atomicOr(&nxt[r], 1u << z);
+                                atomicOr(&chg[r], 1u << z);
+                                any = true;
                             }
                         } else if (m < KEY_UNREACHED) {
                             overflow = true;
-                        }
-                    }
-                    const unsigned b = __ballot_sync(kFull, lowered);
-                    if (b) {
-                        any = true;
-                        if (lane == 0) {
-                            nxt[r] = b;
-                            chg[r] |= b;
                         }
                     }
                 }
@@ -275,6 +278,7 @@ __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __re
                 if (!__syncthreads_or(any)) break;
             }
         }
+        if (t == 0) wl.seen[tile] = (uint8_t)wl.epoch;
 
         // ---- write back the rows that changed (warp per row: one 128-byte line), wake the neighbours that saw them change
         unsigned nchanged = 0;
@@ -329,9 +333,9 @@ vf_status job_begin(vf_grid* grid, Job& j)
     j.c = c;
     j.g = make_geom(grid->X, grid->Y, grid->Z);
     const size_t nt = (size_t)j.g.ntiles();
-    // layout: stats[8] count[3]+pad | list0 | list1 | stamp | occ
+    // layout: stats[8] count[3]+pad | list0 | list1 | stamp | occ | seen
     const size_t words = 16 + 3 * nt;
-    VF_TRY(vf_scratch_reserve(c, c->tiles, words * 4 + nt + 256));
+    VF_TRY(vf_scratch_reserve(c, c->tiles, words * 4 + 2 * nt + 256));
     uint32_t* base = (uint32_t*)c->tiles.ptr;
     j.wl.stats = base;
     j.wl.count = base + 8;
@@ -339,8 +343,10 @@ vf_status job_begin(vf_grid* grid, Job& j)
     j.wl.list[1] = base + 16 + nt;
     j.wl.stamp = base + 16 + 2 * nt;
     j.wl.occ = (uint8_t*)(base + 16 + 3 * nt);
+    j.wl.seen = j.wl.occ + nt;
+    j.wl.epoch = 1;
     VF_CUDA(cudaMemsetAsync(base, 0, 16 * 4, c->stream));
-    VF_CUDA(cudaMemsetAsync(j.wl.stamp, 0, nt * 4 + nt, c->stream));
+    VF_CUDA(cudaMemsetAsync(j.wl.stamp, 0, nt * 4 + 2 * nt, c->stream));
     j.round = 1;
     j.h_mail = (uint32_t*)((char*)c->pinned + 65536);  // upper half of the mailbox; the lower half carries seeds
     j.blocks_stream = c->num_sms * 8;
@@ -460,6 +466,7 @@ extern "C" vf_status vf_fracture_flood(vf_grid* grid, const uint32_t* seeds, uin
         st.freed_voxels = hs[ST_FREED];
         if (hs[ST_FREED] != 0) {
             // ---- phase 2: re-flood from every labelled cell (FloodFracturer.cpp:135-177, second trip of the loop)
+            j.wl.epoch = 2;  // every labelled cell is a source now: tiles start over with a full entry check
             flood_init_keys_kernel<true><<<j.blocks_stream, 256, 0, c->stream>>>(grid->d, keys, j.g, j.wl.occ, d_order);
             VF_LAUNCHED(c);
             enqueue_tiles_with_free_kernel<<<j.blocks_stream, 256, 0, c->stream>>>(grid->d, j.g, j.wl, j.round);

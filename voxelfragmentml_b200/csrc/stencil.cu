@@ -220,9 +220,21 @@ __global__ void __launch_bounds__(256) histogram_kernel(const uint16_t* __restri
             if (v[k].x == first * 0x10001u && v[k].y == v[k].x && v[k].z == v[k].x && v[k].w == v[k].x) {
                 take(first, 8);
             } else {
-                const uint32_t w[4] = { v[k].x, v[k].y, v[k].z, v[k].w };
-#pragma unroll
-                for (int c = 0; c < 8; ++c) take((w[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu, 1);
+                // runs of equal cells inside the vector (a fragment border: usually two): "differs from its predecessor" on packed
+                // lanes, gathered into a byte whose set bits are the run starts
+                const uint32_t one = 0x00010001u;
+                const uint32_t n0 = __vminu2(v[k].x ^ __byte_perm(v[k].x, 0, 0x1010), one), n1 = __vminu2(v[k].y ^ __byte_perm(v[k].x, v[k].y, 0x5432), one);
+                const uint32_t n2 = __vminu2(v[k].z ^ __byte_perm(v[k].y, v[k].z, 0x5432), one), n3 = __vminu2(v[k].w ^ __byte_perm(v[k].z, v[k].w, 0x5432), one);
+                const uint32_t b = n0 | n1 << 2 | n2 << 4 | n3 << 6;
+                uint32_t starts = ((b | b >> 15) & 0xFFu) | 1u;
+                const unsigned long long lo = (unsigned long long)v[k].y << 32 | v[k].x, hi = (unsigned long long)v[k].w << 32 | v[k].z;
+                while (starts) {
+                    const int i = __ffs(starts) - 1;
+                    starts &= starts - 1;
+                    const int end = starts ? __ffs(starts) - 1 : 8;
+                    const uint32_t raw = (uint32_t)((i < 4 ? lo >> (16 * i) : hi >> (16 * (i - 4))) & 0xFFFFu);
+                    take(raw, (uint32_t)(end - i));
+                }
             }
         }
     }

@@ -42,6 +42,8 @@ struct Worklist {
     uint32_t* stamp;     // [ntiles] round id at which the tile was last enqueued (dedupe)
     uint8_t* occ;        // [ntiles] tile holds at least one non-wall cell
     uint32_t* stats;     // [8]: 0 tile visits, 1 non-empty rounds, 2 error flags, 3 freed voxels, 4 max dist, 5 scratch
+    uint8_t* seen;       // [ntiles] flood: phase id (epoch) of the tile's last relaxation visit
+    uint32_t epoch;      // flood: current phase id (1, or 2 for the re-flood of F3)
 };
 
 #ifdef __CUDACC__
