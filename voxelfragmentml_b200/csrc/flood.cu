@@ -10,13 +10,22 @@
 // (dist << 15 | order), which makes the result independent of the evaluation schedule: tiles can be relaxed in any order,
 // concurrently, on any number of GPUs, and still give bit-identical labels.
 //
+// Schedule: worklist rounds over 16 x 16 x 32 tiles (tiles.cuh).  A round only lowers cells to distance levels below
+// lo + kLevelsPerRound, where lo is the lowest level a candidate was deferred at in the previous round (delta-stepping with
+// unit weights): fronts from different seeds then reach a cell in distance order, so almost every cell is lowered once, instead
+// of being claimed by whichever front arrives first in tile order and corrected later.  Deferred candidates stay marked in a
+// per-tile mask and the tile re-enqueues itself.
+//
 // F3 (extra seeds, words = fragId | prefix << 8): the reference's in-flood prefix merge converges, inside every connected set
 // of equal-fragId cells, to the lowest prefix present; the disjoint step then frees every cell whose prefix is not its
 // fragment's minimum and re-floods from all labelled cells.  Restated: keep, per fragment id, only the component (under the
 // flood neighbourhood, through equal-fragId cells) that contains the fragment's lowest-prefix source; free the rest; re-flood
 // with order(cell) = index of that source.  One such round reaches the reference loop's fixed point (numDisjointVoxels == 0).
+#include <cuda.h>  // CUtensorMap (types only; the encoder comes through cudaGetDriverEntryPoint)
+
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "tiles.cuh"
@@ -29,10 +38,12 @@ constexpr uint32_t KEY_WALL = 0xFFFFFFFFu, KEY_UNREACHED = 0xFFFFFFFEu;
 constexpr int KEY_SHIFT = 15;
 constexpr uint32_t KEY_LEVEL = 1u << KEY_SHIFT;
 constexpr uint32_t KEY_LIMIT = 0xFFFF0000u;  // keys at or above this cannot take another level (dist >= 2^17 - 2)
+constexpr uint32_t kLevelsPerRound = 16;     // width of a round's distance window (one tile edge)
+constexpr uint32_t kNoLevel = 0xFFFFFFFFu;
 
-enum { ST_VISITS = 0, ST_ROUNDS = 1, ST_ERROR = 2, ST_FREED = 3, ST_MAXDIST = 4, ST_CHANGED = 5 };
+enum { ST_VISITS = 0, ST_ROUNDS = 1, ST_ERROR = 2, ST_FREED = 3, ST_MAXDIST = 4, ST_CHANGED = 5, ST_STEPS = 6, ST_MAXSTEPS = 7 };
 
-constexpr size_t kSmemBytes = (size_t)(kCells + 4 * kThreads + 8) * sizeof(uint32_t);
+constexpr size_t kSmemBytes = (size_t)(kCells + 5 * kThreads + 8 + 2) * sizeof(uint32_t);  // tile | 5 row-mask arrays | misc | mbarrier
 
 // ------------------------------------------------------------------------------------------------ key field set-up
 // phase 1: homogenize (FloodFracturer.cpp:99) folded in: EMPTY -> WALL, anything else -> UNREACHED.
@@ -63,6 +74,7 @@ __global__ void __launch_bounds__(256) flood_init_keys_kernel(const uint16_t* __
 __global__ void flood_seed_kernel(uint32_t* __restrict__ keys, TileGeom g, Worklist wl, const ushort4* __restrict__ seeds, int S, uint32_t round)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    wl.lo[round % 3] = 0, wl.lo[(round + 1) % 3] = kNoLevel;  // the first round's window starts at level 0
     for (int s = 0; s < S; ++s) {
         const ushort4 sd = seeds[s];
         keys[((size_t)sd.x * g.Y + sd.y) * g.Z + sd.z] = (uint32_t)s;  // dist 0, order s
@@ -76,6 +88,7 @@ __global__ void flood_seed_kernel(uint32_t* __restrict__ keys, TileGeom g, Workl
 __global__ void flood_seed_order_kernel(uint32_t* __restrict__ keys, TileGeom g, Worklist wl, const ushort4* __restrict__ seeds, int S, uint32_t round)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    wl.lo[round % 3] = 0, wl.lo[(round + 1) % 3] = kNoLevel;
     for (int s = 0; s < S; ++s) {
         const ushort4 sd = seeds[s];
         keys[((size_t)sd.x * g.Y + sd.y) * g.Z + sd.z] = (uint32_t)sd.w;
@@ -89,6 +102,7 @@ __global__ void flood_seed_order_kernel(uint32_t* __restrict__ keys, TileGeom g,
 __global__ void __launch_bounds__(256) enqueue_tiles_with_free_kernel(const uint16_t* __restrict__ grid, TileGeom g, Worklist wl, uint32_t round)
 {
     const size_t n = (size_t)g.X * g.Y * g.Z;
+    if (blockIdx.x == 0 && threadIdx.x == 0) wl.lo[round % 3] = 0, wl.lo[(round + 1) % 3] = kNoLevel;  // every source sits at level 0
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         if (grid[i] != VF_VOXEL_FREE) continue;
         const int z = (int)(i % g.Z);
@@ -135,6 +149,43 @@ __device__ __forceinline__ void load_tile_async(uint32_t* sk, const uint32_t* __
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// The same staging as ONE TMA box load (18 x 18 rows x 40 keys; the box starts ZPAD keys before the tile in z because its first
+// element must sit on a 16-byte boundary, and one row / plane before it in y / x).  The copy engine zero-fills what lies outside
+// the grid, and a zero key would be a seed, so tiles on the grid border patch those cells to WALL.
+__device__ __forceinline__ void load_tile_tma(uint32_t* sk, const CUtensorMap* map, unsigned bar, unsigned& parity, const TileGeom& g, int gx0, int gy0,
+                                              int gz0)
+{
+    const int t = threadIdx.x;
+    if (t == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the previous visit's accesses to the tile come first
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)(kCells * 4)) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                         (unsigned)__cvta_generic_to_shared(sk)),
+                     "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar), "r"(gz0 - ZPAD), "r"(gy0 - 1), "r"(gx0 - 1)
+                     : "memory");
+    }
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+    parity ^= 1u;
+    if (gx0 == 0 || gy0 == 0 || gz0 == 0 || gx0 + TX >= g.X || gy0 + TY >= g.Y || gz0 + TZ >= g.Z) {
+        for (int row = t; row < (TX + 2) * SY; row += kThreads) {
+            const int gx = gx0 + row / SY - 1, gy = gy0 + row % SY - 1;
+            uint32_t* p = &sk[row * SZ];
+            if ((unsigned)gx >= (unsigned)g.X || (unsigned)gy >= (unsigned)g.Y) {
+#pragma unroll
+                for (int k = 0; k < SZ; k += 4) *reinterpret_cast<uint4*>(p + k) = make_uint4(KEY_WALL, KEY_WALL, KEY_WALL, KEY_WALL);
+            } else {
+                if (gz0 == 0) *reinterpret_cast<uint4*>(p) = make_uint4(KEY_WALL, KEY_WALL, KEY_WALL, KEY_WALL);
+                for (int k = max(0, g.Z - gz0 + ZPAD); k < SZ; ++k) p[k] = KEY_WALL;  // staged cell k holds gz = gz0 - ZPAD + k
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ F2: key relaxation round
 template <int NNEIGH>
 __device__ __forceinline__ uint32_t min_neighbour_key(const uint32_t* sk, int x, int y, int z)
@@ -157,49 +208,67 @@ __device__ __forceinline__ uint32_t min_neighbour_key(const uint32_t* sk, int x,
 }
 
 template <int NNEIGH>
-__global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __restrict__ keys, TileGeom g, Worklist wl, uint32_t round)
+__global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __restrict__ keys, const __grid_constant__ CUtensorMap keys_map, int use_tma,
+                                                                  TileGeom g, Worklist wl, uint32_t round)
 {
-    extern __shared__ uint32_t sm[];
+    extern __shared__ __align__(128) uint32_t sm[];
     uint32_t* sk = sm;
     uint32_t* act = sm + kCells;        // [2][kThreads] wavefront bitmasks, one word per z-row
     uint32_t* chg = act + 2 * kThreads;  // [kThreads]    cells whose key was lowered during this visit
     uint32_t* nw = chg + kThreads;       // [kThreads]    cells that are not walls
-    uint32_t* misc = nw + kThreads;      // [3] neighbour-tile mask
+    uint32_t* pnd = nw + kThreads;       // [kThreads]    candidates whose new level lies beyond this round's window
+    uint32_t* misc = pnd + kThreads;     // [0..3] neighbour-tile mask, [4] lowest deferred level
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(misc + 8);  // 8-byte aligned mbarrier for the TMA loads
+    unsigned parity = 0;
+    if (use_tma) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
 
     const uint32_t count = wl.count[round % 3];
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     if (blockIdx.x == 0 && t == 0) {
         wl.count[(round + 2) % 3] = 0;
+        wl.lo[(round + 2) % 3] = kNoLevel;
         if (count) atomicAdd(&wl.stats[ST_ROUNDS], 1u);
     }
+    const uint32_t lo = wl.lo[round % 3];
+    const uint32_t hi = lo >= kNoLevel - kLevelsPerRound ? kNoLevel : lo + kLevelsPerRound;  // levels this round may assign: < hi
     for (uint32_t wi = blockIdx.x; wi < count; wi += gridDim.x) {
         const uint32_t tile = wl.list[round & 1][wi];
         const int tz = tile % g.ntz, ty = (tile / g.ntz) % g.nty, tx = tile / (g.ntz * g.nty);
         const int gx0 = tx * TX, gy0 = ty * TY, gz0 = tz * TZ;
 
-        load_tile_async<NNEIGH>(sk, keys, g, gx0, gy0, gz0, KEY_WALL);
+        if (use_tma) load_tile_tma(sk, &keys_map, bar, parity, g, gx0, gy0, gz0);
+        else load_tile_async<NNEIGH>(sk, keys, g, gx0, gy0, gz0, KEY_WALL);
         if (t < 4) misc[t] = 0;
+        if (t == 4) misc[4] = kNoLevel;
         __syncthreads();
 
-        // ---- per-row masks, thread per row (odd row stride: conflict-free): non-wall cells and the entry candidates.
+        // ---- per-row masks: non-wall cells and the entry candidates.
         //      A tile that was already relaxed in this phase left its own edges repaired, and its cells have not changed since
         //      (only this tile writes them): new violations can only end in the layer of cells next to the halo.  The first visit
         //      (seeds or phase-2 sources inside) and slab tiles that contain a neighbour GPU's plane check every cell.
-        const bool full_entry = wl.seen[tile] != wl.epoch || (g.fix_lo && tx == 0) || (g.fix_hi && tx == g.ntx - 1);
-        {
-            const int r = t, x = r / TY, y = r % TY;
+        const uint32_t sflag = wl.seen[tile];
+        const bool revisit = (sflag & 0x7Fu) == wl.epoch, has_pending = revisit && (sflag & 0x80u);
+        const bool full_entry = !revisit || (g.fix_lo && tx == 0) || (g.fix_hi && tx == g.ntx - 1);
+        for (int r = warp * 32; r < warp * 32 + 32; ++r) {  // warp per row, lane = z: conflict-free whatever the row stride
+            const int x = r / TY, y = r % TY;
             // slab mode: halo planes are copies of a neighbour GPU's cells — sources only
             const bool fixed = (g.fix_lo && gx0 + x == 0) || (g.fix_hi && gx0 + x == g.X - 1);
-            unsigned w = 0;
-            if (!fixed) {
-                const uint32_t* row = &sk[sidx(x, y, 0)];
-#pragma unroll
-                for (int z = 0; z < TZ; ++z) w |= (row[z] != KEY_WALL ? 1u : 0u) << z;
+            const unsigned w = __ballot_sync(kFull, !fixed && sk[sidx(x, y, lane)] != KEY_WALL);
+            if (lane == 0) {
+                const bool face = x == 0 || x == TX - 1 || y == 0 || y == TY - 1;
+                nw[r] = w;
+                chg[r] = 0;
+                pnd[r] = 0;
+                unsigned entry = (full_entry || face) ? 0xFFFFFFFFu : 0x80000001u;
+                if (has_pending) entry |= wl.pend[(size_t)tile * kThreads + r];  // candidates deferred by the previous visit
+                act[r] = w & entry;
             }
-            const bool face = x == 0 || x == TX - 1 || y == 0 || y == TY - 1;
-            nw[r] = w;
-            chg[r] = 0;
-            act[r] = w & ((full_entry || face) ? 0xFFFFFFFFu : 0x80000001u);
         }
         __syncthreads();
 
@@ -213,6 +282,7 @@ __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __re
         //      path, so reading a neighbour while another warp lowers it is harmless; the fixed point is the same.
         {
             const int myrow = lane * 8 + warp, mx = myrow / TY, my = myrow % TY;
+            uint32_t dmin = kNoLevel;
             for (int it = 0; it < TX * TY * TZ; ++it) {
                 const uint32_t* cur = act + (it & 1) * kThreads;
                 uint32_t* nxt = act + ((it & 1) ^ 1) * kThreads;
@@ -264,10 +334,15 @@ __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __re
                         if (m < KEY_LIMIT) {
                             const uint32_t c = m + KEY_LEVEL;
                             if (c < sk[sidx(x, y, z)]) {
-                                sk[sidx(x, y, z)] = c;
-                                atomicOr(&nxt[r], 1u << z);
-                                atomicOr(&chg[r], 1u << z);
-                                any = true;
+                                if ((c >> KEY_SHIFT) < hi) {
+                                    sk[sidx(x, y, z)] = c;
+                                    atomicOr(&nxt[r], 1u << z);
+                                    atomicOr(&chg[r], 1u << z);
+                                    any = true;
+                                } else {  // beyond this round's window: keep the cell as a candidate for a later round
+                                    atomicOr(&pnd[r], 1u << z);
+                                    dmin = min(dmin, c >> KEY_SHIFT);
+                                }
                             }
                         } else if (m < KEY_UNREACHED) {
                             overflow = true;
@@ -275,10 +350,27 @@ __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __re
                     }
                 }
                 if (overflow) atomicOr(&wl.stats[ST_ERROR], 1u);
-                if (!__syncthreads_or(any)) break;
+                if (!__syncthreads_or(any)) {
+                    if (t == 0) atomicAdd(&wl.stats[ST_STEPS], (uint32_t)it + 1), atomicMax(&wl.stats[ST_MAXSTEPS], (uint32_t)it + 1);
+                    break;
+                }
+            }
+            dmin = __reduce_min_sync(kFull, dmin);
+            if (lane == 0 && dmin != kNoLevel) atomicMin(&misc[4], dmin);
+        }
+        __syncthreads();
+        {
+            // deferred candidates: remember them, come back next round, and tell the next round where its window starts
+            const uint32_t tile_dmin = misc[4];
+            if (tile_dmin != kNoLevel) wl.pend[(size_t)tile * kThreads + t] = pnd[t];
+            if (t == 0) {
+                wl.seen[tile] = (uint8_t)(wl.epoch | (tile_dmin != kNoLevel ? 0x80u : 0u));
+                if (tile_dmin != kNoLevel) {
+                    atomicMin(&wl.lo[(round + 1) % 3], tile_dmin);
+                    enqueue_tile(wl, tile, round + 1);
+                }
             }
         }
-        if (t == 0) wl.seen[tile] = (uint8_t)wl.epoch;
 
         // ---- write back the rows that changed (warp per row: one 128-byte line), wake the neighbours that saw them change
         unsigned nchanged = 0;
@@ -333,9 +425,10 @@ vf_status job_begin(vf_grid* grid, Job& j)
     j.c = c;
     j.g = make_geom(grid->X, grid->Y, grid->Z);
     const size_t nt = (size_t)j.g.ntiles();
-    // layout: stats[8] count[3]+pad | list0 | list1 | stamp | occ | seen
+    // layout: stats[8] count[3] lo[3] pad[2] | list0 | list1 | stamp | occ | seen | (aligned) pend[nt][kThreads]
     const size_t words = 16 + 3 * nt;
-    VF_TRY(vf_scratch_reserve(c, c->tiles, words * 4 + 2 * nt + 256));
+    const size_t pend_off = (words * 4 + 2 * nt + 255) & ~(size_t)255;
+    VF_TRY(vf_scratch_reserve(c, c->tiles, pend_off + nt * kThreads * 4 + 256));
     uint32_t* base = (uint32_t*)c->tiles.ptr;
     j.wl.stats = base;
     j.wl.count = base + 8;
@@ -345,6 +438,8 @@ vf_status job_begin(vf_grid* grid, Job& j)
     j.wl.occ = (uint8_t*)(base + 16 + 3 * nt);
     j.wl.seen = j.wl.occ + nt;
     j.wl.epoch = 1;
+    j.wl.lo = base + 11;
+    j.wl.pend = (uint32_t*)((char*)base + pend_off);
     VF_CUDA(cudaMemsetAsync(base, 0, 16 * 4, c->stream));
     VF_CUDA(cudaMemsetAsync(j.wl.stamp, 0, nt * 4 + 2 * nt, c->stream));
     j.round = 1;
@@ -382,12 +477,35 @@ vf_status read_stats(Job& j, uint32_t out[8])
     return VF_OK;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// tensor map over the key field as (Z, Y, X) uint32 with a box of one staged tile; false when the layout does not qualify
+bool make_keys_map(CUtensorMap* map, const uint32_t* keys, const TileGeom& g)
+{
+    static EncodeTiledFn encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+        return (EncodeTiledFn)fn;
+    }();
+    std::memset(map, 0, sizeof(*map));
+    if (!encode || g.Z % 4 != 0 || ((uintptr_t)keys & 15) != 0) return false;  // global strides must be multiples of 16 bytes
+    const cuuint64_t dims[3] = { (cuuint64_t)g.Z, (cuuint64_t)g.Y, (cuuint64_t)g.X };
+    const cuuint64_t strides[2] = { (cuuint64_t)g.Z * 4, (cuuint64_t)g.Z * g.Y * 4 };
+    const cuuint32_t box[3] = { SZ, SY, TX + 2 }, estr[3] = { 1, 1, 1 };
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint32_t*>(keys), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int NNEIGH>
 vf_status flood_phase(Job& j, uint32_t* keys)
 {
     auto kern = flood_round_kernel<NNEIGH>;
     VF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    return run_rounds(j, [&](uint32_t r) { kern<<<j.blocks_tiles, kThreads, kSmemBytes, j.c->stream>>>(keys, j.g, j.wl, r); });
+    CUtensorMap map;
+    const int use_tma = make_keys_map(&map, keys, j.g) ? 1 : 0;  // otherwise: per-row cp.async staging
+    return run_rounds(j, [&](uint32_t r) { kern<<<j.blocks_tiles, kThreads, kSmemBytes, j.c->stream>>>(keys, map, use_tma, j.g, j.wl, r); });
 }
 
 }  // namespace
@@ -439,6 +557,10 @@ extern "C" vf_status vf_fracture_flood(vf_grid* grid, const uint32_t* seeds, uin
     flood_seed_kernel<<<1, 32, 0, c->stream>>>(keys, j.g, j.wl, d_seeds, (int)nseeds, j.round);
     VF_LAUNCHED(c);
     VF_TRY(nneigh == 6 ? flood_phase<6>(j, keys) : flood_phase<26>(j, keys));
+    if (std::getenv("VF_FLOOD_DEBUG")) {
+        VF_TRY(read_stats(j, hs));
+        std::fprintf(stderr, "[flood] phase 1: rounds %u visits %u steps %u max steps/visit %u\n", hs[ST_ROUNDS], hs[ST_VISITS], hs[ST_STEPS], hs[ST_MAXSTEPS]);
+    }
     const bool need_f3 = id_bits == 8 && prefixes;
     flood_finalize_kernel<<<j.blocks_stream, 256, 0, c->stream>>>(keys, grid->d, n, d_seeds, (id_bits == 8 && !need_f3) ? 0xFFu : 0xFFFFu, j.wl.stats);
     VF_LAUNCHED(c);
@@ -527,6 +649,7 @@ __global__ void __launch_bounds__(256) slab_ingest_kernel(uint32_t* __restrict__
         if (r < halo[i]) {
             halo[i] = r;
             ++c;
+            atomicMin(&wl.lo[round % 3], r >> KEY_SHIFT);  // the next round's window starts at the lowest level that came in
             const int z = (int)(i % g.Z), y = (int)(i / g.Z);
             const uint32_t tile = ((uint32_t)tx * g.nty + y / TY) * g.ntz + z / TZ;
             if (wl.stamp[tile] != round) {

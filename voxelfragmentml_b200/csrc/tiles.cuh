@@ -15,7 +15,8 @@ namespace vft {
 constexpr int TX = 16, TY = 16, TZ = 32;
 constexpr int kThreads = TX * TY;              // one thread per z-row in the thread-per-row phases
 constexpr int SY = TY + 2;                     // rows incl. halo
-constexpr int SZ = TZ + 3;                     // 34 used + 1 pad word: odd row stride => conflict-free thread-per-row access
+constexpr int ZPAD = 4;                        // staged rows start 4 keys before the tile: a TMA box must start on a 16-byte boundary
+constexpr int SZ = TZ + 2 * ZPAD;              // 160-byte rows = the inner extent of the TMA box; z = -1 sits at slot 3, z = TZ at slot 36
 constexpr int kCells = (TX + 2) * SY * SZ;     // shared-memory words per tile
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
@@ -42,14 +43,16 @@ struct Worklist {
     uint32_t* stamp;     // [ntiles] round id at which the tile was last enqueued (dedupe)
     uint8_t* occ;        // [ntiles] tile holds at least one non-wall cell
     uint32_t* stats;     // [8]: 0 tile visits, 1 non-empty rounds, 2 error flags, 3 freed voxels, 4 max dist, 5 scratch
-    uint8_t* seen;       // [ntiles] flood: phase id (epoch) of the tile's last relaxation visit
+    uint8_t* seen;       // [ntiles] flood: phase id (epoch) of the tile's last relaxation visit | 0x80 when candidates were deferred
     uint32_t epoch;      // flood: current phase id (1, or 2 for the re-flood of F3)
+    uint32_t* lo;        // [3] rotating like `count`: lowest distance level among the candidates deferred to the next round
+    uint32_t* pend;      // [ntiles][kThreads] flood: per-row masks of the deferred candidate cells of a tile
 };
 
 #ifdef __CUDACC__
 __device__ __forceinline__ int sidx(int x, int y, int z)  // x,y,z in [-1, T]
 {
-    return ((x + 1) * SY + (y + 1)) * SZ + (z + 1);
+    return ((x + 1) * SY + (y + 1)) * SZ + (z + ZPAD);
 }
 
 __device__ __forceinline__ void enqueue_tile(const Worklist& wl, uint32_t tile, uint32_t round)
