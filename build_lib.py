@@ -27,6 +27,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-ccbin", HOSTCXX, "-Xcompiler", "-fPIC,-O2,-Wall,-ffp-contract=off",
           "-I", INCLUDE, "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 PER_FILE = {"voxelize.cu": ["-fmad=false"]}
+EXTRA = os.environ.get("VF_NVCC_EXTRA", "").split()  # e.g. -DVF_FLOOD_TIMING for the instrumented flood kernel (tools/ only)
 
 
 def sources():
@@ -46,7 +47,7 @@ def _compile(src, verbose):
     path = os.path.join(CSRC, src)
     if not _stale(out, [path] + hdrs):
         return out, ""
-    cmd = [NVCC, *ARCH, *COMMON, *PER_FILE.get(src, []), "-x", "cu", "-c", path, "-o", out]
+    cmd = [NVCC, *ARCH, *COMMON, *PER_FILE.get(src, []), *EXTRA, "-x", "cu", "-c", path, "-o", out]
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{' '.join(cmd)}\n{p.stdout}\n{p.stderr}")

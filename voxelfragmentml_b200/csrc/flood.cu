@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __re
         if (count) atomicAdd(&wl.stats[ST_ROUNDS], 1u);
     }
     const uint32_t lo = wl.lo[round % 3];
-    const uint32_t hi = lo >= kNoLevel - kLevelsPerRound ? kNoLevel : lo + kLevelsPerRound;  // levels this round may assign: < hi
+    const uint32_t hi = lo >= kNoLevel - wl.levels ? kNoLevel : lo + wl.levels;  // levels this round may assign: < hi
     for (uint32_t wi = blockIdx.x; wi < count; wi += gridDim.x) {
         const uint32_t tile = wl.list[round & 1][wi];
         const int tz = tile % g.ntz, ty = (tile / g.ntz) % g.nty, tx = tile / (g.ntz * g.nty);
@@ -439,6 +439,8 @@ vf_status job_begin(vf_grid* grid, Job& j)
     j.wl.seen = j.wl.occ + nt;
     j.wl.epoch = 1;
     j.wl.lo = base + 11;
+    j.wl.levels = kLevelsPerRound;
+    if (const char* e = std::getenv("VF_FLOOD_LEVELS")) j.wl.levels = (uint32_t)std::max(1, std::atoi(e));  // tuning knob for tools/
     j.wl.pend = (uint32_t*)((char*)base + pend_off);
     VF_CUDA(cudaMemsetAsync(base, 0, 16 * 4, c->stream));
     VF_CUDA(cudaMemsetAsync(j.wl.stamp, 0, nt * 4 + 2 * nt, c->stream));

@@ -47,6 +47,7 @@ struct Worklist {
     uint32_t epoch;      // flood: current phase id (1, or 2 for the re-flood of F3)
     uint32_t* lo;        // [3] rotating like `count`: lowest distance level among the candidates deferred to the next round
     uint32_t* pend;      // [ntiles][kThreads] flood: per-row masks of the deferred candidate cells of a tile
+    uint32_t levels;     // flood: width of a round's distance window
 };
 
 #ifdef __CUDACC__
