@@ -226,14 +226,20 @@ __global__ void __launch_bounds__(256) histogram_kernel(const uint16_t* __restri
                 const uint32_t n0 = __vminu2(v[k].x ^ __byte_perm(v[k].x, 0, 0x1010), one), n1 = __vminu2(v[k].y ^ __byte_perm(v[k].x, v[k].y, 0x5432), one);
                 const uint32_t n2 = __vminu2(v[k].z ^ __byte_perm(v[k].y, v[k].z, 0x5432), one), n3 = __vminu2(v[k].w ^ __byte_perm(v[k].z, v[k].w, 0x5432), one);
                 const uint32_t b = n0 | n1 << 2 | n2 << 4 | n3 << 6;
-                uint32_t starts = ((b | b >> 15) & 0xFFu) | 1u;
-                const unsigned long long lo = (unsigned long long)v[k].y << 32 | v[k].x, hi = (unsigned long long)v[k].w << 32 | v[k].z;
-                while (starts) {
-                    const int i = __ffs(starts) - 1;
-                    starts &= starts - 1;
-                    const int end = starts ? __ffs(starts) - 1 : 8;
-                    const uint32_t raw = (uint32_t)((i < 4 ? lo >> (16 * i) : hi >> (16 * (i - 4))) & 0xFFFFu);
-                    take(raw, (uint32_t)(end - i));
+                const uint32_t starts = ((b | b >> 15) & 0xFFu) | 1u;
+                if (__popc(starts) == 2) {  // one label change inside the vector: the common case at a fragment border
+                    const int k8 = __ffs(starts & ~1u) - 1;
+                    take(first, (uint32_t)k8);
+                    take(v[k].w >> 16, (uint32_t)(8 - k8));
+                } else {
+                    const unsigned long long lo = (unsigned long long)v[k].y << 32 | v[k].x, hi = (unsigned long long)v[k].w << 32 | v[k].z;
+                    for (uint32_t st = starts; st;) {
+                        const int i = __ffs(st) - 1;
+                        st &= st - 1;
+                        const int end = st ? __ffs(st) - 1 : 8;
+                        const uint32_t raw = (uint32_t)((i < 4 ? lo >> (16 * i) : hi >> (16 * (i - 4))) & 0xFFFFu);
+                        take(raw, (uint32_t)(end - i));
+                    }
                 }
             }
         }
