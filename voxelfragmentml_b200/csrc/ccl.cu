@@ -44,6 +44,16 @@ __device__ __forceinline__ bool same(uint32_t a, uint32_t b)
     return MODE == MODE_C1 ? a == b : ((a ^ b) & 0xFFu) == 0;
 }
 
+// 26-neighbourhood: the diagonal pair (my cell z, neighbour row's cell z + dz) joins nothing new when a straight pair joins the
+// same two runs: the neighbour's cells z and z + dz are active in one run (then the pair at z does it), or my cells z and z + dz are
+// (then the pair at z + dz does it) — runs carry one label, and the straight pairs of the same two rows are examined by the dz = 0
+// call.  Masks are the unshifted (active, run-start) words of the two rows; cells of other segments never count as continuing.
+__device__ __forceinline__ unsigned diagonal_redundant(unsigned Am, unsigned Sm, unsigned An, unsigned Sn, int dz)
+{
+    if (dz > 0) return (An & (An >> 1) & ~(Sn >> 1)) | ((Am >> 1) & ~(Sm >> 1));
+    return (An & (An << 1) & ~Sn) | ((Am << 1) & ~Sm);
+}
+
 // position of the run start that covers bit z (S has bit 0 set)
 __device__ __forceinline__ int run_start(unsigned S, int z) { return 31 - __clz(S & (0xFFFFFFFFu >> (31 - z))); }
 
@@ -206,16 +216,24 @@ __global__ void __launch_bounds__(256) ccl_tile_kernel(const uint16_t* __restric
         auto against = [&](int nx, int ny, int dz) {
             if (nx < 0 || ny < 0 || ny >= LY) return;  // other tiles: stage 2
             const int rn = nx * LY + ny;
-            unsigned An = sA[rn], Sn = sS[rn];
+            const unsigned An0 = sA[rn], Sn0 = sS[rn];
+            unsigned An = An0, Sn = Sn0;
             if (dz < 0) An <<= 1, Sn <<= 1;   // position z of the shifted row is neighbour cell z-1
             if (dz > 0) An >>= 1, Sn >>= 1;   // ... neighbour cell z+1
             unsigned m = (Sm | Sn) & Am & An;
+            if (dz != 0) m &= ~diagonal_redundant(Am, Sm, An0, Sn0, dz);
             while (m) {
                 const int z = __ffs(m) - 1;
                 m &= m - 1;
                 const int zn = z + dz;
-                if (same<MODE>(lab(r, z), lab(rn, zn)))
-                    unite_local(par, r * LZ + run_start(Sm, z), rn * LZ + run_start(sS[rn], zn));
+                const uint32_t mine = lab(r, z);
+                if (!same<MODE>(mine, lab(rn, zn))) continue;
+                if (nx != x && ny != y) {
+                    // diagonal in (x, y): nothing new when (nx, y, z) or (x, ny, z) carries the same label (see stage 2)
+                    const int r1 = nx * LY + y, r2 = x * LY + ny;
+                    if (((sA[r1] >> z & 1u) && same<MODE>(lab(r1, z), mine)) || ((sA[r2] >> z & 1u) && same<MODE>(lab(r2, z), mine))) continue;
+                }
+                unite_local(par, r * LZ + run_start(Sm, z), rn * LZ + run_start(sS[rn], zn));
             }
         };
         // (b1) rows of one x-plane first.  The warps move in lockstep, so nearly every thread finds both runs still their own
@@ -311,7 +329,7 @@ __global__ void __launch_bounds__(256) ccl_border_kernel(const uint16_t* __restr
         auto against = [&](int nx, int ny, int dz) {
             if (nx < 0 || ny < 0 || ny >= g.Y) return;
             const bool other_tile = (nx / LX != x / LX) || (ny / LY != y / LY);
-            if (!other_tile && dz == 0) return;
+            if (!other_tile && (dz == 0 || !(Am & (dz < 0 ? 1u : 0x80000000u)))) return;  // in-tile pairs: stage 1, except the cell that leaves the segment
             const uint32_t nrow = (uint32_t)nx * g.Y + ny;
             const uint32_t nsg = nrow * g.segs + seg;
             const uint2 cm = masks[nsg];
@@ -325,6 +343,7 @@ __global__ void __launch_bounds__(256) ccl_border_kernel(const uint16_t* __restr
                 An = (An >> 1) | (qm.x << 31), Sn = (Sn >> 1) | 0x80000000u;
             }
             unsigned m = (Sm | Sn) & Am & An;
+            if (dz != 0) m &= ~diagonal_redundant(Am, Sm, cm.x, cm.y, dz);
             if (!other_tile) m &= dz < 0 ? 1u : 0x80000000u;  // same tile row: only the cell that leaves the segment crosses a border
             const uint32_t nbase = nrow * (uint32_t)g.Z + seg * 32;
             while (m) {
@@ -335,9 +354,15 @@ __global__ void __launch_bounds__(256) ccl_border_kernel(const uint16_t* __restr
                 if (!same<MODE>(vi, vn)) continue;
                 // witness one plane back (pair crosses a y border only) or one row back (pair crosses an x border only)
                 bool skip = false;
-                if (NNEIGH == 6) {
-                    if (ny != y && x % LX != 0) skip = witnessed(i, n, vi, vn, YZ);
-                    else if (nx != x && y % LY != 0) skip = witnessed(i, n, vi, vn, g.Z);
+                if (nx == x) {  // crosses a y border only
+                    if (x % LX != 0) skip = witnessed(i, n, vi, vn, YZ);
+                } else if (ny == y) {  // crosses an x border only
+                    if (y % LY != 0) skip = witnessed(i, n, vi, vn, g.Z);
+                } else {
+                    // diagonal in (x, y): nothing new when a cell next to both — (nx, y, z) or (x, ny, z) — carries the same label:
+                    // it is joined to my cell and to the neighbour by pairs that are straight in (x, y)
+                    const uint32_t c1 = grid[((size_t)nx * g.Y + y) * g.Z + seg * 32 + z], c2 = grid[((size_t)x * g.Y + ny) * g.Z + seg * 32 + z];
+                    skip = (active<MODE>(c1) && same<MODE>(c1, vi)) || (active<MODE>(c2) && same<MODE>(c2, vi));
                 }
                 if (skip) continue;
                 // union-find nodes are run starts: translate both cells (P[run start] is its tile-local root: depth-1 entry points)
