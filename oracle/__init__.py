@@ -102,6 +102,8 @@ def _declare(L):
     L.orc_encode_rle.argtypes = [_u16p, _u32p, C.c_void_p, C.c_uint64]
     L.orc_decode_rle.restype = C.c_int
     L.orc_decode_rle.argtypes = [C.c_char_p, C.c_uint64, _u32p, C.c_void_p, C.c_uint64]
+    L.orc_halton.restype = C.c_float
+    L.orc_halton.argtypes = [C.c_uint, C.c_uint]
     L.orc_encode_vox.restype = C.c_uint64
     L.orc_encode_vox.argtypes = [_u16p, _u32p, C.c_int, C.c_void_p, C.c_uint64]
     L.orc_encode_bing_squared.restype = C.c_uint64
@@ -323,6 +325,10 @@ def encode_bing_squared(grid) -> bytes:
     buf = np.empty(need, dtype=np.uint8)
     lib().orc_encode_bing_squared(grid, d, buf.ctypes.data, need)
     return buf.tobytes()
+
+
+def halton(dimension: int, index: int) -> float:
+    return float(lib().orc_halton(dimension, index))
 
 
 def encode_vox(grid, squared: bool) -> bytes:

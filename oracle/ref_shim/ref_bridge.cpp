@@ -63,6 +63,30 @@ int ref_seed_uniform(uint16_t* grid, const uint32_t dims[3], uint32_t n, int loc
     return 0;
 }
 
+// Seeder::uniform with the HALTON generator (Seeder.cpp:18,28 + Utilities/HaltonSampler.h as it is)
+int ref_seed_halton(uint16_t* grid, const uint32_t dims[3], uint32_t n, int location, uint32_t* out)
+{
+    RegularGrid g(grid, uvec3(dims[0], dims[1], dims[2]));
+    try {
+        std::vector<glm::uvec4> s = fracturer::Seeder::uniform(g, n, FractureParameters::HALTON, static_cast<fracturer::Seeder::Location>(location));
+        for (uint32_t i = 0; i < s.size(); ++i) out[4 * i] = s[i].x, out[4 * i + 1] = s[i].y, out[4 * i + 2] = s[i].z, out[4 * i + 3] = s[i].w;
+    } catch (const fracturer::Seeder::SeederSearchError&) {
+        return -1;
+    }
+    return 0;
+}
+
+// Halton_sampler::sample after init_faure, straight from the reference header
+float ref_halton(unsigned dimension, unsigned index)
+{
+    static Halton_sampler sampler = [] {
+        Halton_sampler h;
+        h.init_faure();
+        return h;
+    }();
+    return sampler.sample(dimension, index);
+}
+
 void ref_merge_seeds(const uint32_t* frags, uint32_t nfrags, uint32_t* seeds, uint32_t nseeds, int dfunc)
 {
     std::vector<glm::uvec4> s = to_seeds(seeds, nseeds);

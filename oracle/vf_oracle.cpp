@@ -315,11 +315,58 @@ struct U3Less {
 };
 }  // namespace
 
+/* Halton_sampler::sample for the three dimensions Seeder::uniform uses (HaltonSampler.h:625-632), after init_faure (:572-602):
+ * dimension 0 = base-2 radical inverse written into a float mantissa (:1416-1430); dimensions 1, 2 = radical inverses in base 3 / 5
+ * over 20 / 12 digits with the Faure digit permutation (tables m_perm3 / m_perm5 of :903-906 hold 5 / 3 digits each and are
+ * combined most-significant first, :1432-1446), scaled by float(0x1.fffffcp-1 / base^digits).  The permutation is built by
+ * Faure's recursion (:576-600): identity up to base 3; even b: [2 s(b/2), 2 s(b/2) + 1]; odd b: s(b-1) with the values >= b/2
+ * shifted up and b/2 inserted in the middle. */
+static std::vector<unsigned> faure_permutation(unsigned base)
+{
+    std::vector<unsigned> p(base);
+    if (base <= 3) {
+        for (unsigned i = 0; i < base; ++i) p[i] = i;
+        return p;
+    }
+    const unsigned half = base / 2;
+    if (base % 2 == 0) {
+        const std::vector<unsigned> q = faure_permutation(half);
+        for (unsigned i = 0; i < half; ++i) p[i] = 2 * q[i], p[half + i] = 2 * q[i] + 1;
+    } else {
+        const std::vector<unsigned> q = faure_permutation(base - 1);
+        for (unsigned i = 0; i + 1 < base; ++i) p[i + (i >= half ? 1 : 0)] = q[i] + (q[i] >= half ? 1 : 0);
+        p[half] = half;
+    }
+    return p;
+}
+
+extern "C" float orc_halton(unsigned dimension, unsigned index)
+{
+    if (dimension == 0) {
+        unsigned rev = 0;
+        for (int b = 0; b < 32; ++b) rev |= ((index >> b) & 1u) << (31 - b);
+        const unsigned bits = 0x3f800000u | (rev >> 9);
+        float f;
+        std::memcpy(&f, &bits, 4);
+        return f - 1.f;
+    }
+    const unsigned base = dimension == 1 ? 3u : 5u, digits = dimension == 1 ? 20u : 12u;
+    static const std::vector<unsigned> perm3 = faure_permutation(3), perm5 = faure_permutation(5);
+    const std::vector<unsigned>& perm = dimension == 1 ? perm3 : perm5;
+    unsigned numerator = 0; /* digit-reversed, permuted; < base^digits < 2^32 */
+    for (unsigned d = 0; d < digits; ++d) {
+        numerator = numerator * base + perm[index % base];
+        index /= base;
+    }
+    const float scale = dimension == 1 ? float(0x1.fffffcp-1 / 3486784401u) : float(0x1.fffffcp-1 / 244140625u);
+    return numerator * scale;
+}
+
 extern "C" int orc_seed_uniform(orc_rng* rng, const uint16_t* grid, const uint32_t dims[3], uint32_t n, int random_mode,
                                 int location, uint32_t* out, uint32_t* attempts_out)
 {
     /* Seeder.cpp:154-208 */
-    if (random_mode != ORC_STD_UNIFORM) return ORC_ERR_UNSUPPORTED; /* HALTON / BOOST_NORMAL: parity unpinned, SURVEY §8a S3 */
+    if (random_mode != ORC_STD_UNIFORM && random_mode != ORC_HALTON) return ORC_ERR_UNSUPPORTED; /* BOOST_NORMAL: parity unpinned, SURVEY §8a S3 */
     std::set<U3, U3Less> seeds;
     const int nd[3] = { (int)dims[0] - 2, (int)dims[1] - 2, (int)dims[2] - 2 }; /* :165 numDivs - 2 */
     const uint32_t MAX_TRIES = 1000000;                                         /* Seeder.h:48 */
@@ -330,9 +377,16 @@ extern "C" int orc_seed_uniform(orc_rng* rng, const uint16_t* grid, const uint32
             return ORC_ERR_SEEDER_EXHAUSTED; /* :173-174 SeederSearchError */
         }
         /* :177-179 — three draws per attempt, consumed even when rejected */
-        const int x = orc_rng_uniform_int(rng, 0, nd[0] + 1);
-        const int y = orc_rng_uniform_int(rng, 0, nd[1] + 1);
-        const int z = orc_rng_uniform_int(rng, 0, nd[2] + 1);
+        int x, y, z;
+        if (random_mode == ORC_HALTON) { /* Seeder.cpp:28: int(sample(coord, attempt) * (max - min) + min), float32; no generator state */
+            x = (int)(orc_halton(0, attempt) * (float)(nd[0] + 1) + 0.0f);
+            y = (int)(orc_halton(1, attempt) * (float)(nd[1] + 1) + 0.0f);
+            z = (int)(orc_halton(2, attempt) * (float)(nd[2] + 1) + 0.0f);
+        } else {
+            x = orc_rng_uniform_int(rng, 0, nd[0] + 1);
+            y = orc_rng_uniform_int(rng, 0, nd[1] + 1);
+            z = orc_rng_uniform_int(rng, 0, nd[2] + 1);
+        }
         const U3 v = { (uint32_t)x, (uint32_t)y, (uint32_t)z };
         const bool occupied = grid[lin(x, y, z, dims)] != ORC_VOXEL_EMPTY; /* RegularGrid.cpp:561-564 */
         const bool boundary = grid_is_boundary(grid, dims, x, y, z);

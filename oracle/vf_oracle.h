@@ -75,6 +75,8 @@ int orc_voxelize_sat(const float* verts, uint32_t nv, const uint32_t* faces, uin
 
 /* ---- S1/S2: seeding — SRC/Fracturer/Seeder.cpp:154-208,115-152; RegularGrid.cpp:543-564 ---- */
 /* out_seeds: n x {x,y,z,label}.  *attempts (optional) receives the number of attempts consumed. */
+/* Halton_sampler::sample(dimension 0..2, index) after init_faure (Utilities/HaltonSampler.h:572-632,1416-1446) */
+float orc_halton(unsigned dimension, unsigned index);
 int orc_seed_uniform(orc_rng*, const uint16_t* grid, const uint32_t dims[3], uint32_t n, int random_mode,
                      int location, uint32_t* out_seeds, uint32_t* attempts);
 /* seeds: nseeds x uvec4, w rewritten in place;  frags: nfrags x uvec4 */

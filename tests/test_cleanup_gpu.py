@@ -145,6 +145,26 @@ def test_seed_uniform_matches_reference_stream(ctx, orc, vessel_grid, location):
     g.close()
 
 
+@pytest.mark.parametrize("location", [0, 1, 2])
+def test_seed_halton_matches_reference_sampler(ctx, orc, vessel_grid, location):
+    """S3: HALTON seeding (Faure-permuted sampler, pinned against the reference header in tests/test_oracle_vs_ref.py): same
+    seeds, same attempt count, and the mt19937 state untouched (the Halton mode draws nothing from it)."""
+    import voxelfragmentml_b200 as vf
+
+    g = _grid(ctx, vessel_grid)
+    for n in (1, 8, 64, 300):
+        ctx.initSeed(7)
+        before = ctx.rng_raw()
+        ctx.initSeed(7)
+        got, att = vf.Seeder.uniform(g, n, randomSeedFunction=vf.RandomUniformType.HALTON, location=location, return_attempts=True)
+        want, watt = orc.seed_uniform(orc.Rng(7), vessel_grid, n, mode=1, location=location)
+        assert np.array_equal(got, want) and att == watt
+        assert ctx.rng_raw() == before
+    with pytest.raises(vf.VoxFragError):
+        vf.Seeder.uniform(g, 4, randomSeedFunction=vf.RandomUniformType.BOOST_NORMAL_DISTRIBUTION)
+    g.close()
+
+
 def test_make_seeds_with_extras_and_exhaustion(ctx, orc, vessel_grid):
     import voxelfragmentml_b200 as vf
 
@@ -160,7 +180,7 @@ def test_make_seeds_with_extras_and_exhaustion(ctx, orc, vessel_grid):
         vf.Seeder.uniform(empty, 1)
     empty.close()
     with pytest.raises(vf.VoxFragError) as e:
-        vf.Seeder.uniform(_grid(ctx, vessel_grid), 2, randomSeedFunction=vf.RandomUniformType.HALTON)
+        vf.Seeder.uniform(_grid(ctx, vessel_grid), 2, randomSeedFunction=vf.RandomUniformType.BOOST_NORMAL_DISTRIBUTION)
     assert e.value.status == 7
 
 

@@ -89,6 +89,33 @@ def test_seeder_uniform(ref, orc, vessel_grid, location):
     assert ref.ref_seed_uniform(empty, _dims(empty), 1, 1, 1, np.zeros((1, 4), np.uint32), None) == -1  # SeederSearchError
 
 
+def test_halton_sampler_and_seeding(ref, orc, vessel_grid):
+    """S3: the Faure-permuted Halton sampler (dimensions 0..2) bit for bit, then Seeder::uniform in HALTON mode on the vessel."""
+    ref.ref_halton.restype = C.c_float
+    ref.ref_halton.argtypes = [C.c_uint, C.c_uint]
+    rs = np.random.RandomState(5)
+    idx = np.concatenate([np.arange(0, 5000), rs.randint(0, 2 ** 31 - 1, 5000), [999999, 1000000, 3 ** 20 - 1, 5 ** 12 - 1, 2 ** 32 - 1]])
+    for d in (0, 1, 2):
+        for i in idx:
+            a, b = ref.ref_halton(d, int(i)), orc.halton(d, int(i))
+            assert np.float32(a).tobytes() == np.float32(b).tobytes(), (d, int(i), a, b)
+    ref.ref_seed_halton.restype = C.c_int
+    ref.ref_seed_halton.argtypes = [_u16, _u32, C.c_uint32, C.c_int, _u32]
+    grids = [vessel_grid, (random_blob_grid((37, 50, 29), 3) * 1).astype(np.uint16)]
+    for g in grids:
+        g = np.ascontiguousarray(g)
+        for location in (0, 1, 2):
+            for n in (1, 8, 40):
+                a = np.zeros((n, 4), np.uint32)
+                rc = ref.ref_seed_halton(g.copy(), _dims(g), n, location, a)
+                try:
+                    b, _ = orc.seed_uniform(orc.Rng(80), g, n, mode=1, location=location)
+                except orc.OracleError:
+                    assert rc == -1
+                    continue
+                assert rc == 0 and np.array_equal(a, b), (g.shape, location, n)
+
+
 def test_merge_seeds(ref, orc):
     rs = np.random.RandomState(9)
     for dfunc in (0, 1, 2):

@@ -49,13 +49,36 @@ struct U3 {
 
 }  // namespace
 
+// Halton_sampler::sample for dimensions 0..2 with Faure permutations (Utilities/HaltonSampler.h:572-632, 1416-1446): the radical
+// inverse of the attempt index in base 2 (bits mirrored into a float mantissa), base 3 (20 digits) and base 5 (12 digits).  Faure's
+// permutation is the identity for base 3 and (0 3 2 1 4) for base 5; the scale constants are the reference's float32 literals.
+static float halton_sample(int dim, uint32_t index)
+{
+    if (dim == 0) {
+        uint32_t mirrored = 0;
+        for (uint32_t v = index, k = 0; k < 32; ++k, v >>= 1) mirrored = (mirrored << 1) | (v & 1u);
+        const uint32_t word = 0x3f800000u | (mirrored >> 9);
+        float f;
+        std::memcpy(&f, &word, sizeof f);
+        return f - 1.f;
+    }
+    static const uint32_t kDigit5[5] = { 0, 3, 2, 1, 4 };
+    uint32_t acc = 0;
+    if (dim == 1) {
+        for (int d = 0; d < 20; ++d, index /= 3) acc = acc * 3 + index % 3;
+        return acc * float(0x1.fffffcp-1 / 3486784401u);
+    }
+    for (int d = 0; d < 12; ++d, index /= 5) acc = acc * 5 + kDigit5[index % 5];
+    return acc * float(0x1.fffffcp-1 / 244140625u);
+}
+
 extern "C" vf_status vf_seed_uniform(vf_grid* g, uint32_t n, int random_mode, int location, uint32_t* out, uint32_t* attempts_out)
 {
     VF_REQUIRE(g != nullptr && out != nullptr, VF_ERR_INVALID_ARGUMENT, "null argument");
     vf_ctx* c = g->ctx;
     VF_TRY(vf_enter(c));
-    VF_REQUIRE(random_mode == VF_STD_UNIFORM, VF_ERR_UNSUPPORTED,
-               "seeding mode %d: only STD_UNIFORM is implemented (HALTON / BOOST_NORMAL are parity-unpinned, SURVEY §8a S3)", random_mode);
+    VF_REQUIRE(random_mode == VF_STD_UNIFORM || random_mode == VF_HALTON, VF_ERR_UNSUPPORTED,
+               "seeding mode %d: STD_UNIFORM and HALTON are implemented (BOOST_NORMAL is parity-unpinned, SURVEY §8a S3)", random_mode);
     VF_REQUIRE(location >= 0 && location <= 2, VF_ERR_INVALID_ARGUMENT, "bad seed location %d", location);
     VF_REQUIRE(g->X >= 2 && g->Y >= 2 && g->Z >= 2, VF_ERR_INVALID_ARGUMENT, "grid too small to seed");
     VF_TRY(vf_scratch_reserve(c, c->small, 1 << 20));
@@ -76,7 +99,14 @@ extern "C" vf_status vf_seed_uniform(vf_grid* g, uint32_t n, int random_mode, in
             return vf_set_error(VF_ERR_SEEDER_EXHAUSTED, "Max. number of tries surpassed (%u)", kMaxTries);  // :173-174
         }
         for (int i = 0; i < batch; ++i) {  // :177-179
-            const int x = c->rng.uniform_int(0, ndx + 1), y = c->rng.uniform_int(0, ndy + 1), z = c->rng.uniform_int(0, ndz + 1);
+            int x, y, z;
+            if (random_mode == VF_HALTON) {  // Seeder.cpp:28: int(sample(coord, attempt) * (max - min) + min) in float32; stateless
+                x = (int)(halton_sample(0, attempt + i) * (float)(ndx + 1) + 0.0f);
+                y = (int)(halton_sample(1, attempt + i) * (float)(ndy + 1) + 0.0f);
+                z = (int)(halton_sample(2, attempt + i) * (float)(ndz + 1) + 0.0f);
+            } else {
+                x = c->rng.uniform_int(0, ndx + 1), y = c->rng.uniform_int(0, ndy + 1), z = c->rng.uniform_int(0, ndz + 1);
+            }
             h_cand[i] = make_ushort4((unsigned short)x, (unsigned short)y, (unsigned short)z, 0);
         }
         VF_CUDA(cudaMemcpyAsync(d_cand, h_cand, batch * sizeof(ushort4), cudaMemcpyHostToDevice, c->stream));
@@ -97,7 +127,7 @@ extern "C" vf_status vf_seed_uniform(vf_grid* g, uint32_t n, int random_mode, in
             }
         }
         attempt += used;
-        if (used != batch) {  // rewind to the reference's RNG position: exactly 3 draws per attempt
+        if (used != batch && random_mode == VF_STD_UNIFORM) {  // rewind to the reference's RNG position: exactly 3 draws per attempt
             c->rng = saved;
             for (int i = 0; i < 3 * used; ++i) c->rng.next();
         }
