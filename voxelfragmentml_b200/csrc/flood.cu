@@ -70,6 +70,48 @@ __global__ void __launch_bounds__(256) flood_init_keys_kernel(const uint16_t* __
     }
 }
 
+// The same, 8 voxels per thread (Z % 8 == 0): one 128-bit label load, two 128-bit key stores, no per-voxel index arithmetic.
+// A warp walks the chunks of one z-row, so (x, y) are decomposed once per row; a chunk never straddles a tile (8 | TZ).
+template <bool PHASE2>
+__global__ void __launch_bounds__(256) flood_init_keys_vec_kernel(const uint16_t* __restrict__ grid, uint32_t* __restrict__ keys, TileGeom g,
+                                                                  uint8_t* __restrict__ occ, const uint16_t* __restrict__ order_of_frag)
+{
+    const int lane = threadIdx.x & 31, cpr = g.Z / 8;  // chunks per row
+    const size_t rows = (size_t)g.X * g.Y, nwarps = (size_t)gridDim.x * (blockDim.x / 32);
+    for (size_t row = (size_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32; row < rows; row += nwarps) {
+        const int y = (int)(row % g.Y), x = (int)(row / g.Y);
+        const uint32_t tile_row = ((uint32_t)(x / TX) * g.nty + y / TY) * g.ntz;
+        for (int ch = lane; ch < cpr; ch += 32) {
+            const size_t i = row * g.Z + (size_t)ch * 8;
+            const uint4 v = vf_ldg_stream(reinterpret_cast<const uint4*>(grid + i));
+            const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+            uint32_t k[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint32_t lab = (w[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu;
+                k[c] = lab == VF_VOXEL_EMPTY ? KEY_WALL : (!PHASE2 || lab == VF_VOXEL_FREE) ? KEY_UNREACHED : (uint32_t)order_of_frag[lab & 0xFFu];
+            }
+            vf_stg_stream(reinterpret_cast<uint4*>(keys + i), make_uint4(k[0], k[1], k[2], k[3]));
+            vf_stg_stream(reinterpret_cast<uint4*>(keys + i + 4), make_uint4(k[4], k[5], k[6], k[7]));
+            if ((v.x | v.y | v.z | v.w) != 0) {
+                const uint32_t tile = tile_row + (uint32_t)(ch * 8) / TZ;
+                if (!occ[tile]) occ[tile] = 1;
+            }
+        }
+    }
+}
+
+template <bool PHASE2>
+vf_status launch_init_keys(vf_ctx* c, const uint16_t* grid, uint32_t* keys, const TileGeom& g, uint8_t* occ, const uint16_t* order, int blocks)
+{
+    if (g.Z % 8 == 0 && (((uintptr_t)grid | (uintptr_t)keys) & 15) == 0)
+        flood_init_keys_vec_kernel<PHASE2><<<blocks, 256, 0, c->stream>>>(grid, keys, g, occ, order);
+    else
+        flood_init_keys_kernel<PHASE2><<<blocks, 256, 0, c->stream>>>(grid, keys, g, occ, order);
+    VF_LAUNCHED(c);
+    return VF_OK;
+}
+
 // FloodFracturer.cpp:102-103,127-132: seeds written in order (a later seed on the same cell overwrites), their cells pushed.
 __global__ void flood_seed_kernel(uint32_t* __restrict__ keys, TileGeom g, Worklist wl, const ushort4* __restrict__ seeds, int S, uint32_t round)
 {
@@ -275,9 +317,9 @@ __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __re
         // ---- relaxation steps in shared memory, pull style, one barrier per step.  Thread t owns row (lane * 8 + warp): rows are
         //      dealt round-robin so that a flat front spreads over all warps.  Step 0 takes the entry candidates; step k > 0 takes
         //      the cells next to the cells lowered in step k-1 (wavefront masks shifted by +-1 in z | masks of the neighbouring
-        //      rows) & not-wall.  The candidate CELLS of a warp's 32 rows are then dealt to its lanes 32 at a time (prefix sum of
-        //      the popcounts, owner by binary search, n-th set bit), so a step costs ceil(candidates / 32) neighbourhood
-        //      evaluations per warp whatever the orientation of the front.  Every candidate takes min(neighbour keys) + 1 level;
+        //      rows) & not-wall.  A warp serves its 32 rows either row by row (lane = z; cheapest when the rows are well filled) or
+        //      by dealing the candidate CELLS to its lanes 32 at a time (prefix sum of the popcounts, owner by binary search, n-th
+        //      set bit; ceil(candidates / 32) neighbourhood evaluations whatever the orientation of the front).  Every candidate takes min(neighbour keys) + 1 level;
         //      the cells that got lower are the next wavefront.  Keys only decrease and every written value is the key of a real
         //      path, so reading a neighbour while another warp lowers it is harmless; the fixed point is the same.
         {
@@ -308,44 +350,71 @@ __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __re
                 }
                 nxt[myrow] = 0;
                 __syncwarp();
-                int incl = __popc(cand);
-#pragma unroll
-                for (int dlt = 1; dlt < 32; dlt <<= 1) {
-                    const int up = __shfl_up_sync(kFull, incl, dlt);
-                    if (lane >= dlt) incl += up;
-                }
-                const int total = __shfl_sync(kFull, incl, 31);
                 bool any = false, overflow = false;
-                for (int base = 0; base < total; base += 32) {
-                    const int j = base + lane;
-                    int owner = 0;  // first lane whose inclusive prefix exceeds j
-#pragma unroll
-                    for (int sft = 16; sft >= 1; sft >>= 1) {
-                        const int v = __shfl_sync(kFull, incl, owner + sft - 1);
-                        if (v <= j) owner += sft;
-                    }
-                    owner = min(owner, 31);
-                    const unsigned cw = __shfl_sync(kFull, cand, owner);
-                    const int before = __shfl_sync(kFull, incl, owner) - __popc(cw);
-                    if (j < total) {
-                        const int z = __fns(cw, 0, j - before + 1);
-                        const int r = owner * 8 + warp, x = r / TY, y = r % TY;
-                        const uint32_t m = min_neighbour_key<NNEIGH>(sk, x, y, z);
-                        if (m < KEY_LIMIT) {
-                            const uint32_t c = m + KEY_LEVEL;
-                            if (c < sk[sidx(x, y, z)]) {
-                                if ((c >> KEY_SHIFT) < hi) {
-                                    sk[sidx(x, y, z)] = c;
-                                    atomicOr(&nxt[r], 1u << z);
-                                    atomicOr(&chg[r], 1u << z);
-                                    any = true;
-                                } else {  // beyond this round's window: keep the cell as a candidate for a later round
-                                    atomicOr(&pnd[r], 1u << z);
-                                    dmin = min(dmin, c >> KEY_SHIFT);
-                                }
+                // relax one candidate cell; its fate: 0 unchanged, 1 lowered, 2 deferred (beyond this round's window)
+                auto relax = [&](int x, int y, int z) -> int {
+                    const uint32_t m = min_neighbour_key<NNEIGH>(sk, x, y, z);
+                    if (m < KEY_LIMIT) {
+                        const uint32_t c = m + KEY_LEVEL;
+                        if (c < sk[sidx(x, y, z)]) {
+                            if ((c >> KEY_SHIFT) < hi) {
+                                sk[sidx(x, y, z)] = c;
+                                return 1;
                             }
-                        } else if (m < KEY_UNREACHED) {
-                            overflow = true;
+                            dmin = min(dmin, c >> KEY_SHIFT);
+                            return 2;
+                        }
+                    } else if (m < KEY_UNREACHED) {
+                        overflow = true;
+                    }
+                    return 0;
+                };
+                const unsigned rows = __ballot_sync(kFull, cand != 0);  // bit l <-> row l * 8 + warp
+                const int total = (int)__reduce_add_sync(kFull, (unsigned)__popc(cand));
+                if (2 * __popc(rows) <= 3 * ((total + 31) / 32) + 1) {
+                    // well-filled rows (a thick front in a solid region): row by row, lane = z, results by ballot
+                    for (unsigned rr = rows; rr; rr &= rr - 1) {
+                        const int l = __ffs(rr) - 1;
+                        const unsigned cw = __shfl_sync(kFull, cand, l);
+                        const int r = l * 8 + warp;
+                        const int f = (cw >> lane & 1u) ? relax(r / TY, r % TY, lane) : 0;
+                        const unsigned low = __ballot_sync(kFull, f == 1), def = __ballot_sync(kFull, f == 2);
+                        if (lane == 0) {
+                            if (low) nxt[r] = low, chg[r] |= low;
+                            if (def) pnd[r] |= def;
+                        }
+                        any = any || low != 0;
+                    }
+                } else {
+                    // sparse rows (thin shells, fronts moving along z): deal the candidate cells to the lanes 32 at a time
+                    int incl = __popc(cand);
+#pragma unroll
+                    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                        const int up = __shfl_up_sync(kFull, incl, dlt);
+                        if (lane >= dlt) incl += up;
+                    }
+                    for (int base = 0; base < total; base += 32) {
+                        const int j = base + lane;
+                        int owner = 0;  // first lane whose inclusive prefix exceeds j
+#pragma unroll
+                        for (int sft = 16; sft >= 1; sft >>= 1) {
+                            const int v = __shfl_sync(kFull, incl, owner + sft - 1);
+                            if (v <= j) owner += sft;
+                        }
+                        owner = min(owner, 31);
+                        const unsigned cw = __shfl_sync(kFull, cand, owner);
+                        const int before = __shfl_sync(kFull, incl, owner) - __popc(cw);
+                        if (j < total) {
+                            const int z = __fns(cw, 0, j - before + 1);
+                            const int r = owner * 8 + warp;
+                            const int f = relax(r / TY, r % TY, z);
+                            if (f == 1) {
+                                atomicOr(&nxt[r], 1u << z);
+                                atomicOr(&chg[r], 1u << z);
+                                any = true;
+                            } else if (f == 2) {
+                                atomicOr(&pnd[r], 1u << z);
+                            }
                         }
                     }
                 }
@@ -393,16 +462,22 @@ __global__ void __launch_bounds__(256) flood_finalize_kernel(const uint32_t* __r
                                                              const ushort4* __restrict__ seeds, uint32_t mask, uint32_t* __restrict__ stats)
 {
     uint32_t maxd = 0;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t k = keys[i];
-        uint16_t v;
-        if (k == KEY_WALL) v = VF_VOXEL_EMPTY;
-        else if (k == KEY_UNREACHED) v = VF_VOXEL_FREE;
-        else {
-            v = (uint16_t)(seeds[k & (KEY_LEVEL - 1)].w & mask);
-            maxd = max(maxd, k >> KEY_SHIFT);
+    auto label_of = [&](uint32_t k) -> uint32_t {
+        if (k == KEY_WALL) return VF_VOXEL_EMPTY;
+        if (k == KEY_UNREACHED) return VF_VOXEL_FREE;
+        maxd = max(maxd, k >> KEY_SHIFT);
+        return seeds[k & (KEY_LEVEL - 1)].w & mask;
+    };
+    if (n % 8 == 0 && (((uintptr_t)grid | (uintptr_t)keys) & 15) == 0) {  // 8 voxels per thread: two 128-bit key loads, one 128-bit label store
+        for (size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x; c < n / 8; c += (size_t)gridDim.x * blockDim.x) {
+            const uint4 a = vf_ldg_stream(reinterpret_cast<const uint4*>(keys + c * 8)), b = vf_ldg_stream(reinterpret_cast<const uint4*>(keys + c * 8 + 4));
+            uint4 o;
+            o.x = label_of(a.x) | label_of(a.y) << 16, o.y = label_of(a.z) | label_of(a.w) << 16;
+            o.z = label_of(b.x) | label_of(b.y) << 16, o.w = label_of(b.z) | label_of(b.w) << 16;
+            vf_stg_stream(reinterpret_cast<uint4*>(grid + c * 8), o);
         }
-        grid[i] = v;
+    } else {
+        for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) grid[i] = (uint16_t)label_of(keys[i]);
     }
     maxd = __reduce_max_sync(kFull, maxd);
     if ((threadIdx.x & 31) == 0 && maxd) atomicMax(&stats[ST_MAXDIST], maxd);
@@ -554,8 +629,7 @@ extern "C" vf_status vf_fracture_flood(vf_grid* grid, const uint32_t* seeds, uin
     }
 
     // ---- phase 1
-    flood_init_keys_kernel<false><<<j.blocks_stream, 256, 0, c->stream>>>(grid->d, keys, j.g, j.wl.occ, nullptr);
-    VF_LAUNCHED(c);
+    VF_TRY(launch_init_keys<false>(c, grid->d, keys, j.g, j.wl.occ, nullptr, j.blocks_stream));
     flood_seed_kernel<<<1, 32, 0, c->stream>>>(keys, j.g, j.wl, d_seeds, (int)nseeds, j.round);
     VF_LAUNCHED(c);
     VF_TRY(nneigh == 6 ? flood_phase<6>(j, keys) : flood_phase<26>(j, keys));
@@ -591,8 +665,7 @@ extern "C" vf_status vf_fracture_flood(vf_grid* grid, const uint32_t* seeds, uin
         if (hs[ST_FREED] != 0) {
             // ---- phase 2: re-flood from every labelled cell (FloodFracturer.cpp:135-177, second trip of the loop)
             j.wl.epoch = 2;  // every labelled cell is a source now: tiles start over with a full entry check
-            flood_init_keys_kernel<true><<<j.blocks_stream, 256, 0, c->stream>>>(grid->d, keys, j.g, j.wl.occ, d_order);
-            VF_LAUNCHED(c);
+            VF_TRY(launch_init_keys<true>(c, grid->d, keys, j.g, j.wl.occ, d_order, j.blocks_stream));
             enqueue_tiles_with_free_kernel<<<j.blocks_stream, 256, 0, c->stream>>>(grid->d, j.g, j.wl, j.round);
             VF_LAUNCHED(c);
             VF_TRY(nneigh == 6 ? flood_phase<6>(j, keys) : flood_phase<26>(j, keys));
@@ -685,8 +758,7 @@ extern "C" vf_status vf_flood_slab_init(vf_grid* slab_grid, uint32_t* keys_dev, 
     s->job.g.fix_hi = has_hi ? 1 : 0;
     VF_TRY(vf_scratch_reserve(c, c->small, 1 << 20));
     s->d_changed = (uint32_t*)((char*)c->small.ptr + (704 << 10));
-    flood_init_keys_kernel<false><<<s->job.blocks_stream, 256, 0, c->stream>>>(slab_grid->d, keys_dev, s->job.g, s->job.wl.occ, nullptr);
-    VF_LAUNCHED(c);
+    VF_TRY(launch_init_keys<false>(c, slab_grid->d, keys_dev, s->job.g, s->job.wl.occ, nullptr, s->job.blocks_stream));
     if (nseeds) {
         // seeds_local: {x (slab-local, halo planes included), y, z, GLOBAL order}.  The order goes into the key, labels are
         // looked up at finalize time from the global seed list.
