@@ -118,6 +118,21 @@ def test_extra_seeds_on_random_blobs(ctx, orc):
             assert gst.freed_voxels == st.freed_voxels
 
 
+@pytest.mark.parametrize("fill", [0.35, 0.5, 0.7])
+def test_extra_seeds_on_unsmoothed_noise_across_tiles(ctx, orc, fill):
+    """Raw occupancy noise on a grid of several tiles per axis: most contacts between fragments' cells are diagonal-only and runs are
+    one or two cells long, which is the worst case for the component step of F3 (diagonal-pair filtering, witness skipping across tile
+    borders under the 26-neighbourhood) and for the flood's dealt-candidate steps."""
+    for trial in range(3):
+        g = random_blob_grid((40, 36, 72), 900 + trial, fill=fill, smooth=0)
+        seeds = orc.make_seeds(orc.Rng(10 + trial), g, 4, 20, merge_dfunc=trial % 3)
+        for dfunc in (2, 1):
+            want, st = orc.flood(g.copy(), seeds, dfunc)
+            got, gst = _run_flood(ctx, g, seeds, dfunc)
+            assert np.array_equal(got, want), (fill, trial, dfunc)
+            assert gst.freed_voxels == st.freed_voxels
+
+
 def test_id_bits_15_many_labels(ctx, orc):
     """cfg5's label space: 256+ seeds need ids beyond 8 bits (SURVEY finding 7) -> whole word is the id, no prefixes."""
     g = random_blob_grid((64, 64, 64), 5, fill=0.6, smooth=1)
