@@ -206,6 +206,7 @@ vf_status vf_export(vf_grid* g, const char* path_without_extension, int export_t
 uint64_t  vf_encode_rle(const uint16_t* grid, const uint32_t dims[3], uint8_t* out, uint64_t cap);          /* exportRLE :672-714 */
 uint64_t  vf_encode_bing_squared(const uint16_t* grid, const uint32_t dims[3], uint8_t* out, uint64_t cap); /* exportRawCompressed squared :638-666 */
 uint64_t  vf_encode_vox(const uint16_t* grid, const uint32_t dims[3], int squared, uint8_t* out, uint64_t cap); /* exportVox :740-798 + VoxWriter.cpp:449-540 */
+uint64_t  vf_encode_qstack(const uint16_t* grid, const uint32_t dims[3], uint8_t* out, uint64_t cap);       /* exportQuadStack :716-725 + SRC/DataStructures/QuadStack.h:91-226, GStack.h:278-319 */
 
 /* ------------------------------------------------------------------ benchmark input synthesis (no reference counterpart) */
 /* analytic solid vessel of revolution sampled at cell centres of an n^3 grid; the grid holds planes x_offset .. x_offset + X - 1 */

@@ -106,6 +106,8 @@ def _declare(L):
     L.orc_halton.argtypes = [C.c_uint, C.c_uint]
     L.orc_encode_vox.restype = C.c_uint64
     L.orc_encode_vox.argtypes = [_u16p, _u32p, C.c_int, C.c_void_p, C.c_uint64]
+    L.orc_encode_qstack.restype = C.c_uint64
+    L.orc_encode_qstack.argtypes = [_u16p, _u32p, C.c_void_p, C.c_uint64]
     L.orc_encode_bing_squared.restype = C.c_uint64
     L.orc_encode_bing_squared.argtypes = [_u16p, _u32p, C.c_void_p, C.c_uint64]
     L.orc_num_threads.restype = C.c_int
@@ -336,6 +338,14 @@ def encode_vox(grid, squared: bool) -> bytes:
     need = lib().orc_encode_vox(grid, d, int(bool(squared)), None, 0)
     buf = np.empty(need, dtype=np.uint8)
     lib().orc_encode_vox(grid, d, int(bool(squared)), buf.ctypes.data, need)
+    return buf.tobytes()
+
+
+def encode_qstack(grid) -> bytes:
+    d = _dims(grid)
+    need = lib().orc_encode_qstack(grid, d, None, 0)
+    buf = np.empty(need, dtype=np.uint8)
+    lib().orc_encode_qstack(grid, d, buf.ctypes.data, need)
     return buf.tobytes()
 
 

@@ -33,6 +33,19 @@ public:
     }
     void swap(CellGrid* src, size_t n) { std::copy(src, src + n, _cells); }
     static unsigned getPositionIndex(int x, int y, int z, const uvec3& numDivs) { return x * numDivs.y * numDivs.z + y * numDivs.z + z; }
+    // RegularGrid.h:370-391 (QuadStack::loadCube reads the grid through this): vectors only ever grow
+    template <typename T>
+    void getData(std::vector<std::vector<std::vector<T>>>& data)
+    {
+        if (data.size() < _numDivs.x) data.resize(_numDivs.x);
+        for (unsigned x = 0; x < _numDivs.x; ++x) {
+            if (data[x].size() < _numDivs.y) data[x].resize(_numDivs.y);
+            for (unsigned y = 0; y < _numDivs.y; ++y) {
+                if (data[x][y].size() < _numDivs.z) data[x][y].resize(_numDivs.z);
+                for (unsigned z = 0; z < _numDivs.z; ++z) data[x][y][z] = static_cast<T>(at(x, y, z));
+            }
+        }
+    }
 
 private:
     CellGrid* _cells;

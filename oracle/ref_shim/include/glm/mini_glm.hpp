@@ -53,6 +53,8 @@ struct mat3 { float m[9]; }; struct mat4 { float m[16]; };
 
 template <class T> T min(T a, T b) { return b < a ? b : a; }
 template <class T> T max(T a, T b) { return a < b ? b : a; }
+template <class T> vec<2, T> min(vec<2, T> a, vec<2, T> b) { return vec<2, T>(min(a.x, b.x), min(a.y, b.y)); }  // component-wise, as glm (GStack::updateBoundaries)
+template <class T> vec<2, T> max(vec<2, T> a, vec<2, T> b) { return vec<2, T>(max(a.x, b.x), max(a.y, b.y)); }
 template <class T> T abs(T a) { return a < 0 ? -a : a; }
 template <class T> T clamp(T v, T lo, T hi) { return min(max(v, lo), hi); }
 template <class T> T dot(const vec<3, T>& a, const vec<3, T>& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }

@@ -1129,6 +1129,194 @@ extern "C" uint64_t orc_encode_vox(const uint16_t* grid, const uint32_t dims[3],
     return w.pos;
 }
 
+/* ---- .qstack: RegularGrid::exportQuadStack (RegularGrid.cpp:716-725) = QuadStack<uint16_t>::loadCube, compress_y, compress_x,
+ * saveCheckpoint (SRC/DataStructures/QuadStack.h:99-140,188-226,247-310,343-433) over GStack<uint16_t> (SRC/DataStructures/GStack.h).
+ * A call-by-call restatement that keeps the structure's observable quirks: interval counts are read through a uint8_t
+ * (GStack.h:50), columns are "identical" when their value sequences agree whatever the run lengths (GStack.h:202-205,104-111),
+ * leaf height fields are cumulative (QuadStack.h:289-303: the matrix is not reset between layers), and mergeStacks erases the
+ * merged interval from the children while its depth-0 loop keeps counting (GStack.h:278-319).  loadCube's function-static
+ * materialMatrix only ever grows (QuadStack.h:125-126, RegularGrid.h:370-391); the restatement is the first export of a process.
+ * Pinned byte-for-byte against the reference's own headers compiled in place (tests/test_oracle_vs_ref.py). */
+namespace {
+struct QsInterval {
+    uint16_t value;
+    std::vector<std::vector<uint16_t>> length;
+};
+struct QsStack {
+    QsStack* children[2][2] = { { nullptr, nullptr }, { nullptr, nullptr } };
+    std::vector<QsInterval> intervals;
+    uint32_t maxp[2] = { 0, 0 }, minp[2] = { UINT_MAX, UINT_MAX }; /* GStack.h:57 */
+    ~QsStack()
+    {
+        for (auto& r : children)
+            for (auto*& c : r) delete c;
+    }
+    uint8_t numIntervals() const { return (uint8_t)intervals.size(); } /* GStack.h:50 */
+    uint8_t numChildren() const
+    {
+        uint8_t n = 0;
+        for (auto& r : children)
+            for (auto* c : r) n += c != nullptr;
+        return n;
+    }
+    bool isWildcard(uint8_t i) const { return intervals[i].value == 0xFFFF; } /* GStack.h:171-175 */
+    void bound(uint32_t x, uint32_t y) /* GStack.h:240-244 */
+    {
+        maxp[0] = std::max(maxp[0], x), maxp[1] = std::max(maxp[1], y);
+        minp[0] = std::min(minp[0], x), minp[1] = std::min(minp[1], y);
+    }
+    bool sameColours(const QsStack& o) const /* operator== + areColorEqual, GStack.h:202-205,104-111 */
+    {
+        if (o.intervals.size() != intervals.size()) return false;
+        for (size_t i = 0; i < o.intervals.size(); ++i)
+            if (o.intervals[i].value != intervals[i].value) return false;
+        return true;
+    }
+};
+
+struct QsTree {
+    uint16_t W, H, D;
+    std::vector<std::vector<QsStack>> cols; /* _gStacks after compress_y */
+    QsStack* root = nullptr;
+    ~QsTree() { delete root; }
+
+    QsStack* create(uint16_t x0, uint16_t x1, uint16_t y0, uint16_t y1, bool leaf = false, QsStack* node = nullptr) /* QuadStack.h:281-310 */
+    {
+        QsStack* g = node ? node : new QsStack;
+        g->bound(x0, y0), g->bound(x1, y1);
+        if (leaf) {
+            const size_t layers = cols[x0][y0].intervals.size();
+            std::vector<std::vector<uint16_t>> m(x1 - x0, std::vector<uint16_t>(y1 - y0, 0));
+            for (size_t l = 0; l < layers; ++l) {
+                for (uint16_t x = x0; x < x1; ++x)
+                    for (uint16_t y = y0; y < y1; ++y) m[x - x0][y - y0] += cols[x][y].intervals[l].length[0][0];
+                g->intervals.push_back({ cols[x0][y0].intervals[l].value, m });
+            }
+        }
+        return g;
+    }
+    void split(uint16_t x0, uint16_t x1, uint16_t y0, uint16_t y1, QsStack* node) /* recursiveSplitQuadtree, QuadStack.h:376-433 */
+    {
+        if ((x1 - x0) <= 1 && (y1 - y0) <= 1) {
+            create(x0, x1, y0, y1, true, node);
+            return;
+        }
+        bool same = true;
+        for (uint16_t x = x0; x < x1 && same; ++x)
+            for (uint16_t y = y0; y < y1 && same; ++y) same &= cols[x0][y0].sameColours(cols[x][y]);
+        if (same) {
+            create(x0, x1, y0, y1, true, node);
+            return;
+        }
+        const size_t sx = x1 - x0, ex = (sx + 1) / 2, sy = y1 - y0, ey = (sy + 1) / 2;
+        node->children[0][0] = create(x0, x0 + ex, y0, y0 + ey);
+        split(x0, x0 + ex, y0, y0 + ey, node->children[0][0]);
+        if (sy > 1) {
+            node->children[0][1] = create(x0, x0 + ex, y0 + ey, y1);
+            split(x0, x0 + ex, y0 + ey, y1, node->children[0][1]);
+        }
+        if (sx > 1) {
+            node->children[1][0] = create(x0 + ex, x1, y0, y0 + ey);
+            split(x0 + ex, x1, y0, y0 + ey, node->children[1][0]);
+        }
+        if (sx > 1 && sy > 1) {
+            node->children[1][1] = create(x0 + ex, x1, y0 + ey, y1);
+            split(x0 + ex, x1, y0 + ey, y1, node->children[1][1]);
+        }
+    }
+    static bool merge(QsStack* rootn, std::vector<QsStack*>& st, std::vector<uint8_t>& it, uint8_t depth) /* GStack.h:278-319 */
+    {
+        if (depth == it.size()) {
+            bool same = true, wildcard = st[0]->isWildcard(it[0]);
+            for (size_t k = 1; k < st.size() && same && !wildcard; ++k) {
+                same &= st[k]->intervals[it[k]].value == st[k - 1]->intervals[it[k - 1]].value;
+                wildcard |= st[k]->isWildcard(it[k]);
+            }
+            if (same && !wildcard) {
+                QsInterval iv; /* mergeInterval, GStack.h:185-196 */
+                iv.value = st[0]->intervals[it[0]].value;
+                iv.length.assign(rootn->maxp[0] - rootn->minp[0], std::vector<uint16_t>(rootn->maxp[1] - rootn->minp[1], 0));
+                for (size_t k = 0; k < st.size(); ++k)
+                    for (unsigned x = st[k]->minp[0]; x < st[k]->maxp[0]; ++x)
+                        for (unsigned y = st[k]->minp[1]; y < st[k]->maxp[1]; ++y)
+                            iv.length[x - rootn->minp[0]][y - rootn->minp[1]] = st[k]->intervals[it[k]].length[x - st[k]->minp[0]][y - st[k]->minp[1]];
+                rootn->intervals.push_back(iv);
+                for (size_t k = 0; k < st.size(); ++k) st[k]->intervals.erase(st[k]->intervals.begin() + it[k]);
+            }
+            return true;
+        }
+        const size_t start = depth > 0 ? it[depth - 1] : 0;
+        for (size_t i = start; i < st[depth]->numIntervals(); ++i) {
+            it[depth] = (uint8_t)i;
+            if (merge(rootn, st, it, depth + 1) && depth > 0) return true;
+        }
+        return false;
+    }
+    void compress(QsStack* node) /* compressQuadStack(root, depth, true), QuadStack.h:260-279 */
+    {
+        if (!node || !node->numChildren()) return;
+        for (auto& r : node->children)
+            for (auto* c : r) compress(c);
+        std::vector<QsStack*> kids;
+        for (auto& r : node->children)
+            for (auto* c : r)
+                if (c) kids.push_back(c);
+        std::vector<uint8_t> it(kids.size(), 0);
+        merge(node, kids, it, 0);
+    }
+    void leaves(QsStack* node, std::vector<QsStack*>& out) /* QuadStack::getLeaves, QuadStack.h:33-44 */
+    {
+        if (!node) return;
+        if (node->numIntervals()) out.push_back(node);
+        for (auto& r : node->children)
+            for (auto* c : r) leaves(c, out);
+    }
+};
+}  // namespace
+
+extern "C" uint64_t orc_encode_qstack(const uint16_t* grid, const uint32_t dims[3], uint8_t* out, uint64_t cap)
+{
+    QsTree t;
+    t.W = (uint16_t)dims[0], t.H = (uint16_t)dims[1], t.D = (uint16_t)dims[2];
+    if (!t.W || !t.H || !t.D) return 0; /* loadCube fails; compress_x would dereference an empty structure */
+    /* loadCube + compress_y: one unit interval per cell (GStack.h:177-183), then addColor per cell (GStack.h:89-101,127-138) */
+    t.cols.assign(t.W, std::vector<QsStack>(t.H));
+    for (uint32_t x = 0; x < t.W; ++x)
+        for (uint32_t y = 0; y < t.H; ++y) {
+            QsStack& c = t.cols[x][y];
+            for (uint32_t z = 0; z < t.D; ++z) {
+                const uint16_t v = grid[lin(x, y, z, dims)];
+                if (c.intervals.empty() || c.intervals.back().value != v)
+                    c.intervals.push_back({ v, { { 1 } } });
+                else
+                    ++c.intervals.back().length[0][0];
+            }
+            c.bound(x, y);
+        }
+    /* compress_x: buildQuadStack + compressQuadStack (QuadStack.h:91-96,228-234) */
+    t.root = t.create(0, t.W, 0, t.H);
+    t.split(0, t.W, 0, t.H, t.root);
+    t.compress(t.root);
+    /* saveCheckpoint, QuadStack.h:188-226 (size_t is 8 bytes on the reference's x64 target) */
+    ByteSink w{ out, cap, 0 };
+    std::vector<QsStack*> nodes;
+    t.leaves(t.root, nodes);
+    const uint64_t tSize = sizeof(uint16_t), numNodes = nodes.size();
+    w.put(&tSize, 8), w.put(&t.W, 2), w.put(&t.H, 2), w.put(&t.D, 2), w.put(&numNodes, 8);
+    for (QsStack* n : nodes) {
+        const uint64_t ni = n->numIntervals();
+        w.put(&ni, 8), w.put(n->maxp, 8), w.put(n->minp, 8);
+        for (uint64_t i = 0; i < ni; ++i) {
+            const QsInterval& iv = n->intervals[i];
+            const uint8_t lw = (uint8_t)iv.length.size(), lh = (uint8_t)iv.length[0].size();
+            w.put(&lw, 1), w.put(&lh, 1), w.put(&iv.value, 2);
+            for (auto& row : iv.length)
+                for (uint16_t l : row) w.put(&l, 2);
+        }
+    }
+    return w.pos;
+}
+
 extern "C" void orc_set_num_threads(int n)
 {
 #ifdef _OPENMP

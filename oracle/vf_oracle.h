@@ -131,6 +131,8 @@ int      orc_decode_rle(const uint8_t* data, uint64_t len, uint32_t dims_out[3],
 uint64_t orc_encode_bing_squared(const uint16_t* grid, const uint32_t dims[3], uint8_t* out, uint64_t cap);
 /* RegularGrid::exportVox (RegularGrid.cpp:740-798) through VoxWriter (Libraries/MagicaVoxel_File_Writer/VoxWriter.cpp:449-540) */
 uint64_t orc_encode_vox(const uint16_t* grid, const uint32_t dims[3], int squared, uint8_t* out, uint64_t cap);
+/* exportQuadStack, RegularGrid.cpp:716-725 over SRC/DataStructures/QuadStack.h + GStack.h */
+uint64_t orc_encode_qstack(const uint16_t* grid, const uint32_t dims[3], uint8_t* out, uint64_t cap);
 
 /* ---- composite used by the CPU baseline (bench.py): cfg3 pipeline on one grid ---- */
 int orc_num_threads(void);

@@ -143,6 +143,32 @@ def test_host_vox_encoder_reproduces_reference_writer_hashes():
             assert hashlib.sha256(buf.tobytes()).hexdigest() == want["sha256"], (name, squared)
 
 
+def test_host_qstack_encoder_reproduces_reference_quadstack_hashes():
+    """vf_encode_qstack is host code: checked on CPU against hashes of the bytes the reference's own QuadStack.h / GStack.h wrote
+    (tests/golden/make_qstack_golden.py; no oracle involved)."""
+    import hashlib
+    import json
+
+    import numpy as np
+    from conftest import GOLDEN
+    from vox_cases import all_qstack_cases
+
+    import voxelfragmentml_b200 as vf
+
+    lib = vf._capi.load()
+    gold = json.load(open(os.path.join(GOLDEN, "qstack_golden.json")))
+    for name, grid in all_qstack_cases():
+        dims = np.asarray(grid.shape, np.uint32)
+        need = lib.vf_encode_qstack(grid.ctypes.data, dims.ctypes.data, None, 0)
+        assert need == gold[name]["bytes"], name
+        small = np.zeros(64, np.uint8)  # a too-small buffer must not be written past its end
+        assert lib.vf_encode_qstack(grid.ctypes.data, dims.ctypes.data, small.ctypes.data, 30) == need
+        assert not small[30:].any()
+        buf = np.zeros(need, np.uint8)
+        lib.vf_encode_qstack(grid.ctypes.data, dims.ctypes.data, buf.ctypes.data, need)
+        assert hashlib.sha256(buf.tobytes()).hexdigest() == gold[name]["sha256"], name
+
+
 def test_merge_seeds_host_matches_oracle(orc):
     import numpy as np
 

@@ -232,6 +232,6 @@ def test_export_rle_and_bing(ctx, orc, labelled_vessel, tmp_path):
     for squared in (False, True):
         g.exportGrid(base, squared, vf.ExportGrid.VOX)
         assert open(base + ".vox", "rb").read() == orc.encode_vox(lab, squared)
-    with pytest.raises(vf.VoxFragError):
-        g.exportGrid(base, True, vf.ExportGrid.QUADSTACK)
+    g.exportGrid(base, True, vf.ExportGrid.QUADSTACK)
+    assert open(base + ".qstack", "rb").read() == orc.encode_qstack(lab)
     g.close()

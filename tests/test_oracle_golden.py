@@ -114,6 +114,42 @@ def test_vox_golden_hashes_from_reference_writer(orc):
             assert len(b) == want["bytes"] and hashlib.sha256(b).hexdigest() == want["sha256"], (name, squared)
 
 
+def test_qstack_golden_hashes_from_reference_quadstack(orc):
+    """sha256 of the bytes the reference's own QuadStack.h / GStack.h wrote (tests/golden/make_qstack_golden.py) == the oracle's."""
+    from vox_cases import all_qstack_cases
+
+    gold = json.load(open(os.path.join(GOLDEN, "qstack_golden.json")))
+    for name, grid in all_qstack_cases():
+        b = orc.encode_qstack(grid)
+        assert len(b) == gold[name]["bytes"] and hashlib.sha256(b).hexdigest() == gold[name]["sha256"], name
+
+
+def test_qstack_decodes_back_to_the_grid_where_the_format_is_lossless(orc):
+    """Structure check independent of the reference headers: walk the file, and for nodes that were written as uniform leaves
+    of a grid whose columns all share one run structure (cumulative height fields) rebuild the columns."""
+    import struct
+
+    g = np.zeros((6, 5, 12), np.uint16)
+    g[:, :, 3:9] = 2
+    g[:, :, 9:] = 3
+    b = orc.encode_qstack(g)
+    tsize, w, h, d, nodes = struct.unpack_from("<QHHHQ", b, 0)
+    assert (tsize, w, h, d, nodes) == (2, 6, 5, 12, 1)
+    pos = 22
+    ni, mxx, mxy, mnx, mny = struct.unpack_from("<QIIII", b, pos)
+    pos += 24
+    assert (ni, mxx, mxy, mnx, mny) == (3, 6, 5, 0, 0)
+    tops = []
+    for _ in range(ni):
+        lw, lh, value = struct.unpack_from("<BBH", b, pos)
+        pos += 4
+        field = np.frombuffer(b, np.uint16, lw * lh, pos).reshape(lw, lh)
+        pos += lw * lh * 2
+        assert (lw, lh) == (6, 5) and (field == field[0, 0]).all()
+        tops.append((value, int(field[0, 0])))
+    assert pos == len(b) and tops == [(0, 3), (2, 9), (3, 12)]
+
+
 def test_rng_recipe_matches_libstdcxx_and_survey_draws(orc):
     assert orc.selfcheck_rng(80, 200000) == 0
     assert orc.selfcheck_rng(12345, 200000) == 0

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from conftest import ROOT, pick_seeds, random_blob_grid
-from vox_cases import vox_cases
+from vox_cases import all_qstack_cases, vox_cases
 
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libvf_ref.so")
 pytestmark = pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref not built (needs /root/reference)")
@@ -173,3 +173,46 @@ def test_vox_bytes_match_reference_writer(ref, orc, tmp_path, name, grid, square
     buf = np.zeros(need, np.uint8)
     assert lib.vf_encode_vox(grid.ctypes.data, d.ctypes.data, int(squared), buf.ctypes.data, need) == need
     assert buf.tobytes() == want
+
+
+QSTACK_SO = os.path.join(ROOT, "oracle", "_ref", "libvf_ref_qstack.so")
+
+
+@pytest.mark.skipif(not os.path.exists(QSTACK_SO), reason="oracle/_ref qstack bridge not built")
+@pytest.mark.parametrize("name,grid", all_qstack_cases(), ids=[c[0] for c in all_qstack_cases()])
+def test_qstack_bytes_match_reference_quadstack(orc, tmp_path, name, grid):
+    """orc_encode_qstack and the product's vf_encode_qstack (host code) == the bytes the reference's QuadStack.h / GStack.h write
+    for exportQuadStack's call sequence."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_qstack_golden import ref_qstack_bytes
+
+    import voxelfragmentml_b200 as vf
+
+    want = ref_qstack_bytes(grid, str(tmp_path))
+    assert orc.encode_qstack(grid) == want
+    lib = vf._capi.load()
+    d = _dims(grid)
+    need = lib.vf_encode_qstack(grid.ctypes.data, d.ctypes.data, None, 0)
+    assert need == len(want)
+    buf = np.zeros(need, np.uint8)
+    assert lib.vf_encode_qstack(grid.ctypes.data, d.ctypes.data, buf.ctypes.data, need) == need
+    assert buf.tobytes() == want
+
+
+@pytest.mark.skipif(not os.path.exists(QSTACK_SO), reason="oracle/_ref qstack bridge not built")
+def test_qstack_random_grids_match_reference_quadstack(orc, tmp_path):
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_qstack_golden import ref_qstack_bytes
+
+    rs = np.random.RandomState(5)
+    for i in range(30):
+        shape = tuple(int(v) for v in rs.randint(1, 18, 3))
+        g = (rs.randint(0, 2 + i % 4, size=shape) * (rs.rand(*shape) < 0.7)).astype(np.uint16)
+        if i % 3 == 0:  # columns that repeat across (x, y): uniform regions and merges
+            g[:] = rs.randint(0, 3, size=(1, 1, shape[2]))
+            g[shape[0] // 2:, :, ::2] = 4
+        assert orc.encode_qstack(g) == ref_qstack_bytes(g, str(tmp_path)), (i, shape)

@@ -37,3 +37,28 @@ def labelled_fixture():
 
 def all_vox_cases():
     return vox_cases() + [("AL_12B_blocks", labelled_fixture())]
+
+
+def qstack_cases():
+    """Grids for the `.qstack` exporter: noise (1x1 leaves), block labellings (uniform regions + bottom-up merges), columns with
+    more than 255 runs (the uint8 interval counts wrap), the 0xFFFF wildcard value, odd dims, one-cell grids."""
+    rs = np.random.RandomState(17)
+    cases = [("one_cell", np.full((1, 1, 1), 5, np.uint16))]
+    cases.append(("noise", (rs.randint(0, 5, size=(13, 9, 11)) * (rs.rand(13, 9, 11) < 0.6)).astype(np.uint16)))
+    x, y, z = np.meshgrid(np.arange(40), np.arange(33), np.arange(20), indexing="ij")
+    cases.append(("blocks", (2 + (x // 8 + 2 * (y // 8) + 3 * (z // 5)) % 7).astype(np.uint16)))
+    g = np.zeros((16, 16, 24), np.uint16)
+    g[:, :, 4:20] = 1
+    g[3:9, 5:12, 8:15] = 4
+    g[10:, :, 10:12] = 0xFFFF  # wildcard value: never merged upwards
+    cases.append(("layers_with_wildcard", g))
+    g = np.tile((np.arange(700) % 2 + 2).astype(np.uint16), (3, 2, 1))
+    g[1, 1, ::5] = 9
+    g[2, 0, :300] = 2
+    cases.append(("more_than_255_runs", np.ascontiguousarray(g)))
+    cases.append(("uniform", np.full((7, 5, 3), 2, np.uint16)))
+    return cases
+
+
+def all_qstack_cases():
+    return qstack_cases() + [("AL_12B_blocks", labelled_fixture())]

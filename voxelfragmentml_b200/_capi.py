@@ -92,6 +92,7 @@ SIGNATURES = {
     "vf_encode_rle": (C.c_uint64, [_vp, _vp, _vp, C.c_uint64]),
     "vf_encode_bing_squared": (C.c_uint64, [_vp, _vp, _vp, C.c_uint64]),
     "vf_encode_vox": (C.c_uint64, [_vp, _vp, C.c_int, _vp, C.c_uint64]),
+    "vf_encode_qstack": (C.c_uint64, [_vp, _vp, _vp, C.c_uint64]),
     "vf_synth_solid_vessel": (C.c_int, [_vp, C.c_int, _u32, C.c_float, C.c_float, C.c_float]),
     "vf_fracture_model": (C.c_int, [_vp, C.POINTER(VfParams), _vp, C.POINTER(_u32), C.POINTER(VfFloodStats)]),
 }

@@ -7,7 +7,7 @@
 // The reference's non-squared `.bing` writes the std::vector object instead of its data (:636, SURVEY finding 10); here it
 // writes the intended dims + raw cells.
 // `.vox` = exportVox (:740-798) over the vendored MagicaVoxel writer (Libraries/MagicaVoxel_File_Writer/VoxWriter.cpp): see
-// vf_encode_vox below.  `.qstack` is not on this round's path (VF_ERR_UNSUPPORTED).
+// vf_encode_vox below.  `.qstack` = exportQuadStack (:716-725) over DataStructures/QuadStack.h + GStack.h: see vf_encode_qstack.
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -212,13 +212,156 @@ extern "C" uint64_t vf_encode_vox(const uint16_t* grid, const uint32_t dims[3], 
     return w.pos;
 }
 
+// ---- .qstack ------------------------------------------------------------------------------------------------------------
+// exportQuadStack (RegularGrid.cpp:716-725): QuadStack<uint16_t>::loadCube -> compress_y -> compress_x -> saveCheckpoint
+// (DataStructures/QuadStack.h:99-140,91-96,188-226) over GStack<uint16_t> (DataStructures/GStack.h).  What the file holds:
+//   z-columns are run-length coded (compress_y); a quadtree over (x, y) stops where every column of a region has the same value
+//   sequence — run lengths are not compared (GStack.h:202-205) — and stores per layer the CUMULATIVE height field of the region
+//   (QuadStack.h:289-303); bottom-up, a parent takes over layer i from all its children when they agree on its value
+//   (GStack::mergeStacks, GStack.h:278-319), erasing it from the children while the layer counter keeps running, so the layer
+//   after a merged one is skipped; every count is read through a uint8_t (GStack.h:50); nodes that keep at least one layer
+//   are written in pre-order.
+// The same bytes are produced here from flat arrays: columns in CSR form, nodes in creation (= pre-) order so that a reverse
+// sweep is a post-order merge, height fields in one pool.  mergeStacks' recursion over per-child iterators collapses to one
+// loop: below depth 0 every iterator starts at the previous one and the first candidate returns, so the only index tuples ever
+// tried are (i, i, ..., i), and a tuple is tried iff every child still has a layer i.
+namespace {
+
+struct QsLayer {
+    uint16_t value;
+    uint64_t field;  // offset of the node-sized height field in the pool
+};
+struct QsNode {
+    uint32_t x0, y0, x1, y1;  // _minPoints / _maxPoints
+    int32_t child[4];         // [0][0], [0][1], [1][0], [1][1]; -1 = none
+    std::vector<QsLayer> layers;
+    uint32_t w() const { return x1 - x0; }
+    uint32_t h() const { return y1 - y0; }
+    uint8_t count() const { return (uint8_t)layers.size(); }
+};
+
+}  // namespace
+
+extern "C" uint64_t vf_encode_qstack(const uint16_t* grid, const uint32_t dims[3], uint8_t* out, uint64_t cap)
+{
+    const uint32_t W = dims[0], H = dims[1], D = dims[2];
+    if (!W || !H || !D || W > 0xFFFF || H > 0xFFFF || D > 0xFFFF) return 0;  // _width/_height/_depth are uint16_t (QuadStack.h:9)
+    // compress_y: runs per column
+    std::vector<uint64_t> first((size_t)W * H + 1, 0);
+    std::vector<uint16_t> rval, rlen;
+    for (size_t c = 0; c < (size_t)W * H; ++c) {
+        const uint16_t* col = grid + c * D;
+        for (uint32_t z = 0; z < D;) {
+            uint32_t e = z + 1;
+            while (e < D && col[e] == col[z]) ++e;
+            rval.push_back(col[z]), rlen.push_back((uint16_t)(e - z));
+            z = e;
+        }
+        first[c + 1] = rval.size();
+    }
+    auto same_values = [&](size_t a, size_t b) {
+        const uint64_t na = first[a + 1] - first[a];
+        return na == first[b + 1] - first[b] && std::memcmp(&rval[first[a]], &rval[first[b]], na * 2) == 0;
+    };
+
+    // buildQuadStack: explicit stack, children pushed in reverse so that nodes are numbered in the reference's recursion order
+    std::vector<QsNode> nodes;
+    std::vector<uint16_t> pool;
+    nodes.push_back({ 0, 0, W, H, { -1, -1, -1, -1 }, {} });
+    struct Pending { int32_t parent, slot; uint32_t x0, y0, x1, y1; };
+    std::vector<Pending> pending;  // regions waiting to become nodes, LIFO
+    auto visit = [&](int32_t id) {
+        const uint32_t x0 = nodes[id].x0, y0 = nodes[id].y0, x1 = nodes[id].x1, y1 = nodes[id].y1;
+        const size_t c0 = (size_t)x0 * H + y0;
+        bool uniform = true;
+        if (x1 - x0 > 1 || y1 - y0 > 1)
+            for (uint32_t x = x0; x < x1 && uniform; ++x)
+                for (uint32_t y = y0; y < y1 && uniform; ++y) uniform = same_values(c0, (size_t)x * H + y);
+        if (uniform) {
+            const uint32_t w = x1 - x0, h = y1 - y0;
+            const uint64_t nl = first[c0 + 1] - first[c0];
+            const uint64_t base = pool.size();
+            pool.resize(base + nl * w * h);
+            for (uint32_t x = 0; x < w; ++x)
+                for (uint32_t y = 0; y < h; ++y) {
+                    const uint64_t r = first[(size_t)(x0 + x) * H + y0 + y];
+                    uint16_t top = 0;
+                    for (uint64_t l = 0; l < nl; ++l) top = (uint16_t)(top + rlen[r + l]), pool[base + l * w * h + (size_t)x * h + y] = top;
+                }
+            for (uint64_t l = 0; l < nl; ++l) nodes[id].layers.push_back({ rval[first[c0] + l], base + l * w * h });
+            return;
+        }
+        const uint32_t mx = x0 + (x1 - x0 + 1) / 2, my = y0 + (y1 - y0 + 1) / 2;
+        const bool sx = x1 - x0 > 1, sy = y1 - y0 > 1;
+        if (sx && sy) pending.push_back({ id, 3, mx, my, x1, y1 });
+        if (sx) pending.push_back({ id, 2, mx, y0, x1, my });
+        if (sy) pending.push_back({ id, 1, x0, my, mx, y1 });
+        pending.push_back({ id, 0, x0, y0, mx, my });
+    };
+    visit(0);
+    while (!pending.empty()) {
+        const Pending p = pending.back();
+        pending.pop_back();
+        const int32_t id = (int32_t)nodes.size();
+        nodes.push_back({ p.x0, p.y0, p.x1, p.y1, { -1, -1, -1, -1 }, {} });
+        nodes[p.parent].child[p.slot] = id;
+        visit(id);
+    }
+
+    // compressQuadStack: descendants have larger numbers than their ancestors
+    for (int32_t id = (int32_t)nodes.size() - 1; id >= 0; --id) {
+        int32_t kids[4], nk = 0;
+        for (int32_t c : nodes[id].child)
+            if (c >= 0) kids[nk++] = c;
+        if (!nk) continue;
+        const uint32_t w = nodes[id].w(), h = nodes[id].h();
+        for (size_t i = 0; i < nodes[kids[0]].count(); ++i) {
+            bool all = true;
+            for (int32_t k = 1; k < nk; ++k) all = all && i < nodes[kids[k]].count();
+            if (!all) continue;
+            const uint16_t v = nodes[kids[0]].layers[i].value;
+            for (int32_t k = 1; k < nk && all; ++k) all = nodes[kids[k]].layers[i].value == v;
+            if (!all || v == 0xFFFF) continue;  // 0xFFFF is the wildcard value (GStack.h:171-175)
+            const uint64_t base = pool.size();
+            pool.resize(base + (uint64_t)w * h, 0);
+            for (int32_t k = 0; k < nk; ++k) {
+                QsNode& c = nodes[kids[k]];
+                const uint16_t* src = &pool[c.layers[i].field];
+                for (uint32_t x = 0; x < c.w(); ++x)
+                    std::memcpy(&pool[base + (uint64_t)(c.x0 - nodes[id].x0 + x) * h + (c.y0 - nodes[id].y0)], src + (size_t)x * c.h(), (size_t)c.h() * 2);
+                c.layers.erase(c.layers.begin() + i);
+            }
+            nodes[id].layers.push_back({ v, base });
+        }
+    }
+
+    // saveCheckpoint (QuadStack.h:188-226); size_t fields are 8 bytes on the reference's x64 target
+    VoxBytes f{ out, cap, 0 };
+    uint64_t kept = 0;
+    for (const QsNode& n : nodes) kept += n.count() != 0;
+    const uint64_t tsize = 2;
+    const uint16_t whd[3] = { (uint16_t)W, (uint16_t)H, (uint16_t)D };
+    f.raw(&tsize, 8), f.raw(whd, 6), f.raw(&kept, 8);
+    for (const QsNode& n : nodes) {
+        const uint64_t nl = n.count();
+        if (!nl) continue;
+        const uint32_t mx[2] = { n.x1, n.y1 }, mn[2] = { n.x0, n.y0 };
+        f.raw(&nl, 8), f.raw(mx, 8), f.raw(mn, 8);
+        const uint8_t lw = (uint8_t)n.w(), lh = (uint8_t)n.h();  // written through a uint8_t (QuadStack.h:212-213)
+        for (uint64_t l = 0; l < nl; ++l) {
+            f.raw(&lw, 1), f.raw(&lh, 1), f.raw(&n.layers[l].value, 2);
+            f.raw(&pool[n.layers[l].field], (uint64_t)n.w() * n.h() * 2);
+        }
+    }
+    return f.pos;
+}
+
 extern "C" vf_status vf_export(vf_grid* g, const char* path, int type, int squared)
 {
     VF_REQUIRE(g && path, VF_ERR_INVALID_ARGUMENT, "null argument");
     VF_TRY(vf_enter(g->ctx));
     static const char* ext[4] = { "rle", "qstack", "vox", "bing" };  // FractureParameters::ExportGrid_STR, FractureParameters.h:36
     VF_REQUIRE(type >= 0 && type < 4, VF_ERR_INVALID_ARGUMENT, "bad export type %d", type);
-    VF_REQUIRE(type != VF_QUADSTACK, VF_ERR_UNSUPPORTED, ".%s export is not implemented in this round", ext[type]);
     std::vector<uint16_t> host(g->n());
     VF_TRY(vf_grid_download(g, host.data()));
     const uint32_t dims[3] = { g->X, g->Y, g->Z };
@@ -226,6 +369,9 @@ extern "C" vf_status vf_export(vf_grid* g, const char* path, int type, int squar
     if (type == VF_RLE) {
         bytes.resize(vf_encode_rle(host.data(), dims, nullptr, 0));
         vf_encode_rle(host.data(), dims, bytes.data(), bytes.size());
+    } else if (type == VF_QUADSTACK) {
+        bytes.resize(vf_encode_qstack(host.data(), dims, nullptr, 0));
+        vf_encode_qstack(host.data(), dims, bytes.data(), bytes.size());
     } else if (type == VF_VOX) {
         bytes.resize(vf_encode_vox(host.data(), dims, squared, nullptr, 0));
         vf_encode_vox(host.data(), dims, squared, bytes.data(), bytes.size());
