@@ -147,6 +147,13 @@ void      vf_dims_rule(const float aabb_min[3], const float aabb_max[3], uint32_
  * triangle passes Intersections3D::intersect(Triangle3D&, AABB&) (SRC/Geometry/3D/Intersections3D.h:204-420) against the
  * voxel box of RegularGrid.cpp:258-259.  verts/faces are HOST pointers: float[nv][3], uint32[nf][3]. */
 vf_status vf_voxelize(vf_grid* g, const float* verts, uint32_t nv, const uint32_t* faces, uint32_t nf);
+/* V1: RegularGrid::fill(Model3D*) as the reference runs it today: Tetravoxelizer (SRC/Graphics/Core/Tetravoxelizer.cpp:198-315,
+ * geometry shader :42-92) — a cell is FREE iff an odd number of (face, centroid) tetrahedra cover (cell centre x, slice plane
+ * y = -1 + slice * 2/Y accumulated in float32, cell centre z) of the grid AABB's NDC space: solid interiors, one model component
+ * per call.  The reference's pixel coverage is decided by the GL rasteriser; the rule used here is stated in csrc/voxelize.cu.
+ * The grid is cleared first (setAABB -> cleanGrid, RegularGrid.cpp:426-441).  *occupied_out (optional) = FREE cells written; the
+ * reference falls back to random surface sampling (fillNaive, :800-816) when that is 0 — that fallback is not on this path. */
+vf_status vf_voxelize_solid(vf_grid* g, const float* verts, uint32_t nv, const uint32_t* faces, uint32_t nf, uint64_t* occupied_out);
 
 /* ------------------------------------------------------------------ S1/S2: seeding (class fracturer::Seeder) */
 /* Seeder::uniform (Seeder.cpp:154-208).  The grid stays on the device: candidate draws are made on the host in the

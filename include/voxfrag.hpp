@@ -149,6 +149,13 @@ public:
     }
     // fill(Model3D*): vertices float[nv][3], faces uint32[nf][3]
     void fill(const float* vertices, uint32_t numVertices, const uint32_t* faces, uint32_t numFaces) { check(vf_voxelize(_h, vertices, numVertices, faces, numFaces)); }
+    // fill(Model3D*) with the Tetravoxelizer occupancy the reference computes today (solid interiors); returns the FREE cell count
+    uint64_t fillSolid(const float* vertices, uint32_t numVertices, const uint32_t* faces, uint32_t numFaces)
+    {
+        uint64_t occupied = 0;
+        check(vf_voxelize_solid(_h, vertices, numVertices, faces, numFaces, &occupied));
+        return occupied;
+    }
     void detectBoundaries(int boundarySize) { check(vf_detect_boundaries(_h, boundarySize)); }
     void erode(FractureParameters::ErosionType type, uint32_t convolutionSize, uint16_t numIterations, float erosionProbability, float erosionThreshold,
                int boundaryMode = 0)

@@ -75,6 +75,8 @@ def _declare(L):
     L.orc_tri_box_intersect.argtypes = [_f32p] * 5
     L.orc_voxelize_sat.restype = C.c_int
     L.orc_voxelize_sat.argtypes = [_f32p, C.c_uint32, _u32p, C.c_uint32, _f32p, _f32p, _u32p, _u16p, C.c_int, C.c_void_p]
+    L.orc_voxelize_solid.restype = C.c_int
+    L.orc_voxelize_solid.argtypes = [_f32p, C.c_uint32, _u32p, C.c_uint32, _f32p, _f32p, _u32p, _u16p, C.c_int]
     L.orc_seed_uniform.restype = C.c_int
     L.orc_seed_uniform.argtypes = [C.c_void_p, _u16p, _u32p, C.c_uint32, C.c_int, C.c_int, _u32p, C.POINTER(C.c_uint32)]
     L.orc_merge_seeds.argtypes = [_u32p, C.c_uint32, _u32p, C.c_uint32, C.c_int]
@@ -195,6 +197,19 @@ def voxelize_sat(verts, faces, aabb_min, aabb_max, dims, want_margin=False):
     if rc:
         raise OracleError(rc, "voxelize_sat")
     return (grid, margin) if want_margin else grid
+
+
+def voxelize_solid(verts, faces, aabb_min, aabb_max, dims):
+    """Tetravoxelizer occupancy (the reference's live RegularGrid::fill), rasteriser rule as fixed in vf_oracle.cpp"""
+    verts = np.ascontiguousarray(verts, np.float32)
+    faces = np.ascontiguousarray(faces, np.uint32)
+    d = _dims(dims)
+    grid = np.zeros(tuple(int(v) for v in d), dtype=np.uint16)
+    rc = lib().orc_voxelize_solid(verts, len(verts), faces, len(faces), np.ascontiguousarray(aabb_min, np.float32),
+                                  np.ascontiguousarray(aabb_max, np.float32), d, grid, 1)
+    if rc:
+        raise OracleError(rc, "voxelize_solid")
+    return grid
 
 
 def seed_uniform(rng: Rng, grid, n, mode=STD_UNIFORM, location=OUTER):

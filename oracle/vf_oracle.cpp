@@ -289,6 +289,132 @@ extern "C" int orc_voxelize_sat(const float* verts, uint32_t nv, const uint32_t*
     return ORC_OK;
 }
 
+/* ---- V1: the live occupancy of RegularGrid::fill(Model3D*) (RegularGrid.cpp:173-212) = Tetravoxelizer (SRC/Graphics/Core/
+ * Tetravoxelizer.{h,cpp}): every face + the vertex-average centroid is a tetrahedron in the grid AABB's NDC space
+ * (initializeModel :198-247, scaleToNDC Tetravoxelizer.h:70-72, 4-element sort :75-81); for slice s the geometry shader (:42-92)
+ * cuts each tetrahedron with the plane y = ySlice (ySlice starts at -1 and is ACCUMULATED in float32, compute :282-299) into one
+ * or two triangles in (x, z), which the GL rasteriser draws into an X x Z R8UI target under glLogicOp(GL_XOR) (:271-272);
+ * the slice is read back as uint8[y][z][x] (:303) and cells holding 1 become VOXEL_FREE (RegularGrid.cpp:186-199).
+ * The FILTER_TETRAHEDRA_BY_Y path only drops tetrahedra that lie wholly below the next slice (its qsort comparator truncates
+ * float differences to int, Tetravoxelizer.h:84-89, but dropping is conservative whatever the order), so it changes nothing.
+ *
+ * PARITY UNPINNED BY CONSTRUCTION: pixel coverage is decided by the GPU's rasteriser (sub-pixel snapping, fill rule on shared
+ * edges, mix() contraction are implementation-defined in OpenGL).  The rule fixed here: shader arithmetic in float32 with
+ * mix(a, b, t) = a*(1-t) + b*t un-fused; window coordinates xw = x*(X/2) + X/2 snapped to 1/256 pixel (round half to even);
+ * a pixel centre is covered iff it is strictly inside, or on an edge whose direction (dx, dy) in the counter-clockwise
+ * orientation has dy > 0 or (dy == 0 and dx < 0); zero-area triangles cover nothing.  Because neighbouring tetrahedra
+ * interpolate a shared edge from the same (lower-y, higher-y) vertex pair, their cross-sections share exact vertices and the
+ * XOR is the parity of the tetrahedra containing the sample point (cell centre in x and z, slice plane in y). */
+namespace {
+struct SolidPt { int64_t x, y; };
+inline int64_t solid_snap(float w)
+{
+    float f = std::nearbyintf(w * 256.0f); /* default rounding mode: to nearest even */
+    if (!(f > -268435456.0f)) f = -268435456.0f; /* also catches NaN */
+    if (f > 268435456.0f) f = 268435456.0f;
+    return (int64_t)f;
+}
+inline int64_t floor_shift8(int64_t v) { return v >> 8; } /* arithmetic shift = floor(v / 256) */
+/* XOR the pixels of one triangle into slice[z * X + x] */
+void solid_raster(uint8_t* slice, int X, int Z, SolidPt a, SolidPt b, SolidPt c)
+{
+    int64_t area2 = (b.x - a.x) * (c.y - a.y) - (b.y - a.y) * (c.x - a.x);
+    if (area2 == 0) return;
+    if (area2 < 0) std::swap(b, c);
+    const SolidPt v[3] = { a, b, c };
+    int64_t dx[3], dy[3];
+    int own[3];
+    for (int e = 0; e < 3; ++e) {
+        dx[e] = v[(e + 1) % 3].x - v[e].x, dy[e] = v[(e + 1) % 3].y - v[e].y;
+        own[e] = (dy[e] > 0 || (dy[e] == 0 && dx[e] < 0)) ? 1 : 0;
+    }
+    const int64_t minx = std::min(a.x, std::min(b.x, c.x)), maxx = std::max(a.x, std::max(b.x, c.x));
+    const int64_t miny = std::min(a.y, std::min(b.y, c.y)), maxy = std::max(a.y, std::max(b.y, c.y));
+    /* pixel i has its centre at 256 i + 128 */
+    const int i0 = (int)std::max<int64_t>(0, floor_shift8(minx - 128 + 255)), i1 = (int)std::min<int64_t>(X - 1, floor_shift8(maxx - 128));
+    const int k0 = (int)std::max<int64_t>(0, floor_shift8(miny - 128 + 255)), k1 = (int)std::min<int64_t>(Z - 1, floor_shift8(maxy - 128));
+    for (int k = k0; k <= k1; ++k)
+        for (int i = i0; i <= i1; ++i) {
+            const int64_t px = 256 * (int64_t)i + 128, py = 256 * (int64_t)k + 128;
+            bool in = true;
+            for (int e = 0; e < 3 && in; ++e) in = dx[e] * (py - v[e].y) - dy[e] * (px - v[e].x) + own[e] > 0;
+            if (in) slice[(size_t)k * X + i] ^= 1;
+        }
+}
+}  // namespace
+
+extern "C" int orc_voxelize_solid(const float* verts, uint32_t nv, const uint32_t* faces, uint32_t nf, const float amin[3],
+                                  const float amax[3], const uint32_t dims[3], uint16_t* grid, int clear)
+{
+    const int X = (int)dims[0], Y = (int)dims[1], Z = (int)dims[2];
+    const uint64_t N = (uint64_t)X * Y * Z;
+    if (clear) std::memset(grid, 0, N * sizeof(uint16_t));
+    if (!nv || !nf) return ORC_OK;
+    /* initializeModel :204-217 */
+    float cen[3] = { 0.0f, 0.0f, 0.0f };
+    for (uint32_t i = 0; i < nv; ++i)
+        for (int q = 0; q < 3; ++q) cen[q] += verts[3 * i + q];
+    for (int q = 0; q < 3; ++q) cen[q] /= (float)nv;
+    float dim[3], ctr[3];
+    for (int q = 0; q < 3; ++q) dim[q] = amax[q] - amin[q], ctr[q] = 0.5f * (amin[q] + amax[q]);
+    auto ndc = [&](const float* v, float* o) { /* Tetravoxelizer.h:70-72: 2.0f * (v - centre) / dim */
+        for (int q = 0; q < 3; ++q) o[q] = (2.0f * (v[q] - ctr[q])) / dim[q];
+    };
+    float cn[3];
+    ndc(cen, cn);
+    struct Tet { float v[4][3]; };
+    std::vector<Tet> tets(nf);
+    for (uint32_t f = 0; f < nf; ++f) {
+        Tet& t = tets[f];
+        for (int k = 0; k < 3; ++k) {
+            if (faces[3 * f + k] >= nv) return ORC_ERR_CAPACITY;
+            ndc(verts + 3 * (size_t)faces[3 * f + k], t.v[k]);
+        }
+        for (int q = 0; q < 3; ++q) t.v[3][q] = cn[q];
+        auto sw = [&](int a, int b) { /* sort4Vec3ByLowerY, Tetravoxelizer.h:75-81 */
+            if (t.v[a][1] > t.v[b][1])
+                for (int q = 0; q < 3; ++q) std::swap(t.v[a][q], t.v[b][q]);
+        };
+        sw(0, 1), sw(2, 3), sw(0, 2), sw(1, 3), sw(1, 2);
+    }
+    /* compute :282-304 */
+    std::vector<float> ys(Y);
+    {
+        float ySlice = -1.0f;
+        const float yStep = 2.0f / (float)Y;
+        for (int s = 0; s < Y; ++s) ys[s] = ySlice, ySlice += yStep;
+    }
+    const float hx = (float)X * 0.5f, hz = (float)Z * 0.5f;
+#pragma omp parallel
+    {
+        std::vector<uint8_t> slice((size_t)X * Z);
+#pragma omp for schedule(dynamic, 1)
+        for (int s = 0; s < Y; ++s) {
+            std::fill(slice.begin(), slice.end(), 0);
+            const float sl = ys[s];
+            for (const Tet& t : tets) {
+                const float *A = t.v[0], *B = t.v[1], *C = t.v[2], *D = t.v[3];
+                if (!(A[1] < sl && sl <= D[1])) continue;
+                auto interp = [&](const float* p, const float* q) { /* INTERP, :46: mix(p, q, (s - p.y) / (q.y - p.y)).xz -> window, snapped */
+                    const float w = (sl - p[1]) / (q[1] - p[1]);
+                    const float x = p[0] * (1.0f - w) + q[0] * w, z = p[2] * (1.0f - w) + q[2] * w;
+                    return SolidPt{ solid_snap(x * hx + hx), solid_snap(z * hz + hz) };
+                };
+                const SolidPt p0 = interp(A, D);
+                const SolidPt v1 = (sl <= B[1]) ? interp(A, B) : interp(B, D);
+                const SolidPt v2 = (sl <= C[1]) ? interp(A, C) : interp(C, D);
+                solid_raster(slice.data(), X, Z, p0, v1, v2);
+                if (B[1] < sl && sl <= C[1]) solid_raster(slice.data(), X, Z, interp(B, C), v2, v1);
+            }
+            /* RegularGrid.cpp:186-199: result[y][z][x] == 1 -> set(x, y, z, VOXEL_FREE) */
+            for (int z = 0; z < Z; ++z)
+                for (int x = 0; x < X; ++x)
+                    if (slice[(size_t)z * X + x] == 1) grid[lin(x, s, z, dims)] = ORC_VOXEL_FREE;
+        }
+    }
+    return ORC_OK;
+}
+
 /* ===================================================================================== S1/S2: seeding */
 
 namespace {

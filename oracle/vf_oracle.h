@@ -72,6 +72,9 @@ int orc_tri_box_intersect(const float p1[3], const float p2[3], const float p3[3
 int orc_voxelize_sat(const float* verts, uint32_t nv, const uint32_t* faces, uint32_t nf,
                      const float aabb_min[3], const float aabb_max[3], const uint32_t dims[3],
                      uint16_t* grid, int clear, float* margin);
+/* V1: Tetravoxelizer occupancy (SRC/Graphics/Core/Tetravoxelizer.cpp:198-315), rasteriser rule fixed in vf_oracle.cpp */
+int orc_voxelize_solid(const float* verts, uint32_t nv, const uint32_t* faces, uint32_t nf, const float amin[3],
+                       const float amax[3], const uint32_t dims[3], uint16_t* grid, int clear);
 
 /* ---- S1/S2: seeding — SRC/Fracturer/Seeder.cpp:154-208,115-152; RegularGrid.cpp:543-564 ---- */
 /* out_seeds: n x {x,y,z,label}.  *attempts (optional) receives the number of attempts consumed. */

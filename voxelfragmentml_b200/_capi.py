@@ -69,6 +69,7 @@ SIGNATURES = {
     "vf_grid_fill": (C.c_int, [_vp, C.c_uint16]),
     "vf_dims_rule": (None, [_vp, _vp, _u32, _vp]),
     "vf_voxelize": (C.c_int, [_vp, _vp, _u32, _vp, _u32]),
+    "vf_voxelize_solid": (C.c_int, [_vp, _vp, _u32, _vp, _u32, _vp]),
     "vf_seed_uniform": (C.c_int, [_vp, _u32, C.c_int, C.c_int, _vp, C.POINTER(_u32)]),
     "vf_merge_seeds": (C.c_int, [_vp, _u32, _vp, _u32, C.c_int]),
     "vf_make_seeds": (C.c_int, [_vp, _u32, _u32, C.c_int, C.c_int, _vp, _u32, C.POINTER(_u32)]),

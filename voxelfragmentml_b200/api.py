@@ -235,6 +235,16 @@ class RegularGrid:
         f = np.ascontiguousarray(faces, np.uint32)
         check(self._lib.vf_voxelize(self._h, ptr(v), len(v), ptr(f), len(f)))
 
+    # ---- V1
+    def fillSolid(self, vertices, faces) -> int:
+        """RegularGrid::fill(Model3D*) as the reference runs it today (Tetravoxelizer, Tetravoxelizer.cpp:198-315): solid
+        occupancy by XOR-ed tetrahedron slices.  Returns the number of FREE cells written."""
+        v = np.ascontiguousarray(vertices, np.float32)
+        f = np.ascontiguousarray(faces, np.uint32)
+        occ = C.c_uint64(0)
+        check(self._lib.vf_voxelize_solid(self._h, ptr(v), len(v), ptr(f), len(f), C.byref(occ)))
+        return int(occ.value)
+
     # ---- C1..C4
     def detectBoundaries(self, boundarySize: int = 1):
         check(self._lib.vf_detect_boundaries(self._h, int(boundarySize)))

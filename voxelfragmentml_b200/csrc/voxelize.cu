@@ -309,3 +309,275 @@ extern "C" vf_status vf_voxelize(vf_grid* grid, const float* verts, uint32_t nv,
     VF_LAUNCHED(c);
     return VF_OK;
 }
+
+// =========================================================================================================================
+// V1: solid occupancy — the LIVE path of RegularGrid::fill(Model3D*) (RegularGrid.cpp:173-212): Tetravoxelizer
+// (SRC/Graphics/Core/Tetravoxelizer.{h,cpp}).  Every face and the vertex-average centroid form a tetrahedron in the grid AABB's
+// NDC space (initializeModel :198-247); for every y-slice the geometry shader (:42-92) cuts it with the plane y = ySlice
+// (accumulated float32, :282-299) into one or two (x, z) triangles that are drawn with glLogicOp(GL_XOR) (:271-272), so a cell
+// ends up FREE iff an odd number of tetrahedra cover (cell centre x, slice plane y, cell centre z).  The reference needs one draw +
+// glReadPixels + glFinish per slice (:288-304) and a host pass over the uint8[y][z][x] result (RegularGrid.cpp:186-199).
+//
+// Pixel coverage in the reference is whatever the GL rasteriser of the machine decides (implementation-defined snapping and
+// fill rule): parity is unpinned by construction.  The rule implemented here — identical in the CPU checker — is: shader
+// arithmetic in float32 with mix(a,b,t) = a*(1-t) + b*t (this file is built with -fmad=false), window coordinates snapped to
+// 1/256 pixel (round half even), a centre on an edge belongs to the triangle iff the edge's counter-clockwise direction has
+// dy > 0 or (dy == 0 and dx < 0), 64-bit integer edge functions.
+//
+// B200 design: one CTA per (slice, band of x-rows) keeps the band's bit-plane in shared memory.  Its warps scan the (min y, max y)
+// pairs of all tetrahedra (8 B each, L2 resident), each lane cuts its own hit into triangles, tiny cross-sections (the common
+// case: a face is a few cells wide) are XOR-ed by their own lane, larger ones are broadcast and rastered by the whole warp.
+// The plane is then expanded to uint16 labels and written once, coalesced — no global atomics, no bit grid in HBM, no memset:
+// 2 B/voxel written + 56 B/tetrahedron read per CTA from L2.
+namespace {
+
+struct SolidGeom {
+    int X, Y, Z;
+    int zw;       // 32-bit words per (x, slice) row of the bit plane
+    int rows;     // x-rows per band
+    float ctr[3], dim[3], cen[3];  // AABB centre and size, centroid in NDC
+    float hx, hz; // X/2, Z/2
+};
+
+__global__ void __launch_bounds__(256) tetra_setup_kernel(const float* __restrict__ verts, const uint32_t* __restrict__ faces, uint32_t nf, SolidGeom g,
+                                                          float4* __restrict__ tets, float2* __restrict__ yrange)
+{
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    float v[4][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float* p = verts + 3 * (size_t)faces[3 * f + k];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) v[k][q] = (2.0f * (p[q] - g.ctr[q])) / g.dim[q];  // scaleToNDC, Tetravoxelizer.h:70-72
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) v[3][q] = g.cen[q];
+#define VF_CSWAP(a, b)                                    \
+    if (v[a][1] > v[b][1]) {                              \
+        _Pragma("unroll") for (int q = 0; q < 3; ++q) {   \
+            const float t_ = v[a][q];                     \
+            v[a][q] = v[b][q], v[b][q] = t_;              \
+        }                                                 \
+    }
+    VF_CSWAP(0, 1) VF_CSWAP(2, 3) VF_CSWAP(0, 2) VF_CSWAP(1, 3) VF_CSWAP(1, 2)  // sort4Vec3ByLowerY, Tetravoxelizer.h:75-81
+#undef VF_CSWAP
+    tets[3 * (size_t)f + 0] = make_float4(v[0][0], v[0][1], v[0][2], v[1][0]);
+    tets[3 * (size_t)f + 1] = make_float4(v[1][1], v[1][2], v[2][0], v[2][1]);
+    tets[3 * (size_t)f + 2] = make_float4(v[2][2], v[3][0], v[3][1], v[3][2]);
+    yrange[f] = make_float2(v[0][1], v[3][1]);
+}
+
+__device__ __forceinline__ int solid_snap(float w)
+{
+    float f = rintf(w * 256.0f);
+    if (!(f > -268435456.0f)) f = -268435456.0f;
+    if (f > 268435456.0f) f = 268435456.0f;
+    return (int)f;
+}
+
+// a cross-section triangle in 24.8 fixed-point window coordinates, made counter-clockwise; n = pixels in its clipped box
+struct SolidTri {
+    int x0, y0, x1, y1, x2, y2;
+    int i0, k0, bw, n;  // first row (x), first column (z), box width in z, box pixels (0 = nothing to draw)
+};
+
+__device__ __forceinline__ void solid_tri_finish(SolidTri& t, const SolidGeom& g, int row_lo, int row_hi)
+{
+    const long long area2 = (long long)(t.x1 - t.x0) * (t.y2 - t.y0) - (long long)(t.y1 - t.y0) * (t.x2 - t.x0);
+    t.n = 0;
+    if (area2 == 0) return;
+    if (area2 < 0) {
+        const int tx = t.x1, ty = t.y1;
+        t.x1 = t.x2, t.y1 = t.y2, t.x2 = tx, t.y2 = ty;
+    }
+    const int minx = min(t.x0, min(t.x1, t.x2)), maxx = max(t.x0, max(t.x1, t.x2));
+    const int miny = min(t.y0, min(t.y1, t.y2)), maxy = max(t.y0, max(t.y1, t.y2));
+    const int i0 = max(row_lo, (minx + 127) >> 8), i1 = min(row_hi, (maxx - 128) >> 8);  // pixel centre = 256 i + 128
+    const int k0 = max(0, (miny + 127) >> 8), k1 = min(g.Z - 1, (maxy - 128) >> 8);
+    if (i0 > i1 || k0 > k1) return;
+    t.i0 = i0, t.k0 = k0, t.bw = k1 - k0 + 1;
+    t.n = t.bw * (i1 - i0 + 1);
+}
+
+// covered(pixel p of the box) for a counter-clockwise triangle
+__device__ __forceinline__ bool solid_covers(const SolidTri& t, int i, int k)
+{
+    const int px = 256 * i + 128, py = 256 * k + 128;
+    const int dx0 = t.x1 - t.x0, dy0 = t.y1 - t.y0, dx1 = t.x2 - t.x1, dy1 = t.y2 - t.y1, dx2 = t.x0 - t.x2, dy2 = t.y0 - t.y2;
+    const long long e0 = (long long)dx0 * (py - t.y0) - (long long)dy0 * (px - t.x0) + ((dy0 > 0 || (dy0 == 0 && dx0 < 0)) ? 1 : 0);
+    const long long e1 = (long long)dx1 * (py - t.y1) - (long long)dy1 * (px - t.x1) + ((dy1 > 0 || (dy1 == 0 && dx1 < 0)) ? 1 : 0);
+    const long long e2 = (long long)dx2 * (py - t.y2) - (long long)dy2 * (px - t.x2) + ((dy2 > 0 || (dy2 == 0 && dx2 < 0)) ? 1 : 0);
+    return e0 > 0 && e1 > 0 && e2 > 0;
+}
+
+__device__ __forceinline__ void solid_draw(uint32_t* plane, const SolidGeom& g, int row_lo, const SolidTri& t, int first, int step)
+{
+    for (int p = first; p < t.n; p += step) {
+        const int r = p / t.bw, i = t.i0 + r, k = t.k0 + (p - r * t.bw);
+        if (solid_covers(t, i, k)) atomicXor(&plane[(i - row_lo) * g.zw + (k >> 5)], 1u << (k & 31));
+    }
+}
+
+__device__ __forceinline__ SolidTri solid_bcast(const SolidTri& t, int src)
+{
+    SolidTri o;
+    o.x0 = __shfl_sync(kFull, t.x0, src), o.y0 = __shfl_sync(kFull, t.y0, src);
+    o.x1 = __shfl_sync(kFull, t.x1, src), o.y1 = __shfl_sync(kFull, t.y1, src);
+    o.x2 = __shfl_sync(kFull, t.x2, src), o.y2 = __shfl_sync(kFull, t.y2, src);
+    o.i0 = __shfl_sync(kFull, t.i0, src), o.k0 = __shfl_sync(kFull, t.k0, src);
+    o.bw = __shfl_sync(kFull, t.bw, src), o.n = __shfl_sync(kFull, t.n, src);
+    return o;
+}
+
+constexpr int kSolidSelf = 12;  // cross-sections of at most this many box pixels are drawn by the lane that owns them
+
+__global__ void __launch_bounds__(256) solid_slice_kernel(uint16_t* __restrict__ grid, const float4* __restrict__ tets, const float2* __restrict__ yrange,
+                                                          uint32_t nf, const float* __restrict__ ys, SolidGeom g, unsigned long long* __restrict__ occupied)
+{
+    extern __shared__ uint32_t plane[];  // [rows][zw]
+    const int s = blockIdx.x, row_lo = blockIdx.y * g.rows, row_hi = min(g.X, row_lo + g.rows) - 1;
+    const int nrows = row_hi - row_lo + 1, words = nrows * g.zw;
+    for (int w = threadIdx.x; w < words; w += blockDim.x) plane[w] = 0;
+    __syncthreads();
+    const float sl = ys[s];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (uint32_t base = warp * 32; base < nf; base += nwarps * 32) {
+        const uint32_t f = base + lane;
+        bool hit = false;
+        if (f < nf) {
+            const float2 yr = yrange[f];
+            hit = yr.x < sl && sl <= yr.y;  // geometry shader :58
+        }
+        if (!__any_sync(kFull, hit)) continue;
+        SolidTri t1, t2;
+        t1.n = t2.n = 0;
+        if (hit) {
+            const float4 q0 = tets[3 * (size_t)f], q1 = tets[3 * (size_t)f + 1], q2 = tets[3 * (size_t)f + 2];
+            const float A[3] = { q0.x, q0.y, q0.z }, B[3] = { q0.w, q1.x, q1.y }, C[3] = { q1.z, q1.w, q2.x }, D[3] = { q2.y, q2.z, q2.w };
+            // INTERP(P, Q, s).xz (:46) -> window coordinates of the X x Z viewport (:177) -> 1/256 pixel
+            auto cut = [&](const float* P, const float* Q, int& wx, int& wy) {
+                const float w = (sl - P[1]) / (Q[1] - P[1]);
+                const float x = P[0] * (1.0f - w) + Q[0] * w, z = P[2] * (1.0f - w) + Q[2] * w;
+                wx = solid_snap(x * g.hx + g.hx), wy = solid_snap(z * g.hz + g.hz);
+            };
+            cut(A, D, t1.x0, t1.y0);
+            if (sl <= B[1]) cut(A, B, t1.x1, t1.y1); else cut(B, D, t1.x1, t1.y1);  // v1 (:62-64)
+            if (sl <= C[1]) cut(A, C, t1.x2, t1.y2); else cut(C, D, t1.x2, t1.y2);  // v2 (:68-70)
+            const bool two = B[1] < sl && sl <= C[1];                                // extra triangle (:77)
+            if (two) {
+                cut(B, C, t2.x0, t2.y0);
+                t2.x1 = t1.x2, t2.y1 = t1.y2, t2.x2 = t1.x1, t2.y2 = t1.y1;
+            }
+            solid_tri_finish(t1, g, row_lo, row_hi);
+            if (two) solid_tri_finish(t2, g, row_lo, row_hi);
+        }
+        const bool self = t1.n + t2.n <= kSolidSelf;
+        if (self) {
+            solid_draw(plane, g, row_lo, t1, 0, 1);
+            solid_draw(plane, g, row_lo, t2, 0, 1);
+        }
+        unsigned big = __ballot_sync(kFull, !self);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            const SolidTri a = solid_bcast(t1, src), b = solid_bcast(t2, src);
+            solid_draw(plane, g, row_lo, a, lane, 32);
+            solid_draw(plane, g, row_lo, b, lane, 32);
+        }
+    }
+    __syncthreads();
+    // expand the bit plane to labels: row (x, s) is Z contiguous cells; RegularGrid.cpp:186-199 after cleanGrid (:591-599)
+    unsigned cnt = 0;
+    if ((g.Z & 7) == 0) {
+        const int vec_per_row = g.Z >> 3;  // 8 cells = 16 bytes
+        for (int e = threadIdx.x; e < nrows * vec_per_row; e += blockDim.x) {
+            const int r = e / vec_per_row, c = e - r * vec_per_row;
+            const uint32_t bits = (plane[r * g.zw + (c >> 2)] >> ((c & 3) * 8)) & 0xFFu;
+            cnt += __popc(bits);
+            uint4 o;
+            o.x = (bits & 1u) | ((bits & 2u) << 15), o.y = ((bits >> 2) & 1u) | ((bits & 8u) << 13);
+            o.z = ((bits >> 4) & 1u) | ((bits & 32u) << 11), o.w = ((bits >> 6) & 1u) | ((bits & 128u) << 9);
+            *reinterpret_cast<uint4*>(grid + ((size_t)(row_lo + r) * g.Y + s) * g.Z + (size_t)c * 8) = o;
+        }
+    } else {
+        for (int e = threadIdx.x; e < nrows * g.Z; e += blockDim.x) {
+            const int r = e / g.Z, k = e - r * g.Z;
+            const uint32_t bit = (plane[r * g.zw + (k >> 5)] >> (k & 31)) & 1u;
+            cnt += bit;
+            grid[((size_t)(row_lo + r) * g.Y + s) * g.Z + k] = (uint16_t)bit;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(kFull, cnt, o);
+    if (lane == 0 && cnt) atomicAdd(occupied, (unsigned long long)cnt);
+}
+
+}  // namespace
+
+extern "C" vf_status vf_voxelize_solid(vf_grid* grid, const float* verts, uint32_t nv, const uint32_t* faces, uint32_t nf, uint64_t* occupied_out)
+{
+    VF_REQUIRE(grid && verts && faces && nv > 0, VF_ERR_INVALID_ARGUMENT, "voxelize_solid: null or empty mesh");
+    vf_ctx* c = grid->ctx;
+    VF_TRY(vf_enter(c));
+    for (uint32_t i = 0; i < 3 * nf; ++i) VF_REQUIRE(faces[i] < nv, VF_ERR_INVALID_ARGUMENT, "face %u references vertex %u >= %u", i / 3, faces[i], nv);
+    if (occupied_out) *occupied_out = 0;
+    if (nf == 0) {
+        VF_CUDA(cudaMemsetAsync(grid->d, 0, grid->n() * sizeof(uint16_t), c->stream));
+        return VF_OK;
+    }
+    SolidGeom g;
+    g.X = (int)grid->X, g.Y = (int)grid->Y, g.Z = (int)grid->Z;
+    g.zw = (g.Z + 31) / 32;
+    // initializeModel :204-217: centroid = float32 sum in vertex order / count, then scaleToNDC
+    float cen[3] = { 0.0f, 0.0f, 0.0f };
+    for (uint32_t i = 0; i < nv; ++i)
+        for (int q = 0; q < 3; ++q) cen[q] += verts[3 * (size_t)i + q];
+    for (int q = 0; q < 3; ++q) {
+        cen[q] /= (float)nv;
+        g.dim[q] = grid->aabb_max[q] - grid->aabb_min[q];
+        g.ctr[q] = 0.5f * (grid->aabb_min[q] + grid->aabb_max[q]);
+        g.cen[q] = (2.0f * (cen[q] - g.ctr[q])) / g.dim[q];
+    }
+    g.hx = (float)g.X * 0.5f, g.hz = (float)g.Z * 0.5f;
+    // bands: a band's bit plane fits 48 KB of shared memory, and there are at least two CTAs per SM
+    const int rows_max = std::max(1, (48 * 1024) / (g.zw * 4));
+    int nbands = std::max((g.X + rows_max - 1) / rows_max, (2 * c->num_sms + g.Y - 1) / g.Y);
+    nbands = std::min(nbands, g.X);
+    g.rows = (g.X + nbands - 1) / nbands;
+    nbands = (g.X + g.rows - 1) / g.rows;
+    VF_REQUIRE(g.Y <= 65535 * 1 && nbands <= 65535, VF_ERR_CAPACITY, "voxelize_solid: grid too large");
+
+    // arena: verts | faces | tets[nf][3] float4 | yrange[nf] float2 | ys[Y] | occupied
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t vbytes = up((size_t)nv * 12), fbytes = up((size_t)nf * 12), tbytes = up((size_t)nf * 48), rbytes = up((size_t)nf * 8), ybytes = up((size_t)g.Y * 4);
+    VF_TRY(vf_scratch_reserve(c, c->mesh, vbytes + fbytes + tbytes + rbytes + ybytes + 256));
+    char* base = (char*)c->mesh.ptr;
+    float* d_verts = (float*)base;
+    uint32_t* d_faces = (uint32_t*)(base + vbytes);
+    float4* d_tets = (float4*)(base + vbytes + fbytes);
+    float2* d_yr = (float2*)(base + vbytes + fbytes + tbytes);
+    float* d_ys = (float*)(base + vbytes + fbytes + tbytes + rbytes);
+    unsigned long long* d_occ = (unsigned long long*)(base + vbytes + fbytes + tbytes + rbytes + ybytes);
+    // slice planes: ySlice starts at -1 and is accumulated (compute :282-299)
+    std::vector<float> ys((size_t)g.Y);
+    {
+        float y = -1.0f;
+        const float step = 2.0f / (float)g.Y;
+        for (int s = 0; s < g.Y; ++s) ys[s] = y, y += step;
+    }
+    VF_CUDA(cudaMemcpyAsync(d_verts, verts, (size_t)nv * 12, cudaMemcpyHostToDevice, c->stream));
+    VF_CUDA(cudaMemcpyAsync(d_faces, faces, (size_t)nf * 12, cudaMemcpyHostToDevice, c->stream));
+    VF_CUDA(cudaMemcpyAsync(d_ys, ys.data(), (size_t)g.Y * 4, cudaMemcpyHostToDevice, c->stream));
+    VF_CUDA(cudaMemsetAsync(d_occ, 0, 8, c->stream));
+    tetra_setup_kernel<<<(nf + 255) / 256, 256, 0, c->stream>>>(d_verts, d_faces, nf, g, d_tets, d_yr);
+    VF_LAUNCHED(c);
+    const size_t smem = (size_t)g.rows * g.zw * 4;
+    solid_slice_kernel<<<dim3((unsigned)g.Y, (unsigned)nbands), 256, smem, c->stream>>>(grid->d, d_tets, d_yr, nf, d_ys, g, d_occ);
+    VF_LAUNCHED(c);
+    unsigned long long* h_occ = (unsigned long long*)((char*)c->pinned + 65536 + 64);
+    VF_CUDA(cudaMemcpyAsync(h_occ, d_occ, 8, cudaMemcpyDeviceToHost, c->stream));
+    VF_CUDA(cudaStreamSynchronize(c->stream));  // also covers the pageable uploads (verts, faces, ys)
+    if (occupied_out) *occupied_out = *h_occ;
+    return VF_OK;
+}
