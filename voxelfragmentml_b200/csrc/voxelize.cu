@@ -324,23 +324,25 @@ extern "C" vf_status vf_voxelize(vf_grid* grid, const float* verts, uint32_t nv,
 // 1/256 pixel (round half even), a centre on an edge belongs to the triangle iff the edge's counter-clockwise direction has
 // dy > 0 or (dy == 0 and dx < 0), 64-bit integer edge functions.
 //
-// B200 design: one CTA per (slice, band of x-rows) keeps the band's bit-plane in shared memory.  Its warps scan the (min y, max y)
-// pairs of all tetrahedra (8 B each, L2 resident), each lane cuts its own hit into triangles, tiny cross-sections (the common
-// case: a face is a few cells wide) are XOR-ed by their own lane, larger ones are broadcast and rastered by the whole warp.
-// The plane is then expanded to uint16 labels and written once, coalesced — no global atomics, no bit grid in HBM, no memset:
-// 2 B/voxel written + 56 B/tetrahedron read per CTA from L2.
+// B200 design: the unit of work is a (tetrahedron, slice) pair.  One warp owns a tetrahedron (its 12 floats are loaded once,
+// its slice range comes from a binary search in the table of accumulated slice planes) and its lanes take the slices 32 at a
+// time, so every lane cuts and draws its own cross-section; a face is a few cells wide, so a cross-section is a handful of
+// pixels, walked row by row with incremental 64-bit edge functions and XOR-ed into a bit grid (1 bit/voxel, L2 resident) with
+// one atomic per touched 32-bit word.  Cross-sections with a large box are voted out (ballot) and drawn by the whole warp, one
+// lane per row.  A last pass expands the bit grid to uint16 labels, coalesced, and counts the FREE cells: 2 B/voxel written,
+// N/8 B of bits written and read, 48 B/tetrahedron read — no per-slice draw call, read-back or host pass.
 namespace {
 
 struct SolidGeom {
     int X, Y, Z;
-    int zw;       // 32-bit words per (x, slice) row of the bit plane
-    int rows;     // x-rows per band
+    int zw;       // 32-bit words per (x, slice) row of the bit grid
     float ctr[3], dim[3], cen[3];  // AABB centre and size, centroid in NDC
     float hx, hz; // X/2, Z/2
 };
 
+// per face: the tetrahedron (face + centroid) in NDC sorted by y, and the slices s with A.y < ys[s] <= D.y (geometry shader :58)
 __global__ void __launch_bounds__(256) tetra_setup_kernel(const float* __restrict__ verts, const uint32_t* __restrict__ faces, uint32_t nf, SolidGeom g,
-                                                          float4* __restrict__ tets, float2* __restrict__ yrange)
+                                                          const float* __restrict__ ys, float4* __restrict__ tets, int2* __restrict__ srange)
 {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nf) return;
@@ -365,7 +367,19 @@ __global__ void __launch_bounds__(256) tetra_setup_kernel(const float* __restric
     tets[3 * (size_t)f + 0] = make_float4(v[0][0], v[0][1], v[0][2], v[1][0]);
     tets[3 * (size_t)f + 1] = make_float4(v[1][1], v[1][2], v[2][0], v[2][1]);
     tets[3 * (size_t)f + 2] = make_float4(v[2][2], v[3][0], v[3][1], v[3][2]);
-    yrange[f] = make_float2(v[0][1], v[3][1]);
+    // ys is strictly increasing: first slice above A.y, last slice not above D.y
+    int lo = 0, hi = g.Y;
+    while (lo < hi) {
+        const int m = (lo + hi) >> 1;
+        if (ys[m] > v[0][1]) hi = m; else lo = m + 1;
+    }
+    const int s0 = lo;
+    lo = 0, hi = g.Y;
+    while (lo < hi) {
+        const int m = (lo + hi) >> 1;
+        if (ys[m] <= v[3][1]) lo = m + 1; else hi = m;
+    }
+    srange[f] = make_int2(s0, lo - 1);
 }
 
 __device__ __forceinline__ int solid_snap(float w)
@@ -376,16 +390,16 @@ __device__ __forceinline__ int solid_snap(float w)
     return (int)f;
 }
 
-// a cross-section triangle in 24.8 fixed-point window coordinates, made counter-clockwise; n = pixels in its clipped box
+// a cross-section triangle in 24.8 fixed-point window coordinates, made counter-clockwise, with its clipped pixel box
 struct SolidTri {
     int x0, y0, x1, y1, x2, y2;
-    int i0, k0, bw, n;  // first row (x), first column (z), box width in z, box pixels (0 = nothing to draw)
+    int i0, i1, k0, k1;  // rows (x) and columns (z) of the box; i1 < i0 = nothing to draw
 };
 
-__device__ __forceinline__ void solid_tri_finish(SolidTri& t, const SolidGeom& g, int row_lo, int row_hi)
+__device__ __forceinline__ void solid_tri_finish(SolidTri& t, const SolidGeom& g)
 {
     const long long area2 = (long long)(t.x1 - t.x0) * (t.y2 - t.y0) - (long long)(t.y1 - t.y0) * (t.x2 - t.x0);
-    t.n = 0;
+    t.i0 = 0, t.i1 = -1, t.k0 = 0, t.k1 = -1;
     if (area2 == 0) return;
     if (area2 < 0) {
         const int tx = t.x1, ty = t.y1;
@@ -393,29 +407,68 @@ __device__ __forceinline__ void solid_tri_finish(SolidTri& t, const SolidGeom& g
     }
     const int minx = min(t.x0, min(t.x1, t.x2)), maxx = max(t.x0, max(t.x1, t.x2));
     const int miny = min(t.y0, min(t.y1, t.y2)), maxy = max(t.y0, max(t.y1, t.y2));
-    const int i0 = max(row_lo, (minx + 127) >> 8), i1 = min(row_hi, (maxx - 128) >> 8);  // pixel centre = 256 i + 128
+    const int i0 = max(0, (minx + 127) >> 8), i1 = min(g.X - 1, (maxx - 128) >> 8);  // pixel centre = 256 i + 128
     const int k0 = max(0, (miny + 127) >> 8), k1 = min(g.Z - 1, (maxy - 128) >> 8);
     if (i0 > i1 || k0 > k1) return;
-    t.i0 = i0, t.k0 = k0, t.bw = k1 - k0 + 1;
-    t.n = t.bw * (i1 - i0 + 1);
+    t.i0 = i0, t.i1 = i1, t.k0 = k0, t.k1 = k1;
 }
 
-// covered(pixel p of the box) for a counter-clockwise triangle
-__device__ __forceinline__ bool solid_covers(const SolidTri& t, int i, int k)
-{
-    const int px = 256 * i + 128, py = 256 * k + 128;
-    const int dx0 = t.x1 - t.x0, dy0 = t.y1 - t.y0, dx1 = t.x2 - t.x1, dy1 = t.y2 - t.y1, dx2 = t.x0 - t.x2, dy2 = t.y0 - t.y2;
-    const long long e0 = (long long)dx0 * (py - t.y0) - (long long)dy0 * (px - t.x0) + ((dy0 > 0 || (dy0 == 0 && dx0 < 0)) ? 1 : 0);
-    const long long e1 = (long long)dx1 * (py - t.y1) - (long long)dy1 * (px - t.x1) + ((dy1 > 0 || (dy1 == 0 && dx1 < 0)) ? 1 : 0);
-    const long long e2 = (long long)dx2 * (py - t.y2) - (long long)dy2 * (px - t.x2) + ((dy2 > 0 || (dy2 == 0 && dx2 < 0)) ? 1 : 0);
-    return e0 > 0 && e1 > 0 && e2 > 0;
-}
+__device__ __forceinline__ int solid_rows(const SolidTri& t) { return t.i1 - t.i0 + 1; }
 
-__device__ __forceinline__ void solid_draw(uint32_t* plane, const SolidGeom& g, int row_lo, const SolidTri& t, int first, int step)
+// XOR rows i_first, i_first + i_step, ... of the triangle's box into the bit rows of slice s.  A centre is covered iff all three
+// edge functions (+1 on the edges the triangle owns) are positive.  Along a row each of them is linear in the column, so it
+// bounds the covered columns from one side: the bound is estimated in float32 and then moved to the exact integer answer with
+// the 64-bit function itself, and the row costs three such solves whatever the width of the box (cross-sections are thin
+// diagonal slivers: their boxes hold ten times more pixels than they cover).
+__device__ __forceinline__ void solid_draw(uint32_t* __restrict__ bits, const SolidGeom& g, int s, const SolidTri& t, int i_first, int i_step)
 {
-    for (int p = first; p < t.n; p += step) {
-        const int r = p / t.bw, i = t.i0 + r, k = t.k0 + (p - r * t.bw);
-        if (solid_covers(t, i, k)) atomicXor(&plane[(i - row_lo) * g.zw + (k >> 5)], 1u << (k & 31));
+    if (i_first > t.i1) return;
+    const int dx[3] = { t.x1 - t.x0, t.x2 - t.x1, t.x0 - t.x2 }, dy[3] = { t.y1 - t.y0, t.y2 - t.y1, t.y0 - t.y2 };
+    const int vx[3] = { t.x0, t.x1, t.x2 }, vy[3] = { t.y0, t.y1, t.y2 };
+    const int px = 256 * i_first + 128, py = 256 * t.k0 + 128, bw = t.k1 - t.k0 + 1;
+    long long r[3], c[3], n[3];
+    float rc[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        r[j] = (long long)dx[j] * (py - vy[j]) - (long long)dy[j] * (px - vx[j]) + ((dy[j] > 0 || (dy[j] == 0 && dx[j] < 0)) ? 1 : 0);
+        c[j] = 256ll * dx[j];                  // one column (z) further
+        n[j] = -256ll * dy[j] * i_step;        // this lane's next row
+        rc[j] = dx[j] ? -1.0f / (float)c[j] : 0.0f;
+    }
+    for (int i = i_first; i <= t.i1; i += i_step) {
+        int lo = 0, hi = bw - 1;  // covered columns, relative to k0
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const long long R = r[j], Cc = c[j];
+            if (Cc == 0) {
+                if (R <= 0) hi = -1;
+                continue;
+            }
+            const float q = fminf(fmaxf((float)R * rc[j], -2.0f), (float)bw + 1.0f);  // zero crossing, approximately
+            if (Cc > 0) {  // smallest column with R + k Cc > 0
+                int k = (int)floorf(q) + 1;
+                k = max(0, min(k, bw));
+                while (k > 0 && R + (long long)(k - 1) * Cc > 0) --k;
+                while (k < bw && R + (long long)k * Cc <= 0) ++k;
+                lo = max(lo, k);
+            } else {       // largest column with R + k Cc > 0
+                int k = (int)ceilf(q) - 1;
+                k = max(-1, min(k, bw - 1));
+                while (k < bw - 1 && R + (long long)(k + 1) * Cc > 0) ++k;
+                while (k >= 0 && R + (long long)k * Cc <= 0) --k;
+                hi = min(hi, k);
+            }
+        }
+        if (lo <= hi) {
+            uint32_t* row = bits + ((size_t)i * g.Y + s) * g.zw;
+            const int ka = t.k0 + lo, kb = t.k0 + hi;
+            for (int w = ka >> 5; w <= (kb >> 5); ++w) {
+                const int a = max(ka, 32 * w) & 31, b = min(kb, 32 * w + 31) & 31;
+                atomicXor(row + w, (0xFFFFFFFFu >> (31 - b + a)) << a);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) r[j] += n[j];
     }
 }
 
@@ -425,36 +478,30 @@ __device__ __forceinline__ SolidTri solid_bcast(const SolidTri& t, int src)
     o.x0 = __shfl_sync(kFull, t.x0, src), o.y0 = __shfl_sync(kFull, t.y0, src);
     o.x1 = __shfl_sync(kFull, t.x1, src), o.y1 = __shfl_sync(kFull, t.y1, src);
     o.x2 = __shfl_sync(kFull, t.x2, src), o.y2 = __shfl_sync(kFull, t.y2, src);
-    o.i0 = __shfl_sync(kFull, t.i0, src), o.k0 = __shfl_sync(kFull, t.k0, src);
-    o.bw = __shfl_sync(kFull, t.bw, src), o.n = __shfl_sync(kFull, t.n, src);
+    o.i0 = __shfl_sync(kFull, t.i0, src), o.i1 = __shfl_sync(kFull, t.i1, src);
+    o.k0 = __shfl_sync(kFull, t.k0, src), o.k1 = __shfl_sync(kFull, t.k1, src);
     return o;
 }
 
-constexpr int kSolidSelf = 12;  // cross-sections of at most this many box pixels are drawn by the lane that owns them
+constexpr int kSolidSelf = 48;  // cross-sections whose boxes have at most this many rows are drawn by the lane that cut them
+                               // (the slices of one tetrahedron have similar cross-sections, so the lanes of a warp stay in step)
 
-__global__ void __launch_bounds__(256) solid_slice_kernel(uint16_t* __restrict__ grid, const float4* __restrict__ tets, const float2* __restrict__ yrange,
-                                                          uint32_t nf, const float* __restrict__ ys, SolidGeom g, unsigned long long* __restrict__ occupied)
+__global__ void __launch_bounds__(256) solid_scatter_kernel(uint32_t* __restrict__ bits, const float4* __restrict__ tets, const int2* __restrict__ srange,
+                                                            uint32_t nf, const float* __restrict__ ys, SolidGeom g)
 {
-    extern __shared__ uint32_t plane[];  // [rows][zw]
-    const int s = blockIdx.x, row_lo = blockIdx.y * g.rows, row_hi = min(g.X, row_lo + g.rows) - 1;
-    const int nrows = row_hi - row_lo + 1, words = nrows * g.zw;
-    for (int w = threadIdx.x; w < words; w += blockDim.x) plane[w] = 0;
-    __syncthreads();
-    const float sl = ys[s];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (uint32_t base = warp * 32; base < nf; base += nwarps * 32) {
-        const uint32_t f = base + lane;
-        bool hit = false;
-        if (f < nf) {
-            const float2 yr = yrange[f];
-            hit = yr.x < sl && sl <= yr.y;  // geometry shader :58
-        }
-        if (!__any_sync(kFull, hit)) continue;
+    const uint32_t f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (f >= nf) return;  // whole warps leave together
+    const int lane = threadIdx.x & 31;
+    const int2 sr = srange[f];
+    if (sr.y < sr.x) return;
+    const float4 q0 = tets[3 * (size_t)f], q1 = tets[3 * (size_t)f + 1], q2 = tets[3 * (size_t)f + 2];
+    const float A[3] = { q0.x, q0.y, q0.z }, B[3] = { q0.w, q1.x, q1.y }, C[3] = { q1.z, q1.w, q2.x }, D[3] = { q2.y, q2.z, q2.w };
+    for (int base = sr.x; base <= sr.y; base += 32) {
+        const int s = base + lane;
         SolidTri t1, t2;
-        t1.n = t2.n = 0;
-        if (hit) {
-            const float4 q0 = tets[3 * (size_t)f], q1 = tets[3 * (size_t)f + 1], q2 = tets[3 * (size_t)f + 2];
-            const float A[3] = { q0.x, q0.y, q0.z }, B[3] = { q0.w, q1.x, q1.y }, C[3] = { q1.z, q1.w, q2.x }, D[3] = { q2.y, q2.z, q2.w };
+        t1.i0 = t2.i0 = 0, t1.i1 = t2.i1 = -1;
+        if (s <= sr.y) {
+            const float sl = ys[s];
             // INTERP(P, Q, s).xz (:46) -> window coordinates of the X x Z viewport (:177) -> 1/256 pixel
             auto cut = [&](const float* P, const float* Q, int& wx, int& wy) {
                 const float w = (sl - P[1]) / (Q[1] - P[1]);
@@ -464,53 +511,60 @@ __global__ void __launch_bounds__(256) solid_slice_kernel(uint16_t* __restrict__
             cut(A, D, t1.x0, t1.y0);
             if (sl <= B[1]) cut(A, B, t1.x1, t1.y1); else cut(B, D, t1.x1, t1.y1);  // v1 (:62-64)
             if (sl <= C[1]) cut(A, C, t1.x2, t1.y2); else cut(C, D, t1.x2, t1.y2);  // v2 (:68-70)
-            const bool two = B[1] < sl && sl <= C[1];                                // extra triangle (:77)
-            if (two) {
+            if (B[1] < sl && sl <= C[1]) {                                          // extra triangle (:77)
                 cut(B, C, t2.x0, t2.y0);
                 t2.x1 = t1.x2, t2.y1 = t1.y2, t2.x2 = t1.x1, t2.y2 = t1.y1;
+                solid_tri_finish(t2, g);
             }
-            solid_tri_finish(t1, g, row_lo, row_hi);
-            if (two) solid_tri_finish(t2, g, row_lo, row_hi);
+            solid_tri_finish(t1, g);
         }
-        const bool self = t1.n + t2.n <= kSolidSelf;
+        const bool self = max(solid_rows(t1), solid_rows(t2)) <= kSolidSelf;
         if (self) {
-            solid_draw(plane, g, row_lo, t1, 0, 1);
-            solid_draw(plane, g, row_lo, t2, 0, 1);
+            solid_draw(bits, g, s, t1, t1.i0, 1);
+            solid_draw(bits, g, s, t2, t2.i0, 1);
         }
         unsigned big = __ballot_sync(kFull, !self);
         while (big) {
             const int src = __ffs(big) - 1;
             big &= big - 1;
             const SolidTri a = solid_bcast(t1, src), b = solid_bcast(t2, src);
-            solid_draw(plane, g, row_lo, a, lane, 32);
-            solid_draw(plane, g, row_lo, b, lane, 32);
+            solid_draw(bits, g, base + src, a, a.i0 + lane, 32);
+            solid_draw(bits, g, base + src, b, b.i0 + lane, 32);
         }
     }
-    __syncthreads();
-    // expand the bit plane to labels: row (x, s) is Z contiguous cells; RegularGrid.cpp:186-199 after cleanGrid (:591-599)
+}
+
+// bit grid -> labels (RegularGrid.cpp:186-199 after cleanGrid :591-599) + FREE count; one thread per 8 cells when Z % 8 == 0
+__global__ void __launch_bounds__(256) solid_expand_kernel(uint16_t* __restrict__ grid, const uint32_t* __restrict__ bits, SolidGeom g, unsigned long long* __restrict__ occupied)
+{
+    const size_t rows = (size_t)g.X * g.Y;
     unsigned cnt = 0;
     if ((g.Z & 7) == 0) {
-        const int vec_per_row = g.Z >> 3;  // 8 cells = 16 bytes
-        for (int e = threadIdx.x; e < nrows * vec_per_row; e += blockDim.x) {
-            const int r = e / vec_per_row, c = e - r * vec_per_row;
-            const uint32_t bits = (plane[r * g.zw + (c >> 2)] >> ((c & 3) * 8)) & 0xFFu;
-            cnt += __popc(bits);
+        const int vec_per_row = g.Z >> 3;
+        const size_t total = rows * vec_per_row;
+        for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+            const size_t r = e / vec_per_row;
+            const int c = (int)(e - r * vec_per_row);
+            const uint32_t b = (bits[r * g.zw + (c >> 2)] >> ((c & 3) * 8)) & 0xFFu;
+            cnt += __popc(b);
             uint4 o;
-            o.x = (bits & 1u) | ((bits & 2u) << 15), o.y = ((bits >> 2) & 1u) | ((bits & 8u) << 13);
-            o.z = ((bits >> 4) & 1u) | ((bits & 32u) << 11), o.w = ((bits >> 6) & 1u) | ((bits & 128u) << 9);
-            *reinterpret_cast<uint4*>(grid + ((size_t)(row_lo + r) * g.Y + s) * g.Z + (size_t)c * 8) = o;
+            o.x = (b & 1u) | ((b & 2u) << 15), o.y = ((b >> 2) & 1u) | ((b & 8u) << 13);
+            o.z = ((b >> 4) & 1u) | ((b & 32u) << 11), o.w = ((b >> 6) & 1u) | ((b & 128u) << 9);
+            *reinterpret_cast<uint4*>(grid + r * g.Z + (size_t)c * 8) = o;
         }
     } else {
-        for (int e = threadIdx.x; e < nrows * g.Z; e += blockDim.x) {
-            const int r = e / g.Z, k = e - r * g.Z;
-            const uint32_t bit = (plane[r * g.zw + (k >> 5)] >> (k & 31)) & 1u;
-            cnt += bit;
-            grid[((size_t)(row_lo + r) * g.Y + s) * g.Z + k] = (uint16_t)bit;
+        const size_t total = rows * g.Z;
+        for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+            const size_t r = e / g.Z;
+            const int k = (int)(e - r * g.Z);
+            const uint32_t b = (bits[r * g.zw + (k >> 5)] >> (k & 31)) & 1u;
+            cnt += b;
+            grid[e] = (uint16_t)b;
         }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(kFull, cnt, o);
-    if (lane == 0 && cnt) atomicAdd(occupied, (unsigned long long)cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(occupied, (unsigned long long)cnt);
 }
 
 }  // namespace
@@ -540,25 +594,20 @@ extern "C" vf_status vf_voxelize_solid(vf_grid* grid, const float* verts, uint32
         g.cen[q] = (2.0f * (cen[q] - g.ctr[q])) / g.dim[q];
     }
     g.hx = (float)g.X * 0.5f, g.hz = (float)g.Z * 0.5f;
-    // bands: a band's bit plane fits 48 KB of shared memory, and there are at least two CTAs per SM
-    const int rows_max = std::max(1, (48 * 1024) / (g.zw * 4));
-    int nbands = std::max((g.X + rows_max - 1) / rows_max, (2 * c->num_sms + g.Y - 1) / g.Y);
-    nbands = std::min(nbands, g.X);
-    g.rows = (g.X + nbands - 1) / nbands;
-    nbands = (g.X + g.rows - 1) / g.rows;
-    VF_REQUIRE(g.Y <= 65535 * 1 && nbands <= 65535, VF_ERR_CAPACITY, "voxelize_solid: grid too large");
 
-    // arena: verts | faces | tets[nf][3] float4 | yrange[nf] float2 | ys[Y] | occupied
+    // arena: verts | faces | tets[nf][3] float4 | srange[nf] int2 | ys[Y] | occupied | bit grid
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t vbytes = up((size_t)nv * 12), fbytes = up((size_t)nf * 12), tbytes = up((size_t)nf * 48), rbytes = up((size_t)nf * 8), ybytes = up((size_t)g.Y * 4);
-    VF_TRY(vf_scratch_reserve(c, c->mesh, vbytes + fbytes + tbytes + rbytes + ybytes + 256));
+    const size_t bbytes = up((size_t)g.X * g.Y * g.zw * 4);
+    VF_TRY(vf_scratch_reserve(c, c->mesh, vbytes + fbytes + tbytes + rbytes + ybytes + 256 + bbytes));
     char* base = (char*)c->mesh.ptr;
     float* d_verts = (float*)base;
     uint32_t* d_faces = (uint32_t*)(base + vbytes);
     float4* d_tets = (float4*)(base + vbytes + fbytes);
-    float2* d_yr = (float2*)(base + vbytes + fbytes + tbytes);
+    int2* d_sr = (int2*)(base + vbytes + fbytes + tbytes);
     float* d_ys = (float*)(base + vbytes + fbytes + tbytes + rbytes);
     unsigned long long* d_occ = (unsigned long long*)(base + vbytes + fbytes + tbytes + rbytes + ybytes);
+    uint32_t* d_bits = (uint32_t*)(base + vbytes + fbytes + tbytes + rbytes + ybytes + 256);
     // slice planes: ySlice starts at -1 and is accumulated (compute :282-299)
     std::vector<float> ys((size_t)g.Y);
     {
@@ -569,12 +618,17 @@ extern "C" vf_status vf_voxelize_solid(vf_grid* grid, const float* verts, uint32
     VF_CUDA(cudaMemcpyAsync(d_verts, verts, (size_t)nv * 12, cudaMemcpyHostToDevice, c->stream));
     VF_CUDA(cudaMemcpyAsync(d_faces, faces, (size_t)nf * 12, cudaMemcpyHostToDevice, c->stream));
     VF_CUDA(cudaMemcpyAsync(d_ys, ys.data(), (size_t)g.Y * 4, cudaMemcpyHostToDevice, c->stream));
-    VF_CUDA(cudaMemsetAsync(d_occ, 0, 8, c->stream));
-    tetra_setup_kernel<<<(nf + 255) / 256, 256, 0, c->stream>>>(d_verts, d_faces, nf, g, d_tets, d_yr);
+    VF_CUDA(cudaMemsetAsync(d_occ, 0, 256 + bbytes, c->stream));  // counter + bit grid
+    tetra_setup_kernel<<<(nf + 255) / 256, 256, 0, c->stream>>>(d_verts, d_faces, nf, g, d_ys, d_tets, d_sr);
     VF_LAUNCHED(c);
-    const size_t smem = (size_t)g.rows * g.zw * 4;
-    solid_slice_kernel<<<dim3((unsigned)g.Y, (unsigned)nbands), 256, smem, c->stream>>>(grid->d, d_tets, d_yr, nf, d_ys, g, d_occ);
+    solid_scatter_kernel<<<(nf + 7) / 8, 256, 0, c->stream>>>(d_bits, d_tets, d_sr, nf, d_ys, g);  // one warp per tetrahedron
     VF_LAUNCHED(c);
+    {
+        const size_t units = (g.Z & 7) == 0 ? grid->n() / 8 : grid->n();
+        const unsigned blocks = (unsigned)std::min<size_t>((units + 255) / 256, (size_t)c->num_sms * 16);
+        solid_expand_kernel<<<blocks, 256, 0, c->stream>>>(grid->d, d_bits, g, d_occ);
+        VF_LAUNCHED(c);
+    }
     unsigned long long* h_occ = (unsigned long long*)((char*)c->pinned + 65536 + 64);
     VF_CUDA(cudaMemcpyAsync(h_occ, d_occ, 8, cudaMemcpyDeviceToHost, c->stream));
     VF_CUDA(cudaStreamSynchronize(c->stream));  // also covers the pageable uploads (verts, faces, ys)
