@@ -209,6 +209,9 @@ vf_status vf_histogram(vf_grid* g, uint32_t* counts, uint64_t* occupied);
 
 /* ------------------------------------------------------------------ X1: export */
 vf_status vf_export(vf_grid* g, const char* path_without_extension, int export_type, int squared); /* RegularGrid::exportGrid, :161-171 */
+/* exportRLE (:672-714) with the runs found on the device: *bytes_out = 12 + 6 * runs; the byte stream is written to the HOST
+ * buffer `out` when out != NULL && cap >= *bytes_out (otherwise the call is a size query).  Only the stream crosses PCIe. */
+vf_status vf_grid_encode_rle(vf_grid* g, uint8_t* out, uint64_t cap, uint64_t* bytes_out);
 /* in-memory encoders (host): return bytes needed; write when out != NULL && cap is large enough */
 uint64_t  vf_encode_rle(const uint16_t* grid, const uint32_t dims[3], uint8_t* out, uint64_t cap);          /* exportRLE :672-714 */
 uint64_t  vf_encode_bing_squared(const uint16_t* grid, const uint32_t dims[3], uint8_t* out, uint64_t cap); /* exportRawCompressed squared :638-666 */

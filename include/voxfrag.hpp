@@ -168,6 +168,15 @@ public:
     void undoMask() { check(vf_undo_mask(_h)); }
     void resetFilling() { check(vf_reset_filling(_h)); }
     void homogenize() { check(vf_homogenize(_h)); }
+    // the `.rle` byte stream (exportRLE) with the runs found on the device
+    std::vector<uint8_t> encodeRLE()
+    {
+        uint64_t need = 0;
+        check(vf_grid_encode_rle(_h, nullptr, 0, &need));
+        std::vector<uint8_t> bytes(need);
+        check(vf_grid_encode_rle(_h, bytes.data(), bytes.size(), &need));
+        return bytes;
+    }
     void exportGrid(const std::string& filename, bool squared, FractureParameters::ExportGrid exportType) { check(vf_export(_h, filename.c_str(), (int)exportType, squared)); }
     // host access: updateGrid() downloads, updateSSBO() uploads, data() is the last downloaded copy
     void updateGrid()

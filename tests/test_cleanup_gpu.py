@@ -1,4 +1,5 @@
 """C2-C4 / H1 / S1-S2 / X1 / fractureModel parity on the GPU against the oracle (bit-exact)."""
+import ctypes as C
 import os
 import struct
 
@@ -235,3 +236,24 @@ def test_export_rle_and_bing(ctx, orc, labelled_vessel, tmp_path):
     g.exportGrid(base, True, vf.ExportGrid.QUADSTACK)
     assert open(base + ".qstack", "rb").read() == orc.encode_qstack(lab)
     g.close()
+
+
+def test_device_rle_encoder_matches_oracle(ctx, orc, labelled_vessel):
+    """vf_grid_encode_rle: runs found on the device == exportRLE's bytes, on label grids, noise (one run per cell), uniform
+    grids (one run), cell counts that are not a multiple of the 8-cell vectors or of the 2048-cell tiles, and 1-cell grids."""
+    lab, _ = labelled_vessel
+    rs = np.random.RandomState(9)
+    grids = [lab, np.ones((1, 1, 1), np.uint16), np.zeros((64, 64, 64), np.uint16), np.full((3, 5, 7), 4, np.uint16),
+             rs.randint(0, 3, size=(17, 13, 11)).astype(np.uint16), rs.randint(0, 60000, size=(40, 41, 43)).astype(np.uint16),
+             np.repeat(rs.randint(0, 9, size=(33, 9, 5)).astype(np.uint16), 13, axis=2)]
+    for a in grids:
+        g = _grid(ctx, a)
+        want = orc.encode_rle(a)
+        got = g.encodeRLE()
+        assert got == want, a.shape
+        # size query + too-small buffer leave the caller's memory alone
+        need = C.c_uint64(0)
+        small = np.zeros(8, np.uint8)
+        assert g._lib.vf_grid_encode_rle(g._h, small.ctypes.data, 8, C.byref(need)) == 0
+        assert need.value == len(want) and not small.any()
+        g.close()

@@ -90,6 +90,7 @@ SIGNATURES = {
     "vf_homogenize": (C.c_int, [_vp]),
     "vf_histogram": (C.c_int, [_vp, _vp, C.POINTER(C.c_uint64)]),
     "vf_export": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int]),
+    "vf_grid_encode_rle": (C.c_int, [_vp, _vp, C.c_uint64, _vp]),
     "vf_encode_rle": (C.c_uint64, [_vp, _vp, _vp, C.c_uint64]),
     "vf_encode_bing_squared": (C.c_uint64, [_vp, _vp, _vp, C.c_uint64]),
     "vf_encode_vox": (C.c_uint64, [_vp, _vp, C.c_int, _vp, C.c_uint64]),

@@ -280,6 +280,14 @@ class RegularGrid:
         return self.countValues()[1]
 
     # ---- X1
+    def encodeRLE(self) -> bytes:
+        """the `.rle` byte stream of exportRLE (RegularGrid.cpp:672-714), runs found on the device; only the stream is downloaded"""
+        need = C.c_uint64(0)
+        check(self._lib.vf_grid_encode_rle(self._h, None, 0, C.byref(need)))
+        buf = np.empty(need.value, np.uint8)
+        check(self._lib.vf_grid_encode_rle(self._h, ptr(buf), buf.size, C.byref(need)))
+        return buf.tobytes()
+
     def exportGrid(self, filename: str, squared: bool, exportType):
         check(self._lib.vf_export(self._h, filename.encode(), int(exportType), int(bool(squared))))
 

@@ -115,7 +115,7 @@ extern "C" void vf_ctx_destroy(vf_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    VfScratch* all[] = { &c->keys, &c->grid2, &c->tiles, &c->small, &c->noise, &c->mesh };
+    VfScratch* all[] = { &c->keys, &c->grid2, &c->tiles, &c->small, &c->noise, &c->mesh, &c->codec };
     for (VfScratch* s : all)
         if (s->ptr) cudaFree(s->ptr);
     if (c->pinned) cudaFreeHost(c->pinned);

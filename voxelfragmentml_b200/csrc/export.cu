@@ -356,32 +356,225 @@ extern "C" uint64_t vf_encode_qstack(const uint16_t* grid, const uint32_t dims[3
     return f.pos;
 }
 
+// ---- .rle on the device -------------------------------------------------------------------------------------------------
+// exportRLE (RegularGrid.cpp:672-714) walks the host copy of the grid cell by cell; with the grid resident in HBM that costs a
+// 2 B/voxel download per export.  Here the runs are found where the grid lives: a cell starts a run iff it
+// differs from its predecessor in the x-major array (cell 0 always does), so   count starts per 2048-cell tile -> exclusive scan
+// of the tile counts -> every start writes {cell index, value} at its rank -> repetitions = next start - this start, packed
+// into the file's 6-byte records {uint16 value, uint32 repetitions}.  Only the finished byte stream (12 + 6 R bytes, R = runs)
+// crosses PCIe.  Reads 2 x 2 B/voxel, writes 12 B/run.
+namespace {
+
+constexpr int kRleThreads = 256, kRleCells = 8, kRleTile = kRleThreads * kRleCells;
+
+// bit j of the result = cell (first + j) starts a run; cells[] receives the 8 values (cells past the end repeat the last one)
+__device__ __forceinline__ uint32_t rle_flags(const uint16_t* __restrict__ grid, uint64_t n, uint64_t first, uint16_t cells[kRleCells])
+{
+    if (first >= n) return 0;
+    uint16_t prev = first ? grid[first - 1] : (uint16_t)~grid[0];
+    if (first + kRleCells <= n) {
+        const uint4 v = *reinterpret_cast<const uint4*>(grid + first);  // first % 8 == 0 and the grid is 16-byte aligned
+        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cells[2 * j] = (uint16_t)w[j], cells[2 * j + 1] = (uint16_t)(w[j] >> 16);
+    } else {
+#pragma unroll
+        for (int j = 0; j < kRleCells; ++j) cells[j] = first + j < n ? grid[first + j] : (uint16_t)0;
+    }
+    uint32_t flags = 0;
+#pragma unroll
+    for (int j = 0; j < kRleCells; ++j) {
+        if (first + j < n && cells[j] != prev) flags |= 1u << j;
+        prev = cells[j];
+    }
+    return flags;
+}
+
+__global__ void __launch_bounds__(kRleThreads) rle_count_kernel(const uint16_t* __restrict__ grid, uint64_t n, uint32_t* __restrict__ counts)
+{
+    __shared__ uint32_t warp_sums[kRleThreads / 32];
+    uint16_t cells[kRleCells];
+    const uint64_t first = ((uint64_t)blockIdx.x * kRleThreads + threadIdx.x) * kRleCells;
+    uint32_t c = __popc(rle_flags(grid, n, first, cells));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int w = 0; w < kRleThreads / 32; ++w) t += warp_sums[w];
+        counts[blockIdx.x] = t;
+    }
+}
+
+// exclusive scan of the tile counts by one CTA; *total = number of runs
+__global__ void __launch_bounds__(1024) rle_scan_kernel(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets, uint32_t n, uint32_t* __restrict__ total)
+{
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n ? counts[i] : 0;
+        uint32_t s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, s, o);
+            if ((threadIdx.x & 31) >= o) s += t;
+        }
+        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = warp_sums[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, w, o);
+                if (threadIdx.x >= o) w += t;
+            }
+            warp_sums[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const uint32_t before = carry + (threadIdx.x >= 32 ? warp_sums[(threadIdx.x >> 5) - 1] : 0) + s - v;
+        if (i < n) offsets[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(kRleThreads) rle_emit_kernel(const uint16_t* __restrict__ grid, uint64_t n, const uint32_t* __restrict__ offsets,
+                                                                uint32_t* __restrict__ starts, uint16_t* __restrict__ values)
+{
+    __shared__ uint32_t warp_sums[kRleThreads / 32];
+    uint16_t cells[kRleCells];
+    const uint64_t first = ((uint64_t)blockIdx.x * kRleThreads + threadIdx.x) * kRleCells;
+    const uint32_t flags = rle_flags(grid, n, first, cells);
+    const uint32_t mine = __popc(flags);
+    uint32_t s = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, s, o);
+        if ((threadIdx.x & 31) >= o) s += t;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = s;
+    __syncthreads();
+    uint32_t rank = offsets[blockIdx.x] + s - mine;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) rank += warp_sums[w];
+    uint32_t f = flags;
+    while (f) {
+        const int j = __ffs(f) - 1;
+        f &= f - 1;
+        starts[rank] = (uint32_t)(first + j);
+        values[rank] = cells[j];
+        ++rank;
+    }
+}
+
+// records {uint16 value, uint32 repetitions}, 6 bytes each, after the 12-byte header (all 2-byte aligned)
+__global__ void __launch_bounds__(256) rle_pack_kernel(const uint32_t* __restrict__ starts, const uint16_t* __restrict__ values, uint32_t runs, uint64_t n,
+                                                       uint3 dims, uint16_t* __restrict__ out)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0) {
+        out[0] = (uint16_t)dims.x, out[1] = (uint16_t)(dims.x >> 16), out[2] = (uint16_t)dims.y;
+        out[3] = (uint16_t)(dims.y >> 16), out[4] = (uint16_t)dims.z, out[5] = (uint16_t)(dims.z >> 16);
+    }
+    if (r >= runs) return;
+    const uint32_t rep = (uint32_t)((r + 1 < runs ? (uint64_t)starts[r + 1] : n) - starts[r]);
+    uint16_t* rec = out + 6 + 3 * (size_t)r;
+    rec[0] = values[r], rec[1] = (uint16_t)rep, rec[2] = (uint16_t)(rep >> 16);
+}
+
+}  // namespace
+
+// `grow` (optional) is resized to the stream's size and receives it; otherwise `out`/`cap` as in the public entry point
+static vf_status rle_encode_device(vf_grid* g, std::vector<uint8_t>* grow, uint8_t* out, uint64_t cap, uint64_t* bytes_out)
+{
+    VF_REQUIRE(g && bytes_out, VF_ERR_INVALID_ARGUMENT, "null argument");
+    vf_ctx* c = g->ctx;
+    VF_TRY(vf_enter(c));
+    const uint64_t n = g->n();
+    VF_REQUIRE(n > 0 && n < (1ull << 32), VF_ERR_CAPACITY, "the .rle layout holds uint32 cell counts (RegularGrid.cpp:681)");
+    const uint32_t ntiles = (uint32_t)((n + kRleTile - 1) / kRleTile);
+    const size_t tb = ((size_t)ntiles * 4 + 255) & ~(size_t)255;
+    VF_TRY(vf_scratch_reserve(c, c->codec, 2 * tb + 256));
+    uint32_t* d_counts = (uint32_t*)c->codec.ptr;
+    uint32_t* d_offsets = (uint32_t*)((char*)c->codec.ptr + tb);
+    uint32_t* d_total = (uint32_t*)((char*)c->codec.ptr + 2 * tb);
+    rle_count_kernel<<<ntiles, kRleThreads, 0, c->stream>>>(g->d, n, d_counts);
+    VF_LAUNCHED(c);
+    rle_scan_kernel<<<1, 1024, 0, c->stream>>>(d_counts, d_offsets, ntiles, d_total);
+    VF_LAUNCHED(c);
+    uint32_t* h_total = (uint32_t*)((char*)c->pinned + 65536 + 128);
+    VF_CUDA(cudaMemcpyAsync(h_total, d_total, 4, cudaMemcpyDeviceToHost, c->stream));
+    VF_CUDA(cudaStreamSynchronize(c->stream));
+    const uint64_t runs = *h_total, bytes = 12 + 6 * runs;
+    *bytes_out = bytes;
+    if (grow) {
+        grow->resize(bytes);
+        out = grow->data(), cap = bytes;
+    }
+    if (!out || cap < bytes) return VF_OK;  // size query, like the host encoders
+    const size_t sb = ((size_t)runs * 4 + 255) & ~(size_t)255, vb = ((size_t)runs * 2 + 255) & ~(size_t)255;
+    if (c->codec.bytes < 2 * tb + 256 + sb + vb + bytes) {
+        // the arena moves: keep the tile offsets (cheaper to copy than to recount)
+        VfScratch old = c->codec;
+        c->codec = VfScratch();
+        VF_TRY(vf_scratch_reserve(c, c->codec, 2 * tb + 256 + sb + vb + bytes + 256));
+        VF_CUDA(cudaMemcpyAsync(c->codec.ptr, old.ptr, 2 * tb + 256, cudaMemcpyDeviceToDevice, c->stream));
+        VF_CUDA(cudaStreamSynchronize(c->stream));
+        VF_CUDA(cudaFree(old.ptr));
+        d_offsets = (uint32_t*)((char*)c->codec.ptr + tb);
+    }
+    uint32_t* d_starts = (uint32_t*)((char*)c->codec.ptr + 2 * tb + 256);
+    uint16_t* d_values = (uint16_t*)((char*)d_starts + sb);
+    uint16_t* d_out = (uint16_t*)((char*)d_values + vb);
+    rle_emit_kernel<<<ntiles, kRleThreads, 0, c->stream>>>(g->d, n, d_offsets, d_starts, d_values);
+    VF_LAUNCHED(c);
+    rle_pack_kernel<<<(unsigned)((runs + 255) / 256), 256, 0, c->stream>>>(d_starts, d_values, (uint32_t)runs, n, make_uint3(g->X, g->Y, g->Z), d_out);
+    VF_LAUNCHED(c);
+    VF_CUDA(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, c->stream));
+    VF_CUDA(cudaStreamSynchronize(c->stream));
+    return VF_OK;
+}
+
+extern "C" vf_status vf_grid_encode_rle(vf_grid* g, uint8_t* out, uint64_t cap, uint64_t* bytes_out) { return rle_encode_device(g, nullptr, out, cap, bytes_out); }
+
 extern "C" vf_status vf_export(vf_grid* g, const char* path, int type, int squared)
 {
     VF_REQUIRE(g && path, VF_ERR_INVALID_ARGUMENT, "null argument");
     VF_TRY(vf_enter(g->ctx));
     static const char* ext[4] = { "rle", "qstack", "vox", "bing" };  // FractureParameters::ExportGrid_STR, FractureParameters.h:36
     VF_REQUIRE(type >= 0 && type < 4, VF_ERR_INVALID_ARGUMENT, "bad export type %d", type);
-    std::vector<uint16_t> host(g->n());
-    VF_TRY(vf_grid_download(g, host.data()));
     const uint32_t dims[3] = { g->X, g->Y, g->Z };
     std::vector<uint8_t> bytes;
-    if (type == VF_RLE) {
-        bytes.resize(vf_encode_rle(host.data(), dims, nullptr, 0));
-        vf_encode_rle(host.data(), dims, bytes.data(), bytes.size());
-    } else if (type == VF_QUADSTACK) {
-        bytes.resize(vf_encode_qstack(host.data(), dims, nullptr, 0));
-        vf_encode_qstack(host.data(), dims, bytes.data(), bytes.size());
-    } else if (type == VF_VOX) {
-        bytes.resize(vf_encode_vox(host.data(), dims, squared, nullptr, 0));
-        vf_encode_vox(host.data(), dims, squared, bytes.data(), bytes.size());
-    } else if (squared) {
-        bytes.resize(vf_encode_bing_squared(host.data(), dims, nullptr, 0));
-        vf_encode_bing_squared(host.data(), dims, bytes.data(), bytes.size());
+    if (type == VF_RLE && g->n() < (1ull << 32)) {
+        // runs are found on the device; only the finished byte stream is downloaded
+        uint64_t need = 0;
+        VF_TRY(rle_encode_device(g, &bytes, nullptr, 0, &need));
     } else {
-        bytes.resize(12 + host.size() * 2);
-        std::memcpy(bytes.data(), dims, 12);
-        std::memcpy(bytes.data() + 12, host.data(), host.size() * 2);
+        std::vector<uint16_t> host(g->n());
+        VF_TRY(vf_grid_download(g, host.data()));
+        if (type == VF_RLE) {
+            bytes.resize(vf_encode_rle(host.data(), dims, nullptr, 0));
+            vf_encode_rle(host.data(), dims, bytes.data(), bytes.size());
+        } else if (type == VF_QUADSTACK) {
+            bytes.resize(vf_encode_qstack(host.data(), dims, nullptr, 0));
+            vf_encode_qstack(host.data(), dims, bytes.data(), bytes.size());
+        } else if (type == VF_VOX) {
+            bytes.resize(vf_encode_vox(host.data(), dims, squared, nullptr, 0));
+            vf_encode_vox(host.data(), dims, squared, bytes.data(), bytes.size());
+        } else if (squared) {
+            bytes.resize(vf_encode_bing_squared(host.data(), dims, nullptr, 0));
+            vf_encode_bing_squared(host.data(), dims, bytes.data(), bytes.size());
+        } else {
+            bytes.resize(12 + host.size() * 2);
+            std::memcpy(bytes.data(), dims, 12);
+            std::memcpy(bytes.data() + 12, host.data(), host.size() * 2);
+        }
     }
     const std::string file = std::string(path) + "." + ext[type];
     FILE* f = std::fopen(file.c_str(), "wb");

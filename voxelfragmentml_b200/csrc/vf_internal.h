@@ -99,6 +99,7 @@ struct vf_ctx {
     VfScratch small;     // seeds, counters, histogram bins, masks
     VfScratch noise;     // erosion noise table
     VfScratch mesh;      // voxelizer: vertices, faces, bins
+    VfScratch codec;     // device-side .rle encoder: tile counts, run starts / values, packed records
     void* pinned = nullptr;  // small pinned host mailbox for counters
     size_t pinned_bytes = 0;
     // Host shadows of what the seed area of `small` and the `noise` arena hold on the device.  A call that brings the same
