@@ -227,6 +227,40 @@ vf_status vf_synth_solid_vessel(vf_grid* g, int x_offset, uint32_t n, float base
  * numSeeds*2+numExtraSeeds entries of uint32[4]) receives the seed list used. */
 vf_status vf_fracture_model(vf_grid* g, const vf_params* p, uint32_t* seeds_out, uint32_t* nseeds_out, vf_flood_stats* stats);
 
+/* ------------------------------------------------------------------ f1: the dataset driver (CADScene::generateDataset, CADScene.cpp:209-507) */
+/* struct FragmentationProcedure (SRC/Graphics/Core/FragmentationProcedure.h:6-60), voxel-path fields only */
+typedef struct vf_procedure {
+    vf_params fractureParameters;   /* :10, with the constructor's overrides (:41-60): biasSeeds 0, erode 0, voxelPerMetricUnit = clamp, RLE grids */
+    int32_t   fragmentInterval[2];  /* :12  (2, 10) */
+    int32_t   iterationInterval[2]; /* :13  (25, 15) */
+    uint64_t  maxFragmentsModel;    /* :16  1000 */
+    int32_t   exportGrid;           /* FractureParameters::_exportGrid, :52: 1 */
+    /* -- extensions (0 = reference behaviour / north-star occupancy) -- */
+    int32_t   solidVoxelization;    /* 0: SAT surface occupancy (vf_voxelize); 1: Tetravoxelizer occupancy (vf_voxelize_solid) */
+    int32_t   writerThreads;        /* file writers running beside the GPU loop (0 = write synchronously like the reference); default 2 */
+} vf_procedure;
+
+typedef struct vf_dataset_stats {
+    uint64_t models, fragmentations, fragments, files, bytes_written, bytes_downloaded, voxels;
+    double   seconds_voxelize, seconds_fracture, seconds_export;   /* host wall clock per phase (ResourceTracker's events, CADScene.cpp:236-238) */
+} vf_dataset_stats;
+
+void      vf_procedure_default(vf_procedure* p);                               /* FragmentationProcedure::FragmentationProcedure() */
+void      vf_dataset_dims_rule(const float aabb_min[3], const float aabb_max[3], int32_t voxelPerMetricUnit, int32_t clampVoxelMetricUnit,
+                               uint32_t dims_out[3]);                        /* CADScene.cpp:262-273 */
+int32_t   vf_dataset_iterations(const vf_procedure* p, int32_t numFragments);  /* glm::mix of the iteration interval, CADScene.cpp:304-306 */
+/* the body of generateDataset's model loop (:240-466) for one already-loaded model: dims rule, setAABB + fill, starting-grid export,
+ * every (numFragments, iteration) fragmentation with its grid export and metadata rows, exportMetadata.  `g` must have capacity for
+ * the dims rule's result (allocate (clamp+3) x clamp x (clamp+3)).  The context's RNG stream is continued, not re-seeded. */
+vf_status vf_dataset_model(vf_grid* g, const vf_procedure* proc, const char* model_name, const float* verts, uint32_t nv, const uint32_t* faces,
+                           uint32_t nf, const char* destination_folder, vf_dataset_stats* stats);
+/* generateDataset itself: searchFiles(folder, extension) + _startVessel skip + one grid for the whole run.  Models are read with a
+ * minimal Wavefront .obj reader (Assimp is not on this path) and normalised as CADModel::load does (CADModel.cpp:148-152). */
+vf_status vf_dataset_generate(vf_ctx* ctx, const vf_procedure* proc, const char* folder, const char* extension, const char* start_vessel,
+                              const char* destination_folder, vf_dataset_stats* stats);
+vf_status vf_load_obj(const char* path, float** verts_out, uint32_t* nv_out, uint32_t** faces_out, uint32_t* nf_out); /* free with vf_free_host */
+void      vf_free_host(void* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,7 +24,10 @@ from .api import (  # noqa: E402
     fracture_model,
 )
 
+from .dataset import FragmentationProcedure, generateDataset  # noqa: E402
+
 __all__ = [
+    "FragmentationProcedure", "generateDataset",
     "Context", "DistanceFunction", "ErosionType", "ExportGrid", "FloodFracturer", "FractureAlgorithm", "FractureParameters",
     "NaiveFracturer", "RandomUniformType", "RegularGrid", "Seeder", "SeederSearchError", "VoxFragError", "VOXEL_EMPTY",
     "VOXEL_FREE", "fracture_model",

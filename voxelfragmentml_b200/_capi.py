@@ -28,6 +28,19 @@ class VfParams(C.Structure):
     ]
 
 
+class VfProcedure(C.Structure):
+    """struct vf_procedure == FragmentationProcedure's voxel-path fields (FragmentationProcedure.h:6-60)."""
+
+    _fields_ = [("fractureParameters", VfParams), ("fragmentInterval", C.c_int32 * 2), ("iterationInterval", C.c_int32 * 2),
+                ("maxFragmentsModel", C.c_uint64), ("exportGrid", C.c_int32), ("solidVoxelization", C.c_int32), ("writerThreads", C.c_int32)]
+
+
+class VfDatasetStats(C.Structure):
+    _fields_ = [("models", C.c_uint64), ("fragmentations", C.c_uint64), ("fragments", C.c_uint64), ("files", C.c_uint64),
+                ("bytes_written", C.c_uint64), ("bytes_downloaded", C.c_uint64), ("voxels", C.c_uint64),
+                ("seconds_voxelize", C.c_double), ("seconds_fracture", C.c_double), ("seconds_export", C.c_double)]
+
+
 class VfFloodStats(C.Structure):
     _fields_ = [("tile_rounds", C.c_uint32), ("tile_visits", C.c_uint32), ("disjoint_rounds", C.c_uint32),
                 ("freed_voxels", C.c_uint32), ("max_dist", C.c_uint32)]
@@ -90,6 +103,13 @@ SIGNATURES = {
     "vf_homogenize": (C.c_int, [_vp]),
     "vf_histogram": (C.c_int, [_vp, _vp, C.POINTER(C.c_uint64)]),
     "vf_export": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int]),
+    "vf_procedure_default": (None, [C.POINTER(VfProcedure)]),
+    "vf_dataset_dims_rule": (None, [_vp, _vp, C.c_int32, C.c_int32, _vp]),
+    "vf_dataset_iterations": (C.c_int32, [C.POINTER(VfProcedure), C.c_int32]),
+    "vf_dataset_model": (C.c_int, [_vp, C.POINTER(VfProcedure), C.c_char_p, _vp, _u32, _vp, _u32, C.c_char_p, C.POINTER(VfDatasetStats)]),
+    "vf_dataset_generate": (C.c_int, [_vp, C.POINTER(VfProcedure), C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(VfDatasetStats)]),
+    "vf_load_obj": (C.c_int, [C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(_u32), C.POINTER(C.POINTER(_u32)), C.POINTER(_u32)]),
+    "vf_free_host": (None, [_vp]),
     "vf_grid_encode_rle": (C.c_int, [_vp, _vp, C.c_uint64, _vp]),
     "vf_encode_rle": (C.c_uint64, [_vp, _vp, _vp, C.c_uint64]),
     "vf_encode_bing_squared": (C.c_uint64, [_vp, _vp, _vp, C.c_uint64]),
