@@ -541,6 +541,64 @@ def run_batch(args):
         dist.destroy_process_group()
 
 
+def run_dataset(args):
+    """The batch workload through the NATIVE dataset driver (csrc/dataset.cpp = CADScene::generateDataset's voxel path): per mesh
+    the dims rule at clamp 256, SAT voxelization, 10 fragmentations (numFragments 2..11, one iteration each, FLOOD CHEBYSHEV, 2n extra
+    seeds), histogram, undoMask, and — unlike `--workload batch` — the `.rle` export of every grid (runs found on the device, files
+    written by the driver's writer threads to --out).  Mesh m -> rank m mod N, RNG seed 80 + m."""
+    import shutil
+    import tempfile
+
+    import torch
+
+    import voxelfragmentml_b200 as vf
+    from voxelfragmentml_b200 import dataset, synth
+
+    rank, local_rank, world, dist = _dist_setup()
+    ctx = vf.Context(local_rank)
+    pool = [synth.vessel_mesh(i) for i in range(args.mesh_pool)]
+    proc = vf.FragmentationProcedure(_fragmentInterval=(2, 11), _iterationInterval=(1, 1), _maxFragmentsModel=1 << 40)
+    proc._fractureParameters._clampVoxelMetricUnit = 256
+    proc._fractureParameters._voxelPerMetricUnit = 256
+    grid = dataset.dataset_grid(ctx, proc)
+    out = tempfile.mkdtemp(prefix=f"vf_dataset_r{rank}_", dir=args.out or None)
+    my = [m for m in range(args.meshes) if m % world == rank]
+    st = vf._capi.VfDatasetStats()
+
+    def one_mesh(m, stats):
+        v, f = pool[m % len(pool)]
+        ctx.initSeed(80 + m)
+        dataset.generate_model(grid, proc, f"VS_{m:04d}", v, f, out + "/", stats)
+
+    for m in my[: args.warmup]:
+        one_mesh(m, vf._capi.VfDatasetStats())
+    ctx.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for m in my:
+        one_mesh(m, st)
+    ctx.synchronize()
+    dt = time.perf_counter() - t0
+    shutil.rmtree(out, ignore_errors=True)
+    if dist is not None:
+        tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt[0])
+    if rank == 0:
+        print(json.dumps({
+            "metric": "models/s batch voxelize+fragment+export", "value": args.meshes / dt, "unit": "models/s", "n_gpus": world, "steps": args.meshes,
+            "warmup": args.warmup, "ms_per_step": dt / args.meshes * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u16 labels", "data": "synthetic",
+            "config": {"workload": f"cfg4-dataset: {args.meshes} synthetic vessels (pool of {len(pool)} shapes) x 10 fragmentations at clamp 256 through the native "
+                                   "driver, FLOOD CHEBYSHEV, n = 2..11 seeds + 2n extra, .rle export of every grid (device run detection, async writers)",
+                       "rank0": {k: getattr(st, k) for k, _ in st._fields_}, "fragmentations_per_s": args.meshes * 10 / dt},
+        }))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -550,7 +608,9 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--cpu-size", type=int, default=0, help="edge of the CPU sample grid (default: 512 once for cpu_baseline, 384 per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "slab", "batch"], help="cfg3 = the driver's default; slab = cfg5; batch = cfg4")
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "slab", "batch", "dataset"],
+                    help="cfg3 = the driver's default; slab = cfg5; batch = cfg4; dataset = cfg4 through the native driver with .rle export")
+    ap.add_argument("--out", default="", help="dataset workload: parent directory of the (temporary) output folder")
     ap.add_argument("--seeds", type=int, default=256, help="slab workload: number of seeds")
     ap.add_argument("--meshes", type=int, default=64, help="batch workload: number of meshes")
     ap.add_argument("--mesh-pool", type=int, default=8, help="batch workload: distinct synthetic shapes generated up front")
@@ -559,6 +619,8 @@ def main():
         run_reference(args)
     elif args.workload == "slab":
         run_slab(args)
+    elif args.workload == "dataset":
+        run_dataset(args)
     elif args.workload == "batch":
         run_batch(args)
     else:

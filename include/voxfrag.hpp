@@ -19,6 +19,7 @@ namespace voxfrag {
 struct uvec4 { uint32_t x, y, z, w; };
 struct uvec3 { uint32_t x, y, z; };
 struct ivec3 { int32_t x, y, z; };
+struct ivec2 { int32_t x, y; };
 struct vec3 { float x, y, z; };
 
 struct AABB {  // SRC/Geometry/3D/AABB.h: only min()/max()/size() are used on the path
@@ -322,6 +323,51 @@ inline std::string fractureModel(RegularGrid& grid, FractureParameters& fractPar
     seeds.resize(n);
     if (seedsOut) *seedsOut = seeds;
     return "";
+}
+
+// SRC/Graphics/Core/FragmentationProcedure.h:6-60 — the voxel-path fields, same names and defaults (the constructor's overrides of
+// FractureParameters included).
+struct FragmentationProcedure {
+    FractureParameters _fractureParameters;
+    ivec2 _fragmentInterval, _iterationInterval;
+    size_t _maxFragmentsModel;
+    std::string _startVessel = "", _searchExtension = ".obj";
+    bool _exportGrid;
+    bool _solidVoxelization = false;  // extension: Tetravoxelizer occupancy instead of the SAT surface occupancy
+    int _writerThreads = 2;           // extension: file writers beside the GPU loop
+
+    FragmentationProcedure()
+    {
+        vf_procedure p;
+        vf_procedure_default(&p);
+        _fractureParameters.from_c(p.fractureParameters);
+        _fragmentInterval = { p.fragmentInterval[0], p.fragmentInterval[1] };
+        _iterationInterval = { p.iterationInterval[0], p.iterationInterval[1] };
+        _maxFragmentsModel = p.maxFragmentsModel, _exportGrid = p.exportGrid != 0;
+    }
+    vf_procedure to_c() const
+    {
+        vf_procedure p;
+        vf_procedure_default(&p);
+        p.fractureParameters = _fractureParameters.to_c();
+        p.fragmentInterval[0] = _fragmentInterval.x, p.fragmentInterval[1] = _fragmentInterval.y;
+        p.iterationInterval[0] = _iterationInterval.x, p.iterationInterval[1] = _iterationInterval.y;
+        p.maxFragmentsModel = _maxFragmentsModel, p.exportGrid = _exportGrid, p.solidVoxelization = _solidVoxelization, p.writerThreads = _writerThreads;
+        return p;
+    }
+};
+
+// CADScene::generateDataset(fractureProcedure, folder, extension, destinationFolder) (CADScene.cpp:209-507), voxel path
+inline vf_dataset_stats generateDataset(Context& ctx, FragmentationProcedure& fractureProcedure, const std::string& folder, const std::string& extension,
+                                        const std::string& destinationFolder)
+{
+    vf_dataset_stats st{};
+    const vf_procedure p = fractureProcedure.to_c();
+    const vf_status s = vf_dataset_generate(ctx.handle(), &p, folder.c_str(), extension.c_str(), fractureProcedure._startVessel.c_str(), destinationFolder.c_str(), &st);
+    if (s == VF_ERR_SEEDER_EXHAUSTED) throw fracturer::Seeder::SeederSearchError(vf_last_error());
+    if (s == VF_ERR_IO && std::string(vf_last_error()).rfind("No files found", 0) == 0) throw std::runtime_error(vf_last_error());  // :213-214
+    check(s);
+    return st;
 }
 
 }  // namespace voxfrag

@@ -3,6 +3,7 @@
 // exportGrid(RLE).  Input: an .rle occupancy grid.  Prints an FNV-1a checksum of the labelled grid and the seed list so that
 // tests/test_cpp_mirror_gpu.py can compare it with the oracle.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iterator>
@@ -13,6 +14,18 @@ using namespace voxfrag;
 
 int main(int argc, char** argv)
 {
+    if (argc == 5 && std::strcmp(argv[1], "dataset") == 0) {
+        // main.cpp:37-39 in GENERATE_DATASET mode: FragmentationProcedure procedure; scene->generateDataset(procedure, folder, ext, dest)
+        Context ctx(0);
+        FragmentationProcedure procedure;
+        procedure._fragmentInterval = { 2, 3 }, procedure._iterationInterval = { 2, 1 };
+        procedure._fractureParameters._clampVoxelMetricUnit = procedure._fractureParameters._voxelPerMetricUnit = std::atoi(argv[4]);
+        ctx.initSeed(procedure._fractureParameters._seed);
+        const vf_dataset_stats st = generateDataset(ctx, procedure, argv[2], procedure._searchExtension, argv[3]);
+        std::printf("models %llu fragmentations %llu fragments %llu files %llu\n", (unsigned long long)st.models, (unsigned long long)st.fragmentations,
+                    (unsigned long long)st.fragments, (unsigned long long)st.files);
+        return 0;
+    }
     if (argc < 4) {
         std::fprintf(stderr, "usage: mirror_demo in.rle out_basename naive|flood\n");
         return 2;

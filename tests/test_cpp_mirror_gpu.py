@@ -55,3 +55,30 @@ def test_cpp_mirror_reference_call_sequence(orc, vessel_grid, tmp_path, algo):
     assert open(out + ".rle", "rb").read() == orc.encode_rle(want)
     assert int(lines[2].split()[1]) == int((want > 1).sum())
     assert got_hash != 0
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_generate_dataset(orc, tmp_path):
+    """voxfrag::generateDataset (the call main.cpp:37-39 makes) over a folder with one .obj: files == the oracle replay."""
+    from test_dataset_gpu import _replay
+
+    import voxelfragmentml_b200 as vf
+    from voxelfragmentml_b200 import dataset, synth
+
+    _build()
+    src = tmp_path / "in"
+    src.mkdir()
+    v, f = synth.vessel_mesh(3, n_ang=30, n_prof=14)
+    with open(src / "VS_77.obj", "w") as fh:
+        fh.write("".join(f"v {float(a)!r} {float(b)!r} {float(c)!r}\n" for a, b, c in v))
+        fh.write("".join(f"f {a + 1} {b + 1} {c + 1}\n" for a, b, c in f))
+    dest = str(tmp_path / "out") + "/"
+    p = subprocess.run([BIN, "dataset", str(src), dest, "36"], capture_output=True, text=True, check=True)
+    proc = vf.FragmentationProcedure(_fragmentInterval=(2, 3), _iterationInterval=(2, 1))
+    proc._fractureParameters._clampVoxelMetricUnit = 36
+    proc._fractureParameters._voxelPerMetricUnit = 36
+    v2, f2 = dataset.load_obj(str(src / "VS_77.obj"))
+    files, rows, generated, fragmentations, md, dims = _replay(orc, "VS_77", v2, f2, proc, orc.Rng(80))
+    for rel, want in files.items():
+        assert open(os.path.join(dest, rel), "rb").read() == want, rel
+    assert p.stdout.split() == ["models", "1", "fragmentations", str(fragmentations), "fragments", str(generated), "files", str(len(files) + 3)]
