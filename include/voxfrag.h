@@ -123,6 +123,8 @@ vf_status vf_ctx_timer_stop(vf_ctx* ctx, float* elapsed_ms);             /* sync
 
 /* ------------------------------------------------------------------ RNG (process-global in the reference, per context here) */
 vf_status vf_rng_seed(vf_ctx* ctx, uint32_t seed);                       /* RandomUtilities::initSeed, SRC/Utilities/RandomUtilities.h:86-89; CADScene.cpp:36-37 */
+vf_status vf_crand_seed(vf_ctx* ctx, uint32_t seed);                     /* srand(), CADScene.cpp:36 (vf_rng_seed does both, as :36-37 do) */
+int       vf_crand_next(vf_ctx* ctx);                                    /* rand() of the reference's C runtime (MSVC): state * 214013 + 2531011, bits 16..30 */
 float     vf_rng_uniform(vf_ctx* ctx);                                   /* RandomUtilities::getUniformRandom, :103-106 (libstdc++ float recipe, SURVEY finding 9) */
 uint32_t  vf_rng_raw(vf_ctx* ctx);
 vf_status vf_fill_noise(vf_ctx* ctx, float* noise, uint32_t n);          /* RegularGrid::fillNoiseBuffer, RegularGrid.cpp:238-244 (serial draw order) */
@@ -161,6 +163,10 @@ vf_status vf_voxelize_solid(vf_grid* g, const float* verts, uint32_t nv, const u
 vf_status vf_seed_uniform(vf_grid* g, uint32_t n, int random_mode, int location, uint32_t* seeds_out, uint32_t* attempts_out);
 /* Seeder::mergeSeeds (Seeder.cpp:115-152) — host only */
 vf_status vf_merge_seeds(const uint32_t* frags, uint32_t nfrags, uint32_t* seeds, uint32_t nseeds, int dfunc);
+/* Seeder::nearSeeds (Seeder.cpp:49-113): impact-biased boundary seeds around randomly chosen fragments; returns frags + the new seeds
+ * (labels continue after the last fragment's).  `out` may alias `frags`.  The offsets come from C rand() — the MSVC LCG, per context. */
+vf_status vf_seed_near(vf_grid* g, const uint32_t* frags, uint32_t nfrags, uint32_t num_impacts, uint32_t num_seeds, uint32_t spreading,
+                       uint32_t* out, uint32_t capacity, uint32_t* count_out);
 /* seed block of CADScene::fractureModel (CADScene.cpp:626-655, numImpacts == 0): returns n or n + n + n_extra seeds */
 vf_status vf_make_seeds(vf_grid* g, uint32_t n, uint32_t n_extra, int random_mode, int merge_dfunc, uint32_t* seeds_out,
                         uint32_t capacity, uint32_t* count_out);
@@ -224,7 +230,7 @@ vf_status vf_synth_solid_vessel(vf_grid* g, int x_offset, uint32_t n, float base
 
 /* ------------------------------------------------------------------ the caller's block: CADScene::fractureModel */
 /* CADScene.cpp:624-691: seeds -> Fracturer::build -> erode | detectBoundaries(1).  seeds_out (optional, capacity
- * numSeeds*2+numExtraSeeds entries of uint32[4]) receives the seed list used. */
+ * (numSeeds [+ biasSeeds when numImpacts > 0]) * 2 + numExtraSeeds entries of uint32[4]) receives the seed list used. */
 vf_status vf_fracture_model(vf_grid* g, const vf_params* p, uint32_t* seeds_out, uint32_t* nseeds_out, vf_flood_stats* stats);
 
 /* ------------------------------------------------------------------ f1: the dataset driver (CADScene::generateDataset, CADScene.cpp:209-507) */

@@ -301,6 +301,18 @@ public:
         check(s);
         return out;
     }
+    // nearSeeds(grid, frags, numImpacts, numSeeds, spreading), Seeder.h:62-64
+    static std::vector<uvec4> nearSeeds(const RegularGrid& grid, const std::vector<uvec4>& frags, unsigned numImpacts, unsigned numSeeds, unsigned spreading)
+    {
+        std::vector<uvec4> out(frags.size() + numSeeds);
+        uint32_t n = 0;
+        const vf_status s = vf_seed_near(grid.handle(), reinterpret_cast<const uint32_t*>(frags.data()), (uint32_t)frags.size(), numImpacts, numSeeds, spreading,
+                                         reinterpret_cast<uint32_t*>(out.data()), (uint32_t)out.size(), &n);
+        if (s == VF_ERR_SEEDER_EXHAUSTED) throw SeederSearchError(vf_last_error());
+        check(s);
+        out.resize(n);
+        return out;
+    }
     static void mergeSeeds(const std::vector<uvec4>& frags, std::vector<uvec4>& seeds, DistanceFunction dfunc)
     {
         check(vf_merge_seeds(reinterpret_cast<const uint32_t*>(frags.data()), (uint32_t)frags.size(), reinterpret_cast<uint32_t*>(seeds.data()), (uint32_t)seeds.size(), (int)dfunc));

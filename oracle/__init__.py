@@ -82,6 +82,9 @@ def _declare(L):
     L.orc_merge_seeds.argtypes = [_u32p, C.c_uint32, _u32p, C.c_uint32, C.c_int]
     L.orc_make_seeds.restype = C.c_int
     L.orc_make_seeds.argtypes = [C.c_void_p, _u16p, _u32p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, _u32p, C.c_uint32]
+    L.orc_near_seeds.restype = C.c_int
+    L.orc_near_seeds.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32), _u16p, _u32p, _u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                 _u32p, C.c_uint32]
     L.orc_naive.argtypes = [_u16p, _u32p, _u32p, C.c_uint32, C.c_int, C.c_int]
     L.orc_flood.restype = C.c_int
     L.orc_flood.argtypes = [_u16p, _u32p, _u32p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(FloodStats)]
@@ -235,6 +238,17 @@ def make_seeds(rng: Rng, grid, n, n_extra=0, mode=STD_UNIFORM, merge_dfunc=EUCLI
     if rc < 0:
         raise OracleError(rc, "make_seeds")
     return out[:rc]
+
+
+def near_seeds(rng: Rng, grid, frags, num_impacts, num_seeds, spreading, crand_state=80, crand_mode=0):
+    """Seeder::nearSeeds; returns (seeds, crand_state afterwards).  crand_mode 0 = MSVC LCG (the reference's platform), 1 = libc rand()."""
+    frags = _seeds(frags)
+    out = np.zeros((len(frags) + num_seeds, 4), dtype=np.uint32)
+    st = C.c_uint32(crand_state)
+    rc = lib().orc_near_seeds(rng._h, crand_mode, C.byref(st), grid, _dims(grid), frags, len(frags), num_impacts, num_seeds, spreading, out, len(out))
+    if rc < 0:
+        raise OracleError(rc, "near_seeds")
+    return out[:rc], int(st.value)
 
 
 def naive(grid, seeds, dfunc=EUCLIDEAN, decode_mode=0):

@@ -87,6 +87,18 @@ float ref_halton(unsigned dimension, unsigned index)
     return sampler.sample(dimension, index);
 }
 
+// Seeder::nearSeeds (Seeder.cpp:49-113) as it is; consumes RandomUtilities' generator and this process's ::rand()
+int ref_near_seeds(uint16_t* grid, const uint32_t dims[3], const uint32_t* frags, uint32_t nfrags, unsigned numImpacts, unsigned numSeeds, unsigned spreading,
+                   int rng_seed, unsigned crand_seed, uint32_t* out)
+{
+    RegularGrid g(grid, uvec3(dims[0], dims[1], dims[2]));
+    RandomUtilities::initSeed(rng_seed);
+    srand(crand_seed);
+    std::vector<glm::uvec4> s = fracturer::Seeder::nearSeeds(g, to_seeds(frags, nfrags), numImpacts, numSeeds, spreading);
+    for (uint32_t i = 0; i < s.size(); ++i) out[4 * i] = s[i].x, out[4 * i + 1] = s[i].y, out[4 * i + 2] = s[i].z, out[4 * i + 3] = s[i].w;
+    return (int)s.size();
+}
+
 void ref_merge_seeds(const uint32_t* frags, uint32_t nfrags, uint32_t* seeds, uint32_t nseeds, int dfunc)
 {
     std::vector<glm::uvec4> s = to_seeds(seeds, nseeds);

@@ -12,6 +12,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <map>
@@ -574,6 +575,68 @@ extern "C" int orc_make_seeds(orc_rng* rng, const uint16_t* grid, const uint32_t
         orc_merge_seeds(out, n, extra.data(), n + n_extra, merge_dfunc); /* :653 */
         std::memcpy(out + 4 * n, extra.data(), 16 * (size_t)(n + n_extra)); /* :654 */
     }
+    return (int)total;
+}
+
+/* ---- S3: Seeder::nearSeeds (Seeder.cpp:49-113): impact-biased seeds.  Two generators are involved: RandomUtilities' mt19937 picks the
+ * impacted fragment and the seed count per impact (:67-68), and C rand() drives getBiasedRandomInt (RandomUtilities.h:146-156),
+ * seeded by srand(_fractParameters._seed) at CADScene.cpp:36.  rand() is the C runtime's: the reference is an MSVC program, whose
+ * rand() is the documented LCG  state = state * 214013 + 2531011; return (state >> 16) & 0x7fff  (crand_mode 0, *crand_state is
+ * the LCG word).  crand_mode 1 calls this process's ::rand() instead, which lets the test pin every other line of the function
+ * against the reference's own Seeder.cpp compiled in place (both then consume the same glibc stream).
+ * The reference loops without bound when no candidate qualifies; the restatement gives up after 1e6 candidates per impact. */
+namespace {
+inline int crand_next(int mode, uint32_t* state)
+{
+    if (mode == 1) return std::rand();
+    *state = *state * 214013u + 2531011u;
+    return (int)((*state >> 16) & 0x7fffu);
+}
+}  // namespace
+
+extern "C" int orc_near_seeds(orc_rng* rng, int crand_mode, uint32_t* crand_state, const uint16_t* grid, const uint32_t dims[3], const uint32_t* frags,
+                              uint32_t nfrags, uint32_t numImpacts, uint32_t numSeeds, uint32_t spreading, uint32_t* out, uint32_t cap)
+{
+    if (!nfrags || !spreading) return ORC_ERR_UNSUPPORTED;
+    for (int q = 0; q < 3; ++q)
+        if ((int)dims[q] / (int)spreading == 0) return ORC_ERR_UNSUPPORTED; /* rand() % 0 in getBiasedRandomInt */
+    std::set<std::array<uint32_t, 3>> seeds; /* lexicographic comparator, :52-59 */
+    unsigned numPendingSeeds = numSeeds;
+    const uint32_t half[3] = { dims[0] / 2, dims[1] / 2, dims[2] / 2 };
+    const unsigned minDiv = std::min(dims[0], std::min(dims[1], dims[2])) / 2;
+    auto biased = [&](int mx) { /* RandomUtilities.h:146-156 with min = 0 */
+        int number = 0;
+        mx /= (int)spreading;
+        for (uint32_t i = 0; i < spreading; ++i) number += crand_next(crand_mode, crand_state) % mx;
+        return number;
+    };
+    for (uint32_t idx = 0; idx < numImpacts; ++idx) {
+        const uint32_t* frag = frags + 4 * (size_t)orc_rng_uniform_int(rng, 0, (int)nfrags - 1);
+        const unsigned nseeds = (unsigned)orc_rng_uniform_int(rng, 1, (int)numPendingSeeds);
+        unsigned currentSeeds = 0;
+        uint64_t tries = 0;
+        while (currentSeeds != nseeds) {
+            if (++tries > 1000000) return ORC_ERR_SEEDER_EXHAUSTED;
+            int x = (int)(half[0] - (uint32_t)biased((int)dims[0]));
+            int y = (int)(half[1] - (uint32_t)biased((int)dims[1]));
+            int z = (int)(half[2] - (uint32_t)biased((int)dims[2]));
+            x = (int)((frag[0] + (uint32_t)x + dims[0]) % dims[0]);
+            y = (int)((frag[1] + (uint32_t)y + dims[1]) % dims[1]);
+            z = (int)((frag[2] + (uint32_t)z + dims[2]) % dims[2]);
+            const float dx = (float)x - (float)frag[0], dy = (float)y - (float)frag[1], dz = (float)z - (float)frag[2];
+            if (std::sqrt(dx * dx + dy * dy + dz * dz) > (float)minDiv) continue; /* :87 */
+            const bool occupied = grid[lin(x, y, z, dims)] != ORC_VOXEL_EMPTY;
+            const bool isFree = seeds.find({ (uint32_t)x, (uint32_t)y, (uint32_t)z }) == seeds.end();
+            const bool isBoundary = grid_is_boundary(grid, dims, x, y, z);
+            if (occupied && isFree && isBoundary) seeds.insert({ (uint32_t)x, (uint32_t)y, (uint32_t)z }), ++currentSeeds;
+        }
+        numPendingSeeds -= nseeds;
+    }
+    const uint32_t total = nfrags + (uint32_t)seeds.size();
+    if (total > cap) return ORC_ERR_CAPACITY;
+    std::memcpy(out, frags, 16 * (size_t)nfrags); /* :103 result = frags */
+    uint32_t nseed = frags[4 * (size_t)(nfrags - 1) + 3], k = nfrags;
+    for (const auto& sd : seeds) out[4 * k] = sd[0], out[4 * k + 1] = sd[1], out[4 * k + 2] = sd[2], out[4 * k + 3] = ++nseed, ++k;
     return (int)total;
 }
 

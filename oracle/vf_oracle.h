@@ -87,6 +87,9 @@ void orc_merge_seeds(const uint32_t* frags, uint32_t nfrags, uint32_t* seeds, ui
 /* CADScene.cpp:626-655 call pattern: returns total seed count written to out (n + (n_extra? n + n_extra : 0)) */
 int orc_make_seeds(orc_rng*, const uint16_t* grid, const uint32_t dims[3], uint32_t n, uint32_t n_extra,
                    int random_mode, int merge_dfunc, uint32_t* out_seeds, uint32_t out_capacity);
+/* S3: Seeder::nearSeeds (Seeder.cpp:49-113); crand_mode 0 = MSVC rand() LCG on *crand_state, 1 = this process's ::rand() */
+int orc_near_seeds(orc_rng* rng, int crand_mode, uint32_t* crand_state, const uint16_t* grid, const uint32_t dims[3], const uint32_t* frags,
+                   uint32_t nfrags, uint32_t numImpacts, uint32_t numSeeds, uint32_t spreading, uint32_t* out, uint32_t cap);
 
 /* ---- F1: naive — SRC/Fracturer/NaiveFracturer.cpp:26-68; SH/Fracturer/naiveFracturer-comp.glsl:19-43 ---- */
 void orc_naive(uint16_t* grid, const uint32_t dims[3], const uint32_t* seeds, uint32_t nseeds, int dfunc, int decode_mode);

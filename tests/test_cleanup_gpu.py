@@ -257,3 +257,33 @@ def test_device_rle_encoder_matches_oracle(ctx, orc, labelled_vessel):
         assert g._lib.vf_grid_encode_rle(g._h, small.ctypes.data, 8, C.byref(need)) == 0
         assert need.value == len(want) and not small.any()
         g.close()
+
+
+def test_near_seeds_and_fracture_model_with_impacts(ctx, orc, vessel_grid):
+    """S3: Seeder::nearSeeds on the device-resident grid == the oracle (MSVC rand() LCG + mt19937), including both generators'
+    positions afterwards; then CADScene::fractureModel with _numImpacts > 0 (uniform -> nearSeeds -> extra seeds -> flood)."""
+    import voxelfragmentml_b200 as vf
+
+    g = _grid(ctx, vessel_grid)
+    frags = pick_seeds(vessel_grid, 6, 5)
+    for impacts, nseeds, spreading, seed in [(1, 12, 5, 80), (3, 20, 3, 7), (2, 2, 8, 11)]:
+        ctx.initSeed(seed)
+        got = vf.Seeder.nearSeeds(g, frags, impacts, nseeds, spreading)
+        r = orc.Rng(seed)
+        want, st = orc.near_seeds(r, vessel_grid, frags, impacts, nseeds, spreading, crand_state=seed)
+        assert np.array_equal(got, want)
+        assert ctx._lib.vf_crand_next(ctx._h) == (((st * 214013 + 2531011) & 0xFFFFFFFF) >> 16) & 0x7FFF
+        assert ctx.getUniformRandom() == r.uniform()
+    p = vf.FractureParameters(_numSeeds=5, _numExtraSeeds=10, _numImpacts=2, _biasSeeds=9, _biasFocus=4)
+    ctx.initSeed(80)
+    seeds, _ = vf.fracture_model(g, p)
+    r = orc.Rng(80)
+    s0, _ = orc.seed_uniform(r, vessel_grid, 5)
+    s1, _ = orc.near_seeds(r, vessel_grid, s0, 2, 9, 4, crand_state=80)
+    extra, _ = orc.seed_uniform(r, vessel_grid, 10, location=orc.BOTH)
+    merged = orc.merge_seeds(s1, np.concatenate([s1, extra]), 0)
+    wseeds = np.concatenate([s1, merged])
+    assert np.array_equal(seeds, wseeds)
+    want, _ = orc.flood(vessel_grid.copy(), wseeds, orc.CHEBYSHEV)
+    assert np.array_equal(g.updateGrid(), orc.detect_boundaries(want, 1))
+    g.close()

@@ -431,3 +431,30 @@ def test_sat_voxelize_plane(orc):
     g2 = orc.voxelize_sat(verts, faces, [-0.5] * 3, [0.5] * 3, (16, 16, 16))
     assert np.array_equal(g, g2)
     assert (margin[g == 1] < 1e30).all()
+
+
+def test_msvc_rand_known_answers(orc):
+    """The C runtime rand() of the reference's platform: the first values after srand(1) are 41, 18467, 6334, 26500, 19169, 15724
+    (the sequence every MSVC program prints); the oracle's crand_mode 0 must walk exactly that LCG."""
+    state, got = 1, []
+    for _ in range(6):
+        state = (state * 214013 + 2531011) & 0xFFFFFFFF
+        got.append((state >> 16) & 0x7FFF)
+    assert got == [41, 18467, 6334, 26500, 19169, 15724]
+    # one impact, one seed, spreading 1 on a 6^3 block inside an 8^3 grid: three rand() draws per candidate
+    g = np.zeros((8, 8, 8), np.uint16)
+    g[1:7, 1:7, 1:7] = 1
+    frags = np.uint32([[4, 4, 4, 2]])
+    seeds, st = orc.near_seeds(orc.Rng(80), g, frags, 1, 1, 1, crand_state=1)
+    # candidates until one is an occupied cell next to an EMPTY one (a face cell of the block): replay by hand
+    state, tries = 1, 0
+    while True:
+        c = []
+        for d in range(3):
+            state = (state * 214013 + 2531011) & 0xFFFFFFFF
+            c.append((4 + (4 - ((state >> 16) & 0x7FFF) % 8) + 8) % 8)
+        tries += 1
+        far = np.sqrt(np.float32(sum((a - 4) ** 2 for a in c))) > 4
+        if not far and all(1 <= a <= 6 for a in c) and (1 in c or 6 in c):
+            break
+    assert seeds.tolist() == [[4, 4, 4, 2], c + [3]] and st == state and tries >= 1

@@ -216,3 +216,20 @@ def test_qstack_random_grids_match_reference_quadstack(orc, tmp_path):
             g[:] = rs.randint(0, 3, size=(1, 1, shape[2]))
             g[shape[0] // 2:, :, ::2] = 4
         assert orc.encode_qstack(g) == ref_qstack_bytes(g, str(tmp_path)), (i, shape)
+
+
+def test_near_seeds_matches_reference_seeder(ref, orc, vessel_grid):
+    """Seeder::nearSeeds compiled in place vs the oracle in crand_mode 1 (both consume this process's ::rand() after srand(seed) and
+    RandomUtilities' generator after initSeed): identical seed lists, so everything but the C runtime's rand() itself is pinned."""
+    libc = C.CDLL(None)
+    ref.ref_near_seeds.restype = C.c_int
+    ref.ref_near_seeds.argtypes = [_u16, _u32, _u32, C.c_uint32, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_uint, _u32]
+    for grid, nfr in [(vessel_grid.astype(np.uint16), 6), ((random_blob_grid((40, 36, 44), 3) != 0).astype(np.uint16), 4)]:
+        frags = pick_seeds(grid, nfr, 5)
+        for impacts, nseeds, spreading, seed in [(1, 12, 5, 80), (3, 20, 3, 7), (2, 2, 8, 11)]:
+            out = np.zeros((nfr + nseeds, 4), np.uint32)
+            n = ref.ref_near_seeds(grid.copy(), _dims(grid), frags, nfr, impacts, nseeds, spreading, seed, seed, out)
+            libc.srand(seed)
+            mine, _ = orc.near_seeds(orc.Rng(seed), grid, frags, impacts, nseeds, spreading, crand_mode=1)
+            assert n == len(mine) and np.array_equal(out[:n], mine), (impacts, nseeds, spreading)
+            assert n > nfr

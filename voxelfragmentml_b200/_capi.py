@@ -66,6 +66,9 @@ SIGNATURES = {
     "vf_ctx_timer_start": (C.c_int, [_vp]),
     "vf_ctx_timer_stop": (C.c_int, [_vp, _f32p]),
     "vf_rng_seed": (C.c_int, [_vp, _u32]),
+    "vf_crand_seed": (C.c_int, [_vp, _u32]),
+    "vf_crand_next": (C.c_int, [_vp]),
+    "vf_seed_near": (C.c_int, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _u32, C.POINTER(_u32)]),
     "vf_rng_uniform": (C.c_float, [_vp]),
     "vf_rng_raw": (C.c_uint32, [_vp]),
     "vf_fill_noise": (C.c_int, [_vp, _vp, _u32]),

@@ -313,6 +313,15 @@ class Seeder:
         return s
 
     @staticmethod
+    def nearSeeds(grid: RegularGrid, frags, numImpacts: int, numSeeds: int, spreading: int):
+        """Seeder::nearSeeds (Seeder.cpp:49-113): frags + impact-biased boundary seeds (C rand() = the MSVC LCG kept by the context)."""
+        f = _seed_array(frags)
+        out = np.zeros((len(f) + int(numSeeds), 4), dtype=np.uint32)
+        cnt = C.c_uint32(0)
+        check(grid._lib.vf_seed_near(grid._h, ptr(f), len(f), int(numImpacts), int(numSeeds), int(spreading), ptr(out), len(out), C.byref(cnt)))
+        return out[: cnt.value]
+
+    @staticmethod
     def make(grid: RegularGrid, numSeeds: int, numExtraSeeds: int = 0, randomSeedFunction=RandomUniformType.STD_UNIFORM,
              mergeDFunc=DistanceFunction.EUCLIDEAN):
         """Seed block of CADScene::fractureModel (CADScene.cpp:626-655)."""
@@ -379,7 +388,7 @@ class FloodFracturer(_Fracturer):
 
 def fracture_model(grid: RegularGrid, params: FractureParameters):
     """CADScene::fractureModel (CADScene.cpp:624-691): seeds -> build -> erode | detectBoundaries(1).  Returns (seeds, stats)."""
-    cap = params._numSeeds * 2 + params._numExtraSeeds
+    cap = (params._numSeeds + (max(params._biasSeeds, 0) if params._numImpacts > 0 else 0)) * 2 + params._numExtraSeeds
     seeds = np.zeros((cap, 4), dtype=np.uint32)
     n = C.c_uint32(0)
     st = VfFloodStats()

@@ -181,7 +181,19 @@ extern "C" vf_status vf_rng_seed(vf_ctx* ctx, uint32_t seed)
 {
     VF_REQUIRE(ctx != nullptr, VF_ERR_INVALID_ARGUMENT, "null context");
     ctx->rng.seed(seed);
+    ctx->crand = seed;  // CADScene.cpp:36 srand(_fractParameters._seed) next to :37 RandomUtilities::initSeed
     return VF_OK;
+}
+extern "C" vf_status vf_crand_seed(vf_ctx* ctx, uint32_t seed)
+{
+    VF_REQUIRE(ctx != nullptr, VF_ERR_INVALID_ARGUMENT, "null context");
+    ctx->crand = seed;
+    return VF_OK;
+}
+extern "C" int vf_crand_next(vf_ctx* ctx)
+{
+    ctx->crand = ctx->crand * 214013u + 2531011u;  // the MSVC runtime's rand()
+    return (int)((ctx->crand >> 16) & 0x7fffu);
 }
 extern "C" float vf_rng_uniform(vf_ctx* ctx) { return ctx->rng.uniform(); }
 extern "C" uint32_t vf_rng_raw(vf_ctx* ctx) { return ctx->rng.next(); }

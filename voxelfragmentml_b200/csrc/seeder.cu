@@ -8,6 +8,7 @@
 // consumed even when rejected), a small kernel evaluates isOccupied / isBoundary (RegularGrid.cpp:543-564) for a batch of
 // candidates, and the host replays the acceptance rule on the flags.  When the n-th seed is found mid-batch the generator is
 // rewound to the state the reference's would have, so everything drawn afterwards (extra seeds, erosion noise) matches.
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -141,6 +142,84 @@ extern "C" vf_status vf_seed_uniform(vf_grid* g, uint32_t n, int random_mode, in
     return VF_OK;
 }
 
+// Seeder::nearSeeds (Seeder.cpp:49-113): numImpacts impacts, each on a fragment drawn from `frags`, each adding a random share of
+// numSeeds (= _biasSeeds) boundary cells around it; the offsets come from RandomUtilities::getBiasedRandomInt (RandomUtilities.h:
+// 146-156), i.e. from the C runtime's rand() — the MSVC LCG on the reference's platform, kept per context (vf_crand_seed).
+// As in vf_seed_uniform the host draws the candidates in the reference's order, a kernel evaluates isOccupied / isBoundary for a
+// batch, and the host replays the acceptance rule; the LCG is put back to the state it had after the accepted candidate.
+// The reference's search loop has no bound; this one gives up after 1e6 candidates per impact (VF_ERR_SEEDER_EXHAUSTED).
+extern "C" vf_status vf_seed_near(vf_grid* g, const uint32_t* frags, uint32_t nfrags, uint32_t num_impacts, uint32_t num_seeds, uint32_t spreading,
+                                  uint32_t* out, uint32_t capacity, uint32_t* count_out)
+{
+    VF_REQUIRE(g && frags && out && count_out, VF_ERR_INVALID_ARGUMENT, "null argument");
+    VF_REQUIRE(nfrags > 0 && spreading > 0, VF_ERR_INVALID_ARGUMENT, "nearSeeds needs fragments and a positive spreading");
+    vf_ctx* c = g->ctx;
+    VF_TRY(vf_enter(c));
+    const uint32_t dims[3] = { g->X, g->Y, g->Z };
+    for (int q = 0; q < 3; ++q) VF_REQUIRE(dims[q] / spreading > 0, VF_ERR_INVALID_ARGUMENT, "spreading %u exceeds a grid dimension (rand() %% 0 in the reference)", spreading);
+    VF_TRY(vf_scratch_reserve(c, c->small, 1 << 20));
+    ushort4* d_cand = (ushort4*)((char*)c->small.ptr + (768 << 10));
+    uint8_t* d_flags = (uint8_t*)(d_cand + kBatch);
+    ushort4* h_cand = (ushort4*)c->pinned;
+    uint8_t* h_flags = (uint8_t*)c->pinned + 65536;
+    std::vector<uint32_t> after(kBatch);  // LCG word after each candidate of the batch
+
+    std::set<U3> seeds;
+    unsigned numPendingSeeds = num_seeds;
+    const uint32_t half[3] = { dims[0] / 2, dims[1] / 2, dims[2] / 2 };
+    const float minDiv = (float)(std::min(dims[0], std::min(dims[1], dims[2])) / 2);
+    auto biased = [&](uint32_t dim) {
+        int number = 0;
+        const int mx = (int)dim / (int)spreading;
+        for (uint32_t i = 0; i < spreading; ++i) number += vf_crand_next(c) % mx;
+        return (uint32_t)number;
+    };
+    for (uint32_t impact = 0; impact < num_impacts; ++impact) {
+        const uint32_t* frag = frags + 4 * (size_t)c->rng.uniform_int(0, (int)nfrags - 1);  // :67
+        const unsigned nseeds = (unsigned)c->rng.uniform_int(1, (int)numPendingSeeds);       // :68
+        unsigned currentSeeds = 0;
+        uint64_t tries = 0;
+        while (currentSeeds != nseeds) {
+            VF_REQUIRE(tries < kMaxTries, VF_ERR_SEEDER_EXHAUSTED, "nearSeeds: no boundary cell near fragment (%u, %u, %u) after %u candidates", frag[0], frag[1],
+                       frag[2], kMaxTries);
+            VF_CUDA(cudaStreamSynchronize(c->stream));
+            for (int i = 0; i < kBatch; ++i) {  // :74-83
+                const uint32_t x = (frag[0] + (half[0] - biased(dims[0])) + dims[0]) % dims[0];
+                const uint32_t y = (frag[1] + (half[1] - biased(dims[1])) + dims[1]) % dims[1];
+                const uint32_t z = (frag[2] + (half[2] - biased(dims[2])) + dims[2]) % dims[2];
+                h_cand[i] = make_ushort4((unsigned short)x, (unsigned short)y, (unsigned short)z, 0);
+                after[i] = c->crand;
+            }
+            VF_CUDA(cudaMemcpyAsync(d_cand, h_cand, kBatch * sizeof(ushort4), cudaMemcpyHostToDevice, c->stream));
+            seed_probe_kernel<<<(kBatch + 127) / 128, 128, 0, c->stream>>>(g->d, (int)g->X, (int)g->Y, (int)g->Z, d_cand, kBatch, d_flags);
+            VF_LAUNCHED(c);
+            VF_CUDA(cudaMemcpyAsync(h_flags, d_flags, kBatch, cudaMemcpyDeviceToHost, c->stream));
+            VF_CUDA(cudaStreamSynchronize(c->stream));
+            for (int i = 0; i < kBatch; ++i) {
+                const U3 v = { h_cand[i].x, h_cand[i].y, h_cand[i].z };
+                const float dx = (float)v.x - (float)frag[0], dy = (float)v.y - (float)frag[1], dz = (float)v.z - (float)frag[2];
+                if (sqrtf(dx * dx + dy * dy + dz * dz) > minDiv) continue;  // :87
+                if ((h_flags[i] & 1) && (h_flags[i] & 2) && seeds.find(v) == seeds.end()) {
+                    seeds.insert(v);
+                    if (++currentSeeds == nseeds) {
+                        c->crand = after[i];
+                        break;
+                    }
+                }
+            }
+            tries += kBatch;
+        }
+        numPendingSeeds -= nseeds;
+    }
+    const uint32_t total = nfrags + (uint32_t)seeds.size();
+    VF_REQUIRE(total <= capacity, VF_ERR_CAPACITY, "nearSeeds: %u seeds do not fit the output (%u)", total, capacity);
+    if (out != frags) std::memmove(out, frags, 16 * (size_t)nfrags);  // :103 result = frags
+    uint32_t nseed = out[4 * (size_t)(nfrags - 1) + 3], k = nfrags;
+    for (const U3& s : seeds) out[4 * k] = s.x, out[4 * k + 1] = s.y, out[4 * k + 2] = s.z, out[4 * k + 3] = ++nseed, ++k;
+    *count_out = total;
+    return VF_OK;
+}
+
 extern "C" vf_status vf_merge_seeds(const uint32_t* frags, uint32_t nfrags, uint32_t* seeds, uint32_t nseeds, int dfunc)
 {
     // Seeder.cpp:115-152, float32 distances on integer coordinates, strict '<' (lowest fragment index wins ties)
@@ -190,12 +269,23 @@ extern "C" vf_status vf_fracture_model(vf_grid* g, const vf_params* p, uint32_t*
     VF_REQUIRE(g && p, VF_ERR_INVALID_ARGUMENT, "null argument");
     vf_ctx* c = g->ctx;
     VF_TRY(vf_enter(c));
-    VF_REQUIRE(p->numImpacts == 0, VF_ERR_UNSUPPORTED, "nearSeeds (numImpacts > 0) uses C rand(): parity-unpinned, not implemented (SURVEY §8a S3)");
-    VF_REQUIRE(p->numSeeds > 0 && p->numExtraSeeds >= 0, VF_ERR_INVALID_ARGUMENT, "bad seed counts");
-    const uint32_t cap = (uint32_t)p->numSeeds * 2 + (uint32_t)p->numExtraSeeds;
+    VF_REQUIRE(p->numSeeds > 0 && p->numExtraSeeds >= 0 && p->numImpacts >= 0, VF_ERR_INVALID_ARGUMENT, "bad seed counts");
+    // seeds = uniform(OUTER) [-> nearSeeds] (:629-639); with extra seeds: [originals..., copies of the originals..., extras...] (:647-655)
+    const uint32_t nmax = (uint32_t)p->numSeeds + (p->numImpacts > 0 ? (uint32_t)std::max(p->biasSeeds, 0) : 0u);
+    const uint32_t cap = nmax * 2 + (uint32_t)p->numExtraSeeds;
     std::vector<uint32_t> seeds(4 * (size_t)cap);
-    uint32_t ns = 0;
-    VF_TRY(vf_make_seeds(g, (uint32_t)p->numSeeds, (uint32_t)p->numExtraSeeds, p->seedingRandom, p->mergeSeedsDistanceFunction, seeds.data(), cap, &ns));
+    uint32_t ns = (uint32_t)p->numSeeds;
+    VF_TRY(vf_seed_uniform(g, ns, p->seedingRandom, VF_OUTER, seeds.data(), nullptr));
+    if (p->numImpacts > 0) VF_TRY(vf_seed_near(g, seeds.data(), ns, (uint32_t)p->numImpacts, (uint32_t)p->biasSeeds, (uint32_t)p->biasFocus, seeds.data(), nmax, &ns));
+    if (p->numExtraSeeds > 0) {
+        const uint32_t ne = (uint32_t)p->numExtraSeeds;
+        std::vector<uint32_t> extra(4 * (size_t)(ns + ne));
+        VF_TRY(vf_seed_uniform(g, ne, p->seedingRandom, VF_BOTH, extra.data() + 4 * (size_t)ns, nullptr));
+        std::memcpy(extra.data(), seeds.data(), 16 * (size_t)ns);
+        VF_TRY(vf_merge_seeds(seeds.data(), ns, extra.data(), ns + ne, p->mergeSeedsDistanceFunction));
+        std::memcpy(seeds.data() + 4 * (size_t)ns, extra.data(), 16 * (size_t)(ns + ne));
+        ns += ns + ne;
+    }
     if (p->fractureAlgorithm == VF_NAIVE) {
         VF_REQUIRE(p->distanceFunction >= 0 && p->distanceFunction <= 2, VF_ERR_INVALID_DISTANCE, "Invalid distance function");  // CADScene.cpp:665
         VF_TRY(vf_fracture_naive(g, seeds.data(), ns, p->distanceFunction));

@@ -92,6 +92,7 @@ struct vf_ctx {
     uint64_t launches = 0;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     VfMt19937 rng;
+    uint32_t crand = 80;  // state of the C runtime's rand() as the reference's platform implements it (MSVC LCG); srand(_seed), CADScene.cpp:36
     // scratch arenas, grown on demand (FloodFracturer.cpp:116-120 "grown on demand")
     VfScratch keys;      // flood: 4 B / voxel (dist<<15 | order)
     VfScratch grid2;     // second label grid (erode destination, snapshot sweeps): 2 B / voxel
