@@ -328,6 +328,15 @@ def run_cuda(args):
                 "serial_ms_per_step": serial_s * 1e3, "serial_value": world * N / serial_s / 1e9},
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    if not args.no_batch:
+        # BASELINE.json's second metric (cfg4, models/s), measured briefly beside the headline: 32 meshes per GPU
+        jobs = args.jobs or default_jobs(world)
+        bm = 32 * world
+        bdt, _, npool = batch_measure(rank, local_rank, world, dist if world > 1 else None, bm, 2, jobs, 4)
+        out["batch"] = {"metric": "models/s batch voxelize+fragment", "value": bm / bdt, "unit": "models/s", "meshes": bm, "jobs_per_gpu": jobs,
+                        "fragmentations_per_s": bm * 10 / bdt, "scaling": "weak",
+                        "workload": f"cfg4-batch: {bm} synthetic vessels (pool of {npool} shapes) x 10 fragmentations at 256-max, FLOOD CHEBYSHEV, nf 2..10, "
+                                    "2*nf extra seeds; full-size run: bench.py --workload batch --meshes 1024"}
     if rank == 0 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args.cpu_size or 512, stages_run)
     if rank == 0:
@@ -477,27 +486,40 @@ def run_slab(args):
         dist.destroy_process_group()
 
 
-def run_batch(args):
+def default_jobs(world):
+    """concurrent contexts per GPU for the batch workload: enough to fill the SMs (8), within the host cores this rank may use"""
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    return max(1, min(8, cores // max(1, world)))
+
+
+def batch_measure(rank, local_rank, world, dist, meshes, warmup, jobs, mesh_pool):
     """BASELINE config 4: dataset generation — per mesh: SAT voxelization at 256-max, then 10 fragmentations with the reference's
     dataset defaults (FLOOD + CHEBYSHEV, numSeeds = nf cycling 2..10, numExtraSeeds = 2 nf, detectBoundaries, histogram, undoMask;
     CADScene.cpp:294-332, FragmentationProcedure.h:12-13).  Mesh m goes to rank m mod N with RNG seed 80 + m, so results do not
-    depend on N.  No collective on the data path."""
+    depend on N.  No collective on the data path.  A flood round of a 256-max shell keeps ~170 tiles busy — a fraction of one B200 —
+    so every rank drives `jobs` contexts (one CUDA stream and one host thread each; ctypes releases the GIL inside a call): the
+    latency-bound rounds of different meshes overlap on the SMs.  Results do not depend on `jobs` either (per-mesh RNG stream).
+    Returns (seconds for all meshes: max over ranks, checksum of this rank, number of distinct shapes)."""
+    import threading
+
     import torch
 
     import voxelfragmentml_b200 as vf
     from voxelfragmentml_b200 import synth
 
-    rank, local_rank, world, dist = _dist_setup()
-    ctx = vf.Context(local_rank)
-    pool = [synth.vessel_mesh(i) for i in range(args.mesh_pool)]  # distinct shapes, generated once outside the timed region
+    pool = [synth.vessel_mesh(i) for i in range(mesh_pool)]  # distinct shapes, generated once outside the timed region
     lib = vf._capi.load()
-    grid = vf.RegularGrid(ctx, (256, 256, 256))  # allocated once at the clamp size, re-dimensioned per model (CADScene.cpp:529-543)
-    ctx.reserve((256, 256, 256))
-    my = [m for m in range(args.meshes) if m % world == rank]
-    checksum = 0
+    my = [m for m in range(meshes) if m % world == rank]
+    checksums = [0] * jobs
+    workers = []
+    for j in range(jobs):
+        ctx = vf.Context(local_rank)
+        grid = vf.RegularGrid(ctx, (256, 256, 256))  # allocated once at the clamp size, re-dimensioned per model (CADScene.cpp:529-543)
+        ctx.reserve((256, 256, 256))
+        workers.append((ctx, grid))
 
-    def one_mesh(m):
-        nonlocal checksum
+    def one_mesh(j, m):
+        ctx, grid = workers[j]
         v, f = pool[m % len(pool)]
         mn, mx = synth.mesh_aabb(v)
         dims = np.zeros(3, np.uint32)
@@ -512,30 +534,50 @@ def run_batch(args):
             vf.fracture_model(grid, p)
             counts, occ = grid.countValues()
             grid.undoMask()
-            checksum += int(occ)
+            checksums[j] += int(occ)
 
-    for m in my[: args.warmup]:
-        one_mesh(m)
-    ctx.synchronize()
+    def run(todo):
+        def work(j):
+            for m in todo[j::jobs]:
+                one_mesh(j, m)
+            workers[j][0].synchronize()
+
+        ts = [threading.Thread(target=work, args=(j,)) for j in range(jobs)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+
+    run(my[: max(warmup, jobs)])
+    checksums[:] = [0] * jobs  # the checksum covers the timed pass only: it must not depend on `jobs` or N
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for m in my:
-        one_mesh(m)
-    ctx.synchronize()
+    run(my)
     dt = time.perf_counter() - t0
     if dist is not None:
         tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt[0])
+    for ctx, grid in workers:
+        grid.close()
+        ctx.close()
+    return dt, int(sum(checksums)), len(pool)
+
+
+def run_batch(args):
+    rank, local_rank, world, dist = _dist_setup()
+    jobs = args.jobs or default_jobs(world)
+    dt, checksum, npool = batch_measure(rank, local_rank, world, dist, args.meshes, args.warmup, jobs, args.mesh_pool)
     if rank == 0:
         print(json.dumps({
             "metric": "models/s batch voxelize+fragment", "value": args.meshes / dt, "unit": "models/s", "n_gpus": world, "steps": args.meshes,
             "warmup": args.warmup, "ms_per_step": dt / args.meshes * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u16 labels", "data": "synthetic",
-            "config": {"workload": f"cfg4-batch: {args.meshes} synthetic vessels (pool of {len(pool)} shapes) x 10 fragmentations at 256-max, FLOOD CHEBYSHEV, "
-                                   "nf 2..10, 2*nf extra seeds, per-mesh RNG seed 80+m, mesh m -> rank m mod N", "fragmentations_per_s": args.meshes * 10 / dt},
+            "config": {"workload": f"cfg4-batch: {args.meshes} synthetic vessels (pool of {npool} shapes) x 10 fragmentations at 256-max, FLOOD CHEBYSHEV, "
+                                   "nf 2..10, 2*nf extra seeds, per-mesh RNG seed 80+m, mesh m -> rank m mod N", "jobs_per_gpu": jobs,
+                       "fragmentations_per_s": args.meshes * 10 / dt, "checksum_rank0": checksum},
         }))
     if dist is not None:
         dist.destroy_process_group()
@@ -545,9 +587,10 @@ def run_dataset(args):
     """The batch workload through the NATIVE dataset driver (csrc/dataset.cpp = CADScene::generateDataset's voxel path): per mesh
     the dims rule at clamp 256, SAT voxelization, 10 fragmentations (numFragments 2..11, one iteration each, FLOOD CHEBYSHEV, 2n extra
     seeds), histogram, undoMask, and — unlike `--workload batch` — the `.rle` export of every grid (runs found on the device, files
-    written by the driver's writer threads to --out).  Mesh m -> rank m mod N, RNG seed 80 + m."""
+    written by the driver's writer threads to --out).  Mesh m -> rank m mod N, RNG seed 80 + m; --jobs contexts per GPU."""
     import shutil
     import tempfile
+    import threading
 
     import torch
 
@@ -555,31 +598,39 @@ def run_dataset(args):
     from voxelfragmentml_b200 import dataset, synth
 
     rank, local_rank, world, dist = _dist_setup()
-    ctx = vf.Context(local_rank)
+    jobs = args.jobs or default_jobs(world)
     pool = [synth.vessel_mesh(i) for i in range(args.mesh_pool)]
     proc = vf.FragmentationProcedure(_fragmentInterval=(2, 11), _iterationInterval=(1, 1), _maxFragmentsModel=1 << 40)
     proc._fractureParameters._clampVoxelMetricUnit = 256
     proc._fractureParameters._voxelPerMetricUnit = 256
-    grid = dataset.dataset_grid(ctx, proc)
+    workers = []
+    for j in range(jobs):
+        ctx = vf.Context(local_rank)
+        workers.append((ctx, dataset.dataset_grid(ctx, proc), vf._capi.VfDatasetStats()))
     out = tempfile.mkdtemp(prefix=f"vf_dataset_r{rank}_", dir=args.out or None)
     my = [m for m in range(args.meshes) if m % world == rank]
-    st = vf._capi.VfDatasetStats()
 
-    def one_mesh(m, stats):
-        v, f = pool[m % len(pool)]
-        ctx.initSeed(80 + m)
-        dataset.generate_model(grid, proc, f"VS_{m:04d}", v, f, out + "/", stats)
+    def run(todo, timed):
+        def work(j):
+            ctx, grid, st = workers[j]
+            for m in todo[j::jobs]:
+                v, f = pool[m % len(pool)]
+                ctx.initSeed(80 + m)
+                dataset.generate_model(grid, proc, f"VS_{m:04d}", v, f, out + "/", st if timed else vf._capi.VfDatasetStats())
+            ctx.synchronize()
 
-    for m in my[: args.warmup]:
-        one_mesh(m, vf._capi.VfDatasetStats())
-    ctx.synchronize()
+        ts = [threading.Thread(target=work, args=(j,)) for j in range(jobs)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+
+    run(my[: max(args.warmup, jobs)], False)
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for m in my:
-        one_mesh(m, st)
-    ctx.synchronize()
+    run(my, True)
     dt = time.perf_counter() - t0
     shutil.rmtree(out, ignore_errors=True)
     if dist is not None:
@@ -587,13 +638,14 @@ def run_dataset(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt[0])
     if rank == 0:
+        tot = {k: sum(getattr(w[2], k) for w in workers) for k, _ in workers[0][2]._fields_}
         print(json.dumps({
             "metric": "models/s batch voxelize+fragment+export", "value": args.meshes / dt, "unit": "models/s", "n_gpus": world, "steps": args.meshes,
             "warmup": args.warmup, "ms_per_step": dt / args.meshes * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u16 labels", "data": "synthetic",
             "config": {"workload": f"cfg4-dataset: {args.meshes} synthetic vessels (pool of {len(pool)} shapes) x 10 fragmentations at clamp 256 through the native "
                                    "driver, FLOOD CHEBYSHEV, n = 2..11 seeds + 2n extra, .rle export of every grid (device run detection, async writers)",
-                       "rank0": {k: getattr(st, k) for k, _ in st._fields_}, "fragmentations_per_s": args.meshes * 10 / dt},
+                       "jobs_per_gpu": jobs, "rank0": tot, "fragmentations_per_s": args.meshes * 10 / dt},
         }))
     if dist is not None:
         dist.destroy_process_group()
@@ -613,6 +665,8 @@ def main():
     ap.add_argument("--out", default="", help="dataset workload: parent directory of the (temporary) output folder")
     ap.add_argument("--seeds", type=int, default=256, help="slab workload: number of seeds")
     ap.add_argument("--meshes", type=int, default=64, help="batch workload: number of meshes")
+    ap.add_argument("--jobs", type=int, default=0, help="batch workload: concurrent contexts (streams + host threads) per GPU; 0 = 8 or what the host cores allow")
+    ap.add_argument("--no-batch", action="store_true", help="default workload: skip the short cfg4 batch measurement reported under \"batch\"")
     ap.add_argument("--mesh-pool", type=int, default=8, help="batch workload: distinct synthetic shapes generated up front")
     args = ap.parse_args()
     if args.impl == "reference":
