@@ -180,8 +180,8 @@ def run_cuda(args):
         stage("remove_isolated", lambda: vf.NaiveFracturer.removeIsolatedRegions(grid, seeds))
         et, es, ei, ep, eth = CFG3["erosion"]
         stage("erode", lambda: grid.erode(et, es, ei, ep, eth, noise=noise))
-        stage("histogram", lambda: grid.countValues())
-        stage("undo_mask", lambda: grid.undoMask())
+        # prepareScene's grid side: countValues (toTriangleMesh) then undoMask — one fused pass (vf_histogram_undo_mask)
+        stage("histogram_undo_mask", lambda: grid.countValuesUndoMask())
         if record is not None:
             record.append(t)
 
@@ -235,7 +235,7 @@ def run_cuda(args):
     # per-stage achieved GB/s on algorithmic bytes (B = 2N read + 2 N_w written; dense grid => N_w = N for the stages
     # that rewrite labels, 0 for the histogram; erode = 3 x (detect + erode) + sweep counted as 7 passes of one read each and
     # 4 passes that rewrite every label)
-    passes = {"naive": (1, 1), "remove_isolated": (1, 0), "erode": (7, 4), "histogram": (1, 0), "undo_mask": (1, 1)}
+    passes = {"naive": (1, 1), "remove_isolated": (1, 0), "erode": (7, 4), "histogram": (1, 0), "undo_mask": (1, 1), "histogram_undo_mask": (1, 1)}
     stage_roofline = {k: {"algorithmic_bytes": 2.0 * N * (passes[k][0] + passes[k][1]), "achieved_gbs": 2.0 * N * (passes[k][0] + passes[k][1]) / (v * 1e-3) / 1e9,
                           "frac": 2.0 * N * (passes[k][0] + passes[k][1]) / (v * 1e-3) / 1e9 / peak, "share_of_step": v / sum(stage_ms.values())}
                       for k, v in stage_ms.items() if k in passes}
@@ -290,8 +290,7 @@ def run_cuda(args):
             naive.build(g, seeds)
             vf.NaiveFracturer.removeIsolatedRegions(g, seeds)
             g.erode(et, es, ei, ep, eth, noise=noise)
-            g.countValues()
-            g.undoMask()
+            g.countValuesUndoMask()
         last = (nsteps - 1) % 3
         slots[last][1].download_async(slots[last][2])
         for c, _, _ in slots:
@@ -354,6 +353,9 @@ def oracle_pipeline(orc, grid, seeds, noise, stages):
     if "erode" in stages:
         et, es, ei, ep, eth = CFG3["erosion"]
         orc.erode(grid, noise, et, es, ei, ep, eth)
+    if "histogram_undo_mask" in stages:
+        orc.count_values(grid)
+        orc.undo_mask(grid, 15, False)
     if "histogram" in stages:
         orc.count_values(grid)
     if "undo_mask" in stages:
@@ -532,8 +534,7 @@ def batch_measure(rank, local_rank, world, dist, meshes, warmup, jobs, mesh_pool
             p = vf.FractureParameters(_numSeeds=nf, _numExtraSeeds=2 * nf)
             grid.homogenize()  # resetFilling/homogenize between fragmentations (CADScene::rebuildGrid, FloodFracturer.cpp:99)
             vf.fracture_model(grid, p)
-            counts, occ = grid.countValues()
-            grid.undoMask()
+            counts, occ = grid.countValuesUndoMask()
             checksums[j] += int(occ)
 
     def run(todo):

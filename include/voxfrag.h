@@ -212,6 +212,9 @@ vf_status vf_homogenize(vf_grid* g);                                     /* Regu
 /* RegularGrid::countValues + numOccupiedVoxels (RegularGrid.cpp:601-625, 280-287): counts[VF_HISTOGRAM_BINS] indexed by
  * (value & 0x7FFF) over cells with value > FREE; *occupied = number of such cells. */
 vf_status vf_histogram(vf_grid* g, uint32_t* counts, uint64_t* occupied);
+/* The grid side of CADScene::prepareScene (CADScene.cpp:813-832) in one pass over the grid: toTriangleMesh's countValues
+ * (RegularGrid.cpp:443-471) followed by undoMask (:832) — same counts, bit 15 cleared afterwards. */
+vf_status vf_histogram_undo_mask(vf_grid* g, uint32_t* counts, uint64_t* occupied);
 
 /* ------------------------------------------------------------------ X1: export */
 vf_status vf_export(vf_grid* g, const char* path_without_extension, int export_type, int squared); /* RegularGrid::exportGrid, :161-171 */

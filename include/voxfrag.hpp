@@ -212,6 +212,16 @@ public:
         for (uint32_t c : countsByLabel) distinct += c != 0;
         return distinct;
     }
+    // countValues followed by undoMask (the grid side of CADScene::prepareScene, CADScene.cpp:813-832) in one pass over the grid
+    size_t countValuesUndoMask(std::vector<uint32_t>& countsByLabel)
+    {
+        countsByLabel.assign(VF_HISTOGRAM_BINS, 0);
+        uint64_t occ = 0;
+        check(vf_histogram_undo_mask(_h, countsByLabel.data(), &occ));
+        size_t distinct = 0;
+        for (uint32_t c : countsByLabel) distinct += c != 0;
+        return distinct;
+    }
     unsigned numOccupiedVoxels()
     {
         std::vector<uint32_t> c(VF_HISTOGRAM_BINS);

@@ -287,3 +287,39 @@ def test_near_seeds_and_fracture_model_with_impacts(ctx, orc, vessel_grid):
     want, _ = orc.flood(vessel_grid.copy(), wseeds, orc.CHEBYSHEV)
     assert np.array_equal(g.updateGrid(), orc.detect_boundaries(want, 1))
     g.close()
+
+
+def test_histogram_undo_mask_fused(ctx, orc, labelled_vessel):
+    """vf_histogram_undo_mask == countValues followed by undoMask (prepareScene's grid side), incl. cell counts not divisible by 8"""
+    lab, _ = labelled_vessel
+    rs = np.random.RandomState(4)
+    tagged = orc.detect_boundaries(lab.copy(), 1)
+    odd = (rs.randint(0, 40, size=(13, 7, 9)) | (rs.rand(13, 7, 9) < 0.3) * 0x8000).astype(np.uint16)
+    big_ids = (rs.randint(0, 30000, size=(16, 16, 40)) | (rs.rand(16, 16, 40) < 0.5) * 0x8000).astype(np.uint16)
+    for a in (tagged, odd, big_ids, np.zeros((8, 8, 8), np.uint16)):
+        g = _grid(ctx, a)
+        counts, occ = g.countValuesUndoMask()
+        wcounts, wocc = orc.count_values(a)
+        assert occ == wocc and np.array_equal(counts, wcounts)
+        assert np.array_equal(g.updateGrid(), orc.undo_mask(a.copy(), 15, False))
+        g.close()
+
+
+def test_connected_to_seed_with_whole_tile_regions(ctx, orc):
+    """C1 on grids whose 16 x 16 x 32 tiles are mostly interior to one label (the union-find shortcut for whole-region tiles):
+    solid blocks split by planes, an island of the same label cut off by another label, tiles cut by the grid border."""
+    import voxelfragmentml_b200 as vf
+
+    rs = np.random.RandomState(21)
+    for dims in [(64, 48, 96), (40, 40, 72), (33, 50, 64)]:
+        g0 = np.full(dims, 2, np.uint16)
+        g0[dims[0] // 2:, :, :] = 3
+        g0[:, dims[1] // 2:, dims[2] // 2:] = 4
+        g0[4:12, 4:12, 4:20] = 3            # an island of label 3 inside label 2: not connected to seed 3's region
+        g0[:, :, dims[2] - 5] = rs.randint(2, 5, size=dims[:2])  # a noisy plane
+        g0[20:22, :, :] = 0                 # an EMPTY slab: label 2 and 4 regions beyond it survive only with their own seed
+        seeds = np.uint32([[1, 1, 1, 2], [dims[0] - 2, 1, 1, 3], [1, dims[1] - 2, dims[2] - 2, 4]])
+        g = _grid(ctx, g0)
+        vf.NaiveFracturer.removeIsolatedRegions(g, seeds)
+        assert np.array_equal(g.updateGrid(), orc.remove_isolated_regions_cpu(g0.copy(), seeds)), dims
+        g.close()

@@ -7,7 +7,8 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
 
 # ---- bench lines
 for src, dst in (("bench_cfg3.json", f"{tag}_bench.json"), ("bench_reference.json", f"{tag}_bench_reference.json"), ("bench_batch.json", f"{tag}_bench_batch_1gpu.json"),
-                 ("flood_timings.txt", f"{tag}_flood_timings.txt")):
+                 ("bench_batch_1job.json", f"{tag}_bench_batch_1gpu_1job.json"), ("bench_dataset.json", f"{tag}_bench_dataset_1gpu.json"),
+                 ("flood_timings.txt", f"{tag}_flood_timings.txt"), ("voxelizer_timings.txt", f"{tag}_voxelizer_timings.txt")):
     if os.path.exists(os.path.join(G, src)):
         shutil.copyfile(os.path.join(G, src), os.path.join(P, dst))
 
@@ -30,7 +31,7 @@ with open(os.path.join(P, f"{tag}_launches_summary.md"), "w") as f:
     sm = bench["stage_ms"]
     st = sum(sm.values())
     f.write("\nbench.py `stage_ms` of the same build (CUDA events, warm): " + ", ".join(f"{k} {v:.3f} ms ({100 * v / st:.1f}%)" for k, v in sm.items()) + "\n\n")
-    grp = {"naive": ["naive_brick"], "remove_isolated": ["ccl_", "zero_kernel"], "erode": ["stencil_"], "histogram": ["histogram"], "undo_mask": ["pointwise"]}
+    grp = {"naive": ["naive_brick"], "remove_isolated": ["ccl_", "zero_kernel"], "erode": ["stencil_"], "histogram_undo_mask": ["histogram", "pointwise"]}
     f.write("Launch-list shares grouped the same way: " + ", ".join(
         f"{g} {100 * sum(sum(v) for k, v in agg.items() if any(p in k for p in pats)) / tot:.1f}%" for g, pats in grp.items()) + "\n")
 
@@ -53,10 +54,11 @@ def raw(rep):
 with open(os.path.join(P, f"{tag}_ncu_full_summary.md"), "w") as f:
     f.write(f"# {tag} — ncu --set full summaries (one B200)\n\nCommands (tools/collect_profiles.sh): `ncu --set full --clock-control none --import-source on -k regex:\"naive_brick|"
             "stencil_fast|ccl_tile|ccl_border|ccl_select|histogram|pointwise\" -s 14 -c 14 python tools/prof_stage.py 512 naive,c1,erode,hist 2` (the cfg3 stages on the dense "
-            "512^3 grid) and `-k regex:flood_round -s 6 -c 2 python tools/prof_flood1.py 1` (cfg2 vessel). One row per distinct kernel (first captured launch); "
+            "512^3 grid), `-k regex:flood_round -s 6 -c 2 python tools/prof_flood1.py 1` (cfg2 vessel) and `-k regex:\"solid_scatter|solid_expand|tetra_setup|voxelize_brick\" "
+            "-s 8 -c 4 python tools/prof_solid.py 256` (V1 / V2 on the 19.8k-triangle vessel at 176x256x176). One row per distinct kernel (first captured launch); "
             "read with `ncu -i ... --page raw --csv`.\n")
     traffic = {}
-    for rep in ("cfg3_full.ncu-rep", "flood_full.ncu-rep"):
+    for rep in ("cfg3_full.ncu-rep", "flood_full.ncu-rep", "voxelizer_full.ncu-rep"):
         path = os.path.join(G, rep)
         if not os.path.exists(path):
             continue

@@ -105,6 +105,7 @@ SIGNATURES = {
     "vf_reset_filling": (C.c_int, [_vp]),
     "vf_homogenize": (C.c_int, [_vp]),
     "vf_histogram": (C.c_int, [_vp, _vp, C.POINTER(C.c_uint64)]),
+    "vf_histogram_undo_mask": (C.c_int, [_vp, _vp, C.POINTER(C.c_uint64)]),
     "vf_export": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int]),
     "vf_procedure_default": (None, [C.POINTER(VfProcedure)]),
     "vf_dataset_dims_rule": (None, [_vp, _vp, C.c_int32, C.c_int32, _vp]),

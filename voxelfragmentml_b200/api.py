@@ -276,6 +276,13 @@ class RegularGrid:
         check(self._lib.vf_histogram(self._h, ptr(counts), C.byref(occ)))
         return counts, int(occ.value)
 
+    def countValuesUndoMask(self):
+        """countValues followed by undoMask — the grid side of CADScene::prepareScene (CADScene.cpp:813-832) — in one pass."""
+        counts = np.zeros(_capi.HISTOGRAM_BINS, dtype=np.uint32)
+        occ = C.c_uint64(0)
+        check(self._lib.vf_histogram_undo_mask(self._h, ptr(counts), C.byref(occ)))
+        return counts, int(occ.value)
+
     def numOccupiedVoxels(self) -> int:
         return self.countValues()[1]
 

@@ -209,6 +209,18 @@ __global__ void __launch_bounds__(256) ccl_tile_kernel(const uint16_t* __restric
     }
     __syncthreads();
 
+    // (a') a tile that lies wholly inside one region — every row one full run, all rows alike: the interior of a fragment, i.e.
+    //      most tiles of a solid grid — is one component whatever the neighbourhood: every row's run start points at the tile's
+    //      first cell and the union-find phases are skipped.  (A full active mask also means the row lies inside the grid.)
+    {
+        const int r = threadIdx.x;
+        const bool whole = sA[r] == 0xFFFFFFFFu && sS[r] == 1u && same<MODE>(lab(r, 0), lab(0, 0));
+        if (__syncthreads_and(whole)) {
+            P[((size_t)(gx0 + r / LY) * g.Y + gy0 + r % LY) * g.Z + gz0] = ((uint32_t)gx0 * g.Y + gy0) * g.Z + gz0;
+            return;
+        }
+    }
+
     // (b) thread per row: unite my runs with the runs of the backward neighbour rows at the key positions
     {
         const int r = threadIdx.x, x = r / LY, y = r % LY;

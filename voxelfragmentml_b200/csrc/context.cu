@@ -100,7 +100,7 @@ static vf_status ctx_create(int device, void* stream, bool borrow, vf_ctx** out)
     }
     VF_CUDA(cudaEventCreate(&c->ev_start));
     VF_CUDA(cudaEventCreate(&c->ev_stop));
-    c->pinned_bytes = 1 << 17;  // [0, 64K) seed staging, [64K, 128K) counter mailbox
+    c->pinned_bytes = (1 << 17) + (VF_HISTOGRAM_BINS * 4 + 64);  // [0, 64K) seed staging, [64K, 128K) counter mailbox, then the histogram read-back
     VF_CUDA(cudaMallocHost(&c->pinned, c->pinned_bytes));
     c->rng.seed(80);  // FractureParameters::_seed default (FractureParameters.h:116), applied at CADScene.cpp:36-37
     *out = c;

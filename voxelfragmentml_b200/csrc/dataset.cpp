@@ -264,8 +264,7 @@ extern "C" vf_status vf_dataset_model(vf_grid* g, const vf_procedure* proc, cons
             VF_TRY(vf_reset_filling(g));                                   // fractureGrid -> rebuildGrid (:174, :835-838)
             VF_TRY(vf_fracture_model(g, &fp, nullptr, nullptr, nullptr));  // :175
             uint64_t occupied = 0;                                          // prepareScene -> toTriangleMesh: countValues (:813, RegularGrid.cpp:443-471)
-            VF_TRY(vf_histogram(g, counts.data(), &occupied));
-            VF_TRY(vf_undo_mask(g));                                       // :832
+            VF_TRY(vf_histogram_undo_mask(g, counts.data(), &occupied));  // ... and undoMask (:832), one pass
             local.seconds_fracture += now() - t0;
             uint64_t fragments = 0;
             for (uint32_t v = 2; v < VF_HISTOGRAM_BINS; ++v) fragments += counts[v] != 0;

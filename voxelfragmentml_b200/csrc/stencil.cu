@@ -179,7 +179,9 @@ __global__ void __launch_bounds__(256) erode_generic_kernel(const uint16_t* __re
 // label change instead of one per vector.  Shared bins for ids < 4096, global atomics beyond.
 constexpr int kSmemBins = 4096;
 constexpr int kHistBatch = 4;
-__global__ void __launch_bounds__(256) histogram_kernel(const uint16_t* __restrict__ grid, size_t n, uint32_t* __restrict__ counts,
+// UNMASK: the same pass also clears bit 15 (undoMask) — vectors that carry a tag are written back, the others are only read.
+template <bool UNMASK>
+__global__ void __launch_bounds__(256) histogram_kernel(uint16_t* __restrict__ grid, size_t n, uint32_t* __restrict__ counts,
                                                         unsigned long long* __restrict__ occupied)
 {
     __shared__ uint32_t bins[kSmemBins];
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(256) histogram_kernel(const uint16_t* __restri
     __syncthreads();
     unsigned occ = 0;
     const size_t nvec = n / 8;
-    const uint4* g4 = reinterpret_cast<const uint4*>(grid);
+    uint4* g4 = reinterpret_cast<uint4*>(grid);
     auto add = [&](uint32_t label, uint32_t c) {
         if (label < kSmemBins) atomicAdd(&bins[label], c);
         else atomicAdd(&counts[label], c);
@@ -213,6 +215,13 @@ __global__ void __launch_bounds__(256) histogram_kernel(const uint16_t* __restri
         for (int k = 0; k < kHistBatch; ++k) {
             const size_t i = base + k * 32 + lane;
             v[k] = i < nvec ? vf_ldg_stream(g4 + i) : make_uint4(0, 0, 0, 0);  // EMPTY counts nowhere
+        }
+        if (UNMASK) {
+#pragma unroll
+            for (int k = 0; k < kHistBatch; ++k) {
+                if ((v[k].x | v[k].y | v[k].z | v[k].w) & 0x80008000u)  // out-of-range vectors were loaded as zeros
+                    vf_stg_stream(g4 + base + k * 32 + lane, make_uint4(v[k].x & 0x7FFF7FFFu, v[k].y & 0x7FFF7FFFu, v[k].z & 0x7FFF7FFFu, v[k].w & 0x7FFF7FFFu));
+            }
         }
 #pragma unroll
         for (int k = 0; k < kHistBatch; ++k) {
@@ -244,7 +253,11 @@ __global__ void __launch_bounds__(256) histogram_kernel(const uint16_t* __restri
             }
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x < n % 8) take(grid[nvec * 8 + threadIdx.x], 1);
+    if (blockIdx.x == 0 && threadIdx.x < n % 8) {
+        const uint16_t raw = grid[nvec * 8 + threadIdx.x];
+        take(raw, 1);
+        if (UNMASK && (raw & 0x8000u)) grid[nvec * 8 + threadIdx.x] = raw & 0x7FFFu;
+    }
     if (run) add(run_label, run);
     occ = __reduce_add_sync(kFull, occ);
     if ((threadIdx.x & 31) == 0 && occ) atomicAdd(occupied, (unsigned long long)occ);
@@ -637,7 +650,7 @@ extern "C" vf_status vf_erode(vf_grid* g, int type, uint32_t size, uint32_t iter
     return VF_OK;
 }
 
-extern "C" vf_status vf_histogram(vf_grid* g, uint32_t* counts, uint64_t* occupied)
+static vf_status histogram_impl(vf_grid* g, uint32_t* counts, uint64_t* occupied, bool unmask)
 {
     VF_REQUIRE(g != nullptr && counts != nullptr, VF_ERR_INVALID_ARGUMENT, "null argument");
     vf_ctx* c = g->ctx;
@@ -648,12 +661,18 @@ extern "C" vf_status vf_histogram(vf_grid* g, uint32_t* counts, uint64_t* occupi
     unsigned long long* d_occ = (unsigned long long*)(d_counts + VF_HISTOGRAM_BINS);
     VF_TRY(vf_k_zero(c, d_counts, VF_HISTOGRAM_BINS * 4 + 8));
     const int blocks = (int)std::min((size_t)c->num_sms * 8, (g->n() / 8 + 255) / 256 + 1);
-    histogram_kernel<<<blocks, 256, 0, c->stream>>>(g->d, g->n(), d_counts, d_occ);
+    if (unmask) histogram_kernel<true><<<blocks, 256, 0, c->stream>>>(g->d, g->n(), d_counts, d_occ);
+    else histogram_kernel<false><<<blocks, 256, 0, c->stream>>>(g->d, g->n(), d_counts, d_occ);
     VF_LAUNCHED(c);
-    VF_CUDA(cudaMemcpyAsync(counts, d_counts, VF_HISTOGRAM_BINS * 4, cudaMemcpyDeviceToHost, c->stream));
-    unsigned long long h_occ = 0;
-    VF_CUDA(cudaMemcpyAsync(&h_occ, d_occ, 8, cudaMemcpyDeviceToHost, c->stream));
+    // bins + occupied count are contiguous on the device: one copy into the context's pinned read-back area (a copy into the caller's
+    // pageable buffer is staged by the runtime and costs two extra synchronisations), then a host memcpy
+    char* h = (char*)c->pinned + (1 << 17);
+    VF_CUDA(cudaMemcpyAsync(h, d_counts, VF_HISTOGRAM_BINS * 4 + 8, cudaMemcpyDeviceToHost, c->stream));
     VF_CUDA(cudaStreamSynchronize(c->stream));
-    if (occupied) *occupied = h_occ;
+    std::memcpy(counts, h, VF_HISTOGRAM_BINS * 4);
+    if (occupied) std::memcpy(occupied, h + VF_HISTOGRAM_BINS * 4, 8);
     return VF_OK;
 }
+
+extern "C" vf_status vf_histogram(vf_grid* g, uint32_t* counts, uint64_t* occupied) { return histogram_impl(g, counts, occupied, false); }
+extern "C" vf_status vf_histogram_undo_mask(vf_grid* g, uint32_t* counts, uint64_t* occupied) { return histogram_impl(g, counts, occupied, true); }
