@@ -115,6 +115,9 @@ vf_status vf_ctx_create_on_stream(int device, void* cuda_stream, vf_ctx** out); 
 void      vf_ctx_destroy(vf_ctx* ctx);
 vf_status vf_ctx_reserve(vf_ctx* ctx, uint32_t X, uint32_t Y, uint32_t Z); /* Fracturer::prepareSSBOs / init, Fracturer.h:43-48; FloodFracturer.cpp:47-59 */
 vf_status vf_ctx_synchronize(vf_ctx* ctx);
+/* on: host waits of this context sleep on a blocking event instead of spinning — for producers that drive more contexts than
+ * they have host cores (batch generation overlaps several jobs per GPU); off (default): lowest latency */
+vf_status vf_ctx_set_blocking_sync(vf_ctx* ctx, int on);
 void*     vf_ctx_stream(vf_ctx* ctx);                                    /* the cudaStream_t every call of this context is issued on */
 uint64_t  vf_ctx_kernel_launches(vf_ctx* ctx);                           /* kernels launched by this context so far (bench "gpu_launches") */
 /* CUDA-event timing on the context's stream (ResourceTracker's role, SRC/Utilities/ResourceTracker.cpp:58-72) */

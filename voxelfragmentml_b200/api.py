@@ -117,6 +117,10 @@ class Context:
     def reserve(self, dims):  # Fracturer::prepareSSBOs
         check(self._lib.vf_ctx_reserve(self._h, *[int(d) for d in dims]))
 
+    def setBlockingSync(self, on: bool = True):
+        """host waits sleep instead of spinning (more contexts than host cores)"""
+        check(self._lib.vf_ctx_set_blocking_sync(self._h, int(bool(on))))
+
     def synchronize(self):
         check(self._lib.vf_ctx_synchronize(self._h))
 

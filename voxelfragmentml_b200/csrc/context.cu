@@ -100,10 +100,18 @@ static vf_status ctx_create(int device, void* stream, bool borrow, vf_ctx** out)
     }
     VF_CUDA(cudaEventCreate(&c->ev_start));
     VF_CUDA(cudaEventCreate(&c->ev_stop));
+    VF_CUDA(cudaEventCreateWithFlags(&c->ev_block, cudaEventBlockingSync | cudaEventDisableTiming));
     c->pinned_bytes = (1 << 17) + (VF_HISTOGRAM_BINS * 4 + 64);  // [0, 64K) seed staging, [64K, 128K) counter mailbox, then the histogram read-back
     VF_CUDA(cudaMallocHost(&c->pinned, c->pinned_bytes));
     c->rng.seed(80);  // FractureParameters::_seed default (FractureParameters.h:116), applied at CADScene.cpp:36-37
     *out = c;
+    return VF_OK;
+}
+
+extern "C" vf_status vf_ctx_set_blocking_sync(vf_ctx* ctx, int on)
+{
+    VF_REQUIRE(ctx != nullptr, VF_ERR_INVALID_ARGUMENT, "null context");
+    ctx->blocking_sync = on != 0;
     return VF_OK;
 }
 
@@ -114,13 +122,14 @@ extern "C" void vf_ctx_destroy(vf_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    vf_sync(c);
     VfScratch* all[] = { &c->keys, &c->grid2, &c->tiles, &c->small, &c->noise, &c->mesh, &c->codec };
     for (VfScratch* s : all)
         if (s->ptr) cudaFree(s->ptr);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->ev_start) cudaEventDestroy(c->ev_start);
     if (c->ev_stop) cudaEventDestroy(c->ev_stop);
+    if (c->ev_block) cudaEventDestroy(c->ev_block);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -131,7 +140,7 @@ vf_status vf_scratch_reserve(vf_ctx* ctx, VfScratch& s, size_t bytes)
     if (&s == &ctx->small) ctx->seed_shadow.clear();   // the arena moves: what the shadows describe is gone
     if (&s == &ctx->noise) ctx->noise_shadow.clear();
     if (s.ptr) {
-        VF_CUDA(cudaStreamSynchronize(ctx->stream));
+        VF_CUDA(vf_sync(ctx));
         VF_CUDA(cudaFree(s.ptr));
         s.ptr = nullptr;
         s.bytes = 0;
@@ -154,7 +163,7 @@ extern "C" vf_status vf_ctx_reserve(vf_ctx* ctx, uint32_t X, uint32_t Y, uint32_
 extern "C" vf_status vf_ctx_synchronize(vf_ctx* ctx)
 {
     VF_TRY(vf_enter(ctx));
-    VF_CUDA(cudaStreamSynchronize(ctx->stream));
+    VF_CUDA(vf_sync(ctx));
     return VF_OK;
 }
 
@@ -254,7 +263,7 @@ extern "C" void vf_grid_destroy(vf_grid* g)
     if (!g) return;
     if (g->own && g->d) {
         cudaSetDevice(g->ctx->device);
-        cudaStreamSynchronize(g->ctx->stream);
+        vf_sync(g->ctx);
         cudaFree(g->d);
     }
     delete g;
@@ -309,13 +318,13 @@ extern "C" vf_status vf_grid_download_async(vf_grid* g, uint16_t* host)
 extern "C" vf_status vf_grid_upload(vf_grid* g, const uint16_t* host)
 {
     VF_TRY(vf_grid_upload_async(g, host));
-    VF_CUDA(cudaStreamSynchronize(g->ctx->stream));
+    VF_CUDA(vf_sync(g->ctx));
     return VF_OK;
 }
 extern "C" vf_status vf_grid_download(vf_grid* g, uint16_t* host)
 {
     VF_TRY(vf_grid_download_async(g, host));
-    VF_CUDA(cudaStreamSynchronize(g->ctx->stream));
+    VF_CUDA(vf_sync(g->ctx));
     return VF_OK;
 }
 
@@ -352,7 +361,7 @@ vf_status vf_upload_seeds(vf_ctx* ctx, const uint32_t* seeds, uint32_t n, uint32
     *d_out = (ushort4*)ctx->small.ptr;
     if (ctx->seed_shadow.size() == n && std::memcmp(ctx->seed_shadow.data(), packed.data(), (size_t)n * sizeof(ushort4)) == 0) return VF_OK;  // already there
     // the pinned mailbox may still be in flight from a previous call on this stream
-    VF_CUDA(cudaStreamSynchronize(ctx->stream));
+    VF_CUDA(vf_sync(ctx));
     std::memcpy(ctx->pinned, packed.data(), (size_t)n * sizeof(ushort4));
     ctx->seed_shadow.clear();
     VF_CUDA(cudaMemcpyAsync(ctx->small.ptr, ctx->pinned, (size_t)n * sizeof(ushort4), cudaMemcpyHostToDevice, ctx->stream));

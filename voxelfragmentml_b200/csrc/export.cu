@@ -510,7 +510,7 @@ static vf_status rle_encode_device(vf_grid* g, std::vector<uint8_t>* grow, uint8
     VF_LAUNCHED(c);
     uint32_t* h_total = (uint32_t*)((char*)c->pinned + 65536 + 128);
     VF_CUDA(cudaMemcpyAsync(h_total, d_total, 4, cudaMemcpyDeviceToHost, c->stream));
-    VF_CUDA(cudaStreamSynchronize(c->stream));
+    VF_CUDA(vf_sync(c));
     const uint64_t runs = *h_total, bytes = 12 + 6 * runs;
     *bytes_out = bytes;
     if (grow) {
@@ -525,7 +525,7 @@ static vf_status rle_encode_device(vf_grid* g, std::vector<uint8_t>* grow, uint8
         c->codec = VfScratch();
         VF_TRY(vf_scratch_reserve(c, c->codec, 2 * tb + 256 + sb + vb + bytes + 256));
         VF_CUDA(cudaMemcpyAsync(c->codec.ptr, old.ptr, 2 * tb + 256, cudaMemcpyDeviceToDevice, c->stream));
-        VF_CUDA(cudaStreamSynchronize(c->stream));
+        VF_CUDA(vf_sync(c));
         VF_CUDA(cudaFree(old.ptr));
         d_offsets = (uint32_t*)((char*)c->codec.ptr + tb);
     }
@@ -537,7 +537,7 @@ static vf_status rle_encode_device(vf_grid* g, std::vector<uint8_t>* grow, uint8
     rle_pack_kernel<<<(unsigned)((runs + 255) / 256), 256, 0, c->stream>>>(d_starts, d_values, (uint32_t)runs, n, make_uint3(g->X, g->Y, g->Z), d_out);
     VF_LAUNCHED(c);
     VF_CUDA(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, c->stream));
-    VF_CUDA(cudaStreamSynchronize(c->stream));
+    VF_CUDA(vf_sync(c));
     return VF_OK;
 }
 

@@ -539,7 +539,7 @@ vf_status run_rounds(Job& j, LaunchF launch)
         }
         j.round += batch;
         VF_CUDA(cudaMemcpyAsync(j.h_mail, j.wl.count + (j.round % 3), 4, cudaMemcpyDeviceToHost, c->stream));
-        VF_CUDA(cudaStreamSynchronize(c->stream));
+        VF_CUDA(vf_sync(c));
         if (j.h_mail[0] == 0) return VF_OK;
         batch = std::min(batch * 2, 32);
     }
@@ -647,7 +647,7 @@ extern "C" vf_status vf_fracture_flood(vf_grid* grid, const uint32_t* seeds, uin
         ushort4* h = (ushort4*)c->pinned;
         uint16_t* h_order = (uint16_t*)(h + 256);
         int nstart = 0;
-        VF_CUDA(cudaStreamSynchronize(c->stream));  // the mailbox still carries the seed upload
+        VF_CUDA(vf_sync(c));  // the mailbox still carries the seed upload
         for (int f = 0; f < 256; ++f) {
             h_order[f] = 0;
             if (principal[f] < 0) continue;
@@ -763,7 +763,7 @@ extern "C" vf_status vf_flood_slab_init(vf_grid* slab_grid, uint32_t* keys_dev, 
         // seeds_local: {x (slab-local, halo planes included), y, z, GLOBAL order}.  The order goes into the key, labels are
         // looked up at finalize time from the global seed list.
         VF_REQUIRE((size_t)nseeds * sizeof(ushort4) <= 65536, VF_ERR_CAPACITY, "too many seeds in one slab");
-        VF_CUDA(cudaStreamSynchronize(c->stream));
+        VF_CUDA(vf_sync(c));
         ushort4* h = (ushort4*)c->pinned;
         for (uint32_t i = 0; i < nseeds; ++i) {
             VF_REQUIRE(seeds_local[4 * i] < slab_grid->X && seeds_local[4 * i + 1] < slab_grid->Y && seeds_local[4 * i + 2] < slab_grid->Z, VF_ERR_INVALID_ARGUMENT,
@@ -813,7 +813,7 @@ extern "C" vf_status vf_flood_slab_ingest(vf_slab* s, int side, const uint32_t* 
     slab_ingest_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>(halo, plane_dev, s->job.g, s->job.wl, side == 0 ? 0 : s->job.g.ntx - 1, s->job.round, s->d_changed);
     VF_LAUNCHED(c);
     VF_CUDA(cudaMemcpyAsync(s->job.h_mail, s->d_changed, 4, cudaMemcpyDeviceToHost, c->stream));
-    VF_CUDA(cudaStreamSynchronize(c->stream));
+    VF_CUDA(vf_sync(c));
     if (changed) *changed = s->job.h_mail[0];
     return VF_OK;
 }
@@ -826,7 +826,7 @@ extern "C" vf_status vf_flood_slab_finalize(vf_slab* s, const uint32_t* seeds_gl
     ushort4* d_seeds = nullptr;
     // only .w is read by the finalize kernel; coordinates are global and may exceed the slab, so upload without range checks
     VF_REQUIRE((size_t)nseeds_total * sizeof(ushort4) <= 65536, VF_ERR_CAPACITY, "too many seeds");
-    VF_CUDA(cudaStreamSynchronize(c->stream));
+    VF_CUDA(vf_sync(c));
     ushort4* h = (ushort4*)c->pinned;
     for (uint32_t i = 0; i < nseeds_total; ++i) h[i] = make_ushort4(0, 0, 0, (unsigned short)seeds_global[4 * i + 3]);
     d_seeds = (ushort4*)c->small.ptr;

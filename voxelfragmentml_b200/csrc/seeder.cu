@@ -92,7 +92,7 @@ extern "C" vf_status vf_seed_uniform(vf_grid* g, uint32_t n, int random_mode, in
     const int ndx = (int)g->X - 2, ndy = (int)g->Y - 2, ndz = (int)g->Z - 2;  // :165
     uint32_t attempt = 0;
     while (seeds.size() != n) {
-        VF_CUDA(cudaStreamSynchronize(c->stream));  // the pinned staging areas may still be in flight
+        VF_CUDA(vf_sync(c));  // the pinned staging areas may still be in flight
         const VfMt19937 saved = c->rng;
         const int batch = (int)std::min<uint32_t>(kBatch, kMaxTries - attempt);
         if (batch == 0) {
@@ -114,7 +114,7 @@ extern "C" vf_status vf_seed_uniform(vf_grid* g, uint32_t n, int random_mode, in
         seed_probe_kernel<<<(batch + 127) / 128, 128, 0, c->stream>>>(g->d, (int)g->X, (int)g->Y, (int)g->Z, d_cand, batch, d_flags);
         VF_LAUNCHED(c);
         VF_CUDA(cudaMemcpyAsync(h_flags, d_flags, batch, cudaMemcpyDeviceToHost, c->stream));
-        VF_CUDA(cudaStreamSynchronize(c->stream));
+        VF_CUDA(vf_sync(c));
         int used = batch;
         for (int i = 0; i < batch; ++i) {
             const U3 v = { h_cand[i].x, h_cand[i].y, h_cand[i].z };
@@ -182,7 +182,7 @@ extern "C" vf_status vf_seed_near(vf_grid* g, const uint32_t* frags, uint32_t nf
         while (currentSeeds != nseeds) {
             VF_REQUIRE(tries < kMaxTries, VF_ERR_SEEDER_EXHAUSTED, "nearSeeds: no boundary cell near fragment (%u, %u, %u) after %u candidates", frag[0], frag[1],
                        frag[2], kMaxTries);
-            VF_CUDA(cudaStreamSynchronize(c->stream));
+            VF_CUDA(vf_sync(c));
             for (int i = 0; i < kBatch; ++i) {  // :74-83
                 const uint32_t x = (frag[0] + (half[0] - biased(dims[0])) + dims[0]) % dims[0];
                 const uint32_t y = (frag[1] + (half[1] - biased(dims[1])) + dims[1]) % dims[1];
@@ -194,7 +194,7 @@ extern "C" vf_status vf_seed_near(vf_grid* g, const uint32_t* frags, uint32_t nf
             seed_probe_kernel<<<(kBatch + 127) / 128, 128, 0, c->stream>>>(g->d, (int)g->X, (int)g->Y, (int)g->Z, d_cand, kBatch, d_flags);
             VF_LAUNCHED(c);
             VF_CUDA(cudaMemcpyAsync(h_flags, d_flags, kBatch, cudaMemcpyDeviceToHost, c->stream));
-            VF_CUDA(cudaStreamSynchronize(c->stream));
+            VF_CUDA(vf_sync(c));
             for (int i = 0; i < kBatch; ++i) {
                 const U3 v = { h_cand[i].x, h_cand[i].y, h_cand[i].z };
                 const float dx = (float)v.x - (float)frag[0], dy = (float)v.y - (float)frag[1], dz = (float)v.z - (float)frag[2];

@@ -668,7 +668,7 @@ static vf_status histogram_impl(vf_grid* g, uint32_t* counts, uint64_t* occupied
     // pageable buffer is staged by the runtime and costs two extra synchronisations), then a host memcpy
     char* h = (char*)c->pinned + (1 << 17);
     VF_CUDA(cudaMemcpyAsync(h, d_counts, VF_HISTOGRAM_BINS * 4 + 8, cudaMemcpyDeviceToHost, c->stream));
-    VF_CUDA(cudaStreamSynchronize(c->stream));
+    VF_CUDA(vf_sync(c));
     std::memcpy(counts, h, VF_HISTOGRAM_BINS * 4);
     if (occupied) std::memcpy(occupied, h + VF_HISTOGRAM_BINS * 4, 8);
     return VF_OK;

@@ -91,6 +91,8 @@ struct vf_ctx {
     int smem_optin = 0;
     uint64_t launches = 0;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    cudaEvent_t ev_block = nullptr;  // cudaEventBlockingSync: waits that give the host core back (vf_ctx_set_blocking_sync)
+    bool blocking_sync = false;
     VfMt19937 rng;
     uint32_t crand = 80;  // state of the C runtime's rand() as the reference's platform implements it (MSVC LCG); srand(_seed), CADScene.cpp:36
     // scratch arenas, grown on demand (FloodFracturer.cpp:116-120 "grown on demand")
@@ -120,6 +122,16 @@ struct vf_grid {
     float aabb_max[3] = { 0.5f, 0.5f, 0.5f };
     size_t n() const { return (size_t)X * Y * Z; }
 };
+
+// Every host wait on the context's stream goes through here.  Spinning (the runtime's default) has the lowest latency and is right
+// for one job per host core; a producer that drives more contexts than it has cores (batch mode: the SMs are filled by overlapping
+// the latency-bound rounds of several jobs) asks for blocking waits, which sleep on an event instead of burning the core.
+inline cudaError_t vf_sync(vf_ctx* c)
+{
+    if (!c->blocking_sync) return cudaStreamSynchronize(c->stream);
+    const cudaError_t e = cudaEventRecord(c->ev_block, c->stream);
+    return e != cudaSuccess ? e : cudaEventSynchronize(c->ev_block);
+}
 
 vf_status vf_scratch_reserve(vf_ctx* ctx, VfScratch& s, size_t bytes);
 vf_status vf_enter(vf_ctx* ctx);  // cudaSetDevice

@@ -285,7 +285,7 @@ extern "C" vf_status vf_voxelize(vf_grid* grid, const float* verts, uint32_t nv,
     VF_LAUNCHED(c);
     uint32_t* h_total = (uint32_t*)((char*)c->pinned + 65536);
     VF_CUDA(cudaMemcpyAsync(h_total, d_total, 4, cudaMemcpyDeviceToHost, c->stream));
-    VF_CUDA(cudaStreamSynchronize(c->stream));  // also covers the pageable verts/faces uploads
+    VF_CUDA(vf_sync(c));  // also covers the pageable verts/faces uploads
     const size_t total = *h_total;
     VF_REQUIRE(total < (1ull << 31), VF_ERR_CAPACITY, "voxelize: triangle/brick list too long (%zu)", total);
     if (need + total * 4 > c->mesh.bytes) {
@@ -294,7 +294,7 @@ extern "C" vf_status vf_voxelize(vf_grid* grid, const float* verts, uint32_t nv,
         c->mesh = VfScratch();
         VF_TRY(vf_scratch_reserve(c, c->mesh, need + total * 4 + 256));
         VF_CUDA(cudaMemcpyAsync(c->mesh.ptr, old.ptr, need, cudaMemcpyDeviceToDevice, c->stream));
-        VF_CUDA(cudaStreamSynchronize(c->stream));
+        VF_CUDA(vf_sync(c));
         VF_CUDA(cudaFree(old.ptr));
         base = (char*)c->mesh.ptr;
         d_verts = (float*)base;
@@ -631,7 +631,7 @@ extern "C" vf_status vf_voxelize_solid(vf_grid* grid, const float* verts, uint32
     }
     unsigned long long* h_occ = (unsigned long long*)((char*)c->pinned + 65536 + 64);
     VF_CUDA(cudaMemcpyAsync(h_occ, d_occ, 8, cudaMemcpyDeviceToHost, c->stream));
-    VF_CUDA(cudaStreamSynchronize(c->stream));  // also covers the pageable uploads (verts, faces, ys)
+    VF_CUDA(vf_sync(c));  // also covers the pageable uploads (verts, faces, ys)
     if (occupied_out) *occupied_out = *h_occ;
     return VF_OK;
 }
