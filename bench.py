@@ -382,6 +382,39 @@ def cpu_baseline(n, stages, steps=1):
 ALL_STAGES = ["naive", "remove_isolated", "erode", "histogram", "undo_mask"]
 
 
+def load_ref_lib():
+    """oracle/_ref/libvf_ref.so: the reference's own NaiveFracturer.cpp (buildCPU, removeIsolatedRegionsCPU) compiled in place in the
+    build container (oracle/ref_shim/Makefile); it travels to the GPU box with the snapshot.  None when it was not built."""
+    import ctypes as C
+
+    path = os.path.join(ROOT, "oracle", "_ref", "libvf_ref.so")
+    if not os.path.exists(path):
+        return None
+    try:
+        L = C.CDLL(path)
+    except OSError:
+        return None
+    u16 = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
+    u32 = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+    L.ref_naive_build_cpu.argtypes = [u16, u32, u32, C.c_uint32, C.c_int]
+    L.ref_remove_isolated_regions_cpu.argtypes = [u16, u32, u32, C.c_uint32]
+    return L
+
+
+def reference_pipeline(ref, orc, grid, seeds, noise):
+    """cfg3 on the host with as much of the REFERENCE'S OWN code as exists for the CPU: NaiveFracturer::buildCPU and
+    removeIsolatedRegionsCPU (NaiveFracturer.cpp:26-68, 111-150; serial, as written) from oracle/_ref; erosion, histogram and undoMask
+    exist only as GLSL in the reference, so those stages run the oracle's OpenMP restatement."""
+    dims = np.asarray(grid.shape, np.uint32)
+    s32 = np.ascontiguousarray(seeds, np.uint32)
+    ref.ref_naive_build_cpu(grid, dims, s32, len(s32), CFG3["dfunc"])
+    ref.ref_remove_isolated_regions_cpu(grid, dims, s32, len(s32))
+    et, es, ei, ep, eth = CFG3["erosion"]
+    orc.erode(grid, noise, et, es, ei, ep, eth)
+    orc.count_values(grid)
+    orc.undo_mask(grid, 15, False)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -389,27 +422,51 @@ def run_reference(args):
     import oracle as orc
 
     orc.use_all_cores()
-    n = args.cpu_size or 384
+    ref = None if args.ref_impl == "port" else load_ref_lib()
+    if args.ref_impl == "ref" and ref is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libvf_ref.so was not built (needs /root/reference at build time)"}))
+        return
+    # bounded sample: the reference's buildCPU is a serial loop with a std::function call per (cell, seed) — about 5 s per step at 256^3
+    n = args.cpu_size or (256 if ref is not None else 384)
     seeds = synth_seeds_dense(n, CFG3["nseeds"], rng_uniform_stream(CFG3["rng_seed"]))
     noise = noise_table(CFG3["rng_seed"] + 1000, CFG3["nnoise"])
-    for _ in range(min(args.warmup, 1)):
-        oracle_pipeline(orc, np.ones((n, n, n), np.uint16), seeds, noise, ALL_STAGES)
+
+    def step(g):
+        if ref is not None:
+            reference_pipeline(ref, orc, g, seeds, noise)
+        else:
+            oracle_pipeline(orc, g, seeds, noise, ALL_STAGES)
+
+    # one untimed step; it also sizes the sample so that the timed steps end within about two and a half minutes
+    t0 = time.perf_counter()
+    step(np.ones((n, n, n), np.uint16))
+    t_probe = time.perf_counter() - t0
+    if not args.cpu_size and t_probe * args.steps > 150.0:
+        n = max(96, int(n * (150.0 / (t_probe * args.steps)) ** (1.0 / 3.0)) // 32 * 32)
+        seeds = synth_seeds_dense(n, CFG3["nseeds"], rng_uniform_stream(CFG3["rng_seed"]))
     times = []
     for _ in range(args.steps):
         g = np.ones((n, n, n), np.uint16)
         t0 = time.perf_counter()
-        oracle_pipeline(orc, g, seeds, noise, ALL_STAGES)
+        step(g)
         times.append(time.perf_counter() - t0)
     total = float(sum(times))
     v = n**3 * args.steps / total / 1e9
+    if ref is not None:
+        kind, cores = "reference", 1
+        what = (f"cfg3-dense pipeline on a bounded {n}^3 sample: NaiveFracturer::buildCPU + removeIsolatedRegionsCPU are the reference's own code compiled in "
+                "place (oracle/_ref; serial as written, 1 core); erode + countValues + undoMask exist only as GLSL in the reference and run the oracle's "
+                f"OpenMP restatement ({orc.num_threads()} threads)")
+    else:
+        kind, cores = "port", orc.num_threads()
+        what = (f"cfg3-dense pipeline on a bounded {n}^3 sample (oracle/_ref not built; this is the CPU oracle, a restatement of NaiveFracturer::buildCPU + "
+                "erode + removeIsolatedRegionsCPU + countValues, OpenMP)")
     print(json.dumps({
         "impl": "reference", "metric": "Gvoxels/s fragmented at 512^3", "value": v, "unit": "Gvoxels/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u16 labels / f32 distances", "data": "synthetic",
-        "config": {"workload": f"cfg3-dense pipeline on a bounded {n}^3 sample (the reference has no native CPU path; this is the CPU oracle, "
-                               "a restatement of NaiveFracturer::buildCPU + erode + removeIsolatedRegionsCPU + countValues)", "stages": ALL_STAGES,
-                   "grid": [n, n, n]},
-        "cpu_baseline": {"value": v, "unit": "Gvoxels/s", "cores": orc.num_threads(), "kind": "port", "sample": f"{n}^3 dense grid x {args.steps} steps"},
+        "config": {"workload": what, "stages": ALL_STAGES, "grid": [n, n, n]},
+        "cpu_baseline": {"value": v, "unit": "Gvoxels/s", "cores": cores, "kind": kind, "sample": f"{n}^3 dense grid x {args.steps} steps"},
         "e2e": {"value": v, "unit": "Gvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -668,6 +725,9 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--cpu-size", type=int, default=0, help="edge of the CPU sample grid (default: 512 once for cpu_baseline, 384 per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-impl", default="auto", choices=["auto", "ref", "port"],
+                    help="--impl reference: ref = the reference's own buildCPU / removeIsolatedRegionsCPU from oracle/_ref (+ oracle for the GLSL-only stages), "
+                         "port = the OpenMP oracle throughout, auto = ref when oracle/_ref was built")
     ap.add_argument("--workload", default="cfg3", choices=["cfg3", "slab", "batch", "dataset"],
                     help="cfg3 = the driver's default; slab = cfg5; batch = cfg4; dataset = cfg4 through the native driver with .rle export")
     ap.add_argument("--out", default="", help="dataset workload: parent directory of the (temporary) output folder")
