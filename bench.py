@@ -579,6 +579,8 @@ def batch_measure(rank, local_rank, world, dist, meshes, warmup, jobs, mesh_pool
     for j in range(jobs):
         ctx = vf.Context(local_rank)
         ctx.setBlockingSync(block)
+        if jobs > 1:
+            ctx.setFloodLevels(8)  # throughput setting: with several jobs per GPU total tile work matters, not the latency of one flood
         grid = vf.RegularGrid(ctx, (256, 256, 256))  # allocated once at the clamp size, re-dimensioned per model (CADScene.cpp:529-543)
         ctx.reserve((256, 256, 256))
         workers.append((ctx, grid))
@@ -671,6 +673,9 @@ def run_dataset(args):
     workers = []
     for j in range(jobs):
         ctx = vf.Context(local_rank)
+        ctx.setBlockingSync(jobs * world > host_cores())
+        if jobs > 1:
+            ctx.setFloodLevels(8)
         workers.append((ctx, dataset.dataset_grid(ctx, proc), vf._capi.VfDatasetStats()))
     out = tempfile.mkdtemp(prefix=f"vf_dataset_r{rank}_", dir=args.out or None)
     my = [m for m in range(args.meshes) if m % world == rank]

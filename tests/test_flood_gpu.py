@@ -193,3 +193,23 @@ def test_c1_islands_free_cells_and_foreign_seed_cell(ctx, orc):
             want = orc.remove_isolated_regions_cpu(lab.copy(), sd)
             got = _run_c1(ctx, lab, sd)
             assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("levels", [1, 3, 8, 40, 100000])
+def test_result_does_not_depend_on_the_distance_window_or_blocking_waits(orc, vessel_grid, levels):
+    """vf_ctx_set_flood_levels / vf_ctx_set_blocking_sync are scheduling knobs: labels stay bit-exact (plain and extra-seed floods)."""
+    import voxelfragmentml_b200 as vf
+
+    c = vf.Context(0)
+    c.setFloodLevels(levels)
+    c.setBlockingSync(levels % 2 == 1)
+    seeds, _ = orc.seed_uniform(orc.Rng(80), vessel_grid, 12)
+    for dfunc in (1, 2):
+        want, _ = orc.flood(vessel_grid.copy(), seeds, dfunc)
+        got, _ = _run_flood(c, vessel_grid, seeds, dfunc)
+        assert np.array_equal(got, want)
+    wseeds = orc.make_seeds(orc.Rng(80), vessel_grid, 6, 12, merge_dfunc=0)
+    want, _ = orc.flood(vessel_grid.copy(), wseeds, orc.CHEBYSHEV)
+    got, _ = _run_flood(c, vessel_grid, wseeds, 2)
+    assert np.array_equal(got, want)
+    c.close()

@@ -121,6 +121,10 @@ class Context:
         """host waits sleep instead of spinning (more contexts than host cores)"""
         check(self._lib.vf_ctx_set_blocking_sync(self._h, int(bool(on))))
 
+    def setFloodLevels(self, levels: int):
+        """distance window of a flood round (0 = default 16: best latency; 8: best throughput with several jobs per GPU)"""
+        check(self._lib.vf_ctx_set_flood_levels(self._h, int(levels)))
+
     def synchronize(self):
         check(self._lib.vf_ctx_synchronize(self._h))
 

@@ -115,6 +115,13 @@ extern "C" vf_status vf_ctx_set_blocking_sync(vf_ctx* ctx, int on)
     return VF_OK;
 }
 
+extern "C" vf_status vf_ctx_set_flood_levels(vf_ctx* ctx, uint32_t levels)
+{
+    VF_REQUIRE(ctx != nullptr, VF_ERR_INVALID_ARGUMENT, "null context");
+    ctx->flood_levels = levels;
+    return VF_OK;
+}
+
 extern "C" vf_status vf_ctx_create(int device, vf_ctx** out) { return ctx_create(device, nullptr, false, out); }
 extern "C" vf_status vf_ctx_create_on_stream(int device, void* s, vf_ctx** out) { return ctx_create(device, s, true, out); }
 

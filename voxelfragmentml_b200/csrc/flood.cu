@@ -514,7 +514,7 @@ vf_status job_begin(vf_grid* grid, Job& j)
     j.wl.seen = j.wl.occ + nt;
     j.wl.epoch = 1;
     j.wl.lo = base + 11;
-    j.wl.levels = kLevelsPerRound;
+    j.wl.levels = c->flood_levels ? c->flood_levels : kLevelsPerRound;
     if (const char* e = std::getenv("VF_FLOOD_LEVELS")) j.wl.levels = (uint32_t)std::max(1, std::atoi(e));  // tuning knob for tools/
     j.wl.pend = (uint32_t*)((char*)base + pend_off);
     VF_CUDA(cudaMemsetAsync(base, 0, 16 * 4, c->stream));

@@ -93,6 +93,7 @@ struct vf_ctx {
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     cudaEvent_t ev_block = nullptr;  // cudaEventBlockingSync: waits that give the host core back (vf_ctx_set_blocking_sync)
     bool blocking_sync = false;
+    uint32_t flood_levels = 0;  // width of a flood round's distance window; 0 = the library default (vf_ctx_set_flood_levels)
     VfMt19937 rng;
     uint32_t crand = 80;  // state of the C runtime's rand() as the reference's platform implements it (MSVC LCG); srand(_seed), CADScene.cpp:36
     // scratch arenas, grown on demand (FloodFracturer.cpp:116-120 "grown on demand")
