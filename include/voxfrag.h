@@ -243,6 +243,26 @@ vf_status vf_synth_solid_vessel(vf_grid* g, int x_offset, uint32_t n, float base
  * (numSeeds [+ biasSeeds when numImpacts > 0]) * 2 + numExtraSeeds entries of uint32[4]) receives the seed list used. */
 vf_status vf_fracture_model(vf_grid* g, const vf_params* p, uint32_t* seeds_out, uint32_t* nseeds_out, vf_flood_stats* stats);
 
+/* ------------------------------------------------------------------ f2: per-fragment marching cubes (RegularGrid::toTriangleMesh's mesh side) */
+/* FractureParameters' marching-cubes fields (FractureParameters.h:45,56,60; defaults :93-94,105,109-110) */
+typedef struct vf_mc_params {
+    float   boundaryMCIterations;     /* 0.048: iterations = unsigned(max grid dim * this), MarchingCubes.cpp:399-400 */
+    float   boundaryMCWeight;         /* 0.2 */
+    float   nonBoundaryMCIterations;  /* 0.048 */
+    float   nonBoundaryMCWeight;      /* 0.9 */
+    int32_t marchingCubesSubdivisions;/* 1 (other values: VF_ERR_UNSUPPORTED) */
+} vf_mc_params;
+typedef struct vf_mesh vf_mesh;       /* device-resident result: vertices float[nv][4] = xyz + boundary flag, faces uint32[nf][4] = 3 vertex numbers + boundary flag */
+void      vf_mc_params_default(vf_mc_params* p);
+/* MarchingCubes::setGrid + triangulateFieldGPU (SRC/Graphics/Core/MarchingCubes.cpp:523-540, 364-432) for one fragment label: marching cubes
+ * on the padded grid (isolevel 0.5 on label == target_value, bit 15 ignored), Morton-sorted vertex fusion, model matrix
+ * (RegularGrid.cpp:478-480), boundary marking, two-pass Laplacian smoothing.  Call between fractureModel and undoMask, as
+ * prepareScene does (CADScene.cpp:813-832).  The reference's vertex / face ORDER is a race; the order here is deterministic (csrc/mesh.cu). */
+vf_status vf_marching_cubes(vf_grid* g, uint32_t target_value, const vf_mc_params* params /* NULL = defaults */, vf_mesh** out);
+vf_status vf_mesh_counts(const vf_mesh* m, uint32_t* num_vertices, uint32_t* num_faces);
+vf_status vf_mesh_download(vf_mesh* m, float* vertices /* [nv][4] */, uint32_t* faces /* [nf][4] */);
+void      vf_mesh_destroy(vf_mesh* m);
+
 /* ------------------------------------------------------------------ f1: the dataset driver (CADScene::generateDataset, CADScene.cpp:209-507) */
 /* struct FragmentationProcedure (SRC/Graphics/Core/FragmentationProcedure.h:6-60), voxel-path fields only */
 typedef struct vf_procedure {

@@ -157,6 +157,19 @@ public:
         check(vf_voxelize_solid(_h, vertices, numVertices, faces, numFaces, &occupied));
         return occupied;
     }
+    // MarchingCubes::triangulateFieldGPU for one fragment label (RegularGrid::toTriangleMesh runs it per value, RegularGrid.cpp:482-483):
+    // vertices = xyz + boundary flag, faces = three vertex numbers + boundary flag
+    void triangulateField(uint16_t targetValue, std::vector<float>& vertices4, std::vector<uint32_t>& faces4, const vf_mc_params* params = nullptr)
+    {
+        vf_mesh* m = nullptr;
+        check(vf_marching_cubes(_h, targetValue, params, &m));
+        uint32_t nv = 0, nf = 0;
+        vf_mesh_counts(m, &nv, &nf);
+        vertices4.resize(4 * (size_t)nv), faces4.resize(4 * (size_t)nf);
+        const vf_status s = vf_mesh_download(m, vertices4.data(), faces4.data());
+        vf_mesh_destroy(m);
+        check(s);
+    }
     void detectBoundaries(int boundarySize) { check(vf_detect_boundaries(_h, boundarySize)); }
     void erode(FractureParameters::ErosionType type, uint32_t convolutionSize, uint16_t numIterations, float erosionProbability, float erosionThreshold,
                int boundaryMode = 0)

@@ -115,6 +115,9 @@ def _declare(L):
     L.orc_encode_qstack.argtypes = [_u16p, _u32p, C.c_void_p, C.c_uint64]
     L.orc_encode_bing_squared.restype = C.c_uint64
     L.orc_encode_bing_squared.argtypes = [_u16p, _u32p, C.c_void_p, C.c_uint64]
+    L.orc_marching_cubes.restype = C.c_int
+    L.orc_marching_cubes.argtypes = [_u16p, _u32p, C.c_uint32, _f32p, _f32p, C.c_uint32, C.c_float, C.c_uint32, C.c_float, C.c_void_p, C.c_uint32,
+                                     C.c_void_p, C.c_uint32, _u32p]
     L.orc_num_threads.restype = C.c_int
     L.orc_set_num_threads.argtypes = [C.c_int]
 
@@ -376,6 +379,23 @@ def encode_qstack(grid) -> bytes:
     buf = np.empty(need, dtype=np.uint8)
     lib().orc_encode_qstack(grid, d, buf.ctypes.data, need)
     return buf.tobytes()
+
+
+def marching_cubes(grid, target, aabb_min, aabb_max, nb_iters=None, nb_weight=0.9, b_iters=None, b_weight=0.2):
+    """per-fragment marching cubes + vertex fusion + two-pass Laplacian smoothing; iterations default to unsigned(max dim * 0.048f)
+    (FractureParameters.h:93,109; MarchingCubes.cpp:399-400).  Returns (vertices float32[nv][4], faces uint32[nf][4])."""
+    d = _dims(grid)
+    it = int(np.float32(max(int(v) for v in d)) * np.float32(0.048))
+    nb_iters = it if nb_iters is None else nb_iters
+    b_iters = it if b_iters is None else b_iters
+    mn, mx = np.ascontiguousarray(aabb_min, np.float32), np.ascontiguousarray(aabb_max, np.float32)
+    counts = np.zeros(2, np.uint32)
+    lib().orc_marching_cubes(grid, d, int(target), mn, mx, nb_iters, nb_weight, b_iters, b_weight, None, 0, None, 0, counts)
+    v = np.zeros((int(counts[0]), 4), np.float32)
+    f = np.zeros((int(counts[1]), 4), np.uint32)
+    if len(v) and len(f):
+        lib().orc_marching_cubes(grid, d, int(target), mn, mx, nb_iters, nb_weight, b_iters, b_weight, v.ctypes.data, len(v), f.ctypes.data, len(f), counts)
+    return v, f
 
 
 def num_threads() -> int:

@@ -1506,6 +1506,165 @@ extern "C" uint64_t orc_encode_qstack(const uint16_t* grid, const uint32_t dims[
     return w.pos;
 }
 
+/* ---- f2: per-fragment marching cubes — RegularGrid::toTriangleMesh's mesh side (RegularGrid.cpp:473-486) = MarchingCubes::setGrid +
+ * triangulateFieldGPU (SRC/Graphics/Core/MarchingCubes.cpp:523-540, 364-432) over the shaders marchingCubes-comp.glsl:96-168,
+ * computeMortonCodes-comp.glsl, findSameVertices_01/02-comp.glsl, buildMarchingCubesFaces-comp.glsl, markBoundaryTriangles-comp.glsl,
+ * resetLaplacianBuffer / laplacianSmoothing / finishLaplacianSmoothing-comp.glsl, for _marchingCubesSubdivisions == 1 (the default).
+ * The reference hands out vertex slots and fused-vertex numbers with atomicAdd (marchingCubes-comp.glsl:139, findSameVertices_01:28),
+ * so the ORDER of its vertices and faces is a race; positions, connectivity and flags are not.  The deterministic rule fixed here
+ * ("what the shaders give when their threads run in index order"): triangles in (cell index, row position) order; vertices sorted by
+ * (30-bit Morton code as computed by the shader, then x, y, z) — the reference sorts by the Morton code alone, stably — and numbered in
+ * that order; a fused vertex takes position and boundary flag from its first copy.  float32 throughout, mix(a, b, w) = a*(1-w) + b*w,
+ * model matrix applied as x*scale + (min + (-scale)).  PARITY UNPINNED BY CONSTRUCTION (GLSL only, racy order). */
+namespace {
+const uint64_t kMcRows[256] = {
+#include "../voxelfragmentml_b200/csrc/mc_tritable.inc"
+};
+const int kMcCorner[8][3] = { { 0, 0, 0 }, { 0, 0, 1 }, { -1, 0, 1 }, { -1, 0, 0 }, { 0, 1, 0 }, { 0, 1, 1 }, { -1, 1, 1 }, { -1, 1, 0 } }; /* marchingCubes-comp.glsl:28-38 */
+const int kMcEdge[12][2] = { { 0, 1 }, { 1, 2 }, { 2, 3 }, { 3, 0 }, { 4, 5 }, { 5, 6 }, { 6, 7 }, { 7, 4 }, { 0, 4 }, { 1, 5 }, { 2, 6 }, { 3, 7 } }; /* :40-54 */
+inline uint32_t mc_expand_bits(uint32_t v) /* computeMortonCodes-comp.glsl expandBits */
+{
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+struct McVert {
+    float p[3];
+    float w;
+    uint32_t morton;
+};
+}  // namespace
+
+extern "C" int orc_marching_cubes(const uint16_t* grid, const uint32_t dims[3], uint32_t target, const float amin[3], const float amax[3], uint32_t nb_iters,
+                                  float nb_weight, uint32_t b_iters, float b_weight, float* verts, uint32_t cap_v, uint32_t* faces, uint32_t cap_f,
+                                  uint32_t counts[2])
+{
+    /* setGrid, MarchingCubes.cpp:523-540: dims + 2, a ring of VOXEL_FREE */
+    const int PX = (int)dims[0] + 2, PY = (int)dims[1] + 2, PZ = (int)dims[2] + 2;
+    std::vector<uint16_t> P((size_t)PX * PY * PZ, (uint16_t)ORC_VOXEL_FREE);
+    for (int x = 1; x < PX - 1; ++x)
+        for (int y = 1; y < PY - 1; ++y)
+            for (int z = 1; z < PZ - 1; ++z) P[((size_t)x * PY + y) * PZ + z] = grid[lin(x - 1, y - 1, z - 1, dims)];
+    /* march, marchingCubes-comp.glsl:96-156, cells in index order */
+    std::vector<McVert> soup;
+    const float pd[3] = { (float)PX, (float)PY, (float)PZ };
+    for (int x = 0; x < PX; ++x)
+        for (int y = 0; y < PY; ++y)
+            for (int z = 0; z < PZ; ++z) {
+                if (x == 0 || y == PY - 1 || z == PZ - 1) continue; /* :102-103 */
+                float values[8];
+                int configuration = 0;
+                for (int i = 0; i < 8; ++i) {
+                    const uint16_t v = P[((size_t)(x + kMcCorner[i][0]) * PY + (y + kMcCorner[i][1])) * PZ + (z + kMcCorner[i][2])];
+                    values[i] = (uint16_t)(v & 0x7FFFu) == (uint16_t)target ? 1.0f : 0.0f;
+                    if (values[i] < 0.5f) configuration |= 1 << i;
+                }
+                const uint64_t row = kMcRows[configuration];
+                if ((row & 0xF) == 0xF) continue;
+                const float wflag = (P[((size_t)x * PY + y) * PZ + z] >> 15) != 0 ? 1.0f : 0.0f; /* :147 */
+                auto edge_vertex = [&](int e, float out[3]) { /* findVertex :67-87 with isolevel 0.5 and values in {0, 1} */
+                    const int a = kMcEdge[e][0], b = kMcEdge[e][1];
+                    const float mu = (0.5f - values[a]) / (values[b] - values[a]);
+                    const int c[3] = { x, y, z };
+                    for (int q = 0; q < 3; ++q) {
+                        const float p1 = (float)(c[q] + kMcCorner[a][q]), p2 = (float)(c[q] + kMcCorner[b][q]);
+                        out[q] = p1 + mu * (p2 - p1);
+                    }
+                };
+                for (int t = 0; t < 5; ++t) {
+                    const int e0 = (int)((row >> (12 * t)) & 0xF);
+                    if (e0 == 0xF) break; /* rows are packed front to back */
+                    const int e1 = (int)((row >> (12 * t + 4)) & 0xF), e2 = (int)((row >> (12 * t + 8)) & 0xF);
+                    const int order[3] = { e0, e2, e1 }; /* :141-143 */
+                    for (int k = 0; k < 3; ++k) {
+                        McVert v;
+                        edge_vertex(order[k], v.p);
+                        v.w = wflag;
+                        /* computeMortonCodes-comp.glsl: (p - 0) / (numDivs - 0) * 1024, truncated */
+                        const uint32_t xx = mc_expand_bits((uint32_t)((v.p[0] / pd[0]) * 1024.0f)), yy = mc_expand_bits((uint32_t)((v.p[1] / pd[1]) * 1024.0f)),
+                                       zz = mc_expand_bits((uint32_t)((v.p[2] / pd[2]) * 1024.0f));
+                        v.morton = xx * 4 + yy * 2 + zz;
+                        soup.push_back(v);
+                    }
+                }
+            }
+    const uint32_t nsoup = (uint32_t)soup.size(), nf = nsoup / 3;
+    /* sortMortonCodes + findSameVertices_01/02 under the deterministic order */
+    std::vector<uint32_t> idx(nsoup);
+    for (uint32_t i = 0; i < nsoup; ++i) idx[i] = i;
+    std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) {
+        const McVert &A = soup[a], &B = soup[b];
+        if (A.morton != B.morton) return A.morton < B.morton;
+        for (int q = 0; q < 3; ++q)
+            if (A.p[q] != B.p[q]) return A.p[q] < B.p[q];
+        return false;
+    });
+    /* model matrix, RegularGrid.cpp:478-480 */
+    float scale[3], shift[3];
+    for (int q = 0; q < 3; ++q) scale[q] = (amax[q] - amin[q]) / (float)dims[q], shift[q] = amin[q] + (-scale[q]);
+    std::vector<float> V; /* xyzw */
+    std::vector<uint32_t> fused(nsoup);
+    for (uint32_t k = 0; k < nsoup; ++k) {
+        const McVert& v = soup[idx[k]];
+        bool fresh = k == 0;
+        if (!fresh) {
+            const McVert& u = soup[idx[k - 1]];
+            fresh = !(u.p[0] == v.p[0] && u.p[1] == v.p[1] && u.p[2] == v.p[2]); /* distance > 1e-8 on half-integer coordinates */
+        }
+        if (fresh) {
+            for (int q = 0; q < 3; ++q) V.push_back(v.p[q] * scale[q] + shift[q]);
+            V.push_back(v.w);
+        }
+        fused[idx[k]] = (uint32_t)(V.size() / 4 - 1);
+    }
+    const uint32_t nv = (uint32_t)(V.size() / 4);
+    counts[0] = nv, counts[1] = nf;
+    if (!verts || !faces || cap_v < nv || cap_f < nf) return ORC_OK;
+    std::vector<uint32_t> F((size_t)nf * 4);
+    for (uint32_t f = 0; f < nf; ++f) {
+        for (int k = 0; k < 3; ++k) F[4 * (size_t)f + k] = fused[3 * f + k]; /* buildMarchingCubesFaces-comp.glsl */
+        const float m = std::max(V[4 * (size_t)F[4 * (size_t)f] + 3], std::max(V[4 * (size_t)F[4 * (size_t)f + 1] + 3], V[4 * (size_t)F[4 * (size_t)f + 2] + 3]));
+        F[4 * (size_t)f + 3] = (uint32_t)m; /* markBoundaryTriangles-comp.glsl */
+    }
+    /* smoothSurface, MarchingCubes.cpp:498-521: non-boundary pass, then boundary pass */
+    std::vector<int32_t> L((size_t)nv * 4);
+    auto smooth = [&](uint32_t iters, float weight, bool boundary) {
+        const float tgt = boundary ? 1.0f : 0.0f;
+        for (uint32_t it = 0; it < iters; ++it) {
+            std::fill(L.begin(), L.end(), 0);
+            for (uint32_t f = 0; f < nf; ++f) { /* laplacianSmoothing-comp.glsl */
+                const uint32_t* fc = &F[4 * (size_t)f];
+                bool valid = true;
+                if (!boundary)
+                    for (int i = 0; i < 3 && valid; ++i) valid = std::fabs(V[4 * (size_t)fc[i] + 3] - tgt) < 0.00000001f;
+                if (!valid) continue;
+                for (int i = 0; i < 3; ++i) {
+                    const float* p = &V[4 * (size_t)fc[i]];
+                    const int32_t q[4] = { (int32_t)(p[0] * 10000.0f), (int32_t)(p[1] * 10000.0f), (int32_t)(p[2] * 10000.0f), 1 };
+                    for (int n = 1; n <= 2; ++n)
+                        for (int c = 0; c < 4; ++c) L[4 * (size_t)fc[(i + n) % 3] + c] += q[c];
+                }
+            }
+            for (uint32_t v = 0; v < nv; ++v) { /* finishLaplacianSmoothing-comp.glsl */
+                float* p = &V[4 * (size_t)v];
+                const int32_t* l = &L[4 * (size_t)v];
+                if (std::fabs(p[3] - tgt) < 0.00000001f && l[3] > 0)
+                    for (int c = 0; c < 3; ++c) {
+                        const float avg = (float)l[c] / (float)l[3] / 10000.0f;
+                        p[c] = p[c] * (1.0f - weight) + avg * weight;
+                    }
+            }
+        }
+    };
+    smooth(nb_iters, nb_weight, false);
+    smooth(b_iters, b_weight, true);
+    std::memcpy(verts, V.data(), V.size() * sizeof(float));
+    std::memcpy(faces, F.data(), F.size() * sizeof(uint32_t));
+    return ORC_OK;
+}
+
 extern "C" void orc_set_num_threads(int n)
 {
 #ifdef _OPENMP

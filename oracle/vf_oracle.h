@@ -137,6 +137,10 @@ int      orc_decode_rle(const uint8_t* data, uint64_t len, uint32_t dims_out[3],
 uint64_t orc_encode_bing_squared(const uint16_t* grid, const uint32_t dims[3], uint8_t* out, uint64_t cap);
 /* RegularGrid::exportVox (RegularGrid.cpp:740-798) through VoxWriter (Libraries/MagicaVoxel_File_Writer/VoxWriter.cpp:449-540) */
 uint64_t orc_encode_vox(const uint16_t* grid, const uint32_t dims[3], int squared, uint8_t* out, uint64_t cap);
+/* f2: per-fragment marching cubes (MarchingCubes::triangulateFieldGPU, MarchingCubes.cpp:364-432 + shaders); verts float[nv][4] =
+ * xyz + boundary flag, faces uint32[nf][4] = three vertex numbers + boundary flag; counts = {nv, nf}; buffers too small = size query */
+int orc_marching_cubes(const uint16_t* grid, const uint32_t dims[3], uint32_t target, const float amin[3], const float amax[3], uint32_t nb_iters,
+                       float nb_weight, uint32_t b_iters, float b_weight, float* verts, uint32_t cap_v, uint32_t* faces, uint32_t cap_f, uint32_t counts[2]);
 /* exportQuadStack, RegularGrid.cpp:716-725 over SRC/DataStructures/QuadStack.h + GStack.h */
 uint64_t orc_encode_qstack(const uint16_t* grid, const uint32_t dims[3], uint8_t* out, uint64_t cap);
 

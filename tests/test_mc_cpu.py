@@ -1,0 +1,94 @@
+"""f2 on the host: the packed marching-cubes case table (consistency everywhere, identity with the reference's copy where /root/reference
+exists) and properties of the oracle's marching cubes + fusion + smoothing that do not depend on any other implementation."""
+import os
+import re
+from collections import Counter
+
+import numpy as np
+
+from conftest import ROOT, random_blob_grid
+
+EDGES = [(0, 1), (1, 2), (2, 3), (3, 0), (4, 5), (5, 6), (6, 7), (7, 4), (0, 4), (1, 5), (2, 6), (3, 7)]  # marchingCubes-comp.glsl:40-54
+
+
+def _rows():
+    text = open(os.path.join(ROOT, "voxelfragmentml_b200", "csrc", "mc_tritable.inc")).read()
+    words = [int(w, 16) for w in re.findall(r"0x([0-9A-F]{16})ull", text)]
+    assert len(words) == 256
+    rows = []
+    for w in words:
+        nib = [(w >> (4 * k)) & 0xF for k in range(16)]
+        n = nib.index(0xF)
+        assert n % 3 == 0 and n <= 15 and all(v == 0xF for v in nib[n:])
+        rows.append(nib[:n])
+    return rows
+
+
+def test_case_table_is_consistent_with_the_corner_numbering():
+    rows = _rows()
+    for case, row in enumerate(rows):
+        cut = {e for e, (a, b) in enumerate(EDGES) if ((case >> a) & 1) != ((case >> b) & 1)}
+        assert set(row) <= cut and all(v < 12 for v in row), case           # a triangle only uses edges its case cuts
+        assert (len(row) == 0) == (case in (0, 255))
+        assert set(row) == cut                                               # ... and every cut edge carries surface
+    assert max(len(r) for r in rows) == 15
+
+
+def test_case_table_equals_the_reference_copy():
+    src = "/root/reference/MeshFragments/Source/Graphics/Core/MarchingCubes.cpp"
+    if not os.path.exists(src):
+        import pytest
+
+        pytest.skip("reference tree not present")
+    text = open(src).read()
+    body = text[text.index("_triangleTable[256 * 16]"):]
+    vals = [int(v) for v in re.findall(r"-?\d+", body[body.index("{") + 1:body.index("};")])]
+    want = [[v for v in vals[16 * i:16 * i + 16] if v >= 0] for i in range(256)]
+    assert _rows() == want
+
+
+def _edge_use(f):
+    c = Counter()
+    for t in f[:, :3]:
+        for a, b in ((t[0], t[1]), (t[1], t[2]), (t[2], t[0])):
+            c[(min(int(a), int(b)), max(int(a), int(b)))] += 1
+    return c
+
+
+def test_fragment_surface_is_closed_and_fused(orc):
+    """every fragment of a labelled blob gives a closed 2-manifold-ish surface: each edge is shared by an even number of faces, no
+    duplicated vertex positions before smoothing, flags in {0, 1}, coordinates inside the AABB grown by one cell."""
+    occ = random_blob_grid((28, 24, 30), 3)
+    seeds = np.uint32([[5, 5, 5, 2], [20, 18, 22, 3], [12, 20, 8, 4]])
+    lab = orc.detect_boundaries(orc.naive((occ != 0).astype(np.uint16), seeds, 0), 1)
+    mn, mx = np.float32([-0.4, -0.3, -0.5]), np.float32([0.4, 0.3, 0.5])
+    for target in (2, 3, 4):
+        v, f = orc.marching_cubes(lab, target, mn, mx, nb_iters=0, b_iters=0)
+        assert len(f) > 0 and f[:, :3].max() == len(v) - 1
+        assert all(n % 2 == 0 for n in _edge_use(f).values())
+        assert len(np.unique(v[:, :3], axis=0)) == len(v)
+        assert set(np.unique(v[:, 3])) <= {0.0, 1.0} and set(np.unique(f[:, 3])) <= {0, 1}
+        cell = (mx - mn) / np.float32(lab.shape)
+        assert (v[:, :3] >= mn - cell - 1e-6).all() and (v[:, :3] <= mx + cell + 1e-6).all()
+        # a face is a boundary face iff one of its vertices is
+        assert np.array_equal(f[:, 3], v[f[:, :3], 3].max(axis=1).astype(np.uint32))
+        vs, fs = orc.marching_cubes(lab, target, mn, mx, nb_iters=4, b_iters=4)
+        assert np.array_equal(fs, f) and not np.array_equal(vs[:, :3], v[:, :3])  # smoothing moves vertices, never the connectivity
+
+
+def test_single_voxel_and_absent_label(orc):
+    g = np.zeros((5, 5, 5), np.uint16)
+    g[2, 2, 2] = 7
+    v, f = orc.marching_cubes(g, 7, np.float32([0, 0, 0]), np.float32([5, 5, 5]), nb_iters=0, b_iters=0)
+    assert len(v) == 6 and len(f) == 8  # an octahedron around the cell
+    # padded-grid vertex p maps to p * 1 + (0 - 1): the six edge midpoints around cell (2, 2, 2) whose padded centre is 3
+    assert sorted(map(tuple, v[:, :3].tolist())) == sorted([(1.5, 2.0, 2.0), (2.5, 2.0, 2.0), (2.0, 1.5, 2.0), (2.0, 2.5, 2.0), (2.0, 2.0, 1.5), (2.0, 2.0, 2.5)])
+    v, f = orc.marching_cubes(g, 9, np.float32([0, 0, 0]), np.float32([5, 5, 5]))
+    assert len(v) == 0 and len(f) == 0
+
+
+def test_fragment_touching_the_grid_faces_is_closed_by_the_padding(orc):
+    g = np.full((6, 4, 5), 2, np.uint16)
+    v, f = orc.marching_cubes(g, 2, np.float32([0, 0, 0]), np.float32([6, 4, 5]), nb_iters=0, b_iters=0)
+    assert all(n == 2 for n in _edge_use(f).values())
+    assert len(v) - len(_edge_use(f)) + len(f) == 2  # Euler characteristic of a sphere

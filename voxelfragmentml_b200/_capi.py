@@ -28,6 +28,11 @@ class VfParams(C.Structure):
     ]
 
 
+class VfMcParams(C.Structure):
+    _fields_ = [("boundaryMCIterations", C.c_float), ("boundaryMCWeight", C.c_float), ("nonBoundaryMCIterations", C.c_float),
+                ("nonBoundaryMCWeight", C.c_float), ("marchingCubesSubdivisions", C.c_int32)]
+
+
 class VfProcedure(C.Structure):
     """struct vf_procedure == FragmentationProcedure's voxel-path fields (FragmentationProcedure.h:6-60)."""
 
@@ -109,6 +114,11 @@ SIGNATURES = {
     "vf_histogram": (C.c_int, [_vp, _vp, C.POINTER(C.c_uint64)]),
     "vf_histogram_undo_mask": (C.c_int, [_vp, _vp, C.POINTER(C.c_uint64)]),
     "vf_export": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int]),
+    "vf_mc_params_default": (None, [C.POINTER(VfMcParams)]),
+    "vf_marching_cubes": (C.c_int, [_vp, _u32, C.POINTER(VfMcParams), C.POINTER(_vp)]),
+    "vf_mesh_counts": (C.c_int, [_vp, C.POINTER(_u32), C.POINTER(_u32)]),
+    "vf_mesh_download": (C.c_int, [_vp, _vp, _vp]),
+    "vf_mesh_destroy": (None, [_vp]),
     "vf_procedure_default": (None, [C.POINTER(VfProcedure)]),
     "vf_dataset_dims_rule": (None, [_vp, _vp, C.c_int32, C.c_int32, _vp]),
     "vf_dataset_iterations": (C.c_int32, [C.POINTER(VfProcedure), C.c_int32]),

@@ -253,6 +253,23 @@ class RegularGrid:
         check(self._lib.vf_voxelize_solid(self._h, ptr(v), len(v), ptr(f), len(f), C.byref(occ)))
         return int(occ.value)
 
+    # ---- f2
+    def triangulateField(self, targetValue: int, boundaryMCIterations=0.048, boundaryMCWeight=0.2, nonBoundaryMCIterations=0.048, nonBoundaryMCWeight=0.9):
+        """MarchingCubes::triangulateFieldGPU for one fragment label (what RegularGrid::toTriangleMesh runs per value, RegularGrid.cpp:482-483):
+        -> (vertices float32[nv][4] = xyz + boundary flag, faces uint32[nf][4] = three vertex numbers + boundary flag)."""
+        mp = _capi.VfMcParams(boundaryMCIterations, boundaryMCWeight, nonBoundaryMCIterations, nonBoundaryMCWeight, 1)
+        h = C.c_void_p()
+        check(self._lib.vf_marching_cubes(self._h, int(targetValue), C.byref(mp), C.byref(h)))
+        try:
+            nv, nf = C.c_uint32(0), C.c_uint32(0)
+            check(self._lib.vf_mesh_counts(h, C.byref(nv), C.byref(nf)))
+            v = np.zeros((nv.value, 4), np.float32)
+            f = np.zeros((nf.value, 4), np.uint32)
+            check(self._lib.vf_mesh_download(h, ptr(v) if nv.value else None, ptr(f) if nf.value else None))
+        finally:
+            self._lib.vf_mesh_destroy(h)
+        return v, f
+
     # ---- C1..C4
     def detectBoundaries(self, boundarySize: int = 1):
         check(self._lib.vf_detect_boundaries(self._h, int(boundarySize)))
