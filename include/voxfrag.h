@@ -273,6 +273,8 @@ typedef struct vf_procedure {
     int32_t   exportGrid;           /* FractureParameters::_exportGrid, :52: 1 */
     /* -- extensions (0 = reference behaviour / north-star occupancy) -- */
     int32_t   solidVoxelization;    /* 0: SAT surface occupancy (vf_voxelize); 1: Tetravoxelizer occupancy (vf_voxelize_solid) */
+    int32_t   exportMesh;           /* 1: per fragment marching cubes -> <itFile>_<idx>.binm (CADModel::saveBinary) + mesh metadata rows, i.e. the reference's
+                                       _exportMesh with an empty _targetTriangles list (CADScene.cpp:344-420; simplification is not on this path); default 0 */
     int32_t   writerThreads;        /* file writers running beside the GPU loop (0 = write synchronously like the reference); default 2 */
 } vf_procedure;
 

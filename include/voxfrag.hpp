@@ -368,6 +368,7 @@ struct FragmentationProcedure {
     size_t _maxFragmentsModel;
     std::string _startVessel = "", _searchExtension = ".obj";
     bool _exportGrid;
+    bool _exportMesh = false;         // fragment meshes as .binm + mesh metadata rows (the reference's _exportMesh with _targetTriangles empty)
     bool _solidVoxelization = false;  // extension: Tetravoxelizer occupancy instead of the SAT surface occupancy
     int _writerThreads = 2;           // extension: file writers beside the GPU loop
 
@@ -388,6 +389,7 @@ struct FragmentationProcedure {
         p.fragmentInterval[0] = _fragmentInterval.x, p.fragmentInterval[1] = _fragmentInterval.y;
         p.iterationInterval[0] = _iterationInterval.x, p.iterationInterval[1] = _iterationInterval.y;
         p.maxFragmentsModel = _maxFragmentsModel, p.exportGrid = _exportGrid, p.solidVoxelization = _solidVoxelization, p.writerThreads = _writerThreads;
+        p.exportMesh = _exportMesh;
         return p;
     }
 };

@@ -21,6 +21,7 @@ def _replay(orc, name, v, f, proc, rng, solid=False):
     ext = ["rle", "qstack", "vox", "bing"][fp._exportGridExtension]
     files = {f"{name}/{name}_grid_{md}r.{ext}": enc(grid)}
     rows, generated, fragmentations = [], 0, 0
+    mesh_rows = []
     n0, n1 = proc._fragmentInterval
     for nfr in range(n0, n1 + 1):
         if generated >= proc._maxFragmentsModel:
@@ -32,14 +33,52 @@ def _replay(orc, name, v, f, proc, rng, solid=False):
             seeds = orc.make_seeds(rng, grid, nfr, 2 * nfr, merge_dfunc=fp._mergeSeedsDistanceFunction)
             grid, _ = orc.flood(grid, seeds, fp._distanceFunction)
             grid = orc.detect_boundaries(grid, 1)
-            counts, _ = orc.count_values(grid)
-            grid = orc.undo_mask(grid)
+            counts, occupied = orc.count_values(grid)
             rel = f"{name}/{name}_{nfr}f_{md}r_{it}it.{ext}"
+            if proc._exportMesh:  # toTriangleMesh before undoMask; CADModel::saveBinary layout
+                for idx, label in enumerate(int(v) for v in np.nonzero(counts)[0]):
+                    mv, mf = orc.marching_cubes(grid, label, mn, mx)
+                    vb = np.zeros((len(mv), 16), np.float32)
+                    vb[:, :3] = mv[:, :3]
+                    fb = np.zeros((len(mf), 4), np.uint32)
+                    fb[:, :3] = mf[:, :3]
+                    stem = rel[: -len(ext) - 1] + f"_{idx}"
+                    files[stem + ".binm"] = np.uint32(len(mv)).tobytes() + vb.tobytes() + np.uint32(len(mf)).tobytes() + fb.tobytes()
+                    pct = np.float32(counts[label]) / np.float32(occupied)
+                    mesh_rows.append(f"{stem}.binm\t{idx}\t{dims[0]}x{dims[1]}x{dims[2]}\t{counts[label]}\t{occupied}\t{'%g' % float(pct)}\t{len(mv)}\t{len(mf)}\t")
+            grid = orc.undo_mask(grid)
             files[rel] = enc(grid)
             rows.append((rel, dims))
             generated += int((counts[2:] != 0).sum())
             fragmentations += 1
+    _replay.mesh_rows = mesh_rows
     return files, rows, generated, fragmentations, md, dims
+
+
+def test_dataset_model_with_fragment_meshes(orc, tmp_path):
+    """exportMesh: every fragment's marching-cubes mesh as .binm (CADModel::saveBinary layout) and the mesh metadata rows"""
+    import voxelfragmentml_b200 as vf
+    from voxelfragmentml_b200 import dataset, synth
+
+    v, f = synth.vessel_mesh(1, n_ang=36, n_prof=18)
+    proc = vf.FragmentationProcedure(_fragmentInterval=(2, 3), _iterationInterval=(2, 1), _exportMesh=True)
+    proc._fractureParameters._clampVoxelMetricUnit = 44
+    proc._fractureParameters._voxelPerMetricUnit = 44
+    ctx = vf.Context(0)
+    ctx.initSeed(80)
+    grid = dataset.dataset_grid(ctx, proc)
+    dest = str(tmp_path / "out") + "/"
+    st = dataset.generate_model(grid, proc, "VS_02", v, f, dest)
+    files, rows, generated, fragmentations, md, dims = _replay(orc, "VS_02", v, f, proc, orc.Rng(80))
+    assert sum(k.endswith(".binm") for k in files) == generated > 0
+    for rel, want in files.items():
+        assert open(os.path.join(dest, rel), "rb").read() == want, rel
+    meta = open(os.path.join(dest, "VS_02", f"VS_02_{md}_metadata_mesh.txt")).read().split("\n")
+    assert meta[0] == "Filename\tFragment id\tVoxelization size\tVoxels\tOccupied voxels\tPercentage\tVertices\tFaces" and meta[-1] == ""
+    assert meta[1:-1] == [dest + r for r in _replay.mesh_rows]
+    assert st["files"] == len(files) + 3 and st["fragments"] == generated
+    grid.close()
+    ctx.close()
 
 
 @pytest.mark.parametrize("ext,solid,writers", [(0, False, 2), (0, True, 0), (3, False, 1), (1, False, 2)])

@@ -37,7 +37,8 @@ class VfProcedure(C.Structure):
     """struct vf_procedure == FragmentationProcedure's voxel-path fields (FragmentationProcedure.h:6-60)."""
 
     _fields_ = [("fractureParameters", VfParams), ("fragmentInterval", C.c_int32 * 2), ("iterationInterval", C.c_int32 * 2),
-                ("maxFragmentsModel", C.c_uint64), ("exportGrid", C.c_int32), ("solidVoxelization", C.c_int32), ("writerThreads", C.c_int32)]
+                ("maxFragmentsModel", C.c_uint64), ("exportGrid", C.c_int32), ("solidVoxelization", C.c_int32), ("exportMesh", C.c_int32),
+                ("writerThreads", C.c_int32)]
 
 
 class VfDatasetStats(C.Structure):

@@ -9,8 +9,9 @@
 //
 // Not on this path (SURVEY §8 out of scope): Assimp loading (a minimal Wavefront .obj reader stands in: v / f records, fan
 // triangulation, CADModel::load's normalisation :148-152), marching cubes -> fragment meshes, point clouds, zip post-processing.
-// Consequently the mesh / point-cloud metadata files hold their header only, as in the reference with _exportMesh /
-// _exportPointCloud switched off.
+// Fragment meshes (marching cubes, csrc/mesh.cu) are written as `.binm` with their metadata rows when the procedure asks for them
+// (exportMesh: the reference's behaviour with an empty _targetTriangles list; mesh simplification is not on this path); the
+// point-cloud metadata file holds its header only, as in the reference with _exportPointCloud switched off.
 //
 // Host design: the grid never leaves the GPU inside the loop — seeds are tested on the device, `.rle` runs are found on the
 // device — and finished byte streams go to a small pool of writer threads so that file I/O overlaps the next fragmentation
@@ -151,6 +152,22 @@ vf_status export_async(vf_grid* g, const std::string& base, int type, int square
     return VF_OK;
 }
 
+// CADModel::saveBinary (SRC/Graphics/Core/CADModel.cpp:839-855): uint32 numVertices, numVertices x Model3D::VertexGPUData (64 bytes: position
+// + padding, normal + padding, texture coordinate + padding, tangent + padding — everything but the position is zero in dataset mode,
+// where CADModel::insert value-initialises the struct (:93-101) and endInsertionBatch skips computeMeshData (:66-83)), uint32 numTriangles,
+// numTriangles x Model3D::FaceGPUData (uvec3 vertices + modelCompID = 0)
+std::vector<uint8_t> encode_binm(const std::vector<float>& v4, const std::vector<uint32_t>& f4)
+{
+    const uint32_t nv = (uint32_t)(v4.size() / 4), nf = (uint32_t)(f4.size() / 4);
+    std::vector<uint8_t> out(8 + (size_t)nv * 64 + (size_t)nf * 16, 0);
+    uint8_t* p = out.data();
+    std::memcpy(p, &nv, 4), p += 4;
+    for (uint32_t i = 0; i < nv; ++i, p += 64) std::memcpy(p, &v4[4 * (size_t)i], 12);
+    std::memcpy(p, &nf, 4), p += 4;
+    for (uint32_t i = 0; i < nf; ++i, p += 16) std::memcpy(p, &f4[4 * (size_t)i], 12);
+    return out;
+}
+
 std::string dims_str(const uint32_t d[3])
 {
     return std::to_string(d[0]) + "x" + std::to_string(d[1]) + "x" + std::to_string(d[2]);
@@ -173,6 +190,7 @@ extern "C" void vf_procedure_default(vf_procedure* p)
     p->maxFragmentsModel = 1000;                                // :16
     p->exportGrid = 1;                                          // :52
     p->solidVoxelization = 0;
+    p->exportMesh = 0;
     p->writerThreads = 2;
 }
 
@@ -243,7 +261,7 @@ extern "C" vf_status vf_dataset_model(vf_grid* g, const vf_procedure* proc, cons
     }
     VF_TRY(vf_ctx_synchronize(c));
     local.seconds_voxelize += now() - t0;
-    std::vector<std::string> gridRows;  // VOXEL metadata rows (:333-337), in order
+    std::vector<std::string> gridRows, meshRows;  // VOXEL / MESH metadata rows (:333-337, :413-418), in order
     if (proc->exportGrid) {  // :291-292 -> exportGrid(params, folder) :89
         t0 = now();
         VF_TRY(export_async(g, meshFolder + name + "_grid_" + std::to_string(maxDimension) + "r", ext, 1, pool, &local));
@@ -264,9 +282,38 @@ extern "C" vf_status vf_dataset_model(vf_grid* g, const vf_procedure* proc, cons
             VF_TRY(vf_reset_filling(g));                                   // fractureGrid -> rebuildGrid (:174, :835-838)
             VF_TRY(vf_fracture_model(g, &fp, nullptr, nullptr, nullptr));  // :175
             uint64_t occupied = 0;                                          // prepareScene -> toTriangleMesh: countValues (:813, RegularGrid.cpp:443-471)
-            VF_TRY(vf_histogram_undo_mask(g, counts.data(), &occupied));  // ... and undoMask (:832), one pass
-            local.seconds_fracture += now() - t0;
             uint64_t fragments = 0;
+            if (!proc->exportMesh) {
+                VF_TRY(vf_histogram_undo_mask(g, counts.data(), &occupied));  // ... and undoMask (:832), one pass
+            } else {
+                // toTriangleMesh (RegularGrid.cpp:443-486): one mesh per value in ascending order, before undoMask clears the boundary tags
+                VF_TRY(vf_histogram(g, counts.data(), &occupied));
+                uint32_t idx = 0;
+                for (uint32_t v = 2; v < VF_HISTOGRAM_BINS; ++v) {
+                    if (!counts[v]) continue;
+                    vf_mesh* mesh = nullptr;
+                    VF_TRY(vf_marching_cubes(g, v, nullptr, &mesh));
+                    uint32_t nv = 0, nf = 0;
+                    vf_mesh_counts(mesh, &nv, &nf);
+                    auto v4 = std::make_shared<std::vector<float>>(4 * (size_t)nv);
+                    auto f4 = std::make_shared<std::vector<uint32_t>>(4 * (size_t)nf);
+                    const vf_status ds = vf_mesh_download(mesh, v4->data(), f4->data());
+                    vf_mesh_destroy(mesh);
+                    VF_TRY(ds);
+                    local.bytes_downloaded += 16ull * nv + 16ull * nf;
+                    // CADScene.cpp:344-420 with _targetTriangles empty: <itFile>_<idx>.binm, and the fragment's metadata row (:413-418, exportMetadata :605-615)
+                    const std::string filename = itFile + "_" + std::to_string(idx);
+                    std::ostringstream row;
+                    row << filename << ".binm\t" << idx << "\t" << dims_str(dims) << "\t" << counts[v] << "\t" << (uint32_t)occupied << "\t"
+                        << (float)counts[v] / static_cast<float>((uint32_t)occupied) << "\t" << nv << "\t" << nf << "\t";
+                    meshRows.push_back(row.str());
+                    pool.submit([filename, v4, f4] { return write_file(filename + ".binm", encode_binm(*v4, *f4)); });
+                    ++local.files;
+                    ++idx;
+                }
+                VF_TRY(vf_undo_mask(g));  // :832
+            }
+            local.seconds_fracture += now() - t0;
             for (uint32_t v = 2; v < VF_HISTOGRAM_BINS; ++v) fragments += counts[v] != 0;
             if (proc->exportGrid) {  // :325-338
                 t0 = now();
@@ -291,6 +338,7 @@ extern "C" vf_status vf_dataset_model(vf_grid* g, const vf_procedure* proc, cons
         meshOut << "Filename\tFragment id\tVoxelization size\tVoxels\tOccupied voxels\tPercentage\tVertices\tFaces" << std::endl;
         pcOut << "Filename\tVoxelization size\tPoints" << std::endl;
         for (const std::string& r : gridRows) gridOut << r << std::endl;
+        for (const std::string& r : meshRows) meshOut << r << std::endl;
         local.files += 3;
     }
     t0 = now();

@@ -26,6 +26,7 @@ class FragmentationProcedure:
         self._exportGrid = True
         self._startVessel = ""
         self._searchExtension = ".obj"
+        self._exportMesh = False          # fragment meshes as .binm + mesh metadata rows (the reference's _exportMesh with _targetTriangles empty)
         self._solidVoxelization = False   # extension: Tetravoxelizer occupancy instead of the SAT surface occupancy
         self._writerThreads = 2           # extension: asynchronous file writers
         for k, v in kw.items():
@@ -41,6 +42,7 @@ class FragmentationProcedure:
         c.maxFragmentsModel = int(self._maxFragmentsModel)
         c.exportGrid = int(bool(self._exportGrid))
         c.solidVoxelization = int(bool(self._solidVoxelization))
+        c.exportMesh = int(bool(self._exportMesh))
         c.writerThreads = int(self._writerThreads)
         return c
 
