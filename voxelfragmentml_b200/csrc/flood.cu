@@ -262,20 +262,22 @@ __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __re
     uint32_t* misc = pnd + kThreads;     // [0..3] neighbour-tile mask, [4] lowest deferred level
     const unsigned bar = (unsigned)__cvta_generic_to_shared(misc + 8);  // 8-byte aligned mbarrier for the TMA loads
     unsigned parity = 0;
-    if (use_tma) {
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-    }
-
     const uint32_t count = wl.count[round % 3];
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     if (blockIdx.x == 0 && t == 0) {
         wl.count[(round + 2) % 3] = 0;
         wl.lo[(round + 2) % 3] = kNoLevel;
         if (count) atomicAdd(&wl.stats[ST_ROUNDS], 1u);
+    }
+    // Rounds are launched in batches without knowing how long the worklists are: CTAs beyond the list — all of them once the flood
+    // has converged — leave before they set anything up, so that an empty round costs the GPU (and the other jobs sharing it) nothing.
+    if (blockIdx.x >= count) return;
+    if (use_tma) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
     }
     const uint32_t lo = wl.lo[round % 3];
     const uint32_t hi = lo >= kNoLevel - wl.levels ? kNoLevel : lo + wl.levels;  // levels this round may assign: < hi
