@@ -29,6 +29,25 @@ sys.path.insert(0, ROOT)
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """The driver reads ONE JSON line from stdout.  Libraries write there too (NCCL prints its version banner with printf at communicator
+    creation, whatever NCCL_DEBUG_FILE says), so fd 1 is pointed at stderr for the whole run and the JSON line goes to a saved copy of it."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit_json(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(line + "\n")
+    out.flush()
+
+
 def load_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -133,7 +152,6 @@ def run_cuda(args):
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only (NCCL prints its version banner there otherwise)
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
@@ -340,7 +358,7 @@ def run_cuda(args):
     if rank == 0 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args.cpu_size or 512, stages_run)
     if rank == 0:
-        print(json.dumps(out))
+        emit_json(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -425,7 +443,7 @@ def run_reference(args):
     orc.use_all_cores()
     ref = None if args.ref_impl == "port" else load_ref_lib()
     if args.ref_impl == "ref" and ref is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libvf_ref.so was not built (needs /root/reference at build time)"}))
+        emit_json(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libvf_ref.so was not built (needs /root/reference at build time)"}))
         return
     # bounded sample: the reference's buildCPU is a serial loop with a std::function call per (cell, seed) — about 5 s per step at 256^3
     n = args.cpu_size or (256 if ref is not None else 384)
@@ -462,7 +480,7 @@ def run_reference(args):
         kind, cores = "port", orc.num_threads()
         what = (f"cfg3-dense pipeline on a bounded {n}^3 sample (oracle/_ref not built; this is the CPU oracle, a restatement of NaiveFracturer::buildCPU + "
                 "erode + removeIsolatedRegionsCPU + countValues, OpenMP)")
-    print(json.dumps({
+    emit_json(json.dumps({
         "impl": "reference", "metric": "Gvoxels/s fragmented at 512^3", "value": v, "unit": "Gvoxels/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u16 labels / f32 distances", "data": "synthetic",
@@ -486,7 +504,6 @@ def _dist_setup():
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     return rank, local_rank, world, dist
 
@@ -536,7 +553,7 @@ def run_slab(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total, moved, maxd = float(tt[0]), float(tt[1]), float(tt[2])
     if rank == 0:
-        print(json.dumps({
+        emit_json(json.dumps({
             "metric": "Gvoxels/s flood-fragmented, one grid over N GPUs", "value": n**3 * args.steps / total / 1e9, "unit": "Gvoxels/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32 keys (dist<<15|order)", "data": "synthetic",
@@ -639,7 +656,7 @@ def run_batch(args):
     jobs = args.jobs or default_jobs(world)
     dt, checksum, npool = batch_measure(rank, local_rank, world, dist, args.meshes, args.warmup, jobs, args.mesh_pool, args.blocking_sync)
     if rank == 0:
-        print(json.dumps({
+        emit_json(json.dumps({
             "metric": "models/s batch voxelize+fragment", "value": args.meshes / dt, "unit": "models/s", "n_gpus": world, "steps": args.meshes,
             "warmup": args.warmup, "ms_per_step": dt / args.meshes * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u16 labels", "data": "synthetic",
@@ -711,7 +728,7 @@ def run_dataset(args):
         dt = float(tt[0])
     if rank == 0:
         tot = {k: sum(getattr(w[2], k) for w in workers) for k, _ in workers[0][2]._fields_}
-        print(json.dumps({
+        emit_json(json.dumps({
             "metric": "models/s batch voxelize+fragment+export", "value": args.meshes / dt, "unit": "models/s", "n_gpus": world, "steps": args.meshes,
             "warmup": args.warmup, "ms_per_step": dt / args.meshes * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u16 labels", "data": "synthetic",
@@ -746,6 +763,7 @@ def main():
     ap.add_argument("--no-batch", action="store_true", help="default workload: skip the short cfg4 batch measurement reported under \"batch\"")
     ap.add_argument("--mesh-pool", type=int, default=8, help="batch workload: distinct synthetic shapes generated up front")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "slab":
