@@ -180,3 +180,33 @@ def test_merge_seeds_host_matches_oracle(orc):
         extra = np.concatenate([rs.randint(0, 60, size=(20, 3)), np.zeros((20, 1), int)], 1).astype(np.uint32)
         seeds = np.concatenate([frags, extra])
         assert np.array_equal(vf.Seeder.mergeSeeds(frags, seeds, dfunc), orc.merge_seeds(frags, seeds, dfunc))
+
+
+def test_ctypes_struct_layouts_match_the_header(tmp_path):
+    """sizeof / offsetof of every struct that crosses the C ABI, compiled from include/voxfrag.h, against the ctypes mirrors"""
+    import ctypes as C
+    import subprocess
+
+    from conftest import ROOT
+
+    from voxelfragmentml_b200 import _capi
+
+    structs = {"vf_params": _capi.VfParams, "vf_flood_stats": _capi.VfFloodStats, "vf_procedure": _capi.VfProcedure,
+               "vf_dataset_stats": _capi.VfDatasetStats, "vf_mc_params": _capi.VfMcParams}
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "voxfrag.h"', 'int main(void) {']
+    for name, cls in structs.items():
+        src.append(f'printf("{name} %zu", sizeof({name}));')
+        for field, _ in cls._fields_:
+            src.append(f'printf(" %zu", offsetof({name}, {field}));')
+        src.append('printf("\\n");')
+    src.append('return 0; }')
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    for line in out:
+        name, size, *offs = line.split()
+        cls = structs[name]
+        assert int(size) == C.sizeof(cls), name
+        assert [int(o) for o in offs] == [getattr(cls, f).offset for f, _ in cls._fields_], name
