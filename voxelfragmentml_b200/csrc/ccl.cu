@@ -26,7 +26,6 @@
 
 namespace vfccl {
 
-constexpr uint32_t NONE = 0xFFFFFFFFu;
 constexpr uint32_t KEEP = 0x80000000u;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 enum { MODE_C1 = 0, MODE_F3 = 1 };
