@@ -48,7 +48,7 @@ def test_detect_boundaries_twice_and_undo_mask(ctx, orc, labelled_vessel):
     g.close()
 
 
-@pytest.mark.parametrize("shape", [(19, 23, 70), (8, 8, 64), (9, 17, 65), (3, 2, 5)])
+@pytest.mark.parametrize("shape", [(19, 23, 70), (8, 8, 64), (9, 17, 65), (3, 2, 5), (19, 23, 68), (16, 9, 140), (9, 9, 4), (8, 8, 12), (20, 20, 76)])
 def test_detect_boundaries_ragged(ctx, orc, shape):
     g0 = random_blob_grid(shape, 1, fill=0.6, smooth=0)
     lab = orc.naive(g0.copy(), pick_seeds(g0, min(5, int((g0 != 0).sum())), 3), 1)
@@ -82,6 +82,27 @@ def test_erode_probability_threshold_variants(ctx, orc):
         g.erode(1, 3, 3, prob, thr, noise=noise)
         assert np.array_equal(g.updateGrid(), want)
         g.close()
+
+
+@pytest.mark.parametrize("shape", [(30, 26, 68), (17, 40, 140), (12, 12, 12), (9, 10, 4)])
+def test_stencils_on_grids_whose_z_is_a_multiple_of_4_only(ctx, orc, shape):
+    """Z % 8 == 4: the fast stencil path without the TMA box (the reference's dataset dims rule yields such grids, e.g. 140 x 200 x 140):
+    erosion (all three masks), boundary tags in and out, the 3^3 sweep."""
+    g0 = random_blob_grid(shape, 8, fill=0.6, smooth=1)
+    lab = orc.naive(g0.copy(), pick_seeds(g0, min(6, int((g0 != 0).sum())), 1), 0)
+    noise = orc.Rng(5).fill_noise(4099)
+    for etype, mode in [(1, 0), (0, 0), (2, 1)]:
+        want = orc.erode(lab.copy(), noise, etype, 3, 3, 0.6, 0.6, boundary_mode=mode)
+        g = _grid(ctx, lab)
+        g.erode(etype, 3, 3, 0.6, 0.6, noise=noise, boundaryMode=mode)
+        assert np.array_equal(g.updateGrid(), want), (shape, etype, mode)
+        g.close()
+    speck = lab.copy()
+    speck[::3, ::2, ::3] = 9
+    g = _grid(ctx, speck)
+    g.removeIsolatedRegions()
+    assert np.array_equal(g.updateGrid(), orc.remove_isolated_regions_grid(speck.copy()))
+    g.close()
 
 
 def test_remove_isolated_regions_grid(ctx, orc, labelled_vessel):

@@ -385,9 +385,25 @@ __device__ __forceinline__ void stencil_pair(const uint16_t* s, const Dims& d, i
     *reinterpret_cast<unsigned*>(dst + gi) = eroded(ownA, countA, gz, ia) | eroded(ownB, countB, gz + 1, ib) << 16;
 }
 
-template <int OP>
-__global__ void __launch_bounds__(256) stencil_fast_kernel(const __grid_constant__ CUtensorMap src_map, uint16_t* __restrict__ dst, Dims d, ErodeArgs ea,
-                                                           int uniform_erodes)
+// 8 cells of a z-row of `dst`: one 128-bit store where rows are 16-byte aligned (Z % 8 == 0), otherwise two 64-bit halves, the second
+// of which lies outside the grid in the last chunk of a row when Z % 8 == 4
+template <bool ALIGNED16>
+__device__ __forceinline__ void store_chunk(uint16_t* __restrict__ p, const uint4& v, int gz, int Z)
+{
+    if (ALIGNED16) {
+        *reinterpret_cast<uint4*>(p) = v;
+    } else {
+        *reinterpret_cast<uint2*>(p) = make_uint2(v.x, v.y);
+        if (gz + 4 < Z) *reinterpret_cast<uint2*>(p + 4) = make_uint2(v.z, v.w);
+    }
+}
+
+// TMA: the tile is staged by one tensor-map box load, which needs 16-byte row pitches (Z % 8 == 0).  !TMA: grids whose Z is a multiple
+// of 4 only (the reference's dataset dims rule rounds x and z to multiples of 4, CADScene.cpp:272-273) stage the same box with 64-bit
+// loads; everything after the staging is shared.
+template <int OP, bool TMA>
+__global__ void __launch_bounds__(256) stencil_fast_kernel(const __grid_constant__ CUtensorMap src_map, const uint16_t* src, uint16_t* dst, Dims d, ErodeArgs ea,
+                                                           int uniform_erodes)  // src == dst for the in-place detect pass: no __restrict__
 {
     __shared__ __align__(128) uint16_t s[FROWS * FRS];
     __shared__ __align__(8) unsigned long long tma_bar;
@@ -403,7 +419,18 @@ __global__ void __launch_bounds__(256) stencil_fast_kernel(const __grid_constant
     //      so staging costs the CTA one instruction instead of a thousand address computations.
     const int ch = t & 7;
     const int gzc = gz0 + ch * 8;
-    {
+    if (!TMA) {
+        // 100 rows x 20 half-chunks of 4 cells; Z % 4 == 0 puts every half wholly inside or wholly outside the grid
+        for (int h = t; h < FROWS * (FRS / 4); h += 256) {
+            const int row = h / (FRS / 4), hh = h - row * (FRS / 4);
+            const int gx = gx0 + row / HY - 1, gy = gy0 + row % HY - 1, gz = gz0 - 8 + 4 * hh;
+            uint2 v = make_uint2(0u, 0u);  // kOutside
+            if ((unsigned)gx < (unsigned)d.X && (unsigned)gy < (unsigned)d.Y && gz >= 0 && gz < d.Z)
+                v = __ldcg(reinterpret_cast<const uint2*>(src + ((size_t)((unsigned)gx * (unsigned)d.Y + gy)) * d.Z + gz));  // coherent: detect runs in place
+            *reinterpret_cast<uint2*>(&s[row * FRS + 4 * hh]) = v;
+        }
+        __syncthreads();
+    } else {
         const unsigned bar = (unsigned)__cvta_generic_to_shared(&tma_bar);
         if (t == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
@@ -444,7 +471,7 @@ __global__ void __launch_bounds__(256) stencil_fast_kernel(const __grid_constant
             for (int k = 0; k < 2; ++k) {
                 const int y = (t >> 3) & 7, x = (t >> 6) + 4 * k;
                 const int gx = gx0 + x, gy = gy0 + y;
-                if (gx < d.X && gy < d.Y && gzc < d.Z) *reinterpret_cast<uint4*>(dst + ((size_t)((unsigned)gx * (unsigned)d.Y + gy)) * d.Z + gzc) = fill;
+                if (gx < d.X && gy < d.Y && gzc < d.Z) store_chunk<TMA>(dst + ((size_t)((unsigned)gx * (unsigned)d.Y + gy)) * d.Z + gzc, fill, gzc, d.Z);
             }
         }
         return;
@@ -465,7 +492,7 @@ __global__ void __launch_bounds__(256) stencil_fast_kernel(const __grid_constant
             for (int dy = 0; dy <= 2; ++dy) diff |= sp[(dx * HY + dy) * 8] ^ su;
         if (diff == 0 && !(OP == OP_ERODE3 && uniform_erodes)) {
             if (OP != OP_DETECT)
-                *reinterpret_cast<uint4*>(dst + ((size_t)((unsigned)gx * (unsigned)d.Y + gy)) * d.Z + gzc) = *reinterpret_cast<const uint4*>(&s[f_at(x, y, ch * 8)]);
+                store_chunk<TMA>(dst + ((size_t)((unsigned)gx * (unsigned)d.Y + gy)) * d.Z + gzc, *reinterpret_cast<const uint4*>(&s[f_at(x, y, ch * 8)]), gzc, d.Z);
         } else {
             tasks[atomicAdd(&ntasks, 1)] = (uint16_t)((x << 6) | (y << 3) | ch);
         }
@@ -478,6 +505,7 @@ __global__ void __launch_bounds__(256) stencil_fast_kernel(const __grid_constant
         const int c = tasks[q >> 2], k = q & 3;
         const int zc = c & 7, y = (c >> 3) & 7, x = c >> 6, z = zc * 8 + k * 2;
         const int gx = gx0 + x, gy = gy0 + y, gz = gz0 + z;
+        if (!TMA && gz >= d.Z) continue;  // second half of a row's last chunk when Z % 8 == 4
         const size_t gi = ((size_t)gx * d.Y + gy) * d.Z + gz;
         stencil_pair<OP>(s, d, x, y, z, gx, gy, gz, gi, ea, dst);
     }
@@ -510,7 +538,8 @@ vf_status launch_stencil(vf_grid* g, int op, const uint16_t* src, uint16_t* dst,
     Dims d = { (int)g->X, (int)g->Y, (int)g->Z };
     const int ntx = (d.X + SX - 1) / SX, nty = (d.Y + SYT - 1) / SYT, ntz = (d.Z + SZT - 1) / SZT;
     const int blocks = ntx * nty * ntz;
-    if (d.Z % 8 == 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0 && nty <= 65535 && ntx <= 65535) {
+    const bool tma_ok = d.Z % 8 == 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
+    if ((tma_ok || (d.Z % 4 == 0 && (((uintptr_t)src | (uintptr_t)dst) & 7) == 0)) && nty <= 65535 && ntx <= 65535) {
         // would a voxel with a completely uniform neighbourhood erode?  (count = mask population, visited = 27; true only for
         // unusual thresholds, e.g. CROSS with threshold > 0.78).  Evaluated with the kernel's float32 expression.
         int uniform_erodes = 0;
@@ -519,13 +548,21 @@ vf_status launch_stencil(vf_grid* g, int op, const uint16_t* src, uint16_t* dst,
             uniform_erodes = activation < ea.activations * ea.thr;
         }
         // tensor map over the source grid as (Z, Y, X) uint16 with a box of (FRS, HY, HX) cells
-        CUtensorMap map;
-        VF_TRY(make_grid_map(&map, src, d));
+        CUtensorMap map = {};
+        if (tma_ok) VF_TRY(make_grid_map(&map, src, d));
         const dim3 grid3(ntz, nty, ntx);
-        switch (op) {
-        case OP_DETECT: stencil_fast_kernel<OP_DETECT><<<grid3, 256, 0, c->stream>>>(map, dst, d, ea, 0); break;
-        case OP_ERODE3: stencil_fast_kernel<OP_ERODE3><<<grid3, 256, 0, c->stream>>>(map, dst, d, ea, uniform_erodes); break;
-        default: stencil_fast_kernel<OP_SWEEP><<<grid3, 256, 0, c->stream>>>(map, dst, d, ea, 0); break;
+        if (tma_ok) {
+            switch (op) {
+            case OP_DETECT: stencil_fast_kernel<OP_DETECT, true><<<grid3, 256, 0, c->stream>>>(map, src, dst, d, ea, 0); break;
+            case OP_ERODE3: stencil_fast_kernel<OP_ERODE3, true><<<grid3, 256, 0, c->stream>>>(map, src, dst, d, ea, uniform_erodes); break;
+            default: stencil_fast_kernel<OP_SWEEP, true><<<grid3, 256, 0, c->stream>>>(map, src, dst, d, ea, 0); break;
+            }
+        } else {
+            switch (op) {
+            case OP_DETECT: stencil_fast_kernel<OP_DETECT, false><<<grid3, 256, 0, c->stream>>>(map, src, dst, d, ea, 0); break;
+            case OP_ERODE3: stencil_fast_kernel<OP_ERODE3, false><<<grid3, 256, 0, c->stream>>>(map, src, dst, d, ea, uniform_erodes); break;
+            default: stencil_fast_kernel<OP_SWEEP, false><<<grid3, 256, 0, c->stream>>>(map, src, dst, d, ea, 0); break;
+            }
         }
         VF_LAUNCHED(c);
         return VF_OK;
