@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(256) ccl_tile_kernel(const uint16_t* __restric
     //     on packed 16-bit lanes (VIMNMX.U16x2) and gathered into byte masks; two shuffles assemble the row's 32-bit masks.
     //     Cells outside the grid read as EMPTY.
     const bool vec_ok = (g.Z % 8 == 0) && ((reinterpret_cast<uintptr_t>(grid) & 15) == 0);
+    const bool half_ok = (g.Z % 4 == 0) && ((reinterpret_cast<uintptr_t>(grid) & 7) == 0);
     constexpr int kIts = LROWS * 4 / 256;  // 8-cell chunks per thread
     uint4 chunk[kIts];
 #pragma unroll
@@ -160,6 +161,10 @@ __global__ void __launch_bounds__(256) ccl_tile_kernel(const uint16_t* __restric
             const uint16_t* src = grid + ((size_t)gx * g.Y + gy) * g.Z + gz;
             if (vec_ok) {
                 chunk[it] = __ldg(reinterpret_cast<const uint4*>(src));
+            } else if (half_ok) {  // Z % 8 == 4: rows are 8-byte aligned and the second half of a row's last chunk lies outside the grid
+                const uint2 lo = __ldg(reinterpret_cast<const uint2*>(src));
+                const uint2 hi = gz + 4 < g.Z ? __ldg(reinterpret_cast<const uint2*>(src + 4)) : make_uint2(0u, 0u);
+                chunk[it] = make_uint4(lo.x, lo.y, hi.x, hi.y);
             } else {
                 uint32_t w[4] = { 0, 0, 0, 0 };
                 for (int k = 0; k < 8 && gz + k < g.Z; ++k) w[k >> 1] |= (uint32_t)src[k] << ((k & 1) * 16);

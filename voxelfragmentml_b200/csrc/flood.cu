@@ -70,31 +70,37 @@ __global__ void __launch_bounds__(256) flood_init_keys_kernel(const uint16_t* __
     }
 }
 
-// The same, 8 voxels per thread (Z % 8 == 0): one 128-bit label load, two 128-bit key stores, no per-voxel index arithmetic.
-// A warp walks the chunks of one z-row, so (x, y) are decomposed once per row; a chunk never straddles a tile (8 | TZ).
-template <bool PHASE2>
+// The same, CH = 8 or 4 voxels per thread (Z % CH == 0): one 128- or 64-bit label load, 128-bit key stores, no per-voxel index
+// arithmetic.  A warp walks the chunks of one z-row, so (x, y) are decomposed once per row; a chunk never straddles a tile (CH | TZ).
+template <bool PHASE2, int CH>
 __global__ void __launch_bounds__(256) flood_init_keys_vec_kernel(const uint16_t* __restrict__ grid, uint32_t* __restrict__ keys, TileGeom g,
                                                                   uint8_t* __restrict__ occ, const uint16_t* __restrict__ order_of_frag)
 {
-    const int lane = threadIdx.x & 31, cpr = g.Z / 8;  // chunks per row
+    const int lane = threadIdx.x & 31, cpr = g.Z / CH;  // chunks per row
     const size_t rows = (size_t)g.X * g.Y, nwarps = (size_t)gridDim.x * (blockDim.x / 32);
     for (size_t row = (size_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32; row < rows; row += nwarps) {
         const int y = (int)(row % g.Y), x = (int)(row / g.Y);
         const uint32_t tile_row = ((uint32_t)(x / TX) * g.nty + y / TY) * g.ntz;
         for (int ch = lane; ch < cpr; ch += 32) {
-            const size_t i = row * g.Z + (size_t)ch * 8;
-            const uint4 v = vf_ldg_stream(reinterpret_cast<const uint4*>(grid + i));
-            const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+            const size_t i = row * g.Z + (size_t)ch * CH;
+            uint32_t w[4] = { 0, 0, 0, 0 };
+            if (CH == 8) {
+                const uint4 v = vf_ldg_stream(reinterpret_cast<const uint4*>(grid + i));
+                w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
+            } else {
+                const uint2 v = vf_ldg_stream(reinterpret_cast<const uint2*>(grid + i));
+                w[0] = v.x, w[1] = v.y;
+            }
             uint32_t k[8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < CH; ++c) {
                 const uint32_t lab = (w[c >> 1] >> ((c & 1) * 16)) & 0xFFFFu;
                 k[c] = lab == VF_VOXEL_EMPTY ? KEY_WALL : (!PHASE2 || lab == VF_VOXEL_FREE) ? KEY_UNREACHED : (uint32_t)order_of_frag[lab & 0xFFu];
             }
             vf_stg_stream(reinterpret_cast<uint4*>(keys + i), make_uint4(k[0], k[1], k[2], k[3]));
-            vf_stg_stream(reinterpret_cast<uint4*>(keys + i + 4), make_uint4(k[4], k[5], k[6], k[7]));
-            if ((v.x | v.y | v.z | v.w) != 0) {
-                const uint32_t tile = tile_row + (uint32_t)(ch * 8) / TZ;
+            if (CH == 8) vf_stg_stream(reinterpret_cast<uint4*>(keys + i + 4), make_uint4(k[4], k[5], k[6], k[7]));
+            if ((w[0] | w[1] | w[2] | w[3]) != 0) {
+                const uint32_t tile = tile_row + (uint32_t)(ch * CH) / TZ;
                 if (!occ[tile]) occ[tile] = 1;
             }
         }
@@ -105,7 +111,9 @@ template <bool PHASE2>
 vf_status launch_init_keys(vf_ctx* c, const uint16_t* grid, uint32_t* keys, const TileGeom& g, uint8_t* occ, const uint16_t* order, int blocks)
 {
     if (g.Z % 8 == 0 && (((uintptr_t)grid | (uintptr_t)keys) & 15) == 0)
-        flood_init_keys_vec_kernel<PHASE2><<<blocks, 256, 0, c->stream>>>(grid, keys, g, occ, order);
+        flood_init_keys_vec_kernel<PHASE2, 8><<<blocks, 256, 0, c->stream>>>(grid, keys, g, occ, order);
+    else if (g.Z % 4 == 0 && ((uintptr_t)grid & 7) == 0 && ((uintptr_t)keys & 15) == 0)  // the reference's dataset dims: x and z multiples of 4
+        flood_init_keys_vec_kernel<PHASE2, 4><<<blocks, 256, 0, c->stream>>>(grid, keys, g, occ, order);
     else
         flood_init_keys_kernel<PHASE2><<<blocks, 256, 0, c->stream>>>(grid, keys, g, occ, order);
     VF_LAUNCHED(c);
