@@ -192,13 +192,13 @@ __global__ void __launch_bounds__(256) ccl_tile_kernel(const uint16_t* __restric
         const uint32_t S = ~(~Nq & A & (A << 1));  // a run continues where the cell and its predecessor are active and alike
         uint32_t* lw = &labw[r * LABW + ch * 4];
         lw[0] = v.x, lw[1] = v.y, lw[2] = v.z, lw[3] = v.w;
-        // every node starts as its own root; written by storage slot (see slot()): slot p of row r holds node r*32 + ((p - r) & 31)
-        const uint32_t p0 = ch * 8, rb = r * LZ;
-        uint32_t idv[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) idv[k] = rb + ((p0 + k - r) & 31u);
-        *reinterpret_cast<uint4*>(&par[rb + p0]) = make_uint4(idv[0], idv[1], idv[2], idv[3]);
-        *reinterpret_cast<uint4*>(&par[rb + p0 + 4]) = make_uint4(idv[4], idv[5], idv[6], idv[7]);
+        // every node starts as its own root.  Only the starts of active runs are nodes (unite_local / find_local are entered through
+        // run_start() of an active cell), so only those entries are initialised: one store per row inside a fragment instead of 32
+        const uint32_t rb = r * LZ;
+        for (uint32_t st = ((S & A) >> (8 * ch)) & 0xFFu; st; st &= st - 1) {
+            const uint32_t id = rb + 8 * ch + (__ffs(st) - 1);
+            par[slot(id)] = id;
+        }
         const uint32_t lastw = __shfl_down_sync(kFull, v.w, 3);  // for ch == 0: the row's last word (cells 30, 31)
         if (ch == 0) {
             const int gx = gx0 + r / LY, gy = gy0 + r % LY;
