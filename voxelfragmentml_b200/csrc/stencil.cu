@@ -402,7 +402,7 @@ __device__ __forceinline__ void store_chunk(uint16_t* __restrict__ p, const uint
 // of 4 only (the reference's dataset dims rule rounds x and z to multiples of 4, CADScene.cpp:272-273) stage the same box with 64-bit
 // loads; everything after the staging is shared.
 template <int OP, bool TMA>
-__global__ void __launch_bounds__(256) stencil_fast_kernel(const __grid_constant__ CUtensorMap src_map, const uint16_t* src, uint16_t* dst, Dims d, ErodeArgs ea,
+__global__ void __launch_bounds__(256, 8) stencil_fast_kernel(const __grid_constant__ CUtensorMap src_map, const uint16_t* src, uint16_t* dst, Dims d, ErodeArgs ea,
                                                            int uniform_erodes)  // src == dst for the in-place detect pass: no __restrict__
 {
     __shared__ __align__(128) uint16_t s[FROWS * FRS];
