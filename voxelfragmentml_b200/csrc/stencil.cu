@@ -697,7 +697,8 @@ static vf_status histogram_impl(vf_grid* g, uint32_t* counts, uint64_t* occupied
     uint32_t* d_counts = (uint32_t*)((char*)c->small.ptr + (512 << 10));
     unsigned long long* d_occ = (unsigned long long*)(d_counts + VF_HISTOGRAM_BINS);
     VF_TRY(vf_k_zero(c, d_counts, VF_HISTOGRAM_BINS * 4 + 8));
-    const int blocks = (int)std::min((size_t)c->num_sms * 8, (g->n() / 8 + 255) / 256 + 1);
+    // 38-40 registers: six CTAs are resident per SM, so the grid is one full wave (measured equal to eight per SM within noise)
+    const int blocks = (int)std::min((size_t)c->num_sms * 6, (g->n() / 8 + 255) / 256 + 1);
     if (unmask) histogram_kernel<true><<<blocks, 256, 0, c->stream>>>(g->d, g->n(), d_counts, d_occ);
     else histogram_kernel<false><<<blocks, 256, 0, c->stream>>>(g->d, g->n(), d_counts, d_occ);
     VF_LAUNCHED(c);
