@@ -317,10 +317,13 @@ def run_cuda(args):
 
     pipe_steps = max(6, 2 * args.steps)
     run_pipelined(3)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    run_pipelined(pipe_steps)
-    e2e_s = (time.perf_counter() - t0) / pipe_steps
+    e2e_runs = []  # three passes of pipe_steps steps each; the median pass is reported (host-side DMA scheduling varies from pass to pass)
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run_pipelined(pipe_steps)
+        e2e_runs.append((time.perf_counter() - t0) / pipe_steps)
+    e2e_s = sorted(e2e_runs)[1]
     if world > 1:
         tt = torch.tensor([e2e_s, serial_s], device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -343,7 +346,7 @@ def run_cuda(args):
                 "d2h_bytes_per_step": 2 * N + 4 * 32768, "ms_per_step": e2e_s * 1e3, "steps": pipe_steps,
                 "mode": "3 grids in rotation: upload / kernels / download of consecutive steps overlap; every step copies its own input grid and "
                         "result grid; the seed list and noise table are identical every step and are sent once (the library skips unchanged tables)",
-                "serial_ms_per_step": serial_s * 1e3, "serial_value": world * N / serial_s / 1e9},
+                "passes_ms_per_step": [t * 1e3 for t in e2e_runs], "serial_ms_per_step": serial_s * 1e3, "serial_value": world * N / serial_s / 1e9},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if not args.no_batch:
