@@ -215,6 +215,30 @@ public:
         return data()[((size_t)x * d.y + y) * d.z + z]._value;
     }
     static unsigned getPositionIndex(int x, int y, int z, const uvec3& numDivs) { return x * numDivs.y * numDivs.z + y * numDivs.z + z; }
+    // Host-side cell accessors of the reference (RegularGrid.cpp:523-531, 543-569, 1031-1039): they act on the host copy, as `_grid`
+    // does there; call updateSSBO() to publish set() calls to the device and updateGrid() to refresh the copy after device work.
+    void set(int x, int y, int z, uint16_t i)
+    {
+        const uvec3 d = getNumSubdivisions();
+        data()[((size_t)x * d.y + y) * d.z + z]._value = i;
+    }
+    bool isOccupied(int x, int y, int z) { return at(x, y, z) != VF_VOXEL_EMPTY; }
+    bool isEmpty(int x, int y, int z) { return at(x, y, z) == VF_VOXEL_EMPTY; }
+    bool isBoundary(int x, int y, int z, int neighbourhoodSize = 1)  // "some cell of the clamped box is EMPTY" (RegularGrid.cpp:543-559)
+    {
+        if (neighbourhoodSize % 2 == 0) ++neighbourhoodSize;
+        const uvec3 d = getNumSubdivisions();
+        auto clampi = [](int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); };
+        const int x0 = clampi(x - neighbourhoodSize, (int)d.x - 1), x1 = clampi(x + neighbourhoodSize, (int)d.x - 1);
+        const int y0 = clampi(y - neighbourhoodSize, (int)d.y - 1), y1 = clampi(y + neighbourhoodSize, (int)d.y - 1);
+        const int z0 = clampi(z - neighbourhoodSize, (int)d.z - 1), z1 = clampi(z + neighbourhoodSize, (int)d.z - 1);
+        const CellGrid* g = data();
+        for (int a = x0; a <= x1; ++a)
+            for (int b = y0; b <= y1; ++b)
+                for (int c = z0; c <= z1; ++c)
+                    if (g[((size_t)a * d.y + b) * d.z + c]._value == VF_VOXEL_EMPTY) return true;
+        return false;
+    }
     // countValues + numOccupiedVoxels
     size_t countValues(std::vector<uint32_t>& countsByLabel)
     {

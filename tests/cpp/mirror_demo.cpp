@@ -66,6 +66,13 @@ int main(int argc, char** argv)
             fracturer::Seeder::mergeSeeds(seeds, extraSeeds, mergeDFunc);
             seeds.insert(seeds.end(), extraSeeds.begin(), extraSeeds.end());
         }
+        // the host-side cell accessors of the reference (Seeder::uniform's OUTER rule, RegularGrid.cpp:543-564), on the host copy
+        for (int i = 0; i < params._numSeeds; ++i)
+            if (!grid.isOccupied(seeds[i].x, seeds[i].y, seeds[i].z) || grid.isEmpty(seeds[i].x, seeds[i].y, seeds[i].z) ||
+                !grid.isBoundary(seeds[i].x, seeds[i].y, seeds[i].z)) {
+                std::fprintf(stderr, "seed %d is not an occupied OUTER cell\n", i);
+                return 4;
+            }
         fracturer::Fracturer* fracturer = naive ? static_cast<fracturer::Fracturer*>(fracturer::NaiveFracturer::getInstance())
                                                 : static_cast<fracturer::Fracturer*>(fracturer::FloodFracturer::getInstance());
         if (!fracturer->setDistanceFunction(dfunc)) return 3;
