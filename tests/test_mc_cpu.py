@@ -92,3 +92,62 @@ def test_fragment_touching_the_grid_faces_is_closed_by_the_padding(orc):
     v, f = orc.marching_cubes(g, 2, np.float32([0, 0, 0]), np.float32([6, 4, 5]), nb_iters=0, b_iters=0)
     assert all(n == 2 for n in _edge_use(f).values())
     assert len(v) - len(_edge_use(f)) + len(f) == 2  # Euler characteristic of a sphere
+
+
+# ---- the marching stage restated a second time, literally from the shader text (marchingCubes-comp.glsl:57-168 + MarchingCubes::setGrid,
+# MarchingCubes.cpp:516-533 + the transformation of RegularGrid::toTriangleMesh, RegularGrid.cpp:477-479), compared with the oracle as an
+# ORDER-FREE multiset of oriented triangles: the reference's vertex / face order is an atomicAdd race, geometry is not.
+NEIGHBORS = [(0, 0, 0), (0, 0, 1), (-1, 0, 1), (-1, 0, 0), (0, 1, 0), (0, 1, 1), (-1, 1, 1), (-1, 1, 0)]  # marchingCubes-comp.glsl:27-37
+
+
+def _march_literal(grid, target):
+    """triangles in PADDED-grid coordinates doubled (all coordinates are half-integers: the field is 0/1 and isolevel 0.5, so mu = 0.5)"""
+    X, Y, Z = (s + 2 for s in grid.shape)
+    pad = np.full((X, Y, Z), 1, np.uint16)  # setGrid: border = VOXEL_FREE
+    pad[1:-1, 1:-1, 1:-1] = grid
+    field = ((pad & 0x7FFF) == target).astype(np.float32)  # :117 unmaskedBit(value, 15) == targetValue
+    rows = _rows()
+    tris = []
+    for x in range(X):
+        for y in range(Y):
+            for z in range(Z):
+                if x == 0 or y == Y - 1 or z == Z - 1:  # :106-107
+                    continue
+                values = [field[x + n[0], y + n[1], z + n[2]] for n in NEIGHBORS]
+                configuration = sum(1 << i for i in range(8) if values[i] < 0.5)  # :119-120
+                if not rows[configuration]:
+                    continue
+                vlist = {}
+                for i, (a, b) in enumerate(EDGES):
+                    if (values[a] < 0.5) != (values[b] < 0.5):  # configurationTable[configuration] & (1 << i): the cut edges
+                        p1 = np.float32([x + NEIGHBORS[a][0], y + NEIGHBORS[a][1], z + NEIGHBORS[a][2]])
+                        p2 = np.float32([x + NEIGHBORS[b][0], y + NEIGHBORS[b][1], z + NEIGHBORS[b][2]])
+                        mu = (np.float32(0.5) - values[a]) / (values[b] - values[a])  # findVertex :63-79 (neither EPSILON branch can fire)
+                        vlist[i] = p1 + mu * (p2 - p1)
+                row = rows[configuration]
+                for i in range(0, len(row), 3):  # :140-151: vertices 0, 2, 1 of the table row
+                    tri = [vlist[row[i]], vlist[row[i + 2]], vlist[row[i + 1]]]
+                    tris.append(tuple(tuple(int(round(2 * float(c))) for c in p) for p in tri))
+    return tris
+
+
+def _canon(tri):  # oriented triangle up to rotation of its vertices
+    k = tri.index(min(tri))
+    return tri[k:] + tri[:k]
+
+
+def test_marching_stage_matches_the_shader_text(orc):
+    occ = random_blob_grid((13, 11, 14), 5)
+    seeds = np.uint32([[3, 3, 3, 2], [9, 8, 10, 3], [6, 9, 4, 4]])
+    lab = orc.detect_boundaries(orc.naive((occ != 0).astype(np.uint16), seeds, 0), 1)  # tagged words: the shader unmasks bit 15
+    lab[0, :, :] = np.where(lab[0, :, :] > 1, lab[0, :, :], 2)                      # a fragment that touches a grid face
+    mn, mx = np.float32([-0.45, -0.25, -0.5]), np.float32([0.35, 0.3, 0.45])
+    scale = (mx - mn) / np.float32(lab.shape)
+    t = mn - scale  # translate(-scale) * translate(minPoint) * scale(scale)
+    for target in (2, 3, 4):
+        v, f = orc.marching_cubes(lab, target, mn, mx, nb_iters=0, b_iters=0)
+        q = np.rint(2.0 * (v[:, :3].astype(np.float64) - t) / scale).astype(np.int64)  # back to doubled padded-grid coordinates
+        assert np.abs(2.0 * (v[:, :3].astype(np.float64) - t) / scale - q).max() < 1e-3
+        got = Counter(_canon(tuple(tuple(int(c) for c in q[i]) for i in tri[:3])) for tri in f)
+        want = Counter(_canon(tri) for tri in _march_literal(lab, target))
+        assert sum(want.values()) > 50 and got == want, target
