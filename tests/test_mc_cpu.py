@@ -151,3 +151,49 @@ def test_marching_stage_matches_the_shader_text(orc):
         got = Counter(_canon(tuple(tuple(int(c) for c in q[i]) for i in tri[:3])) for tri in f)
         want = Counter(_canon(tri) for tri in _march_literal(lab, target))
         assert sum(want.values()) > 50 and got == want, target
+
+
+# ---- the smoothing passes transcribed from resetLaplacianBuffer / laplacianSmoothing / finishLaplacianSmoothing-comp.glsl and the host loop
+# MarchingCubes::smoothSurface (MarchingCubes.cpp:498-521; called non-boundary first, then boundary, :399-400).  Integer atomics: the result does
+# not depend on invocation order, so the oracle must reproduce it bit for bit given the same fused mesh.
+def _smooth_literal(v, f, iters, weight, boundary):
+    f32 = np.float32
+    v = v.copy()
+    EPS, UINT_MULT = f32(0.00000001), f32(10000.0)
+    target = f32(1.0 if boundary else 0.0)
+    check_validity = 0 if boundary else 1
+    for _ in range(iters):
+        lap = np.zeros((len(v), 4), np.int64)
+        for face in f:
+            valid = True
+            if check_validity == 1:
+                for i in range(3):
+                    valid = valid and abs(v[face[i], 3] - target) < EPS
+            if not valid:
+                continue
+            for i in range(3):
+                vertex = [int(c) for c in (v[face[i], :3] * UINT_MULT)] + [1]  # ivec3(xyz * UINT_MULT): truncation towards zero
+                for other in (face[(i + 1) % 3], face[(i + 2) % 3]):
+                    lap[other] += vertex
+        lap = ((lap + 2 ** 31) % 2 ** 32 - 2 ** 31).astype(np.int32)  # the buffers are 32-bit ints
+        for idx in range(len(v)):
+            if abs(v[idx, 3] - target) < EPS and lap[idx, 3] > 0:
+                mean = [f32(lap[idx, k]) / f32(lap[idx, 3]) / UINT_MULT for k in range(3)]
+                for k in range(3):  # mix(a, b, w) = a * (1 - w) + b * w
+                    v[idx, k] = f32(v[idx, k] * f32(f32(1.0) - f32(weight))) + f32(mean[k] * f32(weight))
+    return v
+
+
+def test_smoothing_matches_the_shader_text(orc):
+    occ = random_blob_grid((12, 10, 13), 7)
+    seeds = np.uint32([[3, 3, 3, 2], [8, 7, 9, 3]])
+    lab = orc.detect_boundaries(orc.naive((occ != 0).astype(np.uint16), seeds, 0), 1)
+    mn, mx = np.float32([-0.45, -0.25, -0.5]), np.float32([0.35, 0.3, 0.45])
+    for target in (2, 3):
+        v0, f = orc.marching_cubes(lab, target, mn, mx, nb_iters=0, b_iters=0)
+        assert 0 < v0[:, 3].sum() < len(v0)  # both vertex kinds occur
+        for nb, wnb, b, wb in ((2, 0.9, 0, 0.2), (0, 0.9, 3, 0.2), (2, 0.9, 2, 0.2)):
+            vs, fs = orc.marching_cubes(lab, target, mn, mx, nb_iters=nb, nb_weight=wnb, b_iters=b, b_weight=wb)
+            want = _smooth_literal(_smooth_literal(v0, f[:, :3], nb, wnb, False), f[:, :3], b, wb, True)
+            assert np.array_equal(fs, f)
+            assert np.array_equal(vs.view(np.uint32), want.view(np.uint32)), (target, nb, b)
