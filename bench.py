@@ -355,7 +355,8 @@ def run_cuda(args):
         bm = 32 * world
         bdt, _, npool = batch_measure(rank, local_rank, world, dist if world > 1 else None, bm, 2, jobs, 4)
         out["batch"] = {"metric": "models/s batch voxelize+fragment", "value": bm / bdt, "unit": "models/s", "meshes": bm, "jobs_per_gpu": jobs,
-                        "fragmentations_per_s": bm * 10 / bdt, "scaling": "weak",
+                        "fragmentations_per_s": bm * 10 / bdt, "scaling": "weak", "host_cores": host_cores(),
+                        "host_cpu_s_per_model_rank0": LAST_BATCH_INFO.get("host_cpu_s_per_model"),
                         "workload": f"cfg4-batch: {bm} synthetic vessels (pool of {npool} shapes) x 10 fragmentations at 256-max, FLOOD CHEBYSHEV, nf 2..10, "
                                     "2*nf extra seeds; full-size run: bench.py --workload batch --meshes 1024"}
     if rank == 0 and not args.no_cpu_baseline:
@@ -577,6 +578,9 @@ def default_jobs(world):
     return 16 if host_cores() // max(1, world) >= 16 or host_cores() // max(1, world) < 8 else 8
 
 
+LAST_BATCH_INFO = {}  # side information of the last batch_measure call (rank-local)
+
+
 def batch_measure(rank, local_rank, world, dist, meshes, warmup, jobs, mesh_pool, blocking="auto"):
     """BASELINE config 4: dataset generation — per mesh: SAT voxelization at 256-max, then 10 fragmentations with the reference's
     dataset defaults (FLOOD + CHEBYSHEV, numSeeds = nf cycling 2..10, numExtraSeeds = 2 nf, detectBoundaries, histogram, undoMask;
@@ -641,9 +645,11 @@ def batch_measure(rank, local_rank, world, dist, meshes, warmup, jobs, mesh_pool
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
+    t0, c0 = time.perf_counter(), time.process_time()
     run(my)
     dt = time.perf_counter() - t0
+    # host CPU time of this rank (all threads) per model of the timed pass: what a batch producer pays in host cores
+    LAST_BATCH_INFO["host_cpu_s_per_model"] = (time.process_time() - c0) / max(1, len(my))
     if dist is not None:
         tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -666,6 +672,7 @@ def run_batch(args):
             "config": {"workload": f"cfg4-batch: {args.meshes} synthetic vessels (pool of {npool} shapes) x 10 fragmentations at 256-max, FLOOD CHEBYSHEV, "
                                    "nf 2..10, 2*nf extra seeds, per-mesh RNG seed 80+m, mesh m -> rank m mod N", "jobs_per_gpu": jobs,
                        "host_cores": host_cores(), "blocking_sync": args.blocking_sync,
+                       "host_cpu_s_per_model_rank0": LAST_BATCH_INFO.get("host_cpu_s_per_model"),
                        "fragmentations_per_s": args.meshes * 10 / dt, "checksum_rank0": checksum},
         }))
     if dist is not None:
