@@ -699,6 +699,8 @@ def run_dataset(args):
     proc = vf.FragmentationProcedure(_fragmentInterval=(2, 11), _iterationInterval=(1, 1), _maxFragmentsModel=1 << 40)
     proc._fractureParameters._clampVoxelMetricUnit = 256
     proc._fractureParameters._voxelPerMetricUnit = 256
+    if args.no_export:  # the cfg4 batch loop driven natively (one C call per model): what `--workload batch` does from Python threads
+        proc._exportGrid = False
     workers = []
     for j in range(jobs):
         ctx = vf.Context(local_rank)
@@ -728,9 +730,10 @@ def run_dataset(args):
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
+    t0, c0 = time.perf_counter(), time.process_time()
     run(my, True)
     dt = time.perf_counter() - t0
+    host_cpu = (time.process_time() - c0) / max(1, len(my))
     shutil.rmtree(out, ignore_errors=True)
     if dist is not None:
         tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
@@ -744,7 +747,8 @@ def run_dataset(args):
             "dtype": "u16 labels", "data": "synthetic",
             "config": {"workload": f"cfg4-dataset: {args.meshes} synthetic vessels (pool of {len(pool)} shapes) x 10 fragmentations at clamp 256 through the native "
                                    "driver, FLOOD CHEBYSHEV, n = 2..11 seeds + 2n extra, .rle export of every grid (device run detection, async writers)",
-                       "jobs_per_gpu": jobs, "rank0": tot, "fragmentations_per_s": args.meshes * 10 / dt},
+                       "jobs_per_gpu": jobs, "rank0": tot, "fragmentations_per_s": args.meshes * 10 / dt, "grid_export": not args.no_export,
+                       "host_cores": host_cores(), "host_cpu_s_per_model_rank0": host_cpu},
         }))
     if dist is not None:
         dist.destroy_process_group()
@@ -765,6 +769,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=["cfg3", "slab", "batch", "dataset"],
                     help="cfg3 = the driver's default; slab = cfg5; batch = cfg4; dataset = cfg4 through the native driver with .rle export")
     ap.add_argument("--out", default="", help="dataset workload: parent directory of the (temporary) output folder")
+    ap.add_argument("--no-export", action="store_true", help="dataset workload: no grid files (the batch loop through the native driver, metadata files only)")
     ap.add_argument("--seeds", type=int, default=256, help="slab workload: number of seeds")
     ap.add_argument("--meshes", type=int, default=64, help="batch workload: number of meshes")
     ap.add_argument("--jobs", type=int, default=0, help="batch workload: concurrent contexts (streams + host threads) per GPU; 0 = 16, or 8 with 8..15 host cores per rank")
