@@ -213,3 +213,28 @@ def test_result_does_not_depend_on_the_distance_window_or_blocking_waits(orc, ve
     got, _ = _run_flood(c, vessel_grid, wseeds, 2)
     assert np.array_equal(got, want)
     c.close()
+
+
+@pytest.mark.skipif(__import__("os").environ.get("VF_TEST_EXPERIMENTAL") != "1", reason="experimental path: set VF_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("levels", [8, 16])
+def test_graph_driven_round_loop_is_bit_exact(orc, vessel_grid, monkeypatch, levels):
+    """VF_FLOOD_GRAPH=1: the round loop runs as a CUDA graph while-node on the device (csrc/flood.cu run_rounds_graph).  Same fixed point."""
+    import voxelfragmentml_b200 as vf
+
+    monkeypatch.setenv("VF_FLOOD_GRAPH", "1")
+    c = vf.Context(0)
+    c.setFloodLevels(levels)
+    seeds, _ = orc.seed_uniform(orc.Rng(80), vessel_grid, 12)
+    for dfunc in (1, 2):
+        want, _ = orc.flood(vessel_grid.copy(), seeds, dfunc)
+        got, st = _run_flood(c, vessel_grid, seeds, dfunc)
+        assert np.array_equal(got, want) and st.tile_rounds > 0
+    wseeds = orc.make_seeds(orc.Rng(80), vessel_grid, 6, 12, merge_dfunc=0)
+    want, _ = orc.flood(vessel_grid.copy(), wseeds, orc.CHEBYSHEV)
+    got, _ = _run_flood(c, vessel_grid, wseeds, 2)
+    assert np.array_equal(got, want)
+    empty = np.zeros((20, 20, 40), np.uint16)  # nothing to flood: the loop body runs once on an empty list
+    empty[3, 3, 3] = 1
+    got, _ = _run_flood(c, empty, np.uint32([[3, 3, 3, 2]]), 1)
+    assert got[3, 3, 3] == 2 and got.sum() == 2
+    c.close()

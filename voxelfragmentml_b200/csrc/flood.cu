@@ -43,6 +43,7 @@ constexpr uint32_t kNoLevel = 0xFFFFFFFFu;
 
 enum { ST_VISITS = 0, ST_ROUNDS = 1, ST_ERROR = 2, ST_FREED = 3, ST_MAXDIST = 4, ST_CHANGED = 5, ST_STEPS = 6, ST_MAXSTEPS = 7 };
 
+constexpr int kRoundWord = 14;  // worklist header layout: stats[8] count[3] lo[3] | word 14: device-resident round id (graph mode) | word 15 free
 constexpr size_t kSmemBytes = (size_t)(kCells + 5 * kThreads + 8 + 2) * sizeof(uint32_t);  // tile | 5 row-mask arrays | misc | mbarrier
 
 // ------------------------------------------------------------------------------------------------ key field set-up
@@ -257,10 +258,13 @@ __device__ __forceinline__ uint32_t min_neighbour_key(const uint32_t* sk, int x,
     return m;
 }
 
-template <int NNEIGH>
+// DEVROUND: the round id is read from device memory (word kRoundWord of the worklist header) instead of the launch parameter, so that
+// the same launch can be replayed by a CUDA graph loop (run_rounds_graph below; opt-in).
+template <int NNEIGH, bool DEVROUND>
 __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __restrict__ keys, const __grid_constant__ CUtensorMap keys_map, int use_tma,
-                                                                  TileGeom g, Worklist wl, uint32_t round)
+                                                                  TileGeom g, Worklist wl, uint32_t round_arg)
 {
+    const uint32_t round = DEVROUND ? __ldcg(wl.stats + kRoundWord) : round_arg;
     extern __shared__ __align__(128) uint32_t sm[];
     uint32_t* sk = sm;
     uint32_t* act = sm + kCells;        // [2][kThreads] wavefront bitmasks, one word per z-row
@@ -502,6 +506,7 @@ struct Job {
     uint32_t* h_mail;     // pinned mailbox
     int blocks_stream;    // grid for streaming kernels
     int blocks_tiles;     // grid for tile kernels
+    bool graph;           // rounds driven by a CUDA graph while-loop on the device (VF_FLOOD_GRAPH=1; experimental, off by default)
 };
 
 vf_status job_begin(vf_grid* grid, Job& j)
@@ -533,6 +538,8 @@ vf_status job_begin(vf_grid* grid, Job& j)
     j.h_mail = (uint32_t*)((char*)c->pinned + 65536);  // upper half of the mailbox; the lower half carries seeds
     j.blocks_stream = c->num_sms * 8;
     j.blocks_tiles = c->num_sms * 4;
+    const char* ge = std::getenv("VF_FLOOD_GRAPH");
+    j.graph = ge != nullptr && ge[0] == '1';
     return VF_OK;
 }
 
@@ -585,13 +592,86 @@ bool make_keys_map(CUtensorMap* map, const uint32_t* keys, const TileGeom& g)
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// ---- experimental (VF_FLOOD_GRAPH=1): the round loop as a CUDA graph `while` node.  The body is one round kernel that reads its round id
+// from the worklist header, followed by a one-thread kernel that advances the id and keeps the loop alive while the next round's list is
+// not empty.  A flood phase is then one graph launch and one 4-byte read-back instead of ~60 kernel launches and ~4 host synchronisations:
+// less host work per flood (batch producers with few cores per GPU) and no empty rounds.
+__global__ void flood_set_round_kernel(Worklist wl, uint32_t round) { wl.stats[kRoundWord] = round; }
+
+__global__ void flood_advance_kernel(Worklist wl, cudaGraphConditionalHandle loop, uint32_t last_round)
+{
+    const uint32_t next = wl.stats[kRoundWord] + 1;
+    wl.stats[kRoundWord] = next;
+    cudaGraphSetConditional(loop, (wl.count[next % 3] != 0 && next < last_round) ? 1u : 0u);
+}
+
+template <int NNEIGH>
+vf_status run_rounds_graph(Job& j, uint32_t* keys, CUtensorMap& map, int use_tma)
+{
+    vf_ctx* c = j.c;
+    auto kern = flood_round_kernel<NNEIGH, true>;
+    VF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    flood_set_round_kernel<<<1, 1, 0, c->stream>>>(j.wl, j.round);
+    VF_LAUNCHED(c);
+    struct Holder {  // released on every exit path
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        ~Holder()
+        {
+            if (exec) cudaGraphExecDestroy(exec);
+            if (graph) cudaGraphDestroy(graph);
+        }
+    } h;
+    VF_CUDA(cudaGraphCreate(&h.graph, 0));
+    cudaGraphConditionalHandle loop;
+    VF_CUDA(cudaGraphConditionalHandleCreate(&loop, h.graph, 1, cudaGraphCondAssignDefault));  // the first iteration always runs
+    cudaGraphNodeParams cp = {};
+    cp.type = cudaGraphNodeTypeConditional;
+    cp.conditional.handle = loop;
+    cp.conditional.type = cudaGraphCondTypeWhile;
+    cp.conditional.size = 1;
+    cudaGraphNode_t loop_node;
+    VF_CUDA(cudaGraphAddNode(&loop_node, h.graph, nullptr, 0, &cp));
+    cudaGraph_t body = cp.conditional.phGraph_out[0];
+
+    uint32_t unused_round = 0;
+    void* round_args[] = { &keys, &map, &use_tma, &j.g, &j.wl, &unused_round };
+    cudaKernelNodeParams rp = {};
+    rp.func = (void*)kern;
+    rp.gridDim = dim3((unsigned)j.blocks_tiles), rp.blockDim = dim3(kThreads);
+    rp.sharedMemBytes = (unsigned)kSmemBytes;
+    rp.kernelParams = round_args;
+    cudaGraphNode_t round_node;
+    VF_CUDA(cudaGraphAddKernelNode(&round_node, body, nullptr, 0, &rp));
+
+    uint32_t last_round = j.round + 100000;  // the guard of run_rounds
+    void* adv_args[] = { &j.wl, &loop, &last_round };
+    cudaKernelNodeParams ap = {};
+    ap.func = (void*)flood_advance_kernel;
+    ap.gridDim = dim3(1), ap.blockDim = dim3(1);
+    ap.kernelParams = adv_args;
+    cudaGraphNode_t adv_node;
+    VF_CUDA(cudaGraphAddKernelNode(&adv_node, body, &round_node, 1, &ap));
+
+    VF_CUDA(cudaGraphInstantiate(&h.exec, h.graph, 0));
+    VF_CUDA(cudaGraphLaunch(h.exec, c->stream));
+    VF_CUDA(cudaMemcpyAsync(j.h_mail, j.wl.stats + kRoundWord, 4, cudaMemcpyDeviceToHost, c->stream));
+    VF_CUDA(vf_sync(c));
+    const uint32_t reached = j.h_mail[0];
+    c->launches += 2ull * (reached - j.round);  // the kernels the loop ran
+    j.round = reached;
+    if (reached >= last_round) return vf_set_error(VF_ERR_CAPACITY, "tile worklist did not drain");
+    return VF_OK;
+}
+
 template <int NNEIGH>
 vf_status flood_phase(Job& j, uint32_t* keys)
 {
-    auto kern = flood_round_kernel<NNEIGH>;
+    auto kern = flood_round_kernel<NNEIGH, false>;
     VF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     CUtensorMap map;
     const int use_tma = make_keys_map(&map, keys, j.g) ? 1 : 0;  // otherwise: per-row cp.async staging
+    if (j.graph) return run_rounds_graph<NNEIGH>(j, keys, map, use_tma);
     return run_rounds(j, [&](uint32_t r) { kern<<<j.blocks_tiles, kThreads, kSmemBytes, j.c->stream>>>(keys, map, use_tma, j.g, j.wl, r); });
 }
 
