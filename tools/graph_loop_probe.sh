@@ -4,6 +4,8 @@
 set -u
 O=gpurun_out
 mkdir -p $O
+# the graph loop is compiled only on request (its device-side cudaGraphSetConditional is resolved by the driver at module load)
+VF_NVCC_EXTRA=-DVF_FLOOD_GRAPH_BUILD python build_lib.py --force > $O/graph_build.log 2>&1 || { tail -5 $O/graph_build.log; exit 1; }
 VF_TEST_EXPERIMENTAL=1 timeout 120 python -m pytest tests/test_flood_gpu.py -m gpu -q -k graph_driven > $O/graph_parity.log 2>&1
 tail -3 $O/graph_parity.log
 grep -q passed $O/graph_parity.log || exit 1

@@ -592,7 +592,10 @@ bool make_keys_map(CUtensorMap* map, const uint32_t* keys, const TileGeom& g)
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// ---- experimental (VF_FLOOD_GRAPH=1): the round loop as a CUDA graph `while` node.  The body is one round kernel that reads its round id
+#ifdef VF_FLOOD_GRAPH_BUILD
+// ---- experimental, compiled only with -DVF_FLOOD_GRAPH_BUILD (VF_NVCC_EXTRA of build_lib.py) because the loop's device-side
+// cudaGraphSetConditional is an extern the driver resolves when the module is loaded: kept out of the default cubin until it has run on the
+// target driver.  Selected at run time with VF_FLOOD_GRAPH=1: the round loop as a CUDA graph `while` node.  The body is one round kernel that reads its round id
 // from the worklist header, followed by a one-thread kernel that advances the id and keeps the loop alive while the next round's list is
 // not empty.  A flood phase is then one graph launch and one 4-byte read-back instead of ~60 kernel launches and ~4 host synchronisations:
 // less host work per flood (batch producers with few cores per GPU) and no empty rounds.
@@ -663,6 +666,7 @@ vf_status run_rounds_graph(Job& j, uint32_t* keys, CUtensorMap& map, int use_tma
     if (reached >= last_round) return vf_set_error(VF_ERR_CAPACITY, "tile worklist did not drain");
     return VF_OK;
 }
+#endif  // VF_FLOOD_GRAPH_BUILD
 
 template <int NNEIGH>
 vf_status flood_phase(Job& j, uint32_t* keys)
@@ -671,7 +675,11 @@ vf_status flood_phase(Job& j, uint32_t* keys)
     VF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     CUtensorMap map;
     const int use_tma = make_keys_map(&map, keys, j.g) ? 1 : 0;  // otherwise: per-row cp.async staging
+#ifdef VF_FLOOD_GRAPH_BUILD
     if (j.graph) return run_rounds_graph<NNEIGH>(j, keys, map, use_tma);
+#else
+    VF_REQUIRE(!j.graph, VF_ERR_UNSUPPORTED, "VF_FLOOD_GRAPH=1 needs a library built with -DVF_FLOOD_GRAPH_BUILD (VF_NVCC_EXTRA)");
+#endif
     return run_rounds(j, [&](uint32_t r) { kern<<<j.blocks_tiles, kThreads, kSmemBytes, j.c->stream>>>(keys, map, use_tma, j.g, j.wl, r); });
 }
 
