@@ -201,3 +201,29 @@ def test_position_decode_of_the_shader_is_exact_on_these_sizes(orc):
     dims = (7, 6, 9)
     for index in range(7 * 6 * 9):
         assert get_position(index, dims) == np.unravel_index(index, dims)
+
+
+@pytest.mark.parametrize("case", range(12))
+def test_boundary_detection_after_the_first_iteration_is_a_no_op(orc, case):
+    """RegularGrid::erode calls detectBoundaries(1) in every iteration (RegularGrid.cpp:133-135).  Tags are never cleared and erosion never
+    creates a label, so from the second iteration on the pass cannot change the grid — which is why vf_erode launches it once
+    (csrc/stencil.cu).  Checked on the literal transcription: the repeated pass is the identity, and the pipeline without it equals the
+    oracle's pipeline with it, also when the grid arrives with tags already set."""
+    rs = np.random.RandomState(100 + case)
+    shape = tuple(int(v) for v in rs.randint(3, 9, 3))
+    g = _labelled(shape, case, nlabels=int(rs.randint(2, 6)), fill=float(rs.uniform(0.5, 0.98)))
+    if case % 3 == 0:
+        g[rs.rand(*shape) < 0.2] |= 0x8000
+    etype, size = int(rs.randint(0, 3)), int(rs.choice([3, 3, 5]))
+    iters, prob, thr = int(rs.randint(2, 5)), float(rs.uniform(0.3, 1.0)), float(rs.uniform(0.3, 1.0))
+    noise = orc.Rng(case).fill_noise(int(rs.randint(50, 400)))
+    k, mask, act = build_mask_literal(etype, size)
+    b = g.copy()
+    for it in range(iters):
+        tagged = detect_boundaries_literal(b, 1, range(b.size))
+        if it == 0:
+            b = tagged
+        else:
+            assert np.array_equal(tagged, b)
+        b = erode_pass_literal(b, mask, k, noise, act, prob, thr)
+    assert np.array_equal(sweep_literal(b), orc.erode(g.copy(), noise, etype, size, iters, prob, thr, boundary_mode=0))

@@ -672,7 +672,12 @@ extern "C" vf_status vf_erode(vf_grid* g, int type, uint32_t size, uint32_t iter
     vf_grid view = *g;  // shallow view used to run passes on either buffer
     for (uint32_t it = 0; it < iterations; ++it) {
         view.d = a;
-        VF_TRY(launch_stencil(&view, OP_DETECT, a, a, ea));  // RegularGrid.cpp:135
+        // RegularGrid.cpp:135 calls detectBoundaries(1) in every iteration; only the first call can change the grid.  The pass tags an
+        // untagged labelled cell iff its clamped 3^3 box holds another label (> FREE, tag ignored) and never clears a tag; erosion copies
+        // words, tags included, or writes EMPTY.  After the first pass every cell whose box holds another label is tagged, and a later
+        // pass could only tag a cell whose box GAINED another label — no pass creates labels.  (Checked against the literal shader
+        // transcription with and without the repeated passes: tests/test_oracle_literal_shaders.py.)
+        if (it == 0) VF_TRY(launch_stencil(&view, OP_DETECT, a, a, ea));
         if (size == 3) {
             VF_TRY(launch_stencil(&view, OP_ERODE3, a, b, ea));
         } else {
