@@ -238,3 +238,28 @@ def test_graph_driven_round_loop_is_bit_exact(orc, vessel_grid, monkeypatch, lev
     got, _ = _run_flood(c, empty, np.uint32([[3, 3, 3, 2]]), 1)
     assert got[3, 3, 3] == 2 and got.sum() == 2
     c.close()
+
+
+@pytest.mark.skipif(__import__("os").environ.get("VF_TEST_EXPERIMENTAL") != "1", reason="experimental path: set VF_TEST_EXPERIMENTAL=1")
+def test_c1_descent_formulation_is_bit_exact(ctx, orc, vessel_grid, monkeypatch):
+    """VF_C1_DESCENT=1 (csrc/c1_descent.cu): certificate pass + list work instead of the union-find; same cases as the C1 tests above plus a
+    dense Voronoi grid (few failing cells), labels without a seed and a grid whose Z is not a multiple of 8 (declines, union-find runs)."""
+    monkeypatch.setenv("VF_C1_DESCENT", "1")
+    for dfunc in (0, 1, 2):
+        seeds, _ = orc.seed_uniform(orc.Rng(80), vessel_grid, 12)
+        lab = orc.naive(vessel_grid.copy(), seeds, dfunc)
+        assert np.array_equal(_run_c1(ctx, lab, seeds), orc.remove_isolated_regions_cpu(lab.copy(), seeds))
+        dense = np.ones((96, 80, 128), np.uint16)
+        ds = pick_seeds(dense, 40, dfunc)
+        dl = orc.naive(dense.copy(), ds, dfunc)
+        assert np.array_equal(_run_c1(ctx, dl, ds), orc.remove_isolated_regions_cpu(dl.copy(), ds))
+        assert np.array_equal(_run_c1(ctx, dl, ds[:30]), orc.remove_isolated_regions_cpu(dl.copy(), ds[:30]))  # ten labels lose their seed
+    for trial in range(5):
+        g = random_blob_grid((35, 33, 72 if trial % 2 else 70), 300 + trial, fill=0.45, smooth=1)
+        seeds = pick_seeds(g, 8, trial)
+        lab = orc.naive(g.copy(), seeds, 1)
+        lab[1:3, 1:3, 1:3] = 1
+        s2 = seeds.copy()
+        s2[0, :3] = np.argwhere(lab == s2[1, 3])[0]
+        for sd in (seeds, s2):
+            assert np.array_equal(_run_c1(ctx, lab, sd), orc.remove_isolated_regions_cpu(lab.copy(), sd))

@@ -1,7 +1,9 @@
 #!/bin/bash
 # Builds the library with one compile-time experimental variant, runs the GPU parity suite and the default bench line, then restores the
 # default build.  usage (through gpurun): tools/variant_probe.sh VF_CCL_JUMP   [more -D names ...]
-# Variants staged in the sources: VF_CCL_JUMP (ccl.cu: pointer jumping instead of per-lane chain walks in the in-tile flatten phase),
+# Run-time variants need no rebuild: `VF_C1_DESCENT=1 python bench.py ...` (c1_descent.cu: certificate pass + list work instead of the union-find
+# for C1; parity: `VF_TEST_EXPERIMENTAL=1 python -m pytest tests/test_flood_gpu.py -m gpu -k descent`).
+# Compile-time variants staged in the sources: VF_CCL_JUMP (ccl.cu: pointer jumping instead of per-lane chain walks in the in-tile flatten phase),
 # VF_FLOOD_GRAPH_BUILD (flood.cu: CUDA-graph round loop, additionally needs VF_FLOOD_GRAPH=1 at run time; see tools/graph_loop_probe.sh).
 set -u
 O=gpurun_out

@@ -790,6 +790,13 @@ extern "C" vf_status vf_remove_isolated_regions(vf_grid* grid, const uint32_t* s
     VF_TRY(vf_enter(c));
     ushort4* d_seeds = nullptr;
     VF_TRY(vf_upload_seeds(c, seeds, nseeds, grid->X, grid->Y, grid->Z, &d_seeds));
+    if (const char* e = std::getenv("VF_C1_DESCENT")) {  // experimental formulation (c1_descent.cu); falls through when it declines
+        if (e[0] == '1') {
+            int handled = 0;
+            VF_TRY(vf_k_c1_descent(grid, d_seeds, (int)nseeds, &handled));
+            if (handled) return VF_OK;
+        }
+    }
     return vf_k_keep_seed_components(grid, d_seeds, (int)nseeds, 0, 6, nullptr);
 }
 

@@ -142,6 +142,7 @@ vf_status vf_k_zero(vf_ctx* ctx, void* d, size_t bytes);  // zero-fill by kernel
 // ---------------------------------------------------------------------------------------------- kernels (one per file)
 vf_status vf_k_naive(vf_grid* g, const ushort4* d_seeds, uint32_t nseeds, int dfunc);
 vf_status vf_k_keep_seed_components(vf_grid* grid, const ushort4* d_starts, int nstarts, int mode, int nneigh, uint32_t* d_freed);  // ccl.cu
+vf_status vf_k_c1_descent(vf_grid* grid, const ushort4* d_seeds, int nseeds, int* handled);  // c1_descent.cu (experimental, VF_C1_DESCENT=1)
 vf_status vf_k_pointwise(vf_grid* g, int op);  // 0 undoMask(bit15) 1 undoMask(rightmost 8) 2 resetFilling 3 homogenize
 enum { VF_PW_UNMASK15 = 0, VF_PW_RIGHTMOST8 = 1, VF_PW_RESET_FILLING = 2, VF_PW_HOMOGENIZE = 3 };
 
