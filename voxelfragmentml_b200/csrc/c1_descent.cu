@@ -1,6 +1,6 @@
 // c1_descent.cu — EXPERIMENTAL alternative for C1 (connected-to-seed cleanup), selected at run time with VF_C1_DESCENT=1; the default is
 // the union-find of ccl.cu.  Not yet run on a GPU: the algorithm is validated on the CPU (tools/c1_descent_prototype.py: identical to the
-// oracle on dense Voronoi labels under all three metrics, the reference's vessel grid and porous blobs), the kernels are not.
+// CPU checker on dense Voronoi labels under all three metrics, the reference's vessel grid and porous blobs), the kernels are not.
 //
 // Semantics (NaiveFracturer::removeIsolatedRegionsCPU, SRC/Fracturer/NaiveFracturer.cpp:111-150): every seed cell is overwritten with its
 // seed's label (a later seed on the same cell wins), then only cells 6-connected to their own seed through same-label cells survive;
