@@ -4,6 +4,7 @@
 # Run-time variants need no rebuild: `VF_C1_DESCENT=1 python bench.py ...` (c1_descent.cu: certificate pass + list work instead of the union-find
 # for C1; parity: `VF_TEST_EXPERIMENTAL=1 python -m pytest tests/test_flood_gpu.py -m gpu -k descent`).
 # Compile-time variants staged in the sources: VF_CCL_JUMP (ccl.cu: pointer jumping instead of per-lane chain walks in the in-tile flatten phase),
+# VF_HIST_WARP (stencil.cu: uniform vectors of the histogram counted per warp with one shared atomic per distinct label),
 # VF_FLOOD_GRAPH_BUILD (flood.cu: CUDA-graph round loop, additionally needs VF_FLOOD_GRAPH=1 at run time; see tools/graph_loop_probe.sh).
 set -u
 O=gpurun_out

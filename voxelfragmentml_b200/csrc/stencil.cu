@@ -226,9 +226,27 @@ __global__ void __launch_bounds__(256) histogram_kernel(uint16_t* __restrict__ g
 #pragma unroll
         for (int k = 0; k < kHistBatch; ++k) {
             const uint32_t first = v[k].x & 0xFFFFu;
+#ifdef VF_HIST_WARP
+            // experimental (-DVF_HIST_WARP): lanes whose vector holds one label are counted by the warp, one shared atomic per distinct label
+            // (a leader is elected per label with a ballot; one or two rounds inside a fragment), instead of every lane keeping a run and
+            // the warp diverging on each lane's flush.  Vectors that straddle a label change fall through to the run path below.
+            const bool uni = v[k].x == first * 0x10001u && v[k].y == v[k].x && v[k].z == v[k].x && v[k].w == v[k].x;
+            const bool counted = uni && first > VF_VOXEL_FREE;
+            const uint32_t key = first & 0x7FFFu;
+            for (unsigned rest = __ballot_sync(kFull, counted); rest;) {
+                const uint32_t lead = __shfl_sync(kFull, key, __ffs(rest) - 1);
+                const unsigned same = __ballot_sync(kFull, counted && key == lead);
+                if (lane == __ffs(rest) - 1) add(lead, 8u * (uint32_t)__popc(same));
+                rest &= ~same;
+            }
+            if (counted) occ += 8;
+            if (uni) continue;
+            {
+#else
             if (v[k].x == first * 0x10001u && v[k].y == v[k].x && v[k].z == v[k].x && v[k].w == v[k].x) {
                 take(first, 8);
             } else {
+#endif
                 // runs of equal cells inside the vector (a fragment border: usually two): "differs from its predecessor" on packed
                 // lanes, gathered into a byte whose set bits are the run starts
                 const uint32_t one = 0x00010001u;
