@@ -18,11 +18,10 @@ def c1_descent(grid, seeds):
     X, Y, Z = g.shape
     for x, y, z, w in seeds:  # NaiveFracturer.cpp:120-123: the seed cell carries the seed's label, a later seed wins
         g[x, y, z] = w
-    pos = {}
+    pos = {}  # every seed is the start of its own label, also one whose cell a later seed took (the reference's front holds all seeds)
     for x, y, z, w in seeds:
-        if g[x, y, z] == w:
-            assert int(w) not in pos, "two surviving seeds with one label: the CUDA path falls back to the union-find"
-            pos[int(w)] = (int(x), int(y), int(z))
+        assert int(w) not in pos, "two seeds with one label: the CUDA path falls back to the union-find"
+        pos[int(w)] = (int(x), int(y), int(z))
     table = np.full((65536, 3), -(10 ** 6), np.int64)  # labels without a seed: no descent neighbour can exist
     has_seed = np.zeros(65536, bool)
     for w, p in pos.items():
@@ -38,6 +37,8 @@ def c1_descent(grid, seeds):
         nidx = list(idx)
         nidx[a] = np.clip(idx[a] - step[..., a], 0, g.shape[a] - 1)
         cert |= (step[..., a] != 0) & (g[nidx[0], nidx[1], nidx[2]] == g)
+    cert |= np.abs(C - P).sum(axis=-1) == 1  # next to the start: entered from it whatever label the start's cell carries
+    cert &= has_seed[g]                      # a label without a seed has no start at all
     is_seed = (step == 0).all(axis=-1) & has_seed[g]
     F = active & ~cert & ~is_seed
     D = set(map(tuple, np.argwhere(F)))

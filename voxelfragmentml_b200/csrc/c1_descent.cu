@@ -3,8 +3,8 @@
 // CPU checker on dense Voronoi labels under all three metrics, the reference's vessel grid and porous blobs), the kernels are not.
 //
 // Semantics (NaiveFracturer::removeIsolatedRegionsCPU, SRC/Fracturer/NaiveFracturer.cpp:111-150): every seed cell is overwritten with its
-// seed's label (a later seed on the same cell wins), then only cells 6-connected to their own seed through same-label cells survive;
-// everything else, FREE cells included, becomes EMPTY.
+// seed's label (a later seed on the same cell wins), then only cells 6-connected to their own seed's cell through same-label cells survive
+// (the seed's cell is the start even when a later seed took it); everything else, FREE cells included, becomes EMPTY.
 //
 // Idea: a labelled cell that has a same-label 6-neighbour ONE MANHATTAN STEP CLOSER to its own seed ("descent neighbour") is connected to the
 // seed if that neighbour is, and the distance strictly decreases, so a cell with a descent neighbour outside the set D below is connected.
@@ -36,22 +36,26 @@ struct Ctl {  // device control block
 __device__ __forceinline__ bool bit(const uint32_t* b, uint32_t i) { return (b[i >> 5] >> (i & 31u)) & 1u; }
 __device__ __forceinline__ uint32_t cell(const Dims& d, int x, int y, int z) { return ((uint32_t)x * d.Y + y) * d.Z + z; }
 
-// seed s plants its label unless a later seed sits on the same cell (NaiveFracturer.cpp:120-123), and registers as the seed of that label
+// seed s registers as the start of its label, and plants the label unless a later seed sits on the same cell (NaiveFracturer.cpp:120-123)
 __global__ void plant_kernel(uint16_t* __restrict__ grid, Dims d, const ushort4* __restrict__ seeds, int S, uint32_t* __restrict__ table, Ctl* ctl)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     const ushort4 sd = seeds[s];
+    // every seed is a start for its own label, also one whose cell a later seed takes (the search of NaiveFracturer.cpp:116-146 is seeded
+    // with all seeds and enters the neighbours that hold the label the front element carries)
+    const uint32_t old = atomicCAS(&table[sd.w], kNone, (uint32_t)s);
+    if (old != kNone) ctl->dup = 1;  // two seeds with one label: "own seed" is ambiguous, the union-find decides
     for (int t = s + 1; t < S; ++t)
         if (seeds[t].x == sd.x && seeds[t].y == sd.y && seeds[t].z == sd.z) return;
     grid[cell(d, sd.x, sd.y, sd.z)] = sd.w;
-    const uint32_t old = atomicCAS(&table[sd.w], kNone, (uint32_t)s);
-    if (old != kNone) ctl->dup = 1;  // two surviving seeds with one label: "own seed" is ambiguous, the union-find decides
 }
 
 // same-label 6-neighbour one Manhattan step closer to p?  The neighbour lies between the cell and p: always inside the grid.
+// A cell next to p is entered from the start itself, whatever label p's cell carries (a later seed may have taken it).
 __device__ __forceinline__ bool descends(const uint16_t* g, const Dims& d, int x, int y, int z, uint32_t L, const ushort4& p)
 {
+    if (abs(x - (int)p.x) + abs(y - (int)p.y) + abs(z - (int)p.z) == 1) return true;
     if (z != p.z && g[cell(d, x, y, z + (z > p.z ? -1 : 1))] == L) return true;
     if (y != p.y && g[cell(d, x, y + (y > p.y ? -1 : 1), z)] == L) return true;
     if (x != p.x && g[cell(d, x + (x > p.x ? -1 : 1), y, z)] == L) return true;

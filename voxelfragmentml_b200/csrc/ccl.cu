@@ -421,24 +421,42 @@ __global__ void __launch_bounds__(256) ccl_border_kernel(const uint16_t* __restr
     }
 }
 
-// mark the root of each start cell's component
-__global__ void ccl_mark_kernel(uint32_t* __restrict__ P, const uint2* __restrict__ masks, Geo g, const ushort4* __restrict__ starts, int S)
+// mark the root of each start cell's component.
+// C1 (c1 != 0): every seed is searched from with its OWN label (NaiveFracturer.cpp:116-146: the front is seeded with all seeds, a neighbour is
+// entered when the grid holds the label the front element carries).  A seed whose cell was taken by a later seed — CADScene's copies of the
+// original seeds sit on the originals' cells (CADScene.cpp:651) — therefore still keeps the components of ITS label that touch the cell.
+__global__ void ccl_mark_kernel(const uint16_t* __restrict__ grid, uint32_t* __restrict__ P, const uint2* __restrict__ masks, Geo g,
+                                const ushort4* __restrict__ starts, int S, int c1)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     const ushort4 sd = starts[s];
-    const uint32_t row = (uint32_t)sd.x * g.Y + sd.y;
-    const int seg = sd.z / 32, z = sd.z % 32;
-    const uint2 mm = masks[(size_t)row * g.segs + seg];
-    if (!(mm.x >> z & 1u)) return;  // the start cell is not part of any region
-    uint32_t r = P[row * (uint32_t)g.Z + seg * 32 + run_start(mm.y, z)];
-    r &= ~KEEP;  // the run start may itself be a root that another start already marked
-    while (true) {
-        const uint32_t q = __ldcg(&P[r]) & ~KEEP;
-        if (q == r) break;
-        r = q;
+    auto mark = [&](int x, int y, int zz) {
+        const uint32_t row = (uint32_t)x * g.Y + y;
+        const int seg = zz / 32, z = zz % 32;
+        const uint2 mm = masks[(size_t)row * g.segs + seg];
+        if (!(mm.x >> z & 1u)) return;  // the cell is not part of any region
+        uint32_t r = P[row * (uint32_t)g.Z + seg * 32 + run_start(mm.y, z)];
+        r &= ~KEEP;  // the run start may itself be a root that another start already marked
+        while (true) {
+            const uint32_t q = __ldcg(&P[r]) & ~KEEP;
+            if (q == r) break;
+            r = q;
+        }
+        atomicOr(&P[r], KEEP);
+    };
+    if (c1 && grid[((size_t)sd.x * g.Y + sd.y) * g.Z + sd.z] != sd.w) {
+        // the cell carries a later seed's label: this seed's search enters the 6-neighbours that hold its own label
+        const int x = sd.x, y = sd.y, z = sd.z;
+        if (x + 1 < g.X && grid[((size_t)(x + 1) * g.Y + y) * g.Z + z] == sd.w) mark(x + 1, y, z);
+        if (x > 0 && grid[((size_t)(x - 1) * g.Y + y) * g.Z + z] == sd.w) mark(x - 1, y, z);
+        if (y + 1 < g.Y && grid[((size_t)x * g.Y + y + 1) * g.Z + z] == sd.w) mark(x, y + 1, z);
+        if (y > 0 && grid[((size_t)x * g.Y + y - 1) * g.Z + z] == sd.w) mark(x, y - 1, z);
+        if (z + 1 < g.Z && grid[((size_t)x * g.Y + y) * g.Z + z + 1] == sd.w) mark(x, y, z + 1);
+        if (z > 0 && grid[((size_t)x * g.Y + y) * g.Z + z - 1] == sd.w) mark(x, y, z - 1);
+        return;
     }
-    atomicOr(&P[r], KEEP);
+    mark(sd.x, sd.y, sd.z);
 }
 
 // C1: everything that is not in a kept component becomes EMPTY (the reference rebuilds from an all-EMPTY grid);
@@ -552,7 +570,7 @@ vf_status vf_k_keep_seed_components(vf_grid* grid, const ushort4* d_starts, int 
     } else {
         VF_TRY((run_ccl<MODE_F3, 26>(grid, g, P, masks, ends, blocks_lin)));
     }
-    ccl_mark_kernel<<<(nstarts + 127) / 128, 128, 0, c->stream>>>(P, masks, g, d_starts, nstarts);
+    ccl_mark_kernel<<<(nstarts + 127) / 128, 128, 0, c->stream>>>(grid->d, P, masks, g, d_starts, nstarts, mode == MODE_C1 ? 1 : 0);
     VF_LAUNCHED(c);
     if (mode == MODE_C1) ccl_select_kernel<MODE_C1><<<blocks_lin, 256, 0, c->stream>>>(grid->d, P, masks, g, d_freed);
     else ccl_select_kernel<MODE_F3><<<blocks_lin, 256, 0, c->stream>>>(grid->d, P, masks, g, d_freed);
