@@ -58,7 +58,7 @@ def test_detect_boundaries_ragged(ctx, orc, shape):
     g.close()
 
 
-@pytest.mark.parametrize("etype,size,iters,mode", [(1, 3, 3, 0), (2, 3, 3, 0), (0, 3, 2, 0), (1, 3, 1, 1), (1, 5, 2, 0), (0, 4, 1, 0), (1, 3, 0, 0)])
+@pytest.mark.parametrize("etype,size,iters,mode", [(1, 3, 3, 0), (2, 3, 3, 0), (0, 3, 2, 0), (1, 3, 1, 1), (1, 3, 3, 1), (1, 5, 2, 0), (0, 4, 1, 0), (1, 3, 0, 0)])
 def test_erode(ctx, orc, labelled_vessel, etype, size, iters, mode):
     lab, _ = labelled_vessel
     noise = orc.Rng(80).fill_noise(100003)
