@@ -13,6 +13,10 @@ for cores in 4 8 $ALL; do
   taskset -c 0-$((cores-1)) python bench.py --workload batch --meshes $N --warmup 2 > $O/host_batch_py_${cores}c.json 2> $O/host_batch_py_${cores}c.err
   taskset -c 0-$((cores-1)) python bench.py --workload dataset --no-export --meshes $N --warmup 2 > $O/host_batch_native_${cores}c.json 2> $O/host_batch_native_${cores}c.err
 done
+# CTAs per SM of a flood round launch (default 4): fewer idle CTAs when 16 jobs share the GPU?
+for k in 1 2; do
+  VF_FLOOD_CTAS_PER_SM=$k python bench.py --workload batch --meshes $N --warmup 2 > $O/host_batch_py_ctas${k}.json 2> $O/host_batch_py_ctas${k}.err
+done
 python - <<'PY'
 import glob, json
 for f in sorted(glob.glob("gpurun_out/host_batch_*.json")):

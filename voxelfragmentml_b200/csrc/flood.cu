@@ -538,6 +538,9 @@ vf_status job_begin(vf_grid* grid, Job& j)
     j.h_mail = (uint32_t*)((char*)c->pinned + 65536);  // upper half of the mailbox; the lower half carries seeds
     j.blocks_stream = c->num_sms * 8;
     j.blocks_tiles = c->num_sms * 4;
+    // tuning knob for tools/: CTAs per SM of a round launch.  A round of a 256-max shell lists ~170 tiles, so most of the 4 x 148 CTAs leave at
+    // once; with many jobs per GPU those CTAs still take a launch slot each (57 KB of shared memory) for a microsecond.
+    if (const char* e = std::getenv("VF_FLOOD_CTAS_PER_SM")) j.blocks_tiles = c->num_sms * std::min(4, std::max(1, std::atoi(e)));
     const char* ge = std::getenv("VF_FLOOD_GRAPH");
     j.graph = ge != nullptr && ge[0] == '1';
     return VF_OK;
