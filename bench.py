@@ -9,7 +9,9 @@ Workload (N=1 default) = BASELINE.json configs[2], the configuration the metric 
 thr .5), connected-to-seed small-fragment removal and the per-fragment histogram.  The grid is the DENSE variant (every cell
 occupied: worst case, algorithmic bytes 4N for the naive kernel); the sparse synthetic-vessel variant is reported alongside.
 A step = one pass of that pipeline over one grid; with N GPUs every rank runs its own grid (weak scaling, no collective on
-the data path).  Inputs (256 MiB) are larger than L2 (126 MB), so no explicit L2 flush is needed between iterations.
+the data path).  The input grid is rewritten before every timed call, so between the rewrite and the timed region a 256 MiB
+scratch buffer (larger than the 126 MB L2) is overwritten on the same stream: the timed kernels start on a grid that is not L2-resident.
+The last step's result is compared with the oracle's on the same seeds and noise (`parity_checked`).
 """
 from __future__ import annotations
 
@@ -171,10 +173,15 @@ def run_cuda(args):
     naive.setDistanceFunction(CFG3["dfunc"])
     stream = torch.cuda.ExternalStream(ctx.stream)
     stages_run = []
+    stage_launches = {}
+
+    flush_buf = torch.empty(max(N, 128 << 20), dtype=torch.int16, device="cuda")  # >= 256 MiB: twice the L2
 
     def restore():
+        """rewrite the input, then push it out of L2 (VERDICT r1 weak #8: the rewrite left up to 126 MB of the grid L2-resident)"""
         with torch.cuda.stream(stream):
             work.copy_(pristine)
+            flush_buf.fill_(1)
 
     def pipeline(record=None):
         """one step of cfg3 on the device-resident grid; returns the histogram when the stage exists"""
@@ -183,10 +190,12 @@ def run_cuda(args):
         def stage(name, fn):
             try:
                 if record is not None:
+                    l0 = ctx.kernel_launches
                     ctx.timer_start()
                 fn()
                 if record is not None:
                     t[name] = ctx.timer_stop()
+                    stage_launches[name] = ctx.kernel_launches - l0
                 if name not in stages_run:
                     stages_run.append(name)
             except vf.VoxFragError as e:
@@ -266,6 +275,65 @@ def run_cuda(args):
             traffic = json.load(open(tpath)).get(str(n))
         except Exception:
             traffic = None
+    # `roofline` = the dominant kernel of the timed step (largest share of the step's device time); the F1 kernel the north star's 60 % target
+    # names stays beside it as `roofline_f1`, the whole step as `roofline_step`.  Algorithmic bytes per launch = the stage's algorithmic bytes
+    #  / the launches the library issued for it; launch duration = the stage's CUDA-event time / the same count.
+    dom = max(stage_ms, key=stage_ms.get)
+    dom_launches = max(1, int(stage_launches.get(dom, 1)))
+    dom_bytes = stage_roofline[dom]["algorithmic_bytes"] / dom_launches
+    dom_ms = stage_ms[dom] / dom_launches
+    dom_kernels = {"naive": "naive_brick_kernel<EUCLIDEAN,8>", "remove_isolated": "ccl_* (tile + border + select)", "erode": "stencil_fast_kernel<OP,TMA>",
+                   "histogram_undo_mask": "histogram_kernel<UNMASK>"}
+    step_bytes = float(sum(v["algorithmic_bytes"] for v in stage_roofline.values()))
+
+    # ---- the sparse variant BASELINE.md lists as cfg3's primary input: the ~20k-triangle synthetic vessel voxelized at 512-max (352 x 512 x 352),
+    #      64 OUTER seeds from RNG seed 80, same pipeline.  Reported beside the dense headline (parity: tests/test_fullsize_gpu.py).
+    vessel = None
+    if not args.no_vessel and n == 512:
+        from voxelfragmentml_b200 import synth
+
+        vv, vfaces = synth.vessel_mesh(0)
+        vmn, vmx = synth.mesh_aabb(vv)
+        vdims = np.zeros(3, np.uint32)
+        vf._capi.load().vf_dims_rule(vmn.ctypes.data, vmx.ctypes.data, 512, vdims.ctypes.data)
+        vdims = tuple(int(d) for d in vdims)
+        vN = int(np.prod(vdims))
+        vwork = torch.empty(vN, dtype=torch.int16, device="cuda")
+        vgrid = vf.RegularGrid(ctx, vdims, device_ptr=vwork.data_ptr())
+        vgrid.setAABB(vmn, vmx, vdims)
+        vox_ms = []
+        for _ in range(4):
+            ctx.synchronize()
+            ctx.timer_start()
+            vgrid.fill(vv, vfaces)
+            vox_ms.append(ctx.timer_stop())
+        ctx.initSeed(CFG3["rng_seed"])
+        vseeds = vf.Seeder.uniform(vgrid, CFG3["nseeds"])
+        vpristine = vwork.clone()
+        vstage, vstep = [], []
+        et, es, ei, ep, eth = CFG3["erosion"]
+        for it in range(3 + max(5, min(args.steps, 10))):
+            with torch.cuda.stream(stream):
+                vwork.copy_(vpristine)
+                flush_buf.fill_(1)
+            ctx.synchronize()
+            t = {}
+            ctx.timer_start()
+            naive.build(vgrid, vseeds)
+            vf.NaiveFracturer.removeIsolatedRegions(vgrid, vseeds)
+            vgrid.erode(et, es, ei, ep, eth, noise=noise)
+            _, vocc = vgrid.countValuesUndoMask()
+            if it >= 3:
+                vstep.append(ctx.timer_stop())
+        vms = float(np.median(vstep))
+        occupied_in = int((vpristine != 0).sum().item())
+        vessel = {"workload": f"cfg3-vessel: synthetic vessel ({len(vfaces)} triangles) SAT-voxelized at {vdims[0]}x{vdims[1]}x{vdims[2]}, {CFG3['nseeds']} OUTER seeds, "
+                              "same pipeline as the headline", "grid": list(vdims), "occupied_voxels": occupied_in, "labelled_after_cleanup": int(vocc),
+                  "ms_per_step": vms, "value": vN / (vms * 1e-3) / 1e9, "unit": "Gvoxels/s (grid cells)", "occupied_gvoxels_per_s": occupied_in / (vms * 1e-3) / 1e9,
+                  "voxelize_ms": float(np.median(vox_ms)),
+                  "algorithmic_bytes": 2.0 * vN * 9 + 2.0 * occupied_in * 6, "roofline_frac": (2.0 * vN * 9 + 2.0 * occupied_in * 6) / (vms * 1e-3) / 1e9 / peak}
+        vgrid.close()
+        del vwork, vpristine
 
     # ---- end to end through the public API with HOST buffers: pinned upload -> pipeline -> download, every step.
     # (a) serial: one grid, each step waits for its own download (latency of one call sequence);
@@ -336,13 +404,19 @@ def run_cuda(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "u16 labels / int32 distance keys", "data": "synthetic",
         "config": {"workload": f"cfg3-dense: {n}^3 all-occupied grid, NAIVE EUCLIDEAN {CFG3['nseeds']} seeds + connected-to-seed cleanup"
                                " + erode(ELLIPSE,3,3it,p.5,thr.5) + histogram + undoMask", "stages": stages_run, "grid": list(dims),
-                   "l2": "inputs (256 MiB at 512^3) larger than L2 (126 MB); no explicit flush", "parallelism": f"replicas x{world} (one grid per GPU)"},
+                   "l2": "input rewritten, then a 256 MiB scratch buffer (2x the 126 MB L2) overwritten on the same stream before every timed call", "parallelism": f"replicas x{world} (one grid per GPU)"},
         "stage_ms": stage_ms,
         "stage_roofline": stage_roofline,
         "fragmentation_only": {"value": world * N / naive_t / 1e9, "unit": "Gvoxels/s", "note": "F1 operator alone (NaiveFracturer::build without cleanup), CUDA events"},
-        "roofline": {"kernel": "naive_brick_kernel<EUCLIDEAN,8>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": algo_bytes,
-                     "kernel_ms": naive_t * 1e3},
+        "roofline": {"kernel": dom_kernels.get(dom, dom), "stage": dom, "bound": "hbm", "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes": dom_bytes,
+                     "kernel_ms": dom_ms, "launches_per_step": dom_launches, "share_of_step": stage_ms[dom] / sum(stage_ms.values())},
+        "roofline_f1": {"kernel": "naive_brick_kernel<EUCLIDEAN,8>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": algo_bytes,
+                        "kernel_ms": naive_t * 1e3, "note": "the operator BASELINE.json's >= 60 % target names, timed alone"},
+        "roofline_step": {"bound": "hbm", "algorithmic_bytes": step_bytes, "achieved": step_bytes / (total_ms / args.steps * 1e-3) / 1e9, "peak": peak,
+                          "unit": "GB/s", "frac": step_bytes / (total_ms / args.steps * 1e-3) / 1e9 / peak,
+                          "note": "all stages of the timed step: sum of the per-stage algorithmic bytes / ms_per_step"},
         "e2e": {"value": world * N / e2e_s / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": 2 * N,
                 "d2h_bytes_per_step": 2 * N + 4 * 32768, "ms_per_step": e2e_s * 1e3, "steps": pipe_steps,
                 "mode": "3 grids in rotation: upload / kernels / download of consecutive steps overlap; every step copies its own input grid and "
@@ -350,6 +424,8 @@ def run_cuda(args):
                 "passes_ms_per_step": [t * 1e3 for t in e2e_runs], "serial_ms_per_step": serial_s * 1e3, "serial_value": world * N / serial_s / 1e9},
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    if vessel is not None:
+        out["vessel"] = vessel
     if not args.no_batch:
         # BASELINE.json's second metric (cfg4, models/s), measured briefly beside the headline: 32 meshes per GPU
         jobs = args.jobs or default_jobs(world)
@@ -361,7 +437,26 @@ def run_cuda(args):
                         "workload": f"cfg4-batch: {bm} synthetic vessels (pool of {npool} shapes) x 10 fragmentations at 256-max, FLOOD CHEBYSHEV, nf 2..10, "
                                     "2*nf extra seeds; full-size run: bench.py --workload batch --meshes 1024"}
     if rank == 0 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(args.cpu_size or 512, stages_run)
+        cn = args.cpu_size or n
+        out["cpu_baseline"], want = cpu_baseline(cn, stages_run)
+        # parity of exactly what was timed: one more step on the device from the same input, its final grid and histogram against the oracle's
+        # (same seeds, same noise table; oracle = checker only).  A mismatch is reported, never hidden: the line still prints, with the count.
+        if cn == n and stages_run == ["naive", "remove_isolated", "erode", "histogram_undo_mask"]:
+            restore()
+            naive.build(grid, seeds)
+            vf.NaiveFracturer.removeIsolatedRegions(grid, seeds)
+            et, es, ei, ep, eth = CFG3["erosion"]
+            grid.erode(et, es, ei, ep, eth, noise=noise)
+            counts, occ = grid.countValuesUndoMask()
+            got = grid.updateGrid()
+            bad = int((got.reshape(-1) != want["grid"].reshape(-1)).sum())
+            hist_ok = bool(np.array_equal(np.asarray(counts), want["counts"]) and int(occ) == int(want["occupied"]))
+            out["parity_checked"] = bad == 0 and hist_ok
+            out["parity"] = {"against": "oracle (OpenMP restatement; C++-sourced stages pinned by the reference's own code, tests/test_oracle_vs_ref.py)",
+                             "cells": int(N), "mismatching_cells": bad, "histogram_equal": hist_ok, "occupied": int(occ)}
+        else:
+            out["parity_checked"] = False
+            out["parity"] = {"skipped": f"cpu sample {cn}^3 differs from the timed {n}^3 grid or a stage is missing"}
     if rank == 0:
         emit_json(json.dumps(out))
     if world > 1:
@@ -370,6 +465,8 @@ def run_cuda(args):
 
 # ------------------------------------------------------------------------------------------------ CPU arms (oracle)
 def oracle_pipeline(orc, grid, seeds, noise, stages):
+    """cfg3 with the oracle's operators, in place; returns the histogram (counts, occupied) taken before undoMask"""
+    hist = (None, None)
     if "naive" in stages:
         orc.naive(grid, seeds, CFG3["dfunc"])
     if "remove_isolated" in stages:
@@ -378,15 +475,17 @@ def oracle_pipeline(orc, grid, seeds, noise, stages):
         et, es, ei, ep, eth = CFG3["erosion"]
         orc.erode(grid, noise, et, es, ei, ep, eth)
     if "histogram_undo_mask" in stages:
-        orc.count_values(grid)
+        hist = orc.count_values(grid)
         orc.undo_mask(grid, 15, False)
     if "histogram" in stages:
-        orc.count_values(grid)
+        hist = orc.count_values(grid)
     if "undo_mask" in stages:
         orc.undo_mask(grid, 15, False)
+    return hist
 
 
 def cpu_baseline(n, stages, steps=1):
+    """-> (the cpu_baseline block, {"grid", "counts", "occupied"} of the oracle's result for the parity check)"""
     import oracle as orc
 
     orc.use_all_cores()
@@ -396,11 +495,12 @@ def cpu_baseline(n, stages, steps=1):
     for _ in range(steps):
         g = np.ones((n, n, n), np.uint16)
         t0 = time.perf_counter()
-        oracle_pipeline(orc, g, seeds, noise, stages)
+        counts, occ = oracle_pipeline(orc, g, seeds, noise, stages)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return {"value": n**3 / best / 1e9, "unit": "Gvoxels/s", "cores": orc.num_threads(), "kind": "port",
+    info = {"value": n**3 / best / 1e9, "unit": "Gvoxels/s", "cores": orc.num_threads(), "kind": "port",
             "sample": f"{n}^3 dense grid, same pipeline and seed count (stages {stages}), {best:.2f} s", "seconds": best}
+    return info, {"grid": g, "counts": counts, "occupied": occ}
 
 
 ALL_STAGES = ["naive", "remove_isolated", "erode", "histogram", "undo_mask"]
@@ -776,6 +876,7 @@ def main():
     ap.add_argument("--jobs", type=int, default=0, help="batch workload: concurrent contexts (streams + host threads) per GPU; 0 = 16, or 8 with 8..15 host cores per rank")
     ap.add_argument("--blocking-sync", default="auto", choices=["auto", "on", "off"],
                     help="batch workload: contexts wait on blocking events instead of spinning (auto: when jobs x ranks exceed the host cores)")
+    ap.add_argument("--no-vessel", action="store_true", help="default workload: skip the sparse cfg3-vessel sub-line reported under \"vessel\"")
     ap.add_argument("--no-batch", action="store_true", help="default workload: skip the short cfg4 batch measurement reported under \"batch\"")
     ap.add_argument("--mesh-pool", type=int, default=8, help="batch workload: distinct synthetic shapes generated up front")
     args = ap.parse_args()
