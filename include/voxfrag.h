@@ -122,6 +122,10 @@ vf_status vf_ctx_set_blocking_sync(vf_ctx* ctx, int on);
  * latency for one job).  A narrower window orders the fronts better at the price of more rounds: 8 gives the highest throughput
  * when several jobs share the GPU (measured: 182 -> 200 models/s in batch generation). */
 vf_status vf_ctx_set_flood_levels(vf_ctx* ctx, uint32_t levels);
+/* How vf_remove_isolated_regions (C1) is computed; the result is the same.  0 (default): one streaming "descent certificate" pass plus list
+ * work on the cells it cannot certify, falling back to the union-find when those lists outgrow 65 536 cells, two seeds share a label or
+ * the rows are not 16-byte aligned.  1: the union-find only. */
+vf_status vf_ctx_set_c1_mode(vf_ctx* ctx, int mode);
 void*     vf_ctx_stream(vf_ctx* ctx);                                    /* the cudaStream_t every call of this context is issued on */
 uint64_t  vf_ctx_kernel_launches(vf_ctx* ctx);                           /* kernels launched by this context so far (bench "gpu_launches") */
 /* CUDA-event timing on the context's stream (ResourceTracker's role, SRC/Utilities/ResourceTracker.cpp:58-72) */

@@ -1,0 +1,82 @@
+// glsl_rt.h — TEST INFRASTRUCTURE (oracle/): just enough of the GLSL 4.50 compute language, as C++, for the reference's fracturer
+// shaders to compile unmodified where they lie (oracle/ref_shim/glsl2cpp.py turns each `*-comp.glsl` under
+// /root/reference/MeshFragments/Assets/Shaders/Compute/Fracturer into an include file: `#include <...>` expanded the way
+// ShaderProgram::includeLibraries does (ShaderProgram.cpp:362-404), buffer blocks turned into pointers, `main` renamed; nothing in a
+// shader's body is rewritten except `.xyz` -> `.xyz()`).  Only what those shaders use is here.  Arithmetic follows the GLSL rules the
+// shaders rely on: uint wraps modulo 2^32, float is IEEE binary32 (the file is compiled with -ffp-contract=off), uvec + ivec adds in uint.
+#pragma once
+
+#include <stdint.h>
+
+#include <cmath>
+
+typedef unsigned int uint;
+
+struct uvec3;
+struct ivec3;
+
+struct vec3 {
+    float x, y, z;
+    vec3() : x(0), y(0), z(0) {}
+    vec3(float a, float b, float c) : x(a), y(b), z(c) {}
+    vec3(const uvec3& v);  // implicit, as GLSL converts uvec3 -> vec3 in a call
+};
+
+struct uvec3 {
+    uint x, y, z;
+    uvec3() : x(0), y(0), z(0) {}
+    template <typename A, typename B, typename C>
+    uvec3(A a, B b, C c) : x((uint)a), y((uint)b), z((uint)c) {}  // uvec3(float, float, float) truncates towards zero
+    explicit uvec3(uint s) : x(s), y(s), z(s) {}
+};
+inline vec3::vec3(const uvec3& v) : x((float)v.x), y((float)v.y), z((float)v.z) {}
+
+struct ivec3 {
+    int x, y, z;
+    ivec3() : x(0), y(0), z(0) {}
+    ivec3(int a, int b, int c) : x(a), y(b), z(c) {}
+    explicit ivec3(int s) : x(s), y(s), z(s) {}
+    explicit ivec3(uint s) : x((int)s), y((int)s), z((int)s) {}
+    explicit ivec3(const uvec3& v) : x((int)v.x), y((int)v.y), z((int)v.z) {}
+};
+inline ivec3 operator+(const ivec3& a, const ivec3& b) { return ivec3(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline ivec3 operator-(const ivec3& a, const ivec3& b) { return ivec3(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline int glsl_clamp1(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }  // min(max(x, minVal), maxVal)
+inline ivec3 clamp(const ivec3& v, const ivec3& lo, const ivec3& hi) { return ivec3(glsl_clamp1(v.x, lo.x, hi.x), glsl_clamp1(v.y, lo.y, hi.y), glsl_clamp1(v.z, lo.z, hi.z)); }
+
+struct ivec4 {
+    int x, y, z, w;
+};
+struct uvec4 {
+    uint x, y, z, w;
+    uvec4() : x(0), y(0), z(0), w(0) {}
+    uvec4(uint a, uint b, uint c, uint d) : x(a), y(b), z(c), w(d) {}
+    template <typename W>
+    uvec4(const uvec3& v, W d) : x(v.x), y(v.y), z(v.z), w((uint)d) {}
+    uvec3 xyz() const { return uvec3(x, y, z); }
+};
+// uvec4 + ivec4: the signed operand converts to unsigned, the sum wraps (floodFracturer-comp.glsl:33 relies on it for "-1")
+inline uvec4 operator+(const uvec4& a, const ivec4& b) { return uvec4(a.x + (uint)b.x, a.y + (uint)b.y, a.z + (uint)b.z, a.w + (uint)b.w); }
+
+inline float distance(const vec3& p, const vec3& q)
+{
+    const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
+    return sqrtf(dx * dx + dy * dy + dz * dz);
+}
+inline float abs(float v) { return fabsf(v); }
+inline float max(float a, float b) { return a < b ? b : a;  }
+inline float floor(uint v) { return (float)v; }  // floor(index / numNeighbors): the quotient is an integer already
+
+inline uint atomicAdd(uint& mem, uint data) { return __atomic_fetch_add(&mem, data, __ATOMIC_RELAXED); }
+inline uint atomicMin(uint& mem, uint data)
+{
+    uint old = __atomic_load_n(&mem, __ATOMIC_RELAXED);
+    while (data < old && !__atomic_compare_exchange_n(&mem, &old, data, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
+
+// gl_GlobalInvocationID of the invocation running on this host thread
+extern thread_local uvec3 gl_GlobalInvocationID;
+
+#define uniform      /* a plain namespace-scope variable the driver assigns */
+#define in           /* parameter qualifier */

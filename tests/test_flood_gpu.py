@@ -240,11 +240,19 @@ def test_graph_driven_round_loop_is_bit_exact(orc, vessel_grid, monkeypatch, lev
     c.close()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("VF_TEST_EXPERIMENTAL") != "1", reason="experimental path: set VF_TEST_EXPERIMENTAL=1")
-def test_c1_descent_formulation_is_bit_exact(ctx, orc, vessel_grid, monkeypatch):
-    """VF_C1_DESCENT=1 (csrc/c1_descent.cu): certificate pass + list work instead of the union-find; same cases as the C1 tests above plus a
-    dense Voronoi grid (few failing cells), labels without a seed and a grid whose Z is not a multiple of 8 (declines, union-find runs)."""
-    monkeypatch.setenv("VF_C1_DESCENT", "1")
+@pytest.mark.parametrize("c1_mode", [0, 1])
+def test_c1_both_formulations_are_bit_exact(ctx, orc, vessel_grid, c1_mode):
+    """C1 by descent certificate (csrc/c1_descent.cu, the default: certificate pass + list work) and by the union-find alone (setC1Mode(1));
+    same cases as the C1 tests above plus a dense Voronoi grid (few failing cells), labels without a seed and a grid whose Z is not a
+    multiple of 8 (the certificate declines, the union-find runs)."""
+    ctx.setC1Mode(c1_mode)
+    try:
+        _c1_cases(ctx, orc, vessel_grid)
+    finally:
+        ctx.setC1Mode(0)
+
+
+def _c1_cases(ctx, orc, vessel_grid):
     for dfunc in (0, 1, 2):
         seeds, _ = orc.seed_uniform(orc.Rng(80), vessel_grid, 12)
         lab = orc.naive(vessel_grid.copy(), seeds, dfunc)

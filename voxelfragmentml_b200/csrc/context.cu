@@ -118,7 +118,16 @@ extern "C" vf_status vf_ctx_set_blocking_sync(vf_ctx* ctx, int on)
 extern "C" vf_status vf_ctx_set_flood_levels(vf_ctx* ctx, uint32_t levels)
 {
     VF_REQUIRE(ctx != nullptr, VF_ERR_INVALID_ARGUMENT, "null context");
+    VF_REQUIRE(levels < (1u << 17), VF_ERR_INVALID_ARGUMENT, "flood levels %u: the key field holds 17 bits of distance (0 = library default)", levels);
     ctx->flood_levels = levels;
+    return VF_OK;
+}
+
+extern "C" vf_status vf_ctx_set_c1_mode(vf_ctx* ctx, int mode)
+{
+    VF_REQUIRE(ctx != nullptr, VF_ERR_INVALID_ARGUMENT, "null context");
+    VF_REQUIRE(mode == 0 || mode == 1, VF_ERR_INVALID_ARGUMENT, "c1 mode %d (0 = descent certificate + fallback, 1 = union-find only)", mode);
+    ctx->c1_mode = mode;
     return VF_OK;
 }
 

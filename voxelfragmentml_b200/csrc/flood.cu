@@ -506,7 +506,6 @@ struct Job {
     uint32_t* h_mail;     // pinned mailbox
     int blocks_stream;    // grid for streaming kernels
     int blocks_tiles;     // grid for tile kernels
-    bool graph;           // rounds driven by a CUDA graph while-loop on the device (VF_FLOOD_GRAPH=1; experimental, off by default)
 };
 
 vf_status job_begin(vf_grid* grid, Job& j)
@@ -530,7 +529,6 @@ vf_status job_begin(vf_grid* grid, Job& j)
     j.wl.epoch = 1;
     j.wl.lo = base + 11;
     j.wl.levels = c->flood_levels ? c->flood_levels : kLevelsPerRound;
-    if (const char* e = std::getenv("VF_FLOOD_LEVELS")) j.wl.levels = (uint32_t)std::max(1, std::atoi(e));  // tuning knob for tools/
     j.wl.pend = (uint32_t*)((char*)base + pend_off);
     VF_CUDA(cudaMemsetAsync(base, 0, 16 * 4, c->stream));
     VF_CUDA(cudaMemsetAsync(j.wl.stamp, 0, nt * 4 + 2 * nt, c->stream));
@@ -538,11 +536,6 @@ vf_status job_begin(vf_grid* grid, Job& j)
     j.h_mail = (uint32_t*)((char*)c->pinned + 65536);  // upper half of the mailbox; the lower half carries seeds
     j.blocks_stream = c->num_sms * 8;
     j.blocks_tiles = c->num_sms * 4;
-    // tuning knob for tools/: CTAs per SM of a round launch.  A round of a 256-max shell lists ~170 tiles, so most of the 4 x 148 CTAs leave at
-    // once; with many jobs per GPU those CTAs still take a launch slot each (57 KB of shared memory) for a microsecond.
-    if (const char* e = std::getenv("VF_FLOOD_CTAS_PER_SM")) j.blocks_tiles = c->num_sms * std::min(4, std::max(1, std::atoi(e)));
-    const char* ge = std::getenv("VF_FLOOD_GRAPH");
-    j.graph = ge != nullptr && ge[0] == '1';
     return VF_OK;
 }
 
@@ -595,81 +588,6 @@ bool make_keys_map(CUtensorMap* map, const uint32_t* keys, const TileGeom& g)
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-#ifdef VF_FLOOD_GRAPH_BUILD
-// ---- experimental, compiled only with -DVF_FLOOD_GRAPH_BUILD (VF_NVCC_EXTRA of build_lib.py) because the loop's device-side
-// cudaGraphSetConditional is an extern the driver resolves when the module is loaded: kept out of the default cubin until it has run on the
-// target driver.  Selected at run time with VF_FLOOD_GRAPH=1: the round loop as a CUDA graph `while` node.  The body is one round kernel that reads its round id
-// from the worklist header, followed by a one-thread kernel that advances the id and keeps the loop alive while the next round's list is
-// not empty.  A flood phase is then one graph launch and one 4-byte read-back instead of ~60 kernel launches and ~4 host synchronisations:
-// less host work per flood (batch producers with few cores per GPU) and no empty rounds.
-__global__ void flood_set_round_kernel(Worklist wl, uint32_t round) { wl.stats[kRoundWord] = round; }
-
-__global__ void flood_advance_kernel(Worklist wl, cudaGraphConditionalHandle loop, uint32_t last_round)
-{
-    const uint32_t next = wl.stats[kRoundWord] + 1;
-    wl.stats[kRoundWord] = next;
-    cudaGraphSetConditional(loop, (wl.count[next % 3] != 0 && next < last_round) ? 1u : 0u);
-}
-
-template <int NNEIGH>
-vf_status run_rounds_graph(Job& j, uint32_t* keys, CUtensorMap& map, int use_tma)
-{
-    vf_ctx* c = j.c;
-    auto kern = flood_round_kernel<NNEIGH, true>;
-    VF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    flood_set_round_kernel<<<1, 1, 0, c->stream>>>(j.wl, j.round);
-    VF_LAUNCHED(c);
-    struct Holder {  // released on every exit path
-        cudaGraph_t graph = nullptr;
-        cudaGraphExec_t exec = nullptr;
-        ~Holder()
-        {
-            if (exec) cudaGraphExecDestroy(exec);
-            if (graph) cudaGraphDestroy(graph);
-        }
-    } h;
-    VF_CUDA(cudaGraphCreate(&h.graph, 0));
-    cudaGraphConditionalHandle loop;
-    VF_CUDA(cudaGraphConditionalHandleCreate(&loop, h.graph, 1, cudaGraphCondAssignDefault));  // the first iteration always runs
-    cudaGraphNodeParams cp = {};
-    cp.type = cudaGraphNodeTypeConditional;
-    cp.conditional.handle = loop;
-    cp.conditional.type = cudaGraphCondTypeWhile;
-    cp.conditional.size = 1;
-    cudaGraphNode_t loop_node;
-    VF_CUDA(cudaGraphAddNode(&loop_node, h.graph, nullptr, 0, &cp));
-    cudaGraph_t body = cp.conditional.phGraph_out[0];
-
-    uint32_t unused_round = 0;
-    void* round_args[] = { &keys, &map, &use_tma, &j.g, &j.wl, &unused_round };
-    cudaKernelNodeParams rp = {};
-    rp.func = (void*)kern;
-    rp.gridDim = dim3((unsigned)j.blocks_tiles), rp.blockDim = dim3(kThreads);
-    rp.sharedMemBytes = (unsigned)kSmemBytes;
-    rp.kernelParams = round_args;
-    cudaGraphNode_t round_node;
-    VF_CUDA(cudaGraphAddKernelNode(&round_node, body, nullptr, 0, &rp));
-
-    uint32_t last_round = j.round + 100000;  // the guard of run_rounds
-    void* adv_args[] = { &j.wl, &loop, &last_round };
-    cudaKernelNodeParams ap = {};
-    ap.func = (void*)flood_advance_kernel;
-    ap.gridDim = dim3(1), ap.blockDim = dim3(1);
-    ap.kernelParams = adv_args;
-    cudaGraphNode_t adv_node;
-    VF_CUDA(cudaGraphAddKernelNode(&adv_node, body, &round_node, 1, &ap));
-
-    VF_CUDA(cudaGraphInstantiate(&h.exec, h.graph, 0));
-    VF_CUDA(cudaGraphLaunch(h.exec, c->stream));
-    VF_CUDA(cudaMemcpyAsync(j.h_mail, j.wl.stats + kRoundWord, 4, cudaMemcpyDeviceToHost, c->stream));
-    VF_CUDA(vf_sync(c));
-    const uint32_t reached = j.h_mail[0];
-    c->launches += 2ull * (reached - j.round);  // the kernels the loop ran
-    j.round = reached;
-    if (reached >= last_round) return vf_set_error(VF_ERR_CAPACITY, "tile worklist did not drain");
-    return VF_OK;
-}
-#endif  // VF_FLOOD_GRAPH_BUILD
 
 template <int NNEIGH>
 vf_status flood_phase(Job& j, uint32_t* keys)
@@ -678,11 +596,6 @@ vf_status flood_phase(Job& j, uint32_t* keys)
     VF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     CUtensorMap map;
     const int use_tma = make_keys_map(&map, keys, j.g) ? 1 : 0;  // otherwise: per-row cp.async staging
-#ifdef VF_FLOOD_GRAPH_BUILD
-    if (j.graph) return run_rounds_graph<NNEIGH>(j, keys, map, use_tma);
-#else
-    VF_REQUIRE(!j.graph, VF_ERR_UNSUPPORTED, "VF_FLOOD_GRAPH=1 needs a library built with -DVF_FLOOD_GRAPH_BUILD (VF_NVCC_EXTRA)");
-#endif
     return run_rounds(j, [&](uint32_t r) { kern<<<j.blocks_tiles, kThreads, kSmemBytes, j.c->stream>>>(keys, map, use_tma, j.g, j.wl, r); });
 }
 
@@ -734,10 +647,6 @@ extern "C" vf_status vf_fracture_flood(vf_grid* grid, const uint32_t* seeds, uin
     flood_seed_kernel<<<1, 32, 0, c->stream>>>(keys, j.g, j.wl, d_seeds, (int)nseeds, j.round);
     VF_LAUNCHED(c);
     VF_TRY(nneigh == 6 ? flood_phase<6>(j, keys) : flood_phase<26>(j, keys));
-    if (std::getenv("VF_FLOOD_DEBUG")) {
-        VF_TRY(read_stats(j, hs));
-        std::fprintf(stderr, "[flood] phase 1: rounds %u visits %u steps %u max steps/visit %u\n", hs[ST_ROUNDS], hs[ST_VISITS], hs[ST_STEPS], hs[ST_MAXSTEPS]);
-    }
     const bool need_f3 = id_bits == 8 && prefixes;
     flood_finalize_kernel<<<j.blocks_stream, 256, 0, c->stream>>>(keys, grid->d, n, d_seeds, (id_bits == 8 && !need_f3) ? 0xFFu : 0xFFFFu, j.wl.stats);
     VF_LAUNCHED(c);
@@ -793,12 +702,12 @@ extern "C" vf_status vf_remove_isolated_regions(vf_grid* grid, const uint32_t* s
     VF_TRY(vf_enter(c));
     ushort4* d_seeds = nullptr;
     VF_TRY(vf_upload_seeds(c, seeds, nseeds, grid->X, grid->Y, grid->Z, &d_seeds));
-    if (const char* e = std::getenv("VF_C1_DESCENT")) {  // experimental formulation (c1_descent.cu); falls through when it declines
-        if (e[0] == '1') {
-            int handled = 0;
-            VF_TRY(vf_k_c1_descent(grid, d_seeds, (int)nseeds, &handled));
-            if (handled) return VF_OK;
-        }
+    if (c->c1_mode == 0) {  // descent certificate (c1_descent.cu); the union-find below takes over when it declines
+        int handled = 0;
+        uint32_t max_label = 0;
+        for (uint32_t i = 0; i < nseeds; ++i) max_label = std::max(max_label, seeds[4 * i + 3]);
+        VF_TRY(vf_k_c1_descent(grid, d_seeds, (int)nseeds, max_label, &handled));
+        if (handled) return VF_OK;
     }
     return vf_k_keep_seed_components(grid, d_seeds, (int)nseeds, 0, 6, nullptr);
 }

@@ -94,6 +94,7 @@ struct vf_ctx {
     cudaEvent_t ev_block = nullptr;  // cudaEventBlockingSync: waits that give the host core back (vf_ctx_set_blocking_sync)
     bool blocking_sync = false;
     uint32_t flood_levels = 0;  // width of a flood round's distance window; 0 = the library default (vf_ctx_set_flood_levels)
+    int c1_mode = 0;            // C1: 0 = descent certificate with the union-find as its fallback, 1 = union-find only (vf_ctx_set_c1_mode)
     VfMt19937 rng;
     uint32_t crand = 80;  // state of the C runtime's rand() as the reference's platform implements it (MSVC LCG); srand(_seed), CADScene.cpp:36
     // scratch arenas, grown on demand (FloodFracturer.cpp:116-120 "grown on demand")
@@ -142,7 +143,7 @@ vf_status vf_k_zero(vf_ctx* ctx, void* d, size_t bytes);  // zero-fill by kernel
 // ---------------------------------------------------------------------------------------------- kernels (one per file)
 vf_status vf_k_naive(vf_grid* g, const ushort4* d_seeds, uint32_t nseeds, int dfunc);
 vf_status vf_k_keep_seed_components(vf_grid* grid, const ushort4* d_starts, int nstarts, int mode, int nneigh, uint32_t* d_freed);  // ccl.cu
-vf_status vf_k_c1_descent(vf_grid* grid, const ushort4* d_seeds, int nseeds, int* handled);  // c1_descent.cu (experimental, VF_C1_DESCENT=1)
+vf_status vf_k_c1_descent(vf_grid* grid, const ushort4* d_seeds, int nseeds, uint32_t max_label, int* handled);  // c1_descent.cu
 vf_status vf_k_pointwise(vf_grid* g, int op);  // 0 undoMask(bit15) 1 undoMask(rightmost 8) 2 resetFilling 3 homogenize
 enum { VF_PW_UNMASK15 = 0, VF_PW_RIGHTMOST8 = 1, VF_PW_RESET_FILLING = 2, VF_PW_HOMOGENIZE = 3 };
 
