@@ -402,9 +402,7 @@ def run_cuda(args):
         "metric": "Gvoxels/s fragmented at 512^3", "value": world * N * args.steps / (total_ms * 1e-3) / 1e9, "unit": "Gvoxels/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u16 labels / int32 distance keys", "data": "synthetic",
-        "config": {"workload": f"cfg3-dense: {n}^3 all-occupied grid, NAIVE EUCLIDEAN {CFG3['nseeds']} seeds + connected-to-seed cleanup"
-                               " + erode(ELLIPSE,3,3it,p.5,thr.5) + histogram + undoMask", "stages": stages_run, "grid": list(dims),
-                   "l2": "input rewritten, then a 256 MiB scratch buffer (2x the 126 MB L2) overwritten on the same stream before every timed call", "parallelism": f"replicas x{world} (one grid per GPU)"},
+        "config": cfg3_config(n, stages_run, world),
         "stage_ms": stage_ms,
         "stage_roofline": stage_roofline,
         "fragmentation_only": {"value": world * N / naive_t / 1e9, "unit": "Gvoxels/s", "note": "F1 operator alone (NaiveFracturer::build without cleanup), CUDA events"},
@@ -452,7 +450,7 @@ def run_cuda(args):
             bad = int((got.reshape(-1) != want["grid"].reshape(-1)).sum())
             hist_ok = bool(np.array_equal(np.asarray(counts), want["counts"]) and int(occ) == int(want["occupied"]))
             out["parity_checked"] = bad == 0 and hist_ok
-            out["parity"] = {"against": "oracle (OpenMP restatement; C++-sourced stages pinned by the reference's own code, tests/test_oracle_vs_ref.py)",
+            out["parity"] = {"against": "oracle (OpenMP restatement, pinned by the reference's C++ compiled in place and by the reference's compute shaders compiled as C++: tests/test_oracle_vs_ref.py, tests/test_oracle_vs_glsl.py)",
                              "cells": int(N), "mismatching_cells": bad, "histogram_equal": hist_ok, "occupied": int(occ)}
         else:
             out["parity_checked"] = False
@@ -525,18 +523,48 @@ def load_ref_lib():
     return L
 
 
-def reference_pipeline(ref, orc, grid, seeds, noise):
-    """cfg3 on the host with as much of the REFERENCE'S OWN code as exists for the CPU: NaiveFracturer::buildCPU and
-    removeIsolatedRegionsCPU (NaiveFracturer.cpp:26-68, 111-150; serial, as written) from oracle/_ref; erosion, histogram and undoMask
-    exist only as GLSL in the reference, so those stages run the oracle's OpenMP restatement."""
+def load_glsl_lib():
+    """oracle/_ref/libvf_ref_glsl.so: the reference's own compute shaders compiled as C++ from the text under /root/reference
+    (oracle/ref_shim/glsl2cpp.py + ref_glsl.cpp, OpenMP over the invocations); built in the build container, travels with the snapshot."""
+    import ctypes as C
+
+    path = os.path.join(ROOT, "oracle", "_ref", "libvf_ref_glsl.so")
+    if not os.path.exists(path):
+        return None
+    try:
+        L = C.CDLL(path)
+    except OSError:
+        return None
+    u16 = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
+    u32 = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+    f32 = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+    L.glsl_naive.argtypes = [u16, u32, u32, C.c_uint32, C.c_int]
+    L.glsl_erode.argtypes = [u16, u32, C.c_int, C.c_uint32, C.c_uint32, C.c_float, C.c_float, f32, C.c_uint32, C.c_int]
+    L.glsl_undo_mask.argtypes = [u16, u32, C.c_uint32, C.c_int]
+    return L
+
+
+def cfg3_config(n, stages, world):
+    """the `config` block of the cfg3 line: the CUDA arm and the reference arm describe the same workload"""
+    return {"workload": f"cfg3-dense: {n}^3 all-occupied grid, NAIVE EUCLIDEAN {CFG3['nseeds']} seeds + connected-to-seed cleanup"
+                        " + erode(ELLIPSE,3,3it,p.5,thr.5) + histogram + undoMask", "stages": stages, "grid": [n, n, n],
+            "l2": "input rewritten, then a 256 MiB scratch buffer (2x the 126 MB L2) overwritten on the same stream before every timed call",
+            "parallelism": f"replicas x{world} (one grid per GPU)"}
+
+
+def reference_pipeline(ref, glsl, orc, grid, seeds, noise):
+    """cfg3 on the host cores with the REFERENCE'S OWN code: naiveFracturer-comp.glsl (NaiveFracturer::buildGPU's dispatch), then
+    NaiveFracturer::removeIsolatedRegionsCPU (NaiveFracturer.cpp:111-150, serial as written; oracle/_ref/libvf_ref.so), then RegularGrid::erode's
+    loop over detectBoundaries / erodeGrid / copyGrid / removeIsolatedRegionsGrid-comp.glsl, then undoMask-comp.glsl.  Only countValues, serial
+    host code inside RegularGrid.cpp (which needs OpenGL to compile), runs the oracle's restatement."""
     dims = np.asarray(grid.shape, np.uint32)
     s32 = np.ascontiguousarray(seeds, np.uint32)
-    ref.ref_naive_build_cpu(grid, dims, s32, len(s32), CFG3["dfunc"])
+    glsl.glsl_naive(grid, dims, s32, len(s32), CFG3["dfunc"])
     ref.ref_remove_isolated_regions_cpu(grid, dims, s32, len(s32))
     et, es, ei, ep, eth = CFG3["erosion"]
-    orc.erode(grid, noise, et, es, ei, ep, eth)
+    glsl.glsl_erode(grid, dims, et, es, ei, ep, eth, noise, len(noise), 2)  # the final sweep concurrently in place, as the GPU runs it
     orc.count_values(grid)
-    orc.undo_mask(grid, 15, False)
+    glsl.glsl_undo_mask(grid, dims, 15, 0)
 
 
 def run_reference(args):
@@ -547,27 +575,37 @@ def run_reference(args):
 
     orc.use_all_cores()
     ref = None if args.ref_impl == "port" else load_ref_lib()
-    if args.ref_impl == "ref" and ref is None:
-        emit_json(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libvf_ref.so was not built (needs /root/reference at build time)"}))
+    glsl = None if args.ref_impl == "port" else load_glsl_lib()
+    have_ref = ref is not None and glsl is not None
+    if args.ref_impl == "ref" and not have_ref:
+        emit_json(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libvf_ref.so / libvf_ref_glsl.so were not built (need /root/reference at build time)"}))
         return
-    # bounded sample: the reference's buildCPU is a serial loop with a std::function call per (cell, seed) — about 5 s per step at 256^3
-    n = args.cpu_size or (256 if ref is not None else 384)
+    full = args.size
+    # bounded sample: a step of the reference's shaders on the host cores takes ~10 s at 256^3 on 8 cores; the grid edge is chosen below so that
+    # the timed steps end within about two and a half minutes.  Throughput per voxel barely depends on the edge (slightly better when smaller).
+    n = args.cpu_size or 256
     seeds = synth_seeds_dense(n, CFG3["nseeds"], rng_uniform_stream(CFG3["rng_seed"]))
-    noise = noise_table(CFG3["rng_seed"] + 1000, CFG3["nnoise"])
+    noise = np.ascontiguousarray(noise_table(CFG3["rng_seed"] + 1000, CFG3["nnoise"]), np.float32)
 
     def step(g):
-        if ref is not None:
-            reference_pipeline(ref, orc, g, seeds, noise)
+        if have_ref:
+            reference_pipeline(ref, glsl, orc, g, seeds, noise)
         else:
             oracle_pipeline(orc, g, seeds, noise, ALL_STAGES)
 
-    # one untimed step; it also sizes the sample so that the timed steps end within about two and a half minutes
-    t0 = time.perf_counter()
-    step(np.ones((n, n, n), np.uint16))
-    t_probe = time.perf_counter() - t0
-    if not args.cpu_size and t_probe * args.steps > 150.0:
-        n = max(96, int(n * (150.0 / (t_probe * args.steps)) ** (1.0 / 3.0)) // 32 * 32)
+    # one untimed probe on a small grid sizes the sample
+    if not args.cpu_size:
+        pn = 96
+        pseeds = synth_seeds_dense(pn, CFG3["nseeds"], rng_uniform_stream(CFG3["rng_seed"]))
+        seeds_keep, seeds = seeds, pseeds
+        t0 = time.perf_counter()
+        step(np.ones((pn, pn, pn), np.uint16))
+        per_voxel = (time.perf_counter() - t0) / pn**3
+        seeds = seeds_keep
+        budget = 150.0 / max(1, args.steps + 1)
+        n = int(min(full, max(64, (budget / per_voxel) ** (1.0 / 3.0))) // 32 * 32)
         seeds = synth_seeds_dense(n, CFG3["nseeds"], rng_uniform_stream(CFG3["rng_seed"]))
+    step(np.ones((n, n, n), np.uint16))  # warm-up at the sample size
     times = []
     for _ in range(args.steps):
         g = np.ones((n, n, n), np.uint16)
@@ -576,24 +614,25 @@ def run_reference(args):
         times.append(time.perf_counter() - t0)
     total = float(sum(times))
     v = n**3 * args.steps / total / 1e9
-    if ref is not None:
-        kind, cores = "reference", 1
-        what = (f"cfg3-dense pipeline on a bounded {n}^3 sample: NaiveFracturer::buildCPU + removeIsolatedRegionsCPU are the reference's own code compiled in "
-                "place (oracle/_ref; serial as written, 1 core); erode + countValues + undoMask exist only as GLSL in the reference and run the oracle's "
-                f"OpenMP restatement ({orc.num_threads()} threads)")
+    cores = orc.num_threads()
+    if have_ref:
+        kind = "reference"
+        what = (f"bounded sample: the same pipeline and seed count on a {n}^3 all-occupied grid per step.  Reference shaders (naiveFracturer, detectBoundaries, "
+                f"erodeGrid, copyGrid, removeIsolatedRegionsGrid, undoMask -comp.glsl compiled as C++ from the reference's text) on {cores} host threads; "
+                "removeIsolatedRegionsCPU is the reference's C++ (serial as written); countValues is the oracle's restatement")
     else:
-        kind, cores = "port", orc.num_threads()
-        what = (f"cfg3-dense pipeline on a bounded {n}^3 sample (oracle/_ref not built; this is the CPU oracle, a restatement of NaiveFracturer::buildCPU + "
-                "erode + removeIsolatedRegionsCPU + countValues, OpenMP)")
+        kind = "port"
+        what = (f"bounded sample: the same pipeline and seed count on a {n}^3 all-occupied grid per step (oracle/_ref not built: the CPU oracle, an OpenMP "
+                f"restatement, {cores} threads)")
     emit_json(json.dumps({
         "impl": "reference", "metric": "Gvoxels/s fragmented at 512^3", "value": v, "unit": "Gvoxels/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u16 labels / f32 distances", "data": "synthetic",
-        "config": {"workload": what, "stages": ALL_STAGES, "grid": [n, n, n]},
-        "cpu_baseline": {"value": v, "unit": "Gvoxels/s", "cores": cores, "kind": kind, "sample": f"{n}^3 dense grid x {args.steps} steps"},
+        "config": cfg3_config(full, ["naive", "remove_isolated", "erode", "histogram_undo_mask"], int(os.environ.get("WORLD_SIZE", "1"))),
+        "sample_grid": [n, n, n], "same_size_as_config": n == full,
+        "cpu_baseline": {"value": v, "unit": "Gvoxels/s", "cores": cores, "kind": kind, "sample": what},
         "e2e": {"value": v, "unit": "Gvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
-
 
 
 # ------------------------------------------------------------------------------------------------ secondary workloads (not the driver's default)

@@ -8,12 +8,18 @@
 
 #include <stdint.h>
 
+#include <stddef.h>
+
 #include <cmath>
 
 typedef unsigned int uint;
 
 struct uvec3;
 struct ivec3;
+
+struct vec2 {
+    float x, y;
+};
 
 struct vec3 {
     float x, y, z;
@@ -63,9 +69,23 @@ inline float distance(const vec3& p, const vec3& q)
     const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
     return sqrtf(dx * dx + dy * dy + dz * dz);
 }
-inline float abs(float v) { return fabsf(v); }
-inline float max(float a, float b) { return a < b ? b : a;  }
-inline float floor(uint v) { return (float)v; }  // floor(index / numNeighbors): the quotient is an integer already
+// abs / max / floor: the including file brings std::abs, std::max and std::floor into each shader's namespace
+
+// A shader storage block `buffer B { T name[]; }`.  Out-of-range accesses behave as under robust buffer access (reads give zero, writes are
+// dropped): floodFracturer-comp.glsl:36 reads grid[] at a wrapped neighbour index BEFORE its bounds test.
+template <typename T>
+struct glsl_buffer {
+    T* p = nullptr;
+    size_t n = 0;
+    T sink;
+    void bind(T* ptr, size_t count) { p = ptr, n = count; }
+    T& operator[](size_t i)
+    {
+        if (i < n) return p[i];
+        sink = T();
+        return sink;
+    }
+};
 
 inline uint atomicAdd(uint& mem, uint data) { return __atomic_fetch_add(&mem, data, __ATOMIC_RELAXED); }
 inline uint atomicMin(uint& mem, uint data)

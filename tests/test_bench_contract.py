@@ -28,8 +28,9 @@ def test_reference_arm_line(ref_impl):
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     if ref_impl == "port":
         assert cb["kind"] == "port"
-    elif os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libvf_ref.so")):
-        assert cb["kind"] == "reference" and cb["cores"] == 1
+    elif all(os.path.exists(os.path.join(ROOT, "oracle", "_ref", f)) for f in ("libvf_ref.so", "libvf_ref_glsl.so")):
+        assert cb["kind"] == "reference" and "shaders" in cb["sample"]
+    assert d["sample_grid"] == [64, 64, 64] and d["same_size_as_config"] is False and d["config"]["grid"] == [512, 512, 512]
 
 
 def test_reference_arm_other_ranks_exit_quietly():
