@@ -122,6 +122,10 @@ vf_status vf_ctx_set_blocking_sync(vf_ctx* ctx, int on);
  * latency for one job).  A narrower window orders the fronts better at the price of more rounds: 8 gives the highest throughput
  * when several jobs share the GPU (measured: 182 -> 200 models/s in batch generation). */
 vf_status vf_ctx_set_flood_levels(vf_ctx* ctx, uint32_t levels);
+/* How a flood phase is driven; the labels do not depend on it.  1..4 (default 4): ONE cooperative launch per phase with that many CTAs per SM,
+ * the round loop on the device (no host read-back until the phase has converged): lowest latency for one job, and with 1 or 2 several jobs
+ * fit on the GPU side by side.  0: one launch per round, read-backs every few rounds (rounds of many jobs interleave freely). */
+vf_status vf_ctx_set_flood_mode(vf_ctx* ctx, int ctas_per_sm);
 /* How vf_remove_isolated_regions (C1) is computed; the result is the same.  0 (default): one streaming "descent certificate" pass plus list
  * work on the cells it cannot certify, falling back to the union-find when those lists outgrow 65 536 cells, two seeds share a label or
  * the rows are not 16-byte aligned.  1: the union-find only. */

@@ -215,28 +215,36 @@ def test_result_does_not_depend_on_the_distance_window_or_blocking_waits(orc, ve
     c.close()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("VF_TEST_EXPERIMENTAL") != "1", reason="experimental path: set VF_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("levels", [8, 16])
-def test_graph_driven_round_loop_is_bit_exact(orc, vessel_grid, monkeypatch, levels):
-    """VF_FLOOD_GRAPH=1: the round loop runs as a CUDA graph while-node on the device (csrc/flood.cu run_rounds_graph).  Same fixed point."""
+@pytest.mark.parametrize("mode", [0, 1, 2, 4])
+def test_result_does_not_depend_on_how_the_round_loop_is_driven(orc, vessel_grid, mode):
+    """setFloodMode: one cooperative launch per phase with 1 / 2 / 4 CTAs per SM (the round loop on the device, default 4) or one launch per
+    round (0).  Plain flood, extra seeds (two phases + union-find in between), a labyrinth (hundreds of rounds), a ragged grid without TMA."""
     import voxelfragmentml_b200 as vf
 
-    monkeypatch.setenv("VF_FLOOD_GRAPH", "1")
     c = vf.Context(0)
-    c.setFloodLevels(levels)
-    seeds, _ = orc.seed_uniform(orc.Rng(80), vessel_grid, 12)
+    c.setFloodMode(mode)
+    seeds, _ = orc.seed_uniform(orc.Rng(80), vessel_grid, 16)
     for dfunc in (1, 2):
-        want, _ = orc.flood(vessel_grid.copy(), seeds, dfunc)
-        got, st = _run_flood(c, vessel_grid, seeds, dfunc)
-        assert np.array_equal(got, want) and st.tile_rounds > 0
-    wseeds = orc.make_seeds(orc.Rng(80), vessel_grid, 6, 12, merge_dfunc=0)
-    want, _ = orc.flood(vessel_grid.copy(), wseeds, orc.CHEBYSHEV)
-    got, _ = _run_flood(c, vessel_grid, wseeds, 2)
+        want, st = orc.flood(vessel_grid.copy(), seeds, dfunc)
+        got, gst = _run_flood(c, vessel_grid, seeds, dfunc)
+        assert np.array_equal(got, want) and gst.max_dist == st.max_dist
+        xs = orc.make_seeds(orc.Rng(85), vessel_grid, 5, 10)
+        want, st = orc.flood(vessel_grid.copy(), xs, dfunc)
+        got, gst = _run_flood(c, vessel_grid, xs, dfunc)
+        assert np.array_equal(got, want) and gst.disjoint_rounds == st.rounds and gst.freed_voxels == st.freed_voxels
+    lab = np.zeros((48, 40, 64), np.uint16)  # serpentine corridor: the front crosses the same tiles again and again
+    lab[1:-1, 1:-1, 1:-1] = 1
+    for x in range(4, 44, 4):
+        lab[x, (1 if (x // 4) % 2 else 4):(36 if (x // 4) % 2 else 39), :] = 0
+    sd = np.uint32([[2, 2, 2, 2], [45, 37, 60, 3]])
+    want, st = orc.flood(lab.copy(), sd, 1)
+    got, gst = _run_flood(c, lab, sd, 1)
+    assert np.array_equal(got, want) and gst.max_dist == st.max_dist
+    rag = random_blob_grid((33, 21, 75), 9, fill=0.6)  # Z % 4 != 0: keys are staged row by row, the loop is driven from the host
+    sd = pick_seeds(rag, 5, 2)
+    want, _ = orc.flood(rag.copy(), sd, 2)
+    got, _ = _run_flood(c, rag, sd, 2)
     assert np.array_equal(got, want)
-    empty = np.zeros((20, 20, 40), np.uint16)  # nothing to flood: the loop body runs once on an empty list
-    empty[3, 3, 3] = 1
-    got, _ = _run_flood(c, empty, np.uint32([[3, 3, 3, 2]]), 1)
-    assert got[3, 3, 3] == 2 and got.sum() == 2
     c.close()
 
 

@@ -70,6 +70,7 @@ SIGNATURES = {
     "vf_ctx_set_blocking_sync": (C.c_int, [_vp, C.c_int]),
     "vf_ctx_set_flood_levels": (C.c_int, [_vp, _u32]),
     "vf_ctx_set_c1_mode": (C.c_int, [_vp, C.c_int]),
+    "vf_ctx_set_flood_mode": (C.c_int, [_vp, C.c_int]),
     "vf_ctx_stream": (_vp, [_vp]),
     "vf_ctx_kernel_launches": (C.c_uint64, [_vp]),
     "vf_ctx_timer_start": (C.c_int, [_vp]),

@@ -125,6 +125,10 @@ class Context:
         """distance window of a flood round (0 = default 16: best latency; 8: best throughput with several jobs per GPU)"""
         check(self._lib.vf_ctx_set_flood_levels(self._h, int(levels)))
 
+    def setFloodMode(self, ctas_per_sm: int):
+        """flood phases: 1..4 = one cooperative launch per phase with that many CTAs per SM (default 4), 0 = one launch per round; same labels"""
+        check(self._lib.vf_ctx_set_flood_mode(self._h, int(ctas_per_sm)))
+
     def setC1Mode(self, mode: int):
         """C1 (removeIsolatedRegions): 0 = descent certificate with the union-find as fallback (default), 1 = union-find only; same result"""
         check(self._lib.vf_ctx_set_c1_mode(self._h, int(mode)))

@@ -123,6 +123,14 @@ extern "C" vf_status vf_ctx_set_flood_levels(vf_ctx* ctx, uint32_t levels)
     return VF_OK;
 }
 
+extern "C" vf_status vf_ctx_set_flood_mode(vf_ctx* ctx, int ctas_per_sm)
+{
+    VF_REQUIRE(ctx != nullptr, VF_ERR_INVALID_ARGUMENT, "null context");
+    VF_REQUIRE(ctas_per_sm >= 0 && ctas_per_sm <= 4, VF_ERR_INVALID_ARGUMENT, "flood mode %d: 0 = one launch per round, 1..4 = CTAs per SM of the cooperative loop", ctas_per_sm);
+    ctx->flood_coop = ctas_per_sm;
+    return VF_OK;
+}
+
 extern "C" vf_status vf_ctx_set_c1_mode(vf_ctx* ctx, int mode)
 {
     VF_REQUIRE(ctx != nullptr, VF_ERR_INVALID_ARGUMENT, "null context");

@@ -21,6 +21,7 @@
 // fragment's minimum and re-floods from all labelled cells.  Restated: keep, per fragment id, only the component (under the
 // flood neighbourhood, through equal-fragId cells) that contains the fragment's lowest-prefix source; free the rest; re-flood
 // with order(cell) = index of that source.  One such round reaches the reference loop's fixed point (numDisjointVoxels == 0).
+#include <cooperative_groups.h>
 #include <cuda.h>  // CUtensorMap (types only; the encoder comes through cudaGetDriverEntryPoint)
 
 #include <algorithm>
@@ -42,6 +43,20 @@ constexpr uint32_t kLevelsPerRound = 16;     // width of a round's distance wind
 constexpr uint32_t kNoLevel = 0xFFFFFFFFu;
 
 enum { ST_VISITS = 0, ST_ROUNDS = 1, ST_ERROR = 2, ST_FREED = 3, ST_MAXDIST = 4, ST_CHANGED = 5, ST_STEPS = 6, ST_MAXSTEPS = 7 };
+
+#ifdef VF_FLOOD_TIMING  // tools/ only (VF_NVCC_EXTRA=-DVF_FLOOD_TIMING): cycles per phase of a tile visit, summed over visits
+__device__ unsigned long long g_flood_cycles[8];  // 0 load, 1 masks, 2 relaxation, 3 write-back + wake, 4 visits, 5 steps
+#define VF_TICK(slot)                                                   \
+    do {                                                                \
+        if (threadIdx.x == 0) {                                         \
+            const long long now__ = clock64();                          \
+            atomicAdd(&g_flood_cycles[slot], (unsigned long long)(now__ - tick__)); \
+            tick__ = now__;                                             \
+        }                                                               \
+    } while (0)
+#else
+#define VF_TICK(slot) do { } while (0)
+#endif
 
 constexpr int kRoundWord = 14;  // worklist header layout: stats[8] count[3] lo[3] | word 14: device-resident round id (graph mode) | word 15 free
 constexpr size_t kSmemBytes = (size_t)(kCells + 5 * kThreads + 8 + 2) * sizeof(uint32_t);  // tile | 5 row-mask arrays | misc | mbarrier
@@ -258,13 +273,14 @@ __device__ __forceinline__ uint32_t min_neighbour_key(const uint32_t* sk, int x,
     return m;
 }
 
-// DEVROUND: the round id is read from device memory (word kRoundWord of the worklist header) instead of the launch parameter, so that
-// the same launch can be replayed by a CUDA graph loop (run_rounds_graph below; opt-in).
-template <int NNEIGH, bool DEVROUND>
+// COOP: ONE cooperative launch runs all rounds of a flood phase — the round loop lives on the device, rounds are separated by a grid barrier
+// instead of a kernel boundary, and the host is not involved until the phase has converged (it reads the id of the next round with the
+// flood's statistics).  Data that other CTAs wrote in an earlier round of the same launch (lists, counters, pending masks, keys) is read
+// past the L1 (__ldcg, TMA; the host only launches this variant when the keys qualify for TMA staging).  !COOP: one launch per round (several jobs sharing a GPU interleave their rounds that way).
+template <int NNEIGH, bool COOP>
 __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __restrict__ keys, const __grid_constant__ CUtensorMap keys_map, int use_tma,
-                                                                  TileGeom g, Worklist wl, uint32_t round_arg)
+                                                                  TileGeom g, Worklist wl, uint32_t round_arg, uint32_t last_round)
 {
-    const uint32_t round = DEVROUND ? __ldcg(wl.stats + kRoundWord) : round_arg;
     extern __shared__ __align__(128) uint32_t sm[];
     uint32_t* sk = sm;
     uint32_t* act = sm + kCells;        // [2][kThreads] wavefront bitmasks, one word per z-row
@@ -274,60 +290,81 @@ __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __re
     uint32_t* misc = pnd + kThreads;     // [0..3] neighbour-tile mask, [4] lowest deferred level
     const unsigned bar = (unsigned)__cvta_generic_to_shared(misc + 8);  // 8-byte aligned mbarrier for the TMA loads
     unsigned parity = 0;
-    const uint32_t count = wl.count[round % 3];
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    if (blockIdx.x == 0 && t == 0) {
-        wl.count[(round + 2) % 3] = 0;
-        wl.lo[(round + 2) % 3] = kNoLevel;
-        if (count) atomicAdd(&wl.stats[ST_ROUNDS], 1u);
-    }
-    // Rounds are launched in batches without knowing how long the worklists are: CTAs beyond the list — all of them once the flood
-    // has converged — leave before they set anything up, so that an empty round costs the GPU (and the other jobs sharing it) nothing.
-    if (blockIdx.x >= count) return;
-    if (use_tma) {
+    if (use_tma && (COOP || blockIdx.x < __ldcg(&wl.count[round_arg % 3]))) {
         if (threadIdx.x == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
     }
-    const uint32_t lo = wl.lo[round % 3];
+  for (uint32_t round = round_arg;; ++round) {
+    const uint32_t count = __ldcg(&wl.count[round % 3]);
+    if (blockIdx.x == 0 && t == 0) {
+        wl.count[(round + 2) % 3] = 0;
+        wl.lo[(round + 2) % 3] = kNoLevel;
+        if (count) atomicAdd(&wl.stats[ST_ROUNDS], 1u);
+    }
+    // !COOP: rounds are launched in batches without knowing how long the worklists are: CTAs beyond the list — all of them once the flood
+    // has converged — leave before they set anything up, so that an empty round costs the GPU (and the other jobs sharing it) nothing.
+    if (!COOP && blockIdx.x >= count) return;
+    const uint32_t lo = __ldcg(&wl.lo[round % 3]);
     const uint32_t hi = lo >= kNoLevel - wl.levels ? kNoLevel : lo + wl.levels;  // levels this round may assign: < hi
     for (uint32_t wi = blockIdx.x; wi < count; wi += gridDim.x) {
-        const uint32_t tile = wl.list[round & 1][wi];
+        const uint32_t tile = __ldcg(&wl.list[round & 1][wi]);
         const int tz = tile % g.ntz, ty = (tile / g.ntz) % g.nty, tx = tile / (g.ntz * g.nty);
         const int gx0 = tx * TX, gy0 = ty * TY, gz0 = tz * TZ;
 
+#ifdef VF_FLOOD_TIMING
+        long long tick__ = clock64();
+#endif
         if (use_tma) load_tile_tma(sk, &keys_map, bar, parity, g, gx0, gy0, gz0);
         else load_tile_async<NNEIGH>(sk, keys, g, gx0, gy0, gz0, KEY_WALL);
         if (t < 4) misc[t] = 0;
         if (t == 4) misc[4] = kNoLevel;
         __syncthreads();
+        VF_TICK(0);
 
         // ---- per-row masks: non-wall cells and the entry candidates.
         //      A tile that was already relaxed in this phase left its own edges repaired, and its cells have not changed since
         //      (only this tile writes them): new violations can only end in the layer of cells next to the halo.  The first visit
         //      (seeds or phase-2 sources inside) and slab tiles that contain a neighbour GPU's plane check every cell.
-        const uint32_t sflag = wl.seen[tile];
+        const uint32_t sflag = __ldcg(&wl.seen[tile]);
         const bool revisit = (sflag & 0x7Fu) == wl.epoch, has_pending = revisit && (sflag & 0x80u);
         const bool full_entry = !revisit || (g.fix_lo && tx == 0) || (g.fix_hi && tx == g.ntx - 1);
-        for (int r = warp * 32; r < warp * 32 + 32; ++r) {  // warp per row, lane = z: conflict-free whatever the row stride
-            const int x = r / TY, y = r % TY;
-            // slab mode: halo planes are copies of a neighbour GPU's cells — sources only
-            const bool fixed = (g.fix_lo && gx0 + x == 0) || (g.fix_hi && gx0 + x == g.X - 1);
-            const unsigned w = __ballot_sync(kFull, !fixed && sk[sidx(x, y, lane)] != KEY_WALL);
-            if (lane == 0) {
-                const bool face = x == 0 || x == TX - 1 || y == 0 || y == TY - 1;
-                nw[r] = w;
-                chg[r] = 0;
-                pnd[r] = 0;
-                unsigned entry = (full_entry || face) ? 0xFFFFFFFFu : 0x80000001u;
-                if (has_pending) entry |= wl.pend[(size_t)tile * kThreads + r];  // candidates deferred by the previous visit
-                act[r] = w & entry;
+        {
+            // warp per row, lane = z (conflict-free whatever the row stride); eight rows' loads in flight at a time, lane i keeps the mask of
+            // row warp * 32 + i, then every lane writes its row's words
+            unsigned myw = 0;
+#pragma unroll
+            for (int i0 = 0; i0 < 32; i0 += 8) {
+                uint32_t v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int r = warp * 32 + i0 + k;
+                    v[k] = sk[sidx(r / TY, r % TY, lane)];
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int r = warp * 32 + i0 + k, x = r / TY;
+                    // slab mode: halo planes are copies of a neighbour GPU's cells — sources only
+                    const bool fixed = (g.fix_lo && gx0 + x == 0) || (g.fix_hi && gx0 + x == g.X - 1);
+                    const unsigned w = __ballot_sync(kFull, !fixed && v[k] != KEY_WALL);
+                    if (lane == i0 + k) myw = w;
+                }
             }
+            const int r = warp * 32 + lane, x = r / TY, y = r % TY;
+            const bool face = x == 0 || x == TX - 1 || y == 0 || y == TY - 1;
+            unsigned entry = (full_entry || face) ? 0xFFFFFFFFu : 0x80000001u;
+            if (has_pending) entry |= __ldcg(&wl.pend[(size_t)tile * kThreads + r]);  // candidates deferred by the previous visit
+            nw[r] = myw;
+            chg[r] = 0;
+            pnd[r] = 0;
+            act[r] = myw & entry;
         }
         __syncthreads();
 
+        VF_TICK(1);
         // ---- relaxation steps in shared memory, pull style, one barrier per step.  Thread t owns row (lane * 8 + warp): rows are
         //      dealt round-robin so that a flat front spreads over all warps.  Step 0 takes the entry candidates; step k > 0 takes
         //      the cells next to the cells lowered in step k-1 (wavefront masks shifted by +-1 in z | masks of the neighbouring
@@ -435,6 +472,9 @@ __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __re
                 if (overflow) atomicOr(&wl.stats[ST_ERROR], 1u);
                 if (!__syncthreads_or(any)) {
                     if (t == 0) atomicAdd(&wl.stats[ST_STEPS], (uint32_t)it + 1), atomicMax(&wl.stats[ST_MAXSTEPS], (uint32_t)it + 1);
+#ifdef VF_FLOOD_TIMING
+                    if (t == 0) atomicAdd(&g_flood_cycles[5], (unsigned long long)it + 1), atomicAdd(&g_flood_cycles[4], 1ull);
+#endif
                     break;
                 }
             }
@@ -442,6 +482,7 @@ __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __re
             if (lane == 0 && dmin != kNoLevel) atomicMin(&misc[4], dmin);
         }
         __syncthreads();
+        VF_TICK(2);
         {
             // deferred candidates: remember them, come back next round, and tell the next round where its window starts
             const uint32_t tile_dmin = misc[4];
@@ -457,18 +498,32 @@ __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __re
 
         // ---- write back the rows that changed (warp per row: one 128-byte line), wake the neighbours that saw them change
         unsigned nchanged = 0;
-        for (int r = warp * 32; r < warp * 32 + 32; ++r) {
-            if (chg[r]) {
+        {
+            const unsigned mine = chg[warp * 32 + lane];
+            nchanged = __popc(mine);
+            for (unsigned rows = __ballot_sync(kFull, mine != 0); rows; rows &= rows - 1) {  // only the rows that changed
+                const int r = warp * 32 + __ffs(rows) - 1;
                 const int x = r / TY, y = r % TY, gz = gz0 + lane;
                 if (gz < g.Z && gx0 + x < g.X && gy0 + y < g.Y) keys[((size_t)(gx0 + x) * g.Y + gy0 + y) * g.Z + gz] = sk[sidx(x, y, lane)];
-                nchanged += __popc(chg[r]);
             }
+            nchanged = __reduce_add_sync(kFull, nchanged);
         }
         if (lane == 0 && nchanged) atomicAdd(&wl.stats[ST_CHANGED], nchanged);
         if (t == 0) atomicAdd(&wl.stats[ST_VISITS], 1u);
         enqueue_neighbours<NNEIGH>(g, wl, tx, ty, tz, chg[t], &misc[3], round + 1);
         __syncthreads();
+        VF_TICK(3);
     }
+    if (!COOP) return;
+    // ---- next round: everybody's key stores, list appends and pending masks are visible (also to the copy engine's reads) after the barrier
+    __threadfence();
+    asm volatile("fence.proxy.async;" ::: "memory");
+    cooperative_groups::this_grid().sync();
+    if (__ldcg(&wl.count[(round + 1) % 3]) == 0 || round + 1 >= last_round) {
+        if (blockIdx.x == 0 && t == 0) wl.stats[kRoundWord] = round + 1;  // the id the next phase starts with
+        return;
+    }
+  }
 }
 
 // keys -> label words.  order -> seeds[order].w & mask; unreached non-empty cells stay FREE (never claimed in the reference).
@@ -506,6 +561,7 @@ struct Job {
     uint32_t* h_mail;     // pinned mailbox
     int blocks_stream;    // grid for streaming kernels
     int blocks_tiles;     // grid for tile kernels
+    bool round_on_device = false;  // a cooperative phase advanced the round id on the device; read_stats brings it back
 };
 
 vf_status job_begin(vf_grid* grid, Job& j)
@@ -561,9 +617,14 @@ vf_status run_rounds(Job& j, LaunchF launch)
 
 vf_status read_stats(Job& j, uint32_t out[8])
 {
-    VF_CUDA(cudaMemcpyAsync(j.h_mail, j.wl.stats, 32, cudaMemcpyDeviceToHost, j.c->stream));
-    VF_CUDA(cudaStreamSynchronize(j.c->stream));
+    VF_CUDA(cudaMemcpyAsync(j.h_mail, j.wl.stats, 64, cudaMemcpyDeviceToHost, j.c->stream));
+    VF_CUDA(vf_sync(j.c));
     for (int i = 0; i < 8; ++i) out[i] = j.h_mail[i];
+    if (j.round_on_device) {  // a cooperative phase ran: the id of the next round is in the header
+        VF_REQUIRE(j.h_mail[kRoundWord] < j.round + 100000, VF_ERR_CAPACITY, "tile worklist did not drain");
+        j.round = j.h_mail[kRoundWord];
+        j.round_on_device = false;
+    }
     return VF_OK;
 }
 
@@ -592,11 +653,28 @@ bool make_keys_map(CUtensorMap* map, const uint32_t* keys, const TileGeom& g)
 template <int NNEIGH>
 vf_status flood_phase(Job& j, uint32_t* keys)
 {
+    CUtensorMap map;
+    int use_tma = make_keys_map(&map, keys, j.g) ? 1 : 0;  // otherwise: per-row cp.async staging
+    vf_ctx* c = j.c;
+    if (use_tma && c->flood_coop) {
+        // one cooperative launch for the whole phase; the grid must be resident at once
+        auto kern = flood_round_kernel<NNEIGH, true>;
+        VF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        int per_sm = 0;
+        VF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, kSmemBytes));
+        if (per_sm >= 1) {
+            int blocks = c->num_sms * std::min(per_sm, c->flood_coop);
+            uint32_t round = j.round, last_round = j.round + 100000;  // the guard of run_rounds
+            void* args[] = { &keys, &map, &use_tma, &j.g, &j.wl, &round, &last_round };
+            VF_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)blocks), dim3(kThreads), args, kSmemBytes, c->stream));
+            ++c->launches;
+            j.round_on_device = true;
+            return VF_OK;
+        }
+    }
     auto kern = flood_round_kernel<NNEIGH, false>;
     VF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    CUtensorMap map;
-    const int use_tma = make_keys_map(&map, keys, j.g) ? 1 : 0;  // otherwise: per-row cp.async staging
-    return run_rounds(j, [&](uint32_t r) { kern<<<j.blocks_tiles, kThreads, kSmemBytes, j.c->stream>>>(keys, map, use_tma, j.g, j.wl, r); });
+    return run_rounds(j, [&](uint32_t r) { kern<<<j.blocks_tiles, kThreads, kSmemBytes, j.c->stream>>>(keys, map, use_tma, j.g, j.wl, r, 0u); });
 }
 
 }  // namespace
@@ -859,3 +937,15 @@ extern "C" vf_status vf_flood_slab_finalize(vf_slab* s, const uint32_t* seeds_gl
 }
 
 extern "C" void vf_flood_slab_destroy(vf_slab* s) { delete s; }
+
+#ifdef VF_FLOOD_TIMING
+extern "C" void vf_debug_flood_cycles(unsigned long long* out, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_flood_cycles, sizeof(g_flood_cycles));
+    if (reset) {
+        unsigned long long z[8] = { 0 };
+        cudaMemcpyToSymbol(g_flood_cycles, z, sizeof(z));
+    }
+}
+#endif
