@@ -434,6 +434,12 @@ def run_cuda(args):
                         "host_cpu_s_per_model_rank0": LAST_BATCH_INFO.get("host_cpu_s_per_model"),
                         "workload": f"cfg4-batch: {bm} synthetic vessels (pool of {npool} shapes) x 10 fragmentations at 256-max, FLOOD CHEBYSHEV, nf 2..10, "
                                     "2*nf extra seeds; full-size run: bench.py --workload batch --meshes 1024"}
+    if world >= 2 and not args.no_slab:
+        # BASELINE config 5 on the driver's record: the slab-partitioned flood over all ranks — 2048^3 on 8 GPUs, 1024^3 on 2 or 4 (the key field of a
+        # slab is 4 B per cell: 2048^3 / 8 ranks = 4.3 GiB of keys + 2.1 GiB of labels per GPU)
+        torch.cuda.empty_cache()
+        sn = args.slab_size or (2048 if world >= 8 else 1024)
+        out["slab"] = slab_measure(rank, local_rank, world, dist, sn, 256, 3, 1, native=True)
     if rank == 0 and not args.no_cpu_baseline:
         cn = args.cpu_size or n
         out["cpu_baseline"], want = cpu_baseline(cn, stages_run)
@@ -652,35 +658,38 @@ def _dist_setup():
     return rank, local_rank, world, dist
 
 
-def run_slab(args):
-    """BASELINE config 5: one n^3 analytic solid, FLOOD MANHATTAN, 256 seeds (15-bit ids), x-slabs over the ranks with key-plane
-    exchange over NCCL.  Labels are bit-exact against the single-address-space oracle at small n (tests/test_slab_gpu.py)."""
+def slab_measure(rank, local_rank, world, dist, n, nseeds, steps, warmup, native=True):
+    """BASELINE config 5: one n^3 analytic solid, FLOOD MANHATTAN, `nseeds` seeds (15-bit ids), x-slabs over the ranks with key-plane exchange
+    over NCCL.  native: the exchange loop runs inside libvoxfrag (C++: grouped ncclSend / ncclRecv + ncclAllReduce on the context's stream,
+    vf_flood_slab_run); otherwise the Python loop over torch.distributed.  Labels are bit-exact against the single-address-space oracle
+    (tests/test_slab_gpu.py, tests/test_fullsize_gpu.py).  Timed: key-field init + seeds, exchange loop, finalize; wall clock, max over ranks."""
     import torch
 
     import voxelfragmentml_b200 as vf
     from voxelfragmentml_b200 import slab, synth
 
-    rank, local_rank, world, dist = _dist_setup()
     ctx = vf.Context(local_rank)
-    n = args.size
     params = synth.solid_vessel_params(0)
-    seeds = synth.solid_vessel_seeds(n, args.seeds, params, 80)
+    seeds = synth.solid_vessel_seeds(n, nseeds, params, 80)
     x0, x1 = slab.partition(n, world)[rank]
     lib = vf._capi.load()
+    comm = slab.nccl_comm(ctx, rank, world, dist) if (native and world > 1) else None
 
     def fill(grid):
         vf._capi.check(lib.vf_synth_solid_vessel(grid._h, x0 - 1, n, *params))
 
     times, iters, moved, maxd = [], 0, 0, 0
-    for it in range(args.warmup + args.steps):
+    for it in range(warmup + steps):
         s = slab.GpuSlab(ctx, fill, seeds, x0, x1, n, 1, shape=(x1 - x0 + 2, n, n), defer_init=True)  # allocation + synthetic input
         ctx.synchronize()
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        s.start()  # timed: key-field init + seeds, exchange loop, finalize
-        if world > 1:
+        s.start()
+        if native:
+            iters, moved = s.run_native(comm, rank, world)
+        elif world > 1:
             iters, moved = slab.run_distributed(s, rank, world, dist)
         else:
             iters, moved = slab.run_local([s])
@@ -689,21 +698,37 @@ def run_slab(args):
         dt = time.perf_counter() - t0
         maxd = s.max_dist
         s.close()
-        if it >= args.warmup:
+        if it >= warmup:
             times.append(dt)
+    if comm is not None:
+        lib.vf_nccl_comm_destroy(comm)
+    ctx.close()
     total = float(sum(times))
     if dist is not None:
         tt = torch.tensor([total, float(moved), float(maxd)], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total, moved, maxd = float(tt[0]), float(tt[1]), float(tt[2])
+    N = n**3
+    ms = total / steps * 1e3
+    peak, _ = load_peak()
+    return {"metric": "Gvoxels/s flood-fragmented, one grid over N GPUs", "value": N * steps / total / 1e9, "unit": "Gvoxels/s", "n_gpus": world,
+            "ms_per_step": ms, "scaling": "strong", "grid": [n, n, n], "seeds": nseeds,
+            "workload": f"cfg5-slab: {n}^3 analytic solid vessel, FLOOD MANHATTAN, {nseeds} seeds (15-bit ids), {world} x-slabs, "
+                        + ("C++ exchange loop over NCCL inside libvoxfrag (vf_flood_slab_run)" if native else "Python exchange loop over torch.distributed"),
+            "exchange_iterations": iters, "halo_bytes_per_rank": moved, "max_geodesic_distance": maxd,
+            # F2's algorithmic bytes: read every label once, write every label once, against the aggregate HBM roofline of the N GPUs
+            "roofline_frac_aggregate": 4.0 * N / (ms * 1e-3) / 1e9 / (peak * world)}
+
+
+def run_slab(args):
+    rank, local_rank, world, dist = _dist_setup()
+    blk = slab_measure(rank, local_rank, world, dist, args.size, args.seeds, args.steps, args.warmup, native=not args.python_exchange)
     if rank == 0:
         emit_json(json.dumps({
-            "metric": "Gvoxels/s flood-fragmented, one grid over N GPUs", "value": n**3 * args.steps / total / 1e9, "unit": "Gvoxels/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "u32 keys (dist<<15|order)", "data": "synthetic",
-            "config": {"workload": f"cfg5-slab: {n}^3 analytic solid vessel, FLOOD MANHATTAN, {args.seeds} seeds, {world} x-slabs, NCCL key-plane exchange",
-                       "exchange_iterations": iters, "halo_bytes_per_rank": moved, "max_geodesic_distance": maxd},
-        }))
+            "metric": blk["metric"], "value": blk["value"], "unit": blk["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": blk["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 keys (dist<<15|order)",
+            "data": "synthetic", "config": {k: blk[k] for k in ("workload", "grid", "seeds", "exchange_iterations", "halo_bytes_per_rank", "max_geodesic_distance")},
+            "roofline_frac_aggregate": blk["roofline_frac_aggregate"]}))
     if dist is not None:
         dist.destroy_process_group()
 
@@ -911,6 +936,9 @@ def main():
     ap.add_argument("--out", default="", help="dataset workload: parent directory of the (temporary) output folder")
     ap.add_argument("--no-export", action="store_true", help="dataset workload: no grid files (the batch loop through the native driver, metadata files only)")
     ap.add_argument("--seeds", type=int, default=256, help="slab workload: number of seeds")
+    ap.add_argument("--python-exchange", action="store_true", help="slab workload: the Python exchange loop over torch.distributed instead of the C++ loop over NCCL")
+    ap.add_argument("--slab-size", type=int, default=0, help="default workload at N >= 2: edge of the cfg5 grid (default 2048 at 8 GPUs, else 1024)")
+    ap.add_argument("--no-slab", action="store_true", help="default workload at N >= 2: skip the cfg5 slab measurement reported under \"slab\"")
     ap.add_argument("--meshes", type=int, default=64, help="batch workload: number of meshes")
     ap.add_argument("--jobs", type=int, default=0, help="batch workload: concurrent contexts (streams + host threads) per GPU; 0 = 16, or 8 with 8..15 host cores per rank")
     ap.add_argument("--blocking-sync", default="auto", choices=["auto", "on", "off"],

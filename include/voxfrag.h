@@ -209,6 +209,15 @@ void*     vf_flood_slab_boundary_ptr(vf_slab* s, int side /* 0 = towards lower x
 vf_status vf_flood_slab_ingest(vf_slab* s, int side, const uint32_t* plane_dev, uint64_t* changed_cells);
 vf_status vf_flood_slab_finalize(vf_slab* s, const uint32_t* seeds_global, uint32_t nseeds_total, uint32_t* max_dist);
 void      vf_flood_slab_destroy(vf_slab* s);
+/* The whole exchange loop on the host side of this library, over NCCL: { relax; grouped ncclSend / ncclRecv of the owned boundary planes
+ * with ranks rank-1 / rank+1 on the context's stream; ingest; ncclAllReduce of the change count } until no rank changed a cell — one
+ * host wait per iteration, change counters and round id stay on the device.  NCCL is taken from the libnccl.so.2 already in the process
+ * (no link-time dependency).  A host application creates the communicator itself (vf_nccl_unique_id on one rank, the 128 bytes carried to
+ * the others by whatever it uses for bootstrap, vf_nccl_comm_create on each) or passes its own ncclComm_t.  world == 1: comm may be NULL. */
+vf_status vf_nccl_unique_id(void* id128);
+vf_status vf_nccl_comm_create(vf_ctx* ctx, const void* id128, int world, int rank, void** comm_out);
+void      vf_nccl_comm_destroy(void* comm);
+vf_status vf_flood_slab_run(vf_slab* s, void* nccl_comm, int rank, int world, uint32_t* iterations, uint64_t* halo_bytes);
 
 /* ------------------------------------------------------------------ C1..C4: cleanup */
 vf_status vf_remove_isolated_regions(vf_grid* g, const uint32_t* seeds, uint32_t nseeds); /* NaiveFracturer::removeIsolatedRegionsCPU semantics, NaiveFracturer.cpp:111-150 */

@@ -64,3 +64,35 @@ def test_solid_vessel_256_seeds(ctx, orc):
     want, _ = orc.flood(g.copy(), seeds, 1, id_bits=15)
     got, iters, moved = _run(ctx, g, seeds, 1, 8)
     assert np.array_equal(got, want) and got.max() == 257
+
+
+def test_native_loop_on_one_rank_equals_the_single_context_flood(ctx, orc, vessel_grid):
+    """vf_flood_slab_run with world == 1 (no communicator): one slab = the whole grid"""
+    from voxelfragmentml_b200 import slab
+
+    seeds, _ = orc.seed_uniform(orc.Rng(80), vessel_grid, 16)
+    for dfunc in (1, 2):
+        want, _ = orc.flood(vessel_grid.copy(), seeds, dfunc, id_bits=15)
+        X = vessel_grid.shape[0]
+        s = slab.GpuSlab(ctx, slab.slab_with_halo(vessel_grid, 0, X), seeds, 0, X, X, dfunc)
+        iters, moved = s.run_native(None, 0, 1)
+        assert np.array_equal(s.finalize(), want) and iters >= 1 and moved == 0
+        s.close()
+
+
+def test_native_exchange_loop_over_nccl():
+    """the C++ exchange loop over NCCL, one rank per GPU (needs >= 2 GPUs: `gpurun --gpus 2`); tests/slab_native_worker.py does the checking"""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least two GPUs")
+    world = 8 if ngpu >= 8 else (4 if ngpu >= 4 else 2)
+    here = os.path.dirname(os.path.abspath(__file__))
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port", "29641",
+                        os.path.join(here, "slab_native_worker.py")], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "SLAB_NATIVE_OK" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]

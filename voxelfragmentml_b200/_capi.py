@@ -107,6 +107,10 @@ SIGNATURES = {
     "vf_flood_slab_ingest": (C.c_int, [_vp, C.c_int, _vp, C.POINTER(C.c_uint64)]),
     "vf_flood_slab_finalize": (C.c_int, [_vp, _vp, _u32, C.POINTER(_u32)]),
     "vf_flood_slab_destroy": (None, [_vp]),
+    "vf_nccl_unique_id": (C.c_int, [_vp]),
+    "vf_nccl_comm_create": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "vf_nccl_comm_destroy": (None, [_vp]),
+    "vf_flood_slab_run": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(_u32), C.POINTER(C.c_uint64)]),
     "vf_remove_isolated_regions": (C.c_int, [_vp, _vp, _u32]),
     "vf_detect_boundaries": (C.c_int, [_vp, C.c_int]),
     "vf_erode": (C.c_int, [_vp, C.c_int, _u32, _u32, C.c_float, C.c_float, _vp, _u32, C.c_int]),

@@ -29,6 +29,7 @@
 #include <cstring>
 #include <vector>
 
+#include "nccl_dyn.h"
 #include "tiles.cuh"
 
 using namespace vft;
@@ -805,13 +806,16 @@ struct vf_slab {
     Job job;
     int nneigh;
     uint32_t* d_changed;  // ingest counter
+    uint32_t* recv = nullptr;            // vf_flood_slab_run: two receive planes + the packed change flags (owned, freed by destroy)
+    unsigned long long* d_flags = nullptr;
 };
 
 namespace {
 
 __global__ void __launch_bounds__(256) slab_ingest_kernel(uint32_t* __restrict__ halo, const uint32_t* __restrict__ recv, TileGeom g, Worklist wl, int tx,
-                                                          uint32_t round, uint32_t* __restrict__ changed)
+                                                          uint32_t round, uint32_t* __restrict__ changed, int round_on_device)
 {
+    if (round_on_device) round = __ldcg(wl.stats + kRoundWord);  // a cooperative phase left the id of the next round in the header
     const size_t n = (size_t)g.Y * g.Z;
     unsigned c = 0;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -905,7 +909,7 @@ extern "C" vf_status vf_flood_slab_ingest(vf_slab* s, int side, const uint32_t* 
     const size_t plane = (size_t)s->grid->Y * s->grid->Z;
     uint32_t* halo = side == 0 ? s->keys : s->keys + plane * (s->grid->X - 1);
     VF_CUDA(cudaMemsetAsync(s->d_changed, 0, 4, c->stream));
-    slab_ingest_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>(halo, plane_dev, s->job.g, s->job.wl, side == 0 ? 0 : s->job.g.ntx - 1, s->job.round, s->d_changed);
+    slab_ingest_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>(halo, plane_dev, s->job.g, s->job.wl, side == 0 ? 0 : s->job.g.ntx - 1, s->job.round, s->d_changed, 0);
     VF_LAUNCHED(c);
     VF_CUDA(cudaMemcpyAsync(s->job.h_mail, s->d_changed, 4, cudaMemcpyDeviceToHost, c->stream));
     VF_CUDA(vf_sync(c));
@@ -936,7 +940,126 @@ extern "C" vf_status vf_flood_slab_finalize(vf_slab* s, const uint32_t* seeds_gl
     return VF_OK;
 }
 
-extern "C" void vf_flood_slab_destroy(vf_slab* s) { delete s; }
+extern "C" void vf_flood_slab_destroy(vf_slab* s)
+{
+    if (!s) return;
+    if (s->recv) {
+        cudaSetDevice(s->grid->ctx->device);
+        cudaFree(s->recv);
+    }
+    delete s;
+}
+
+// ------------------------------------------------------------------------------------------------ the exchange loop in C++ over NCCL
+namespace {
+__global__ void slab_pack_flags_kernel(const uint32_t* __restrict__ stats, const uint32_t* __restrict__ ingested, unsigned long long* __restrict__ flags)
+{
+    flags[0] = (unsigned long long)stats[ST_CHANGED] + *ingested;  // cells this rank lowered in this iteration (relaxation + ingested halo cells)
+    flags[1] = stats[ST_ERROR];
+}
+}  // namespace
+
+#define VF_NCCL(call)                                                                                                            \
+    do {                                                                                                                         \
+        ncclResult_t r__ = (call);                                                                                               \
+        if (r__ != ncclSuccess) return vf_set_error(VF_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, nccl->GetErrorString(r__)); \
+    } while (0)
+
+extern "C" vf_status vf_nccl_unique_id(void* id128)
+{
+    const VfNcclApi* nccl = vf_nccl_api();
+    VF_REQUIRE(nccl != nullptr, VF_ERR_UNSUPPORTED, "libnccl.so.2 is not available in this process");
+    VF_REQUIRE(id128 != nullptr, VF_ERR_INVALID_ARGUMENT, "null id buffer");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    VF_NCCL(nccl->GetUniqueId((ncclUniqueId*)id128));
+    return VF_OK;
+}
+
+extern "C" vf_status vf_nccl_comm_create(vf_ctx* ctx, const void* id128, int world, int rank, void** comm_out)
+{
+    const VfNcclApi* nccl = vf_nccl_api();
+    VF_REQUIRE(nccl != nullptr, VF_ERR_UNSUPPORTED, "libnccl.so.2 is not available in this process");
+    VF_REQUIRE(ctx && id128 && comm_out && world >= 1 && rank >= 0 && rank < world, VF_ERR_INVALID_ARGUMENT, "bad communicator arguments");
+    VF_TRY(vf_enter(ctx));
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    ncclComm_t comm = nullptr;
+    VF_NCCL(nccl->CommInitRank(&comm, world, id, rank));
+    *comm_out = comm;
+    return VF_OK;
+}
+
+extern "C" void vf_nccl_comm_destroy(void* comm)
+{
+    const VfNcclApi* nccl = vf_nccl_api();
+    if (nccl && comm) nccl->CommDestroy((ncclComm_t)comm);
+}
+
+// { relax to the local fixed point; send the two owned boundary planes, receive the neighbours' (grouped ncclSend / ncclRecv on the
+// context's stream); ingest; all-reduce the change count } until no rank changed a cell.  Everything between two iterations' single host
+// wait is enqueued on the stream: the relaxation is one cooperative launch, the round id and the change counters stay on the device.
+// comm == NULL with world == 1 runs the loop without NCCL (one slab = the whole grid).
+extern "C" vf_status vf_flood_slab_run(vf_slab* s, void* comm_, int rank, int world, uint32_t* iterations, uint64_t* halo_bytes)
+{
+    VF_REQUIRE(s != nullptr && world >= 1 && rank >= 0 && rank < world, VF_ERR_INVALID_ARGUMENT, "bad slab run arguments");
+    const VfNcclApi* nccl = world > 1 ? vf_nccl_api() : nullptr;
+    VF_REQUIRE(world == 1 || (nccl != nullptr && comm_ != nullptr), VF_ERR_UNSUPPORTED, "a multi-rank slab run needs NCCL and a communicator");
+    ncclComm_t comm = (ncclComm_t)comm_;
+    vf_ctx* c = s->grid->ctx;
+    VF_TRY(vf_enter(c));
+    Job& j = s->job;
+    const size_t plane = (size_t)s->grid->Y * s->grid->Z;
+    if (!s->recv) {
+        VF_CUDA(cudaMalloc(&s->recv, 2 * plane * 4 + 256));
+        s->d_flags = (unsigned long long*)(s->recv + 2 * plane);
+    }
+    const bool lo = rank > 0, hi = rank + 1 < world;  // neighbours; must agree with has_lo / has_hi of vf_flood_slab_init
+    uint32_t iters = 0;
+    uint64_t moved = 0;
+    for (;;) {
+        ++iters;
+        VF_CUDA(cudaMemsetAsync(j.wl.stats + ST_CHANGED, 0, 4, c->stream));
+        VF_CUDA(cudaMemsetAsync(s->d_changed, 0, 4, c->stream));
+        VF_TRY(s->nneigh == 6 ? flood_phase<6>(j, s->keys) : flood_phase<26>(j, s->keys));
+        if (world > 1) {
+            VF_NCCL(nccl->GroupStart());
+            if (lo) {
+                VF_NCCL(nccl->Send(s->keys + plane, plane, ncclUint32, rank - 1, comm, c->stream));
+                VF_NCCL(nccl->Recv(s->recv, plane, ncclUint32, rank - 1, comm, c->stream));
+            }
+            if (hi) {
+                VF_NCCL(nccl->Send(s->keys + plane * (s->grid->X - 2), plane, ncclUint32, rank + 1, comm, c->stream));
+                VF_NCCL(nccl->Recv(s->recv + plane, plane, ncclUint32, rank + 1, comm, c->stream));
+            }
+            VF_NCCL(nccl->GroupEnd());
+            const int on_dev = j.round_on_device ? 1 : 0;
+            if (lo) {
+                slab_ingest_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>(s->keys, s->recv, j.g, j.wl, 0, j.round, s->d_changed, on_dev);
+                VF_LAUNCHED(c);
+                moved += plane * 4;
+            }
+            if (hi) {
+                slab_ingest_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>(s->keys + plane * (s->grid->X - 1), s->recv + plane, j.g, j.wl, j.g.ntx - 1, j.round,
+                                                                          s->d_changed, on_dev);
+                VF_LAUNCHED(c);
+                moved += plane * 4;
+            }
+        }
+        slab_pack_flags_kernel<<<1, 1, 0, c->stream>>>(j.wl.stats, s->d_changed, s->d_flags);
+        VF_LAUNCHED(c);
+        if (world > 1) VF_NCCL(nccl->AllReduce(s->d_flags, s->d_flags, 2, ncclUint64, ncclSum, comm, c->stream));
+        unsigned long long* h_flags = (unsigned long long*)((char*)j.h_mail + 256);
+        VF_CUDA(cudaMemcpyAsync(h_flags, s->d_flags, 16, cudaMemcpyDeviceToHost, c->stream));
+        uint32_t hs[8];
+        VF_TRY(read_stats(j, hs));  // the iteration's one host wait; also brings the round id back
+        VF_REQUIRE(h_flags[1] == 0, VF_ERR_CAPACITY, "flood: geodesic distance exceeds the 17-bit key field");
+        if (h_flags[0] == 0) break;
+        VF_REQUIRE(iters < 100000, VF_ERR_CAPACITY, "slab exchange did not converge");
+    }
+    if (iterations) *iterations = iters;
+    if (halo_bytes) *halo_bytes = moved;
+    return VF_OK;
+}
 
 #ifdef VF_FLOOD_TIMING
 extern "C" void vf_debug_flood_cycles(unsigned long long* out, int reset)

@@ -96,6 +96,12 @@ class GpuSlab:
         check(self.ctx._lib.vf_flood_slab_ingest(self._h, side, C.c_void_p(plane.data_ptr()), C.byref(n)))
         return int(n.value)
 
+    def run_native(self, comm, rank: int, world: int):
+        """the whole exchange loop inside libvoxfrag (C++ over NCCL, vf_flood_slab_run); comm from nccl_comm() below, None when world == 1"""
+        iters, moved = C.c_uint32(0), C.c_uint64(0)
+        check(self.ctx._lib.vf_flood_slab_run(self._h, comm, rank, world, C.byref(iters), C.byref(moved)))
+        return int(iters.value), int(moved.value)
+
     def finalize(self, download: bool = True):
         md = C.c_uint32(0)
         check(self.ctx._lib.vf_flood_slab_finalize(self._h, ptr(self.seeds_global), len(self.seeds_global), C.byref(md)))
@@ -107,6 +113,24 @@ class GpuSlab:
             self.ctx._lib.vf_flood_slab_destroy(self._h)
             self._h = None
             self.grid.close()
+
+
+def nccl_comm(ctx, rank: int, world: int, dist):
+    """An NCCL communicator owned by libvoxfrag for the native exchange loop: rank 0 draws the unique id (vf_nccl_unique_id), the 128 bytes
+    travel through torch.distributed (any backend), every rank joins (vf_nccl_comm_create).  Free with ctx._lib.vf_nccl_comm_destroy."""
+    import torch
+
+    buf = (C.c_ubyte * 128)()
+    if rank == 0:
+        check(ctx._lib.vf_nccl_unique_id(buf))
+    t = torch.tensor(list(buf), dtype=torch.uint8)
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    dist.broadcast(t, 0)
+    raw = bytes(t.cpu().tolist())
+    comm = C.c_void_p()
+    check(ctx._lib.vf_nccl_comm_create(ctx._h, raw, world, rank, C.byref(comm)))
+    return comm
 
 
 def run_local(slabs):
