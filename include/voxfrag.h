@@ -154,6 +154,10 @@ void*     vf_grid_device_ptr(vf_grid* g);                                /* Regu
 vf_status vf_grid_upload(vf_grid* g, const uint16_t* host);              /* updateSSBO, :511-514 */
 vf_status vf_grid_download(vf_grid* g, uint16_t* host);                  /* updateGrid, :505-509 (synchronises) */
 vf_status vf_grid_upload_async(vf_grid* g, const uint16_t* pinned_host);
+/* Occupancy as ONE BIT per cell instead of a 16-bit word (new: 16x fewer bytes over PCIe for a grid that only holds EMPTY / FREE, which is
+ * what every fragmentation starts from after RegularGrid::fill + homogenize): bit (i & 7) of byte i >> 3 is cell i of the linear x-major
+ * order; set -> VOXEL_FREE, clear -> VOXEL_EMPTY.  Enqueued on the context's stream like vf_grid_upload_async (pinned memory: asynchronous). */
+vf_status vf_grid_upload_bits(vf_grid* g, const uint8_t* host_bits);
 vf_status vf_grid_download_async(vf_grid* g, uint16_t* pinned_host);
 vf_status vf_grid_fill(vf_grid* g, uint16_t value);
 /* interactive dims rule of CADScene::allocateMeshGrid, CADScene.cpp:545-556 (host arithmetic only) */
@@ -303,7 +307,9 @@ typedef struct vf_dataset_stats {
 void      vf_procedure_default(vf_procedure* p);                               /* FragmentationProcedure::FragmentationProcedure() */
 void      vf_dataset_dims_rule(const float aabb_min[3], const float aabb_max[3], int32_t voxelPerMetricUnit, int32_t clampVoxelMetricUnit,
                                uint32_t dims_out[3]);                        /* CADScene.cpp:262-273 */
-int32_t   vf_dataset_iterations(const vf_procedure* p, int32_t numFragments);  /* glm::mix of the iteration interval, CADScene.cpp:304-306 */
+/* glm::mix of the iteration interval, CADScene.cpp:304-306.  A degenerate fragment interval (x == y) makes the reference divide by zero;
+ * this function then returns iterationInterval.x (documented divergence: the reference's result is undefined there). */
+int32_t   vf_dataset_iterations(const vf_procedure* p, int32_t numFragments);
 /* the body of generateDataset's model loop (:240-466) for one already-loaded model: dims rule, setAABB + fill, starting-grid export,
  * every (numFragments, iteration) fragmentation with its grid export and metadata rows, exportMetadata.  `g` must have capacity for
  * the dims rule's result (allocate (clamp+3) x clamp x (clamp+3)).  The context's RNG stream is continued, not re-seeded. */

@@ -48,7 +48,9 @@ def test_cuda_arm_line_small():
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] > 0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and "traffic" in r
     e = d["e2e"]
-    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 2 * 128 ** 3 and e["d2h_bytes_per_step"] >= 2 * 128 ** 3
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 128 ** 3 // 8 and 12 < e["d2h_bytes_per_step"] < 2 * 128 ** 3 and e["rle_stream_equals_grid"] is True
+    f = e["full_grid"]
+    assert f["value"] > 0 and f["h2d_bytes_per_step"] == 2 * 128 ** 3 and f["d2h_bytes_per_step"] >= 2 * 128 ** 3
     assert d["gpu_launches"] > 0 and {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["batch"]["unit"] == "models/s" and d["batch"]["value"] > 0

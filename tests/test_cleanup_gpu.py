@@ -344,3 +344,17 @@ def test_connected_to_seed_with_whole_tile_regions(ctx, orc):
         vf.NaiveFracturer.removeIsolatedRegions(g, seeds)
         assert np.array_equal(g.updateGrid(), orc.remove_isolated_regions_cpu(g0.copy(), seeds)), dims
         g.close()
+
+
+@pytest.mark.parametrize("shape", [(128, 110, 128), (17, 19, 35), (9, 5, 13), (40, 36, 64)])
+def test_upload_bits_expands_one_bit_per_cell(ctx, orc, vessel_grid, shape):
+    """vf_grid_upload_bits: bit (i & 7) of byte i >> 3 is cell i; set -> FREE, clear -> EMPTY (cell counts that are not multiples of 8 included)"""
+    import voxelfragmentml_b200 as vf
+
+    occ = vessel_grid if shape == vessel_grid.shape else random_blob_grid(shape, 3, fill=0.5, smooth=0)
+    g = vf.RegularGrid(ctx, shape)
+    g.fillValue(7)
+    bits = np.packbits((occ.reshape(-1) != 0).astype(np.uint8), bitorder="little")
+    g.upload_bits(bits)
+    assert np.array_equal(g.updateGrid(), (occ != 0).astype(np.uint16))
+    g.close()

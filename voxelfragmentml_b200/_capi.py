@@ -91,6 +91,7 @@ SIGNATURES = {
     "vf_grid_upload": (C.c_int, [_vp, _vp]),
     "vf_grid_download": (C.c_int, [_vp, _vp]),
     "vf_grid_upload_async": (C.c_int, [_vp, _vp]),
+    "vf_grid_upload_bits": (C.c_int, [_vp, _vp]),
     "vf_grid_download_async": (C.c_int, [_vp, _vp]),
     "vf_grid_fill": (C.c_int, [_vp, C.c_uint16]),
     "vf_dims_rule": (None, [_vp, _vp, _u32, _vp]),

@@ -238,6 +238,10 @@ class RegularGrid:
     def upload_async(self, pinned_host):
         check(self._lib.vf_grid_upload_async(self._h, ptr(pinned_host)))
 
+    def upload_bits(self, host_bits):
+        """occupancy as one bit per cell (np.packbits(..., bitorder="little") of the linear grid != 0): set -> FREE, clear -> EMPTY; async on the stream"""
+        check(self._lib.vf_grid_upload_bits(self._h, ptr(host_bits)))
+
     def download_async(self, pinned_host):
         check(self._lib.vf_grid_download_async(self._h, ptr(pinned_host)))
 

@@ -87,22 +87,28 @@ static vf_status ctx_create(int device, void* stream, bool borrow, vf_ctx** out)
     vf_ctx* c = new (std::nothrow) vf_ctx();
     VF_REQUIRE(c != nullptr, VF_ERR_CAPACITY, "out of host memory");
     c->device = device;
+    // any failure below releases what has been created so far (vf_ctx_destroy copes with a half-built context)
+    auto fail = [&](cudaError_t e, const char* what) {
+        vf_ctx_destroy(c);
+        return vf_set_error(VF_ERR_CUDA, "vf_ctx_create: %s -> %s", what, cudaGetErrorString(e));
+    };
+    cudaError_t e;
     cudaDeviceProp prop;
-    VF_CUDA(cudaGetDeviceProperties(&prop, device));
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(e, "cudaGetDeviceProperties");
     c->num_sms = prop.multiProcessorCount;
     c->smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (borrow) {
         c->stream = (cudaStream_t)stream;
         c->own_stream = false;
     } else {
-        VF_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreateWithFlags");
         c->own_stream = true;
     }
-    VF_CUDA(cudaEventCreate(&c->ev_start));
-    VF_CUDA(cudaEventCreate(&c->ev_stop));
-    VF_CUDA(cudaEventCreateWithFlags(&c->ev_block, cudaEventBlockingSync | cudaEventDisableTiming));
+    if ((e = cudaEventCreate(&c->ev_start)) != cudaSuccess) return fail(e, "cudaEventCreate");
+    if ((e = cudaEventCreate(&c->ev_stop)) != cudaSuccess) return fail(e, "cudaEventCreate");
+    if ((e = cudaEventCreateWithFlags(&c->ev_block, cudaEventBlockingSync | cudaEventDisableTiming)) != cudaSuccess) return fail(e, "cudaEventCreateWithFlags");
     c->pinned_bytes = (1 << 17) + (VF_HISTOGRAM_BINS * 4 + 64);  // [0, 64K) seed staging, [64K, 128K) counter mailbox, then the histogram read-back
-    VF_CUDA(cudaMallocHost(&c->pinned, c->pinned_bytes));
+    if ((e = cudaMallocHost(&c->pinned, c->pinned_bytes)) != cudaSuccess) return fail(e, "cudaMallocHost");
     c->rng.seed(80);  // FractureParameters::_seed default (FractureParameters.h:116), applied at CADScene.cpp:36-37
     *out = c;
     return VF_OK;
@@ -146,15 +152,15 @@ extern "C" void vf_ctx_destroy(vf_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    vf_sync(c);
-    VfScratch* all[] = { &c->keys, &c->grid2, &c->tiles, &c->small, &c->noise, &c->mesh, &c->codec };
+    if (c->stream && c->ev_block) vf_sync(c);
+    VfScratch* all[] = { &c->keys, &c->grid2, &c->tiles, &c->small, &c->noise, &c->mesh, &c->codec, &c->bits };
     for (VfScratch* s : all)
         if (s->ptr) cudaFree(s->ptr);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->ev_start) cudaEventDestroy(c->ev_start);
     if (c->ev_stop) cudaEventDestroy(c->ev_stop);
     if (c->ev_block) cudaEventDestroy(c->ev_block);
-    if (c->own_stream) cudaStreamDestroy(c->stream);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 
@@ -339,6 +345,34 @@ extern "C" vf_status vf_grid_download_async(vf_grid* g, uint16_t* host)
     VF_TRY(vf_enter(g->ctx));
     return copy_in_pieces(host, g->d, g->n() * sizeof(uint16_t), cudaMemcpyDeviceToHost, g->ctx->stream);
 }
+// occupancy bit -> label word: one byte of the bitmap = one 128-bit store of eight cells
+__global__ void __launch_bounds__(256) expand_bits_kernel(const uint8_t* __restrict__ bits, uint16_t* __restrict__ grid, size_t n)
+{
+    const size_t nvec = n / 8;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t b = bits[i];
+        uint4 o;
+        o.x = (b & 1u) | (b & 2u) << 15, o.y = (b >> 2 & 1u) | (b >> 2 & 2u) << 15;
+        o.z = (b >> 4 & 1u) | (b >> 4 & 2u) << 15, o.w = (b >> 6 & 1u) | (b >> 6 & 2u) << 15;
+        *reinterpret_cast<uint4*>(grid + i * 8) = o;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < n % 8) grid[nvec * 8 + threadIdx.x] = (bits[nvec] >> threadIdx.x) & 1u;
+}
+
+extern "C" vf_status vf_grid_upload_bits(vf_grid* g, const uint8_t* host_bits)
+{
+    VF_REQUIRE(g && host_bits, VF_ERR_INVALID_ARGUMENT, "null argument");
+    vf_ctx* c = g->ctx;
+    VF_TRY(vf_enter(c));
+    const size_t n = g->n(), nbytes = (n + 7) / 8;
+    VF_REQUIRE(((uintptr_t)g->d & 15) == 0, VF_ERR_INVALID_ARGUMENT, "upload_bits needs a 16-byte aligned grid");
+    VF_TRY(vf_scratch_reserve(c, c->bits, nbytes + 16));
+    VF_TRY(copy_in_pieces(c->bits.ptr, host_bits, nbytes, cudaMemcpyHostToDevice, c->stream));
+    expand_bits_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>((const uint8_t*)c->bits.ptr, g->d, n);
+    VF_LAUNCHED(c);
+    return VF_OK;
+}
+
 extern "C" vf_status vf_grid_upload(vf_grid* g, const uint16_t* host)
 {
     VF_TRY(vf_grid_upload_async(g, host));

@@ -521,12 +521,16 @@ static vf_status rle_encode_device(vf_grid* g, std::vector<uint8_t>* grow, uint8
     const size_t sb = ((size_t)runs * 4 + 255) & ~(size_t)255, vb = ((size_t)runs * 2 + 255) & ~(size_t)255;
     if (c->codec.bytes < 2 * tb + 256 + sb + vb + bytes) {
         // the arena moves: keep the tile offsets (cheaper to copy than to recount)
-        VfScratch old = c->codec;
-        c->codec = VfScratch();
-        VF_TRY(vf_scratch_reserve(c, c->codec, 2 * tb + 256 + sb + vb + bytes + 256));
-        VF_CUDA(cudaMemcpyAsync(c->codec.ptr, old.ptr, 2 * tb + 256, cudaMemcpyDeviceToDevice, c->stream));
-        VF_CUDA(vf_sync(c));
-        VF_CUDA(cudaFree(old.ptr));
+        VfScratch bigger;  // allocated before the old arena is let go, so that no error path leaves device memory behind
+        VF_TRY(vf_scratch_reserve(c, bigger, 2 * tb + 256 + sb + vb + bytes + 256));
+        cudaError_t e = cudaMemcpyAsync(bigger.ptr, c->codec.ptr, 2 * tb + 256, cudaMemcpyDeviceToDevice, c->stream);
+        if (e == cudaSuccess) e = vf_sync(c);
+        if (e != cudaSuccess) {
+            cudaFree(bigger.ptr);
+            return vf_set_error(VF_ERR_CUDA, "%s:%d growing the codec arena -> %s", __FILE__, __LINE__, cudaGetErrorString(e));
+        }
+        cudaFree(c->codec.ptr);
+        c->codec = bigger;
         d_offsets = (uint32_t*)((char*)c->codec.ptr + tb);
     }
     uint32_t* d_starts = (uint32_t*)((char*)c->codec.ptr + 2 * tb + 256);

@@ -661,14 +661,6 @@ extern "C" vf_status vf_erode(vf_grid* g, int type, uint32_t size, uint32_t iter
     VF_TRY(vf_scratch_reserve(c, c->noise, (size_t)nnoise * 4 + mask.size() * 4 + 256));
     float* d_noise = (float*)c->noise.ptr;
     float* d_mask = d_noise + nnoise;
-    // The noise table travels on the stream: from pageable memory the call returns once the driver has staged it; a pinned
-    // table must stay valid until the context is synchronised (documented in voxfrag.h).
-    // A table identical to the one already on the device (compared against a host shadow) is not sent again.
-    if (c->noise_shadow.size() != nnoise || std::memcmp(c->noise_shadow.data(), noise, (size_t)nnoise * 4) != 0) {
-        c->noise_shadow.clear();
-        VF_CUDA(cudaMemcpyAsync(d_noise, noise, (size_t)nnoise * 4, cudaMemcpyHostToDevice, c->stream));
-        c->noise_shadow.assign(noise, noise + nnoise);
-    }
     if (size != 3)  // the 3^3 kernels take the mask as 27 bits; only the generic kernel reads the float mask (pageable: staged before return)
         VF_CUDA(cudaMemcpyAsync(d_mask, mask.data(), mask.size() * 4, cudaMemcpyHostToDevice, c->stream));
     ErodeArgs ea = {};
@@ -690,12 +682,23 @@ extern "C" vf_status vf_erode(vf_grid* g, int type, uint32_t size, uint32_t iter
     vf_grid view = *g;  // shallow view used to run passes on either buffer
     for (uint32_t it = 0; it < iterations; ++it) {
         view.d = a;
+        if (it == 0) {
+            VF_TRY(launch_stencil(&view, OP_DETECT, a, a, ea));  // only in the first iteration: see below
+            // The noise table is handled AFTER the detect pass is queued: comparing a 4 MB table with its shadow takes the host longer than a
+            // kernel launch, and the GPU would sit idle meanwhile.  The table travels on the stream: from pageable memory the call returns once the
+            // driver has staged it; a pinned table must stay valid until the context is synchronised (documented in voxfrag.h).  A table identical
+            // to the one already on the device (compared against a host shadow) is not sent again.
+            if (c->noise_shadow.size() != nnoise || std::memcmp(c->noise_shadow.data(), noise, (size_t)nnoise * 4) != 0) {
+                c->noise_shadow.clear();
+                VF_CUDA(cudaMemcpyAsync(d_noise, noise, (size_t)nnoise * 4, cudaMemcpyHostToDevice, c->stream));
+                c->noise_shadow.assign(noise, noise + nnoise);
+            }
+        }
         // RegularGrid.cpp:135 calls detectBoundaries(1) in every iteration; only the first call can change the grid.  The pass tags an
         // untagged labelled cell iff its clamped 3^3 box holds another label (> FREE, tag ignored) and never clears a tag; erosion copies
         // words, tags included, or writes EMPTY.  After the first pass every cell whose box holds another label is tagged, and a later
         // pass could only tag a cell whose box GAINED another label — no pass creates labels.  (Checked against the literal shader
         // transcription with and without the repeated passes: tests/test_oracle_literal_shaders.py.)
-        if (it == 0) VF_TRY(launch_stencil(&view, OP_DETECT, a, a, ea));
         if (size == 3) {
             VF_TRY(launch_stencil(&view, OP_ERODE3, a, b, ea));
         } else {

@@ -105,6 +105,7 @@ struct vf_ctx {
     VfScratch small;     // seeds, counters, histogram bins, masks
     VfScratch noise;     // erosion noise table
     VfScratch mesh;      // voxelizer: vertices, faces, bins
+    VfScratch bits;      // vf_grid_upload_bits: the occupancy bitmap before it is expanded
     VfScratch codec;     // device-side .rle encoder: tile counts, run starts / values, packed records
     void* pinned = nullptr;  // small pinned host mailbox for counters
     size_t pinned_bytes = 0;
