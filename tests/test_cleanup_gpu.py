@@ -358,3 +358,35 @@ def test_upload_bits_expands_one_bit_per_cell(ctx, orc, vessel_grid, shape):
     g.upload_bits(bits)
     assert np.array_equal(g.updateGrid(), (occ != 0).astype(np.uint16))
     g.close()
+
+
+@pytest.mark.parametrize("b", [0, 2, 3, 5])
+def test_detect_boundaries_with_larger_boundary_size(ctx, orc, labelled_vessel, b):
+    """detectBoundaries-comp.glsl:24-25 takes any boundarySize (the reference passes 1); the oracle's rule is pinned by the shader text itself
+    (tests/test_oracle_vs_glsl.py).  Also on an already tagged grid and on a ragged one."""
+    lab, _ = labelled_vessel
+    for host in (lab, orc.detect_boundaries(lab.copy(), 1)):
+        g = _grid(ctx, host)
+        g.detectBoundaries(b)
+        assert np.array_equal(g.updateGrid(), orc.detect_boundaries(host.copy(), b))
+        g.close()
+    g0 = random_blob_grid((19, 23, 37), 1, fill=0.6, smooth=0)
+    rag = orc.naive(g0.copy(), pick_seeds(g0, 5, 3), 1)
+    g = _grid(ctx, rag)
+    g.detectBoundaries(b)
+    assert np.array_equal(g.updateGrid(), orc.detect_boundaries(rag.copy(), b))
+    g.close()
+
+
+def test_qstack_export_from_device_runs(ctx, orc, tmp_path):
+    """`.qstack` with the z-column runs taken from the device-side run stream (no full-grid download): every case whose bytes the reference's
+    own QuadStack.h / GStack.h pin (tests/golden/qstack_golden.json through the oracle, tests/test_oracle_golden.py)"""
+    import voxelfragmentml_b200 as vf
+    from vox_cases import all_qstack_cases
+
+    for name, grid in all_qstack_cases():
+        g = _grid(ctx, grid)
+        base = str(tmp_path / f"q_{name}")
+        g.exportGrid(base, True, vf.ExportGrid.QUADSTACK)
+        assert open(base + ".qstack", "rb").read() == orc.encode_qstack(grid), name
+        g.close()

@@ -255,7 +255,11 @@ extern "C" vf_status vf_dataset_model(vf_grid* g, const vf_procedure* proc, cons
     if (proc->solidVoxelization) {
         uint64_t occ = 0;
         VF_TRY(vf_voxelize_solid(g, verts, nv, faces, nf, &occ));
-        VF_REQUIRE(occ > 0, VF_ERR_UNSUPPORTED, "no voxel set: the reference falls back to random surface sampling (fillNaive), which is not on this path");
+        // RegularGrid::fill, RegularGrid.cpp:205-211: when the solid voxelizer sets nothing (an open surface) the reference falls back to
+        // fillNaive (:800-816), which marks the cells hit by ~10^4 RANDOM surface samples drawn under an OpenMP race — no two runs of the
+        // reference agree on them.  The deterministic stand-in is the exact surface occupancy (every cell a triangle touches, vf_voxelize),
+        // a superset of every sample set fillNaive can draw.
+        if (occ == 0) VF_TRY(vf_voxelize(g, verts, nv, faces, nf));
     } else {
         VF_TRY(vf_voxelize(g, verts, nv, faces, nf));
     }

@@ -242,6 +242,10 @@ struct QsNode {
 
 }  // namespace
 
+// the quadtree stages over the run-length coded z-columns (CSR: column c owns runs first[c] .. first[c + 1])
+static uint64_t qstack_from_columns(const std::vector<uint64_t>& first, const std::vector<uint16_t>& rval, const std::vector<uint16_t>& rlen, const uint32_t dims[3],
+                                    uint8_t* out, uint64_t cap);
+
 extern "C" uint64_t vf_encode_qstack(const uint16_t* grid, const uint32_t dims[3], uint8_t* out, uint64_t cap)
 {
     const uint32_t W = dims[0], H = dims[1], D = dims[2];
@@ -259,6 +263,40 @@ extern "C" uint64_t vf_encode_qstack(const uint16_t* grid, const uint32_t dims[3
         }
         first[c + 1] = rval.size();
     }
+    return qstack_from_columns(first, rval, rlen, dims, out, cap);
+}
+
+// The same file from the `.rle` stream of the grid (12-byte header, then {uint16 value, uint32 repetitions} records over the x-major array,
+// RegularGrid.cpp:672-714): a z-column is D consecutive cells of that array, so compress_y's column runs are the stream's runs cut at the
+// multiples of D.  With the stream produced on the device (vf_grid_encode_rle) the `.qstack` export downloads runs, not 2 B per voxel.
+static uint64_t qstack_from_rle_stream(const uint8_t* stream, uint64_t bytes, const uint32_t dims[3], uint8_t* out, uint64_t cap)
+{
+    const uint32_t W = dims[0], H = dims[1], D = dims[2];
+    if (!W || !H || !D || W > 0xFFFF || H > 0xFFFF || D > 0xFFFF || bytes < 12) return 0;
+    const uint64_t nrec = (bytes - 12) / 6, ncol = (uint64_t)W * H;
+    std::vector<uint64_t> first(ncol + 1, 0);
+    std::vector<uint16_t> rval, rlen;
+    rval.reserve(nrec + ncol), rlen.reserve(nrec + ncol);
+    uint64_t col = 0, z = 0;  // position of the next cell
+    for (uint64_t r = 0; r < nrec; ++r) {
+        uint16_t v;
+        uint32_t rep;
+        std::memcpy(&v, stream + 12 + 6 * r, 2), std::memcpy(&rep, stream + 12 + 6 * r + 2, 4);
+        while (rep) {
+            const uint32_t take = (uint32_t)std::min<uint64_t>(rep, D - z);
+            rval.push_back(v), rlen.push_back((uint16_t)take);
+            rep -= take, z += take;
+            if (z == D) z = 0, first[++col] = rval.size();
+        }
+    }
+    if (col != ncol) return 0;  // the stream does not cover the grid
+    return qstack_from_columns(first, rval, rlen, dims, out, cap);
+}
+
+static uint64_t qstack_from_columns(const std::vector<uint64_t>& first, const std::vector<uint16_t>& rval, const std::vector<uint16_t>& rlen, const uint32_t dims[3],
+                                    uint8_t* out, uint64_t cap)
+{
+    const uint32_t W = dims[0], H = dims[1], D = dims[2];
     auto same_values = [&](size_t a, size_t b) {
         const uint64_t na = first[a + 1] - first[a];
         return na == first[b + 1] - first[b] && std::memcmp(&rval[first[a]], &rval[first[b]], na * 2) == 0;
@@ -555,10 +593,16 @@ extern "C" vf_status vf_export(vf_grid* g, const char* path, int type, int squar
     VF_REQUIRE(type >= 0 && type < 4, VF_ERR_INVALID_ARGUMENT, "bad export type %d", type);
     const uint32_t dims[3] = { g->X, g->Y, g->Z };
     std::vector<uint8_t> bytes;
-    if (type == VF_RLE && g->n() < (1ull << 32)) {
-        // runs are found on the device; only the finished byte stream is downloaded
+    if ((type == VF_RLE || type == VF_QUADSTACK) && g->n() < (1ull << 32)) {
+        // runs are found on the device; only the finished run stream is downloaded (for .qstack it is then cut into z-columns on the host)
         uint64_t need = 0;
         VF_TRY(rle_encode_device(g, &bytes, nullptr, 0, &need));
+        if (type == VF_QUADSTACK) {
+            std::vector<uint8_t> q(qstack_from_rle_stream(bytes.data(), bytes.size(), dims, nullptr, 0));
+            VF_REQUIRE(!q.empty(), VF_ERR_CAPACITY, "exportQuadStack: dimensions must fit uint16_t (QuadStack.h:9)");
+            qstack_from_rle_stream(bytes.data(), bytes.size(), dims, q.data(), q.size());
+            bytes.swap(q);
+        }
     } else {
         std::vector<uint16_t> host(g->n());
         VF_TRY(vf_grid_download(g, host.data()));

@@ -173,6 +173,30 @@ __global__ void __launch_bounds__(256) erode_generic_kernel(const uint16_t* __re
     }
 }
 
+// detectBoundaries with boundarySize b > 1 (the reference itself only ever passes 1: CADScene.cpp:687, RegularGrid.cpp:135): direct global
+// reads over the clamped (2b + 1)^3 box, as detectBoundaries-comp.glsl:24-40.  In place like the shader: neighbours are compared with bit 15
+// cleared against the centre's raw word, which this pass alone may change, so the result does not depend on the order of the threads.
+__global__ void __launch_bounds__(256) detect_generic_kernel(uint16_t* grid, Dims d, int b)
+{
+    const size_t n = (size_t)d.X * d.Y * d.Z;
+    for (size_t gi = blockIdx.x * (size_t)blockDim.x + threadIdx.x; gi < n; gi += (size_t)gridDim.x * blockDim.x) {
+        const uint16_t own = grid[gi];
+        if (own <= VF_VOXEL_FREE) continue;
+        const int z = (int)(gi % d.Z);
+        const size_t r = gi / d.Z;
+        const int y = (int)(r % d.Y), x = (int)(r / d.Y);
+        const int x0 = max(x - b, 0), x1 = min(x + b, d.X - 1), y0 = max(y - b, 0), y1 = min(y + b, d.Y - 1), z0 = max(z - b, 0), z1 = min(z + b, d.Z - 1);
+        bool boundary = false;
+        for (int a = x0; a <= x1 && !boundary; ++a)
+            for (int bb = y0; bb <= y1 && !boundary; ++bb)
+                for (int c = z0; c <= z1 && !boundary; ++c) {
+                    const uint16_t v = ((volatile uint16_t*)grid)[((size_t)a * d.Y + bb) * d.Z + c] & 0x7FFFu;
+                    boundary = v > VF_VOXEL_FREE && v != own;
+                }
+        if (boundary) grid[gi] = own | 0x8000u;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ H1 histogram
 // one pass over 2 B/voxel.  A warp walks contiguous spans of 32 x 4 vectors (8 voxels each) with its four loads in flight;
 // every lane keeps a (label, count) run across the whole walk, so inside a fragment a lane issues one shared-memory atomic per
@@ -629,7 +653,13 @@ extern "C" vf_status vf_detect_boundaries(vf_grid* g, int boundary_size)
 {
     VF_REQUIRE(g != nullptr, VF_ERR_INVALID_ARGUMENT, "null grid");
     VF_TRY(vf_enter(g->ctx));
-    VF_REQUIRE(boundary_size == 1, VF_ERR_UNSUPPORTED, "detectBoundaries: only boundarySize 1 is used by the reference (CADScene.cpp:687, RegularGrid.cpp:135)");
+    VF_REQUIRE(boundary_size >= 0 && boundary_size <= 64, VF_ERR_INVALID_ARGUMENT, "detectBoundaries: boundarySize %d out of range [0, 64]", boundary_size);
+    if (boundary_size != 1) {  // the reference only ever passes 1 (CADScene.cpp:687, RegularGrid.cpp:135); other sizes take the direct path
+        Dims d = { (int)g->X, (int)g->Y, (int)g->Z };
+        detect_generic_kernel<<<g->ctx->num_sms * 8, 256, 0, g->ctx->stream>>>(g->d, d, boundary_size);
+        VF_LAUNCHED(g->ctx);
+        return VF_OK;
+    }
     ErodeArgs ea = {};
     return launch_stencil(g, OP_DETECT, g->d, g->d, ea);
 }
