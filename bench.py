@@ -477,15 +477,16 @@ def run_cuda(args):
     if vessel is not None:
         out["vessel"] = vessel
     if not args.no_batch:
-        # BASELINE.json's second metric (cfg4, models/s), measured briefly beside the headline: 32 meshes per GPU
+        # BASELINE.json's second metric (cfg4, models/s), measured beside the headline: 128 meshes per GPU, every mesh its own shape (the full
+        # config is 1024 meshes over the box = 128 per GPU at N = 8)
         jobs = args.jobs or default_jobs(world)
-        bm = 32 * world
-        bdt, _, npool = batch_measure(rank, local_rank, world, dist if world > 1 else None, bm, 2, jobs, 4)
+        bm = 128 * world
+        bdt, _, npool = batch_measure(rank, local_rank, world, dist if world > 1 else None, bm, 2, jobs, 0)
         out["batch"] = {"metric": "models/s batch voxelize+fragment", "value": bm / bdt, "unit": "models/s", "meshes": bm, "jobs_per_gpu": jobs,
                         "fragmentations_per_s": bm * 10 / bdt, "scaling": "weak", "host_cores": host_cores(),
                         "host_cpu_s_per_model_rank0": LAST_BATCH_INFO.get("host_cpu_s_per_model"),
-                        "workload": f"cfg4-batch: {bm} synthetic vessels (pool of {npool} shapes) x 10 fragmentations at 256-max, FLOOD CHEBYSHEV, nf 2..10, "
-                                    "2*nf extra seeds; full-size run: bench.py --workload batch --meshes 1024"}
+                        "workload": f"cfg4-batch: {bm} synthetic vessels ({npool} distinct shapes on this rank) x 10 fragmentations at 256-max, FLOOD CHEBYSHEV, "
+                                    "nf 2..10, 2*nf extra seeds, mesh m -> rank m mod N, RNG seed 80 + m"}
     if world >= 2 and not args.no_slab:
         # BASELINE config 5 on the driver's record: the slab-partitioned flood over all ranks — 2048^3 on 8 GPUs, 1024^3 on 2 or 4 (the key field of a
         # slab is 4 B per cell: 2048^3 / 8 ranks = 4.3 GiB of keys + 2.1 GiB of labels per GPU)
@@ -795,6 +796,7 @@ def default_jobs(world):
     return 16 if host_cores() // max(1, world) >= 16 or host_cores() // max(1, world) < 8 else 8
 
 
+BATCH_FLOOD_MODE = 0
 LAST_BATCH_INFO = {}  # side information of the last batch_measure call (rank-local)
 
 
@@ -813,9 +815,13 @@ def batch_measure(rank, local_rank, world, dist, meshes, warmup, jobs, mesh_pool
     import voxelfragmentml_b200 as vf
     from voxelfragmentml_b200 import synth
 
-    pool = [synth.vessel_mesh(i) for i in range(mesh_pool)]  # distinct shapes, generated once outside the timed region
     lib = vf._capi.load()
     my = [m for m in range(meshes) if m % world == rank]
+    # distinct shapes, generated once outside the timed region; mesh_pool <= 0: every mesh its own shape (only this rank's are generated)
+    if mesh_pool <= 0:
+        pool = {m: synth.vessel_mesh(m) for m in my}
+    else:
+        pool = {i: synth.vessel_mesh(i) for i in range(mesh_pool)}
     checksums = [0] * jobs
     workers = []
     block = blocking == "on" or (blocking == "auto" and jobs * world > host_cores())  # measured: 4 cores per rank, 16 jobs: 120 (spin) vs 164 models/s
@@ -824,13 +830,14 @@ def batch_measure(rank, local_rank, world, dist, meshes, warmup, jobs, mesh_pool
         ctx.setBlockingSync(block)
         if jobs > 1:
             ctx.setFloodLevels(8)  # throughput setting: with several jobs per GPU total tile work matters, not the latency of one flood
+            ctx.setFloodMode(BATCH_FLOOD_MODE)  # CTAs per SM of a job's cooperative round loop (0: one launch per round), so that jobs share the SMs
         grid = vf.RegularGrid(ctx, (256, 256, 256))  # allocated once at the clamp size, re-dimensioned per model (CADScene.cpp:529-543)
         ctx.reserve((256, 256, 256))
         workers.append((ctx, grid))
 
     def one_mesh(j, m):
         ctx, grid = workers[j]
-        v, f = pool[m % len(pool)]
+        v, f = pool[m] if mesh_pool <= 0 else pool[m % len(pool)]
         mn, mx = synth.mesh_aabb(v)
         dims = np.zeros(3, np.uint32)
         lib.vf_dims_rule(mn.ctypes.data, mx.ctypes.data, 256, dims.ctypes.data)
@@ -924,6 +931,7 @@ def run_dataset(args):
         ctx.setBlockingSync(jobs * world > host_cores())
         if jobs > 1:
             ctx.setFloodLevels(8)
+            ctx.setFloodMode(BATCH_FLOOD_MODE)
         workers.append((ctx, dataset.dataset_grid(ctx, proc), vf._capi.VfDatasetStats()))
     out = tempfile.mkdtemp(prefix=f"vf_dataset_r{rank}_", dir=args.out or None)
     my = [m for m in range(args.meshes) if m % world == rank]
@@ -972,6 +980,7 @@ def run_dataset(args):
 
 
 def main():
+    global BATCH_FLOOD_MODE
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -987,6 +996,7 @@ def main():
                     help="cfg3 = the driver's default; slab = cfg5; batch = cfg4; dataset = cfg4 through the native driver with .rle export")
     ap.add_argument("--out", default="", help="dataset workload: parent directory of the (temporary) output folder")
     ap.add_argument("--no-export", action="store_true", help="dataset workload: no grid files (the batch loop through the native driver, metadata files only)")
+    ap.add_argument("--flood-mode", type=int, default=0, help="batch workload: vf_ctx_set_flood_mode of the job contexts (0 = one launch per round, 1..4 = CTAs per SM of the cooperative loop)")
     ap.add_argument("--seeds", type=int, default=256, help="slab workload: number of seeds")
     ap.add_argument("--python-exchange", action="store_true", help="slab workload: the Python exchange loop over torch.distributed instead of the C++ loop over NCCL")
     ap.add_argument("--slab-size", type=int, default=0, help="default workload at N >= 2: edge of the cfg5 grid (default 2048 at 8 GPUs, else 1024)")
@@ -999,6 +1009,7 @@ def main():
     ap.add_argument("--no-batch", action="store_true", help="default workload: skip the short cfg4 batch measurement reported under \"batch\"")
     ap.add_argument("--mesh-pool", type=int, default=8, help="batch workload: distinct synthetic shapes generated up front")
     args = ap.parse_args()
+    BATCH_FLOOD_MODE = args.flood_mode
     claim_stdout()
     if args.impl == "reference":
         run_reference(args)

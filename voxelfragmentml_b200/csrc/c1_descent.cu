@@ -11,8 +11,8 @@
 //   F = labelled cells, not seeds, without any descent neighbour                      (one streaming pass, 2 B read per voxel)
 //   D = least set that holds F and every cell ALL of whose descent neighbours are in D (frontier propagation away from the seeds)
 //   kept = cells outside D  +  cells of D reachable inside D from a D-cell that touches a same-label cell outside D
-// On the cfg3 grid (512^3, 64 Voronoi regions) F and D are a few dozen cells, on the reference's vessel shell ~10^4: the union-find over
-// all runs of the grid is replaced by one pass plus list work on D.
+// On the cfg3 grid (512^3, 64 Voronoi regions) F and D are a few dozen cells: the union-find over all runs of the grid is replaced by one
+// pass plus list work on D.  On thin curved shells F runs into the 10^4s; the pass notices (kBailF), stops and leaves the grid to the union-find.
 //
 // The pass: a warp walks 32 consecutive 8-cell chunks of a z-row (one 128-bit load per lane, the next item's load already in flight).  The
 // z-neighbours of a chunk's end cells come from the adjacent lanes by shuffle; a chunk that holds one label certifies seven of its cells by
@@ -31,6 +31,7 @@ namespace vfc1 {
 
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 constexpr uint32_t kCap = 1u << 16;       // list capacity in cells
+constexpr uint32_t kBailF = 4096;         // more uncertified cells than this: the pass stops and the union-find takes the grid (thin shells)
 constexpr uint32_t kHashBits = 18;        // hash set: 4 x the list capacity
 constexpr uint32_t kHashSize = 1u << kHashBits;
 constexpr uint32_t kMaxSeeds = 4096;      // seed positions live in shared memory (32 KB)
@@ -212,6 +213,12 @@ __global__ void __launch_bounds__(kCertWarps * 32) certificate_kernel(uint16_t* 
     int cz = -1 << 20;    // ... and its seed's z (none: far away)
     uint4 vnext = load(row, seg);
     for (uint32_t item = begin; item < end; ++item) {
+        // a grid the certificate does not suit (thin curved shells: the straight way to the seed leaves the label) is recognised early: once
+        // more than kBailF cells are listed every warp stops, the list work is skipped and the caller runs the union-find
+        if ((item & 7u) == 0 && *(volatile uint32_t*)&ctl->tail > kBailF) {
+            ctl->overflow = 1;
+            return;
+        }
         const uint4 v = vnext;
         uint32_t nrow = row, nseg = seg + 1;
         if (nseg == segs) nseg = 0, ++nrow;
@@ -265,7 +272,10 @@ __global__ void __launch_bounds__(kResolveThreads) resolve_kernel(uint16_t* grid
     extern __shared__ ushort4 sp[];
     __shared__ uint32_t s_head, s_tail, s_flag;
     const int t = threadIdx.x;
-    if (t == 0) s_head = 0, s_tail = min(ctl->tail, kCap), s_flag = ctl->overflow | ctl->dup;
+    if (t == 0) {
+        if (ctl->tail > kBailF) ctl->overflow = 1;  // the pass stopped, or ended, with more cells than the list work is meant for
+        s_head = 0, s_tail = min(ctl->tail, kCap), s_flag = ctl->overflow | ctl->dup;
+    }
     __syncthreads();
     if (s_flag || s_tail == 0) return;
     for (int i = t; i < S; i += blockDim.x) sp[i] = seeds[i];

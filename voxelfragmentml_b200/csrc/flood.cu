@@ -781,11 +781,14 @@ extern "C" vf_status vf_remove_isolated_regions(vf_grid* grid, const uint32_t* s
     VF_TRY(vf_enter(c));
     ushort4* d_seeds = nullptr;
     VF_TRY(vf_upload_seeds(c, seeds, nseeds, grid->X, grid->Y, grid->Z, &d_seeds));
-    if (c->c1_mode == 0) {  // descent certificate (c1_descent.cu); the union-find below takes over when it declines
+    // descent certificate (c1_descent.cu); the union-find below takes over when it declines.  A context whose last grid was declined (thin
+    // shells: batch producers work through similar shapes) goes straight to the union-find and tries the certificate again every 16th call.
+    if (c->c1_mode == 0 && (c->c1_declined == 0 || (++c->c1_declined & 15u) == 0)) {
         int handled = 0;
         uint32_t max_label = 0;
         for (uint32_t i = 0; i < nseeds; ++i) max_label = std::max(max_label, seeds[4 * i + 3]);
         VF_TRY(vf_k_c1_descent(grid, d_seeds, (int)nseeds, max_label, &handled));
+        c->c1_declined = handled ? 0u : 1u;
         if (handled) return VF_OK;
     }
     return vf_k_keep_seed_components(grid, d_seeds, (int)nseeds, 0, 6, nullptr);
