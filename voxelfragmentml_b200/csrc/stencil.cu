@@ -55,18 +55,13 @@ struct ErodeArgs {
     unsigned erodes[28];
     unsigned long long nn_magic;  // 2^64 / nnoise + 1: exact 32-bit modulo by multiplication when the grid has < 2^32 cells
     int idx32;
-    // cells this pass empties, for the sparse follow-up passes (erode_sparse_kernel); null: not recorded
-    uint32_t* changed;        // [changed_cap] linear cell indices
-    uint32_t* changed_count;  // entries appended (may exceed changed_cap: then the list is incomplete and the host takes the full passes)
-    uint32_t changed_cap;
+    // cells this pass empties, for the sparse follow-up passes (erode_sparse_kernel): one bit per cell; null: not recorded
+    uint32_t* changed;
 };
 
 __device__ __forceinline__ void note_eroded(const ErodeArgs& ea, size_t gi)
 {
-    if (ea.changed) {
-        const uint32_t j = atomicAdd(ea.changed_count, 1u);
-        if (j < ea.changed_cap) ea.changed[j] = (uint32_t)gi;
-    }
+    if (ea.changed) atomicOr(&ea.changed[gi >> 5], 1u << (gi & 31u));
 }
 
 __device__ __forceinline__ unsigned noise_index(const ErodeArgs& ea, size_t gi)
@@ -187,56 +182,51 @@ __global__ void __launch_bounds__(256) erode_generic_kernel(const uint16_t* __re
 
 // Sparse follow-up pass of the 3^3 erosion (iterations 2..K).  Erosion is a function of a cell's word, its 3^3 window and its noise value: a
 // cell whose window did not change since the previous pass decides as it did then, i.e. it stays.  So pass k only has to look at the cells
-// whose window holds a cell that pass k-1 emptied — the 27 positions around every entry of that pass's list — and `dst`, which still holds
-// the grid of two passes ago, already carries the right word everywhere else (it differs from `src` exactly at the listed cells, which are
+// whose window holds a cell that pass k-1 emptied — the 27 positions around every bit of that pass's bitmap — and `dst`, which still holds
+// the grid of two passes ago, already carries the right word everywhere else (it differs from `src` exactly at the marked cells, which are
 // among the 27).  Each candidate is evaluated exactly as in the full pass (clamped box, mask, noise, float32 comparison through the same
-// table); the thread that turns a word of `dst` to EMPTY (32-bit CAS on the aligned pair) appends the cell to the next list, so a cell
-// reached from several listed neighbours is listed once.
-__global__ void __launch_bounds__(256) erode_sparse_kernel(const uint16_t* __restrict__ src, uint16_t* dst, Dims d, ErodeArgs ea, const uint32_t* __restrict__ list_in,
-                                                           const uint32_t* __restrict__ count_in)
+// table); a candidate reached from several marked neighbours gets the same answer from each.  The bitmaps have a fixed size (one bit per
+// cell), so nothing here depends on how many cells a pass empties and the host never has to look: the whole erode call is asynchronous.
+// A warp scans 32 bitmap words per step and hands the set bits out to its lanes.
+__global__ void __launch_bounds__(256) erode_sparse_kernel(const uint16_t* __restrict__ src, uint16_t* dst, Dims d, ErodeArgs ea, const uint32_t* __restrict__ marked,
+                                                           uint32_t nwords)
 {
-    const uint32_t nin = min(*count_in, ea.changed_cap);
-    const uint64_t total = (uint64_t)nin * 27u;
-    for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < total; w += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t u = list_in[w / 27u];
-        const int p = (int)(w % 27u);
-        const int uz = (int)(u % (uint32_t)d.Z);
-        const uint32_t r = u / (uint32_t)d.Z;
-        const int uy = (int)(r % (uint32_t)d.Y), ux = (int)(r / (uint32_t)d.Y);
-        const int x = ux + p / 9 - 1, y = uy + (p / 3) % 3 - 1, z = uz + p % 3 - 1;
-        if ((unsigned)x >= (unsigned)d.X || (unsigned)y >= (unsigned)d.Y || (unsigned)z >= (unsigned)d.Z) continue;
-        const size_t gi = ((size_t)x * d.Y + y) * d.Z + z;
-        const uint16_t own = src[gi];
-        bool erodes = false;
-        const bool isB = ea.boundary_mode == 0 ? (own & 0x7FFFu) != 0 : (own >> 15) != 0;
-        if (own > VF_VOXEL_FREE && isB && ea.noise[noise_index(ea, gi)] < ea.prob) {
-            unsigned count = 0, visited = 0;
-            for (int dx = -1; dx <= 1; ++dx)
-                for (int dy = -1; dy <= 1; ++dy)
-                    for (int dz = -1; dz <= 1; ++dz) {
-                        const int a = x + dx, b = y + dy, c = z + dz;
+    const int lane = threadIdx.x & 31;
+    const uint32_t nwarps = gridDim.x * (blockDim.x / 32), wid = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    for (uint32_t base = wid * 32u; base < nwords; base += nwarps * 32u) {
+        const uint32_t mine = base + lane < nwords ? marked[base + lane] : 0u;
+        for (unsigned have = __ballot_sync(0xFFFFFFFFu, mine != 0); have; have &= have - 1) {
+            const int src_lane = __ffs(have) - 1;
+            uint32_t bits = __shfl_sync(0xFFFFFFFFu, mine, src_lane);
+            const uint32_t word = base + src_lane;
+            while (bits) {  // one marked cell at a time: its 27 neighbourhood positions go to lanes 0..26
+                const uint32_t u = word * 32u + (__ffs(bits) - 1);
+                bits &= bits - 1;
+                if (lane >= 27) continue;
+                const int uz = (int)(u % (uint32_t)d.Z);
+                const uint32_t r = u / (uint32_t)d.Z;
+                const int uy = (int)(r % (uint32_t)d.Y), ux = (int)(r / (uint32_t)d.Y);
+                const int x = ux + lane / 9 - 1, y = uy + (lane / 3) % 3 - 1, z = uz + lane % 3 - 1;
+                if ((unsigned)x >= (unsigned)d.X || (unsigned)y >= (unsigned)d.Y || (unsigned)z >= (unsigned)d.Z) continue;
+                const size_t gi = ((size_t)x * d.Y + y) * d.Z + z;
+                const uint16_t own = src[gi];
+                bool erodes = false;
+                const bool isB = ea.boundary_mode == 0 ? (own & 0x7FFFu) != 0 : (own >> 15) != 0;
+                if (own > VF_VOXEL_FREE && isB && ea.noise[noise_index(ea, gi)] < ea.prob) {
+                    // visited = cells of the clamped box; only the cells the mask selects are read (7 of 27 for ELLIPSE / CROSS)
+                    const unsigned visited = (1 + (x > 0) + (x < d.X - 1)) * (1 + (y > 0) + (y < d.Y - 1)) * (1 + (z > 0) + (z < d.Z - 1));
+                    unsigned count = 0;
+                    for (unsigned m = ea.maskbits; m; m &= m - 1) {
+                        const int bit = __ffs(m) - 1;
+                        const int a = x + bit / 9 - 1, b = y + (bit / 3) % 3 - 1, c = z + bit % 3 - 1;
                         if ((unsigned)a >= (unsigned)d.X || (unsigned)b >= (unsigned)d.Y || (unsigned)c >= (unsigned)d.Z) continue;
-                        ++visited;
-                        const unsigned bit = (dx + 1) * 9 + (dy + 1) * 3 + (dz + 1);
-                        count += (ea.maskbits >> bit & 1u) && src[((size_t)a * d.Y + b) * d.Z + c] == own;
+                        count += src[((size_t)a * d.Y + b) * d.Z + c] == own;
                     }
-            erodes = ea.erodes[visited] >> count & 1u;
-        }
-        if (!erodes) {
-            dst[gi] = own;  // equal to what dst holds unless the previous pass emptied the cell
-            continue;
-        }
-        unsigned* word = reinterpret_cast<unsigned*>(dst + (gi & ~(size_t)1));
-        const unsigned keep = gi & 1 ? 0x0000FFFFu : 0xFFFF0000u;
-        unsigned seen = *word;
-        for (;;) {
-            if ((seen & ~keep) == 0) break;  // somebody else emptied it (and listed it)
-            const unsigned old = atomicCAS(word, seen, seen & keep);
-            if (old == seen) {
-                note_eroded(ea, gi);
-                break;
+                    erodes = ea.erodes[visited] >> count & 1u;
+                }
+                dst[gi] = erodes ? (uint16_t)VF_VOXEL_EMPTY : own;  // equal to what dst holds unless this or the previous pass empties the cell
+                if (erodes) note_eroded(ea, gi);
             }
-            seen = old;
         }
     }
 }
@@ -782,35 +772,22 @@ extern "C" vf_status vf_erode(vf_grid* g, int type, uint32_t size, uint32_t iter
     uint16_t* b = (uint16_t*)c->grid2.ptr;
     vf_grid view = *g;  // shallow view used to run passes on either buffer
 
-    // Iterations 2..K of the 3^3 erosion run sparsely (erode_sparse_kernel): every pass records the cells it empties, the next one only
-    // re-decides the 27 cells around each of them.  Two lists in the key arena, `cap` entries each; a list that may have overflowed is
-    // checked on the host (one read-back), and an incomplete list is answered with a full pass.  cfg3 (512^3, 64 regions): the first pass
-    // empties ~3 * 10^4 cells, the second ~4 * 10^3, the third ~7 * 10^2.
+    // Iterations 2..K of the 3^3 erosion run sparsely (erode_sparse_kernel): every pass marks the cells it empties in a bitmap (one bit per
+    // cell, two bitmaps in the key arena), the next one only re-decides the 27 cells around each of them.  cfg3 (512^3, 64 regions): the first
+    // pass empties ~3 * 10^4 cells, the second ~4 * 10^3, the third ~7 * 10^2.
     const bool sparse_ok = size == 3 && iterations >= 2 && n <= 0xFFFFFFFFull;
-    uint32_t cap = 0;
-    uint32_t* lists[2] = { nullptr, nullptr };
-    uint32_t* counters = nullptr;
-    uint32_t* h_count = (uint32_t*)((char*)c->pinned + 65536 + 512);
+    const uint32_t nwords = (uint32_t)((n + 31) / 32);
+    uint32_t* maps[2] = { nullptr, nullptr };
     if (sparse_ok) {
-        cap = (uint32_t)std::max<size_t>((size_t)1 << 16, n / 8);
-        VF_TRY(vf_scratch_reserve(c, c->keys, 256 + 2 * (size_t)cap * 4));
-        counters = (uint32_t*)c->keys.ptr;
-        lists[0] = counters + 64, lists[1] = lists[0] + cap;
+        VF_TRY(vf_scratch_reserve(c, c->keys, 2 * (size_t)nwords * 4));
+        maps[0] = (uint32_t*)c->keys.ptr, maps[1] = maps[0] + nwords;
     }
-    uint64_t bound = 0;      // upper bound on the entries of the list the next pass reads
-    bool have_list = false;  // that list is complete
-    auto read_count = [&](int which, uint32_t* out) -> vf_status {
-        VF_CUDA(cudaMemcpyAsync(h_count, counters + which, 4, cudaMemcpyDeviceToHost, c->stream));
-        VF_CUDA(vf_sync(c));
-        *out = *h_count;
-        return VF_OK;
-    };
     for (uint32_t it = 0; it < iterations; ++it) {
         view.d = a;
-        const int out = (int)(it & 1u), in = out ^ 1;  // list written / read by this pass
+        const int out = (int)(it & 1u), in = out ^ 1;  // bitmap written / read by this pass
         const bool record = sparse_ok && it + 1 < iterations;
-        ea.changed = record ? lists[out] : nullptr, ea.changed_count = record ? counters + out : nullptr, ea.changed_cap = cap;
-        if (record) VF_TRY(vf_k_zero(c, counters + out, 4));
+        ea.changed = record ? maps[out] : nullptr;
+        if (record) VF_TRY(vf_k_zero(c, maps[out], (size_t)nwords * 4));
         if (it == 0) {
             VF_TRY(launch_stencil(&view, OP_DETECT, a, a, ea));  // only in the first iteration: see below
             // The noise table is handled AFTER the detect pass is queued: comparing a 4 MB table with its shadow takes the host longer than a
@@ -828,27 +805,14 @@ extern "C" vf_status vf_erode(vf_grid* g, int type, uint32_t size, uint32_t iter
         // words, tags included, or writes EMPTY.  After the first pass every cell whose box holds another label is tagged, and a later
         // pass could only tag a cell whose box GAINED another label — no pass creates labels.  (Checked against the literal shader
         // transcription with and without the repeated passes: tests/test_oracle_literal_shaders.py.)
-        bool full = true;
-        if (it > 0 && have_list) {
-            const uint64_t work = std::max<uint64_t>(bound, 1) * 27;
-            const int blocks = (int)std::min<uint64_t>((uint64_t)c->num_sms * 8, (work + 255) / 256);
-            erode_sparse_kernel<<<blocks, 256, 0, c->stream>>>(a, b, d, ea, lists[in], counters + in);
+        if (it > 0 && sparse_ok) {
+            erode_sparse_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>(a, b, d, ea, maps[in], nwords);
             VF_LAUNCHED(c);
-            bound *= 26;  // every listed cell can take its 26 neighbours along at most
-            full = false;
         } else if (size == 3) {
             VF_TRY(launch_stencil(&view, OP_ERODE3, a, b, ea));
         } else {
             erode_generic_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>(a, b, d, d_mask, (int)size, ea);
             VF_LAUNCHED(c);
-        }
-        if (record && (full || bound > cap)) {  // how long is the list this pass wrote?
-            uint32_t cnt = 0;
-            VF_TRY(read_count(out, &cnt));
-            have_list = cnt <= cap;
-            bound = cnt;
-        } else if (!record) {
-            have_list = false;
         }
         std::swap(a, b);  // replaces copyGrid (:149-152): the eroded grid becomes the current one
     }
