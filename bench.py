@@ -67,9 +67,15 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.first = index, [], None, 0
+
+    def mark(self):
+        """samples from here on are the ones reported (the timed region starts)"""
+        self.first = max(0, len(self.rows) - 1)
 
     def start(self):
+        if self.index < 0:  # ranks other than 0 do not sample: eight nvidia-smi pollers on one box disturb what they measure
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -84,7 +90,7 @@ class ClockSampler:
 
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["not sampled on this rank" if self.index < 0 else "nvidia-smi unavailable"]}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -92,7 +98,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -213,8 +219,16 @@ def run_cuda(args):
         if record is not None:
             record.append(t)
 
-    # ---- warm-up, then K timed steps (CUDA events on the context's stream; the input restore is outside the events)
+    # ---- warm-up, then K timed steps (CUDA events on the context's stream; the input restore is outside the events).
+    # The clock sampler (nvidia-smi -lms 20 on rank 0's GPU) is started BEFORE the warm-up: the tool needs about a second to come up, and the
+    # timed region of this workload lasts tens of milliseconds; it keeps sampling through the timed steps and the per-kernel timing below.
+    sampler = ClockSampler(local_rank if rank == 0 else -1)
+    sampler.start()
+    t_warm = time.perf_counter()
     for _ in range(args.warmup):
+        restore()
+        pipeline()
+    while rank == 0 and not sampler.rows and time.perf_counter() - t_warm < 3.0:  # first sample in: the sampler is live under load
         restore()
         pipeline()
     ctx.synchronize()
@@ -222,8 +236,7 @@ def run_cuda(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     step_ms = []
     for _ in range(args.steps):
         restore()

@@ -396,6 +396,15 @@ __global__ void __launch_bounds__(kResolveThreads) resolve_kernel(uint16_t* grid
     if (freed) atomicAdd(&ctl->freed, freed);
 }
 
+// verdict of the certificate straight into (mapped) pinned host memory: the host polls the word instead of going through a copy + a stream
+// synchronisation (two driver calls and their wake-up latency, which grows when several processes drive GPUs from one box)
+__global__ void publish_kernel(const Ctl* ctl, volatile uint32_t* host_word)
+{
+    const uint32_t v = 1u | (ctl->overflow ? 2u : 0u) | (ctl->dup ? 4u : 0u);
+    *host_word = v;
+    __threadfence_system();
+}
+
 }  // namespace vfc1
 
 // Returns VF_OK with *handled = 1 when the grid now holds C1's result; *handled = 0 when the caller must run the union-find (the grid then
@@ -429,10 +438,31 @@ vf_status vf_k_c1_descent(vf_grid* grid, const ushort4* d_seeds, int nseeds, uin
     VF_LAUNCHED(c);
     resolve_kernel<<<1, kResolveThreads, smem, c->stream>>>(grid->d, d, d_seeds, nseeds, table, set, alive, list, ctl);
     VF_LAUNCHED(c);
-    Ctl* h = (Ctl*)((char*)c->pinned + 65536 + 256);
-    VF_CUDA(cudaMemcpyAsync(h, ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, c->stream));
-    VF_CUDA(vf_sync(c));
-    if (h->overflow || h->dup) return VF_OK;  // too much for one CTA's list work, or ambiguous starts: the union-find is the right tool
+    volatile uint32_t* h_word = (volatile uint32_t*)((char*)c->pinned + 65536 + 256);
+    if (c->blocking_sync) {  // producers that share cores: sleep on the event instead of polling
+        Ctl* h = (Ctl*)((char*)c->pinned + 65536 + 320);
+        VF_CUDA(cudaMemcpyAsync(h, ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, c->stream));
+        VF_CUDA(vf_sync(c));
+        if (h->overflow || h->dup) return VF_OK;  // too much for one CTA's list work, or ambiguous starts: the union-find is the right tool
+        *handled = 1;
+        return VF_OK;
+    }
+    *h_word = 0;
+    publish_kernel<<<1, 1, 0, c->stream>>>(ctl, h_word);
+    VF_LAUNCHED(c);
+    uint32_t verdict = 0;
+    for (uint64_t spins = 0; (verdict = *h_word) == 0; ++spins) {
+        if ((spins & 0xFFFFu) == 0xFFFFu && cudaStreamQuery(c->stream) != cudaErrorNotReady) {  // the stream drained or failed: stop polling
+            VF_CUDA(vf_sync(c));
+            verdict = *h_word;
+            VF_REQUIRE(verdict != 0, VF_ERR_CUDA, "C1: the certificate's verdict never arrived");
+            break;
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    if (verdict & 6u) return VF_OK;  // too much for one CTA's list work, or ambiguous starts: the union-find is the right tool
     *handled = 1;
     return VF_OK;
 }
