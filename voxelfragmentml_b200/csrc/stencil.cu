@@ -256,19 +256,25 @@ __global__ void __launch_bounds__(256) detect_generic_kernel(uint16_t* grid, Dim
 }
 
 // ------------------------------------------------------------------------------------------------ H1 histogram
-// one pass over 2 B/voxel.  A warp walks contiguous spans of 32 x 4 vectors (8 voxels each) with its four loads in flight;
-// every lane keeps a (label, count) run across the whole walk, so inside a fragment a lane issues one shared-memory atomic per
-// label change instead of one per vector.  Shared bins for ids < 4096, global atomics beyond.
+// One pass over 2 B/voxel.  A lane reads four consecutive 8-cell vectors (64 bytes; a warp covers 2 KB) and keeps a (label, count) run in
+// registers: a vector that holds one label — 85 % of them on the cfg3 grid — costs a compare and an add, and a shared-memory atomic only
+// when the lane's label changes.  Vectors that straddle a label change are queued in shared memory and counted 32 at a time, one vector per
+// lane, run by run, so that the warp does not walk the slow path for the sake of a few lanes.  Shared bins for ids < 4096, global atomics
+// beyond.  UNMASK: the same pass also clears bit 15 (undoMask) — vectors that carry a tag are written back, the others are only read.
 constexpr int kSmemBins = 4096;
-constexpr int kHistBatch = 4;
-// UNMASK: the same pass also clears bit 15 (undoMask) — vectors that carry a tag are written back, the others are only read.
+constexpr int kHistBatch = 4, kHistWarps = 8, kHistQueue = 160;  // queue: up to 31 waiting + 4 x 32 pushed per step
+
 template <bool UNMASK>
-__global__ void __launch_bounds__(256) histogram_kernel(uint16_t* __restrict__ grid, size_t n, uint32_t* __restrict__ counts,
-                                                        unsigned long long* __restrict__ occupied)
+__global__ void __launch_bounds__(kHistWarps * 32) histogram_kernel(uint16_t* __restrict__ grid, size_t n, uint32_t* __restrict__ counts,
+                                                                    unsigned long long* __restrict__ occupied)
 {
     __shared__ uint32_t bins[kSmemBins];
+    __shared__ uint4 queue[kHistWarps][kHistQueue];
     for (int i = threadIdx.x; i < kSmemBins; i += blockDim.x) bins[i] = 0;
     __syncthreads();
+    const int lane = threadIdx.x & 31;
+    uint4* q = queue[threadIdx.x >> 5];
+    int qn = 0;
     unsigned occ = 0;
     const size_t nvec = n / 8;
     uint4* g4 = reinterpret_cast<uint4*>(grid);
@@ -276,91 +282,72 @@ __global__ void __launch_bounds__(256) histogram_kernel(uint16_t* __restrict__ g
         if (label < kSmemBins) atomicAdd(&bins[label], c);
         else atomicAdd(&counts[label], c);
     };
-    uint32_t run_label = 0xFFFFFFFFu, run = 0;
-    auto take = [&](uint32_t raw, uint32_t c) {  // c voxels holding the word `raw`
-        if (raw > VF_VOXEL_FREE) {               // RegularGrid.cpp:612: raw value > FREE, then unmask
-            const uint32_t label = raw & 0x7FFFu;
-            occ += c;
-            if (label == run_label) run += c;
-            else {
-                if (run) add(run_label, run);
-                run_label = label, run = c;
+    // the cells of one queued vector, run by run (RegularGrid.cpp:612: raw value > FREE, then unmask)
+    auto count_runs = [&](const uint4& v) {
+        const uint32_t one = 0x00010001u;  // run starts: bit k set <=> cell k differs from cell k - 1
+        const uint32_t n0 = __vminu2(v.x ^ __byte_perm(v.x, 0, 0x1010), one), n1 = __vminu2(v.y ^ __byte_perm(v.x, v.y, 0x5432), one);
+        const uint32_t n2 = __vminu2(v.z ^ __byte_perm(v.y, v.z, 0x5432), one), n3 = __vminu2(v.w ^ __byte_perm(v.z, v.w, 0x5432), one);
+        const uint32_t bb = n0 | n1 << 2 | n2 << 4 | n3 << 6;
+        const unsigned long long lo = (unsigned long long)v.y << 32 | v.x, hi = (unsigned long long)v.w << 32 | v.z;
+        for (uint32_t st = ((bb | bb >> 15) & 0xFFu) | 1u; st;) {
+            const int a = __ffs(st) - 1;
+            st &= st - 1;
+            const int len = (st ? __ffs(st) - 1 : 8) - a;
+            const uint32_t raw = (uint32_t)((a < 4 ? lo >> (16 * a) : hi >> (16 * (a - 4))) & 0xFFFFu);
+            if (raw > VF_VOXEL_FREE) {
+                occ += len;
+                add(raw & 0x7FFFu, (uint32_t)len);
             }
         }
     };
-    const int lane = threadIdx.x & 31;
+    uint32_t run_raw = 0, run = 0;  // the lane's current run: `run` cells holding the word run_raw (> FREE)
     const size_t span = 32 * kHistBatch;
     const size_t nwarps = (size_t)gridDim.x * (blockDim.x / 32);
     for (size_t base = ((size_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32) * span; base < nvec; base += nwarps * span) {
         uint4 v[kHistBatch];
+        const size_t i0 = base + (size_t)lane * kHistBatch;
 #pragma unroll
-        for (int k = 0; k < kHistBatch; ++k) {
-            const size_t i = base + k * 32 + lane;
-            v[k] = i < nvec ? vf_ldg_stream(g4 + i) : make_uint4(0, 0, 0, 0);  // EMPTY counts nowhere
-        }
+        for (int k = 0; k < kHistBatch; ++k) v[k] = i0 + k < nvec ? g4[i0 + k] : make_uint4(0, 0, 0, 0);  // EMPTY counts nowhere
         if (UNMASK) {
 #pragma unroll
-            for (int k = 0; k < kHistBatch; ++k) {
+            for (int k = 0; k < kHistBatch; ++k)
                 if ((v[k].x | v[k].y | v[k].z | v[k].w) & 0x80008000u)  // out-of-range vectors were loaded as zeros
-                    vf_stg_stream(g4 + base + k * 32 + lane, make_uint4(v[k].x & 0x7FFF7FFFu, v[k].y & 0x7FFF7FFFu, v[k].z & 0x7FFF7FFFu, v[k].w & 0x7FFF7FFFu));
-            }
+                    g4[i0 + k] = make_uint4(v[k].x & 0x7FFF7FFFu, v[k].y & 0x7FFF7FFFu, v[k].z & 0x7FFF7FFFu, v[k].w & 0x7FFF7FFFu);
         }
 #pragma unroll
         for (int k = 0; k < kHistBatch; ++k) {
             const uint32_t first = v[k].x & 0xFFFFu;
-#ifdef VF_HIST_WARP
-            // experimental (-DVF_HIST_WARP): lanes whose vector holds one label are counted by the warp, one shared atomic per distinct label
-            // (a leader is elected per label with a ballot; one or two rounds inside a fragment), instead of every lane keeping a run and
-            // the warp diverging on each lane's flush.  Vectors that straddle a label change fall through to the run path below.
             const bool uni = v[k].x == first * 0x10001u && v[k].y == v[k].x && v[k].z == v[k].x && v[k].w == v[k].x;
-            const bool counted = uni && first > VF_VOXEL_FREE;
-            const uint32_t key = first & 0x7FFFu;
-            for (unsigned rest = __ballot_sync(kFull, counted); rest;) {
-                const uint32_t lead = __shfl_sync(kFull, key, __ffs(rest) - 1);
-                const unsigned same = __ballot_sync(kFull, counted && key == lead);
-                if (lane == __ffs(rest) - 1) add(lead, 8u * (uint32_t)__popc(same));
-                rest &= ~same;
-            }
-            if (counted) occ += 8;
-            if (uni) continue;
-            {
-#else
-            if (v[k].x == first * 0x10001u && v[k].y == v[k].x && v[k].z == v[k].x && v[k].w == v[k].x) {
-                take(first, 8);
-            } else {
-#endif
-                // runs of equal cells inside the vector (a fragment border: usually two): "differs from its predecessor" on packed
-                // lanes, gathered into a byte whose set bits are the run starts
-                const uint32_t one = 0x00010001u;
-                const uint32_t n0 = __vminu2(v[k].x ^ __byte_perm(v[k].x, 0, 0x1010), one), n1 = __vminu2(v[k].y ^ __byte_perm(v[k].x, v[k].y, 0x5432), one);
-                const uint32_t n2 = __vminu2(v[k].z ^ __byte_perm(v[k].y, v[k].z, 0x5432), one), n3 = __vminu2(v[k].w ^ __byte_perm(v[k].z, v[k].w, 0x5432), one);
-                const uint32_t b = n0 | n1 << 2 | n2 << 4 | n3 << 6;
-                const uint32_t starts = ((b | b >> 15) & 0xFFu) | 1u;
-                if (__popc(starts) == 2) {  // one label change inside the vector: the common case at a fragment border
-                    const int k8 = __ffs(starts & ~1u) - 1;
-                    take(first, (uint32_t)k8);
-                    take(v[k].w >> 16, (uint32_t)(8 - k8));
+            if (uni && first > VF_VOXEL_FREE) {
+                if (first == run_raw) {
+                    run += 8;
                 } else {
-                    const unsigned long long lo = (unsigned long long)v[k].y << 32 | v[k].x, hi = (unsigned long long)v[k].w << 32 | v[k].z;
-                    for (uint32_t st = starts; st;) {
-                        const int i = __ffs(st) - 1;
-                        st &= st - 1;
-                        const int end = st ? __ffs(st) - 1 : 8;
-                        const uint32_t raw = (uint32_t)((i < 4 ? lo >> (16 * i) : hi >> (16 * (i - 4))) & 0xFFFFu);
-                        take(raw, (uint32_t)(end - i));
-                    }
+                    if (run) occ += run, add(run_raw & 0x7FFFu, run);
+                    run_raw = first, run = 8;
                 }
             }
+            const unsigned m = __ballot_sync(kFull, !uni);
+            if (m) {
+                if (!uni) q[qn + __popc(m & ((1u << lane) - 1u))] = v[k];
+                qn += __popc(m);
+            }
+        }
+        __syncwarp();
+        while (qn >= 32) {
+            qn -= 32;
+            count_runs(q[qn + lane]);
+            __syncwarp();
         }
     }
+    if (lane < qn) count_runs(q[lane]);
     if (blockIdx.x == 0 && threadIdx.x < n % 8) {
         const uint16_t raw = grid[nvec * 8 + threadIdx.x];
-        take(raw, 1);
+        if (raw > VF_VOXEL_FREE) occ += 1, add(raw & 0x7FFFu, 1u);
         if (UNMASK && (raw & 0x8000u)) grid[nvec * 8 + threadIdx.x] = raw & 0x7FFFu;
     }
-    if (run) add(run_label, run);
+    if (run) occ += run, add(run_raw & 0x7FFFu, run);
     occ = __reduce_add_sync(kFull, occ);
-    if ((threadIdx.x & 31) == 0 && occ) atomicAdd(occupied, (unsigned long long)occ);
+    if (lane == 0 && occ) atomicAdd(occupied, (unsigned long long)occ);
     __syncthreads();
     for (int i = threadIdx.x; i < kSmemBins; i += blockDim.x)
         if (bins[i]) atomicAdd(&counts[i], bins[i]);
