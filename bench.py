@@ -498,6 +498,8 @@ def run_cuda(args):
         out["batch"] = {"metric": "models/s batch voxelize+fragment", "value": bm / bdt, "unit": "models/s", "meshes": bm, "jobs_per_gpu": jobs,
                         "fragmentations_per_s": bm * 10 / bdt, "scaling": "weak", "host_cores": host_cores(),
                         "host_cpu_s_per_model_rank0": LAST_BATCH_INFO.get("host_cpu_s_per_model"),
+                        "host_waits_per_fragmentation": LAST_BATCH_INFO.get("host_waits_per_fragmentation"),
+                        "launches_per_fragmentation": LAST_BATCH_INFO.get("launches_per_fragmentation"),
                         "workload": f"cfg4-batch: {bm} synthetic vessels ({npool} distinct shapes on this rank) x 10 fragmentations at 256-max, FLOOD CHEBYSHEV, "
                                     "nf 2..10, 2*nf extra seeds, mesh m -> rank m mod N, RNG seed 80 + m"}
     if world >= 2 and not args.no_slab:
@@ -878,6 +880,7 @@ def batch_measure(rank, local_rank, world, dist, meshes, warmup, jobs, mesh_pool
             t.join()
 
     run(my[: max(warmup, jobs)])
+    waits0, launches0 = sum(w[0].host_waits for w in workers), sum(w[0].kernel_launches for w in workers)
     checksums[:] = [0] * jobs  # the checksum covers the timed pass only: it must not depend on `jobs` or N
     if dist is not None:
         dist.barrier()
@@ -887,6 +890,8 @@ def batch_measure(rank, local_rank, world, dist, meshes, warmup, jobs, mesh_pool
     dt = time.perf_counter() - t0
     # host CPU time of this rank (all threads) per model of the timed pass: what a batch producer pays in host cores
     LAST_BATCH_INFO["host_cpu_s_per_model"] = (time.process_time() - c0) / max(1, len(my))
+    LAST_BATCH_INFO["host_waits_per_fragmentation"] = (sum(w[0].host_waits for w in workers) - waits0) / max(1, 10 * len(my))
+    LAST_BATCH_INFO["launches_per_fragmentation"] = (sum(w[0].kernel_launches for w in workers) - launches0) / max(1, 10 * len(my))
     if dist is not None:
         tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)

@@ -132,6 +132,7 @@ vf_status vf_ctx_set_flood_mode(vf_ctx* ctx, int ctas_per_sm);
 vf_status vf_ctx_set_c1_mode(vf_ctx* ctx, int mode);
 void*     vf_ctx_stream(vf_ctx* ctx);                                    /* the cudaStream_t every call of this context is issued on */
 uint64_t  vf_ctx_kernel_launches(vf_ctx* ctx);                           /* kernels launched by this context so far (bench "gpu_launches") */
+uint64_t  vf_ctx_host_waits(vf_ctx* ctx);                                /* times a call of this context made the host wait for the stream so far */
 /* CUDA-event timing on the context's stream (ResourceTracker's role, SRC/Utilities/ResourceTracker.cpp:58-72) */
 vf_status vf_ctx_timer_start(vf_ctx* ctx);
 vf_status vf_ctx_timer_stop(vf_ctx* ctx, float* elapsed_ms);             /* synchronises on the stop event */

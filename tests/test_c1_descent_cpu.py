@@ -1,5 +1,5 @@
-"""The "descent certificate" formulation of C1 that csrc/c1_descent.cu implements (experimental, VF_C1_DESCENT=1), validated as an ALGORITHM
-on the CPU: tools/c1_descent_prototype.py against the oracle's removeIsolatedRegionsCPU restatement (NaiveFracturer.cpp:111-150)."""
+"""The "descent certificate" formulation of C1 that csrc/c1_descent.cu implements (the default path of vf_remove_isolated_regions), validated as an
+ALGORITHM on the CPU: tools/c1_descent_prototype.py against the oracle's removeIsolatedRegionsCPU restatement (NaiveFracturer.cpp:111-150)."""
 import os
 import sys
 

@@ -73,6 +73,7 @@ SIGNATURES = {
     "vf_ctx_set_flood_mode": (C.c_int, [_vp, C.c_int]),
     "vf_ctx_stream": (_vp, [_vp]),
     "vf_ctx_kernel_launches": (C.c_uint64, [_vp]),
+    "vf_ctx_host_waits": (C.c_uint64, [_vp]),
     "vf_ctx_timer_start": (C.c_int, [_vp]),
     "vf_ctx_timer_stop": (C.c_int, [_vp, _f32p]),
     "vf_rng_seed": (C.c_int, [_vp, _u32]),

@@ -141,6 +141,11 @@ class Context:
         return self._lib.vf_ctx_stream(self._h) or 0
 
     @property
+    def host_waits(self) -> int:
+        """times a call of this context made the host wait for the stream so far"""
+        return int(self._lib.vf_ctx_host_waits(self._h))
+
+    @property
     def kernel_launches(self) -> int:
         return int(self._lib.vf_ctx_kernel_launches(self._h))
 

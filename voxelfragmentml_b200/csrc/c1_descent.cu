@@ -180,11 +180,13 @@ __global__ void __launch_bounds__(kCertWarps * 32) certificate_kernel(uint16_t* 
             if (abs(x - (int)p.x) + abs(y - (int)p.y) + abs(zc - (int)p.z) == 1) continue;  // entered from the start itself
             if (zc > p.z && a == 0 && prev_last == L) continue;
             if (zc < p.z && b == 7 && next_first == L) continue;
-            // y / x neighbour one step closer to the seed (between the cell and the seed: inside the grid); both loads in flight
+            // y / x neighbour one step closer to the seed (between the cell and the seed: inside the grid).  The y neighbour lives in a row this
+            // warp has just streamed (an L2 hit); the x neighbour is a plane away — a 32-byte sector from DRAM for 2 bytes — and is only
+            // looked at when y does not settle it
             const uint32_t u = base + (uint32_t)(zc - z0);
-            const uint32_t ny = y != p.y ? grid[y > p.y ? u - Zu : u + Zu] : 0u;
-            const uint32_t nx = x != p.x ? grid[x > p.x ? u - YZ : u + YZ] : 0u;
-            if (ny != L && nx != L) append_f(u, list, ctl);
+            if (y != p.y && grid[y > p.y ? u - Zu : u + Zu] == L) continue;
+            if (x != p.x && grid[x > p.x ? u - YZ : u + YZ] == L) continue;
+            append_f(u, list, ctl);
         }
         if (has_free) {
             // dropped: the reference rebuilds the grid from an all-EMPTY one.  Neighbours may read this chunk while it is rewritten:

@@ -260,24 +260,6 @@ __global__ void __launch_bounds__(256) ccl_tile_kernel(const uint16_t* __restric
         }
         __syncthreads();
         // (b2) flatten, so that the finds of the plane-to-plane unions below start one step from a root
-#ifdef VF_CCL_JUMP
-        // experimental (-DVF_CCL_JUMP): (b1) links rows of one x-plane only — 16 consecutive lanes of one warp — so four rounds of pointer
-        // jumping inside the warp halve every chain of up to 16 links down to one, in a fixed number of shared accesses per run start,
-        // instead of every lane walking its chain while the warp waits for the longest.  Longer trees (serpentine components) are only
-        // shortened; the finds below do not need flat trees.
-        for (int jump = 0; jump < 4; ++jump) {
-            unsigned st = Sm & Am;
-            while (st) {
-                const int z = __ffs(st) - 1;
-                st &= st - 1;
-                volatile uint32_t* vp = par;
-                const uint32_t p = vp[slot(r * LZ + z)];
-                const uint32_t pp = vp[slot(p)];
-                if (pp != p) vp[slot(r * LZ + z)] = pp;  // an ancestor: safe against concurrent finds
-            }
-            __syncwarp();
-        }
-#else
         {
             unsigned st = Sm & Am;
             while (st) {
@@ -286,7 +268,6 @@ __global__ void __launch_bounds__(256) ccl_tile_kernel(const uint16_t* __restric
                 par[slot(r * LZ + z)] = find_local(par, r * LZ + z);  // writes an ancestor: safe against concurrent finds
             }
         }
-#endif
         __syncthreads();
         // (b3) plane x against plane x-1
         if (Am) {

@@ -199,6 +199,7 @@ extern "C" vf_status vf_ctx_synchronize(vf_ctx* ctx)
 
 extern "C" void* vf_ctx_stream(vf_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 extern "C" uint64_t vf_ctx_kernel_launches(vf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" uint64_t vf_ctx_host_waits(vf_ctx* ctx) { return ctx ? ctx->host_waits : 0; }
 
 extern "C" vf_status vf_ctx_timer_start(vf_ctx* ctx)
 {

@@ -90,6 +90,7 @@ struct vf_ctx {
     int num_sms = 148;
     int smem_optin = 0;
     uint64_t launches = 0;
+    uint64_t host_waits = 0;  // times the host waited for the stream (vf_sync): what a producer with few cores pays per call
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     cudaEvent_t ev_block = nullptr;  // cudaEventBlockingSync: waits that give the host core back (vf_ctx_set_blocking_sync)
     bool blocking_sync = false;
@@ -133,6 +134,7 @@ struct vf_grid {
 // the latency-bound rounds of several jobs) asks for blocking waits, which sleep on an event instead of burning the core.
 inline cudaError_t vf_sync(vf_ctx* c)
 {
+    ++c->host_waits;
     if (!c->blocking_sync) return cudaStreamSynchronize(c->stream);
     const cudaError_t e = cudaEventRecord(c->ev_block, c->stream);
     return e != cudaSuccess ? e : cudaEventSynchronize(c->ev_block);
