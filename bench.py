@@ -295,8 +295,18 @@ def run_cuda(args):
     dom_launches = max(1, int(stage_launches.get(dom, 1)))
     dom_bytes = stage_roofline[dom]["algorithmic_bytes"] / dom_launches
     dom_ms = stage_ms[dom] / dom_launches
-    dom_kernels = {"naive": "naive_brick_kernel<EUCLIDEAN,8>", "remove_isolated": "ccl_* (tile + border + select)", "erode": "stencil_fast_kernel<OP,TMA>",
+    dom_kernels = {"naive": "naive_brick_kernel<EUCLIDEAN,8>", "remove_isolated": "vfc1::certificate_kernel (+ plant / resolve list work)",
+                   "erode": "stencil_fast_kernel<DETECT|ERODE3|SWEEP,TMA> (3 full passes) + erode_sparse_kernel (iterations 2..3)",
                    "histogram_undo_mask": "histogram_kernel<UNMASK>"}
+    # measured DRAM bytes of the dominant stage's kernels (one ncu --set full capture, profiles/kernel_traffic.json), per launch like `achieved`
+    dom_traffic = None
+    try:
+        kt = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))
+        pick = {"naive": ["naive_brick"], "remove_isolated": ["vfc1::"], "erode": ["stencil_fast", "erode_sparse", "erode_sparse"], "histogram_undo_mask": ["histogram"]}[dom]
+        tot_b = sum(v for pat in pick for k, v in kt.items() if pat in k)
+        dom_traffic = tot_b / dom_launches if (n == 512 and tot_b > 0) else None
+    except Exception:
+        dom_traffic = None
     step_bytes = float(sum(v["algorithmic_bytes"] for v in stage_roofline.values()))
 
     # ---- the sparse variant BASELINE.md lists as cfg3's primary input: the ~20k-triangle synthetic vessel voxelized at 512-max (352 x 512 x 352),
@@ -464,7 +474,7 @@ def run_cuda(args):
         "stage_roofline": stage_roofline,
         "fragmentation_only": {"value": world * N / naive_t / 1e9, "unit": "Gvoxels/s", "note": "F1 operator alone (NaiveFracturer::build without cleanup), CUDA events"},
         "roofline": {"kernel": dom_kernels.get(dom, dom), "stage": dom, "bound": "hbm", "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes": dom_bytes,
+                     "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": dom_traffic, "peak_source": peak_src, "algorithmic_bytes": dom_bytes,
                      "kernel_ms": dom_ms, "launches_per_step": dom_launches, "share_of_step": stage_ms[dom] / sum(stage_ms.values())},
         "roofline_f1": {"kernel": "naive_brick_kernel<EUCLIDEAN,8>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": algo_bytes,

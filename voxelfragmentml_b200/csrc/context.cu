@@ -169,12 +169,17 @@ vf_status vf_scratch_reserve(vf_ctx* ctx, VfScratch& s, size_t bytes)
     if (s.bytes >= bytes) return VF_OK;
     if (&s == &ctx->small) ctx->seed_shadow.clear();   // the arena moves: what the shadows describe is gone
     if (&s == &ctx->noise) ctx->noise_shadow.clear();
+    const size_t old_bytes = s.bytes;
     if (s.ptr) {
         VF_CUDA(vf_sync(ctx));
         VF_CUDA(cudaFree(s.ptr));
         s.ptr = nullptr;
         s.bytes = 0;
     }
+    // An arena that has to move grows by at least half: cudaFree / cudaMalloc synchronise the whole device, and a producer that works through
+    // models of slightly different sizes (tile counts, triangle bins) would otherwise pay that once per new maximum, stalling every other
+    // context on the GPU each time.
+    if (old_bytes) bytes = std::max(bytes, old_bytes + old_bytes / 2);
     bytes = (bytes + 255) & ~(size_t)255;
     VF_CUDA(cudaMalloc(&s.ptr, bytes));
     s.bytes = bytes;
@@ -187,6 +192,14 @@ extern "C" vf_status vf_ctx_reserve(vf_ctx* ctx, uint32_t X, uint32_t Y, uint32_
     const size_t n = (size_t)X * Y * Z;
     VF_TRY(vf_scratch_reserve(ctx, ctx->keys, n * 4));
     VF_TRY(vf_scratch_reserve(ctx, ctx->grid2, n * 2));
+    // the smaller arenas a fragmentation of a grid of this size touches, so that no call has to move one later: tile worklists of the flood
+    // (16 x 16 x 32 tiles: 14 B + 1 KiB of pending masks each), seeds / counters / histogram bins, brick bins of the voxelizer (4 x 4 x 32
+    // bricks: 8 B each, plus room for a 64k-triangle mesh and its brick lists)
+    const size_t nt = (size_t)((X + 15) / 16) * ((Y + 15) / 16) * ((Z + 31) / 32);
+    VF_TRY(vf_scratch_reserve(ctx, ctx->tiles, nt * (16 + 1024) + 4096));
+    VF_TRY(vf_scratch_reserve(ctx, ctx->small, 1 << 20));
+    const size_t nb = (size_t)((X + 3) / 4) * ((Y + 3) / 4) * ((Z + 31) / 32);
+    VF_TRY(vf_scratch_reserve(ctx, ctx->mesh, nb * 8 + ((size_t)65536 * (24 + 64)) + 4096));
     return VF_OK;
 }
 
