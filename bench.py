@@ -409,6 +409,8 @@ def run_cuda(args):
 
     pipe_steps = max(6, 2 * args.steps)
     run_pipelined(3)
+    if world > 1:
+        dist.barrier()
     e2e_runs = []  # three passes of pipe_steps steps each; the median pass is reported (host-side DMA scheduling varies from pass to pass)
     for _ in range(3):
         torch.cuda.synchronize()
@@ -443,7 +445,14 @@ def run_cuda(args):
         for t in ths:
             t.join()
 
+    # producers with few cores per GPU (the 8-GPU box: 32 hardware threads for 8 ranks x 3 producer threads) wait on blocking events instead of
+    # spinning, as batch generation does (vf_ctx_set_blocking_sync)
+    e2e_block = args.e2e_blocking == "on" or (args.e2e_blocking == "auto" and host_cores() // max(1, world) < 8)
+    for c, _, _ in slots:
+        c.setBlockingSync(e2e_block)
     run_compact(1)
+    if world > 1:
+        dist.barrier()  # all ranks measure the same phase at the same time (the full-grid passes of a late rank would share the host's DMA with them)
     compact_runs = []
     per_thread = max(2, (2 * args.steps + 2) // 3)
     for _ in range(3):
@@ -452,6 +461,8 @@ def run_cuda(args):
         run_compact(per_thread)
         compact_runs.append((time.perf_counter() - t0) / (3 * per_thread))
     compact_s = sorted(compact_runs)[1]
+    for c, _, _ in slots:
+        c.setBlockingSync(False)
     # parity of the compact path: the decoded stream equals the full-grid download of the same step
     compact_ok = None
     if rank == 0:
@@ -489,7 +500,8 @@ def run_cuda(args):
                 "mode": "compact: input = 1 occupancy bit per cell from pinned memory (vf_grid_upload_bits, expanded on the device), result = the `.rle` "
                         "byte stream (runs found on the device, vf_grid_encode_rle) + the histogram; three host threads with one context each run whole "
                         "steps, so the copies of one step overlap the kernels of another; seeds and noise table are sent once (unchanged tables are skipped)",
-                "passes_ms_per_step": [t * 1e3 for t in compact_runs], "rle_stream_equals_grid": compact_ok,
+                "passes_ms_per_step": [t * 1e3 for t in compact_runs], "rle_stream_equals_grid": compact_ok, "producer_threads": 3,
+                "host_waits": "blocking events" if e2e_block else "spinning", "host_cores_per_rank": host_cores() // max(1, world),
                 "full_grid": {"value": world * N / e2e_s / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": 2 * N, "d2h_bytes_per_step": 2 * N + 4 * 32768,
                               "ms_per_step": e2e_s * 1e3, "steps": pipe_steps,
                               "mode": "3 grids in rotation: upload / kernels / download of consecutive steps overlap; every step copies its own 16-bit input "
@@ -1033,6 +1045,7 @@ def main():
     ap.add_argument("--jobs", type=int, default=0, help="batch workload: concurrent contexts (streams + host threads) per GPU; 0 = 16, or 8 with 8..15 host cores per rank")
     ap.add_argument("--blocking-sync", default="auto", choices=["auto", "on", "off"],
                     help="batch workload: contexts wait on blocking events instead of spinning (auto: when jobs x ranks exceed the host cores)")
+    ap.add_argument("--e2e-blocking", default="auto", choices=["auto", "on", "off"], help="default workload: the end-to-end producer threads wait on blocking events (auto: fewer than 8 host cores per rank)")
     ap.add_argument("--no-vessel", action="store_true", help="default workload: skip the sparse cfg3-vessel sub-line reported under \"vessel\"")
     ap.add_argument("--no-batch", action="store_true", help="default workload: skip the short cfg4 batch measurement reported under \"batch\"")
     ap.add_argument("--mesh-pool", type=int, default=8, help="batch workload: distinct synthetic shapes generated up front")
