@@ -378,8 +378,9 @@ def run_cuda(args):
         ctx.synchronize()
     serial_s = (time.perf_counter() - t0) / e2e_steps
 
+    NPROD = 4  # producer threads of the compact end-to-end path (the full-grid rotation uses the first three slots)
     slots = []
-    for k in range(3):
+    for k in range(NPROD):
         c = ctx if k == 0 else vf.Context(local_rank)
         g = grid if k == 0 else vf.RegularGrid(c, dims)
         c.reserve(dims)
@@ -425,7 +426,7 @@ def run_cuda(args):
     import threading
 
     h_bits = torch.from_numpy(np.packbits(np.ones(N, np.uint8), bitorder="little")).pin_memory()
-    rle_bytes = [0, 0, 0]
+    rle_bytes = [0] * NPROD
 
     def compact_steps(k, nsteps):
         c, g, _ = slots[k]
@@ -439,7 +440,7 @@ def run_cuda(args):
             rle_bytes[k] = len(g.encodeRLE())
 
     def run_compact(per_thread):
-        ths = [threading.Thread(target=compact_steps, args=(k, per_thread)) for k in range(3)]
+        ths = [threading.Thread(target=compact_steps, args=(k, per_thread)) for k in range(NPROD)]
         for t in ths:
             t.start()
         for t in ths:
@@ -454,12 +455,12 @@ def run_cuda(args):
     if world > 1:
         dist.barrier()  # all ranks measure the same phase at the same time (the full-grid passes of a late rank would share the host's DMA with them)
     compact_runs = []
-    per_thread = max(2, (2 * args.steps + 2) // 3)
+    per_thread = max(2, (2 * args.steps + NPROD - 1) // NPROD)
     for _ in range(3):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         run_compact(per_thread)
-        compact_runs.append((time.perf_counter() - t0) / (3 * per_thread))
+        compact_runs.append((time.perf_counter() - t0) / (NPROD * per_thread))
     compact_s = sorted(compact_runs)[1]
     for c, _, _ in slots:
         c.setBlockingSync(False)
@@ -496,11 +497,11 @@ def run_cuda(args):
         # headline end-to-end figure: compact host buffers (what a producer that keeps occupancy as bits and consumes `.rle` moves);
         # "full_grid" is the same step with 16-bit grids both ways, as RegularGrid::updateSSBO / updateGrid move them
         "e2e": {"value": world * N / compact_s / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": int(h_bits.numel()),
-                "d2h_bytes_per_step": int(max(rle_bytes)) + 4 * 32768 + 8, "ms_per_step": compact_s * 1e3, "steps": 3 * per_thread,
+                "d2h_bytes_per_step": int(max(rle_bytes)) + 4 * 32768 + 8, "ms_per_step": compact_s * 1e3, "steps": NPROD * per_thread,
                 "mode": "compact: input = 1 occupancy bit per cell from pinned memory (vf_grid_upload_bits, expanded on the device), result = the `.rle` "
-                        "byte stream (runs found on the device, vf_grid_encode_rle) + the histogram; three host threads with one context each run whole "
+                        "byte stream (runs found on the device, vf_grid_encode_rle) + the histogram; four host threads with one context each run whole "
                         "steps, so the copies of one step overlap the kernels of another; seeds and noise table are sent once (unchanged tables are skipped)",
-                "passes_ms_per_step": [t * 1e3 for t in compact_runs], "rle_stream_equals_grid": compact_ok, "producer_threads": 3,
+                "passes_ms_per_step": [t * 1e3 for t in compact_runs], "rle_stream_equals_grid": compact_ok, "producer_threads": NPROD,
                 "host_waits": "blocking events" if e2e_block else "spinning", "host_cores_per_rank": host_cores() // max(1, world),
                 "full_grid": {"value": world * N / e2e_s / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": 2 * N, "d2h_bytes_per_step": 2 * N + 4 * 32768,
                               "ms_per_step": e2e_s * 1e3, "steps": pipe_steps,

@@ -397,33 +397,40 @@ static uint64_t qstack_from_columns(const std::vector<uint64_t>& first, const st
 // ---- .rle on the device -------------------------------------------------------------------------------------------------
 // exportRLE (RegularGrid.cpp:672-714) walks the host copy of the grid cell by cell; with the grid resident in HBM that costs a
 // 2 B/voxel download per export.  Here the runs are found where the grid lives: a cell starts a run iff it
-// differs from its predecessor in the x-major array (cell 0 always does), so   count starts per 2048-cell tile -> exclusive scan
+// differs from its predecessor in the x-major array (cell 0 always does), so   count starts per 8192-cell tile -> exclusive scan
 // of the tile counts -> every start writes {cell index, value} at its rank -> repetitions = next start - this start, packed
 // into the file's 6-byte records {uint16 value, uint32 repetitions}.  Only the finished byte stream (12 + 6 R bytes, R = runs)
 // crosses PCIe.  Reads 2 x 2 B/voxel, writes 12 B/run.
 namespace {
 
-constexpr int kRleThreads = 256, kRleCells = 8, kRleTile = kRleThreads * kRleCells;
+constexpr int kRleThreads = 256, kRleCells = 32, kRleTile = kRleThreads * kRleCells;  // a thread owns 32 consecutive cells (four 128-bit loads)
 
-// bit j of the result = cell (first + j) starts a run; cells[] receives the 8 values (cells past the end repeat the last one)
-__device__ __forceinline__ uint32_t rle_flags(const uint16_t* __restrict__ grid, uint64_t n, uint64_t first, uint16_t cells[kRleCells])
+// bit j of the result = cell (first + j) starts a run; w[] receives the 32 values, two per word (cells past the end read as the last valid one)
+__device__ __forceinline__ uint32_t rle_flags(const uint16_t* __restrict__ grid, uint64_t n, uint64_t first, uint32_t w[kRleCells / 2])
 {
     if (first >= n) return 0;
-    uint16_t prev = first ? grid[first - 1] : (uint16_t)~grid[0];
+    uint32_t prev = first ? grid[first - 1] : (uint32_t)(uint16_t)~grid[0];
     if (first + kRleCells <= n) {
-        const uint4 v = *reinterpret_cast<const uint4*>(grid + first);  // first % 8 == 0 and the grid is 16-byte aligned
-        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+        const uint4* p = reinterpret_cast<const uint4*>(grid + first);  // first % 32 == 0 and the grid is 16-byte aligned
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cells[2 * j] = (uint16_t)w[j], cells[2 * j + 1] = (uint16_t)(w[j] >> 16);
+        for (int k = 0; k < kRleCells / 8; ++k) {
+            const uint4 v = p[k];
+            w[4 * k] = v.x, w[4 * k + 1] = v.y, w[4 * k + 2] = v.z, w[4 * k + 3] = v.w;
+        }
     } else {
 #pragma unroll
-        for (int j = 0; j < kRleCells; ++j) cells[j] = first + j < n ? grid[first + j] : (uint16_t)0;
+        for (int j = 0; j < kRleCells / 2; ++j) {
+            const uint64_t c = first + 2 * j;
+            const uint32_t lo = c < n ? grid[c] : 0u, hi = c + 1 < n ? grid[c + 1] : 0u;
+            w[j] = lo | hi << 16;
+        }
     }
     uint32_t flags = 0;
 #pragma unroll
     for (int j = 0; j < kRleCells; ++j) {
-        if (first + j < n && cells[j] != prev) flags |= 1u << j;
-        prev = cells[j];
+        const uint32_t cell = (w[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
+        if (first + j < n && cell != prev) flags |= 1u << j;
+        prev = cell;
     }
     return flags;
 }
@@ -431,9 +438,9 @@ __device__ __forceinline__ uint32_t rle_flags(const uint16_t* __restrict__ grid,
 __global__ void __launch_bounds__(kRleThreads) rle_count_kernel(const uint16_t* __restrict__ grid, uint64_t n, uint32_t* __restrict__ counts)
 {
     __shared__ uint32_t warp_sums[kRleThreads / 32];
-    uint16_t cells[kRleCells];
+    uint32_t w[kRleCells / 2];
     const uint64_t first = ((uint64_t)blockIdx.x * kRleThreads + threadIdx.x) * kRleCells;
-    uint32_t c = __popc(rle_flags(grid, n, first, cells));
+    uint32_t c = __popc(rle_flags(grid, n, first, w));
 #pragma unroll
     for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
     if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = c;
@@ -441,22 +448,25 @@ __global__ void __launch_bounds__(kRleThreads) rle_count_kernel(const uint16_t* 
     if (threadIdx.x == 0) {
         uint32_t t = 0;
 #pragma unroll
-        for (int w = 0; w < kRleThreads / 32; ++w) t += warp_sums[w];
+        for (int k = 0; k < kRleThreads / 32; ++k) t += warp_sums[k];
         counts[blockIdx.x] = t;
     }
 }
 
-// exclusive scan of the tile counts by one CTA; *total = number of runs
+// exclusive scan of the tile counts by one CTA, four counts per thread and step; *total = number of runs
 __global__ void __launch_bounds__(1024) rle_scan_kernel(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets, uint32_t n, uint32_t* __restrict__ total)
 {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (uint32_t base = 0; base < n; base += 1024) {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t v = i < n ? counts[i] : 0;
-        uint32_t s = v;
+    for (uint32_t base = 0; base < n; base += 4096) {
+        const uint32_t i = base + 4 * threadIdx.x;
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = i + k < n ? counts[i + k] : 0;
+        const uint32_t mine = v[0] + v[1] + v[2] + v[3];
+        uint32_t s = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, s, o);
@@ -474,10 +484,14 @@ __global__ void __launch_bounds__(1024) rle_scan_kernel(const uint32_t* __restri
             warp_sums[threadIdx.x] = w;
         }
         __syncthreads();
-        const uint32_t before = carry + (threadIdx.x >= 32 ? warp_sums[(threadIdx.x >> 5) - 1] : 0) + s - v;
-        if (i < n) offsets[i] = before;
+        uint32_t before = carry + (threadIdx.x >= 32 ? warp_sums[(threadIdx.x >> 5) - 1] : 0) + s - mine;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i + k < n) offsets[i + k] = before;
+            before += v[k];
+        }
         __syncthreads();
-        if (threadIdx.x == 1023) carry = before + v;
+        if (threadIdx.x == 1023) carry = before;
         __syncthreads();
     }
     if (threadIdx.x == 0) *total = carry;
@@ -487,9 +501,9 @@ __global__ void __launch_bounds__(kRleThreads) rle_emit_kernel(const uint16_t* _
                                                                 uint32_t* __restrict__ starts, uint16_t* __restrict__ values)
 {
     __shared__ uint32_t warp_sums[kRleThreads / 32];
-    uint16_t cells[kRleCells];
+    uint32_t w[kRleCells / 2];
     const uint64_t first = ((uint64_t)blockIdx.x * kRleThreads + threadIdx.x) * kRleCells;
-    const uint32_t flags = rle_flags(grid, n, first, cells);
+    const uint32_t flags = rle_flags(grid, n, first, w);
     const uint32_t mine = __popc(flags);
     uint32_t s = mine;
 #pragma unroll
@@ -500,14 +514,15 @@ __global__ void __launch_bounds__(kRleThreads) rle_emit_kernel(const uint16_t* _
     if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = s;
     __syncthreads();
     uint32_t rank = offsets[blockIdx.x] + s - mine;
-    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) rank += warp_sums[w];
-    uint32_t f = flags;
-    while (f) {
-        const int j = __ffs(f) - 1;
-        f &= f - 1;
-        starts[rank] = (uint32_t)(first + j);
-        values[rank] = cells[j];
-        ++rank;
+    for (int k = 0; k < (int)(threadIdx.x >> 5); ++k) rank += warp_sums[k];
+    if (!flags) return;
+#pragma unroll
+    for (int j = 0; j < kRleCells; ++j) {  // unrolled: the values stay in registers
+        if (flags >> j & 1u) {
+            starts[rank] = (uint32_t)(first + j);
+            values[rank] = (uint16_t)(w[j >> 1] >> ((j & 1) * 16));
+            ++rank;
+        }
     }
 }
 
