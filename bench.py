@@ -749,7 +749,7 @@ def _dist_setup():
     return rank, local_rank, world, dist
 
 
-def slab_measure(rank, local_rank, world, dist, n, nseeds, steps, warmup, native=True):
+def slab_measure(rank, local_rank, world, dist, n, nseeds, steps, warmup, native=True, args_breakdown=False):
     """BASELINE config 5: one n^3 analytic solid, FLOOD MANHATTAN, `nseeds` seeds (15-bit ids), x-slabs over the ranks with key-plane exchange
     over NCCL.  native: the exchange loop runs inside libvoxfrag (C++: grouped ncclSend / ncclRecv + ncclAllReduce on the context's stream,
     vf_flood_slab_run); otherwise the Python loop over torch.distributed.  Labels are bit-exact against the single-address-space oracle
@@ -778,15 +778,20 @@ def slab_measure(rank, local_rank, world, dist, n, nseeds, steps, warmup, native
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         s.start()
+        if args_breakdown:
+            ctx.synchronize()
+        t1 = time.perf_counter()
         if native:
             iters, moved = s.run_native(comm, rank, world)
         elif world > 1:
             iters, moved = slab.run_distributed(s, rank, world, dist)
         else:
             iters, moved = slab.run_local([s])
+        t2 = time.perf_counter()
         s.finalize(download=False)
         ctx.synchronize()
         dt = time.perf_counter() - t0
+        phases = [(t1 - t0) * 1e3, (t2 - t1) * 1e3, (time.perf_counter() - t2) * 1e3]
         maxd = s.max_dist
         s.close()
         if it >= warmup:
@@ -807,18 +812,20 @@ def slab_measure(rank, local_rank, world, dist, n, nseeds, steps, warmup, native
             "workload": f"cfg5-slab: {n}^3 analytic solid vessel, FLOOD MANHATTAN, {nseeds} seeds (15-bit ids), {world} x-slabs, "
                         + ("C++ exchange loop over NCCL inside libvoxfrag (vf_flood_slab_run)" if native else "Python exchange loop over torch.distributed"),
             "exchange_iterations": iters, "halo_bytes_per_rank": moved, "max_geodesic_distance": maxd,
+            "phases_ms_rank0_last_step": {"init_keys_and_seeds": phases[0], "exchange_loop": phases[1], "finalize": phases[2]} if args_breakdown else None,
             # F2's algorithmic bytes: read every label once, write every label once, against the aggregate HBM roofline of the N GPUs
             "roofline_frac_aggregate": 4.0 * N / (ms * 1e-3) / 1e9 / (peak * world)}
 
 
 def run_slab(args):
     rank, local_rank, world, dist = _dist_setup()
-    blk = slab_measure(rank, local_rank, world, dist, args.size, args.seeds, args.steps, args.warmup, native=not args.python_exchange)
+    blk = slab_measure(rank, local_rank, world, dist, args.size, args.seeds, args.steps, args.warmup, native=not args.python_exchange, args_breakdown=True)
     if rank == 0:
         emit_json(json.dumps({
             "metric": blk["metric"], "value": blk["value"], "unit": blk["unit"], "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": blk["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 keys (dist<<15|order)",
-            "data": "synthetic", "config": {k: blk[k] for k in ("workload", "grid", "seeds", "exchange_iterations", "halo_bytes_per_rank", "max_geodesic_distance")},
+            "data": "synthetic", "config": {k: blk[k] for k in ("workload", "grid", "seeds", "exchange_iterations", "halo_bytes_per_rank", "max_geodesic_distance",
+                                                                  "phases_ms_rank0_last_step")},
             "roofline_frac_aggregate": blk["roofline_frac_aggregate"]}))
     if dist is not None:
         dist.destroy_process_group()

@@ -52,3 +52,54 @@ def test_fracture_model_naive_with_extra_seeds(ctx, orc, vessel_grid):
     want = orc.detect_boundaries(want, 1)
     assert np.array_equal(seeds, wseeds) and np.array_equal(g.updateGrid(), want)
     g.close()
+
+
+def _adversarial_seed_lists(orc, lab, seeds, rs):
+    """seed lists the reference code pins through the oracle (tests/test_oracle_vs_ref.py): several seeds per cell, seeds on EMPTY and on
+    foreign-label cells, displaced seeds whose neighbours lie in other tiles / segments"""
+    out = []
+    s3 = np.concatenate([seeds, seeds[:4], seeds[:4]]).astype(np.uint32)  # three seeds on one cell, three labels
+    s3[len(seeds):len(seeds) + 4, 3] = seeds[:4, 3] | 0x100
+    s3[len(seeds) + 4:, 3] = seeds[:4, 3] | 0x200
+    out.append(s3)
+    empty = np.argwhere(lab == 0)
+    if len(empty):
+        e = seeds.copy()
+        e[0, :3] = empty[rs.randint(len(empty))]  # a seed on an EMPTY cell: its label is planted there
+        out.append(e)
+    foreign = seeds.copy()
+    other = np.argwhere(lab == seeds[1, 3])
+    foreign[0, :3] = other[rs.randint(len(other))]  # a seed on a cell another seed labelled
+    out.append(foreign)
+    # copies placed on cells at tile / segment borders (x, y multiples of 16, z multiples of 32 and their predecessors)
+    edge = np.argwhere((lab > 1) & ((np.indices(lab.shape)[0] % 16 >= 15) | (np.indices(lab.shape)[1] % 16 == 0) | (np.indices(lab.shape)[2] % 32 >= 31)))
+    if len(edge) >= 6:
+        pick = edge[rs.choice(len(edge), 6, replace=False)]
+        a = np.concatenate([pick, lab[tuple(pick.T)][:, None]], 1)
+        b = a.copy()
+        b[:, 3] = 0x300 | (2 + np.arange(6))
+        out.append(np.concatenate([seeds, a, b]).astype(np.uint32))  # the later copies displace seeds that own a region across the border
+    return out
+
+
+@pytest.mark.parametrize("c1_mode", [0, 1])
+def test_c1_adversarial_seed_lists(ctx, orc, vessel_grid, c1_mode):
+    from conftest import pick_seeds, random_blob_grid
+
+    rs = np.random.RandomState(7)
+    ctx.setC1Mode(c1_mode)
+    try:
+        cases = [(vessel_grid, pick_seeds(vessel_grid, 9, 5), 0)]
+        cases += [(random_blob_grid((45, 37, 72), 20 + k, fill=0.5 + 0.05 * k, smooth=1), None, k % 3) for k in range(3)]
+        dense = np.ones((48, 40, 64), np.uint16)
+        cases.append((dense, pick_seeds(dense, 12, 2), 1))
+        for grid, seeds, dfunc in cases:
+            if seeds is None:
+                seeds = pick_seeds(grid, 7, 3)
+            lab = orc.naive(grid.copy(), seeds, dfunc)
+            for sl in _adversarial_seed_lists(orc, lab, seeds, rs):
+                want = orc.remove_isolated_regions_cpu(lab.copy(), sl)
+                got = _c1(ctx, lab, sl)
+                assert np.array_equal(got, want), f"mode {c1_mode}: {int((got != want).sum())} cells differ"
+    finally:
+        ctx.setC1Mode(0)
