@@ -679,7 +679,7 @@ def run_reference(args):
         return
     full = args.size
     # bounded sample: a step of the reference's shaders on the host cores takes ~10 s at 256^3 on 8 cores; the grid edge is chosen below so that
-    # the timed steps end within about two and a half minutes.  Throughput per voxel barely depends on the edge (slightly better when smaller).
+    # the timed steps end within about four minutes.  Throughput per voxel barely depends on the edge (slightly better when smaller).
     n = args.cpu_size or 256
     seeds = synth_seeds_dense(n, CFG3["nseeds"], rng_uniform_stream(CFG3["rng_seed"]))
     noise = np.ascontiguousarray(noise_table(CFG3["rng_seed"] + 1000, CFG3["nnoise"]), np.float32)
@@ -692,14 +692,14 @@ def run_reference(args):
 
     # one untimed probe on a small grid sizes the sample
     if not args.cpu_size:
-        pn = 96
+        pn = 128
         pseeds = synth_seeds_dense(pn, CFG3["nseeds"], rng_uniform_stream(CFG3["rng_seed"]))
         seeds_keep, seeds = seeds, pseeds
         t0 = time.perf_counter()
         step(np.ones((pn, pn, pn), np.uint16))
         per_voxel = (time.perf_counter() - t0) / pn**3
         seeds = seeds_keep
-        budget = 150.0 / max(1, args.steps + 1)
+        budget = 240.0 / max(1, args.steps + 1)  # the whole arm ends within about four minutes
         n = int(min(full, max(64, (budget / per_voxel) ** (1.0 / 3.0))) // 32 * 32)
         seeds = synth_seeds_dense(n, CFG3["nseeds"], rng_uniform_stream(CFG3["rng_seed"]))
     step(np.ones((n, n, n), np.uint16))  # warm-up at the sample size
