@@ -63,17 +63,21 @@ __global__ void __launch_bounds__(256) bin_triangles_kernel(const float* __restr
             }
 }
 
-// exclusive scan of the brick counts by one CTA (a few hundred thousand entries at most); also resets the fill cursors
+// exclusive scan of the brick counts by one CTA, four counts per thread and step (a few hundred thousand entries at most); also resets the
+// fill cursors
 __global__ void __launch_bounds__(1024) scan_counts_kernel(uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets, uint32_t n, uint32_t* __restrict__ total)
 {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (uint32_t base = 0; base < n; base += 1024) {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t v = i < n ? counts[i] : 0;
-        uint32_t s = v;
+    for (uint32_t base = 0; base < n; base += 4096) {
+        const uint32_t i = base + 4 * threadIdx.x;
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = i + k < n ? counts[i + k] : 0;
+        const uint32_t mine = v[0] + v[1] + v[2] + v[3];
+        uint32_t s = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t t = __shfl_up_sync(kFull, s, o);
@@ -91,13 +95,17 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(uint32_t* __restrict_
             warp_sums[threadIdx.x] = w;
         }
         __syncthreads();
-        const uint32_t before = carry + (threadIdx.x >= 32 ? warp_sums[(threadIdx.x >> 5) - 1] : 0) + s - v;
-        if (i < n) {
-            offsets[i] = before;
-            counts[i] = 0;  // becomes the fill cursor
+        uint32_t before = carry + (threadIdx.x >= 32 ? warp_sums[(threadIdx.x >> 5) - 1] : 0) + s - mine;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i + k < n) {
+                offsets[i + k] = before;
+                counts[i + k] = 0;  // becomes the fill cursor
+            }
+            before += v[k];
         }
         __syncthreads();
-        if (threadIdx.x == 1023) carry = before + v;
+        if (threadIdx.x == 1023) carry = before;
         __syncthreads();
     }
     if (threadIdx.x == 0) *total = carry;
@@ -130,6 +138,26 @@ __device__ __forceinline__ bool tri_box_sat(const float c[3], const float r[3], 
         e1[q] = v2[q] - v1[q];
         e2[q] = v0[q] - v2[q];
     }
+    // plane / box next (:256-257, planeBoxOverlap :269-294; normal = cross(edge0, edge1)): the test that rejects the voxels of a triangle's
+    // bounding box that lie off its plane — most of them — before the nine edge axes; the verdict is a conjunction, its order is free
+    float n[3];
+    n[0] = e0[1] * e1[2] - e1[1] * e0[2];
+    n[1] = e0[2] * e1[0] - e1[2] * e0[0];
+    n[2] = e0[0] * e1[1] - e1[0] * e0[1];
+    float vmin[3], vmax[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const float v = v0[q];
+        if (n[q] > 0.0f) {
+            vmin[q] = -r[q] - v;
+            vmax[q] = r[q] - v;
+        } else {
+            vmin[q] = r[q] - v;
+            vmax[q] = -r[q] - v;
+        }
+    }
+    if (n[0] * vmin[0] + n[1] * vmin[1] + n[2] * vmin[2] > 0.0f) return false;
+    if (!(n[0] * vmax[0] + n[1] * vmax[1] + n[2] * vmax[2] >= 0.0f)) return false;
 #define VF_AXIS(pa, pb, rad)                              \
     {                                                     \
         const float pa_ = (pa), pb_ = (pb), rad_ = (rad); \
@@ -162,25 +190,7 @@ __device__ __forceinline__ bool tri_box_sat(const float c[3], const float r[3], 
     a = e2[1], b = e2[0];
     VF_AXIS(a * v1[0] - b * v1[1], a * v2[0] - b * v2[1], fy * r[0] + fx * r[1]);
 #undef VF_AXIS
-    // plane / box (:256-257, planeBoxOverlap :269-294); normal = cross(edge0, edge1)
-    float n[3];
-    n[0] = e0[1] * e1[2] - e1[1] * e0[2];
-    n[1] = e0[2] * e1[0] - e1[2] * e0[0];
-    n[2] = e0[0] * e1[1] - e1[0] * e0[1];
-    float vmin[3], vmax[3];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-        const float v = v0[q];
-        if (n[q] > 0.0f) {
-            vmin[q] = -r[q] - v;
-            vmax[q] = r[q] - v;
-        } else {
-            vmin[q] = r[q] - v;
-            vmax[q] = -r[q] - v;
-        }
-    }
-    if (n[0] * vmin[0] + n[1] * vmin[1] + n[2] * vmin[2] > 0.0f) return false;
-    return n[0] * vmax[0] + n[1] * vmax[1] + n[2] * vmax[2] >= 0.0f;
+    return true;
 }
 
 // fminf/fmaxf above pick min/max of two finite values exactly like the reference's `if (a < b)` swap (ties give equal values).
