@@ -427,6 +427,7 @@ def run_cuda(args):
 
     h_bits = torch.from_numpy(np.packbits(np.ones(N, np.uint8), bitorder="little")).pin_memory()
     rle_bytes = [0] * NPROD
+    rle_out = [torch.empty(max(1 << 20, N // 4), dtype=torch.uint8).pin_memory() for _ in range(NPROD)]  # room for N / 24 runs (cfg3: ~1.6 M of 134 M cells)
 
     def compact_steps(k, nsteps):
         c, g, _ = slots[k]
@@ -437,7 +438,8 @@ def run_cuda(args):
             vf.NaiveFracturer.removeIsolatedRegions(g, seeds)
             g.erode(et, es, ei, ep, eth, noise=noise)
             g.countValuesUndoMask()
-            rle_bytes[k] = len(g.encodeRLE())
+            rle_bytes[k] = g.encodeRLE_into(rle_out[k])  # one call: runs found, packed and copied into the producer's pinned buffer
+            assert rle_bytes[k] > 0
 
     def run_compact(per_thread):
         ths = [threading.Thread(target=compact_steps, args=(k, per_thread)) for k in range(NPROD)]

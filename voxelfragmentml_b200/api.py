@@ -337,6 +337,14 @@ class RegularGrid:
         check(self._lib.vf_grid_encode_rle(self._h, ptr(buf), buf.size, C.byref(need)))
         return buf.tobytes()
 
+    def encodeRLE_into(self, out) -> int:
+        """the `.rle` stream written into a caller-owned host buffer (numpy uint8 array or pinned torch tensor) in ONE call: returns the stream's
+        size; when it exceeds the buffer nothing is written and the size needed comes back negated"""
+        need = C.c_uint64(0)
+        cap = out.numel() * out.element_size() if hasattr(out, "numel") else out.nbytes
+        check(self._lib.vf_grid_encode_rle(self._h, ptr(out), cap, C.byref(need)))
+        return int(need.value) if need.value <= cap else -int(need.value)
+
     def exportGrid(self, filename: str, squared: bool, exportType):
         check(self._lib.vf_export(self._h, filename.encode(), int(exportType), int(bool(squared))))
 
