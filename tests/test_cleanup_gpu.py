@@ -390,3 +390,20 @@ def test_qstack_export_from_device_runs(ctx, orc, tmp_path):
         g.exportGrid(base, True, vf.ExportGrid.QUADSTACK)
         assert open(base + ".qstack", "rb").read() == orc.encode_qstack(grid), name
         g.close()
+
+
+@pytest.mark.parametrize("iters", [2, 3])
+def test_erode_when_passes_empty_millions_of_cells(ctx, orc, iters):
+    """threshold and probability high enough that a pass empties far more than the 2^20 cells the change lists hold: the sparse erosion passes,
+    the sparse sweep and its apply step then scan the change bitmap instead (odd and even iteration counts: the caller's grid holds the output
+    of the last pass or of the one before)"""
+    g0 = np.ones((160, 128, 192), np.uint16)
+    lab = orc.naive(g0.copy(), pick_seeds(g0, 400, 4), 0)  # small regions: most cells sit next to a border
+    noise = orc.Rng(11).fill_noise(100003)
+    orc.use_all_cores()
+    want = orc.erode(lab.copy(), noise, 1, 3, iters, 0.5, 1.6)  # every cell whose noise value is below 0.5 goes in the first pass
+    assert int(((want == 0) & (lab != 0)).sum()) > (1 << 20) and (want != 0).any()
+    g = _grid(ctx, lab)
+    g.erode(1, 3, iters, 0.5, 1.6, noise=noise)
+    assert np.array_equal(g.updateGrid(), want)
+    g.close()
