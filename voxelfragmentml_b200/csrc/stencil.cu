@@ -557,18 +557,26 @@ __device__ __forceinline__ void stencil_pair(const uint16_t* s, const Dims& d, i
         // count: the 27-cell count is the walk's total, the 7-cell count of ELLIPSE / CROSS is the part of it that the six face cells contribute.
         PairAcc full;
         unsigned faceA = 0, faceB = 0;  // differing cells among the six face neighbours
-#pragma unroll
-        for (int r = 0; r < 9; ++r) {
+        auto walk = [&](int r) {
             const uint16_t* p = ctr + ((r / 3 - 1) * HY + (r % 3 - 1)) * FRS;
             const unsigned W0 = *reinterpret_cast<const unsigned*>(p - 2), W1 = *reinterpret_cast<const unsigned*>(p), W2 = *reinterpret_cast<const unsigned*>(p + 2);
             const unsigned n1 = ne2(__byte_perm(W0, W1, 0x5432), AA), n2 = ne2(__byte_perm(W1, W2, 0x5432), BB), n3 = ne2(W1, BA);
             full.a1 += n1, full.a2 += n2, full.a3 += n3;
             if (r == 4) faceA += (n1 & 0xFFFFu) + (n3 >> 16), faceB += (n3 & 0xFFFFu) + (n2 >> 16);        // z - 1 and z + 1 of either cell
             else if (r == 1 || r == 3 || r == 5 || r == 7) faceA += n1 >> 16, faceB += n2 & 0xFFFFu;  // the cell's own z in the x / y face rows
+        };
+        // the centre row and the four face rows first: 14 of a cell's 26 neighbours.  Six equal ones among them already clear the cell for the
+        // sweep, which is the case nearly everywhere (a cell on a flat region border still has 11); the four corner rows are walked only for
+        // pairs that are not cleared yet, or when the erosion count itself needs all 27 cells (SQUARE)
+        walk(1), walk(3), walk(4), walk(5), walk(7);
+        unsigned neA = (full.a1 & 0xFFFFu) + (full.a1 >> 16) + (full.a3 >> 16), neB = (full.a2 & 0xFFFFu) + (full.a2 >> 16) + (full.a3 & 0xFFFFu);
+        const bool clearedA = ownA == VF_VOXEL_EMPTY || 14u - neA >= 6u, clearedB = ownB == VF_VOXEL_EMPTY || 14u - neB >= 6u;
+        if (!(clearedA && clearedB) || ea.maskbits != kStarMask) {
+            walk(0), walk(2), walk(6), walk(8);
+            neA = (full.a1 & 0xFFFFu) + (full.a1 >> 16) + (full.a3 >> 16), neB = (full.a2 & 0xFFFFu) + (full.a2 >> 16) + (full.a3 & 0xFFFFu);
+            const unsigned bits = (ownA != VF_VOXEL_EMPTY && 26u - neA < 6u ? 1u : 0u) | (ownB != VF_VOXEL_EMPTY && 26u - neB < 6u ? 2u : 0u);
+            if (bits) atomicOr(&ea.s0kill[gi >> 5], bits << (gi & 31u));  // gi is even: both bits land in one word
         }
-        const unsigned neA = (full.a1 & 0xFFFFu) + (full.a1 >> 16) + (full.a3 >> 16), neB = (full.a2 & 0xFFFFu) + (full.a2 >> 16) + (full.a3 & 0xFFFFu);
-        const unsigned bits = (ownA != VF_VOXEL_EMPTY && 26u - neA < 6u ? 1u : 0u) | (ownB != VF_VOXEL_EMPTY && 26u - neB < 6u ? 2u : 0u);
-        if (bits) atomicOr(&ea.s0kill[gi >> 5], bits << (gi & 31u));  // gi is even: both bits land in one word
         if (ea.maskbits == kStarMask) countA = 7u - faceA, countB = 7u - faceB;
         else if (ea.maskbits == kFullMask) countA = 27u - neA, countB = 27u - neB;
         else countA = masked_count(ctr, ea.maskbits), countB = masked_count(ctr + 1, ea.maskbits);
