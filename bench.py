@@ -296,13 +296,13 @@ def run_cuda(args):
     dom_bytes = stage_roofline[dom]["algorithmic_bytes"] / dom_launches
     dom_ms = stage_ms[dom] / dom_launches
     dom_kernels = {"naive": "naive_brick_kernel<EUCLIDEAN,8>", "remove_isolated": "vfc1::certificate_kernel (+ plant / resolve list work)",
-                   "erode": "stencil_fast_kernel<DETECT|ERODE3|SWEEP,TMA> (3 full passes) + erode_sparse_kernel (iterations 2..3)",
+                   "erode": "stencil_fast_kernel<DETECT|ERODE3,TMA> (2 full passes) + erode_sparse_kernel x2 + sweep_sparse_kernel + sweep_apply_kernel",
                    "histogram_undo_mask": "histogram_kernel<UNMASK>"}
     # measured DRAM bytes of the dominant stage's kernels (one ncu --set full capture, profiles/kernel_traffic.json), per launch like `achieved`
     dom_traffic = None
     try:
         kt = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))
-        pick = {"naive": ["naive_brick"], "remove_isolated": ["vfc1::"], "erode": ["stencil_fast", "erode_sparse", "erode_sparse"], "histogram_undo_mask": ["histogram"]}[dom]
+        pick = {"naive": ["naive_brick"], "remove_isolated": ["vfc1::"], "erode": ["stencil_fast", "erode_sparse", "erode_sparse", "sweep_sparse", "sweep_apply"], "histogram_undo_mask": ["histogram"]}[dom]
         tot_b = sum(v for pat in pick for k, v in kt.items() if pat in k)
         dom_traffic = tot_b / dom_launches if (n == 512 and tot_b > 0) else None
     except Exception:

@@ -37,10 +37,10 @@ with open(os.path.join(P, f"{tag}_launches_summary.md"), "w") as f:
     sm = bench["stage_ms"]
     st = sum(sm.values())
     f.write("\nbench.py `stage_ms` of the same build (CUDA events, warm): " + ", ".join(f"{k} {v:.3f} ms ({100 * v / st:.1f}%)" for k, v in sm.items()) + "\n\n")
-    grp = {"naive": ["naive_brick"], "remove_isolated": ["vfc1::", "ccl_"], "erode": ["stencil_", "erode_sparse"], "histogram_undo_mask": ["histogram", "pointwise"]}
+    grp = {"naive": ["naive_brick"], "remove_isolated": ["vfc1::", "ccl_"], "erode": ["stencil_", "erode_sparse", "sweep_"], "histogram_undo_mask": ["histogram", "pointwise"]}
     per_step = {g: sum(sum(v) / len(v) * n for k, v in agg.items() for p, n in pats.items() if p in k) for g, pats in
                 {"naive": {"naive_brick": 1}, "remove_isolated": {"fill_kernel": 1, "plant_kernel": 1, "certificate": 1, "resolve": 1, "publish": 1},
-                 "erode": {"stencil_fast_kernel<0": 1, "stencil_fast_kernel<1": 1, "stencil_fast_kernel<2": 1, "erode_sparse": 2}, "histogram_undo_mask": {"histogram": 1}}.items()}
+                 "erode": {"stencil_fast_kernel<0": 1, "stencil_fast_kernel<1": 1, "stencil_fast_kernel<2": 0, "erode_sparse": 2, "sweep_sparse": 1, "sweep_apply": 1, "zero_kernel": 1}, "histogram_undo_mask": {"histogram": 1}}.items()}
     ps = sum(per_step.values())
     f.write("One step's kernels from the list's per-kernel averages (launch counts of one step): " + ", ".join(f"{g} {v:.0f} us ({100 * v / ps:.1f}%)" for g, v in per_step.items()) + "\n")
 
@@ -55,7 +55,7 @@ SCALE = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}
 traffic = {}
 with open(os.path.join(P, f"{tag}_ncu_full_summary.md"), "w") as f:
     f.write(f"# {tag} — ncu --set full summaries (one B200)\n\nCommands (tools/collect_r2.sh): `ncu --set full --clock-control none --import-source on -k regex:\"naive_brick|"
-            "certificate|resolve_kernel|stencil_fast|erode_sparse|histogram\" -s 9 -c 9 python tools/prof_stage.py 512 naive,c1,erode,hist 2` (the cfg3 stages on the dense "
+            "certificate|resolve_kernel|stencil_fast|erode_sparse|sweep_sparse|sweep_apply|histogram\" -s 9 -c 9 python tools/prof_stage.py 512 naive,c1,erode,hist 2` (the cfg3 stages on the dense "
             "512^3 grid, second repetition) and `-k regex:flood_round -c 1 python tools/prof_flood1.py 1` (the cfg2 vessel: one cooperative launch = the whole flood phase). "
             "One section per distinct kernel (first captured launch); read with `ncu -i ... --page raw --csv`.\n")
     for dump in (f"{tag}_cfg3_full_raw.csv", f"{tag}_flood_full_raw.csv"):
