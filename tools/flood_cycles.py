@@ -18,4 +18,4 @@ for df in (1, 2):
         ctx.timer_start(); fl.build(g, seeds); ms = ctx.timer_stop()
     lib.vf_debug_flood_cycles(out, 1)
     nv = max(1, out[4])
-    print(f"df {df}: {ms:.3f} ms, visits {out[4]}, steps/visit {out[5]/nv:.1f}, cycles/visit: load {out[0]/nv:.0f} masks {out[1]/nv:.0f} relax {out[2]/nv:.0f} ({out[2]/max(1,out[5]):.0f}/step) store+wake {out[3]/nv:.0f}")
+    print(f"df {df}: {ms:.3f} ms, visits {out[4]}, steps/visit {out[5]/nv:.1f}, cycles/visit: load {out[0]/nv:.0f} masks {out[1]/nv:.0f} relax {out[2]/nv:.0f} ({out[2]/max(1,out[5]):.0f}/step) store+wake {out[3]/nv:.0f}; entry step {out[6]/nv:.0f}, later steps {(out[2]-out[6])/max(1,out[5]-out[4]):.0f} each, of which warp 0 waits at the barrier {out[7]/max(1,out[5]):.0f} per step")

@@ -42,6 +42,7 @@ constexpr uint32_t KEY_LEVEL = 1u << KEY_SHIFT;
 constexpr uint32_t KEY_LIMIT = 0xFFFF0000u;  // keys at or above this cannot take another level (dist >= 2^17 - 2)
 constexpr uint32_t kLevelsPerRound = 16;     // width of a round's distance window (one tile edge)
 constexpr uint32_t kNoLevel = 0xFFFFFFFFu;
+constexpr unsigned kOwnRowMax = 2;           // rows with at most this many candidates in a step are relaxed by their owner lane
 
 enum { ST_VISITS = 0, ST_ROUNDS = 1, ST_ERROR = 2, ST_FREED = 3, ST_MAXDIST = 4, ST_CHANGED = 5, ST_STEPS = 6, ST_MAXSTEPS = 7 };
 
@@ -378,6 +379,9 @@ __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __re
             const int myrow = lane * 8 + warp, mx = myrow / TY, my = myrow % TY;
             uint32_t dmin = kNoLevel;
             for (int it = 0; it < TX * TY * TZ; ++it) {
+#ifdef VF_FLOOD_TIMING
+                const long long step_t0 = clock64();
+#endif
                 const uint32_t* cur = act + (it & 1) * kThreads;
                 uint32_t* nxt = act + ((it & 1) ^ 1) * kThreads;
                 unsigned cand;
@@ -423,7 +427,20 @@ __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __re
                 };
                 const unsigned rows = __ballot_sync(kFull, cand != 0);  // bit l <-> row l * 8 + warp
                 const int total = (int)__reduce_add_sync(kFull, (unsigned)__popc(cand));
-                if (2 * __popc(rows) <= 3 * ((total + 31) / 32) + 1) {
+                if (__reduce_max_sync(kFull, (unsigned)__popc(cand)) <= kOwnRowMax) {
+                    // thin fronts (the diagonal planes of a Manhattan front, any front moving along z): a candidate or two per row.  Every lane
+                    // relaxes the candidates of its OWN row one after the other — no dealing, no shuffles, no atomics: only the owner writes
+                    // its row's words
+                    unsigned low = 0, def = 0;
+                    for (unsigned cb = cand; cb; cb &= cb - 1) {
+                        const int z = __ffs(cb) - 1;
+                        const int f = relax(mx, my, z);
+                        if (f == 1) low |= 1u << z;
+                        else if (f == 2) def |= 1u << z;
+                    }
+                    if (low) nxt[myrow] = low, chg[myrow] |= low, any = true;
+                    if (def) pnd[myrow] |= def;
+                } else if (2 * __popc(rows) <= 3 * ((total + 31) / 32) + 1) {
                     // well-filled rows (a thick front in a solid region): row by row, lane = z, results by ballot
                     for (unsigned rr = rows; rr; rr &= rr - 1) {
                         const int l = __ffs(rr) - 1;
@@ -471,7 +488,17 @@ __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __re
                     }
                 }
                 if (overflow) atomicOr(&wl.stats[ST_ERROR], 1u);
+#ifdef VF_FLOOD_TIMING
+                const long long step_t1 = clock64();
+                const int more = __syncthreads_or(any);
+                if (t == 0) {
+                    atomicAdd(&g_flood_cycles[7], (unsigned long long)(clock64() - step_t1));  // warp 0's wait at the step barrier
+                    if (it == 0) atomicAdd(&g_flood_cycles[6], (unsigned long long)(clock64() - step_t0));  // the entry step
+                }
+                if (!more) {
+#else
                 if (!__syncthreads_or(any)) {
+#endif
                     if (t == 0) atomicAdd(&wl.stats[ST_STEPS], (uint32_t)it + 1), atomicMax(&wl.stats[ST_MAXSTEPS], (uint32_t)it + 1);
 #ifdef VF_FLOOD_TIMING
                     if (t == 0) atomicAdd(&g_flood_cycles[5], (unsigned long long)it + 1), atomicAdd(&g_flood_cycles[4], 1ull);
@@ -517,6 +544,8 @@ __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __re
     }
     if (!COOP) return;
     // ---- next round: everybody's key stores, list appends and pending masks are visible (also to the copy engine's reads) after the barrier
+    // (a hand-rolled release / acquire counter barrier was measured against grid.sync(): no difference — the round is bound by its slowest
+    // tile visit, not by the barrier)
     __threadfence();
     asm volatile("fence.proxy.async;" ::: "memory");
     cooperative_groups::this_grid().sync();
@@ -571,23 +600,23 @@ vf_status job_begin(vf_grid* grid, Job& j)
     j.c = c;
     j.g = make_geom(grid->X, grid->Y, grid->Z);
     const size_t nt = (size_t)j.g.ntiles();
-    // layout: stats[8] count[3] lo[3] pad[2] | list0 | list1 | stamp | occ | seen | (aligned) pend[nt][kThreads]
-    const size_t words = 16 + 3 * nt;
+    // layout: stats[8] count[3] lo[3] round id, pad | pad[16] | list0 | list1 | stamp | occ | seen | (aligned) pend[nt][kThreads]
+    const size_t words = 32 + 3 * nt;
     const size_t pend_off = (words * 4 + 2 * nt + 255) & ~(size_t)255;
     VF_TRY(vf_scratch_reserve(c, c->tiles, pend_off + nt * kThreads * 4 + 256));
     uint32_t* base = (uint32_t*)c->tiles.ptr;
     j.wl.stats = base;
     j.wl.count = base + 8;
-    j.wl.list[0] = base + 16;
-    j.wl.list[1] = base + 16 + nt;
-    j.wl.stamp = base + 16 + 2 * nt;
-    j.wl.occ = (uint8_t*)(base + 16 + 3 * nt);
+    j.wl.list[0] = base + 32;
+    j.wl.list[1] = base + 32 + nt;
+    j.wl.stamp = base + 32 + 2 * nt;
+    j.wl.occ = (uint8_t*)(base + 32 + 3 * nt);
     j.wl.seen = j.wl.occ + nt;
     j.wl.epoch = 1;
     j.wl.lo = base + 11;
     j.wl.levels = c->flood_levels ? c->flood_levels : kLevelsPerRound;
     j.wl.pend = (uint32_t*)((char*)base + pend_off);
-    VF_CUDA(cudaMemsetAsync(base, 0, 16 * 4, c->stream));
+    VF_CUDA(cudaMemsetAsync(base, 0, 32 * 4, c->stream));
     VF_CUDA(cudaMemsetAsync(j.wl.stamp, 0, nt * 4 + 2 * nt, c->stream));
     j.round = 1;
     j.h_mail = (uint32_t*)((char*)c->pinned + 65536);  // upper half of the mailbox; the lower half carries seeds
