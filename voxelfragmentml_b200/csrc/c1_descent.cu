@@ -268,8 +268,8 @@ __global__ void __launch_bounds__(kCertWarps * 32) certificate_kernel(uint16_t* 
 }
 
 // pass 2 (one CTA; D is small): closure of F, liveness inside D, removal.  Leaves at once when the list is empty.
-__global__ void __launch_bounds__(kResolveThreads) resolve_kernel(uint16_t* grid, Dims d, const ushort4* __restrict__ seeds, int S, const uint32_t* __restrict__ table,
-                                                                  Set set, uint32_t* alive, uint32_t* list, Ctl* ctl)
+__device__ __forceinline__ void resolve_cells(uint16_t* grid, Dims d, const ushort4* __restrict__ seeds, int S, const uint32_t* __restrict__ table, Set set, uint32_t* alive,
+                                              uint32_t* list, Ctl* ctl)
 {
     extern __shared__ ushort4 sp[];
     __shared__ uint32_t s_head, s_tail, s_flag;
@@ -398,13 +398,21 @@ __global__ void __launch_bounds__(kResolveThreads) resolve_kernel(uint16_t* grid
     if (freed) atomicAdd(&ctl->freed, freed);
 }
 
-// verdict of the certificate straight into (mapped) pinned host memory: the host polls the word instead of going through a copy + a stream
-// synchronisation (two driver calls and their wake-up latency, which grows when several processes drive GPUs from one box)
-__global__ void publish_kernel(const Ctl* ctl, volatile uint32_t* host_word)
+// The list work, then the verdict of the certificate straight into (mapped) pinned host memory when `host_word` is given: the host polls the
+// word instead of going through a copy + a stream synchronisation (two driver calls and their wake-up latency, which grows when several
+// processes drive GPUs from one box).
+__global__ void __launch_bounds__(kResolveThreads) resolve_kernel(uint16_t* grid, Dims d, const ushort4* __restrict__ seeds, int S, const uint32_t* __restrict__ table,
+                                                                  Set set, uint32_t* alive, uint32_t* list, Ctl* ctl, volatile uint32_t* host_word)
 {
-    const uint32_t v = 1u | (ctl->overflow ? 2u : 0u) | (ctl->dup ? 4u : 0u);
-    *host_word = v;
-    __threadfence_system();
+    resolve_cells(grid, d, seeds, S, table, set, alive, list, ctl);
+    if (host_word == nullptr) return;
+    __syncthreads();  // the removals and the flags of every thread are in place
+    if (threadIdx.x == 0) {
+        __threadfence_system();  // the grid before the word: the host launches the next stage as soon as it reads it
+        const volatile Ctl* vc = ctl;
+        *host_word = 1u | (vc->overflow ? 2u : 0u) | (vc->dup ? 4u : 0u);
+        __threadfence_system();
+    }
 }
 
 }  // namespace vfc1
@@ -438,9 +446,10 @@ vf_status vf_k_c1_descent(vf_grid* grid, const ushort4* d_seeds, int nseeds, uin
     VF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCertWarps * 32, smem));
     kern<<<c->num_sms * std::max(per_sm, 1), kCertWarps * 32, smem, c->stream>>>(grid->d, d, d_seeds, nseeds, table, list, ctl);
     VF_LAUNCHED(c);
-    resolve_kernel<<<1, kResolveThreads, smem, c->stream>>>(grid->d, d, d_seeds, nseeds, table, set, alive, list, ctl);
-    VF_LAUNCHED(c);
     volatile uint32_t* h_word = (volatile uint32_t*)((char*)c->pinned + 65536 + 256);
+    *h_word = 0;
+    resolve_kernel<<<1, kResolveThreads, smem, c->stream>>>(grid->d, d, d_seeds, nseeds, table, set, alive, list, ctl, c->blocking_sync ? nullptr : h_word);
+    VF_LAUNCHED(c);
     if (c->blocking_sync) {  // producers that share cores: sleep on the event instead of polling
         Ctl* h = (Ctl*)((char*)c->pinned + 65536 + 320);
         VF_CUDA(cudaMemcpyAsync(h, ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, c->stream));
@@ -449,9 +458,6 @@ vf_status vf_k_c1_descent(vf_grid* grid, const ushort4* d_seeds, int nseeds, uin
         *handled = 1;
         return VF_OK;
     }
-    *h_word = 0;
-    publish_kernel<<<1, 1, 0, c->stream>>>(ctl, h_word);
-    VF_LAUNCHED(c);
     uint32_t verdict = 0;
     for (uint64_t spins = 0; (verdict = *h_word) == 0; ++spins) {
         if ((spins & 0xFFFFu) == 0xFFFFu && cudaStreamQuery(c->stream) != cudaErrorNotReady) {  // the stream drained or failed: stop polling

@@ -372,7 +372,7 @@ constexpr int kHistBatch = 4, kHistWarps = 8, kHistQueue = 160;  // queue: up to
 
 template <bool UNMASK>
 __global__ void __launch_bounds__(kHistWarps * 32) histogram_kernel(uint16_t* __restrict__ grid, size_t n, uint32_t* __restrict__ counts,
-                                                                    unsigned long long* __restrict__ occupied)
+                                                                    unsigned long long* __restrict__ occupied, uint32_t* __restrict__ maxbin)
 {
     __shared__ uint32_t bins[kSmemBins];
     __shared__ uint4 queue[kHistWarps][kHistQueue];
@@ -384,9 +384,10 @@ __global__ void __launch_bounds__(kHistWarps * 32) histogram_kernel(uint16_t* __
     unsigned occ = 0;
     const size_t nvec = n / 8;
     uint4* g4 = reinterpret_cast<uint4*>(grid);
+    uint32_t top = 0;  // highest bin this thread touched in global memory
     auto add = [&](uint32_t label, uint32_t c) {
         if (label < kSmemBins) atomicAdd(&bins[label], c);
-        else atomicAdd(&counts[label], c);
+        else atomicAdd(&counts[label], c), top = max(top, label);
     };
     // the cells of one queued vector, run by run (RegularGrid.cpp:612: raw value > FREE, then unmask)
     auto count_runs = [&](const uint4& v) {
@@ -456,7 +457,9 @@ __global__ void __launch_bounds__(kHistWarps * 32) histogram_kernel(uint16_t* __
     if (lane == 0 && occ) atomicAdd(occupied, (unsigned long long)occ);
     __syncthreads();
     for (int i = threadIdx.x; i < kSmemBins; i += blockDim.x)
-        if (bins[i]) atomicAdd(&counts[i], bins[i]);
+        if (bins[i]) atomicAdd(&counts[i], bins[i]), top = max(top, (uint32_t)i);
+    top = __reduce_max_sync(kFull, top);
+    if (lane == 0 && top) atomicMax(maxbin, top);  // the host reads back (and re-zeroes) the bins up to here only
 }
 
 // ------------------------------------------------------------------------------------------------ fast 3^3 stencils
@@ -974,22 +977,35 @@ static vf_status histogram_impl(vf_grid* g, uint32_t* counts, uint64_t* occupied
     vf_ctx* c = g->ctx;
     VF_TRY(vf_enter(c));
     VF_TRY(vf_scratch_reserve(c, c->small, 1 << 20));
-    // device bins live after the seed area of the small arena
-    uint32_t* d_counts = (uint32_t*)((char*)c->small.ptr + (512 << 10));
-    unsigned long long* d_occ = (unsigned long long*)(d_counts + VF_HISTOGRAM_BINS);
-    VF_TRY(vf_k_zero(c, d_counts, VF_HISTOGRAM_BINS * 4 + 8));
+    // device side, after the seed area of the small arena: { occupied (8 B), highest non-empty bin (4 B), pad } | bins.  The bins are zero on
+    // entry: the first call on this arena zeroes all of them, every call re-zeroes what it used AFTER its read-back, off the caller's path.
+    char* d_head = (char*)c->small.ptr + (512 << 10);
+    unsigned long long* d_occ = (unsigned long long*)d_head;
+    uint32_t* d_max = (uint32_t*)(d_head + 8);
+    uint32_t* d_counts = (uint32_t*)(d_head + 16);
+    if (c->hist_clean != d_head) VF_TRY(vf_k_zero(c, d_head, 16 + VF_HISTOGRAM_BINS * 4));
+    c->hist_clean = nullptr;
     // 38-40 registers: six CTAs are resident per SM, so the grid is one full wave (measured equal to eight per SM within noise)
     const int blocks = (int)std::min((size_t)c->num_sms * 6, (g->n() / 8 + 255) / 256 + 1);
-    if (unmask) histogram_kernel<true><<<blocks, 256, 0, c->stream>>>(g->d, g->n(), d_counts, d_occ);
-    else histogram_kernel<false><<<blocks, 256, 0, c->stream>>>(g->d, g->n(), d_counts, d_occ);
+    if (unmask) histogram_kernel<true><<<blocks, 256, 0, c->stream>>>(g->d, g->n(), d_counts, d_occ, d_max);
+    else histogram_kernel<false><<<blocks, 256, 0, c->stream>>>(g->d, g->n(), d_counts, d_occ, d_max);
     VF_LAUNCHED(c);
-    // bins + occupied count are contiguous on the device: one copy into the context's pinned read-back area (a copy into the caller's
-    // pageable buffer is staged by the runtime and costs two extra synchronisations), then a host memcpy
+    // one copy of the head + the first kHead bins into the context's pinned read-back area (a copy into the caller's pageable buffer is staged
+    // by the runtime and costs two extra synchronisations); labels beyond kHead (more than a thousand fragments) cost a second copy
+    constexpr uint32_t kHead = 1024;
     char* h = (char*)c->pinned + (1 << 17);
-    VF_CUDA(cudaMemcpyAsync(h, d_counts, VF_HISTOGRAM_BINS * 4 + 8, cudaMemcpyDeviceToHost, c->stream));
+    VF_CUDA(cudaMemcpyAsync(h, d_head, 16 + kHead * 4, cudaMemcpyDeviceToHost, c->stream));
     VF_CUDA(vf_sync(c));
-    std::memcpy(counts, h, VF_HISTOGRAM_BINS * 4);
-    if (occupied) std::memcpy(occupied, h + VF_HISTOGRAM_BINS * 4, 8);
+    const uint32_t top = std::min(*(const uint32_t*)(h + 8), (uint32_t)VF_HISTOGRAM_BINS - 1);
+    if (top >= kHead) {
+        VF_CUDA(cudaMemcpyAsync(h + 16 + kHead * 4, d_counts + kHead, (size_t)(top + 1 - kHead) * 4, cudaMemcpyDeviceToHost, c->stream));
+        VF_CUDA(vf_sync(c));
+    }
+    const uint32_t have = std::max(top + 1, kHead);
+    std::memcpy(counts, h + 16, (size_t)have * 4);
+    std::memset(counts + have, 0, (size_t)(VF_HISTOGRAM_BINS - have) * 4);
+    if (occupied) std::memcpy(occupied, h, 8);
+    if (vf_k_zero(c, d_head, 16 + (size_t)(top + 1) * 4) == VF_OK) c->hist_clean = d_head;  // enqueued, not waited for
     return VF_OK;
 }
 
