@@ -378,13 +378,18 @@ def run_cuda(args):
         ctx.synchronize()
     serial_s = (time.perf_counter() - t0) / e2e_steps
 
-    NPROD = 4  # producer threads of the compact end-to-end path (the full-grid rotation uses the first three slots)
+    # producer threads of the compact end-to-end path (the full-grid rotation uses the first three slots).  Producers with few cores per GPU
+    # (the 8-GPU box: 32 hardware threads for 8 ranks) sleep on blocking events instead of spinning, as batch generation does
+    # (vf_ctx_set_blocking_sync); a sleeping producer wakes up late, so twice as many of them keep the GPU fed (one GPU, tools/e2e_modes.sh:
+    # spinning x4 0.99 ms per step, blocking x4 1.19, blocking x8 0.99)
+    e2e_block = args.e2e_blocking == "on" or (args.e2e_blocking == "auto" and host_cores() // max(1, world) < 8)
+    NPROD = max(3, args.e2e_producers if args.e2e_producers > 0 else (8 if e2e_block else 4))
     slots = []
     for k in range(NPROD):
         c = ctx if k == 0 else vf.Context(local_rank)
         g = grid if k == 0 else vf.RegularGrid(c, dims)
         c.reserve(dims)
-        slots.append((c, g, h_out if k == 0 else torch.empty(N, dtype=torch.int16).pin_memory()))
+        slots.append((c, g, h_out if k == 0 else (torch.empty(N, dtype=torch.int16).pin_memory() if k < 3 else None)))
 
     def run_pipelined(nsteps):
         # On this platform a transfer submitted while another one is in flight waits for it, whatever the stream or direction;
@@ -448,9 +453,6 @@ def run_cuda(args):
         for t in ths:
             t.join()
 
-    # producers with few cores per GPU (the 8-GPU box: 32 hardware threads for 8 ranks x 3 producer threads) wait on blocking events instead of
-    # spinning, as batch generation does (vf_ctx_set_blocking_sync)
-    e2e_block = args.e2e_blocking == "on" or (args.e2e_blocking == "auto" and host_cores() // max(1, world) < 8)
     for c, _, _ in slots:
         c.setBlockingSync(e2e_block)
     run_compact(1)
@@ -499,9 +501,9 @@ def run_cuda(args):
         # headline end-to-end figure: compact host buffers (what a producer that keeps occupancy as bits and consumes `.rle` moves);
         # "full_grid" is the same step with 16-bit grids both ways, as RegularGrid::updateSSBO / updateGrid move them
         "e2e": {"value": world * N / compact_s / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": int(h_bits.numel()),
-                "d2h_bytes_per_step": int(max(rle_bytes)) + 4 * 32768 + 8, "ms_per_step": compact_s * 1e3, "steps": NPROD * per_thread,
+                "d2h_bytes_per_step": int(max(rle_bytes)) + 16 + 4 * 1024, "ms_per_step": compact_s * 1e3, "steps": NPROD * per_thread,
                 "mode": "compact: input = 1 occupancy bit per cell from pinned memory (vf_grid_upload_bits, expanded on the device), result = the `.rle` "
-                        "byte stream (runs found on the device, vf_grid_encode_rle) + the histogram; four host threads with one context each run whole "
+                        "byte stream (runs found on the device, vf_grid_encode_rle) + the histogram; `producer_threads` host threads with one context each run whole "
                         "steps, so the copies of one step overlap the kernels of another; seeds and noise table are sent once (unchanged tables are skipped)",
                 "passes_ms_per_step": [t * 1e3 for t in compact_runs], "rle_stream_equals_grid": compact_ok, "producer_threads": NPROD,
                 "host_waits": "blocking events" if e2e_block else "spinning", "host_cores_per_rank": host_cores() // max(1, world),
@@ -1057,6 +1059,7 @@ def main():
     ap.add_argument("--jobs", type=int, default=0, help="batch workload: concurrent contexts (streams + host threads) per GPU; 0 = 16 with a core per job, else 32 with blocking waits")
     ap.add_argument("--blocking-sync", default="auto", choices=["auto", "on", "off"],
                     help="batch workload: contexts wait on blocking events instead of spinning (auto: when jobs x ranks exceed the host cores)")
+    ap.add_argument("--e2e-producers", type=int, default=0, help="default workload: host threads (one context each) of the compact end-to-end path (0: 4 when they spin, 8 when they wait on blocking events)")
     ap.add_argument("--e2e-blocking", default="auto", choices=["auto", "on", "off"], help="default workload: the end-to-end producer threads wait on blocking events (auto: fewer than 8 host cores per rank)")
     ap.add_argument("--no-vessel", action="store_true", help="default workload: skip the sparse cfg3-vessel sub-line reported under \"vessel\"")
     ap.add_argument("--no-batch", action="store_true", help="default workload: skip the short cfg4 batch measurement reported under \"batch\"")
