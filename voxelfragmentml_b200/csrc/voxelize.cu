@@ -19,7 +19,7 @@
 
 namespace {
 
-constexpr int BX = 4, BY = 4, BZ = 32;
+constexpr int BX = 8, BY = 8, BZ = 32;  // brick: 64 z-rows of 32 cells
 constexpr int kChunk = 64;  // triangles staged per iteration
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
@@ -43,72 +43,92 @@ __device__ __forceinline__ void tri_range(const VoxGeom& g, const float* p1, con
     }
 }
 
+// One warp per triangle; its lanes take the bricks of the triangle's candidate range (a triangle at 512^3 touches a few dozen), so the
+// atomics of one triangle are in flight together instead of one round trip after the other.  The fill pass writes, per (brick, triangle)
+// pair, a 64-byte record the voxel kernel consumes without any further indirection:
+//   words 0-8 the three vertices, word 9 the candidate range relative to the brick and cut to it (x0 | x1 << 3 | y0 << 6 | y1 << 9 |
+//   z0 << 12 | z1 << 17), words 10-14 a conservative plane pre-test (see kPlaneMargin): nx, ny, nz, d, R — cells with |n . c - d| > R lie
+//   clearly off the triangle's plane and skip the exact test.
+constexpr int kRecWords = 16;
+constexpr float kPlaneMargin = 1.05f;  // the exact plane test rejects when the distance exceeds the box's projected radius; 5 % + rounding slack on top
 template <bool FILL>
 __global__ void __launch_bounds__(256) bin_triangles_kernel(const float* __restrict__ verts, const uint32_t* __restrict__ faces, uint32_t nf, VoxGeom g,
-                                                            uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets, uint32_t* __restrict__ list)
+                                                            uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets, uint4* __restrict__ list)
 {
-    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (f >= nf) return;
     const float* p1 = verts + 3 * (size_t)faces[3 * f];
     const float* p2 = verts + 3 * (size_t)faces[3 * f + 1];
     const float* p3 = verts + 3 * (size_t)faces[3 * f + 2];
     int lo[3], hi[3];
     tri_range(g, p1, p2, p3, lo, hi);
-    for (int bx = lo[0] / BX; bx <= hi[0] / BX; ++bx)
-        for (int by = lo[1] / BY; by <= hi[1] / BY; ++by)
-            for (int bz = lo[2] / BZ; bz <= hi[2] / BZ; ++bz) {
-                const uint32_t b = ((uint32_t)bx * g.nby + by) * g.nbz + bz;
-                const uint32_t pos = atomicAdd(&counts[b], 1u);
-                if (FILL) list[offsets[b] + pos] = f;
+    float n[3] = { 0, 0, 0 }, d = 0, R = 3.0e38f;
+    if (FILL) {
+        const float e0[3] = { p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2] }, e1[3] = { p3[0] - p2[0], p3[1] - p2[1], p3[2] - p2[2] };
+        n[0] = e0[1] * e1[2] - e1[1] * e0[2], n[1] = e0[2] * e1[0] - e1[2] * e0[0], n[2] = e0[0] * e1[1] - e1[0] * e0[1];
+        const float n1 = fabsf(n[0]) + fabsf(n[1]) + fabsf(n[2]);
+        const float l0 = fabsf(e0[0]) + fabsf(e0[1]) + fabsf(e0[2]), l1 = fabsf(e1[0]) + fabsf(e1[1]) + fabsf(e1[2]);
+        // slivers (edges parallel to within 1e-3) and specks (edges below a hundredth of a cell): the cross product is mostly rounding, and the
+        // exact test's own normal — built from vertex-minus-centre differences — may point elsewhere: no pre-test
+        const float speck = 1e-2f * fminf(g.cell[0], fminf(g.cell[1], g.cell[2]));
+        if (n1 > 1e-3f * l0 * l1 && n1 < 1e30f && l0 > speck && l1 > speck) {
+            d = n[0] * p1[0] + n[1] * p1[1] + n[2] * p1[2];
+            float rad = 0, mag = 0;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const float ext = g.cell[q] * (float)(q == 0 ? g.X : q == 1 ? g.Y : g.Z);
+                rad += fabsf(n[q]) * (0.5f * g.cell[q]);
+                mag += fabsf(n[q]) * (fabsf(g.amin[q]) + fabsf(ext));  // bounds |c| and |p| along q
             }
+            R = kPlaneMargin * rad + 1e-5f * mag;
+        }
+    }
+    const int bx0 = lo[0] / BX, by0 = lo[1] / BY, bz0 = lo[2] / BZ;
+    const int ny = hi[1] / BY - by0 + 1, nz = hi[2] / BZ - bz0 + 1, nn = (hi[0] / BX - bx0 + 1) * ny * nz;
+    for (int i = lane; i < nn; i += 32) {
+        const int iz = i % nz, iy = (i / nz) % ny, ix = i / (nz * ny);
+        const int bx = bx0 + ix, by = by0 + iy, bz = bz0 + iz;
+        const uint32_t b = ((uint32_t)bx * g.nby + by) * g.nbz + bz;
+        const uint32_t pos = atomicAdd(&counts[b], 1u);
+        if (FILL) {
+            const int x0 = max(lo[0] - bx * BX, 0), x1 = min(hi[0] - bx * BX, BX - 1), y0 = max(lo[1] - by * BY, 0), y1 = min(hi[1] - by * BY, BY - 1);
+            const int z0 = max(lo[2] - bz * BZ, 0), z1 = min(hi[2] - bz * BZ, BZ - 1);
+            const uint32_t rng = (uint32_t)(x0 | x1 << 3 | y0 << 6 | y1 << 9 | z0 << 12 | z1 << 17);
+            uint4* rec = list + (size_t)(offsets[b] + pos) * (kRecWords / 4);
+            rec[0] = make_uint4(__float_as_uint(p1[0]), __float_as_uint(p1[1]), __float_as_uint(p1[2]), __float_as_uint(p2[0]));
+            rec[1] = make_uint4(__float_as_uint(p2[1]), __float_as_uint(p2[2]), __float_as_uint(p3[0]), __float_as_uint(p3[1]));
+            rec[2] = make_uint4(__float_as_uint(p3[2]), rng, __float_as_uint(n[0]), __float_as_uint(n[1]));
+            rec[3] = make_uint4(__float_as_uint(n[2]), __float_as_uint(d), __float_as_uint(R), 0u);
+        }
+    }
 }
 
-// exclusive scan of the brick counts by one CTA, four counts per thread and step (a few hundred thousand entries at most); also resets the
-// fill cursors
-__global__ void __launch_bounds__(1024) scan_counts_kernel(uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets, uint32_t n, uint32_t* __restrict__ total)
+// Space for every non-empty brick's records (any order: a brick's list is a set) and the list of the non-empty bricks themselves { brick,
+// first record }, which is what the voxel kernel runs over — most bricks of a surface mesh's grid hold no triangle.  One atomic pair per
+// warp.  Also resets the counts, which become the fill cursors.  header[0] = records in total, header[1] = non-empty bricks.
+__global__ void __launch_bounds__(256) reserve_bricks_kernel(uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets, uint32_t nb, uint2* __restrict__ bricks,
+                                                             uint32_t* __restrict__ header)
 {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < n; base += 4096) {
-        const uint32_t i = base + 4 * threadIdx.x;
-        uint32_t v[4];
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const uint32_t c = b < nb ? counts[b] : 0u;
+    uint32_t incl = c;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = i + k < n ? counts[i + k] : 0;
-        const uint32_t mine = v[0] + v[1] + v[2] + v[3];
-        uint32_t s = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(kFull, s, o);
-            if ((threadIdx.x & 31) >= o) s += t;
-        }
-        if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = s;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            uint32_t w = warp_sums[threadIdx.x];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(kFull, w, o);
-                if (threadIdx.x >= o) w += t;
-            }
-            warp_sums[threadIdx.x] = w;
-        }
-        __syncthreads();
-        uint32_t before = carry + (threadIdx.x >= 32 ? warp_sums[(threadIdx.x >> 5) - 1] : 0) + s - mine;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (i + k < n) {
-                offsets[i + k] = before;
-                counts[i + k] = 0;  // becomes the fill cursor
-            }
-            before += v[k];
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = before;
-        __syncthreads();
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += t;
     }
-    if (threadIdx.x == 0) *total = carry;
+    const unsigned some = __ballot_sync(kFull, c != 0);
+    if (some == 0) return;
+    uint32_t base = 0, bbase = 0;
+    if (lane == 31) base = atomicAdd(&header[0], incl), bbase = atomicAdd(&header[1], (uint32_t)__popc(some));
+    base = __shfl_sync(kFull, base, 31), bbase = __shfl_sync(kFull, bbase, 31);
+    if (c) {
+        offsets[b] = base + incl - c;
+        bricks[bbase + __popc(some & ((1u << lane) - 1u))] = make_uint2(b, base + incl - c);
+        counts[b] = 0;
+    }
 }
 
 // Intersections3D.h:204-258 for one voxel box (centre c, half extent r) and one triangle; float32 ops in reference order.
@@ -195,62 +215,139 @@ __device__ __forceinline__ bool tri_box_sat(const float c[3], const float r[3], 
 
 // fminf/fmaxf above pick min/max of two finite values exactly like the reference's `if (a < b)` swap (ties give equal values).
 
-__global__ void __launch_bounds__(256) voxelize_brick_kernel(uint16_t* __restrict__ grid, const float* __restrict__ verts, const uint32_t* __restrict__ faces,
-                                                             VoxGeom g, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
-                                                             const uint32_t* __restrict__ list)
+// Persistent CTAs (four warps) over the NON-EMPTY bricks.  A brick holds a handful of triangles, so a brick's visit is short and what it
+// would wait for is memory latency: the brick after next's header and the next brick's first records are requested before the current brick
+// is computed.
+//
+// Inside a brick the work is dealt by TRIANGLE: a warp takes a record and walks the cells of the triangle's candidate range inside the brick
+// (the range the triangle was binned with, tri_range: cells outside it lie a full cell away from the triangle's bounding box and are never
+// tested by the restated CPU path either), a power-of-two stretch of z per row so that several rows fill the warp.  Every cell gets two
+// cheap conservative tests — its box against the triangle's bounding box, its centre against the triangle's plane (the record's pre-test) —
+// and the survivors, a few per row, are queued per warp; the exact separating-axis test then runs 32 queued cells at a time, i.e. with full
+// warps, and sets the cell's bit in the brick's bitmap.  The brick is written once, as 64-byte rows.
+constexpr int kVoxWarps = 4, kVoxQueue = 96;  // queue: up to 31 waiting + 32 pushed per step, with room to spare
+__global__ void __launch_bounds__(kVoxWarps * 32) voxelize_brick_kernel(uint16_t* __restrict__ grid, VoxGeom g, const uint32_t* __restrict__ counts,
+                                                                         const uint2* __restrict__ bricks, uint32_t nbricks, const uint4* __restrict__ list)
 {
-    __shared__ float tri[kChunk][9];
-    const uint32_t b = blockIdx.x;
-    // after the fill pass `counts` holds the number of ids written per brick
-    const uint32_t cnt = counts[b];
-    if (cnt == 0) return;
-    const int bz = b % g.nbz, by = (b / g.nbz) % g.nby, bx = b / (g.nbz * g.nby);
-    // thread -> two z-adjacent voxels: 16 threads per 32-cell row, 16 rows
-    const int t = threadIdx.x, row = t >> 4, zq = (t & 15) * 2;
-    const int x = bx * BX + row / BY, y = by * BY + row % BY, z = bz * BZ + zq;
-    const bool in0 = x < g.X && y < g.Y && z < g.Z, in1 = in0 && z + 1 < g.Z;
-    float c0[3], c1[3], r0[3], r1[3];
-    {
-        // RegularGrid.cpp:258-259 + AABB.h:41,51
+    constexpr int kStage = kVoxWarps * 32 / (kRecWords / 4);  // records staged per chunk: one 16-byte quarter per thread
+    __shared__ uint4 rec4[kStage * (kRecWords / 4)];
+    __shared__ uint32_t hitbits[BX * BY];  // one word per z-row of the brick
+    __shared__ uint32_t queue[kVoxWarps][kVoxQueue];  // row | z << 6 | record << 11
+    const float* rec = reinterpret_cast<const float*>(rec4);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const uint32_t G = gridDim.x;
+    uint32_t i = blockIdx.x;
+    if (i >= nbricks) return;
+    const uint2 none = make_uint2(0u, 0u);
+    uint2 h0 = bricks[i], h1 = i + G < nbricks ? bricks[i + G] : none;
+    // the list is padded by one chunk: the first chunk of a brick is fetched whole before its length is known
+    uint4 pv = list[(size_t)h0.y * (kRecWords / 4) + t];
+    // box of a cell: RegularGrid.cpp:258-259 + AABB.h:41,51 (min = aabbMin + cell * index, max = min + cell, centre = (max + min) / 2, half extent = max - centre)
+    auto cell_box = [&](int x, int y, int z, float c[3], float r[3]) {
         const float bmin[3] = { g.amin[0] + g.cell[0] * (float)x, g.amin[1] + g.cell[1] * (float)y, g.amin[2] + g.cell[2] * (float)z };
-        const float bmin1z = g.amin[2] + g.cell[2] * (float)(z + 1);
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-            const float lo = bmin[q];
-            const float hi = lo + g.cell[q];
-            c0[q] = (hi + lo) / 2.0f;
-            r0[q] = hi - c0[q];
-            c1[q] = c0[q];
-            r1[q] = r0[q];
+            const float hi = bmin[q] + g.cell[q];
+            c[q] = (hi + bmin[q]) / 2.0f;
+            r[q] = hi - c[q];
         }
-        const float hi1 = bmin1z + g.cell[2];
-        c1[2] = (hi1 + bmin1z) / 2.0f;
-        r1[2] = hi1 - c1[2];
-    }
-    bool hit0 = false, hit1 = false;
-    const uint32_t off = offsets[b];
-    for (uint32_t base = 0; base < cnt; base += kChunk) {
-        const int m = (int)min((uint32_t)kChunk, cnt - base);
+    };
+    // slack of the bounding-box pre-test: a cell passes when its box, grown by 2 % of a cell plus rounding room, reaches the triangle's box
+    float grow[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) grow[q] = 0.51f * g.cell[q] + 1e-5f * (fabsf(g.amin[q]) + g.cell[q] * (float)(q == 0 ? g.X : q == 1 ? g.Y : g.Z));
+    for (; i < nbricks; i += G) {
+        const uint2 h2 = i + 2 * G < nbricks ? bricks[i + 2 * G] : none;
+        uint4 pvn = make_uint4(0u, 0u, 0u, 0u);
+        if (i + G < nbricks) pvn = list[(size_t)h1.y * (kRecWords / 4) + t];
+        const uint32_t b = h0.x, cnt = counts[b];  // after the fill pass: the number of records of the brick
+        const int bz = b % g.nbz, by = (b / g.nbz) % g.nby, bx = b / (g.nbz * g.nby);
+        const int gx0 = bx * BX, gy0 = by * BY, gz0 = bz * BZ;
+        if (t < BX * BY) hitbits[t] = 0;
+        uint32_t* q = queue[warp];
+        int qn = 0;
+        // exact test of the queued cells 32 at a time (`all`: also the last, partial batch)
+        auto drain = [&](bool all) {
+            while (qn >= 32 || (all && qn > 0)) {
+                const int take = min(qn, 32);
+                qn -= take;
+                if (lane < take) {
+                    const uint32_t e = q[qn + lane];
+                    const int row = e & 63, z = e >> 6 & 31, k = e >> 11;
+                    if (!(hitbits[row] >> z & 1u)) {
+                        float c[3], r[3];
+                        cell_box(gx0 + (row >> 3), gy0 + (row & 7), gz0 + z, c, r);
+                        const float* tr = rec + k * kRecWords;
+                        if (tri_box_sat(c, r, tr, tr + 3, tr + 6)) atomicOr(&hitbits[row], 1u << z);
+                    }
+                }
+                __syncwarp();
+            }
+        };
+        for (uint32_t base = 0; base < cnt; base += kStage) {
+            const int m = (int)min((uint32_t)kStage, cnt - base);
+            __syncthreads();  // the previous chunk has been read (and hitbits is cleared)
+            if (t < m * (kRecWords / 4)) rec4[t] = base == 0 ? pv : list[(size_t)(h0.y + base) * (kRecWords / 4) + t];
+            __syncthreads();
+            for (int k = warp; k < m; k += kVoxWarps) {
+                const float* tr = rec + k * kRecWords;
+                const uint32_t rr = __float_as_uint(tr[9]);
+                const int x0 = rr & 7, x1 = rr >> 3 & 7, y0 = rr >> 6 & 7, y1 = rr >> 9 & 7, z0 = rr >> 12 & 31, z1 = rr >> 17 & 31;
+                const int ey = y1 - y0 + 1, ez = z1 - z0 + 1, rows = (x1 - x0 + 1) * ey;
+                const int zsh = ez <= 1 ? 0 : 32 - __clz(ez - 1);  // log2 of the z stretch (ez rounded up to a power of two)
+                const int rps = 32 >> zsh, zl = lane & ((1 << zsh) - 1), rl = lane >> zsh;
+                const float inv_ey = 1.0f / (float)ey;
+                // the triangle's bounding box, for the first pre-test
+                float tmin[3], tmax[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    tmin[a] = fminf(tr[a], fminf(tr[3 + a], tr[6 + a]));
+                    tmax[a] = fmaxf(tr[a], fmaxf(tr[3 + a], tr[6 + a]));
+                }
+                const float nx = tr[10], ny = tr[11], nz = tr[12], nd = tr[13], R = tr[14];
+                for (int r0 = 0; r0 < rows; r0 += rps) {
+                    const int rho = r0 + rl;
+                    const int ix = (int)(((float)rho + 0.5f) * inv_ey), iy = rho - ix * ey;  // rho < 64, ey <= 8: exact
+                    bool cand = rho < rows && zl < ez;
+                    const int cx = x0 + ix, cy = y0 + iy, cz = z0 + zl;
+                    if (cand) {
+                        const int x = gx0 + cx, y = gy0 + cy, z = gz0 + cz;
+                        // centres as the exact test computes them, to within an ulp (the pre-tests carry their own slack)
+                        const float px = g.amin[0] + g.cell[0] * ((float)x + 0.5f), py = g.amin[1] + g.cell[1] * ((float)y + 0.5f), pz = g.amin[2] + g.cell[2] * ((float)z + 0.5f);
+                        cand = px + grow[0] >= tmin[0] && px - grow[0] <= tmax[0] && py + grow[1] >= tmin[1] && py - grow[1] <= tmax[1] &&
+                               pz + grow[2] >= tmin[2] && pz - grow[2] <= tmax[2] && fabsf(nx * px + ny * py + nz * pz - nd) <= R &&
+                               x < g.X && y < g.Y && z < g.Z;
+                    }
+                    const unsigned bal = __ballot_sync(kFull, cand);
+                    if (bal) {
+                        if (cand) q[qn + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)(cx * BY + cy) | (uint32_t)cz << 6 | (uint32_t)k << 11;
+                        qn += __popc(bal);
+                        __syncwarp();
+                        drain(false);
+                    }
+                }
+            }
+            drain(true);  // before the records of this chunk are overwritten
+        }
         __syncthreads();
-        for (int i = t; i < m * 9; i += blockDim.x) {
-            const int k = i / 9, e = i % 9;
-            const uint32_t f = list[off + base + k];
-            tri[k][e] = verts[3 * (size_t)faces[3 * f + e / 3] + e % 3];
+        // the brick's rows: 64 rows x four 16-byte quarters
+        for (int it = t; it < BX * BY * 4; it += kVoxWarps * 32) {
+            const int row = it >> 2, qz = (it & 3) * 8;
+            const int x = gx0 + (row >> 3), y = gy0 + (row & 7), z = gz0 + qz;
+            if (x >= g.X || y >= g.Y || z >= g.Z) continue;
+            const uint32_t bits = hitbits[row] >> qz;
+            uint32_t w[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) w[a] = (bits >> (2 * a) & 1u) | (bits >> (2 * a + 1) & 1u) << 16;  // VF_VOXEL_FREE == 1
+            uint16_t* p = grid + ((size_t)x * g.Y + y) * g.Z + z;
+            if (z + 8 <= g.Z && ((uintptr_t)p & 15) == 0) {
+                *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+            } else {
+                for (int a = 0; a < 8 && z + a < g.Z; ++a) p[a] = (uint16_t)(bits >> a & 1u);
+            }
         }
-        __syncthreads();
-        for (int k = 0; k < m; ++k) {
-            if (in0 && !hit0) hit0 = tri_box_sat(c0, r0, &tri[k][0], &tri[k][3], &tri[k][6]);
-            if (in1 && !hit1) hit1 = tri_box_sat(c1, r1, &tri[k][0], &tri[k][3], &tri[k][6]);
-        }
-    }
-    if (in0) {
-        const size_t gi = ((size_t)x * g.Y + y) * g.Z + z;
-        if (in1 && (gi & 1) == 0) {
-            *reinterpret_cast<uint32_t*>(grid + gi) = (hit0 ? 1u : 0u) | (hit1 ? 0x10000u : 0u);
-        } else {
-            grid[gi] = hit0 ? VF_VOXEL_FREE : VF_VOXEL_EMPTY;
-            if (in1) grid[gi + 1] = hit1 ? VF_VOXEL_FREE : VF_VOXEL_EMPTY;
-        }
+        h0 = h1, h1 = h2, pv = pvn;
+        __syncthreads();  // everybody has read hitbits before the next brick clears it
     }
 }
 
@@ -274,35 +371,39 @@ extern "C" vf_status vf_voxelize(vf_grid* grid, const float* verts, uint32_t nv,
     VF_CUDA(cudaMemsetAsync(grid->d, 0, grid->n() * sizeof(uint16_t), c->stream));  // cleanGrid + every brick without triangles
     if (nf == 0) return VF_OK;
 
-    // arena: verts | faces | counts[nb] | offsets[nb] | total | list
+    // arena: verts | faces | counts[nb] | offsets[nb] | non-empty bricks[nb] | header | records (+ one chunk of padding)
     const size_t vbytes = ((size_t)nv * 12 + 255) & ~(size_t)255, fbytes = ((size_t)nf * 12 + 255) & ~(size_t)255;
     const size_t cbytes = (nb * 4 + 255) & ~(size_t)255;
-    size_t need = vbytes + fbytes + 2 * cbytes + 256;
-    VF_TRY(vf_scratch_reserve(c, c->mesh, need + ((size_t)nf * 16 * 4)));
+    const size_t need = vbytes + fbytes + 4 * cbytes + 256, rec_bytes = kRecWords * 4, pad = (size_t)64 * rec_bytes;
+    VF_TRY(vf_scratch_reserve(c, c->mesh, need + (size_t)nf * 16 * rec_bytes + pad));
     char* base = (char*)c->mesh.ptr;
     float* d_verts = (float*)base;
     uint32_t* d_faces = (uint32_t*)(base + vbytes);
     uint32_t* d_counts = (uint32_t*)(base + vbytes + fbytes);
     uint32_t* d_offsets = (uint32_t*)(base + vbytes + fbytes + cbytes);
-    uint32_t* d_total = (uint32_t*)(base + vbytes + fbytes + 2 * cbytes);
+    uint2* d_bricks = (uint2*)(base + vbytes + fbytes + 2 * cbytes);
+    uint32_t* d_header = (uint32_t*)(base + vbytes + fbytes + 4 * cbytes);
     VF_CUDA(cudaMemcpyAsync(d_verts, verts, (size_t)nv * 12, cudaMemcpyHostToDevice, c->stream));
     VF_CUDA(cudaMemcpyAsync(d_faces, faces, (size_t)nf * 12, cudaMemcpyHostToDevice, c->stream));
     VF_CUDA(cudaMemsetAsync(d_counts, 0, cbytes, c->stream));
-    const int tb = (int)((nf + 255) / 256);
+    VF_CUDA(cudaMemsetAsync(d_header, 0, 8, c->stream));
+    const int tb = (int)((nf + 7) / 8);  // a warp per triangle
     bin_triangles_kernel<false><<<tb, 256, 0, c->stream>>>(d_verts, d_faces, nf, g, d_counts, nullptr, nullptr);
     VF_LAUNCHED(c);
-    scan_counts_kernel<<<1, 1024, 0, c->stream>>>(d_counts, d_offsets, (uint32_t)nb, d_total);
+    reserve_bricks_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, c->stream>>>(d_counts, d_offsets, (uint32_t)nb, d_bricks, d_header);
     VF_LAUNCHED(c);
-    uint32_t* h_total = (uint32_t*)((char*)c->pinned + 65536);
-    VF_CUDA(cudaMemcpyAsync(h_total, d_total, 4, cudaMemcpyDeviceToHost, c->stream));
+    uint32_t* h_header = (uint32_t*)((char*)c->pinned + 65536);
+    VF_CUDA(cudaMemcpyAsync(h_header, d_header, 8, cudaMemcpyDeviceToHost, c->stream));
     VF_CUDA(vf_sync(c));  // also covers the pageable verts/faces uploads
-    const size_t total = *h_total;
-    VF_REQUIRE(total < (1ull << 31), VF_ERR_CAPACITY, "voxelize: triangle/brick list too long (%zu)", total);
-    if (need + total * 4 > c->mesh.bytes) {
-        // grow the arena and redo the uploads + count/scan (rare: only when the mesh has very large triangles)
+    const size_t total = h_header[0];
+    const uint32_t nonempty = h_header[1];
+    VF_REQUIRE(total < (1ull << 27), VF_ERR_CAPACITY, "voxelize: triangle/brick list too long (%zu records)", total);
+    if (nonempty == 0) return VF_OK;
+    if (need + total * rec_bytes + pad > c->mesh.bytes) {
+        // grow the arena, keeping what the passes above left in it (rare: only when the mesh has very large triangles)
         VfScratch old = c->mesh;
         c->mesh = VfScratch();
-        VF_TRY(vf_scratch_reserve(c, c->mesh, need + total * 4 + 256));
+        VF_TRY(vf_scratch_reserve(c, c->mesh, need + total * rec_bytes + pad + 256));
         VF_CUDA(cudaMemcpyAsync(c->mesh.ptr, old.ptr, need, cudaMemcpyDeviceToDevice, c->stream));
         VF_CUDA(vf_sync(c));
         VF_CUDA(cudaFree(old.ptr));
@@ -311,11 +412,15 @@ extern "C" vf_status vf_voxelize(vf_grid* grid, const float* verts, uint32_t nv,
         d_faces = (uint32_t*)(base + vbytes);
         d_counts = (uint32_t*)(base + vbytes + fbytes);
         d_offsets = (uint32_t*)(base + vbytes + fbytes + cbytes);
+        d_bricks = (uint2*)(base + vbytes + fbytes + 2 * cbytes);
     }
-    uint32_t* d_list = (uint32_t*)(base + need);
+    uint4* d_list = (uint4*)(base + need);
     bin_triangles_kernel<true><<<tb, 256, 0, c->stream>>>(d_verts, d_faces, nf, g, d_counts, d_offsets, d_list);
     VF_LAUNCHED(c);
-    voxelize_brick_kernel<<<(unsigned)nb, 256, 0, c->stream>>>(grid->d, d_verts, d_faces, g, d_counts, d_offsets, d_list);
+    int per_sm = 0;
+    VF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, voxelize_brick_kernel, kVoxWarps * 32, 0));
+    const unsigned ctas = std::min<unsigned>(nonempty, (unsigned)(c->num_sms * std::max(per_sm, 1)));
+    voxelize_brick_kernel<<<ctas, kVoxWarps * 32, 0, c->stream>>>(grid->d, g, d_counts, d_bricks, nonempty, d_list);
     VF_LAUNCHED(c);
     return VF_OK;
 }
