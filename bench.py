@@ -876,6 +876,8 @@ def batch_measure(rank, local_rank, world, dist, meshes, warmup, jobs, mesh_pool
     checksums = [0] * jobs
     workers = []
     block = blocking == "on" or (blocking == "auto" and jobs * world > host_cores())  # measured: 4 cores per rank, 16 jobs: 120 (spin) vs 164 models/s
+    if blocking == "yield":
+        block = 2
     for j in range(jobs):
         ctx = vf.Context(local_rank)
         ctx.setBlockingSync(block)
@@ -1057,7 +1059,7 @@ def main():
     ap.add_argument("--no-slab", action="store_true", help="default workload at N >= 2: skip the cfg5 slab measurement reported under \"slab\"")
     ap.add_argument("--meshes", type=int, default=64, help="batch workload: number of meshes")
     ap.add_argument("--jobs", type=int, default=0, help="batch workload: concurrent contexts (streams + host threads) per GPU; 0 = 16 with a core per job, else 32 with blocking waits")
-    ap.add_argument("--blocking-sync", default="auto", choices=["auto", "on", "off"],
+    ap.add_argument("--blocking-sync", default="auto", choices=["auto", "on", "off", "yield"],
                     help="batch workload: contexts wait on blocking events instead of spinning (auto: when jobs x ranks exceed the host cores)")
     ap.add_argument("--e2e-producers", type=int, default=0, help="default workload: host threads (one context each) of the compact end-to-end path (0: 4 when they spin, 8 when they wait on blocking events)")
     ap.add_argument("--e2e-blocking", default="auto", choices=["auto", "on", "off"], help="default workload: the end-to-end producer threads wait on blocking events (auto: fewer than 8 host cores per rank)")

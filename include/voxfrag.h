@@ -115,8 +115,9 @@ vf_status vf_ctx_create_on_stream(int device, void* cuda_stream, vf_ctx** out); 
 void      vf_ctx_destroy(vf_ctx* ctx);
 vf_status vf_ctx_reserve(vf_ctx* ctx, uint32_t X, uint32_t Y, uint32_t Z); /* Fracturer::prepareSSBOs / init, Fracturer.h:43-48; FloodFracturer.cpp:47-59 */
 vf_status vf_ctx_synchronize(vf_ctx* ctx);
-/* on: host waits of this context sleep on a blocking event instead of spinning — for producers that drive more contexts than
- * they have host cores (batch generation overlaps several jobs per GPU); off (default): lowest latency */
+/* on = 1: host waits of this context sleep on a blocking event instead of spinning — for producers that drive more contexts than
+ * they have host cores (batch generation overlaps several jobs per GPU); on = 2: they poll and yield the core between polls (sched_yield);
+ * 0 (default): spin, lowest latency */
 vf_status vf_ctx_set_blocking_sync(vf_ctx* ctx, int on);
 /* Width, in distance levels, of the window a flood round may assign (the result does not depend on it; 0 = default 16, the best
  * latency for one job).  A narrower window orders the fronts better at the price of more rounds: 8 gives the highest throughput

@@ -202,7 +202,7 @@ def test_result_does_not_depend_on_the_distance_window_or_blocking_waits(orc, ve
 
     c = vf.Context(0)
     c.setFloodLevels(levels)
-    c.setBlockingSync(levels % 2 == 1)
+    c.setBlockingSync({1: 1, 3: 2}.get(levels, 0))  # spinning, sleeping on a blocking event (1), polling with sched_yield (2)
     seeds, _ = orc.seed_uniform(orc.Rng(80), vessel_grid, 12)
     for dfunc in (1, 2):
         want, _ = orc.flood(vessel_grid.copy(), seeds, dfunc)
@@ -212,6 +212,30 @@ def test_result_does_not_depend_on_the_distance_window_or_blocking_waits(orc, ve
     want, _ = orc.flood(vessel_grid.copy(), wseeds, orc.CHEBYSHEV)
     got, _ = _run_flood(c, vessel_grid, wseeds, 2)
     assert np.array_equal(got, want)
+    c.close()
+
+
+@pytest.mark.parametrize("wait", [1, 2])
+def test_c1_and_histogram_under_the_other_wait_modes(orc, vessel_grid, wait):
+    """vf_ctx_set_blocking_sync(1 | 2): C1 learns the certificate's verdict through a copy + blocking event, or by polling with sched_yield;
+    the histogram's read-back waits the same way.  Dense grid (the certificate handles it) and the vessel shell (it declines)."""
+    import voxelfragmentml_b200 as vf
+
+    c = vf.Context(0)
+    c.setBlockingSync(wait)
+    dense = np.ones((40, 32, 48), np.uint16)
+    for grid, ns in ((dense, 9), (vessel_grid, 12)):
+        seeds, _ = orc.seed_uniform(orc.Rng(81), grid, ns)
+        lab = orc.naive(grid.copy(), seeds, 0)
+        want = orc.remove_isolated_regions_cpu(lab.copy(), seeds)
+        g = vf.RegularGrid(c, lab.shape)
+        g.updateSSBO(lab)
+        vf.NaiveFracturer.removeIsolatedRegions(g, seeds)
+        counts, occ = g.countValues()
+        assert np.array_equal(g.updateGrid(), want)
+        wc, wocc = orc.count_values(want)
+        assert np.array_equal(np.asarray(counts), np.asarray(wc)) and int(occ) == int(wocc)
+        g.close()
     c.close()
 
 

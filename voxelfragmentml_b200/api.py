@@ -117,9 +117,9 @@ class Context:
     def reserve(self, dims):  # Fracturer::prepareSSBOs
         check(self._lib.vf_ctx_reserve(self._h, *[int(d) for d in dims]))
 
-    def setBlockingSync(self, on: bool = True):
-        """host waits sleep instead of spinning (more contexts than host cores)"""
-        check(self._lib.vf_ctx_set_blocking_sync(self._h, int(bool(on))))
+    def setBlockingSync(self, on=True):
+        """host waits sleep instead of spinning (more contexts than host cores); 2: they poll and yield the core between polls"""
+        check(self._lib.vf_ctx_set_blocking_sync(self._h, int(on)))
 
     def setFloodLevels(self, levels: int):
         """distance window of a flood round (0 = default 16: best latency; 8: best throughput with several jobs per GPU)"""

@@ -466,8 +466,9 @@ vf_status vf_k_c1_descent(vf_grid* grid, const ushort4* d_seeds, int nseeds, uin
             VF_REQUIRE(verdict != 0, VF_ERR_CUDA, "C1: the certificate's verdict never arrived");
             break;
         }
+        if (c->yield_wait) sched_yield();
 #if defined(__x86_64__)
-        __builtin_ia32_pause();
+        else __builtin_ia32_pause();
 #endif
     }
     if (verdict & 6u) return VF_OK;  // too much for one CTA's list work, or ambiguous starts: the union-find is the right tool

@@ -117,7 +117,8 @@ static vf_status ctx_create(int device, void* stream, bool borrow, vf_ctx** out)
 extern "C" vf_status vf_ctx_set_blocking_sync(vf_ctx* ctx, int on)
 {
     VF_REQUIRE(ctx != nullptr, VF_ERR_INVALID_ARGUMENT, "null context");
-    ctx->blocking_sync = on != 0;
+    ctx->blocking_sync = on == 1;
+    ctx->yield_wait = on == 2;
     return VF_OK;
 }
 

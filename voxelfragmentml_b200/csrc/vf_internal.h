@@ -1,5 +1,6 @@
 // vf_internal.h — shared declarations of libvoxfrag (not part of the public ABI; see include/voxfrag.h).
 #pragma once
+#include <sched.h>
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -94,6 +95,7 @@ struct vf_ctx {
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     cudaEvent_t ev_block = nullptr;  // cudaEventBlockingSync: waits that give the host core back (vf_ctx_set_blocking_sync)
     bool blocking_sync = false;
+    bool yield_wait = false;  // waits poll and give the core to any runnable thread between polls (vf_ctx_set_blocking_sync(ctx, 2))
     uint32_t flood_levels = 0;  // width of a flood round's distance window; 0 = the library default (vf_ctx_set_flood_levels)
     int flood_coop = 4;         // flood: CTAs per SM of the cooperative round loop, 0 = one launch per round (vf_ctx_set_flood_mode)
     const void* hist_clean = nullptr;  // histogram: device bins at this address are known to be zero (the previous call left them so)
@@ -136,9 +138,12 @@ struct vf_grid {
 inline cudaError_t vf_sync(vf_ctx* c)
 {
     ++c->host_waits;
-    if (!c->blocking_sync) return cudaStreamSynchronize(c->stream);
-    const cudaError_t e = cudaEventRecord(c->ev_block, c->stream);
-    return e != cudaSuccess ? e : cudaEventSynchronize(c->ev_block);
+    if (!c->blocking_sync && !c->yield_wait) return cudaStreamSynchronize(c->stream);
+    cudaError_t e = cudaEventRecord(c->ev_block, c->stream);
+    if (e != cudaSuccess) return e;
+    if (c->blocking_sync) return cudaEventSynchronize(c->ev_block);
+    while ((e = cudaEventQuery(c->ev_block)) == cudaErrorNotReady) sched_yield();
+    return e;
 }
 
 vf_status vf_scratch_reserve(vf_ctx* ctx, VfScratch& s, size_t bytes);
