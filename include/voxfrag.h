@@ -195,6 +195,10 @@ vf_status vf_make_seeds(vf_grid* g, uint32_t n, uint32_t n_extra, int random_mod
 /* ------------------------------------------------------------------ F1..F3: fragmentation (class fracturer::Fracturer) */
 /* NaiveFracturer::build (NaiveFracturer.cpp:215-225; spec = buildCPU :26-68 / naiveFracturer-comp.glsl:19-43) */
 vf_status vf_fracture_naive(vf_grid* g, const uint32_t* seeds, uint32_t nseeds, int dfunc);
+/* the same on ONE SLAB of a grid cut along x (multi-GPU; the reference is single-GPU): `slab` holds planes x_origin ..
+ * x_origin + X(slab) - 1 of a grid of X_full planes, halo planes included (nearest-seed labels are pointwise: the halo is computed, not
+ * exchanged); seeds in the coordinates of the whole grid.  Bit-identical to the same planes of vf_fracture_naive on the whole grid. */
+vf_status vf_fracture_naive_slab(vf_grid* slab, const uint32_t* seeds, uint32_t nseeds, int dfunc, uint32_t x_origin, uint32_t X_full);
 /* FloodFracturer::build (FloodFracturer.cpp:98-191) under the deterministic lowest-seed-index rule.
  * dfunc MANHATTAN -> 6-neighbourhood, otherwise 26 (FloodFracturer.cpp:114).  id_bits 0/8 or 15 (see vf_params). */
 vf_status vf_fracture_flood(vf_grid* g, const uint32_t* seeds, uint32_t nseeds, int dfunc, int id_bits, vf_flood_stats* stats);
@@ -233,6 +237,12 @@ vf_status vf_detect_boundaries(vf_grid* g, int boundary_size);           /* Regu
  * the context is synchronised. */
 vf_status vf_erode(vf_grid* g, int erosion_type, uint32_t size, uint32_t iterations, float probability, float threshold,
                    const float* noise, uint32_t nnoise, int boundary_mode);
+/* ONE erosion pass of RegularGrid::erode's loop (erodeGrid-comp.glsl + copyGrid, RegularGrid.cpp:137-152) without detectBoundaries before
+ * and without the sweep after it — for a slab of a grid cut along x: vf_detect_boundaries, halo exchange, { vf_erode_pass, halo exchange }
+ * per iteration, vf_remove_isolated_regions_grid (voxelfragmentml_b200/slab.py: LabelSlab).  cell_offset = index of the slab's first cell
+ * (halo included) in the whole grid: the noise is indexed by the cell's position there. */
+vf_status vf_erode_pass(vf_grid* g, int erosion_type, uint32_t size, float probability, float threshold, const float* noise, uint32_t nnoise,
+                        int boundary_mode, uint64_t cell_offset);
 vf_status vf_remove_isolated_regions_grid(vf_grid* g);                   /* RegularGrid::removeIsolatedRegions, RegularGrid.cpp:1006-1015 (snapshot semantics) */
 vf_status vf_undo_mask(vf_grid* g);                                      /* RegularGrid::undoMask, RegularGrid.cpp:488-503 */
 vf_status vf_reset_filling(vf_grid* g);                                  /* RegularGrid::resetFilling, :412-418 */

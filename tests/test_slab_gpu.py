@@ -96,3 +96,66 @@ def test_native_exchange_loop_over_nccl():
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port", "29641",
                         os.path.join(here, "slab_native_worker.py")], capture_output=True, text=True, timeout=900)
     assert p.returncode == 0 and "SLAB_NATIVE_OK" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
+
+
+def _label_slabs(g, nslabs):
+    from voxelfragmentml_b200 import slab
+
+    import voxelfragmentml_b200 as vf
+
+    X = g.shape[0]
+    parts = slab.partition(X, nslabs)
+    ctxs = [vf.Context(0) for _ in parts]
+    slabs = [slab.LabelSlab(c, g[x0 - int(x0 > 0) : x1 + int(x1 < X)], x0, x1, X) for c, (x0, x1) in zip(ctxs, parts)]
+    return ctxs, slabs
+
+
+@pytest.mark.parametrize("nslabs", [2, 3, 5])
+@pytest.mark.parametrize("dims", [(50, 40, 64), (37, 26, 44), (33, 21, 27)])
+def test_label_slabs_naive_and_erode_match_the_whole_grid(orc, nslabs, dims):
+    """the operators that shard with a one-cell halo and no iteration.  Nearest-seed fragmentation per slab (halo planes computed,
+    not exchanged) equals the oracle on the whole grid; detectBoundaries + erosion passes + the 3^3 sweep with a halo exchange after every
+    pass equal RegularGrid::erode on the whole grid, noise indexed by the cell's position in the whole grid.  Tiled (Z % 8, Z % 4) and generic paths."""
+    from voxelfragmentml_b200 import slab
+
+    g = random_blob_grid(dims, 5, fill=0.8).astype(np.uint16)
+    seeds = pick_seeds(g, 9, 4)
+    noise = orc.Rng(1080).fill_noise(7001)
+    for dfunc, bmode in ((0, 0), (1, 1), (2, 0)):
+        want = orc.naive(g.copy(), seeds, dfunc)
+        for k, (etype, iters, prob, thr) in enumerate(((1, 3, 0.5, 0.5), (0, 2, 0.9, 0.8))):
+            ctxs, slabs = _label_slabs(g, nslabs)
+            for s in slabs:
+                s.naive(seeds, dfunc)
+            if k == 0:
+                got = np.concatenate([s.owned() for s in slabs])
+                assert np.array_equal(got, want), f"naive dfunc {dfunc}: {int((got != want).sum())} cells differ"
+                for r in range(len(slabs) - 1):  # the computed halo planes equal the neighbour's owned planes
+                    assert np.array_equal(slabs[r].halo(1).cpu().numpy(), slabs[r + 1].boundary(0).cpu().numpy())
+                    assert np.array_equal(slabs[r + 1].halo(0).cpu().numpy(), slabs[r].boundary(1).cpu().numpy())
+            wantE = orc.erode(want.copy(), noise, etype, 3, iters, prob, thr, boundary_mode=bmode)
+            slab.erode_slabs(slabs, etype, 3, iters, prob, thr, noise, bmode)
+            gotE = np.concatenate([s.owned() for s in slabs])
+            assert np.array_equal(gotE, wantE), f"erode type {etype} dfunc {dfunc} mode {bmode}: {int((gotE != wantE).sum())} cells differ"
+            for s in slabs:
+                s.close()
+            for c in ctxs:
+                c.close()
+
+
+def test_label_slabs_over_nccl():
+    """the same operators with one slab per GPU and the halo planes travelling over NCCL (needs >= 2 GPUs); tests/slab_labels_worker.py checks"""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least two GPUs")
+    world = 8 if ngpu >= 8 else (4 if ngpu >= 4 else 2)
+    here = os.path.dirname(os.path.abspath(__file__))
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port", "29643",
+                        os.path.join(here, "slab_labels_worker.py")], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "SLAB_LABELS_OK" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]

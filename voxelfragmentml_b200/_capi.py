@@ -102,6 +102,7 @@ SIGNATURES = {
     "vf_merge_seeds": (C.c_int, [_vp, _u32, _vp, _u32, C.c_int]),
     "vf_make_seeds": (C.c_int, [_vp, _u32, _u32, C.c_int, C.c_int, _vp, _u32, C.POINTER(_u32)]),
     "vf_fracture_naive": (C.c_int, [_vp, _vp, _u32, C.c_int]),
+    "vf_fracture_naive_slab": (C.c_int, [_vp, _vp, _u32, C.c_int, _u32, _u32]),
     "vf_fracture_flood": (C.c_int, [_vp, _vp, _u32, C.c_int, C.c_int, C.POINTER(VfFloodStats)]),
     "vf_flood_slab_init": (C.c_int, [_vp, _vp, _vp, _u32, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "vf_flood_slab_relax": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
@@ -116,6 +117,7 @@ SIGNATURES = {
     "vf_remove_isolated_regions": (C.c_int, [_vp, _vp, _u32]),
     "vf_detect_boundaries": (C.c_int, [_vp, C.c_int]),
     "vf_erode": (C.c_int, [_vp, C.c_int, _u32, _u32, C.c_float, C.c_float, _vp, _u32, C.c_int]),
+    "vf_erode_pass": (C.c_int, [_vp, C.c_int, _u32, C.c_float, C.c_float, _vp, _u32, C.c_int, C.c_uint64]),
     "vf_remove_isolated_regions_grid": (C.c_int, [_vp]),
     "vf_undo_mask": (C.c_int, [_vp]),
     "vf_reset_filling": (C.c_int, [_vp]),

@@ -182,7 +182,7 @@ __device__ __noinline__ void scan_chunk(const ushort4* __restrict__ seeds, int S
 template <int DF, int VEC>
 __global__ void __launch_bounds__(kWarps * 32, 4)
 naive_brick_kernel(uint16_t* __restrict__ grid, int X, int Y, int Z, const ushort4* __restrict__ seeds_g, int S, FastDiv div_nbz, FastDiv div_nby,
-                   unsigned total_bricks)
+                   unsigned total_bricks, int xb)  // xb: first plane to label (0, or a slab's first plane: `grid` then points at the virtual plane 0)
 {
     typedef typename VecT<VEC>::type V;
     constexpr int BZ = 8 * VEC;  // brick extent along z
@@ -205,7 +205,7 @@ naive_brick_kernel(uint16_t* __restrict__ grid, int X, int Y, int Z, const ushor
         const int bz = brick - t * div_nbz.d;
         const unsigned bx = div_nby.div(t);
         const int by = t - bx * div_nby.d;
-        const int x0 = bx * kIts, y0 = by * 4, z0 = bz * BZ;
+        const int x0 = xb + bx * kIts, y0 = by * 4, z0 = bz * BZ;
         const int y = y0 + ly, z = z0 + lz * VEC;
         const bool rowvalid = (y < Y) && (z < Z);  // Z % VEC == 0, so a valid chunk is entirely inside the row
         const int nits = min(kIts, X - x0);
@@ -377,13 +377,13 @@ naive_brick_kernel(uint16_t* __restrict__ grid, int X, int Y, int Z, const ushor
 
 // generic path: any dims, float32 compare exactly as buildCPU.  One thread per voxel.
 template <int DF>
-__global__ void __launch_bounds__(256) naive_generic_kernel(uint16_t* __restrict__ grid, int X, int Y, int Z, const ushort4* __restrict__ seeds_g, int S)
+__global__ void __launch_bounds__(256) naive_generic_kernel(uint16_t* __restrict__ grid, int X, int Y, int Z, const ushort4* __restrict__ seeds_g, int S, int xb)
 {
     extern __shared__ ushort4 smem[];
     for (int i = threadIdx.x; i < S; i += blockDim.x) smem[i] = seeds_g[i];
     __syncthreads();
     const size_t n = (size_t)X * Y * Z;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    for (size_t i = (size_t)xb * Y * Z + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const unsigned short own = grid[i];
         if (own == VF_VOXEL_EMPTY) continue;
         const int z = (int)(i % Z);
@@ -394,56 +394,76 @@ __global__ void __launch_bounds__(256) naive_generic_kernel(uint16_t* __restrict
 }
 
 template <int DF, int VEC>
-vf_status launch_brick(vf_grid* g, const ushort4* d_seeds, int S)
+vf_status launch_brick(vf_grid* g, const ushort4* d_seeds, int S, int xb)
 {
     vf_ctx* c = g->ctx;
-    const int nbx = (g->X + kIts - 1) / kIts, nby = (g->Y + 3) / 4, nbz = (g->Z + 8 * VEC - 1) / (8 * VEC);
+    const int nbx = (g->X - xb + kIts - 1) / kIts, nby = (g->Y + 3) / 4, nbz = (g->Z + 8 * VEC - 1) / (8 * VEC);
     const unsigned total = (unsigned)nbx * nby * nbz;
     VF_REQUIRE((uint64_t)total * (uint64_t)max(nbz, nby) < (1ull << 32), VF_ERR_CAPACITY, "naive: grid too large for the brick index decode");
     const size_t smem = (size_t)kWarps * kIts * 32 * (VEC * 2) + ((size_t)((S + 3) & ~3) + kWarps * kCMax) * sizeof(ushort4) + (size_t)kWarps * kIts * 32;
     auto kern = naive_brick_kernel<DF, VEC>;
     if (smem > 48 * 1024) VF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned blocks = min((total + kWarps - 1) / kWarps, (unsigned)c->num_sms * 4u);
-    kern<<<blocks, kWarps * 32, smem, c->stream>>>(g->d, (int)g->X, (int)g->Y, (int)g->Z, d_seeds, S, FastDiv((unsigned)nbz), FastDiv((unsigned)nby), total);
+    kern<<<blocks, kWarps * 32, smem, c->stream>>>(g->d, (int)g->X, (int)g->Y, (int)g->Z, d_seeds, S, FastDiv((unsigned)nbz), FastDiv((unsigned)nby), total, xb);
     VF_LAUNCHED(c);
     return VF_OK;
 }
 
 template <int DF>
-vf_status launch_generic(vf_grid* g, const ushort4* d_seeds, int S)
+vf_status launch_generic(vf_grid* g, const ushort4* d_seeds, int S, int xb)
 {
     vf_ctx* c = g->ctx;
     const size_t smem = (size_t)S * sizeof(ushort4);
     auto kern = naive_generic_kernel<DF>;
     if (smem > 48 * 1024) VF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned blocks = (unsigned)min((g->n() + 255) / 256, (size_t)c->num_sms * 16);
-    kern<<<blocks, 256, smem, c->stream>>>(g->d, (int)g->X, (int)g->Y, (int)g->Z, d_seeds, S);
+    const unsigned blocks = (unsigned)min(((size_t)(g->X - xb) * g->Y * g->Z + 255) / 256, (size_t)c->num_sms * 16);
+    kern<<<blocks, 256, smem, c->stream>>>(g->d, (int)g->X, (int)g->Y, (int)g->Z, d_seeds, S, xb);
     VF_LAUNCHED(c);
     return VF_OK;
 }
 
 template <int DF>
-vf_status dispatch(vf_grid* g, const ushort4* d_seeds, int S)
+vf_status dispatch(vf_grid* g, const ushort4* d_seeds, int S, int xb, uint32_t Xfull)
 {
-    const uint32_t maxdim = max(g->X, max(g->Y, g->Z));
+    const uint32_t maxdim = max(Xfull, max(g->Y, g->Z));
     const bool int_exact = DF != VF_EUCLIDEAN || maxdim <= 1182;  // float sqrt injective on integer d^2
     const bool aligned = ((uintptr_t)g->d & 15) == 0;
-    if (int_exact && aligned && g->Z % 8 == 0) return launch_brick<DF, 8>(g, d_seeds, S);
-    if (int_exact && aligned && g->Z % 4 == 0) return launch_brick<DF, 4>(g, d_seeds, S);
-    return launch_generic<DF>(g, d_seeds, S);
+    if (int_exact && aligned && g->Z % 8 == 0) return launch_brick<DF, 8>(g, d_seeds, S, xb);
+    if (int_exact && aligned && g->Z % 4 == 0) return launch_brick<DF, 4>(g, d_seeds, S, xb);
+    return launch_generic<DF>(g, d_seeds, S, xb);
 }
 
 }  // namespace
 
-vf_status vf_k_naive(vf_grid* g, const ushort4* d_seeds, uint32_t nseeds, int dfunc)
+// planes xb .. g->X - 1 of the grid `g` describes (xb = 0: all of it); Xfull: the extent of the whole grid along x, which decides the arithmetic
+static vf_status naive_planes(vf_grid* g, const ushort4* d_seeds, uint32_t nseeds, int dfunc, int xb, uint32_t Xfull)
 {
     VF_REQUIRE(nseeds <= 8192, VF_ERR_CAPACITY, "naive: %u seeds exceed the shared-memory seed table (8192)", nseeds);
     switch (dfunc) {
-    case VF_EUCLIDEAN: return dispatch<VF_EUCLIDEAN>(g, d_seeds, (int)nseeds);
-    case VF_MANHATTAN: return dispatch<VF_MANHATTAN>(g, d_seeds, (int)nseeds);
-    case VF_CHEBYSHEV: return dispatch<VF_CHEBYSHEV>(g, d_seeds, (int)nseeds);
+    case VF_EUCLIDEAN: return dispatch<VF_EUCLIDEAN>(g, d_seeds, (int)nseeds, xb, Xfull);
+    case VF_MANHATTAN: return dispatch<VF_MANHATTAN>(g, d_seeds, (int)nseeds, xb, Xfull);
+    case VF_CHEBYSHEV: return dispatch<VF_CHEBYSHEV>(g, d_seeds, (int)nseeds, xb, Xfull);
     default: return vf_set_error(VF_ERR_INVALID_DISTANCE, "Invalid distance function %d", dfunc);
     }
+}
+
+vf_status vf_k_naive(vf_grid* g, const ushort4* d_seeds, uint32_t nseeds, int dfunc) { return naive_planes(g, d_seeds, nseeds, dfunc, 0, g->X); }
+
+// F1 on one slab of a grid cut along x (multi-GPU): `slab` holds planes x_origin .. x_origin + slab->X - 1 of a grid of X_full planes
+// (halo planes included — nearest-seed labels are pointwise, so the halo is computed, not exchanged); seeds in the coordinates of the whole grid.
+extern "C" vf_status vf_fracture_naive_slab(vf_grid* slab, const uint32_t* seeds, uint32_t nseeds, int dfunc, uint32_t x_origin, uint32_t X_full)
+{
+    VF_REQUIRE(slab != nullptr, VF_ERR_INVALID_ARGUMENT, "null grid");
+    VF_TRY(vf_enter(slab->ctx));
+    VF_REQUIRE(dfunc >= 0 && dfunc <= 2, VF_ERR_INVALID_DISTANCE, "Invalid distance function %d", dfunc);
+    VF_REQUIRE((uint64_t)x_origin + slab->X <= X_full, VF_ERR_INVALID_ARGUMENT, "naive: slab planes %u..%u lie outside a grid of %u planes", x_origin,
+               x_origin + slab->X - 1, X_full);
+    ushort4* d_seeds = nullptr;
+    VF_TRY(vf_upload_seeds(slab->ctx, seeds, nseeds, X_full, slab->Y, slab->Z, &d_seeds));
+    vf_grid view = *slab;  // the slab seen as planes x_origin .. of a grid that starts x_origin planes earlier (those planes are never touched)
+    view.X = x_origin + slab->X;
+    view.d = slab->d - (size_t)x_origin * slab->Y * slab->Z;
+    return naive_planes(&view, d_seeds, nseeds, dfunc, (int)x_origin, X_full);
 }
 
 extern "C" vf_status vf_fracture_naive(vf_grid* g, const uint32_t* seeds, uint32_t nseeds, int dfunc)

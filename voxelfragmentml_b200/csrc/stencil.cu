@@ -55,6 +55,7 @@ struct ErodeArgs {
     unsigned erodes[28];
     unsigned long long nn_magic;  // 2^64 / nnoise + 1: exact 32-bit modulo by multiplication when the grid has < 2^32 cells
     int idx32;
+    unsigned long long cell_offset;  // index of this grid's first cell in the grid the noise is indexed by (a slab of a larger grid; else 0)
     // Change tracking for the sparse follow-up passes (erode_sparse_kernel, sweep_sparse_kernel); all null when nothing is recorded.
     // `ever`: one bit per cell, set when some pass of this call empties the cell (a cell is emptied at most once).  The thread that sets the bit
     // appends the cell to this pass's list and to the call's list, so the lists hold no duplicates; a list that outgrows kListCap is ignored by
@@ -87,6 +88,7 @@ __device__ __forceinline__ void note_eroded(const ErodeArgs& ea, size_t gi)
 
 __device__ __forceinline__ unsigned noise_index(const ErodeArgs& ea, size_t gi)
 {
+    gi += ea.cell_offset;
     if (ea.idx32) return (unsigned)__umul64hi(ea.nn_magic * (unsigned)gi, (unsigned long long)ea.nnoise);
     return (unsigned)(gi % ea.nnoise);
 }
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(256) stencil_kernel(const uint16_t* __restrict
             // erodeGrid-comp.glsl:31-58 for maskSize 3
             uint16_t out = own;
             const bool isB = ea.boundary_mode == 0 ? (own & 0x7FFFu) != 0 : (own >> 15) != 0;
-            if (own > VF_VOXEL_FREE && isB && ea.noise[gi % ea.nnoise] < ea.prob) {
+            if (own > VF_VOXEL_FREE && isB && ea.noise[noise_index(ea, gi)] < ea.prob) {
                 unsigned count = 0, visited = 0;
 #pragma unroll
                 for (int dx = -1; dx <= 1; ++dx)
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(256) erode_generic_kernel(const uint16_t* __re
         const uint16_t own = src[gi];
         uint16_t out = own;
         const bool isB = ea.boundary_mode == 0 ? (own & 0x7FFFu) != 0 : (own >> 15) != 0;
-        if (own > VF_VOXEL_FREE && isB && ea.noise[gi % ea.nnoise] < ea.prob) {
+        if (own > VF_VOXEL_FREE && isB && ea.noise[noise_index(ea, gi)] < ea.prob) {
             const int z = (int)(gi % d.Z);
             const size_t r = gi / d.Z;
             const int y = (int)(r % d.Y), x = (int)(r / d.Y);
@@ -862,8 +864,10 @@ extern "C" vf_status vf_remove_isolated_regions_grid(vf_grid* g)
     return VF_OK;
 }
 
-extern "C" vf_status vf_erode(vf_grid* g, int type, uint32_t size, uint32_t iterations, float prob, float thr, const float* noise, uint32_t nnoise,
-                              int boundary_mode)
+// skip_detect / skip_sweep: the caller runs detectBoundaries / the final sweep itself (a slab of a larger grid exchanges its halo planes between
+// the passes); cell_offset: index of the grid's first cell in the grid the noise table is indexed by.
+static vf_status erode_impl(vf_grid* g, int type, uint32_t size, uint32_t iterations, float prob, float thr, const float* noise, uint32_t nnoise,
+                            int boundary_mode, bool skip_detect, bool skip_sweep, unsigned long long cell_offset)
 {
     VF_REQUIRE(g != nullptr && noise != nullptr && nnoise > 0, VF_ERR_INVALID_ARGUMENT, "erode: null grid or noise table");
     VF_REQUIRE(type >= 0 && type <= 2, VF_ERR_INVALID_ARGUMENT, "erode: bad convolution type %d", type);
@@ -888,7 +892,8 @@ extern "C" vf_status vf_erode(vf_grid* g, int type, uint32_t size, uint32_t iter
             if (activation < limit) ea.erodes[visited] |= 1u << count;
         }
     ea.nn_magic = ~0ull / nnoise + 1;
-    ea.idx32 = n <= 0xFFFFFFFFull;
+    ea.idx32 = cell_offset + n <= 0xFFFFFFFFull;
+    ea.cell_offset = cell_offset;
     if (size == 3)
         for (int i = 0; i < 27; ++i)
             if (mask[i] != 0.0f) ea.maskbits |= 1u << i;
@@ -908,7 +913,7 @@ extern "C" vf_status vf_erode(vf_grid* g, int type, uint32_t size, uint32_t iter
     const int ntx_ = (d.X + SX - 1) / SX, nty_ = (d.Y + SYT - 1) / SYT;
     const bool tiled = ((d.Z % 8 == 0 && (((uintptr_t)a | (uintptr_t)b) & 15) == 0) || (d.Z % 4 == 0 && (((uintptr_t)a | (uintptr_t)b) & 7) == 0)) && nty_ <= 65535 &&
                        ntx_ <= 65535;
-    const bool s0_ok = size == 3 && iterations >= 1 && n <= 0xFFFFFFFFull && tiled;
+    const bool s0_ok = size == 3 && iterations >= 1 && n <= 0xFFFFFFFFull && tiled && !skip_sweep;
     const uint32_t nwords = (uint32_t)((n + 31) / 32);
     constexpr uint32_t kMaxTracked = 60;  // per-pass counters in the header; longer calls take full passes
     const bool track = (sparse_ok || s0_ok) && iterations <= kMaxTracked;
@@ -929,7 +934,7 @@ extern "C" vf_status vf_erode(vf_grid* g, int type, uint32_t size, uint32_t iter
         ea.ever_list = track && s0_ok ? ever_list : nullptr, ea.ever_count = track && s0_ok ? counters + 63 : nullptr;
         ea.s0kill = (track && s0_ok && it == 0) ? s0kill : nullptr;
         if (it == 0) {
-            VF_TRY(launch_stencil(&view, OP_DETECT, a, a, ea));  // only in the first iteration: see below
+            if (!skip_detect) VF_TRY(launch_stencil(&view, OP_DETECT, a, a, ea));  // only in the first iteration: see below
             // The noise table is handled AFTER the detect pass is queued: comparing a 4 MB table with its shadow takes the host longer than a
             // kernel launch, and the GPU would sit idle meanwhile.  The table travels on the stream: from pageable memory the call returns once the
             // driver has staged it; a pinned table must stay valid until the context is synchronised (documented in voxfrag.h).  A table identical
@@ -966,9 +971,29 @@ extern "C" vf_status vf_erode(vf_grid* g, int type, uint32_t size, uint32_t iter
         VF_LAUNCHED(c);
         return VF_OK;
     }
+    if (skip_sweep) {
+        if (a != g->d) VF_CUDA(cudaMemcpyAsync(g->d, a, n * 2, cudaMemcpyDeviceToDevice, c->stream));
+        return VF_OK;
+    }
     VF_TRY(launch_stencil(&view, OP_SWEEP, a, b, ea));  // RegularGrid.cpp:155
     if (b != g->d) VF_CUDA(cudaMemcpyAsync(g->d, b, n * 2, cudaMemcpyDeviceToDevice, c->stream));
     return VF_OK;
+}
+
+extern "C" vf_status vf_erode(vf_grid* g, int type, uint32_t size, uint32_t iterations, float prob, float thr, const float* noise, uint32_t nnoise,
+                              int boundary_mode)
+{
+    return erode_impl(g, type, size, iterations, prob, thr, noise, nnoise, boundary_mode, false, false, 0);
+}
+
+// ONE erosion pass (erodeGrid-comp.glsl + copyGrid, RegularGrid.cpp:137-152) without detectBoundaries before it and without the sweep after it,
+// for a slab of a grid cut along x (multi-GPU): the caller tags the boundaries once (vf_detect_boundaries), exchanges the halo
+// planes, runs this pass + an exchange per iteration, then vf_remove_isolated_regions_grid.  cell_offset = (first plane of the slab, halo
+// included) * Y * Z: the noise is indexed by the cell's position in the whole grid.
+extern "C" vf_status vf_erode_pass(vf_grid* g, int type, uint32_t size, float prob, float thr, const float* noise, uint32_t nnoise, int boundary_mode,
+                                   uint64_t cell_offset)
+{
+    return erode_impl(g, type, size, 1, prob, thr, noise, nnoise, boundary_mode, true, true, cell_offset);
 }
 
 static vf_status histogram_impl(vf_grid* g, uint32_t* counts, uint64_t* occupied, bool unmask)

@@ -115,6 +115,105 @@ class GpuSlab:
             self.grid.close()
 
 
+class LabelSlab:
+    """One slab of a label grid on one GPU for the operators that need no iteration across slabs: nearest-seed
+    fragmentation (pointwise: the halo planes are computed), detectBoundaries / erosion passes / the 3^3 sweep (one-cell stencils: the
+    halo planes are exchanged after every pass).  The slab lives in a torch tensor [(halo?) + xs + (halo?), Y, Z] so that its planes can
+    travel (copies inside one process, NCCL send / recv through torch.distributed across ranks).  Connected-to-seed cleanup (C1) is
+    a whole-grid connectivity question and is not sharded this way."""
+
+    def __init__(self, ctx, occupancy_with_halo, x0: int, x1: int, X: int):
+        """occupancy_with_halo: host uint16 [planes, Y, Z] = planes x0 - (x0 > 0) .. x1 - 1 + (x1 < X) of the whole grid"""
+        import torch
+
+        from .api import RegularGrid
+
+        self.ctx, self.x0, self.x1, self.X = ctx, x0, x1, X
+        self.has_lo, self.has_hi = int(x0 > 0), int(x1 < X)
+        self.origin = x0 - self.has_lo  # plane of the whole grid the slab's plane 0 holds
+        host = np.ascontiguousarray(occupancy_with_halo, np.uint16)
+        assert host.shape[0] == (x1 - x0) + self.has_lo + self.has_hi
+        self.t = torch.from_numpy(host.view(np.int16)).to(f"cuda:{ctx.device}")
+        self.shape = tuple(host.shape)
+        self.grid = RegularGrid(ctx, self.shape, device_ptr=self.t.data_ptr())
+        torch.cuda.synchronize()  # the upload ran on torch's stream, the kernels run on the context's
+
+    def naive(self, seeds_global, dfunc: int):
+        s = np.ascontiguousarray(seeds_global, np.uint32)
+        check(self.ctx._lib.vf_fracture_naive_slab(self.grid._h, ptr(s), len(s), int(dfunc), self.origin, self.X))
+
+    def detect_boundaries(self, size: int = 1):
+        self.grid.detectBoundaries(size)
+
+    def erode_pass(self, etype, size, prob, thr, noise, boundary_mode=0):
+        noise = np.ascontiguousarray(noise, np.float32)
+        offset = self.origin * self.shape[1] * self.shape[2]
+        check(self.ctx._lib.vf_erode_pass(self.grid._h, int(etype), int(size), float(prob), float(thr), ptr(noise), len(noise), int(boundary_mode), offset))
+
+    def sweep(self):
+        self.grid.removeIsolatedRegions()
+
+    def boundary(self, side: int):
+        """owned plane next to the lo (0) / hi (1) halo"""
+        return self.t[1] if side == 0 else self.t[self.shape[0] - 2]
+
+    def halo(self, side: int):
+        return self.t[0] if side == 0 else self.t[self.shape[0] - 1]
+
+    def owned(self):
+        """host copy of the owned planes"""
+        self.ctx.synchronize()
+        a = self.t.cpu().numpy().view(np.uint16)
+        return a[self.has_lo : a.shape[0] - self.has_hi]
+
+    def close(self):
+        self.grid.close()
+
+
+def exchange_labels_local(slabs):
+    """halo planes <- the neighbours' owned boundary planes, all slabs in one process"""
+    import torch
+
+    for s in slabs:
+        s.ctx.synchronize()
+    for r in range(len(slabs) - 1):
+        slabs[r].halo(1).copy_(slabs[r + 1].boundary(0))
+        slabs[r + 1].halo(0).copy_(slabs[r].boundary(1))
+    torch.cuda.synchronize()
+
+
+def exchange_labels(slab, rank: int, world: int, dist):
+    """one slab per rank: the owned boundary planes travel with dist.batch_isend_irecv (NCCL over NVLink on a GPU box)"""
+    import torch
+
+    slab.ctx.synchronize()
+    ops = []
+    for side, peer in ((0, rank - 1), (1, rank + 1)):
+        if 0 <= peer < world:
+            ops.append(dist.P2POp(dist.isend, slab.boundary(side).contiguous(), peer))
+            ops.append(dist.P2POp(dist.irecv, slab.halo(side), peer))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        torch.cuda.synchronize()
+
+
+def erode_slabs(slabs, etype, size, iterations, prob, thr, noise, boundary_mode=0, exchange=None):
+    """RegularGrid::erode (RegularGrid.cpp:82-159) over slabs: detectBoundaries once, an erosion pass per iteration, the 3^3 sweep, with a
+    halo exchange after every pass.  `exchange()` defaults to copies between the slabs of this process."""
+    ex = exchange or (lambda: exchange_labels_local(slabs))
+    for s in slabs:
+        s.detect_boundaries(1)
+    ex()
+    for _ in range(iterations):
+        for s in slabs:
+            s.erode_pass(etype, size, prob, thr, noise, boundary_mode)
+        ex()
+    for s in slabs:
+        s.sweep()
+    ex()
+
+
 def nccl_comm(ctx, rank: int, world: int, dist):
     """An NCCL communicator owned by libvoxfrag for the native exchange loop: rank 0 draws the unique id (vf_nccl_unique_id), the 128 bytes
     travel through torch.distributed (any backend), every rank joins (vf_nccl_comm_create).  Free with ctx._lib.vf_nccl_comm_destroy."""
