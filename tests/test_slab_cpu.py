@@ -84,3 +84,55 @@ def test_gloo_protocol_matches_single_address_space(orc, tmp_path, world, dfunc)
     assert np.array_equal(got, want)
     iters = [int(np.load(tmp_path / f"meta_{r}.npy")[0]) for r in range(world)]
     assert len(set(iters)) == 1 and iters[0] >= 2  # every rank leaves the loop in the same iteration
+
+
+class _HostLabelSlab:
+    """stand-in with LabelSlab's plane surface: planes x0 - (x0 > 0) .. x1 - 1 + (x1 < X) of a host grid as a torch tensor"""
+
+    def __init__(self, g, x0, x1):
+        X = g.shape[0]
+        self.t = torch.from_numpy(g[x0 - int(x0 > 0) : x1 + int(x1 < X)].copy().view(np.int16))
+
+    def boundary(self, side):
+        return self.t[1] if side == 0 else self.t[self.t.shape[0] - 2]
+
+    def halo(self, side):
+        return self.t[0] if side == 0 else self.t[self.t.shape[0] - 1]
+
+
+def _label_worker(rank, world, port, outdir):
+    import sys
+
+    sys.path.insert(0, ROOT)
+    from voxelfragmentml_b200 import slab
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    X = 11
+    g = (np.arange(X * 5 * 8, dtype=np.int64).reshape(X, 5, 8) % 60000).astype(np.uint16)
+    x0, x1 = slab.partition(X, world)[rank]
+    s = _HostLabelSlab(g, x0, x1)
+    for side, peer in ((0, rank - 1), (1, rank + 1)):
+        if 0 <= peer < world:
+            s.halo(side).fill_(-1)
+    slab.exchange_labels(s, rank, world, dist)
+    np.save(os.path.join(outdir, f"slab_{rank}.npy"), s.t.numpy().view(np.uint16))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_label_halo_exchange(tmp_path, world):
+    """exchange_labels (the halo exchange of the one-cell-halo operators, slab.LabelSlab): after it every halo plane holds the neighbour's
+    owned boundary plane, i.e. every rank's tensor is again the slice of the whole grid it stands for."""
+    from voxelfragmentml_b200 import slab
+
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    mp.spawn(_label_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    X = 11
+    g = (np.arange(X * 5 * 8, dtype=np.int64).reshape(X, 5, 8) % 60000).astype(np.uint16)
+    for r, (x0, x1) in enumerate(slab.partition(X, world)):
+        got = np.load(tmp_path / f"slab_{r}.npy")
+        assert np.array_equal(got, g[x0 - int(x0 > 0) : x1 + int(x1 < X)])

@@ -183,19 +183,24 @@ def exchange_labels_local(slabs):
 
 
 def exchange_labels(slab, rank: int, world: int, dist):
-    """one slab per rank: the owned boundary planes travel with dist.batch_isend_irecv (NCCL over NVLink on a GPU box)"""
+    """one slab per rank: the owned boundary planes travel with dist.batch_isend_irecv (NCCL over NVLink on a GPU box).  `slab` needs
+    boundary(side) / halo(side) returning 16-bit planes and, when it computes on a stream of its own, ctx.synchronize()."""
     import torch
 
-    slab.ctx.synchronize()
-    ops = []
+    if getattr(slab, "ctx", None) is not None:
+        slab.ctx.synchronize()
+    ops, cuda = [], False
     for side, peer in ((0, rank - 1), (1, rank + 1)):
         if 0 <= peer < world:
-            ops.append(dist.P2POp(dist.isend, slab.boundary(side).contiguous(), peer))
-            ops.append(dist.P2POp(dist.irecv, slab.halo(side), peer))
+            # planes travel as bytes: NCCL has no 16-bit integer type
+            ops.append(dist.P2POp(dist.isend, slab.boundary(side).contiguous().view(torch.uint8), peer))
+            ops.append(dist.P2POp(dist.irecv, slab.halo(side).view(torch.uint8), peer))
+            cuda = cuda or slab.halo(side).is_cuda
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
-        torch.cuda.synchronize()
+        if cuda:
+            torch.cuda.synchronize()
 
 
 def erode_slabs(slabs, etype, size, iterations, prob, thr, noise, boundary_mode=0, exchange=None):
