@@ -535,6 +535,10 @@ def run_cuda(args):
         torch.cuda.empty_cache()
         sn = args.slab_size or (2048 if world >= 8 else 1024)
         out["slab"] = slab_measure(rank, local_rank, world, dist, sn, 256, 3, 1, native=True)
+        # the operators that shard with a one-cell halo (naive + erode) on a 1024^3 grid cut the same way (the integer-exact Euclidean kernel
+        # covers extents up to 1182)
+        torch.cuda.empty_cache()
+        out["slab"]["labels"] = slab_labels_measure(rank, local_rank, world, dist, 1024, 64, 3, 1)
     if rank == 0 and not args.no_cpu_baseline:
         cn = args.cpu_size or n
         out["cpu_baseline"], want = cpu_baseline(cn, stages_run)
@@ -819,6 +823,67 @@ def slab_measure(rank, local_rank, world, dist, n, nseeds, steps, warmup, native
             "phases_ms_rank0_last_step": {"init_keys_and_seeds": phases[0], "exchange_loop": phases[1], "finalize": phases[2]} if args_breakdown else None,
             # F2's algorithmic bytes: read every label once, write every label once, against the aggregate HBM roofline of the N GPUs
             "roofline_frac_aggregate": 4.0 * N / (ms * 1e-3) / 1e9 / (peak * world)}
+
+
+def slab_labels_measure(rank, local_rank, world, dist, n, nseeds, steps, warmup):
+    """the operators that shard with a one-cell halo and no iteration — nearest-seed fragmentation (halo planes computed) and
+    RegularGrid::erode (detectBoundaries, three erosion passes, the 3^3 sweep; label planes exchanged over NCCL after every pass) on one
+    n^3 analytic solid cut into x-slabs.  Bit-exact against the oracle on the whole grid in tests/test_slab_gpu.py (small grids, NCCL and
+    in-process exchange).  Wall clock per step, max over ranks."""
+    import torch
+
+    import voxelfragmentml_b200 as vf
+    from voxelfragmentml_b200 import slab, synth
+
+    ctx = vf.Context(local_rank)
+    params = synth.solid_vessel_params(0)
+    seeds = synth.solid_vessel_seeds(n, nseeds, params, 80)
+    noise = noise_table(1080, 1000000)
+    x0, x1 = slab.partition(n, world)[rank]
+    lib = vf._capi.load()
+    first = x0 - int(x0 > 0)
+    planes = (x1 - x0) + int(x0 > 0) + int(x1 < n)
+
+    def fill(grid):
+        vf._capi.check(lib.vf_synth_solid_vessel(grid._h, first, n, *params))
+
+    s = slab.LabelSlab(ctx, fill, x0, x1, n, shape=(planes, n, n))
+    ex = (lambda: slab.exchange_labels(s, rank, world, dist)) if world > 1 else (lambda: None)
+    et, es, ei, ep, eth = CFG3["erosion"]
+    times, t_naive = [], 0.0
+    for it in range(warmup + steps):
+        fill(s.grid)
+        ctx.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        s.naive(seeds, CFG3["dfunc"])
+        ctx.synchronize()
+        t1 = time.perf_counter()
+        slab.erode_slabs([s], et, es, ei, ep, eth, noise, 0, exchange=ex)
+        ctx.synchronize()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+            t_naive = t1 - t0
+    occupied = s.grid.numOccupiedVoxels()
+    s.close()
+    ctx.close()
+    total = float(sum(times))
+    if dist is not None:
+        tt = torch.tensor([total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total = float(tt[0])
+    N = n**3
+    ms = total / steps * 1e3
+    peak, _ = load_peak()
+    return {"metric": "Gvoxels/s nearest-seed fragmented + eroded, one grid over N GPUs", "value": N * steps / total / 1e9, "unit": "Gvoxels/s", "n_gpus": world,
+            "ms_per_step": ms, "naive_ms_rank0_last_step": t_naive * 1e3, "scaling": "strong", "grid": [n, n, n], "seeds": nseeds,
+            "workload": f"{n}^3 analytic solid vessel in {world} x-slabs: NAIVE EUCLIDEAN {nseeds} seeds (halo planes computed) + erode(ELLIPSE,3,3it,p.5,thr.5) = "
+                        "detectBoundaries, 3 erosion passes, 3^3 sweep with a label-plane exchange over NCCL after each of the 5 passes",
+            "halo_bytes_per_rank": 5 * 2 * 2 * n * n * (1 if world > 1 else 0), "labelled_cells_incl_halo_rank0": int(occupied),
+            # 4 B per voxel for F1 + 18 B per voxel for the erode stage (SURVEY 8d), against the aggregate HBM roofline of the N GPUs
+            "roofline_frac_aggregate": 22.0 * N / (ms * 1e-3) / 1e9 / (peak * world)}
 
 
 def run_slab(args):

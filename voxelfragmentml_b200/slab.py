@@ -122,8 +122,9 @@ class LabelSlab:
     travel (copies inside one process, NCCL send / recv through torch.distributed across ranks).  Connected-to-seed cleanup (C1) is
     a whole-grid connectivity question and is not sharded this way."""
 
-    def __init__(self, ctx, occupancy_with_halo, x0: int, x1: int, X: int):
-        """occupancy_with_halo: host uint16 [planes, Y, Z] = planes x0 - (x0 > 0) .. x1 - 1 + (x1 < X) of the whole grid"""
+    def __init__(self, ctx, occupancy_with_halo, x0: int, x1: int, X: int, shape=None):
+        """occupancy_with_halo: host uint16 [planes, Y, Z] = planes x0 - (x0 > 0) .. x1 - 1 + (x1 < X) of the whole grid, or a callable
+        fill(grid) that writes those planes on the device (then pass `shape` = (planes, Y, Z))"""
         import torch
 
         from .api import RegularGrid
@@ -131,11 +132,19 @@ class LabelSlab:
         self.ctx, self.x0, self.x1, self.X = ctx, x0, x1, X
         self.has_lo, self.has_hi = int(x0 > 0), int(x1 < X)
         self.origin = x0 - self.has_lo  # plane of the whole grid the slab's plane 0 holds
-        host = np.ascontiguousarray(occupancy_with_halo, np.uint16)
-        assert host.shape[0] == (x1 - x0) + self.has_lo + self.has_hi
-        self.t = torch.from_numpy(host.view(np.int16)).to(f"cuda:{ctx.device}")
-        self.shape = tuple(host.shape)
+        if callable(occupancy_with_halo):
+            self.shape = tuple(int(d) for d in shape)
+            self.t = torch.empty(self.shape, dtype=torch.int16, device=f"cuda:{ctx.device}")
+        else:
+            host = np.ascontiguousarray(occupancy_with_halo, np.uint16)
+            self.shape = tuple(host.shape)
+            self.t = torch.from_numpy(host.view(np.int16)).to(f"cuda:{ctx.device}")
+        assert self.shape[0] == (x1 - x0) + self.has_lo + self.has_hi
         self.grid = RegularGrid(ctx, self.shape, device_ptr=self.t.data_ptr())
+        if callable(occupancy_with_halo):
+            torch.cuda.synchronize()
+            occupancy_with_halo(self.grid)
+            ctx.synchronize()
         torch.cuda.synchronize()  # the upload ran on torch's stream, the kernels run on the context's
 
     def naive(self, seeds_global, dfunc: int):
