@@ -225,7 +225,7 @@ def test_c1_and_histogram_under_the_other_wait_modes(orc, vessel_grid, wait):
     c.setBlockingSync(wait)
     dense = np.ones((40, 32, 48), np.uint16)
     for grid, ns in ((dense, 9), (vessel_grid, 12)):
-        seeds, _ = orc.seed_uniform(orc.Rng(81), grid, ns)
+        seeds = pick_seeds(grid, ns, 81)
         lab = orc.naive(grid.copy(), seeds, 0)
         want = orc.remove_isolated_regions_cpu(lab.copy(), seeds)
         g = vf.RegularGrid(c, lab.shape)

@@ -457,6 +457,20 @@ __global__ void __launch_bounds__(256) ccl_select_kernel(uint16_t* __restrict__ 
         const int ncell = min(32, g.Z - seg * 32);
         const unsigned valid = ncell == 32 ? 0xFFFFFFFFu : ((1u << ncell) - 1);
         unsigned dead = MODE == MODE_C1 ? valid & ~mm.x : 0u;  // C1: inactive non-EMPTY cells (FREE) are dropped as well
+        if (MODE == MODE_C1 && dead && ncell == 32 && ((uintptr_t)(grid + base) & 15) == 0) {
+            // most inactive cells are EMPTY already (all of them on a surface model's grid): find the others with four 128-bit loads instead of
+            // one 16-bit load per cell
+            const uint4* g4 = reinterpret_cast<const uint4*>(grid + base);
+            unsigned nonzero = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint4 v = g4[k];
+                const unsigned w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                for (int j = 0; j < 4; ++j) nonzero |= ((w[j] & 0xFFFFu) ? 1u : 0u) << (8 * k + 2 * j) | ((w[j] >> 16) ? 1u : 0u) << (8 * k + 2 * j + 1);
+            }
+            dead &= nonzero;
+        }
         unsigned starts = mm.y & mm.x;
         // run starts among the active cells: a start bit on an inactive cell opens no run
         unsigned todo = mm.x;
