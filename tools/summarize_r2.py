@@ -56,7 +56,7 @@ traffic = {}
 with open(os.path.join(P, f"{tag}_ncu_full_summary.md"), "w") as f:
     f.write(f"# {tag} — ncu --set full summaries (one B200)\n\nCommands (tools/collect_r2.sh): `ncu --set full --clock-control none --import-source on -k regex:\"naive_brick|"
             "certificate|resolve_kernel|stencil_fast|erode_sparse|sweep_sparse|sweep_apply|histogram\" -s 9 -c 9 python tools/prof_stage.py 512 naive,c1,erode,hist 2` (the cfg3 stages on the dense "
-            "512^3 grid, second repetition) and `-k regex:flood_round -c 1 python tools/prof_flood1.py 1` (the cfg2 vessel: one cooperative launch = the whole flood phase) and `-k regex:voxelize_brick -s 7 -c 1 python tools/prof_voxelize.py 512` (V2 on the 352x512x352 vessel grid, a warm call). "
+            "512^3 grid, second repetition) and `-k regex:flood_round -c 1 python tools/prof_flood1.py 1` (the cfg2 vessel: one cooperative launch = the whole flood phase) and `-k regex:voxelize_brick -s 4 -c 1 python tools/prof_voxelize.py 512` (V2 on the 352x512x352 vessel grid, a warm call). "
             "One section per distinct kernel (first captured launch); read with `ncu -i ... --page raw --csv`.\n")
     for dump in (f"{tag}_cfg3_full_raw.csv", f"{tag}_flood_full_raw.csv", f"{tag}_vox_full_raw.csv"):
         path = os.path.join(G, dump)

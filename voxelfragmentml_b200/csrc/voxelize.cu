@@ -403,10 +403,15 @@ extern "C" vf_status vf_voxelize(vf_grid* grid, const float* verts, uint32_t nv,
         // grow the arena, keeping what the passes above left in it (rare: only when the mesh has very large triangles)
         VfScratch old = c->mesh;
         c->mesh = VfScratch();
-        VF_TRY(vf_scratch_reserve(c, c->mesh, need + total * rec_bytes + pad + 256));
-        VF_CUDA(cudaMemcpyAsync(c->mesh.ptr, old.ptr, need, cudaMemcpyDeviceToDevice, c->stream));
-        VF_CUDA(vf_sync(c));
-        VF_CUDA(cudaFree(old.ptr));
+        const vf_status grown = vf_scratch_reserve(c, c->mesh, need + total * rec_bytes + pad + 256);
+        if (grown != VF_OK) {  // keep the old arena: nothing is lost, the call fails
+            c->mesh = old;
+            return grown;
+        }
+        cudaError_t ce = cudaMemcpyAsync(c->mesh.ptr, old.ptr, need, cudaMemcpyDeviceToDevice, c->stream);
+        if (ce == cudaSuccess) ce = vf_sync(c);
+        cudaFree(old.ptr);  // the new arena is the context's either way
+        VF_CUDA(ce);
         base = (char*)c->mesh.ptr;
         d_verts = (float*)base;
         d_faces = (uint32_t*)(base + vbytes);
