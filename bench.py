@@ -459,7 +459,8 @@ def run_cuda(args):
     if world > 1:
         dist.barrier()  # all ranks measure the same phase at the same time (the full-grid passes of a late rank would share the host's DMA with them)
     compact_runs = []
-    per_thread = max(2, (2 * args.steps + NPROD - 1) // NPROD)
+    # a pass is long enough for its ramp-up / drain (NPROD steps in flight) not to weigh on the figure: at least 10 steps per producer at full length
+    per_thread = max(2, (2 * args.steps + NPROD - 1) // NPROD, min(10, args.steps))
     for _ in range(3):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -866,7 +867,6 @@ def slab_labels_measure(rank, local_rank, world, dist, n, nseeds, steps, warmup)
         if it >= warmup:
             times.append(time.perf_counter() - t0)
             t_naive = t1 - t0
-    occupied = s.grid.numOccupiedVoxels()
     s.close()
     ctx.close()
     total = float(sum(times))
@@ -881,7 +881,7 @@ def slab_labels_measure(rank, local_rank, world, dist, n, nseeds, steps, warmup)
             "ms_per_step": ms, "naive_ms_rank0_last_step": t_naive * 1e3, "scaling": "strong", "grid": [n, n, n], "seeds": nseeds,
             "workload": f"{n}^3 analytic solid vessel in {world} x-slabs: NAIVE EUCLIDEAN {nseeds} seeds (halo planes computed) + erode(ELLIPSE,3,3it,p.5,thr.5) = "
                         "detectBoundaries, 3 erosion passes, 3^3 sweep with a label-plane exchange over NCCL after each of the 5 passes",
-            "halo_bytes_per_rank": 5 * 2 * 2 * n * n * (1 if world > 1 else 0), "labelled_cells_incl_halo_rank0": int(occupied),
+            "halo_bytes_per_rank": 5 * 2 * 2 * n * n * (1 if world > 1 else 0),
             # 4 B per voxel for F1 + 18 B per voxel for the erode stage, against the aggregate HBM roofline of the N GPUs
             "roofline_frac_aggregate": 22.0 * N / (ms * 1e-3) / 1e9 / (peak * world)}
 
