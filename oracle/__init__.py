@@ -115,6 +115,8 @@ def _declare(L):
     L.orc_encode_qstack.argtypes = [_u16p, _u32p, C.c_void_p, C.c_uint64]
     L.orc_encode_bing_squared.restype = C.c_uint64
     L.orc_encode_bing_squared.argtypes = [_u16p, _u32p, C.c_void_p, C.c_uint64]
+    L.orc_mc_soup.restype = C.c_uint32
+    L.orc_mc_soup.argtypes = [_u16p, _u32p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
     L.orc_marching_cubes.restype = C.c_int
     L.orc_marching_cubes.argtypes = [_u16p, _u32p, C.c_uint32, _f32p, _f32p, C.c_uint32, C.c_float, C.c_uint32, C.c_float, C.c_void_p, C.c_uint32,
                                      C.c_void_p, C.c_uint32, _u32p]
@@ -396,6 +398,17 @@ def marching_cubes(grid, target, aabb_min, aabb_max, nb_iters=None, nb_weight=0.
     if len(v) and len(f):
         lib().orc_marching_cubes(grid, d, int(target), mn, mx, nb_iters, nb_weight, b_iters, b_weight, v.ctypes.data, len(v), f.ctypes.data, len(f), counts)
     return v, f
+
+
+def mc_soup(grid, target):
+    """the triangle soup of one fragment before vertex fusion (marchingCubes-comp.glsl over the padded grid) and its Morton codes
+    (computeMortonCodes-comp.glsl): (vertices float32[n][4] in padded-grid cells + boundary flag, codes uint32[n]), 3 vertices per triangle"""
+    d = _dims(grid)
+    n = int(lib().orc_mc_soup(grid, d, int(target), None, None, 0))
+    v, m = np.zeros((n, 4), np.float32), np.zeros(n, np.uint32)
+    if n:
+        lib().orc_mc_soup(grid, d, int(target), v.ctypes.data, m.ctypes.data, n)
+    return v, m
 
 
 def num_threads() -> int:

@@ -10,7 +10,9 @@ What is rewritten — declarations only, the statements of the shader are compil
   * `layout (std430, binding = N) buffer B { T name[]; };`  ->  `glsl_buffer<T> name;` (the driver binds a host array to it)
     `layout (std430, binding = N) buffer B { T name; };`    ->  `T* p_name;` + `#define name (*p_name)` (undefined again at the end)
   * `subroutine R type(args);` -> a function-pointer typedef, `subroutine uniform type name;` -> a variable of it, `subroutine(type)` dropped;
-  * `void main()` -> `void shader_main()`;  `.xyz` -> `.xyz()` (C++ has no swizzles).
+  * `void main()` -> `void shader_main()`;  `.xyz` -> `.xyz()` (C++ has no swizzles);
+  * `T name = ... name(...)` (a variable named like the function its initialiser calls: legal GLSL, the variable is not in scope yet;
+    in C++ it is) -> the variable and its later uses in that block become `name_v` (marchingCubes-comp.glsl:147-150).
 `uniform` and the parameter qualifier `in` are emptied by macros in the including file (oracle/ref_shim/ref_glsl.cpp)."""
 import os
 import re
@@ -29,8 +31,26 @@ def expand(root, rel, seen=()):
     return "\n".join(out)
 
 
+def rename_shadowing(src):
+    lines = src.splitlines()
+    i = 0
+    while i < len(lines):
+        m = re.match(r"(\s*)(\w+)\s+(\w+)\s*=\s*(.*)$", lines[i])
+        if m and re.search(r"\b" + re.escape(m.group(3)) + r"\s*\(", m.group(4)):
+            name, depth = m.group(3), 0
+            lines[i] = f"{m.group(1)}{m.group(2)} {name}_v = {m.group(4)}"
+            for j in range(i + 1, len(lines)):
+                depth += lines[j].count("{") - lines[j].count("}")
+                if depth < 0:
+                    break
+                lines[j] = re.sub(r"\b" + re.escape(name) + r"\b(?!\s*\()", name + "_v", lines[j])
+        i += 1
+    return "\n".join(lines)
+
+
 def translate(src):
     out, undef = [], []
+    src = rename_shadowing(src)
     for line in src.splitlines():
         s = line.strip()
         if s.startswith("#version") or s.startswith("#extension"):

@@ -25,12 +25,23 @@ struct vec3 {
     float x, y, z;
     vec3() : x(0), y(0), z(0) {}
     vec3(float a, float b, float c) : x(a), y(b), z(c) {}
+    explicit vec3(float s) : x(s), y(s), z(s) {}
     vec3(const uvec3& v);  // implicit, as GLSL converts uvec3 -> vec3 in a call
+    vec3(const ivec3& v);  // implicit: `vec3 p = cell + neighbour` (marchingCubes-comp.glsl:70-71)
 };
+inline vec3 operator+(const vec3& a, const vec3& b) { return vec3(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline vec3 operator-(const vec3& a, const vec3& b) { return vec3(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline vec3 operator/(const vec3& a, const vec3& b) { return vec3(a.x / b.x, a.y / b.y, a.z / b.z); }
+inline vec3 operator*(float s, const vec3& a) { return vec3(s * a.x, s * a.y, s * a.z); }
+inline vec3 operator*(const vec3& a, float s) { return vec3(a.x * s, a.y * s, a.z * s); }
+inline vec3 operator/(double s, const vec3& a) { return vec3((float)s / a.x, (float)s / a.y, (float)s / a.z); }  // `1.0 / vec3(...)`: a float literal in GLSL
+inline float dot(const vec3& a, const vec3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline vec3 cross(const vec3& a, const vec3& b) { return vec3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
 
 struct uvec3 {
     uint x, y, z;
     uvec3() : x(0), y(0), z(0) {}
+    uvec3(const ivec3& v);  // implicit int -> uint, component-wise (getPositionIndex(cell + neighbour), marchingCubes-comp.glsl:110)
     template <typename A, typename B, typename C>
     uvec3(A a, B b, C c) : x((uint)a), y((uint)b), z((uint)c) {}  // uvec3(float, float, float) truncates towards zero
     explicit uvec3(uint s) : x(s), y(s), z(s) {}
@@ -45,11 +56,33 @@ struct ivec3 {
     explicit ivec3(uint s) : x((int)s), y((int)s), z((int)s) {}
     explicit ivec3(const uvec3& v) : x((int)v.x), y((int)v.y), z((int)v.z) {}
 };
+inline uvec3::uvec3(const ivec3& v) : x((uint)v.x), y((uint)v.y), z((uint)v.z) {}
+inline vec3::vec3(const ivec3& v) : x((float)v.x), y((float)v.y), z((float)v.z) {}
+inline uvec3 operator+(const uvec3& a, const uvec3& b) { return uvec3(a.x + b.x, a.y + b.y, a.z + b.z); }
 inline ivec3 operator+(const ivec3& a, const ivec3& b) { return ivec3(a.x + b.x, a.y + b.y, a.z + b.z); }
 inline ivec3 operator-(const ivec3& a, const ivec3& b) { return ivec3(a.x - b.x, a.y - b.y, a.z - b.z); }
 inline int glsl_clamp1(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }  // min(max(x, minVal), maxVal)
 inline ivec3 clamp(const ivec3& v, const ivec3& lo, const ivec3& hi) { return ivec3(glsl_clamp1(v.x, lo.x, hi.x), glsl_clamp1(v.y, lo.y, hi.y), glsl_clamp1(v.z, lo.z, hi.z)); }
 
+struct ivec2 {
+    int x, y;
+};
+struct mat4 {
+    float m[16];
+};
+// `v.xyz` of a vec4 as an lvalue: the generator writes `.xyz()`, which yields this view (reads convert to vec3)
+struct vec3ref {
+    float &x, &y, &z;
+    vec3ref& operator=(const vec3& v) { x = v.x, y = v.y, z = v.z; return *this; }
+    vec3ref& operator=(const vec3ref& v) { const float a = v.x, b = v.y, c = v.z; x = a, y = b, z = c; return *this; }
+    operator vec3() const { return vec3(x, y, z); }
+};
+struct vec4 {
+    float x, y, z, w;
+    vec4() : x(0), y(0), z(0), w(0) {}
+    vec3ref xyz() { return vec3ref{ x, y, z }; }
+    vec3 xyz() const { return vec3(x, y, z); }
+};
 struct ivec4 {
     int x, y, z, w;
 };

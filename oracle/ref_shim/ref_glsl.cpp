@@ -57,11 +57,26 @@ namespace sh_djset    { GLSL_NAMES
 namespace sh_djstack  { GLSL_NAMES
 #include "glsl/disjointSetStack-comp.inc"
 }
+namespace sh_march    { GLSL_NAMES
+#include "glsl/marchingCubes-comp.inc"
+}
+namespace sh_morton   { GLSL_NAMES
+#include "glsl/computeMortonCodes-comp.inc"
+}
 // clang-format on
 #undef uniform
 #undef in
+#undef UINT_MAX  // constraints.glsl's own (28-bit) value, not <climits>'
 
 namespace {
+
+// MarchingCubes::_triangleTable / _edgeTable (MarchingCubes.cpp:6-298), cut out of the reference source at build time
+const int mc_triangle_table[256 * 16] = {
+#include "mc_triangle_table.inc"
+};
+const int mc_edge_table[256] = {
+#include "mc_edge_table.inc"
+};
 
 // ComputeShader::execute(numGroups, ...) launches numGroups * groupSize invocations; the ones at or beyond numCells return at once, so only
 // [0, n) is run.  `parallel` only for the order-independent shaders (see the header comment).
@@ -286,6 +301,44 @@ int glsl_flood(uint16_t* grid, const uint32_t* dims, const uint32_t* seeds, uint
     glsl_undo_mask(grid, dims, 8u, 1);  // :180-186
     if (stats) stats[0] = iteration, stats[1] = trips, stats[2] = freed_total;
     return 0;
+}
+
+// MarchingCubes::triangulateFieldGPU's first two dispatches for _marchingCubesSubdivisions == 1 (MarchingCubes.cpp:364-388, 445-453):
+// marchingCubes-comp.glsl over every cell of the PADDED grid (`grid` = MarchingCubes::setGrid's copy: dims + 2, a ring of VOXEL_FREE,
+// :523-534 — restated by the caller), then computeMortonCodes-comp.glsl over the vertices it appended.  The shader hands out vertex slots
+// with an atomic counter, so the order of the triangles is the schedule's (ascending invocation index here); callers compare as sets.
+// Returns the number of vertices (3 per triangle); verts = vec4 per vertex (x, y, z in padded-grid cells, boundary flag), morton = its code.
+uint32_t glsl_mc_soup(const uint16_t* grid, const uint32_t* dims, uint32_t target, float* verts, uint32_t* morton, uint32_t cap)
+{
+    const uint n = dims[0] * dims[1] * dims[2];
+    std::vector<vec4> vertexData(cap + 16), support((size_t)n * 12);
+    std::vector<int> tri(mc_triangle_table, mc_triangle_table + 256 * 16), cfg(mc_edge_table, mc_edge_table + 256);
+    uint counter = 0;  // resetCounter(_numVerticesSSBO), :379
+    sh_march::grid.bind(const_cast<uint16_t*>(grid), n);
+    sh_march::vertexData.bind(vertexData.data(), cap);
+    sh_march::p_numVertices = &counter;
+    sh_march::triangleTable.bind(tri.data(), tri.size());
+    sh_march::configurationTable.bind(cfg.data(), cfg.size());
+    sh_march::vertexList.bind(support.data(), support.size());
+    sh_march::gridDims = dims3(dims);
+    sh_march::isolevel = 0.5f;
+    sh_march::localSize = dims3(dims);
+    sh_march::start = uvec3(0, 0, 0);
+    sh_march::targetValue = (int)target;
+    dispatch(n, false, sh_march::shader_main);
+    const uint nv = std::min(counter, cap);  // :390 (the buffer's capacity)
+    std::vector<uint> codes(nv);
+    sh_morton::vertices.bind(vertexData.data(), nv);
+    sh_morton::mortonCode.bind(codes.data(), nv);
+    sh_morton::numPoints = nv;
+    sh_morton::sceneMaxBoundary = vec3(dims3(dims));  // :450-451
+    sh_morton::sceneMinBoundary = vec3(.0f);
+    dispatch(nv, true, sh_morton::shader_main);
+    for (uint i = 0; i < nv; ++i) {
+        verts[4 * i] = vertexData[i].x, verts[4 * i + 1] = vertexData[i].y, verts[4 * i + 2] = vertexData[i].z, verts[4 * i + 3] = vertexData[i].w;
+        morton[i] = codes[i];
+    }
+    return counter;
 }
 
 }  // extern "C"

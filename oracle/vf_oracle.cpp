@@ -1537,9 +1537,8 @@ struct McVert {
 };
 }  // namespace
 
-extern "C" int orc_marching_cubes(const uint16_t* grid, const uint32_t dims[3], uint32_t target, const float amin[3], const float amax[3], uint32_t nb_iters,
-                                  float nb_weight, uint32_t b_iters, float b_weight, float* verts, uint32_t cap_v, uint32_t* faces, uint32_t cap_f,
-                                  uint32_t counts[2])
+/* setGrid + the march dispatch + computeMortonCodes: the triangle soup of one fragment, three vertices per triangle, cells in index order */
+static void mc_soup(const uint16_t* grid, const uint32_t dims[3], uint32_t target, std::vector<McVert>& soup)
 {
     /* setGrid, MarchingCubes.cpp:523-540: dims + 2, a ring of VOXEL_FREE */
     const int PX = (int)dims[0] + 2, PY = (int)dims[1] + 2, PZ = (int)dims[2] + 2;
@@ -1548,7 +1547,6 @@ extern "C" int orc_marching_cubes(const uint16_t* grid, const uint32_t dims[3], 
         for (int y = 1; y < PY - 1; ++y)
             for (int z = 1; z < PZ - 1; ++z) P[((size_t)x * PY + y) * PZ + z] = grid[lin(x - 1, y - 1, z - 1, dims)];
     /* march, marchingCubes-comp.glsl:96-156, cells in index order */
-    std::vector<McVert> soup;
     const float pd[3] = { (float)PX, (float)PY, (float)PZ };
     for (int x = 0; x < PX; ++x)
         for (int y = 0; y < PY; ++y)
@@ -1590,6 +1588,27 @@ extern "C" int orc_marching_cubes(const uint16_t* grid, const uint32_t dims[3], 
                     }
                 }
             }
+}
+
+/* the soup alone (tests: the reference's marchingCubes-comp.glsl and computeMortonCodes-comp.glsl compiled in place produce the same vertices
+ * and codes, up to the order the shader's atomic counter hands out): verts[4 * i] = x, y, z (padded-grid units), boundary flag */
+extern "C" uint32_t orc_mc_soup(const uint16_t* grid, const uint32_t dims[3], uint32_t target, float* verts, uint32_t* morton, uint32_t cap)
+{
+    std::vector<McVert> soup;
+    mc_soup(grid, dims, target, soup);
+    for (uint32_t i = 0; i < soup.size() && i < cap; ++i) {
+        verts[4 * i] = soup[i].p[0], verts[4 * i + 1] = soup[i].p[1], verts[4 * i + 2] = soup[i].p[2], verts[4 * i + 3] = soup[i].w;
+        morton[i] = soup[i].morton;
+    }
+    return (uint32_t)soup.size();
+}
+
+extern "C" int orc_marching_cubes(const uint16_t* grid, const uint32_t dims[3], uint32_t target, const float amin[3], const float amax[3], uint32_t nb_iters,
+                                  float nb_weight, uint32_t b_iters, float b_weight, float* verts, uint32_t cap_v, uint32_t* faces, uint32_t cap_f,
+                                  uint32_t counts[2])
+{
+    std::vector<McVert> soup;
+    mc_soup(grid, dims, target, soup);
     const uint32_t nsoup = (uint32_t)soup.size(), nf = nsoup / 3;
     /* sortMortonCodes + findSameVertices_01/02 under the deterministic order */
     std::vector<uint32_t> idx(nsoup);

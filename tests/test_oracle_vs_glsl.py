@@ -2,7 +2,8 @@
 from the text where it lies under /root/reference (oracle/ref_shim/glsl2cpp.py + ref_glsl.cpp -> oracle/_ref/libvf_ref_glsl.so), driven by
 restatements of the host loops (RegularGrid.cpp:64-159, 488-503, 1006-1015; FloodFracturer.cpp:98-191; NaiveFracturer.cpp:71-109).
 
-Order-independent shaders (detectBoundaries, erodeGrid, copyGrid, undoMask, naiveFracturer, disjointSet) must match the oracle bit for bit.
+Order-independent shaders (detectBoundaries, erodeGrid, copyGrid, undoMask, naiveFracturer, disjointSet) must match the oracle bit for bit;
+marchingCubes + computeMortonCodes (f2) hand out vertex slots with an atomic counter: their triangle soup is compared as a set.
 removeIsolatedRegionsGrid races with itself in place: it is compared under the "all reads before all writes" schedule, which is the snapshot
 rule the oracle and the CUDA path adopt.  floodFracturer races by design (whichever invocation stores first claims a cell): it runs under one
 legal schedule (ascending invocation index) and is compared through what every schedule must produce — the set of claimed cells, the BFS
@@ -32,6 +33,8 @@ def glsl():
     L.glsl_undo_mask.argtypes = [_u16, _u32, C.c_uint32, C.c_int]
     L.glsl_erode.argtypes = [_u16, _u32, C.c_int, C.c_uint32, C.c_uint32, C.c_float, C.c_float, _f32, C.c_uint32, C.c_int]
     L.glsl_naive.argtypes = [_u16, _u32, _u32, C.c_uint32, C.c_int]
+    L.glsl_mc_soup.restype = C.c_uint32
+    L.glsl_mc_soup.argtypes = [_u16, _u32, C.c_uint32, _f32, _u32, C.c_uint32]
     L.glsl_flood.restype = C.c_int
     L.glsl_flood.argtypes = [_u16, _u32, _u32, C.c_uint32, C.c_int, C.c_uint32, _u32]
     return L
@@ -180,3 +183,27 @@ def test_flood_shader_loop_with_extra_seeds(glsl, orc, vessel_grid, dfunc):
         assert _components_ok(a, principal, nneigh) and _components_ok(want, principal, nneigh)
         assert int(stats[1]) >= 1
         assert float((a == want).mean()) > 0.9
+
+
+def test_marching_cubes_and_morton_shaders(glsl, orc, vessel_grid):
+    """f2, the first two dispatches of MarchingCubes::triangulateFieldGPU (MarchingCubes.cpp:364-388, 445-453): the reference's
+    marchingCubes-comp.glsl over the padded grid and computeMortonCodes-comp.glsl over its vertices give the oracle's triangle soup —
+    the same triangles (bit-identical float32 vertices, boundary flags and Morton codes), in whatever order the atomic counter dealt."""
+    for lab in _labelled_cases(orc, vessel_grid):
+        tagged = orc.detect_boundaries(lab.copy())
+        labels = [int(v) for v in np.unique(lab) if v > 1]
+        for target in labels[:3] + labels[-1:]:
+            pd = np.asarray(tagged.shape, np.uint32) + 2
+            padded = np.ones(tuple(int(v) for v in pd), np.uint16)  # MarchingCubes::setGrid (:523-534): a ring of VOXEL_FREE around the grid
+            padded[1:-1, 1:-1, 1:-1] = tagged
+            wv, wm = orc.mc_soup(tagged, target)
+            cap = len(wv) + 300
+            gv, gm = np.zeros((cap, 4), np.float32), np.zeros(cap, np.uint32)
+            n = glsl.glsl_mc_soup(padded, pd, target, gv.reshape(-1), gm, cap)
+            assert n == len(wv) and n % 3 == 0 and n > 0
+            # one row per triangle: 3 x (x, y, z, flag) as bit patterns + 3 codes; the vertex order inside a triangle is part of the result
+            def rows(v, m):
+                r = np.concatenate([v[:n].view(np.uint32).reshape(n // 3, 12), m[:n].reshape(n // 3, 3)], axis=1)
+                return r[np.lexsort(r.T[::-1])]
+            assert np.array_equal(rows(gv, gm), rows(wv, wm)), f"target {target}"
+            assert gv[:n, 3].max() <= 1.0 and (gv[:n, 3] == 1.0).any()  # tagged cells give flagged triangles
