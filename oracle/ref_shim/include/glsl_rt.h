@@ -55,7 +55,9 @@ struct ivec3 {
     explicit ivec3(int s) : x(s), y(s), z(s) {}
     explicit ivec3(uint s) : x((int)s), y((int)s), z((int)s) {}
     explicit ivec3(const uvec3& v) : x((int)v.x), y((int)v.y), z((int)v.z) {}
+    explicit ivec3(const vec3& v);  // truncation towards zero
 };
+inline ivec3::ivec3(const vec3& v) : x((int)v.x), y((int)v.y), z((int)v.z) {}
 inline uvec3::uvec3(const ivec3& v) : x((uint)v.x), y((uint)v.y), z((uint)v.z) {}
 inline vec3::vec3(const ivec3& v) : x((float)v.x), y((float)v.y), z((float)v.z) {}
 inline uvec3 operator+(const uvec3& a, const uvec3& b) { return uvec3(a.x + b.x, a.y + b.y, a.z + b.z); }
@@ -68,7 +70,7 @@ struct ivec2 {
     int x, y;
 };
 struct mat4 {
-    float m[16];
+    float m[16];  // column-major, as GLSL stores it: m[4 * column + row]
 };
 // `v.xyz` of a vec4 as an lvalue: the generator writes `.xyz()`, which yields this view (reads convert to vec3)
 struct vec3ref {
@@ -80,11 +82,28 @@ struct vec3ref {
 struct vec4 {
     float x, y, z, w;
     vec4() : x(0), y(0), z(0), w(0) {}
+    vec4(const vec3& v, float d) : x(v.x), y(v.y), z(v.z), w(d) {}
     vec3ref xyz() { return vec3ref{ x, y, z }; }
     vec3 xyz() const { return vec3(x, y, z); }
 };
+// matrix * column vector, the four products of a row added left to right (a scale + translation matrix gives s * x + t exactly as written)
+inline vec4 operator*(const mat4& a, const vec4& v)
+{
+    vec4 r;
+    r.x = a.m[0] * v.x + a.m[4] * v.y + a.m[8] * v.z + a.m[12] * v.w;
+    r.y = a.m[1] * v.x + a.m[5] * v.y + a.m[9] * v.z + a.m[13] * v.w;
+    r.z = a.m[2] * v.x + a.m[6] * v.y + a.m[10] * v.z + a.m[14] * v.w;
+    r.w = a.m[3] * v.x + a.m[7] * v.y + a.m[11] * v.z + a.m[15] * v.w;
+    return r;
+}
+inline vec3 mix(const vec3& a, const vec3& b, float t) { return a * (1.0f - t) + b * t; }  // x * (1 - a) + y * a (GLSL 4.50 section 8.3)
+inline int clamp(int v, int lo, int hi) { return glsl_clamp1(v, lo, hi); }
 struct ivec4 {
     int x, y, z, w;
+    ivec4() : x(0), y(0), z(0), w(0) {}
+    ivec4(int a, int b, int c, int d) : x(a), y(b), z(c), w(d) {}
+    ivec4(const ivec3& v, int d) : x(v.x), y(v.y), z(v.z), w(d) {}
+    int& operator[](int i) { return i == 0 ? x : i == 1 ? y : i == 2 ? z : w; }
 };
 struct uvec4 {
     uint x, y, z, w;
@@ -93,6 +112,7 @@ struct uvec4 {
     template <typename W>
     uvec4(const uvec3& v, W d) : x(v.x), y(v.y), z(v.z), w((uint)d) {}
     uvec3 xyz() const { return uvec3(x, y, z); }
+    uint& operator[](uint i) { return i == 0 ? x : i == 1 ? y : i == 2 ? z : w; }
 };
 // uvec4 + ivec4: the signed operand converts to unsigned, the sum wraps (floodFracturer-comp.glsl:33 relies on it for "-1")
 inline uvec4 operator+(const uvec4& a, const ivec4& b) { return uvec4(a.x + (uint)b.x, a.y + (uint)b.y, a.z + (uint)b.z, a.w + (uint)b.w); }
@@ -121,6 +141,7 @@ struct glsl_buffer {
 };
 
 inline uint atomicAdd(uint& mem, uint data) { return __atomic_fetch_add(&mem, data, __ATOMIC_RELAXED); }
+inline int atomicAdd(int& mem, int data) { return __atomic_fetch_add(&mem, data, __ATOMIC_RELAXED); }
 inline uint atomicMin(uint& mem, uint data)
 {
     uint old = __atomic_load_n(&mem, __ATOMIC_RELAXED);

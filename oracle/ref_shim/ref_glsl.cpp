@@ -63,6 +63,27 @@ namespace sh_march    { GLSL_NAMES
 namespace sh_morton   { GLSL_NAMES
 #include "glsl/computeMortonCodes-comp.inc"
 }
+namespace sh_fuse1    { GLSL_NAMES
+#include "glsl/findSameVertices_01-comp.inc"
+}
+namespace sh_fuse2    { GLSL_NAMES
+#include "glsl/findSameVertices_02-comp.inc"
+}
+namespace sh_faces    { GLSL_NAMES
+#include "glsl/buildMarchingCubesFaces-comp.inc"
+}
+namespace sh_markb    { GLSL_NAMES
+#include "glsl/markBoundaryTriangles-comp.inc"
+}
+namespace sh_lapreset { GLSL_NAMES
+#include "glsl/resetLaplacianBuffer-comp.inc"
+}
+namespace sh_lap      { GLSL_NAMES
+#include "glsl/laplacianSmoothing-comp.inc"
+}
+namespace sh_lapfin   { GLSL_NAMES
+#include "glsl/finishLaplacianSmoothing-comp.inc"
+}
 // clang-format on
 #undef uniform
 #undef in
@@ -339,6 +360,119 @@ uint32_t glsl_mc_soup(const uint16_t* grid, const uint32_t* dims, uint32_t targe
         morton[i] = codes[i];
     }
     return counter;
+}
+
+// The whole of MarchingCubes::triangulateFieldGPU for one fragment and _marchingCubesSubdivisions == 1 (MarchingCubes.cpp:364-407): march,
+// Morton codes, the sort, findSameVertices_01 / _02, buildMarchingCubesFaces, markBoundaryTriangles, smoothSurface twice (:498-521).
+// `grid` is the padded copy (see glsl_mc_soup), `dims` the UNPADDED extent (RegularGrid::_numDivs, which scales the model matrix,
+// RegularGrid.cpp:478-480).  The sort: the reference runs a stable 30-pass binary radix sort of the codes (sortMortonCodes, :537-609, generic
+// RadixSort shaders); its result — indices ordered by code, ties in buffer order — is produced here by std::stable_sort.  Every dispatch runs
+// in ascending invocation order (the atomic counters of march and findSameVertices_01 then number triangles and fused vertices in that order).
+// counts = { fused vertices, faces }; nothing is written when the capacities are too small.
+int glsl_marching_cubes(const uint16_t* grid, const uint32_t* dims, uint32_t target, const float* amin, const float* amax, uint32_t nb_iters,
+                        float nb_weight, uint32_t b_iters, float b_weight, float* verts, uint32_t cap_v, uint32_t* faces, uint32_t cap_f, uint32_t* counts)
+{
+    const uint32_t pd[3] = { dims[0] + 2, dims[1] + 2, dims[2] + 2 };
+    const uint n = pd[0] * pd[1] * pd[2];
+    const uint cap = 15u * n;  // five triangles per cell at most
+    std::vector<vec4> soup(cap), support((size_t)n * 12);
+    std::vector<int> tri(mc_triangle_table, mc_triangle_table + 256 * 16), cfg(mc_edge_table, mc_edge_table + 256);
+    uint counter = 0;
+    sh_march::grid.bind(const_cast<uint16_t*>(grid), n);
+    sh_march::vertexData.bind(soup.data(), cap);
+    sh_march::p_numVertices = &counter;
+    sh_march::triangleTable.bind(tri.data(), tri.size());
+    sh_march::configurationTable.bind(cfg.data(), cfg.size());
+    sh_march::vertexList.bind(support.data(), support.size());
+    sh_march::gridDims = dims3(pd);
+    sh_march::isolevel = 0.5f;
+    sh_march::localSize = dims3(pd);
+    sh_march::start = uvec3(0, 0, 0);
+    sh_march::targetValue = (int)target;
+    dispatch(n, false, sh_march::shader_main);
+    const uint nv = counter;
+    counts[0] = counts[1] = 0;
+    if (nv == 0) return 0;
+    // calculateMortonCodes :445-453
+    std::vector<uint> codes(nv);
+    sh_morton::vertices.bind(soup.data(), nv);
+    sh_morton::mortonCode.bind(codes.data(), nv);
+    sh_morton::numPoints = nv;
+    sh_morton::sceneMaxBoundary = vec3(dims3(pd));
+    sh_morton::sceneMinBoundary = vec3(.0f);
+    dispatch(nv, true, sh_morton::shader_main);
+    // sortMortonCodes: indices by code, stable
+    std::vector<uint> indices(nv), indices2(nv, 0u);
+    for (uint i = 0; i < nv; ++i) indices[i] = i;
+    std::stable_sort(indices.begin(), indices.end(), [&](uint a, uint b) { return codes[a] < codes[b]; });
+    // fuseSimilarVertices :455-474 with the model matrix of RegularGrid.cpp:478-480: translate(-scale) * translate(aabb.min) * scale(scale)
+    mat4 model = {};
+    for (int q = 0; q < 3; ++q) {
+        const float scale = (amax[q] - amin[q]) / (float)dims[q];
+        model.m[5 * q] = scale;
+        model.m[12 + q] = amin[q] + (-scale);
+    }
+    model.m[15] = 1.0f;
+    std::vector<vec4> fusedv(nv);
+    uint vertexCount = 0;
+    sh_fuse1::indices.bind(indices.data(), nv);
+    sh_fuse1::indices2.bind(indices2.data(), nv);
+    sh_fuse1::points.bind(soup.data(), nv);
+    sh_fuse1::vertexData.bind(fusedv.data(), nv);
+    sh_fuse1::p_vertexCount = &vertexCount;
+    sh_fuse1::defaultValue = 0xFFFFFFFFu;  // UINT_MAX of <climits> (:457), not the shaders' own 28-bit constant
+    sh_fuse1::modelMatrix = model;
+    sh_fuse1::numPoints = nv;
+    dispatch(nv, false, sh_fuse1::shader_main);
+    sh_fuse2::indices.bind(indices.data(), nv);
+    sh_fuse2::indices2.bind(indices2.data(), nv);
+    sh_fuse2::defaultValue = 0xFFFFFFFFu;
+    sh_fuse2::numPoints = nv;
+    dispatch(nv, false, sh_fuse2::shader_main);
+    const uint nfused = vertexCount, nf = nv / 3;
+    counts[0] = nfused, counts[1] = nf;
+    if (!verts || !faces || cap_v < nfused || cap_f < nf) return 0;
+    // buildMarchingCubesFaces :436-442, markBoundaryTriangles :484-490
+    std::vector<uvec4> face(nf);
+    sh_faces::indices.bind(indices.data(), nv);
+    sh_faces::indices2.bind(indices2.data(), nv);
+    sh_faces::faceData.bind(face.data(), nf);
+    sh_faces::numPoints = nv;
+    dispatch(nv, true, sh_faces::shader_main);
+    sh_markb::points.bind(fusedv.data(), nfused);
+    sh_markb::faceData.bind(face.data(), nf);
+    sh_markb::numFaces = nf;
+    dispatch(nf, true, sh_markb::shader_main);
+    // smoothSurface :498-521
+    std::vector<int> l1(nfused), l2(nfused), l3(nfused), l4(nfused);
+    auto smooth = [&](uint iterations, float weight, bool boundary) {
+        for (uint it = 0; it < iterations; ++it) {
+            sh_lapreset::laplacian01.bind(l1.data(), nfused), sh_lapreset::laplacian02.bind(l2.data(), nfused);
+            sh_lapreset::laplacian03.bind(l3.data(), nfused), sh_lapreset::laplacian04.bind(l4.data(), nfused);
+            sh_lapreset::numVertices = nfused;
+            dispatch(nfused, true, sh_lapreset::shader_main);
+            sh_lap::laplacian01.bind(l1.data(), nfused), sh_lap::laplacian02.bind(l2.data(), nfused);
+            sh_lap::laplacian03.bind(l3.data(), nfused), sh_lap::laplacian04.bind(l4.data(), nfused);
+            sh_lap::vertices.bind(fusedv.data(), nfused);
+            sh_lap::face.bind(face.data(), nf);
+            sh_lap::checkValidity = boundary ? 0u : 1u;
+            sh_lap::numFaces = nf;
+            sh_lap::targetVertexType = boundary ? 1.0f : .0f;
+            dispatch(nf, true, sh_lap::shader_main);  // integer atomic adds commute
+            sh_lapfin::laplacian01.bind(l1.data(), nfused), sh_lapfin::laplacian02.bind(l2.data(), nfused);
+            sh_lapfin::laplacian03.bind(l3.data(), nfused), sh_lapfin::laplacian04.bind(l4.data(), nfused);
+            sh_lapfin::vertices.bind(fusedv.data(), nfused);
+            sh_lapfin::numVertices = nfused;
+            sh_lapfin::targetVertexType = boundary ? 1.0f : .0f;
+            sh_lapfin::weight = weight;
+            dispatch(nfused, true, sh_lapfin::shader_main);
+        }
+    };
+    smooth(nb_iters, nb_weight, false);
+    smooth(b_iters, b_weight, true);
+    for (uint i = 0; i < nfused; ++i) verts[4 * i] = fusedv[i].x, verts[4 * i + 1] = fusedv[i].y, verts[4 * i + 2] = fusedv[i].z, verts[4 * i + 3] = fusedv[i].w;
+    for (uint i = 0; i < nf; ++i) faces[4 * i] = face[i].x, faces[4 * i + 1] = face[i].y, faces[4 * i + 2] = face[i].z, faces[4 * i + 3] = face[i].w;
+    return 0;
 }
 
 }  // extern "C"

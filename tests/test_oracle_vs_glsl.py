@@ -33,6 +33,8 @@ def glsl():
     L.glsl_undo_mask.argtypes = [_u16, _u32, C.c_uint32, C.c_int]
     L.glsl_erode.argtypes = [_u16, _u32, C.c_int, C.c_uint32, C.c_uint32, C.c_float, C.c_float, _f32, C.c_uint32, C.c_int]
     L.glsl_naive.argtypes = [_u16, _u32, _u32, C.c_uint32, C.c_int]
+    L.glsl_marching_cubes.restype = C.c_int
+    L.glsl_marching_cubes.argtypes = [_u16, _u32, C.c_uint32, _f32, _f32, C.c_uint32, C.c_float, C.c_uint32, C.c_float, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, _u32]
     L.glsl_mc_soup.restype = C.c_uint32
     L.glsl_mc_soup.argtypes = [_u16, _u32, C.c_uint32, _f32, _u32, C.c_uint32]
     L.glsl_flood.restype = C.c_int
@@ -207,3 +209,35 @@ def test_marching_cubes_and_morton_shaders(glsl, orc, vessel_grid):
                 return r[np.lexsort(r.T[::-1])]
             assert np.array_equal(rows(gv, gm), rows(wv, wm)), f"target {target}"
             assert gv[:n, 3].max() <= 1.0 and (gv[:n, 3] == 1.0).any()  # tagged cells give flagged triangles
+
+
+@pytest.mark.parametrize("iters", [None, 2])
+def test_marching_cubes_pipeline_shaders(glsl, orc, vessel_grid, iters):
+    """f2 end to end (MarchingCubes::triangulateFieldGPU, MarchingCubes.cpp:364-407): march, Morton codes, sort, findSameVertices_01 / _02,
+    buildMarchingCubesFaces, markBoundaryTriangles and both smoothSurface passes, every shader compiled in place and dispatched in ascending
+    invocation order.  The oracle orders equal Morton codes by position to be schedule independent; where no two DIFFERENT positions share a
+    code (checked below: true for grids of this size) that is the order the shaders produce under this schedule, so vertices (float32 bits)
+    and faces must be identical, numbering included."""
+    mn, mx = np.float32([-0.4, 0.1, -0.3]), np.float32([0.6, 1.3, 0.45])
+    for lab in _labelled_cases(orc, vessel_grid)[1:]:
+        tagged = orc.detect_boundaries(lab.copy())
+        labels = [int(v) for v in np.unique(lab) if v > 1]
+        for target in labels[:2] + labels[-1:]:
+            sv, sm = orc.mc_soup(tagged, target)
+            order = np.lexsort((sv[:, 2], sv[:, 1], sv[:, 0], sm))
+            same_code = sm[order][1:] == sm[order][:-1]
+            same_pos = (sv[order][1:, :3] == sv[order][:-1, :3]).all(axis=1)
+            assert not (same_code & ~same_pos).any()  # premise of the comparison
+            pd = np.asarray(tagged.shape, np.uint32) + 2
+            padded = np.ones(tuple(int(v) for v in pd), np.uint16)
+            padded[1:-1, 1:-1, 1:-1] = tagged
+            d = np.asarray(tagged.shape, np.uint32)
+            it = int(np.float32(max(tagged.shape)) * np.float32(0.048)) if iters is None else iters
+            kw = {} if iters is None else dict(nb_iters=it, b_iters=it)
+            wv, wf = orc.marching_cubes(tagged, target, mn, mx, **kw)
+            counts = np.zeros(2, np.uint32)
+            gv, gf = np.zeros((len(wv) + 8, 4), np.float32), np.zeros((len(wf) + 8, 4), np.uint32)
+            assert glsl.glsl_marching_cubes(padded, d, target, mn, mx, it, 0.9, it, 0.2, gv.ctypes.data, len(gv), gf.ctypes.data, len(gf), counts) == 0
+            assert (int(counts[0]), int(counts[1])) == (len(wv), len(wf)) and len(wv) > 0
+            assert np.array_equal(gf[: len(wf)], wf), f"faces, target {target}"
+            assert np.array_equal(gv[: len(wv)].view(np.uint32), wv.view(np.uint32)), f"vertices, target {target}"
