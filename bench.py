@@ -913,6 +913,7 @@ def default_jobs(world):
 
 
 BATCH_FLOOD_MODE = 0
+BATCH_FLOOD_FRONT = -1
 LAST_BATCH_INFO = {}  # side information of the last batch_measure call (rank-local)
 
 
@@ -948,6 +949,8 @@ def batch_measure(rank, local_rank, world, dist, meshes, warmup, jobs, mesh_pool
         ctx.setBlockingSync(block)
         if jobs > 1:
             ctx.setFloodLevels(8)  # throughput setting: with several jobs per GPU total tile work matters, not the latency of one flood
+            if BATCH_FLOOD_FRONT >= 0:
+                ctx.setFloodFront(BATCH_FLOOD_FRONT)  # --flood-front: widest BFS level of the thin-front solver (0 = tiles only)
             ctx.setFloodMode(BATCH_FLOOD_MODE)  # CTAs per SM of a job's cooperative round loop (0: one launch per round), so that jobs share the SMs
         grid = vf.RegularGrid(ctx, (256, 256, 256))  # allocated once at the clamp size, re-dimensioned per model (CADScene.cpp:529-543)
         ctx.reserve((256, 256, 256))
@@ -1101,7 +1104,7 @@ def run_dataset(args):
 
 
 def main():
-    global BATCH_FLOOD_MODE
+    global BATCH_FLOOD_MODE, BATCH_FLOOD_FRONT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -1118,6 +1121,7 @@ def main():
     ap.add_argument("--out", default="", help="dataset workload: parent directory of the (temporary) output folder")
     ap.add_argument("--no-export", action="store_true", help="dataset workload: no grid files (the batch loop through the native driver, metadata files only)")
     ap.add_argument("--flood-mode", type=int, default=0, help="batch workload: vf_ctx_set_flood_mode of the job contexts (0 = one launch per round, 1..4 = CTAs per SM of the cooperative loop)")
+    ap.add_argument("--flood-front", type=int, default=-1, help="batch workload: vf_ctx_set_flood_front of the job contexts (-1 = library default, 0 = tiles only)")
     ap.add_argument("--seeds", type=int, default=256, help="slab workload: number of seeds")
     ap.add_argument("--python-exchange", action="store_true", help="slab workload: the Python exchange loop over torch.distributed instead of the C++ loop over NCCL")
     ap.add_argument("--slab-size", type=int, default=0, help="default workload at N >= 2: edge of the cfg5 grid (default 2048 at 8 GPUs, else 1024)")
@@ -1133,6 +1137,7 @@ def main():
     ap.add_argument("--mesh-pool", type=int, default=8, help="batch workload: distinct synthetic shapes generated up front")
     args = ap.parse_args()
     BATCH_FLOOD_MODE = args.flood_mode
+    BATCH_FLOOD_FRONT = args.flood_front
     claim_stdout()
     if args.impl == "reference":
         run_reference(args)

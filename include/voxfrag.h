@@ -99,6 +99,7 @@ typedef struct vf_flood_stats {
     uint32_t disjoint_rounds;/* outer `while (numDisjointVoxels != 0)` iterations, FloodFracturer.cpp:135 */
     uint32_t freed_voxels;   /* voxels returned to FREE by the disjoint step, summed */
     uint32_t max_dist;       /* largest geodesic distance reached in phase 1 */
+    uint32_t front_levels;   /* relaxation steps (~ BFS levels) the thin-front solver ran before the phase converged or the tiles took over, summed over phases */
 } vf_flood_stats;
 
 typedef struct vf_ctx vf_ctx;
@@ -123,7 +124,11 @@ vf_status vf_ctx_set_blocking_sync(vf_ctx* ctx, int on);
  * latency for one job).  A narrower window orders the fronts better at the price of more rounds: 8 gives the highest throughput
  * when several jobs share the GPU (measured: 182 -> 200 models/s in batch generation). */
 vf_status vf_ctx_set_flood_levels(vf_ctx* ctx, uint32_t levels);
-/* How a flood phase is driven; the labels do not depend on it.  1..4 (default 4): ONE cooperative launch per phase with that many CTAs per SM,
+/* Every flood phase starts at cell granularity on one thread-block cluster (the front as lists of (cell, key) pairs in shared memory; right for
+ * voxelized surfaces, whose BFS levels hold a few thousand cells: 0.94 -> 0.70 ms at 176x256x176, 16 seeds) and moves to the tile worklist
+ * when more than max_front_cells pairs are pending (solid interiors).  Default 16384; 0 = tiles only; at most 65536.  Same labels. */
+vf_status vf_ctx_set_flood_front(vf_ctx* ctx, uint32_t max_front_cells);
+/* How the tile rounds of a flood phase are driven; the labels do not depend on it.  1..4 (default 4): ONE cooperative launch per phase with that many CTAs per SM,
  * the round loop on the device (no host read-back until the phase has converged): lowest latency for one job, and with 1 or 2 several jobs
  * fit on the GPU side by side.  0: one launch per round, read-backs every few rounds (rounds of many jobs interleave freely). */
 vf_status vf_ctx_set_flood_mode(vf_ctx* ctx, int ctas_per_sm);
@@ -283,7 +288,7 @@ typedef struct vf_mc_params {
     float   boundaryMCWeight;         /* 0.2 */
     float   nonBoundaryMCIterations;  /* 0.048 */
     float   nonBoundaryMCWeight;      /* 0.9 */
-    int32_t marchingCubesSubdivisions;/* 1 (other values: VF_ERR_UNSUPPORTED) */
+    int32_t marchingCubesSubdivisions;/* 1; carried only: the reference never reads it (RegularGrid.cpp:423 passes a literal 1) */
 } vf_mc_params;
 typedef struct vf_mesh vf_mesh;       /* device-resident result: vertices float[nv][4] = xyz + boundary flag, faces uint32[nf][4] = 3 vertex numbers + boundary flag */
 void      vf_mc_params_default(vf_mc_params* p);

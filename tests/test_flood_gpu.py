@@ -36,7 +36,7 @@ def test_vessel_fixture_16_seeds(ctx, orc, vessel_grid, dfunc):
     got, gst = _run_flood(ctx, vessel_grid, seeds, dfunc)
     assert np.array_equal(got, want)
     assert gst.max_dist == st.max_dist and gst.disjoint_rounds == 1 and gst.freed_voxels == 0
-    assert gst.tile_rounds >= 1 and gst.tile_visits >= gst.tile_rounds
+    assert gst.front_levels >= 1 or (gst.tile_rounds >= 1 and gst.tile_visits >= gst.tile_rounds)
 
 
 @pytest.mark.parametrize("shape", [(40, 36, 64), (33, 21, 76), (17, 19, 35), (13, 11, 7), (5, 6, 130), (70, 9, 33)])
@@ -202,6 +202,7 @@ def test_result_does_not_depend_on_the_distance_window_or_blocking_waits(orc, ve
 
     c = vf.Context(0)
     c.setFloodLevels(levels)
+    c.setFloodFront({1: 0, 8: 0, 100000: 0, 3: 150}.get(levels, 600))  # tiles only, or taking over from the thin-front solver somewhere on the way
     c.setBlockingSync({1: 1, 3: 2}.get(levels, 0))  # spinning, sleeping on a blocking event (1), polling with sched_yield (2)
     seeds, _ = orc.seed_uniform(orc.Rng(80), vessel_grid, 12)
     for dfunc in (1, 2):
@@ -247,6 +248,7 @@ def test_result_does_not_depend_on_how_the_round_loop_is_driven(orc, vessel_grid
 
     c = vf.Context(0)
     c.setFloodMode(mode)
+    c.setFloodFront(0)  # the tile rounds do all the work here; test_result_does_not_depend_on_the_front_limit mixes the two solvers
     seeds, _ = orc.seed_uniform(orc.Rng(80), vessel_grid, 16)
     for dfunc in (1, 2):
         want, st = orc.flood(vessel_grid.copy(), seeds, dfunc)
@@ -303,3 +305,64 @@ def _c1_cases(ctx, orc, vessel_grid):
         s2[0, :3] = np.argwhere(lab == s2[1, 3])[0]
         for sd in (seeds, s2):
             assert np.array_equal(_run_c1(ctx, lab, sd), orc.remove_isolated_regions_cpu(lab.copy(), sd))
+
+
+@pytest.mark.parametrize("limit,mode", [(0, 4), (1, 4), (40, 4), (40, 0), (700, 2), (16384, 4), (16384, 0), (65536, 4)])
+def test_result_does_not_depend_on_the_front_limit(orc, vessel_grid, limit, mode):
+    """setFloodFront: every phase starts level by level on one thread-block cluster and moves to the tile worklist once a level holds more than
+    `limit` cells — never (65536 on these grids), at once (1: the seeds themselves are too many), somewhere on the way (40, 700), or not at all
+    (0: tiles only).  Plain floods, extra seeds (both phases start on the front solver), a solid block (wide fronts), a labyrinth, ragged dims
+    without TMA staging, a seed on an EMPTY cell, two seeds on one cell.  Labels, max_dist and the F3 counters stay bit-exact."""
+    import voxelfragmentml_b200 as vf
+
+    c = vf.Context(0)
+    c.setFloodFront(limit)
+    c.setFloodMode(mode)
+    seeds, _ = orc.seed_uniform(orc.Rng(80), vessel_grid, 16)
+    for dfunc in (1, 2):
+        want, st = orc.flood(vessel_grid.copy(), seeds, dfunc)
+        got, gst = _run_flood(c, vessel_grid, seeds, dfunc)
+        assert np.array_equal(got, want) and gst.max_dist == st.max_dist
+        if limit == 0:
+            assert gst.front_levels == 0 and gst.tile_visits >= 1
+        if limit == 65536:
+            assert gst.front_levels >= st.max_dist + 1 and gst.tile_visits == 0  # the front solver ran every level, the tiles had nothing to do
+        xs = orc.make_seeds(orc.Rng(85), vessel_grid, 5, 10)
+        want, st = orc.flood(vessel_grid.copy(), xs, dfunc)
+        got, gst = _run_flood(c, vessel_grid, xs, dfunc)
+        assert np.array_equal(got, want) and gst.disjoint_rounds == st.rounds and gst.freed_voxels == st.freed_voxels
+    solid = np.ones((48, 40, 64), np.uint16)
+    solid[10:20, 5:30, 8:50] = 0
+    sd = pick_seeds(solid, 7, 3)
+    sd15 = sd.copy()
+    sd15[:, 3] = np.uint32([300, 301, 2, 32767, 5000, 77, 1024])
+    for dfunc in (1, 2):
+        want, st = orc.flood(solid.copy(), sd, dfunc)
+        got, gst = _run_flood(c, solid, sd, dfunc)
+        assert np.array_equal(got, want) and gst.max_dist == st.max_dist
+        want, st = orc.flood(solid.copy(), sd15, dfunc, id_bits=15)
+        got, gst = _run_flood(c, solid, sd15, dfunc, id_bits=15)
+        assert np.array_equal(got, want) and gst.max_dist == st.max_dist
+    lab = np.zeros((48, 40, 64), np.uint16)  # serpentine corridor
+    lab[1:-1, 1:-1, 1:-1] = 1
+    for x in range(4, 44, 4):
+        lab[x, (1 if (x // 4) % 2 else 4):(36 if (x // 4) % 2 else 39), :] = 0
+    sd = np.uint32([[2, 2, 2, 2], [45, 37, 60, 3]])
+    want, st = orc.flood(lab.copy(), sd, 1)
+    got, gst = _run_flood(c, lab, sd, 1)
+    assert np.array_equal(got, want) and gst.max_dist == st.max_dist
+    rag = random_blob_grid((33, 21, 75), 9, fill=0.6)  # Z % 4 != 0
+    sd = pick_seeds(rag, 5, 2)
+    for dfunc in (1, 2):
+        want, _ = orc.flood(rag.copy(), sd, dfunc)
+        got, _ = _run_flood(c, rag, sd, dfunc)
+        assert np.array_equal(got, want)
+    g = np.zeros((20, 20, 40), np.uint16)
+    g[2:8, 2:8, 2:30] = 1
+    g[12:18, 12:18, 5:35] = 1  # island without a seed stays FREE
+    sd = np.array([[3, 3, 3, 2], [7, 7, 29, 3], [10, 10, 10, 4], [3, 3, 3, 5], [0, 0, 0, 6], [19, 19, 39, 7]], np.uint32)  # EMPTY cells, a shared cell, grid corners
+    for dfunc in (1, 2):
+        want, _ = orc.flood(g.copy(), sd, dfunc)
+        got, _ = _run_flood(c, g, sd, dfunc)
+        assert np.array_equal(got, want)
+    c.close()

@@ -70,3 +70,6 @@ def test_absent_label_full_grid_and_bad_arguments(ctx, orc):
     with pytest.raises(vf.VoxFragError):
         grid.triangulateField(1)      # FREE is not a fragment label
     grid.close()
+    # _marchingCubesSubdivisions is a dead parameter of the reference (FractureParameters.h:56; RegularGrid.cpp:423 passes a literal 1): same mesh whatever it says
+    sv, sf = _mesh(ctx, g, 2, np.float32([0, 0, 0]), np.float32([6, 4, 5]), marchingCubesSubdivisions=3)
+    assert np.array_equal(sf, wf) and _same(sv, wv)

@@ -7,6 +7,9 @@ from voxelfragmentml_b200 import synth
 
 ctx = vf.Context(0)
 res = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+if len(sys.argv) > 3:
+    ctx.setFloodFront(int(sys.argv[3]))  # 0 = tiles only; default: thin-front solver first (16384 cells)
+    print("flood front limit", int(sys.argv[3]), flush=True)
 v, f = synth.vessel_mesh(0)
 mn, mx = synth.mesh_aabb(v)
 dims = np.zeros(3, np.uint32)
@@ -29,7 +32,7 @@ for name, df, extra in [("manhattan16", 1, 0), ("chebyshev16", 2, 0), ("cheb 8+1
         g.updateSSBO(occ); ctx.synchronize()
         ctx.timer_start(); fl.build(g, sd); ms = ctx.timer_stop()
     st = fl.last_stats
-    print(f"{name}: {ms:.3f} ms rounds {st.tile_rounds} visits {st.tile_visits} maxdist {st.max_dist} disjoint {st.disjoint_rounds} freed {st.freed_voxels}", flush=True)
+    print(f"{name}: {ms:.3f} ms front levels {st.front_levels} rounds {st.tile_rounds} visits {st.tile_visits} maxdist {st.max_dist} disjoint {st.disjoint_rounds} freed {st.freed_voxels}", flush=True)
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 g2 = vf.RegularGrid(ctx, (n, n, n))
 rs = np.random.RandomState(1); pts = rs.randint(0, n, size=(16, 3)); pts = pts[np.lexsort((pts[:, 2], pts[:, 1], pts[:, 0]))]
@@ -39,4 +42,4 @@ for df in (1, 2):
     for rep in range(2):
         g2.fillValue(1); ctx.synchronize(); ctx.timer_start(); fl.build(g2, sd); ms = ctx.timer_stop()
     st = fl.last_stats
-    print(f"dense {n}^3 df={df}: {ms:.3f} ms rounds {st.tile_rounds} visits {st.tile_visits} maxdist {st.max_dist}", flush=True)
+    print(f"dense {n}^3 df={df}: {ms:.3f} ms front levels {st.front_levels} rounds {st.tile_rounds} visits {st.tile_visits} maxdist {st.max_dist}", flush=True)

@@ -49,7 +49,7 @@ class VfDatasetStats(C.Structure):
 
 class VfFloodStats(C.Structure):
     _fields_ = [("tile_rounds", C.c_uint32), ("tile_visits", C.c_uint32), ("disjoint_rounds", C.c_uint32),
-                ("freed_voxels", C.c_uint32), ("max_dist", C.c_uint32)]
+                ("freed_voxels", C.c_uint32), ("max_dist", C.c_uint32), ("front_levels", C.c_uint32)]
 
 
 _vp = C.c_void_p
@@ -69,6 +69,7 @@ SIGNATURES = {
     "vf_ctx_synchronize": (C.c_int, [_vp]),
     "vf_ctx_set_blocking_sync": (C.c_int, [_vp, C.c_int]),
     "vf_ctx_set_flood_levels": (C.c_int, [_vp, _u32]),
+    "vf_ctx_set_flood_front": (C.c_int, [_vp, _u32]),
     "vf_ctx_set_c1_mode": (C.c_int, [_vp, C.c_int]),
     "vf_ctx_set_flood_mode": (C.c_int, [_vp, C.c_int]),
     "vf_ctx_stream": (_vp, [_vp]),

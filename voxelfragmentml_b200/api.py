@@ -125,6 +125,11 @@ class Context:
         """distance window of a flood round (0 = default 16: best latency; 8: best throughput with several jobs per GPU)"""
         check(self._lib.vf_ctx_set_flood_levels(self._h, int(levels)))
 
+    def setFloodFront(self, max_front_cells: int):
+        """flood phases start at cell granularity on one thread-block cluster and move to the tiles when more than this many (cell, key)
+        pairs are pending (default 16384, 0 = tiles only); same labels"""
+        check(self._lib.vf_ctx_set_flood_front(self._h, int(max_front_cells)))
+
     def setFloodMode(self, ctas_per_sm: int):
         """flood phases: 1..4 = one cooperative launch per phase with that many CTAs per SM (default 4), 0 = one launch per round; same labels"""
         check(self._lib.vf_ctx_set_flood_mode(self._h, int(ctas_per_sm)))
@@ -271,10 +276,12 @@ class RegularGrid:
         return int(occ.value)
 
     # ---- f2
-    def triangulateField(self, targetValue: int, boundaryMCIterations=0.048, boundaryMCWeight=0.2, nonBoundaryMCIterations=0.048, nonBoundaryMCWeight=0.9):
+    def triangulateField(self, targetValue: int, boundaryMCIterations=0.048, boundaryMCWeight=0.2, nonBoundaryMCIterations=0.048, nonBoundaryMCWeight=0.9,
+                         marchingCubesSubdivisions=1):
         """MarchingCubes::triangulateFieldGPU for one fragment label (what RegularGrid::toTriangleMesh runs per value, RegularGrid.cpp:482-483):
-        -> (vertices float32[nv][4] = xyz + boundary flag, faces uint32[nf][4] = three vertex numbers + boundary flag)."""
-        mp = _capi.VfMcParams(boundaryMCIterations, boundaryMCWeight, nonBoundaryMCIterations, nonBoundaryMCWeight, 1)
+        -> (vertices float32[nv][4] = xyz + boundary flag, faces uint32[nf][4] = three vertex numbers + boundary flag).
+        marchingCubesSubdivisions is carried only, as in the reference (FractureParameters.h:56 is read nowhere; RegularGrid.cpp:423 passes 1)."""
+        mp = _capi.VfMcParams(boundaryMCIterations, boundaryMCWeight, nonBoundaryMCIterations, nonBoundaryMCWeight, int(marchingCubesSubdivisions))
         h = C.c_void_p()
         check(self._lib.vf_marching_cubes(self._h, int(targetValue), C.byref(mp), C.byref(h)))
         try:

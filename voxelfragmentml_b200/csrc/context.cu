@@ -130,6 +130,15 @@ extern "C" vf_status vf_ctx_set_flood_levels(vf_ctx* ctx, uint32_t levels)
     return VF_OK;
 }
 
+extern "C" vf_status vf_ctx_set_flood_front(vf_ctx* ctx, uint32_t max_front_cells)
+{
+    VF_REQUIRE(ctx != nullptr, VF_ERR_INVALID_ARGUMENT, "null context");
+    VF_REQUIRE(max_front_cells <= (uint32_t)kVfFrontCap, VF_ERR_INVALID_ARGUMENT, "flood front limit %u: the front lists hold %u cells (0 = tiles only)", max_front_cells,
+               (uint32_t)kVfFrontCap);
+    ctx->flood_front = max_front_cells;
+    return VF_OK;
+}
+
 extern "C" vf_status vf_ctx_set_flood_mode(vf_ctx* ctx, int ctas_per_sm)
 {
     VF_REQUIRE(ctx != nullptr, VF_ERR_INVALID_ARGUMENT, "null context");
@@ -197,7 +206,7 @@ extern "C" vf_status vf_ctx_reserve(vf_ctx* ctx, uint32_t X, uint32_t Y, uint32_
     // (16 x 16 x 32 tiles: 14 B + 1 KiB of pending masks each), seeds / counters / histogram bins, brick bins of the voxelizer (4 x 4 x 32
     // bricks: 8 B each, plus room for a 64k-triangle mesh and its brick lists)
     const size_t nt = (size_t)((X + 15) / 16) * ((Y + 15) / 16) * ((Z + 31) / 32);
-    VF_TRY(vf_scratch_reserve(ctx, ctx->tiles, nt * (16 + 1024) + 4096));
+    VF_TRY(vf_scratch_reserve(ctx, ctx->tiles, nt * (16 + 1024) + 4096 + kVfFrontBytes));
     VF_TRY(vf_scratch_reserve(ctx, ctx->small, 1 << 20));
     const size_t nb = (size_t)((X + 3) / 4) * ((Y + 3) / 4) * ((Z + 31) / 32);
     VF_TRY(vf_scratch_reserve(ctx, ctx->mesh, nb * 8 + ((size_t)65536 * (24 + 64)) + 4096));

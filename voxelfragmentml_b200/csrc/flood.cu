@@ -16,6 +16,12 @@
 // of being claimed by whichever front arrives first in tile order and corrected later.  Deferred candidates stay marked in a
 // per-tile mask and the tile re-enqueues itself.
 //
+// Thin fronts first: on voxelized surfaces (shells a few cells thick — what the reference floods) a BFS level holds a few thousand cells,
+// far too few to keep tiles busy, and a flood is a chain of hundreds of dependent levels.  A phase therefore starts at cell granularity
+// (flood_front_kernel: ONE thread-block cluster, the front as lists of (cell, key) pairs in shared memory, the same keys lowered by
+// atomicMin, a cluster barrier every 16 steps) and hands over to the tile worklist as soon as more than vf_ctx_set_flood_front pairs are
+// pending (solid interiors); the keys it leaves are upper bounds realised by real paths, which is all the tiles' relaxation needs.
+//
 // F3 (extra seeds, words = fragId | prefix << 8): the reference's in-flood prefix merge converges, inside every connected set
 // of equal-fragId cells, to the lowest prefix present; the disjoint step then frees every cell whose prefix is not its
 // fragment's minimum and re-floods from all labelled cells.  Restated: keep, per fragment id, only the component (under the
@@ -48,6 +54,7 @@ enum { ST_VISITS = 0, ST_ROUNDS = 1, ST_ERROR = 2, ST_FREED = 3, ST_MAXDIST = 4,
 
 #ifdef VF_FLOOD_TIMING  // tools/ only (VF_NVCC_EXTRA=-DVF_FLOOD_TIMING): cycles per phase of a tile visit, summed over visits
 __device__ unsigned long long g_flood_cycles[8];  // 0 load, 1 masks, 2 relaxation, 3 write-back + wake, 4 visits, 5 steps
+__device__ unsigned long long g_front_cycles[12];  // thin-front solver, thread 0 of CTA 0: 0 level set-up, 1 key loads, 2 claims, 3 pushes, 4 end of level, 5 barrier, 7 levels, 8 CTAs, 9 cells, 10 passes over the own list
 #define VF_TICK(slot)                                                   \
     do {                                                                \
         if (threadIdx.x == 0) {                                         \
@@ -59,8 +66,28 @@ __device__ unsigned long long g_flood_cycles[8];  // 0 load, 1 masks, 2 relaxati
 #else
 #define VF_TICK(slot) do { } while (0)
 #endif
+#ifdef VF_FLOOD_TIMING
+// thread 0 of CTA 0 accumulates in shared memory (no global traffic of its own); `dep` makes the clock read wait for the value it names
+#define VF_FTICK(slot, dep)                                                                  \
+    do {                                                                                     \
+        if (gtid == 0) {                                                                     \
+            long long now__;                                                                 \
+            asm volatile("mov.u64 %0, %%clock64;" : "=l"(now__) : "r"((uint32_t)(dep)) : "memory"); \
+            s_ft[slot] += (unsigned long long)(now__ - ftick__);                             \
+            ftick__ = now__;                                                                 \
+        }                                                                                    \
+    } while (0)
+#else
+#define VF_FTICK(slot, dep) do { } while (0)
+#endif
 
-constexpr int kRoundWord = 14;  // worklist header layout: stats[8] count[3] lo[3] | word 14: device-resident round id (graph mode) | word 15 free
+constexpr int kRoundWord = 14;  // worklist header layout: stats[8] count[3] lo[3] | word 14: device-resident round id | word 15: steps run by the thin-front solver
+constexpr int kFrontWord = 15;
+constexpr int kFrontThreads = 512;             // threads per CTA of the thin-front solver
+constexpr int kFrontLocal = 4096;              // cells of a level one CTA can hold (two lists of this size in shared memory)
+constexpr uint32_t kFrontCap = (uint32_t)kVfFrontCap;  // entries per front list
+constexpr int kFrontSublevels = 16;            // steps a CTA of the thin-front solver runs on its own list between two cluster barriers
+constexpr uint32_t kFrontMaxLevel = 131000;    // the key field holds 17 bits of distance: beyond this the tiles take over (and report the overflow)
 constexpr size_t kSmemBytes = (size_t)(kCells + 5 * kThreads + 8 + 2) * sizeof(uint32_t);  // tile | 5 row-mask arrays | misc | mbarrier
 
 // ------------------------------------------------------------------------------------------------ key field set-up
@@ -556,6 +583,297 @@ __global__ void __launch_bounds__(kThreads, 4) flood_round_kernel(uint32_t* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------------ F2: thin-front solver
+// State in the `tiles` arena behind the worklists: the first front of a phase as the set-up kernel leaves it (hdr[0] cells in `list`).
+struct Front {
+    uint32_t* list;
+    uint32_t* hdr;
+};
+
+// Phase 1 sources.  FloodFracturer.cpp:102-103,127-132: seeds written in order (a later seed on the same cell overwrites); the level-0
+// front holds every seeded cell once.  One CTA.
+__global__ void __launch_bounds__(256) flood_front_seed_kernel(uint32_t* __restrict__ keys, TileGeom g, Worklist wl, Front fr, const ushort4* __restrict__ seeds, int S,
+                                                               uint32_t round)
+{
+    __shared__ uint32_t s_n;
+    if (threadIdx.x == 0) {
+        s_n = 0;
+        wl.lo[round % 3] = 0, wl.lo[(round + 1) % 3] = kNoLevel;  // where the tiles' first window starts, should they take over
+        for (int s = 0; s < S; ++s) {
+            const ushort4 sd = seeds[s];
+            keys[((size_t)sd.x * g.Y + sd.y) * g.Z + sd.z] = (uint32_t)s;  // dist 0, order s
+            wl.occ[((uint32_t)(sd.x / TX) * g.nty + sd.y / TY) * g.ntz + sd.z / TZ] = 1;
+        }
+    }
+    __syncthreads();
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+        const ushort4 sd = seeds[s];
+        const uint32_t cell = ((uint32_t)sd.x * g.Y + sd.y) * g.Z + sd.z;
+        if (__ldcg(keys + cell) == (uint32_t)s) fr.list[atomicAdd(&s_n, 1u)] = cell;  // S <= 4096 <= kFrontCap
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) fr.hdr[0] = s_n;
+}
+
+// Phase 2 sources are all labelled cells (keys of level 0 after launch_init_keys<true>): a FREE cell next to one is a level-1 cell and its key
+// is 1 level | the lowest order among those neighbours.  Level-1 cells are the first front (hdr[0] zeroed by the host).
+template <int NNEIGH>
+__global__ void __launch_bounds__(256) flood_front_level1_kernel(const uint16_t* __restrict__ grid, uint32_t* __restrict__ keys, TileGeom g, Worklist wl, Front fr,
+                                                                 uint32_t round)
+{
+    const uint32_t n = (uint32_t)g.X * g.Y * g.Z, Z = g.Z, YZ = (uint32_t)g.Y * g.Z;
+    if (blockIdx.x == 0 && threadIdx.x == 0) wl.lo[round % 3] = 0, wl.lo[(round + 1) % 3] = kNoLevel;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (grid[i] != VF_VOXEL_FREE) continue;
+        const int x = (int)(i / YZ), r = (int)(i - (uint32_t)x * YZ), y = r / (int)Z, z = r - y * (int)Z;
+        uint32_t m = KEY_WALL;  // a neighbour that became a level-1 cell meanwhile (or is seen stale as unreached) is not a source either way
+        if (NNEIGH == 6) {
+            if (x > 0) m = min(m, keys[i - YZ]);
+            if (x + 1 < g.X) m = min(m, keys[i + YZ]);
+            if (y > 0) m = min(m, keys[i - Z]);
+            if (y + 1 < g.Y) m = min(m, keys[i + Z]);
+            if (z > 0) m = min(m, keys[i - 1]);
+            if (z + 1 < g.Z) m = min(m, keys[i + 1]);
+        } else {
+            for (int dx = -1; dx <= 1; ++dx)
+                for (int dy = -1; dy <= 1; ++dy)
+                    for (int dz = -1; dz <= 1; ++dz) {
+                        if (!(dx | dy | dz) || x + dx < 0 || x + dx >= g.X || y + dy < 0 || y + dy >= g.Y || z + dz < 0 || z + dz >= g.Z) continue;
+                        m = min(m, keys[(int64_t)i + (int64_t)dx * (int)YZ + dy * (int)Z + dz]);
+                    }
+        }
+        if (m < KEY_LEVEL) {
+            keys[i] = m + KEY_LEVEL;
+            const uint32_t q = atomicAdd(&fr.hdr[0], 1u);
+            if (q < kFrontCap) fr.list[q] = i;  // a longer list makes the solver hand over at once: the tiles check every cell on their first visit
+        }
+    }
+}
+
+// atomicMin under a predicate instead of a branch: the claims of one cell (up to 26) are then in flight together; returns the old value, 0 when not executed
+__device__ __forceinline__ uint32_t atom_min_if(uint32_t* p, uint32_t v, bool doit)
+{
+    uint32_t old;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\tmov.u32 %0, 0;\n\t@p atom.global.min.u32 %0, [%1], %2;\n\t}"
+        : "=r"(old)
+        : "l"(p), "r"(v), "r"((uint32_t)doit)
+        : "memory");
+    return old;
+}
+
+// the same for a counter that may live in another CTA's shared memory (generic address): slot reservations of one thread are in flight together
+__device__ __forceinline__ uint32_t atom_inc_if(uint32_t* p, bool doit)
+{
+    uint32_t old;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.u32 %0, 0;\n\t@p atom.add.u32 %0, [%1], 1;\n\t}"
+        : "=r"(old)
+        : "l"(p), "r"((uint32_t)doit)
+        : "memory");
+    return old;
+}
+
+// One launch = one thread-block cluster (every CTA of the grid).  Label-correcting relaxation of the same keys, at cell granularity: the
+// front is a list of (cell, key) pairs in SHARED memory; expanding a pair lowers the neighbours to key + 1 level with atomicMin, and whoever
+// lowers a cell — unreached, or claimed at a higher (level, order) — lists it with the key it wrote.  A pair that is out of date (its cell
+// was lowered again meanwhile) only repeats work: the thread that lowered it listed the better pair.  The least fixed point is the tiles'.
+//
+// A CTA expands its own list for `sublevels` steps between two cluster barriers (a __syncthreads per step; a flood is a chain of hundreds
+// of dependent levels, so what a level costs is memory round trips and barriers, not bandwidth): a front that grew out of one seed stays
+// with one CTA and advances level by level exactly as a BFS; where fronts of different CTAs meet they may run ahead of each other by up to
+// `sublevels` levels and correct each other.  A CTA that holds more than twice its share of the front deals its claims out instead — into
+// the inbox of the CTA a hash of the cell names, through distributed shared memory; inboxes are emptied after each cluster barrier.
+// The neighbour keys are read first (plain loads: a line loaded earlier in the same barrier interval may lack the latest claims, which only
+// costs a redundant atomic; the barrier's acquire empties the L1) and only cells that are not walls and lie above are lowered.  (Measured
+// alternative: atomicMin on every neighbour without looking, walls written back — one round trip less, but slower: 6 atomics per cell.)
+// The launch ends when no pair is pending anywhere (the phase has converged: the tile worklist stays empty), or when more than `limit`
+// pairs are pending or a list overflowed: then every occupied tile is enqueued for round `tile_round` and the tiles' full first-visit check
+// takes it from whatever upper bounds the keys hold.  spread: 0 = lists stay local, 1 = as described, 2 = always dealt out (tools/ only).
+constexpr int kFrontInbox = 2048;  // pairs a CTA can receive between two cluster barriers
+constexpr size_t kFrontSmemBytes = (size_t)(2 * kFrontLocal + 2 * kFrontInbox) * 8;
+
+template <int NNEIGH>
+__global__ void __launch_bounds__(kFrontThreads, 1) flood_front_kernel(uint32_t* __restrict__ keys, TileGeom g, Worklist wl, Front fr,
+                                                                       uint32_t limit, uint32_t tile_round, int spread, int sublevels)
+{
+    namespace cg = cooperative_groups;
+    constexpr uint32_t kLost = 0x80000000u;  // in a pending count: a list overflowed (or a level does not fit the key), some lowered cells are not listed
+    extern __shared__ __align__(16) uint32_t s_dyn[];
+    // two lists (the step's / the next step's) and two inboxes (this / the next barrier interval) of (cell, key) pairs
+    auto list_cell = [&](int b) { return s_dyn + b * kFrontLocal; };
+    auto list_key = [&](int b) { return s_dyn + (2 + b) * kFrontLocal; };
+    auto inbox_cell = [&](int b) { return s_dyn + 4 * kFrontLocal + b * kFrontInbox; };
+    auto inbox_key = [&](int b) { return s_dyn + 4 * kFrontLocal + (2 + b) * kFrontInbox; };
+    __shared__ uint32_t s_cnt[2], s_icnt[2];  // entries (may count past the capacity)
+    __shared__ uint32_t s_sent;               // pairs this CTA dealt out in this interval | kLost
+    __shared__ uint32_t s_tot[2][16];         // pending pairs of every CTA of the cluster, written by its owner before the barrier
+    const cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t t = threadIdx.x, T = blockDim.x, C = gridDim.x, rank = blockIdx.x, nthreads = C * T, gtid = rank * T + t;
+    const uint32_t Z = g.Z, YZ = (uint32_t)g.Y * g.Z;
+#ifdef VF_FLOOD_TIMING
+    __shared__ unsigned long long s_ft[12];
+    if (t < 12) s_ft[t] = 0;
+#endif
+    if (t < 2) s_cnt[t] = 0, s_icnt[t] = 0;
+    if (t == 0) s_sent = 0;
+    __syncthreads();
+    // the first front: the cells the set-up kernel listed in global memory, dealt round-robin to the CTAs, with the keys they hold
+    const uint32_t init_total = fr.hdr[0];
+    const bool skip = init_total > limit;  // already too wide: nothing is listed, the tiles do everything
+    if (!skip)
+        for (uint32_t i = t * C + rank; i < init_total; i += nthreads) {
+            const uint32_t cell = fr.list[i], p = atomicAdd(&s_cnt[0], 1u);
+            if (p < (uint32_t)kFrontLocal) list_cell(0)[p] = cell, list_key(0)[p] = keys[cell];
+        }
+    const bool lost0 = !skip && (init_total + C - 1) / C > (uint32_t)kFrontLocal;  // a small cluster cannot hold a front that wide
+    cluster.sync();  // also: nobody writes into a CTA whose counters are not zeroed yet
+#ifdef VF_FLOOD_TIMING
+    long long ftick__ = clock64();
+#endif
+    uint32_t total = init_total | (lost0 ? kLost : 0u), steps = 0;
+    int cur = 0;
+    bool handover = false;
+    for (uint32_t interval = 0; !skip; ++interval) {
+        if (total == 0) break;  // converged (the same word in every thread of the cluster)
+        if ((total & ~kLost) > limit || (total & kLost) || steps >= kFrontMaxLevel) {
+            handover = true;
+            break;
+        }
+        const uint32_t fair = total / C;
+        const int ib = interval & 1;
+        for (int sl = 0; sl < sublevels; ++sl, cur ^= 1) {
+            const uint32_t mine = min(s_cnt[cur], (uint32_t)kFrontLocal);
+            const bool far = spread == 2 || (spread == 1 && mine > 2 * fair + 64);  // this CTA holds too much of the front: deal its claims out
+            const uint32_t* ccell = list_cell(cur);
+            const uint32_t* ckey = list_key(cur);
+            uint32_t* ncell = list_cell(cur ^ 1);
+            uint32_t* nkey = list_key(cur ^ 1);
+            VF_FTICK(0, mine);
+            // 26 neighbours: three threads per pair (one per x-plane of the neighbourhood), so that a thin front still fills the CTA
+            constexpr int LANES = NNEIGH == 6 ? 1 : 3, NB = NNEIGH == 6 ? 6 : 9;
+            for (uint32_t it = t; it < mine * LANES; it += T) {
+                const uint32_t i = it / LANES;
+                const int dx = NNEIGH == 6 ? 0 : (int)(it - i * LANES) - 1;
+                const uint32_t cell = ccell[i], own = ckey[i];
+                if (own >= KEY_LIMIT) {  // no room for another level in the key: the tiles report it
+                    atomicOr(&s_sent, kLost);
+                    continue;
+                }
+                const uint32_t nk = own + KEY_LEVEL;
+                const int x = (int)(cell / YZ), r = (int)(cell - (uint32_t)x * YZ), y = r / (int)Z, z = r - y * (int)Z;
+                uint32_t nb[NB], kv[NB];
+                uint32_t inside = 0;
+                if (NNEIGH == 6) {
+                    nb[0] = cell - YZ, nb[1] = cell + YZ, nb[2] = cell - Z, nb[3] = cell + Z, nb[4] = cell - 1, nb[5] = cell + 1;
+                    inside = (x > 0 ? 1u : 0u) | (x + 1 < g.X ? 2u : 0u) | (y > 0 ? 4u : 0u) | (y + 1 < g.Y ? 8u : 0u) | (z > 0 ? 16u : 0u) | (z + 1 < g.Z ? 32u : 0u);
+                } else {
+                    const bool xin = x + dx >= 0 && x + dx < g.X;
+                    const uint32_t plane = cell + (uint32_t)(dx * (int)YZ);  // modulo 2^32; only used when the neighbour lies inside the grid
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) {
+                        const int dy = q / 3 - 1, dz = q % 3 - 1;
+                        nb[q] = plane + (uint32_t)(dy * (int)Z + dz);
+                        const bool in = xin && (dx != 0 || q != 4) && y + dy >= 0 && y + dy < g.Y && z + dz >= 0 && z + dz < g.Z;
+                        inside |= (in ? 1u : 0u) << q;
+                    }
+                }
+                // look first (plain loads: a stale line only costs a redundant atomic), then lower what is not a wall and lies above
+#pragma unroll
+                for (int q = 0; q < NB; ++q) kv[q] = (inside >> q & 1u) ? keys[nb[q]] : KEY_WALL;
+#ifdef VF_FLOOD_TIMING
+                {
+                    uint32_t all = nk;
+#pragma unroll
+                    for (int q = 0; q < NB; ++q) all ^= kv[q];
+                    VF_FTICK(1, all);
+                }
+#endif
+#pragma unroll
+                for (int q = 0; q < NB; ++q) kv[q] = atom_min_if(keys + nb[q], nk, kv[q] != KEY_WALL && kv[q] > nk);  // old value; 0 = not executed
+                uint32_t won = 0;  // bit q: this thread lowered neighbour q (unreached, or a correction: claimed at a higher (level, order))
+#pragma unroll
+                for (int q = 0; q < NB; ++q) won |= (kv[q] > nk && kv[q] != KEY_WALL ? 1u : 0u) << q;
+                VF_FTICK(2, won);
+                if (won) {
+                    const uint32_t k = __popc(won);
+                    bool lost = false;
+                    if (!far) {
+                        uint32_t p = atomicAdd(&s_cnt[cur ^ 1], k);
+#pragma unroll
+                        for (int q = 0; q < NB; ++q)
+                            if (won >> q & 1u) {
+                                if (p < (uint32_t)kFrontLocal) ncell[p] = nb[q], nkey[p] = nk;
+                                else lost = true;
+                                ++p;
+                            }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < NB; ++q) {  // reserve all slots, then fill them
+                            const unsigned to = ((nb[q] * 2654435761u) >> 20) & (C - 1);  // C is a power of two
+                            kv[q] = atom_inc_if(cluster.map_shared_rank(&s_icnt[ib], to), won >> q & 1u);
+                        }
+#pragma unroll
+                        for (int q = 0; q < NB; ++q)
+                            if (won >> q & 1u) {
+                                const unsigned to = ((nb[q] * 2654435761u) >> 20) & (C - 1);
+                                if (kv[q] < (uint32_t)kFrontInbox) {
+                                    cluster.map_shared_rank(inbox_cell(ib), to)[kv[q]] = nb[q];
+                                    cluster.map_shared_rank(inbox_key(ib), to)[kv[q]] = nk;
+                                } else {
+                                    lost = true;
+                                }
+                            }
+                        atomicAdd(&s_sent, k);
+                    }
+                    if (lost) atomicOr(&s_sent, kLost);
+                }
+                VF_FTICK(3, won);
+            }
+            __syncthreads();  // the step's list is consumed, the next one complete
+            if (t == 0) s_cnt[cur] = 0;
+#ifdef VF_FLOOD_TIMING
+            if (gtid == 0) s_ft[7] += 1, s_ft[10] += (mine * LANES + T - 1) / T;
+#endif
+            __syncthreads();
+            VF_FTICK(4, 0);
+        }
+        steps += (uint32_t)sublevels;
+        // pending pairs of this CTA: its next list + what it dealt out; told to every CTA of the cluster
+        if (t < C) *cluster.map_shared_rank(&s_tot[ib][rank], t) = (min(s_cnt[cur], (uint32_t)kFrontLocal) + (s_sent & ~kLost)) | (s_sent & kLost) | (s_cnt[cur] > (uint32_t)kFrontLocal ? kLost : 0u);
+#ifdef VF_FLOOD_TIMING
+        if (gtid == 0) s_ft[9] += total & ~kLost, s_ft[11] += 1;
+#endif
+        cluster.sync();  // release / acquire at cluster scope: keys, inbox entries and counts of this interval are visible to every CTA
+        uint32_t sum = 0, flags = 0;
+        for (uint32_t r = 0; r < C; ++r) sum += s_tot[ib][r] & ~kLost, flags |= s_tot[ib][r] & kLost;
+        total = sum | flags;  // the same in every CTA
+        // empty the inbox into the list of the next step (the senders of the next interval use the other inbox)
+        const uint32_t have = min(s_cnt[cur], (uint32_t)kFrontLocal), got = min(s_icnt[ib], (uint32_t)kFrontInbox);
+        const bool spilled = have + got > (uint32_t)kFrontLocal;  // known to this CTA only: it stops everybody through the next exchange
+        for (uint32_t i = t; i < got; i += T)
+            if (have + i < (uint32_t)kFrontLocal) list_cell(cur)[have + i] = inbox_cell(ib)[i], list_key(cur)[have + i] = inbox_key(ib)[i];
+        __syncthreads();
+        if (t == 0) s_cnt[cur] = min(have + got, (uint32_t)kFrontLocal), s_icnt[ib] = 0, s_sent = spilled ? kLost : 0u;
+        __syncthreads();
+        VF_FTICK(5, total);
+    }
+    if (handover || skip) {
+        const uint32_t nt = (uint32_t)g.ntiles();
+        for (uint32_t tile = gtid; tile < nt; tile += nthreads)
+            if (wl.occ[tile]) enqueue_tile(wl, tile, tile_round);
+        if (gtid == 0) wl.lo[tile_round % 3] = steps > 2u * (uint32_t)sublevels ? steps - 2u * (uint32_t)sublevels : 0u;  // where the first window starts (any value is correct)
+    }
+    if (gtid == 0) wl.stats[kFrontWord] += steps;
+    cluster.sync();  // no CTA may exit while another may still write into its shared memory
+#ifdef VF_FLOOD_TIMING
+    if (gtid == 0) {
+        for (int q = 0; q < 12; ++q) g_front_cycles[q] += s_ft[q];
+        g_front_cycles[8] = gridDim.x;
+    }
+#endif
+}
+
 // keys -> label words.  order -> seeds[order].w & mask; unreached non-empty cells stay FREE (never claimed in the reference).
 __global__ void __launch_bounds__(256) flood_finalize_kernel(const uint32_t* __restrict__ keys, uint16_t* __restrict__ grid, size_t n,
                                                              const ushort4* __restrict__ seeds, uint32_t mask, uint32_t* __restrict__ stats)
@@ -592,6 +910,8 @@ struct Job {
     int blocks_stream;    // grid for streaming kernels
     int blocks_tiles;     // grid for tile kernels
     bool round_on_device = false;  // a cooperative phase advanced the round id on the device; read_stats brings it back
+    Front fr;             // thin-front solver state
+    uint32_t front_levels = 0;  // BFS levels it ran so far (read_stats)
 };
 
 vf_status job_begin(vf_grid* grid, Job& j)
@@ -603,8 +923,11 @@ vf_status job_begin(vf_grid* grid, Job& j)
     // layout: stats[8] count[3] lo[3] round id, pad | pad[16] | list0 | list1 | stamp | occ | seen | (aligned) pend[nt][kThreads]
     const size_t words = 32 + 3 * nt;
     const size_t pend_off = (words * 4 + 2 * nt + 255) & ~(size_t)255;
-    VF_TRY(vf_scratch_reserve(c, c->tiles, pend_off + nt * kThreads * 4 + 256));
+    const size_t front_off = (pend_off + nt * kThreads * 4 + 255) & ~(size_t)255;
+    VF_TRY(vf_scratch_reserve(c, c->tiles, front_off + kVfFrontBytes));
     uint32_t* base = (uint32_t*)c->tiles.ptr;
+    j.fr.list = (uint32_t*)((char*)base + front_off);
+    j.fr.hdr = j.fr.list + kFrontCap;
     j.wl.stats = base;
     j.wl.count = base + 8;
     j.wl.list[0] = base + 32;
@@ -650,6 +973,7 @@ vf_status read_stats(Job& j, uint32_t out[8])
     VF_CUDA(cudaMemcpyAsync(j.h_mail, j.wl.stats, 64, cudaMemcpyDeviceToHost, j.c->stream));
     VF_CUDA(vf_sync(j.c));
     for (int i = 0; i < 8; ++i) out[i] = j.h_mail[i];
+    j.front_levels = j.h_mail[kFrontWord];
     if (j.round_on_device) {  // a cooperative phase ran: the id of the next round is in the header
         VF_REQUIRE(j.h_mail[kRoundWord] < j.round + 100000, VF_ERR_CAPACITY, "tile worklist did not drain");
         j.round = j.h_mail[kRoundWord];
@@ -707,6 +1031,73 @@ vf_status flood_phase(Job& j, uint32_t* keys)
     return run_rounds(j, [&](uint32_t r) { kern<<<j.blocks_tiles, kThreads, kSmemBytes, j.c->stream>>>(keys, map, use_tma, j.g, j.wl, r, 0u); });
 }
 
+// Largest cluster the thin-front kernel can run as on this device: 16 CTAs (non-portable size, one GPC), else 8 … else a single CTA.
+template <int NNEIGH>
+int front_cluster_size(vf_ctx* c)
+{
+    static int cached[64];  // per device; 0 = not probed yet (a benign race: every thread computes the same value)
+    const int dev = c->device & 63;
+    if (cached[dev]) return cached[dev];
+    auto kern = flood_front_kernel<NNEIGH>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFrontSmemBytes) != cudaSuccess) {
+        cudaGetLastError();
+        return cached[dev] = -1;  // no thin-front solver on this device
+    }
+    int best = 1;
+#ifdef VF_FLOOD_TIMING  // tools/ only
+    const int want = std::getenv("VF_FRONT_CLUSTER") ? std::atoi(std::getenv("VF_FRONT_CLUSTER")) : 16;
+#else
+    const int want = 16;
+#endif
+    for (int size : { 16, 8, 4, 2 }) {
+        if (size > want) continue;
+        if (size > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        cudaLaunchAttribute at;
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = (unsigned)size, at.val.clusterDim.y = 1, at.val.clusterDim.z = 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)size), cfg.blockDim = dim3(kFrontThreads), cfg.dynamicSmemBytes = kFrontSmemBytes, cfg.stream = c->stream, cfg.attrs = &at, cfg.numAttrs = 1;
+        int clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg) == cudaSuccess && clusters >= 1) {
+            best = size;
+            break;
+        }
+        cudaGetLastError();
+    }
+    return cached[dev] = best;
+}
+
+inline int front_env(const char* name, int dflt)
+{
+#ifdef VF_FLOOD_TIMING  // tools/ only
+    return std::getenv(name) ? std::atoi(std::getenv(name)) : dflt;
+#else
+    (void)name;
+    return dflt;
+#endif
+}
+
+// the cell-granular start of a flood phase (front list and count set up in j.fr); whatever it leaves undone is on the tile worklist afterwards
+template <int NNEIGH>
+vf_status front_phase(Job& j, uint32_t* keys)
+{
+    vf_ctx* c = j.c;
+    const int size = front_cluster_size<NNEIGH>(c);
+    VF_REQUIRE(size >= 1, VF_ERR_CUDA, "the thin-front flood kernel cannot run on this device (vf_ctx_set_flood_front(ctx, 0) selects the tiles)");
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = (unsigned)size, at.val.clusterDim.y = 1, at.val.clusterDim.z = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)size), cfg.blockDim = dim3(kFrontThreads), cfg.dynamicSmemBytes = kFrontSmemBytes, cfg.stream = c->stream, cfg.attrs = &at, cfg.numAttrs = 1;
+    static const int spread = front_env("VF_FRONT_SPREAD", 1), sublevels = std::max(1, front_env("VF_FRONT_SUBLEVELS", kFrontSublevels));
+    VF_CUDA(cudaLaunchKernelEx(&cfg, flood_front_kernel<NNEIGH>, keys, j.g, j.wl, j.fr, c->flood_front, j.round, spread, sublevels));
+    ++c->launches;
+    return VF_OK;
+}
+
 }  // namespace
 
 extern "C" vf_status vf_fracture_flood(vf_grid* grid, const uint32_t* seeds, uint32_t nseeds, int dfunc, int id_bits, vf_flood_stats* stats_out)
@@ -727,7 +1118,7 @@ extern "C" vf_status vf_fracture_flood(vf_grid* grid, const uint32_t* seeds, uin
     uint32_t* keys = (uint32_t*)c->keys.ptr;
     Job j;
     VF_TRY(job_begin(grid, j));
-    vf_flood_stats st = { 0, 0, 0, 0, 0 };
+    vf_flood_stats st = { 0, 0, 0, 0, 0, 0 };
     uint32_t hs[8];
 
     // F3 bookkeeping on the host: effective source per cell (later seed wins), principal (lowest-prefix) source per fragment id
@@ -752,9 +1143,16 @@ extern "C" vf_status vf_fracture_flood(vf_grid* grid, const uint32_t* seeds, uin
 
     // ---- phase 1
     VF_TRY(launch_init_keys<false>(c, grid->d, keys, j.g, j.wl.occ, nullptr, j.blocks_stream));
-    flood_seed_kernel<<<1, 32, 0, c->stream>>>(keys, j.g, j.wl, d_seeds, (int)nseeds, j.round);
-    VF_LAUNCHED(c);
-    VF_TRY(nneigh == 6 ? flood_phase<6>(j, keys) : flood_phase<26>(j, keys));
+    const bool front = c->flood_front != 0 && n < ((size_t)1 << 32);  // thin-front solver first (cell indices are 32-bit there)
+    if (front) {
+        flood_front_seed_kernel<<<1, 256, 0, c->stream>>>(keys, j.g, j.wl, j.fr, d_seeds, (int)nseeds, j.round);
+        VF_LAUNCHED(c);
+        VF_TRY(nneigh == 6 ? front_phase<6>(j, keys) : front_phase<26>(j, keys));
+    } else {
+        flood_seed_kernel<<<1, 32, 0, c->stream>>>(keys, j.g, j.wl, d_seeds, (int)nseeds, j.round);
+        VF_LAUNCHED(c);
+    }
+    VF_TRY(nneigh == 6 ? flood_phase<6>(j, keys) : flood_phase<26>(j, keys));  // nothing to do when the front solver finished the phase
     const bool need_f3 = id_bits == 8 && prefixes;
     flood_finalize_kernel<<<j.blocks_stream, 256, 0, c->stream>>>(keys, grid->d, n, d_seeds, (id_bits == 8 && !need_f3) ? 0xFFu : 0xFFFFu, j.wl.stats);
     VF_LAUNCHED(c);
@@ -784,8 +1182,16 @@ extern "C" vf_status vf_fracture_flood(vf_grid* grid, const uint32_t* seeds, uin
             // ---- phase 2: re-flood from every labelled cell (FloodFracturer.cpp:135-177, second trip of the loop)
             j.wl.epoch = 2;  // every labelled cell is a source now: tiles start over with a full entry check
             VF_TRY(launch_init_keys<true>(c, grid->d, keys, j.g, j.wl.occ, d_order, j.blocks_stream));
-            enqueue_tiles_with_free_kernel<<<j.blocks_stream, 256, 0, c->stream>>>(grid->d, j.g, j.wl, j.round);
-            VF_LAUNCHED(c);
+            if (front) {
+                VF_CUDA(cudaMemsetAsync(j.fr.hdr, 0, 4, c->stream));
+                if (nneigh == 6) flood_front_level1_kernel<6><<<j.blocks_stream, 256, 0, c->stream>>>(grid->d, keys, j.g, j.wl, j.fr, j.round);
+                else flood_front_level1_kernel<26><<<j.blocks_stream, 256, 0, c->stream>>>(grid->d, keys, j.g, j.wl, j.fr, j.round);
+                VF_LAUNCHED(c);
+                VF_TRY(nneigh == 6 ? front_phase<6>(j, keys) : front_phase<26>(j, keys));
+            } else {
+                enqueue_tiles_with_free_kernel<<<j.blocks_stream, 256, 0, c->stream>>>(grid->d, j.g, j.wl, j.round);
+                VF_LAUNCHED(c);
+            }
             VF_TRY(nneigh == 6 ? flood_phase<6>(j, keys) : flood_phase<26>(j, keys));
             flood_finalize_kernel<<<j.blocks_stream, 256, 0, c->stream>>>(keys, grid->d, n, d_seeds, 0xFFu, j.wl.stats);
             VF_LAUNCHED(c);
@@ -799,6 +1205,7 @@ extern "C" vf_status vf_fracture_flood(vf_grid* grid, const uint32_t* seeds, uin
     st.tile_visits = hs[ST_VISITS];
     st.tile_rounds = hs[ST_ROUNDS];
     st.max_dist = hs[ST_MAXDIST];
+    st.front_levels = j.front_levels;
     if (stats_out) *stats_out = st;
     return VF_OK;
 }
@@ -1101,6 +1508,15 @@ extern "C" void vf_debug_flood_cycles(unsigned long long* out, int reset)
     if (reset) {
         unsigned long long z[8] = { 0 };
         cudaMemcpyToSymbol(g_flood_cycles, z, sizeof(z));
+    }
+}
+extern "C" void vf_debug_front_cycles(unsigned long long* out, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_front_cycles, sizeof(g_front_cycles));
+    if (reset) {
+        unsigned long long z[12] = { 0 };
+        cudaMemcpyToSymbol(g_front_cycles, z, sizeof(z));
     }
 }
 #endif

@@ -3,8 +3,9 @@
 // Replaces the mesh side of RegularGrid::toTriangleMesh (SRC/DataStructures/RegularGrid.cpp:473-486): MarchingCubes::setGrid
 // (SRC/Graphics/Core/MarchingCubes.cpp:523-540) + triangulateFieldGPU (:364-432) and its shaders marchingCubes-comp.glsl:96-168,
 // computeMortonCodes-comp.glsl, the 30-pass one-bit radix sort (sortMortonCodes, MarchingCubes.cpp:542-609), findSameVertices_01/02,
-// buildMarchingCubesFaces, markBoundaryTriangles, resetLaplacianBuffer / laplacianSmoothing / finishLaplacianSmoothing-comp.glsl, for
-// _marchingCubesSubdivisions == 1 (the default, FractureParameters.h:105).
+// buildMarchingCubesFaces, markBoundaryTriangles, resetLaplacianBuffer / laplacianSmoothing / finishLaplacianSmoothing-comp.glsl, for one
+// block over the whole grid (the only way the reference runs it: RegularGrid.cpp:423 constructs MarchingCubes with subdivisions = 1, and the
+// parameter FractureParameters::_marchingCubesSubdivisions is read nowhere).
 //
 // What the reference computes: the grid is padded by one cell of VOXEL_FREE; the field is 1 where (label without bit 15) == target and
 // 0 elsewhere, isolevel 0.5, so every surface vertex is the midpoint of a cell edge (half-integer coordinates, exact in float32); a
@@ -303,8 +304,8 @@ extern "C" vf_status vf_marching_cubes(vf_grid* grid, uint32_t target_value, con
     vf_mc_params mp;
     vf_mc_params_default(&mp);
     if (params) mp = *params;
-    VF_REQUIRE(mp.marchingCubesSubdivisions == 1, VF_ERR_UNSUPPORTED, "marching cubes over a subdivided grid (_marchingCubesSubdivisions = %d) is not implemented",
-               mp.marchingCubesSubdivisions);
+    // mp.marchingCubesSubdivisions is carried for the parameter surface only, exactly as in the reference: FractureParameters.h:56 declares it and
+    // nothing reads it — RegularGrid::resetMarchingCubes builds MarchingCubes(*this, 1, _numDivs, 5) (RegularGrid.cpp:423), one block whatever it says.
     VF_REQUIRE(grid->X + 2 <= 1023 && grid->Y + 2 <= 1023 && grid->Z + 2 <= 1023, VF_ERR_CAPACITY, "marching cubes keys hold 11 bits per doubled coordinate (<= 1021 cells per axis)");
     VF_REQUIRE(target_value > VF_VOXEL_FREE && target_value < 0x8000u, VF_ERR_INVALID_ARGUMENT, "target value %u is not a fragment label", target_value);
     if (c->device < 64 && !g_rows_uploaded[c->device]) {
