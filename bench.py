@@ -949,8 +949,9 @@ def batch_measure(rank, local_rank, world, dist, meshes, warmup, jobs, mesh_pool
         ctx.setBlockingSync(block)
         if jobs > 1:
             ctx.setFloodLevels(8)  # throughput setting: with several jobs per GPU total tile work matters, not the latency of one flood
-            if BATCH_FLOOD_FRONT >= 0:
-                ctx.setFloodFront(BATCH_FLOOD_FRONT)  # --flood-front: widest BFS level of the thin-front solver (0 = tiles only)
+            # tiles only (0) unless --flood-front says otherwise: the thin-front solver is the latency path of ONE flood; a 16-CTA cluster per phase of
+            # 16 jobs serialises (measured: 108 models/s against 226-236, profiles/r2j_front_solver_log.md)
+            ctx.setFloodFront(BATCH_FLOOD_FRONT if BATCH_FLOOD_FRONT >= 0 else 0)
             ctx.setFloodMode(BATCH_FLOOD_MODE)  # CTAs per SM of a job's cooperative round loop (0: one launch per round), so that jobs share the SMs
         grid = vf.RegularGrid(ctx, (256, 256, 256))  # allocated once at the clamp size, re-dimensioned per model (CADScene.cpp:529-543)
         ctx.reserve((256, 256, 256))
@@ -1055,6 +1056,7 @@ def run_dataset(args):
         ctx.setBlockingSync(jobs * world > host_cores())
         if jobs > 1:
             ctx.setFloodLevels(8)
+            ctx.setFloodFront(BATCH_FLOOD_FRONT if BATCH_FLOOD_FRONT >= 0 else 0)
             ctx.setFloodMode(BATCH_FLOOD_MODE)
         workers.append((ctx, dataset.dataset_grid(ctx, proc), vf._capi.VfDatasetStats()))
     out = tempfile.mkdtemp(prefix=f"vf_dataset_r{rank}_", dir=args.out or None)
@@ -1121,7 +1123,7 @@ def main():
     ap.add_argument("--out", default="", help="dataset workload: parent directory of the (temporary) output folder")
     ap.add_argument("--no-export", action="store_true", help="dataset workload: no grid files (the batch loop through the native driver, metadata files only)")
     ap.add_argument("--flood-mode", type=int, default=0, help="batch workload: vf_ctx_set_flood_mode of the job contexts (0 = one launch per round, 1..4 = CTAs per SM of the cooperative loop)")
-    ap.add_argument("--flood-front", type=int, default=-1, help="batch workload: vf_ctx_set_flood_front of the job contexts (-1 = library default, 0 = tiles only)")
+    ap.add_argument("--flood-front", type=int, default=-1, help="batch / dataset workloads: vf_ctx_set_flood_front of the job contexts when several share a GPU (-1 = 0 = tiles only)")
     ap.add_argument("--seeds", type=int, default=256, help="slab workload: number of seeds")
     ap.add_argument("--python-exchange", action="store_true", help="slab workload: the Python exchange loop over torch.distributed instead of the C++ loop over NCCL")
     ap.add_argument("--slab-size", type=int, default=0, help="default workload at N >= 2: edge of the cfg5 grid (default 2048 at 8 GPUs, else 1024)")

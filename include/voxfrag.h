@@ -125,8 +125,10 @@ vf_status vf_ctx_set_blocking_sync(vf_ctx* ctx, int on);
  * when several jobs share the GPU (measured: 182 -> 200 models/s in batch generation). */
 vf_status vf_ctx_set_flood_levels(vf_ctx* ctx, uint32_t levels);
 /* Every flood phase starts at cell granularity on one thread-block cluster (the front as lists of (cell, key) pairs in shared memory; right for
- * voxelized surfaces, whose BFS levels hold a few thousand cells: 0.94 -> 0.70 ms at 176x256x176, 16 seeds) and moves to the tile worklist
- * when more than max_front_cells pairs are pending (solid interiors).  Default 16384; 0 = tiles only; at most 65536.  Same labels. */
+ * voxelized surfaces, whose BFS levels hold a few thousand cells: 0.93 -> 0.70-0.80 ms at 176x256x176 with 16 seeds, 1.86 -> 1.21 ms with extra
+ * seeds) and moves to the tile worklist when more than max_front_cells pairs are pending (solid interiors).  Default 8192; 0 = tiles only; at most
+ * 65536.  Same labels.  It is the latency path of ONE flood: producers that drive many contexts per GPU (batch generation) should pass 0 — a
+ * 16-CTA cluster per phase and job serialises the jobs (bench.py does). */
 vf_status vf_ctx_set_flood_front(vf_ctx* ctx, uint32_t max_front_cells);
 /* How the tile rounds of a flood phase are driven; the labels do not depend on it.  1..4 (default 4): ONE cooperative launch per phase with that many CTAs per SM,
  * the round loop on the device (no host read-back until the phase has converged): lowest latency for one job, and with 1 or 2 several jobs

@@ -307,7 +307,7 @@ def _c1_cases(ctx, orc, vessel_grid):
             assert np.array_equal(_run_c1(ctx, lab, sd), orc.remove_isolated_regions_cpu(lab.copy(), sd))
 
 
-@pytest.mark.parametrize("limit,mode", [(0, 4), (1, 4), (40, 4), (40, 0), (700, 2), (16384, 4), (16384, 0), (65536, 4)])
+@pytest.mark.parametrize("limit,mode", [(0, 4), (1, 4), (40, 4), (40, 0), (700, 2), (8192, 4), (8192, 0), (65536, 4)])
 def test_result_does_not_depend_on_the_front_limit(orc, vessel_grid, limit, mode):
     """setFloodFront: every phase starts level by level on one thread-block cluster and moves to the tile worklist once a level holds more than
     `limit` cells — never (65536 on these grids), at once (1: the seeds themselves are too many), somewhere on the way (40, 700), or not at all
@@ -365,4 +365,14 @@ def test_result_does_not_depend_on_the_front_limit(orc, vessel_grid, limit, mode
         want, _ = orc.flood(g.copy(), sd, dfunc)
         got, _ = _run_flood(c, g, sd, dfunc)
         assert np.array_equal(got, want)
+    c.close()
+
+
+def test_front_limit_argument_is_checked():
+    import voxelfragmentml_b200 as vf
+
+    c = vf.Context(0)
+    with pytest.raises(vf.VoxFragError):
+        c.setFloodFront(65537)  # the start list holds 65536 cells
+    c.setFloodFront(65536)
     c.close()

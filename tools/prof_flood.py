@@ -8,7 +8,7 @@ from voxelfragmentml_b200 import synth
 ctx = vf.Context(0)
 res = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 if len(sys.argv) > 3:
-    ctx.setFloodFront(int(sys.argv[3]))  # 0 = tiles only; default: thin-front solver first (16384 cells)
+    ctx.setFloodFront(int(sys.argv[3]))  # 0 = tiles only; default: thin-front solver first (8192 pending cells)
     print("flood front limit", int(sys.argv[3]), flush=True)
 v, f = synth.vessel_mesh(0)
 mn, mx = synth.mesh_aabb(v)

@@ -127,7 +127,7 @@ class Context:
 
     def setFloodFront(self, max_front_cells: int):
         """flood phases start at cell granularity on one thread-block cluster and move to the tiles when more than this many (cell, key)
-        pairs are pending (default 16384, 0 = tiles only); same labels"""
+        pairs are pending (default 8192, 0 = tiles only: the setting for many contexts per GPU); same labels"""
         check(self._lib.vf_ctx_set_flood_front(self._h, int(max_front_cells)))
 
     def setFloodMode(self, ctas_per_sm: int):

@@ -102,7 +102,7 @@ struct vf_ctx {
     bool yield_wait = false;  // waits poll and give the core to any runnable thread between polls (vf_ctx_set_blocking_sync(ctx, 2))
     uint32_t flood_levels = 0;  // width of a flood round's distance window; 0 = the library default (vf_ctx_set_flood_levels)
     int flood_coop = 4;         // flood: CTAs per SM of the cooperative round loop, 0 = one launch per round (vf_ctx_set_flood_mode)
-    uint32_t flood_front = 16384;  // flood: most (cell, key) pairs the thin-front solver keeps pending before it hands over to the tiles; 0 = tiles only (vf_ctx_set_flood_front)
+    uint32_t flood_front = 8192;   // flood: most (cell, key) pairs the thin-front solver keeps pending before it hands over to the tiles; 0 = tiles only (vf_ctx_set_flood_front)
     const void* hist_clean = nullptr;  // histogram: device bins at this address are known to be zero (the previous call left them so)
     uint32_t c1_declined = 0;   // C1: calls since the certificate last declined a grid of this context (0: it handled the last one)
     int c1_mode = 0;            // C1: 0 = descent certificate with the union-find as its fallback, 1 = union-find only (vf_ctx_set_c1_mode)
