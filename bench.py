@@ -949,8 +949,8 @@ def batch_measure(rank, local_rank, world, dist, meshes, warmup, jobs, mesh_pool
         ctx.setBlockingSync(block)
         if jobs > 1:
             ctx.setFloodLevels(8)  # throughput setting: with several jobs per GPU total tile work matters, not the latency of one flood
-            # tiles only (0) unless --flood-front says otherwise: the thin-front solver is the latency path of ONE flood; a 16-CTA cluster per phase of
-            # 16 jobs serialises (measured: 108 models/s against 226-236, profiles/r2j_front_solver_log.md)
+            # tiles only (0) unless --flood-front says otherwise: the thin-front solver is the latency path of ONE flood; this loop is bound by its host
+            # threads and gains nothing from it (profiles/r2j_front_batch.txt), and a 16-CTA cluster per phase and job is the wrong grain when jobs share the SMs
             ctx.setFloodFront(BATCH_FLOOD_FRONT if BATCH_FLOOD_FRONT >= 0 else 0)
             ctx.setFloodMode(BATCH_FLOOD_MODE)  # CTAs per SM of a job's cooperative round loop (0: one launch per round), so that jobs share the SMs
         grid = vf.RegularGrid(ctx, (256, 256, 256))  # allocated once at the clamp size, re-dimensioned per model (CADScene.cpp:529-543)

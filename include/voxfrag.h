@@ -128,7 +128,7 @@ vf_status vf_ctx_set_flood_levels(vf_ctx* ctx, uint32_t levels);
  * voxelized surfaces, whose BFS levels hold a few thousand cells: 0.93 -> 0.70-0.80 ms at 176x256x176 with 16 seeds, 1.86 -> 1.21 ms with extra
  * seeds) and moves to the tile worklist when more than max_front_cells pairs are pending (solid interiors).  Default 8192; 0 = tiles only; at most
  * 65536.  Same labels.  It is the latency path of ONE flood: producers that drive many contexts per GPU (batch generation) should pass 0 — a
- * 16-CTA cluster per phase and job serialises the jobs (bench.py does). */
+ * 16-CTA cluster per phase and job is the wrong grain when jobs share the SMs (bench.py does). */
 vf_status vf_ctx_set_flood_front(vf_ctx* ctx, uint32_t max_front_cells);
 /* How the tile rounds of a flood phase are driven; the labels do not depend on it.  1..4 (default 4): ONE cooperative launch per phase with that many CTAs per SM,
  * the round loop on the device (no host read-back until the phase has converged): lowest latency for one job, and with 1 or 2 several jobs
