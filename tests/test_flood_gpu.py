@@ -357,6 +357,18 @@ def test_result_does_not_depend_on_the_front_limit(orc, vessel_grid, limit, mode
         want, _ = orc.flood(rag.copy(), sd, dfunc)
         got, _ = _run_flood(c, rag, sd, dfunc)
         assert np.array_equal(got, want)
+    if limit >= 8192:
+        # a solid block: (a) one seed in the middle — its front stays with one CTA, which deals it out through the inboxes (2048 pairs per barrier
+        # interval and CTA): the 26-neighbour front outgrows them long before 65536 pairs are pending, lowered cells go unlisted and the tiles have to
+        # find them; (b) two corners; (c) 3000 seeds, whose first front is dealt over the whole cluster
+        big = np.ones((112, 96, 128), np.uint16)
+        big[40:60, :70, 30:90] = 0
+        for sd in (np.uint32([[70, 48, 64, 2]]), np.uint32([[0, 0, 0, 2], [111, 95, 127, 3]]), pick_seeds(big, 3000, 5)):
+            for dfunc in (1, 2):
+                want, st = orc.flood(big.copy(), sd, dfunc, id_bits=15)
+                got, gst = _run_flood(c, big, sd, dfunc, id_bits=15)
+                print(f"limit {limit} seeds {len(sd)} dfunc {dfunc}: front steps {gst.front_levels}, tile visits {gst.tile_visits}, max_dist {gst.max_dist}")
+                assert np.array_equal(got, want) and gst.max_dist == st.max_dist and gst.front_levels >= 1
     g = np.zeros((20, 20, 40), np.uint16)
     g[2:8, 2:8, 2:30] = 1
     g[12:18, 12:18, 5:35] = 1  # island without a seed stays FREE
