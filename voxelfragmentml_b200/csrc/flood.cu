@@ -1086,7 +1086,7 @@ vf_status front_phase(Job& j, uint32_t* keys)
 {
     vf_ctx* c = j.c;
     const int size = front_cluster_size<NNEIGH>(c);
-    VF_REQUIRE(size >= 1, VF_ERR_CUDA, "the thin-front flood kernel cannot run on this device (vf_ctx_set_flood_front(ctx, 0) selects the tiles)");
+    VF_REQUIRE(size >= 1, VF_ERR_CUDA, "the thin-front flood kernel cannot run on this device");  // (vf_fracture_flood asks front_available first)
     cudaLaunchAttribute at;
     at.id = cudaLaunchAttributeClusterDimension;
     at.val.clusterDim.x = (unsigned)size, at.val.clusterDim.y = 1, at.val.clusterDim.z = 1;
@@ -1097,6 +1097,9 @@ vf_status front_phase(Job& j, uint32_t* keys)
     ++c->launches;
     return VF_OK;
 }
+
+// the front kernel needs 96 KB of dynamic shared memory per CTA; a device that cannot give it floods on the tiles alone
+bool front_available(vf_ctx* c, int nneigh) { return (nneigh == 6 ? front_cluster_size<6>(c) : front_cluster_size<26>(c)) >= 1; }
 
 }  // namespace
 
@@ -1143,7 +1146,7 @@ extern "C" vf_status vf_fracture_flood(vf_grid* grid, const uint32_t* seeds, uin
 
     // ---- phase 1
     VF_TRY(launch_init_keys<false>(c, grid->d, keys, j.g, j.wl.occ, nullptr, j.blocks_stream));
-    const bool front = c->flood_front != 0 && n < ((size_t)1 << 32);  // thin-front solver first (cell indices are 32-bit there)
+    const bool front = c->flood_front != 0 && n < ((size_t)1 << 32) && front_available(c, nneigh);  // thin-front solver first (cell indices are 32-bit there)
     if (front) {
         flood_front_seed_kernel<<<1, 256, 0, c->stream>>>(keys, j.g, j.wl, j.fr, d_seeds, (int)nseeds, j.round);
         VF_LAUNCHED(c);
