@@ -522,8 +522,9 @@ def run_cuda(args):
         # config is 1024 meshes over the box = 128 per GPU at N = 8)
         jobs = args.jobs or default_jobs(world)
         bm = 128 * world
-        bdt, _, npool = batch_measure(rank, local_rank, world, dist if world > 1 else None, bm, 2, jobs, 0)
+        bdt, _, npool = batch_measure(rank, local_rank, world, dist if world > 1 else None, bm, 2, jobs, 0, passes=3)
         out["batch"] = {"metric": "models/s batch voxelize+fragment", "value": bm / bdt, "unit": "models/s", "meshes": bm, "jobs_per_gpu": jobs,
+                        "passes_models_per_s_rank0": [bm / t for t in LAST_BATCH_INFO.get("pass_seconds", [])], "reported_pass": "median of 3",
                         "fragmentations_per_s": bm * 10 / bdt, "scaling": "weak", "host_cores": host_cores(),
                         "host_cpu_s_per_model_rank0": LAST_BATCH_INFO.get("host_cpu_s_per_model"),
                         "host_waits_per_fragmentation": LAST_BATCH_INFO.get("host_waits_per_fragmentation"),
@@ -917,13 +918,16 @@ BATCH_FLOOD_FRONT = -1
 LAST_BATCH_INFO = {}  # side information of the last batch_measure call (rank-local)
 
 
-def batch_measure(rank, local_rank, world, dist, meshes, warmup, jobs, mesh_pool, blocking="auto"):
+def batch_measure(rank, local_rank, world, dist, meshes, warmup, jobs, mesh_pool, blocking="auto", passes=1):
     """BASELINE config 4: dataset generation — per mesh: SAT voxelization at 256-max, then 10 fragmentations with the reference's
     dataset defaults (FLOOD + CHEBYSHEV, numSeeds = nf cycling 2..10, numExtraSeeds = 2 nf, detectBoundaries, histogram, undoMask;
     CADScene.cpp:294-332, FragmentationProcedure.h:12-13).  Mesh m goes to rank m mod N with RNG seed 80 + m, so results do not
     depend on N.  No collective on the data path.  A flood round of a 256-max shell keeps ~170 tiles busy — a fraction of one B200 —
     so every rank drives `jobs` contexts (one CUDA stream and one host thread each; ctypes releases the GIL inside a call): the
     latency-bound rounds of different meshes overlap on the SMs.  Results do not depend on `jobs` either (per-mesh RNG stream).
+    `passes` > 1: the timed pass over all meshes is repeated and the MEDIAN pass is reported (a pass of 128 meshes lasts about half a second: one
+    burst of foreign load on the host cores — the producers are host threads — would otherwise decide the figure; every pass is listed in
+    LAST_BATCH_INFO["pass_seconds"]).
     Returns (seconds for all meshes: max over ranks, checksum of this rank, number of distinct shapes)."""
     import threading
 
@@ -988,17 +992,23 @@ def batch_measure(rank, local_rank, world, dist, meshes, warmup, jobs, mesh_pool
 
     run(my[: max(warmup, jobs)])
     waits0, launches0 = sum(w[0].host_waits for w in workers), sum(w[0].kernel_launches for w in workers)
-    checksums[:] = [0] * jobs  # the checksum covers the timed pass only: it must not depend on `jobs` or N
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0, c0 = time.perf_counter(), time.process_time()
-    run(my)
-    dt = time.perf_counter() - t0
-    # host CPU time of this rank (all threads) per model of the timed pass: what a batch producer pays in host cores
-    LAST_BATCH_INFO["host_cpu_s_per_model"] = (time.process_time() - c0) / max(1, len(my))
-    LAST_BATCH_INFO["host_waits_per_fragmentation"] = (sum(w[0].host_waits for w in workers) - waits0) / max(1, 10 * len(my))
-    LAST_BATCH_INFO["launches_per_fragmentation"] = (sum(w[0].kernel_launches for w in workers) - launches0) / max(1, 10 * len(my))
+    passes = max(1, int(passes))
+    pass_s, pass_cpu = [], []
+    for _ in range(passes):
+        checksums[:] = [0] * jobs  # the checksum covers one timed pass only: it must not depend on `jobs` or N
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0, c0 = time.perf_counter(), time.process_time()
+        run(my)
+        pass_s.append(time.perf_counter() - t0)
+        pass_cpu.append(time.process_time() - c0)
+    dt = sorted(pass_s)[(passes - 1) // 2]  # the median pass (the only one when passes == 1)
+    # host CPU time of this rank (all threads) per model of the reported pass: what a batch producer pays in host cores
+    LAST_BATCH_INFO["host_cpu_s_per_model"] = pass_cpu[pass_s.index(dt)] / max(1, len(my))
+    LAST_BATCH_INFO["host_waits_per_fragmentation"] = (sum(w[0].host_waits for w in workers) - waits0) / max(1, 10 * len(my) * passes)
+    LAST_BATCH_INFO["launches_per_fragmentation"] = (sum(w[0].kernel_launches for w in workers) - launches0) / max(1, 10 * len(my) * passes)
+    LAST_BATCH_INFO["pass_seconds"] = list(pass_s)
     if dist is not None:
         tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
