@@ -134,9 +134,11 @@ vf_status vf_ctx_set_flood_front(vf_ctx* ctx, uint32_t max_front_cells);
  * the round loop on the device (no host read-back until the phase has converged): lowest latency for one job, and with 1 or 2 several jobs
  * fit on the GPU side by side.  0: one launch per round, read-backs every few rounds (rounds of many jobs interleave freely). */
 vf_status vf_ctx_set_flood_mode(vf_ctx* ctx, int ctas_per_sm);
-/* How vf_remove_isolated_regions (C1) is computed; the result is the same.  0 (default): one streaming "descent certificate" pass plus list
- * work on the cells it cannot certify, falling back to the union-find when those lists outgrow 65 536 cells, two seeds share a label or
- * the rows are not 16-byte aligned.  1: the union-find only. */
+/* How vf_remove_isolated_regions (C1) is computed; the result is the same.  0 (default): on grids of at least 2^26 cells one streaming "descent
+ * certificate" pass plus list work on the cells it cannot certify (512^3: 0.19 ms against 0.60), falling back to the union-find when those lists
+ * outgrow 65 536 cells, two seeds share a label or the rows are not 16-byte aligned; smaller grids go straight to the union-find (<= 0.1 ms there,
+ * while the certificate's one-CTA list work can take milliseconds on a small thin shell).  1: the union-find only.  2: the certificate on a grid
+ * of any size (tests, tools). */
 vf_status vf_ctx_set_c1_mode(vf_ctx* ctx, int mode);
 void*     vf_ctx_stream(vf_ctx* ctx);                                    /* the cudaStream_t every call of this context is issued on */
 uint64_t  vf_ctx_kernel_launches(vf_ctx* ctx);                           /* kernels launched by this context so far (bench "gpu_launches") */

@@ -224,6 +224,7 @@ def test_c1_and_histogram_under_the_other_wait_modes(orc, vessel_grid, wait):
 
     c = vf.Context(0)
     c.setBlockingSync(wait)
+    c.setC1Mode(2)  # the certificate on these small grids too (the default keeps it for grids of at least 2^26 cells)
     dense = np.ones((40, 32, 48), np.uint16)
     for grid, ns in ((dense, 9), (vessel_grid, 12)):
         seeds = pick_seeds(grid, ns, 81)
@@ -274,11 +275,11 @@ def test_result_does_not_depend_on_how_the_round_loop_is_driven(orc, vessel_grid
     c.close()
 
 
-@pytest.mark.parametrize("c1_mode", [0, 1])
+@pytest.mark.parametrize("c1_mode", [2, 1, 0])
 def test_c1_both_formulations_are_bit_exact(ctx, orc, vessel_grid, c1_mode):
-    """C1 by descent certificate (csrc/c1_descent.cu, the default: certificate pass + list work) and by the union-find alone (setC1Mode(1));
-    same cases as the C1 tests above plus a dense Voronoi grid (few failing cells), labels without a seed and a grid whose Z is not a
-    multiple of 8 (the certificate declines, the union-find runs)."""
+    """C1 by descent certificate (csrc/c1_descent.cu: certificate pass + list work; setC1Mode(2) = on grids of any size, the default 0 keeps it for
+    grids of at least 2^26 cells) and by the union-find alone (setC1Mode(1)); same cases as the C1 tests above plus a dense Voronoi grid (few
+    failing cells), labels without a seed and a grid whose Z is not a multiple of 8 (the certificate declines, the union-find runs)."""
     ctx.setC1Mode(c1_mode)
     try:
         _c1_cases(ctx, orc, vessel_grid)

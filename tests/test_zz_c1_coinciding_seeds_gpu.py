@@ -35,7 +35,12 @@ def test_c1_with_the_seed_copies_of_fracture_model(ctx, orc, vessel_grid, nf, ne
     lab = orc.naive(vessel_grid.copy(), seeds, dfunc)
     want = orc.remove_isolated_regions_cpu(lab.copy(), seeds)
     assert (want > 1).sum() > 100000  # the regions survive: every original seed's cell now carries its copy's label
-    assert np.array_equal(_c1(ctx, lab, seeds), want)
+    for mode in (2, 0):  # the descent certificate (2: on a grid of any size), then the default policy (the union-find on a grid this small)
+        ctx.setC1Mode(mode)
+        try:
+            assert np.array_equal(_c1(ctx, lab, seeds), want), f"c1 mode {mode}"
+        finally:
+            ctx.setC1Mode(0)
 
 
 def test_fracture_model_naive_with_extra_seeds(ctx, orc, vessel_grid):
@@ -82,7 +87,7 @@ def _adversarial_seed_lists(orc, lab, seeds, rs):
     return out
 
 
-@pytest.mark.parametrize("c1_mode", [0, 1])
+@pytest.mark.parametrize("c1_mode", [2, 1, 0])  # 2: the descent certificate on grids of any size, 1: the union-find, 0: the default policy
 def test_c1_adversarial_seed_lists(ctx, orc, vessel_grid, c1_mode):
     from conftest import pick_seeds, random_blob_grid
 

@@ -135,7 +135,8 @@ class Context:
         check(self._lib.vf_ctx_set_flood_mode(self._h, int(ctas_per_sm)))
 
     def setC1Mode(self, mode: int):
-        """C1 (removeIsolatedRegions): 0 = descent certificate with the union-find as fallback (default), 1 = union-find only; same result"""
+        """C1 (removeIsolatedRegions): 0 = descent certificate on grids of >= 2^26 cells with the union-find as fallback (default), 1 = union-find
+        only, 2 = the certificate on grids of any size; same result"""
         check(self._lib.vf_ctx_set_c1_mode(self._h, int(mode)))
 
     def synchronize(self):

@@ -150,7 +150,7 @@ extern "C" vf_status vf_ctx_set_flood_mode(vf_ctx* ctx, int ctas_per_sm)
 extern "C" vf_status vf_ctx_set_c1_mode(vf_ctx* ctx, int mode)
 {
     VF_REQUIRE(ctx != nullptr, VF_ERR_INVALID_ARGUMENT, "null context");
-    VF_REQUIRE(mode == 0 || mode == 1, VF_ERR_INVALID_ARGUMENT, "c1 mode %d (0 = descent certificate + fallback, 1 = union-find only)", mode);
+    VF_REQUIRE(mode >= 0 && mode <= 2, VF_ERR_INVALID_ARGUMENT, "c1 mode %d (0 = descent certificate on large grids + fallback, 1 = union-find only, 2 = certificate on any grid + fallback)", mode);
     ctx->c1_mode = mode;
     return VF_OK;
 }

@@ -1222,7 +1222,12 @@ extern "C" vf_status vf_remove_isolated_regions(vf_grid* grid, const uint32_t* s
     VF_TRY(vf_upload_seeds(c, seeds, nseeds, grid->X, grid->Y, grid->Z, &d_seeds));
     // descent certificate (c1_descent.cu); the union-find below takes over when it declines.  A context whose last grid was declined (thin
     // shells: batch producers work through similar shapes) goes straight to the union-find and tries the certificate again every 16th call.
-    if (c->c1_mode == 0 && (c->c1_declined == 0 || (++c->c1_declined & 15u) == 0)) {
+    // Mode 0 (default) tries it on grids of at least 2^26 cells only: that is where it pays (512^3: 0.19 against 0.60 ms), while on a small
+    // thin shell the certificate keeps fewer than its 4096-cell bail-out uncertified yet leaves one CTA list work over most of the shell —
+    // measured on BASELINE cfg1 (88 x 128 x 88 vessel, 8 seeds): 16.7 ms against 0.09 ms for the union-find (tools/prof_cfg1_stages.py).
+    constexpr size_t kCertificateMinCells = (size_t)1 << 26;
+    const bool certificate = c->c1_mode == 2 || (c->c1_mode == 0 && grid->n() >= kCertificateMinCells);
+    if (certificate && (c->c1_declined == 0 || (++c->c1_declined & 15u) == 0)) {
         int handled = 0;
         uint32_t max_label = 0;
         for (uint32_t i = 0; i < nseeds; ++i) max_label = std::max(max_label, seeds[4 * i + 3]);

@@ -105,7 +105,7 @@ struct vf_ctx {
     uint32_t flood_front = 8192;   // flood: most (cell, key) pairs the thin-front solver keeps pending before it hands over to the tiles; 0 = tiles only (vf_ctx_set_flood_front)
     const void* hist_clean = nullptr;  // histogram: device bins at this address are known to be zero (the previous call left them so)
     uint32_t c1_declined = 0;   // C1: calls since the certificate last declined a grid of this context (0: it handled the last one)
-    int c1_mode = 0;            // C1: 0 = descent certificate with the union-find as its fallback, 1 = union-find only (vf_ctx_set_c1_mode)
+    int c1_mode = 0;            // C1: 0 = descent certificate on grids of >= 2^26 cells with the union-find as its fallback, 1 = union-find only, 2 = certificate at any size (vf_ctx_set_c1_mode)
     VfMt19937 rng;
     uint32_t crand = 80;  // state of the C runtime's rand() as the reference's platform implements it (MSVC LCG); srand(_seed), CADScene.cpp:36
     // scratch arenas, grown on demand (FloodFracturer.cpp:116-120 "grown on demand")
